@@ -1,0 +1,118 @@
+"""ctypes binding of libdfn.so -- the only way into the CUDA kernels (include/dfn.h).
+
+The library is built in-tree by ``__graft_entry__.build()`` / ``make -C dfa-nerf_b200/csrc``.
+Importing this module without it raises: there is no CPU or PyTorch fallback.
+"""
+import ctypes as C
+import os
+
+import torch
+
+PREC_FP32, PREC_BF16, PREC_BF16X3 = 0, 1, 3
+MODEL_FACENERF, MODEL_NERF = 0, 1
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libdfn.so')
+
+
+class DfnError(RuntimeError):
+    pass
+
+
+class ModelDesc(C.Structure):
+    _fields_ = [(n, C.c_int) for n in ('kind', 'D', 'W', 'input_ch', 'input_ch_views', 'dim_aud', 'skip',
+                                       'multires', 'multires_views')]
+
+
+class RenderIO(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in (
+        'rays_o', 'rays_d', 'viewdirs', 'near', 'far', 'bc_rgb', 'latent', 't_vals', 'u_vals', 'perturb_rand',
+        'z_samples_in', 'rgb_map', 'disp_map', 'acc_map', 'last_weight', 'rgb0', 'z_samples_out', 'z_vals_out')] + \
+        [('u_per_ray', C.c_int64)]
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise ImportError('dfa_nerf_b200: %s is missing -- run `python -c "import __graft_entry__ as g; g.build()"` '
+                          '(there is no CPU fallback)' % LIB_PATH)
+    lib_ = C.CDLL(LIB_PATH)
+    vp, i32, i64, f32 = C.c_void_p, C.c_int, C.c_int64, C.c_float
+    sig = {
+        'dfn_abi_version': (i32, []),
+        'dfn_last_error': (C.c_char_p, []),
+        'dfn_last_launch_count': (i32, []),
+        'dfn_get_rays': (i32, [i32, i32, vp, vp, f32, f32, f32, C.POINTER(f32), vp, vp, vp, vp]),
+        'dfn_z_vals': (i32, [i32, i32, vp, vp, vp, vp, vp, vp]),
+        'dfn_embed': (i32, [i64, vp, i32, i32, vp, vp]),
+        'dfn_composite_fields': (i32, [i32, i64, vp, vp, vp, vp, vp]),
+        'dfn_calc_volume_weights': (i32, [i32, i32, vp, vp, vp, f32, vp, vp]),
+        'dfn_raw2outputs': (i32, [i32, i32, vp, vp, vp, vp, i32, i32, f32, vp, vp, vp, vp, vp, vp]),
+        'dfn_sample_pdf': (i32, [i32, i32, vp, vp, i64, i32, vp, i32, vp, vp, vp]),
+        'dfn_invert_cdf': (i32, [i32, i32, vp, vp, i32, vp, i32, vp, vp, vp]),
+        'dfn_sort_merge': (i32, [i32, i32, vp, i32, vp, vp, vp]),
+        'dfn_model_create': (i32, [C.POINTER(ModelDesc), C.POINTER(vp)]),
+        'dfn_model_destroy': (None, [vp]),
+        'dfn_model_num_tensors': (i32, [vp]),
+        'dfn_model_load': (i32, [vp, C.POINTER(vp), i32, vp]),
+        'dfn_mlp_workspace_bytes': (i64, [vp, i64]),
+        'dfn_mlp_forward': (i32, [vp, i64, vp, vp, vp, i64, vp]),
+        'dfn_query_workspace_bytes': (i64, [vp, i64, i32, i32]),
+        'dfn_query_points': (i32, [vp, i64, i32, vp, vp, vp, vp, vp, vp, i32, vp, i64, vp]),
+        'dfn_render_workspace_bytes': (i64, [vp, i64, i32, i32, i32]),
+        'dfn_render_rays': (i32, [vp, vp, i64, i32, i32, C.POINTER(RenderIO), i32, i32, vp, i64, vp]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(lib_, name)
+        fn.restype = res
+        fn.argtypes = args
+    if lib_.dfn_abi_version() != 1:
+        raise ImportError('dfa_nerf_b200: libdfn.so ABI mismatch')
+    return lib_
+
+
+lib = _load()
+EXPORTS = ['dfn_abi_version', 'dfn_last_error', 'dfn_last_launch_count', 'dfn_get_rays', 'dfn_z_vals', 'dfn_embed',
+           'dfn_composite_fields', 'dfn_calc_volume_weights', 'dfn_raw2outputs', 'dfn_sample_pdf', 'dfn_invert_cdf',
+           'dfn_sort_merge', 'dfn_model_create', 'dfn_model_destroy', 'dfn_model_num_tensors', 'dfn_model_load',
+           'dfn_mlp_workspace_bytes', 'dfn_mlp_forward', 'dfn_query_workspace_bytes', 'dfn_query_points',
+           'dfn_render_workspace_bytes', 'dfn_render_rays']
+
+
+def check(rc, what=''):
+    if rc != 0:
+        msg = lib.dfn_last_error()
+        raise DfnError('%s failed (%d): %s' % (what or 'libdfn call', rc, msg.decode() if msg else ''))
+
+
+def stream_ptr():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def dev(t, name='tensor', dtype=torch.float32):
+    """Validates a CUDA tensor for the ABI and returns (contiguous tensor, pointer)."""
+    if not torch.is_tensor(t):
+        raise TypeError('%s must be a torch tensor' % name)
+    if not t.is_cuda:
+        raise DfnError('dfa_nerf_b200 has no CPU path: %s must be a CUDA tensor' % name)
+    if t.dtype != dtype:
+        t = t.to(dtype)
+    t = t.contiguous()
+    return t, C.c_void_p(t.data_ptr())
+
+
+def ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+class Workspace:
+    """Grow-only device scratch buffer per (device, tag); avoids allocator traffic per call."""
+    _bufs = {}
+
+    @classmethod
+    def get(cls, nbytes, device, tag='default'):
+        key = (str(device), tag)
+        buf = cls._bufs.get(key)
+        if buf is None or buf.numel() < nbytes:
+            buf = torch.empty(int(nbytes) + 256, dtype=torch.uint8, device=device)
+            cls._bufs[key] = buf
+        return buf

@@ -1,0 +1,73 @@
+// Model handle shared by the fp32 FFMA path, the tcgen05 path and the C ABI.
+#pragma once
+#include <stdint.h>
+#include <cuda_runtime.h>
+
+#include "../../include/dfn.h"
+
+namespace dfn {
+
+struct Fp32Layer {
+  const float* w = nullptr;  // [out, in] row-major (nn.Linear layout), device
+  const float* b = nullptr;  // [out], device
+  int in = 0, out = 0;
+};
+
+// ---- tcgen05 path: per-layer program -------------------------------------------------------
+// A operand blocks ("K-blocks") are [128 rows x 64 bf16] tiles in the 128-byte-swizzled K-major
+// layout.  Per tile slot: blocks 0..3 hold the 256-wide hidden state h, block 4 the positional
+// encoding of xyz (63 columns + one zero column).
+enum { TC_KB_H0 = 0, TC_KB_PE = 4, TC_KB_PER_TILE = 5 };
+enum { TC_EPI_RELU = 0, TC_EPI_VIEW0 = 1, TC_EPI_RGB = 2 };
+static constexpr int TC_MAX_LAYERS = 14;
+static constexpr int TC_BIAS_STRIDE = 256;  // floats per layer in the bias blob
+
+struct TcLayer {
+  uint32_t woff;     // byte offset of this layer's first weight stage in the (hi) blob
+  uint16_t n;        // output columns computed by the MMAs (multiple of 16)
+  uint8_t nkb;       // number of input K-blocks
+  uint8_t kb[5];     // their block ids, in weight order
+  uint8_t epi;       // TC_EPI_*
+  uint8_t pad[3];
+};
+
+struct TcProgram {
+  int n_layers = 0;
+  TcLayer layers[TC_MAX_LAYERS];
+  int fold_layer[2] = {-1, -1};  // layers whose bias absorbs W[:, latent cols] @ latent
+};
+
+}  // namespace dfn
+
+struct dfn_model {
+  dfn_model_desc desc;
+  bool loaded = false;
+  int n_views = 0;  // number of views_linears
+  // fp32 path
+  float* fp32_blob = nullptr;  // one device allocation holding all weights and biases
+  dfn::Fp32Layer pts[16];
+  dfn::Fp32Layer views[8];
+  dfn::Fp32Layer feature, alpha, rgb;
+  // tcgen05 path
+  dfn::TcProgram prog;
+  uint8_t* tc_hi = nullptr;     // packed bf16 (hi) weight stages
+  uint8_t* tc_lo = nullptr;     // packed bf16 (lo = bf16(w - hi)) weight stages, same offsets
+  int64_t tc_blob_bytes = 0;
+  float* tc_bias = nullptr;     // [n_layers][256] static biases
+  float* tc_fold_w = nullptr;   // [2][W][dim_aud] latent columns of the two folding layers
+  float* tc_view_w = nullptr;   // [W/2][input_ch_views] view-direction columns of views_linears.0
+  float* tc_view_b = nullptr;   // [W/2] its (composed) bias
+};
+
+namespace dfn {
+int64_t mlp_fp32_workspace_bytes(const dfn_model* m, int64_t P);
+int mlp_fp32_forward(const dfn_model* m, int64_t P, const float* x, float* out, void* workspace,
+                     int64_t workspace_bytes, cudaStream_t st);
+
+int tc_pack_model(dfn_model* m, const float* const* t, cudaStream_t st);
+void tc_free_model(dfn_model* m);
+int64_t tc_query_workspace_bytes(const dfn_model* m, int64_t R, int S);
+int tc_query_points(const dfn_model* m, int64_t R, int S, const float* rays_o, const float* rays_d,
+                    const float* viewdirs, const float* z_vals, const float* latent, float* raw,
+                    int precision, void* workspace, int64_t workspace_bytes, cudaStream_t st);
+}  // namespace dfn

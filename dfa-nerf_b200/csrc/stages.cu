@@ -1,0 +1,529 @@
+// Stage kernels either side of the MLP: rays, depth sampling, positional encoding, field
+// compositing, sigma->alpha->weights, raw2outputs, inverse-CDF resampling, sort-merge.
+// All are HBM-bound elementwise / per-ray work: coalesced loads, one warp per ray for the
+// scans, warp-shuffle prefix products and sums.  Reference lines are cited per kernel.
+#include <math_constants.h>
+
+#include "common.cuh"
+
+namespace dfn {
+
+static constexpr int kThreads = 256;
+
+static inline int grid_for(int64_t n, int threads = kThreads, int max_waves = 8) {
+  int64_t blocks = (n + threads - 1) / threads;
+  int64_t cap = (int64_t)num_sms() * max_waves * (2048 / threads);
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (int)blocks;
+}
+
+// ------------------------------------------------------------------------------- a1 get_rays
+struct Pose {
+  float m[12];
+};
+
+// HELP:449-465.  dirs = ((x-cx)/f, -(y-cy)/f, -1); rays_d[a] = (dx*R[a][0] + dy*R[a][1]) + dz*R[a][2]
+// with every product and sum rounded separately in that order (what torch.sum over the size-3
+// axis does), so rays_d is bit-identical to the reference.
+__global__ void get_rays_kernel(int n_rows, int n_cols, const float* __restrict__ xs,
+                                const float* __restrict__ ys, float focal, float cx, float cy,
+                                Pose c2w, float* __restrict__ rays_o, float* __restrict__ rays_d,
+                                float* __restrict__ viewdirs) {
+  int64_t n = (int64_t)n_rows * n_cols;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    int row = (int)(i / n_cols), col = (int)(i % n_cols);
+    float dx = __fdiv_rn(__fsub_rn(xs[col], cx), focal);
+    float dy = -__fdiv_rn(__fsub_rn(ys[row], cy), focal);
+    float dz = -1.0f;
+    float d[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      float p0 = __fmul_rn(dx, c2w.m[a * 4 + 0]);
+      float p1 = __fmul_rn(dy, c2w.m[a * 4 + 1]);
+      float p2 = __fmul_rn(dz, c2w.m[a * 4 + 2]);
+      d[a] = __fadd_rn(__fadd_rn(p0, p1), p2);
+    }
+    if (rays_o) {
+      rays_o[i * 3 + 0] = c2w.m[3];
+      rays_o[i * 3 + 1] = c2w.m[7];
+      rays_o[i * 3 + 2] = c2w.m[11];
+    }
+    rays_d[i * 3 + 0] = d[0];
+    rays_d[i * 3 + 1] = d[1];
+    rays_d[i * 3 + 2] = d[2];
+    if (viewdirs) {
+      float nrm = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(d[0], d[0]), __fmul_rn(d[1], d[1])),
+                                  __fmul_rn(d[2], d[2])));
+      viewdirs[i * 3 + 0] = __fdiv_rn(d[0], nrm);
+      viewdirs[i * 3 + 1] = __fdiv_rn(d[1], nrm);
+      viewdirs[i * 3 + 2] = __fdiv_rn(d[2], nrm);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------- a2 z sampling
+// MAIN:617-619: z = near*(1-t) + far*t (separately rounded).  Optional stratified jitter
+// (upstream render_rays): mids=.5(z[1:]+z[:-1]); lower+(upper-lower)*rand.
+__global__ void z_vals_kernel(int R, int S, const float* __restrict__ t_vals,
+                              const float* __restrict__ near, const float* __restrict__ far,
+                              const float* __restrict__ rnd, float* __restrict__ z_out) {
+  int64_t n = (int64_t)R * S;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    int r = (int)(i / S), s = (int)(i % S);
+    float nr = near[r], fr = far[r];
+    auto zf = [&](int k) {
+      float t = t_vals[k];
+      return __fadd_rn(__fmul_rn(nr, __fsub_rn(1.0f, t)), __fmul_rn(fr, t));
+    };
+    float z = zf(s);
+    if (rnd) {
+      float lower = s == 0 ? z : __fmul_rn(0.5f, __fadd_rn(z, zf(s - 1)));
+      float upper = s == S - 1 ? z : __fmul_rn(0.5f, __fadd_rn(zf(s + 1), z));
+      z = __fadd_rn(lower, __fmul_rn(__fsub_rn(upper, lower), rnd[i]));
+    }
+    z_out[i] = z;
+  }
+}
+
+// ------------------------------------------------------------------------- a4 / a4' encodings
+// One thread per output element so the [P, D] store is coalesced.
+// kind 0 (HELP:21-52): [x | sin(2^k x) | cos(2^k x)]_k, exact power-of-two scaling, no pi.
+// kind 1 (DEC:257-275): p/2 then [sin(2^k pi p) | cos(2^k pi p)]_k with fl32(2^k*pi) as in torch.
+__global__ void embed_kernel(int64_t P, const float* __restrict__ x, int L, int kind,
+                             float* __restrict__ out) {
+  int D = kind == 0 ? 3 + 6 * L : 6 * L;
+  int64_t n = P * D;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t p = i / D;
+    int j = (int)(i % D);
+    float v;
+    if (kind == 0) {
+      if (j < 3) {
+        v = x[p * 3 + j];
+      } else {
+        int k = (j - 3) / 6, r = (j - 3) % 6;
+        float a = __fmul_rn(x[p * 3 + (r % 3)], exp2f((float)k));
+        v = r < 3 ? sinf(a) : cosf(a);
+      }
+    } else {
+      int k = j / 6, r = j % 6;
+      float ph = __fmul_rn(x[p * 3 + (r % 3)], 0.5f);
+      float a = __fmul_rn(__fmul_rn(exp2f((float)k), CUDART_PI_F), ph);
+      v = r < 3 ? sinf(a) : cosf(a);
+    }
+    out[i] = v;
+  }
+}
+
+// --------------------------------------------------------------------- a7 composite_function
+// MAIN:146-166 (sum composition): den = sum_b sigma_b (0 -> 1e-4); feat = sum_b feat_b*sigma_b/den.
+__global__ void composite_fields_kernel(int n_box, int64_t n, const float* __restrict__ sigma,
+                                        const float* __restrict__ feat,
+                                        float* __restrict__ sigma_sum, float* __restrict__ feat_w) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    if (n_box == 1) {
+      sigma_sum[i] = sigma[i];
+      feat_w[i * 3 + 0] = feat[i * 3 + 0];
+      feat_w[i * 3 + 1] = feat[i * 3 + 1];
+      feat_w[i * 3 + 2] = feat[i * 3 + 2];
+      continue;
+    }
+    float den = 0.f;
+    for (int b = 0; b < n_box; ++b) den = b == 0 ? sigma[i] : __fadd_rn(den, sigma[b * n + i]);
+    float ssum = den;
+    if (den == 0.f) den = 1e-4f;
+    float acc[3] = {0.f, 0.f, 0.f};
+    for (int b = 0; b < n_box; ++b) {
+      float w = __fdiv_rn(sigma[b * n + i], den);
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        float t = __fmul_rn(feat[(b * n + i) * 3 + c], w);
+        acc[c] = b == 0 ? t : __fadd_rn(acc[c], t);
+      }
+    }
+    sigma_sum[i] = ssum;
+    feat_w[i * 3 + 0] = acc[0];
+    feat_w[i * 3 + 1] = acc[1];
+    feat_w[i * 3 + 2] = acc[2];
+  }
+}
+
+// ------------------------------------------------------ a8 / a9 weights and raw2outputs
+__device__ __forceinline__ double shfl_up_f64(double v, int delta) {
+  int lo = __double2loint(v), hi = __double2hiint(v);
+  lo = __shfl_up_sync(0xffffffffu, lo, delta);
+  hi = __shfl_up_sync(0xffffffffu, hi, delta);
+  return __hiloint2double(hi, lo);
+}
+__device__ __forceinline__ double shfl_xor_f64(double v, int m) {
+  int lo = __double2loint(v), hi = __double2hiint(v);
+  lo = __shfl_xor_sync(0xffffffffu, lo, m);
+  hi = __shfl_xor_sync(0xffffffffu, hi, m);
+  return __hiloint2double(hi, lo);
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int m = 16; m > 0; m >>= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
+  return v;
+}
+
+static constexpr int kMaxSeg = 8;  // samples per lane: S <= 256
+
+// One warp per ray.  Lane l owns the contiguous samples [l*seg, (l+1)*seg).
+// MAIN:169-179: alpha = 1-exp(-(relu(sigma)+1e-6)*dist*|d|); w = alpha * prod_{j<s}(1-alpha_j+1e-10).
+// The running product is carried in fp64 and rounded per element, as torch's CPU cumprod does;
+// a warp-shuffle exclusive scan combines the per-lane segment products.
+// MODE 0: sigma [R,S] -> weights.  MODE 1: raw [R,S,4] -> maps (raw2outputs).
+template <int MODE>
+__global__ void volume_weights_kernel(int R, int S, const float* __restrict__ src,
+                                      const float* __restrict__ z_vals,
+                                      const float* __restrict__ rays_d,
+                                      const float* __restrict__ bc_rgb, int raw_is_feat,
+                                      int white_bkgd, float last_dist, float* __restrict__ rgb_map,
+                                      float* __restrict__ disp_map, float* __restrict__ acc_map,
+                                      float* __restrict__ weights, float* __restrict__ depth_map,
+                                      float* __restrict__ last_weight) {
+  const int lane = threadIdx.x & 31;
+  const int warps_per_block = blockDim.x >> 5;
+  const int seg = (S + 31) / 32;
+  for (int ray = blockIdx.x * warps_per_block + (threadIdx.x >> 5); ray < R;
+       ray += gridDim.x * warps_per_block) {
+    const float dx = rays_d[ray * 3 + 0], dy = rays_d[ray * 3 + 1], dz = rays_d[ray * 3 + 2];
+    const float nrm = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)));
+    const float* zr = z_vals + (int64_t)ray * S;
+    float alpha[kMaxSeg], zv[kMaxSeg], col[kMaxSeg][3];
+    double local = 1.0;
+    const int s0 = lane * seg;
+#pragma unroll
+    for (int k = 0; k < kMaxSeg; ++k) {
+      int s = s0 + k;
+      alpha[k] = 0.f;
+      zv[k] = 0.f;
+      if (k < seg && s < S) {
+        float sig;
+        if (MODE == 0) {
+          sig = src[(int64_t)ray * S + s];
+        } else {
+          float4 rv = reinterpret_cast<const float4*>(src)[(int64_t)ray * S + s];
+          sig = rv.w;
+          if (raw_is_feat) {
+            col[k][0] = rv.x; col[k][1] = rv.y; col[k][2] = rv.z;
+          } else {
+            col[k][0] = __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-rv.x)));
+            col[k][1] = __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-rv.y)));
+            col[k][2] = __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-rv.z)));
+          }
+          if (s == S - 1 && bc_rgb) {
+            col[k][0] = bc_rgb[ray * 3 + 0]; col[k][1] = bc_rgb[ray * 3 + 1]; col[k][2] = bc_rgb[ray * 3 + 2];
+          }
+        }
+        float z = zr[s];
+        zv[k] = z;
+        float dist = s == S - 1 ? last_dist : __fsub_rn(zr[s + 1], z);
+        dist = __fmul_rn(dist, nrm);
+        float t = __fadd_rn(fmaxf(sig, 0.f), 1e-6f);
+        float a = __fsub_rn(1.0f, expf(-__fmul_rn(t, dist)));
+        alpha[k] = a;
+        local *= (double)__fadd_rn(__fsub_rn(1.0f, a), 1e-10f);
+      }
+    }
+    // exclusive scan of the lane products
+    double incl = local;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      double up = shfl_up_f64(incl, d);
+      if (lane >= d) incl *= up;
+    }
+    double run = shfl_up_f64(incl, 1);
+    if (lane == 0) run = 1.0;
+    float acc_rgb[3] = {0.f, 0.f, 0.f}, acc_w = 0.f, acc_d = 0.f;
+#pragma unroll
+    for (int k = 0; k < kMaxSeg; ++k) {
+      int s = s0 + k;
+      if (k < seg && s < S) {
+        float T = (float)run;
+        float w = __fmul_rn(alpha[k], T);
+        run *= (double)__fadd_rn(__fsub_rn(1.0f, alpha[k]), 1e-10f);
+        if (weights) weights[(int64_t)ray * S + s] = w;
+        if (last_weight && s == S - 1) last_weight[ray] = w;
+        if (MODE == 1) {
+          acc_rgb[0] += w * col[k][0];
+          acc_rgb[1] += w * col[k][1];
+          acc_rgb[2] += w * col[k][2];
+          acc_w += w;
+          acc_d += w * zv[k];
+        }
+      }
+    }
+    if (MODE == 1) {
+      acc_rgb[0] = warp_sum(acc_rgb[0]);
+      acc_rgb[1] = warp_sum(acc_rgb[1]);
+      acc_rgb[2] = warp_sum(acc_rgb[2]);
+      acc_w = warp_sum(acc_w);
+      acc_d = warp_sum(acc_d);
+      if (lane == 0) {
+        if (white_bkgd) {
+          float bgw = 1.0f - acc_w;
+          acc_rgb[0] += bgw; acc_rgb[1] += bgw; acc_rgb[2] += bgw;
+        }
+        if (rgb_map) {
+          rgb_map[ray * 3 + 0] = acc_rgb[0]; rgb_map[ray * 3 + 1] = acc_rgb[1]; rgb_map[ray * 3 + 2] = acc_rgb[2];
+        }
+        if (acc_map) acc_map[ray] = acc_w;
+        if (depth_map) depth_map[ray] = acc_d;
+        if (disp_map) disp_map[ray] = __fdiv_rn(1.0f, fmaxf(1e-10f, __fdiv_rn(acc_d, acc_w)));
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------- a10 sample_pdf
+static constexpr int kMaxBins = 256;
+
+// One warp per ray (HELP:537-581).  cdf: w+=1e-5; pdf = w/sum(w); running fp64 sum rounded per
+// element (torch CPU cumsum).  The row sum is taken in fp64 (order-independent to fp32 rounding).
+// Inversion: inds = #(cdf <= u) (searchsorted right=True); below=max(0,inds-1); above=min(nb-1,inds);
+// denom<1e-5 -> 1; sample = bins_b + (u-cdf_b)/denom*(bins_a-bins_b), each op rounded separately.
+template <bool HAVE_CDF>
+__global__ void sample_pdf_kernel(int R, int nb, const float* __restrict__ bins,
+                                  const float* __restrict__ win, int64_t w_stride, int N,
+                                  const float* __restrict__ u, int u_per_ray,
+                                  float* __restrict__ samples, int64_t* __restrict__ inds) {
+  extern __shared__ float sm[];
+  const int lane = threadIdx.x & 31;
+  const int wib = threadIdx.x >> 5;
+  const int warps_per_block = blockDim.x >> 5;
+  float* cdf = sm + (size_t)wib * 2 * kMaxBins;
+  float* bn = cdf + kMaxBins;
+  for (int ray = blockIdx.x * warps_per_block + wib; ray < R; ray += gridDim.x * warps_per_block) {
+    __syncwarp();
+    for (int i = lane; i < nb; i += 32) bn[i] = bins[(int64_t)ray * nb + i];
+    if (HAVE_CDF) {
+      for (int i = lane; i < nb; i += 32) cdf[i] = win[(int64_t)ray * nb + i];
+    } else {
+      const int nw = nb - 1;
+      const int seg = (nw + 31) / 32;
+      const float* wr = win + (int64_t)ray * w_stride;
+      float wv[kMaxBins / 32];
+      double part = 0.0;
+#pragma unroll
+      for (int k = 0; k < kMaxBins / 32; ++k) {
+        int i = lane * seg + k;
+        wv[k] = 0.f;
+        if (k < seg && i < nw) {
+          wv[k] = __fadd_rn(wr[i], 1e-5f);
+          part += (double)wv[k];
+        }
+      }
+      double tot = part;
+#pragma unroll
+      for (int m = 16; m > 0; m >>= 1) tot += shfl_xor_f64(tot, m);
+      const float total = (float)tot;
+      double lsum = 0.0;
+#pragma unroll
+      for (int k = 0; k < kMaxBins / 32; ++k) {
+        int i = lane * seg + k;
+        if (k < seg && i < nw) {
+          wv[k] = __fdiv_rn(wv[k], total);
+          lsum += (double)wv[k];
+        }
+      }
+      double incl = lsum;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        double up = shfl_up_f64(incl, d);
+        if (lane >= d) incl += up;
+      }
+      double run = shfl_up_f64(incl, 1);
+      if (lane == 0) {
+        run = 0.0;
+        cdf[0] = 0.f;
+      }
+#pragma unroll
+      for (int k = 0; k < kMaxBins / 32; ++k) {
+        int i = lane * seg + k;
+        if (k < seg && i < nw) {
+          run += (double)wv[k];
+          cdf[i + 1] = (float)run;
+        }
+      }
+    }
+    __syncwarp();
+    for (int j = lane; j < N; j += 32) {
+      float uu = u_per_ray ? u[(int64_t)ray * N + j] : u[j];
+      int lo = 0, hi = nb;  // first index with cdf > uu
+      while (lo < hi) {
+        int mid = (lo + hi) >> 1;
+        if (cdf[mid] <= uu) lo = mid + 1; else hi = mid;
+      }
+      int below = max(0, lo - 1), above = min(nb - 1, lo);
+      float cb = cdf[below], ca = cdf[above];
+      float den = __fsub_rn(ca, cb);
+      if (den < 1e-5f) den = 1.0f;
+      float t = __fdiv_rn(__fsub_rn(uu, cb), den);
+      float bb = bn[below], ba = bn[above];
+      samples[(int64_t)ray * N + j] = __fadd_rn(bb, __fmul_rn(t, __fsub_rn(ba, bb)));
+      if (inds) inds[(int64_t)ray * N + j] = lo;
+    }
+  }
+}
+
+// ----------------------------------------------------------------------------- a11 sort-merge
+// out = sort(cat(a, b)) per ray (upstream render_rays).  Bitonic network in shared memory over the
+// next power of two (padding +inf); values only, so the result equals torch.sort's.
+__global__ void sort_merge_kernel(int R, int na, const float* __restrict__ a, int nb,
+                                  const float* __restrict__ b, float* __restrict__ out, int npow2) {
+  extern __shared__ float sm[];
+  const int lane = threadIdx.x & 31;
+  const int wib = threadIdx.x >> 5;
+  const int warps_per_block = blockDim.x >> 5;
+  float* v = sm + (size_t)wib * npow2;
+  const int n = na + nb;
+  for (int ray = blockIdx.x * warps_per_block + wib; ray < R; ray += gridDim.x * warps_per_block) {
+    __syncwarp();
+    for (int i = lane; i < npow2; i += 32) {
+      float x = CUDART_INF_F;
+      if (i < na) x = a[(int64_t)ray * na + i];
+      else if (i < n) x = b[(int64_t)ray * nb + (i - na)];
+      v[i] = x;
+    }
+    __syncwarp();
+    for (int k = 2; k <= npow2; k <<= 1) {
+      for (int j = k >> 1; j > 0; j >>= 1) {
+        for (int t = lane; t < (npow2 >> 1); t += 32) {
+          int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));  // index with bit j clear
+          int p = i | j;
+          bool up = (i & k) == 0;
+          float x = v[i], y = v[p];
+          if ((x > y) == up) {
+            v[i] = y;
+            v[p] = x;
+          }
+        }
+        __syncwarp();
+      }
+    }
+    for (int i = lane; i < n; i += 32) out[(int64_t)ray * n + i] = v[i];
+  }
+}
+
+}  // namespace dfn
+
+using namespace dfn;
+
+extern "C" int dfn_get_rays(int n_rows, int n_cols, const float* xs, const float* ys, float focal,
+                            float cx, float cy, const float* c2w_host, float* rays_o, float* rays_d,
+                            float* viewdirs, void* stream) {
+  DFN_CHECK_ARG(n_rows > 0 && n_cols > 0 && xs && ys && c2w_host && rays_d, "dfn_get_rays: bad argument");
+  Pose p;
+  for (int i = 0; i < 12; ++i) p.m[i] = c2w_host[i];
+  int64_t n = (int64_t)n_rows * n_cols;
+  get_rays_kernel<<<grid_for(n), kThreads, 0, (cudaStream_t)stream>>>(n_rows, n_cols, xs, ys, focal, cx, cy, p,
+                                                                     rays_o, rays_d, viewdirs);
+  DFN_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int dfn_z_vals(int R, int S, const float* t_vals, const float* near, const float* far,
+                          const float* rnd, float* z_out, void* stream) {
+  DFN_CHECK_ARG(R > 0 && S > 0 && t_vals && near && far && z_out, "dfn_z_vals: bad argument");
+  z_vals_kernel<<<grid_for((int64_t)R * S), kThreads, 0, (cudaStream_t)stream>>>(R, S, t_vals, near, far, rnd, z_out);
+  DFN_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int dfn_embed(int64_t P, const float* x, int L, int kind, float* out, void* stream) {
+  DFN_CHECK_ARG(P > 0 && x && out && L > 0 && L <= 16 && (kind == 0 || kind == 1), "dfn_embed: bad argument");
+  int D = kind == 0 ? 3 + 6 * L : 6 * L;
+  embed_kernel<<<grid_for(P * D), kThreads, 0, (cudaStream_t)stream>>>(P, x, L, kind, out);
+  DFN_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int dfn_composite_fields(int n_box, int64_t n, const float* sigma, const float* feat,
+                                    float* sigma_sum, float* feat_w, void* stream) {
+  DFN_CHECK_ARG(n_box >= 1 && n > 0 && sigma && feat && sigma_sum && feat_w, "dfn_composite_fields: bad argument");
+  composite_fields_kernel<<<grid_for(n), kThreads, 0, (cudaStream_t)stream>>>(n_box, n, sigma, feat, sigma_sum, feat_w);
+  DFN_LAUNCH_CHECK();
+  return 0;
+}
+
+static int rays_grid(int R, int warps_per_block) {
+  int64_t blocks = ((int64_t)R + warps_per_block - 1) / warps_per_block;
+  int64_t cap = (int64_t)num_sms() * 16;
+  return (int)(blocks < cap ? (blocks < 1 ? 1 : blocks) : cap);
+}
+
+extern "C" int dfn_calc_volume_weights(int R, int S, const float* z_vals, const float* ray_vector,
+                                       const float* sigma, float last_dist, float* weights, void* stream) {
+  DFN_CHECK_ARG(R > 0 && S > 0 && S <= 32 * kMaxSeg && z_vals && ray_vector && sigma && weights,
+                "dfn_calc_volume_weights: bad argument (S <= 256)");
+  volume_weights_kernel<0><<<rays_grid(R, 8), 256, 0, (cudaStream_t)stream>>>(
+      R, S, sigma, z_vals, ray_vector, nullptr, 0, 0, last_dist, nullptr, nullptr, nullptr, weights, nullptr, nullptr);
+  DFN_LAUNCH_CHECK();
+  return 0;
+}
+
+int dfn::launch_raw2outputs(int R, int S, const float* raw, const float* z_vals, const float* rays_d,
+                            const float* bc_rgb, int raw_is_feat, int white_bkgd, float last_dist, float* rgb_map,
+                            float* disp_map, float* acc_map, float* weights, float* depth_map, float* last_weight,
+                            cudaStream_t st) {
+  DFN_CHECK_ARG(R > 0 && S > 0 && S <= 32 * kMaxSeg && raw && z_vals && rays_d,
+                "dfn_raw2outputs: bad argument (S <= 256)");
+  DFN_CHECK_ARG((reinterpret_cast<uintptr_t>(raw) & 15) == 0, "dfn_raw2outputs: raw must be 16-byte aligned");
+  volume_weights_kernel<1><<<rays_grid(R, 8), 256, 0, st>>>(R, S, raw, z_vals, rays_d, bc_rgb, raw_is_feat, white_bkgd,
+                                                           last_dist, rgb_map, disp_map, acc_map, weights, depth_map,
+                                                           last_weight);
+  DFN_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int dfn_raw2outputs(int R, int S, const float* raw, const float* z_vals, const float* rays_d,
+                               const float* bc_rgb, int raw_is_feat, int white_bkgd, float last_dist,
+                               float* rgb_map, float* disp_map, float* acc_map, float* weights,
+                               float* depth_map, void* stream) {
+  return launch_raw2outputs(R, S, raw, z_vals, rays_d, bc_rgb, raw_is_feat, white_bkgd, last_dist, rgb_map, disp_map,
+                            acc_map, weights, depth_map, nullptr, (cudaStream_t)stream);
+}
+
+extern "C" int dfn_sample_pdf(int R, int nb, const float* bins, const float* weights, int64_t w_stride,
+                              int N, const float* u, int u_per_ray, float* samples, int64_t* inds,
+                              void* stream) {
+  DFN_CHECK_ARG(R > 0 && nb >= 2 && nb <= kMaxBins && bins && weights && N > 0 && u && samples && w_stride >= nb - 1,
+                "dfn_sample_pdf: bad argument (nb <= 256)");
+  const int wpb = 8;
+  size_t smem = (size_t)wpb * 2 * kMaxBins * sizeof(float);
+  sample_pdf_kernel<false><<<rays_grid(R, wpb), wpb * 32, smem, (cudaStream_t)stream>>>(
+      R, nb, bins, weights, w_stride, N, u, u_per_ray, samples, inds);
+  DFN_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int dfn_invert_cdf(int R, int nb, const float* bins, const float* cdf, int N, const float* u,
+                              int u_per_ray, float* samples, int64_t* inds, void* stream) {
+  DFN_CHECK_ARG(R > 0 && nb >= 2 && nb <= kMaxBins && bins && cdf && N > 0 && u && samples,
+                "dfn_invert_cdf: bad argument (nb <= 256)");
+  const int wpb = 8;
+  size_t smem = (size_t)wpb * 2 * kMaxBins * sizeof(float);
+  sample_pdf_kernel<true><<<rays_grid(R, wpb), wpb * 32, smem, (cudaStream_t)stream>>>(
+      R, nb, bins, cdf, nb, N, u, u_per_ray, samples, inds);
+  DFN_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int dfn_sort_merge(int R, int na, const float* a, int nb, const float* b, float* out, void* stream) {
+  DFN_CHECK_ARG(R > 0 && na >= 0 && nb >= 0 && na + nb > 0 && na + nb <= 1024 && out && (na == 0 || a) && (nb == 0 || b),
+                "dfn_sort_merge: bad argument (na+nb <= 1024)");
+  int npow2 = 2;
+  while (npow2 < na + nb) npow2 <<= 1;
+  const int wpb = 8;
+  size_t smem = (size_t)wpb * npow2 * sizeof(float);
+  sort_merge_kernel<<<rays_grid(R, wpb), wpb * 32, smem, (cudaStream_t)stream>>>(R, na, a, nb, b, out, npow2);
+  DFN_LAUNCH_CHECK();
+  return 0;
+}

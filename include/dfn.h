@@ -1,0 +1,191 @@
+/*
+ * dfn.h -- C ABI of libdfn.so, the B200 (sm_100a) volume-rendering hot path for DFA-NeRF.
+ *
+ * The reference (ShunyuYao/DFA-NeRF) has no plugin / FFI layer for this path: it is plain
+ * PyTorch called from NeRFs/DFANeRF/run_nerf_com_trainExpLater.py.
+ * Each entry point below therefore cites the reference *function* it replaces; the
+ * Python shim in dfa-nerf_b200/ binds these with ctypes and re-exports the reference's
+ * own names (INTEGRATION.md shows the stub a maintainer would add).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the parameter name ends in _host;
+ *   - tensors are dense row-major fp32 (indices int64) with the shapes given;
+ *   - all work is enqueued on `stream` (a cudaStream_t passed as void*); nothing
+ *     synchronises, nothing allocates: the caller owns outputs and workspaces;
+ *   - return value: 0 = ok, >0 = cudaError_t, <0 = DFN_E_* below; dfn_last_error()
+ *     returns a thread-local message for the last non-zero return;
+ *   - HELP = NeRFs/DFANeRF/run_nerf_helpers.py, MAIN = NeRFs/DFANeRF/run_nerf_com_trainExpLater.py,
+ *     DEC = NeRFs/DFANeRF/decoder.py (paths relative to the reference root).
+ */
+#ifndef DFN_H_
+#define DFN_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DFN_ABI_VERSION 1
+
+enum {
+  DFN_E_ARG = -1,         /* bad argument (null pointer, size, unsupported shape) */
+  DFN_E_STATE = -2,       /* model not loaded / wrong kind */
+  DFN_E_WORKSPACE = -3,   /* workspace too small */
+  DFN_E_UNSUPPORTED = -4  /* configuration the kernels do not cover */
+};
+
+/* Arithmetic used for the MLP layers. */
+enum {
+  DFN_PREC_FP32 = 0,   /* fp32 FFMA kernels (no tensor cores), reference-exact up to summation order */
+  DFN_PREC_BF16 = 1,   /* tcgen05 kind::f16 bf16 operands, fp32 accumulate in TMEM (throughput mode) */
+  DFN_PREC_BF16X3 = 3  /* tcgen05 split-bf16: A_hi*W_hi + A_lo*W_hi + A_hi*W_lo (fp32-parity mode) */
+};
+
+enum {
+  DFN_MODEL_FACENERF = 0, /* HELP:242-299 FaceNeRF(use_viewdirs=True) */
+  DFN_MODEL_NERF = 1      /* HELP:342-396 NeRF(use_viewdirs=True)     */
+};
+
+int dfn_abi_version(void);
+const char* dfn_last_error(void);
+
+/* ---- a1  get_rays  (HELP:449-465) -------------------------------------------------------
+ * xs[n_cols], ys[n_rows]: the torch.linspace pixel-centre tables (W//stride, H//stride entries);
+ * c2w_host: 12 floats, row-major [3,4], HOST memory.  Outputs [n_rows*n_cols,3]; rays_o is the
+ * broadcast origin; viewdirs (nullable) = rays_d/||rays_d|| (upstream render(); DEC:337). */
+int dfn_get_rays(int n_rows, int n_cols, const float* xs, const float* ys, float focal, float cx,
+                 float cy, const float* c2w_host, float* rays_o, float* rays_d, float* viewdirs,
+                 void* stream);
+
+/* ---- a2  depth sampling  (MAIN:617-619; upstream stratified block) ------------------------
+ * z[r,s] = near[r]*(1-t[s]) + far[r]*t[s];  rand (nullable, [R,S]) applies the stratified jitter. */
+int dfn_z_vals(int R, int S, const float* t_vals, const float* near, const float* far,
+               const float* rand, float* z_out, void* stream);
+
+/* ---- a4 / a4'  positional encodings  (HELP:21-70 Embedder; DEC:257-275 transform_points) ---
+ * kind 0: [x, sin(2^k x), cos(2^k x)]_k  -> out [P, 3+6L];
+ * kind 1: p/=2; [sin(2^k pi p), cos(2^k pi p)]_k -> out [P, 6L]. */
+int dfn_embed(int64_t P, const float* x, int L, int kind, float* out, void* stream);
+
+/* ---- a7  composite_function  (MAIN:146-166) -------------------------------------------------
+ * sigma [n_box,n], feat [n_box,n,3] -> sigma_sum [n], feat_w [n,3]. */
+int dfn_composite_fields(int n_box, int64_t n, const float* sigma, const float* feat,
+                         float* sigma_sum, float* feat_w, void* stream);
+
+/* ---- a8  calc_volume_weights  (MAIN:169-179) ------------------------------------------------ */
+int dfn_calc_volume_weights(int R, int S, const float* z_vals, const float* ray_vector,
+                            const float* sigma, float last_dist, float* weights, void* stream);
+
+/* ---- a8+a9  raw2outputs  (upstream name; core = MAIN:169-179 + MAIN:706) ----------------------
+ * raw [R,S,4] = (rgb pre-sigmoid, sigma).  bc_rgb (nullable, [R,3]) replaces the last sample's
+ * colour (MAIN:669-671).  raw_is_feat != 0: channels 0..2 are already colours (Decoder head, DEC:346).
+ * Outputs (each nullable): rgb_map [R,3], disp_map [R], acc_map [R], weights [R,S], depth_map [R]. */
+int dfn_raw2outputs(int R, int S, const float* raw, const float* z_vals, const float* rays_d,
+                    const float* bc_rgb, int raw_is_feat, int white_bkgd, float last_dist,
+                    float* rgb_map, float* disp_map, float* acc_map, float* weights,
+                    float* depth_map, void* stream);
+
+/* ---- a10  sample_pdf  (HELP:537-581) --------------------------------------------------------
+ * bins [R,nb], weights [R,nb-1] (row stride w_stride floats, so a [R,S] weights tensor can be
+ * passed as weights+1 with w_stride=S for the weights[...,1:-1] slice), u [N] (u_per_ray=0) or
+ * [R,N] (u_per_ray=1).  samples [R,N]; inds (nullable) int64 [R,N] = searchsorted(cdf,u,right). */
+int dfn_sample_pdf(int R, int nb, const float* bins, const float* weights, int64_t w_stride,
+                   int N, const float* u, int u_per_ray, float* samples, int64_t* inds,
+                   void* stream);
+
+/* Inversion only, with the cdf [R,nb] given (HELP:563-579): used to check indices bit-for-bit. */
+int dfn_invert_cdf(int R, int nb, const float* bins, const float* cdf, int N, const float* u,
+                   int u_per_ray, float* samples, int64_t* inds, void* stream);
+
+/* ---- a11  merge  (upstream: z_vals,_ = sort(cat([z_vals, z_samples]))) ------------------------ */
+int dfn_sort_merge(int R, int na, const float* a, int nb, const float* b, float* out, void* stream);
+
+/* ---- a5 / a5'  the 8x256 skip-MLP  (HELP:242-299 FaceNeRF, HELP:342-396 NeRF) ------------------ */
+typedef struct dfn_model dfn_model;
+
+typedef struct {
+  int kind;           /* DFN_MODEL_* */
+  int D;              /* 8 */
+  int W;              /* 256 */
+  int input_ch;       /* 63 = 3+6*multires */
+  int input_ch_views; /* 27 = 3+6*multires_views */
+  int dim_aud;        /* 64 (FaceNeRF) / 0 (NeRF) */
+  int skip;           /* 4 : layer index after which [input_pts, h] is concatenated */
+  int multires;       /* 10 */
+  int multires_views; /* 4 */
+} dfn_model_desc;
+
+int dfn_model_create(const dfn_model_desc* desc, dfn_model** out);
+void dfn_model_destroy(dfn_model* m);
+
+/* Number of tensors dfn_model_load expects, in this order (state_dict order of the reference):
+ * pts_linears.{0..D-1}.{weight,bias}, views_linears.{0..nv-1}.{weight,bias},
+ * feature_linear.{weight,bias}, alpha_linear.{weight,bias}, rgb_linear.{weight,bias}
+ * with nv = 1 + D/4 for FaceNeRF (HELP:265-266) and 1 for NeRF (HELP:358-359). */
+int dfn_model_num_tensors(const dfn_model* m);
+
+/* tensors_host[i]: HOST fp32 pointers in the order above; repacks to the kernel layouts
+ * (fp32 row-major for the FFMA path; bf16 hi/lo planes, K padded to 64, 128-byte swizzled
+ * K-major tiles for the tcgen05 path) and uploads on `stream`. */
+int dfn_model_load(dfn_model* m, const float* const* tensors_host, int n_tensors, void* stream);
+
+/* Module forward on explicit embedded inputs: x [P, input_ch+dim_aud+input_ch_views] -> out [P,4]
+ * (HELP:275-299 / HELP:372-396).  fp32 FFMA path.  workspace: dfn_mlp_workspace_bytes(P) bytes. */
+int64_t dfn_mlp_workspace_bytes(const dfn_model* m, int64_t P);
+int dfn_mlp_forward(const dfn_model* m, int64_t P, const float* x, float* out, void* workspace,
+                    int64_t workspace_bytes, void* stream);
+
+/* network_query_fn (upstream run_network): pts = rays_o + rays_d*z, PE(pts) | latent | PE(viewdir)
+ * -> model, fused.  rays_o/rays_d/viewdirs [R,3], z_vals [R,S], latent [dim_aud] (nullable for
+ * NeRF) -> raw [R,S,4].  precision: DFN_PREC_*.  workspace: dfn_query_workspace_bytes(R,S). */
+int64_t dfn_query_workspace_bytes(const dfn_model* m, int64_t R, int S, int precision);
+int dfn_query_points(const dfn_model* m, int64_t R, int S, const float* rays_o, const float* rays_d,
+                     const float* viewdirs, const float* z_vals, const float* latent, float* raw,
+                     int precision, void* workspace, int64_t workspace_bytes, void* stream);
+
+/* ---- render_rays  (upstream name; MAIN:114 is the reference's dead stub) -----------------------
+ * coarse pass (N_samples) -> raw2outputs -> sample_pdf(z_mid, w[1:-1], N_importance) -> sort-merge
+ * -> fine pass (N_samples+N_importance) with `fine` (or `coarse` when null) -> raw2outputs.
+ * N_importance = 0 stops after the coarse pass.
+ * Inputs: rays_o, rays_d, viewdirs [R,3]; near, far [R]; bc_rgb [R,3] (nullable); latent [dim_aud];
+ *         t_vals [N_samples] and u_vals [N_importance] = torch.linspace(0,1,.) tables;
+ *         perturb_rand (nullable, [R,N_samples]); z_samples_in (nullable, [R,N_importance]):
+ *         teacher-forced fine depths that replace the sample_pdf output.
+ * Outputs (each nullable): rgb_map [R,3], disp_map [R], acc_map [R], last_weight [R],
+ *         rgb0 [R,3], z_samples_out [R,N_importance], z_vals_out [R,N_samples+N_importance]. */
+typedef struct {
+  const float* rays_o;
+  const float* rays_d;
+  const float* viewdirs;
+  const float* near;
+  const float* far;
+  const float* bc_rgb;
+  const float* latent;
+  const float* t_vals;
+  const float* u_vals;
+  const float* perturb_rand;
+  const float* z_samples_in;
+  float* rgb_map;
+  float* disp_map;
+  float* acc_map;
+  float* last_weight;
+  float* rgb0;
+  float* z_samples_out;
+  float* z_vals_out;
+  int64_t u_per_ray; /* 0: u_vals is [N_importance]; 1: u_vals is [R,N_importance] (perturb > 0) */
+} dfn_render_io;
+
+int64_t dfn_render_workspace_bytes(const dfn_model* coarse, int64_t R, int N_samples,
+                                   int N_importance, int precision);
+int dfn_render_rays(const dfn_model* coarse, const dfn_model* fine, int64_t R, int N_samples,
+                    int N_importance, const dfn_render_io* io, int white_bkgd, int precision,
+                    void* workspace, int64_t workspace_bytes, void* stream);
+
+/* Number of kernels the last dfn_render_rays / dfn_query_points call on this thread launched. */
+int dfn_last_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DFN_H_ */

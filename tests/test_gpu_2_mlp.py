@@ -1,0 +1,153 @@
+"""GPU parity of the skip-MLP: fp32 FFMA module forward, then the fused tcgen05 query path
+(bf16x3 against the fp32 oracle at 1e-4 on what compositing consumes; bf16 against the
+bf16-operand restatement of the oracle)."""
+import pytest
+import torch
+
+from oracle import nerf_oracle as O
+from oracle import synth
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda'
+
+
+def maxerr(a, b):
+    return (a.detach().cpu().double() - b.detach().cpu().double()).abs().max().item()
+
+
+@pytest.fixture(scope='module')
+def dfn():
+    import dfa_nerf_b200
+    return dfa_nerf_b200
+
+
+def face(dfn, seed):
+    m = dfn.FaceNeRF(D=8, W=256, input_ch=63, input_ch_views=27, dim_aud=64, output_ch=4, skips=[4], use_viewdirs=True)
+    m.load_state_dict(synth.facenerf_state_dict(seed))
+    return m.to(DEV)
+
+
+def nerf(dfn, seed):
+    m = dfn.NeRF(D=8, W=256, input_ch=63, input_ch_views=27, output_ch=4, skips=[4], use_viewdirs=True)
+    m.load_state_dict(synth.nerf_state_dict(seed))
+    return m.to(DEV)
+
+
+def test_module_forward_fp32_golden(dfn, golden):
+    g = golden('mlp')
+    y = face(dfn, g['face_seed'])(g['x_face'].to(DEV))
+    assert y.shape == (48, 4)
+    # sigma has magnitude ~40 (gain 1431): 2e-4 absolute is ~5e-6 relative
+    assert maxerr(y[:, :3], g['y_face'][:, :3]) < 2e-5
+    assert maxerr(y[:, 3], g['y_face'][:, 3]) < 5e-4
+    yn = nerf(dfn, g['nerf_seed'])(g['x_nerf'].to(DEV))
+    assert maxerr(yn[:, :3], g['y_nerf'][:, :3]) < 2e-5
+    assert maxerr(yn[:, 3], g['y_nerf'][:, 3]) < 5e-4
+
+
+def test_module_forward_fp32_ragged(dfn):
+    sd = synth.facenerf_state_dict(1)
+    m = face(dfn, 1)
+    for P in (1, 63, 1000):
+        x = torch.randn(P, 154)
+        with torch.no_grad():
+            ref = O.facenerf_forward(sd, x)
+        y = m(x.to(DEV))
+        assert maxerr(y[:, :3], ref[:, :3]) < 5e-5 and maxerr(y[:, 3], ref[:, 3]) < 2e-3
+    assert m(torch.zeros(0, 154, device=DEV)).shape == (0, 4)
+    assert m(torch.zeros(2, 5, 154, device=DEV)).shape == (2, 5, 4)
+
+
+def _query_case(R, S, seed=11):
+    fr = synth.frame_inputs(H=R, W=1, seed=seed)
+    g = torch.Generator().manual_seed(seed)
+    ro = fr['c2w'][:3, -1].expand(R, 3).contiguous()
+    rd = torch.randn(R, 3, generator=g) * 0.2 + torch.tensor([0., 0., -1.])
+    vd = rd / torch.norm(rd, dim=-1, keepdim=True)
+    z, _ = torch.sort(torch.rand(R, S, generator=g) * 0.6 + 0.4, -1)
+    return ro, rd, vd, z, fr['aud']
+
+
+def _alpha_err(raw, ref, z, rd):
+    """Error of what compositing consumes: weights and sigmoid colours."""
+    w = O.calc_volume_weights(z, rd, raw[..., 3].cpu())
+    wr = O.calc_volume_weights(z, rd, ref[..., 3])
+    return maxerr(w, wr), maxerr(torch.sigmoid(raw[..., :3]), torch.sigmoid(ref[..., :3]))
+
+
+@pytest.mark.parametrize('R,S', [(2, 64), (37, 64), (21, 192), (300, 64)])
+def test_query_points_fp32(dfn, R, S):
+    ro, rd, vd, z, aud = _query_case(R, S)
+    sd = synth.facenerf_state_dict(0)
+    eng = dfn.RenderEngine(face(dfn, 0), None, S, 0, precision=dfn.PREC_FP32)
+    raw = eng.query_points(eng.network_fn, ro.to(DEV), rd.to(DEV), vd.to(DEV), z.to(DEV), aud.to(DEV))
+    with torch.no_grad():
+        ref = O.run_network(sd, 'facenerf', ro[:, None] + rd[:, None] * z[:, :, None], vd, aud)
+    ew, ec = _alpha_err(raw, ref, z, rd)
+    assert ew < 1e-5 and ec < 1e-5, (ew, ec)
+
+
+@pytest.mark.parametrize('R,S', [(2, 64), (37, 64), (21, 192), (600, 64)])
+def test_query_points_bf16x3_vs_fp32_oracle(dfn, R, S):
+    ro, rd, vd, z, aud = _query_case(R, S)
+    sd = synth.facenerf_state_dict(0)
+    eng = dfn.RenderEngine(face(dfn, 0), None, S, 0, precision=dfn.PREC_BF16X3)
+    raw = eng.query_points(eng.network_fn, ro.to(DEV), rd.to(DEV), vd.to(DEV), z.to(DEV), aud.to(DEV))
+    with torch.no_grad():
+        ref = O.run_network(sd, 'facenerf', ro[:, None] + rd[:, None] * z[:, :, None], vd, aud)
+    assert torch.isfinite(raw).all()
+    ew, ec = _alpha_err(raw, ref, z, rd)
+    print('bf16x3 R=%d S=%d: weights err %.2e, colour err %.2e, raw sigma err %.2e' % (R, S, ew, ec, maxerr(raw[..., 3], ref[..., 3])))
+    assert ew < 1e-4 and ec < 1e-4, (ew, ec)      # north-star tolerance: 1e-4 max-abs
+
+
+@pytest.mark.parametrize('R,S', [(37, 64), (21, 192)])
+def test_query_points_bf16_vs_bf16_oracle(dfn, R, S):
+    ro, rd, vd, z, aud = _query_case(R, S)
+    sd = synth.facenerf_state_dict(0)
+    eng = dfn.RenderEngine(face(dfn, 0), None, S, 0, precision=dfn.PREC_BF16)
+    raw = eng.query_points(eng.network_fn, ro.to(DEV), rd.to(DEV), vd.to(DEV), z.to(DEV), aud.to(DEV))
+    pts = (ro[:, None] + rd[:, None] * z[:, :, None]).reshape(-1, 3)
+    x = torch.cat([O.embed(pts, 10), aud[None].expand(pts.shape[0], -1), O.embed(vd[:, None].expand(R, S, 3).reshape(-1, 3), 4)], -1)
+    with torch.no_grad():
+        ref16 = O.facenerf_forward_bf16(sd, x).reshape(R, S, 4)
+        ref32 = O.facenerf_forward(sd, x).reshape(R, S, 4)
+    assert torch.isfinite(raw).all()
+    # same operand rounding, different accumulation order -> close to the bf16 restatement ...
+    e16 = maxerr(raw[..., :3], ref16[..., :3])
+    s16 = maxerr(raw[..., 3], ref16[..., 3])
+    # ... and the bf16 rounding itself is what separates it from fp32
+    e32 = maxerr(raw[..., :3], ref32[..., :3])
+    s32 = maxerr(raw[..., 3], ref32[..., 3])
+    print('bf16 R=%d S=%d: vs bf16-oracle rgb %.2e sigma %.2e | vs fp32 rgb %.2e sigma %.2e' % (R, S, e16, s16, e32, s32))
+    assert e16 < 0.3 * max(e32, 1e-3) + 2e-3 and s16 < 0.3 * max(s32, 1e-2) + 0.1
+
+
+def test_query_points_nerf_model(dfn):
+    R, S = 19, 64
+    ro, rd, vd, z, aud = _query_case(R, S, seed=5)
+    sd = synth.nerf_state_dict(2)
+    net = nerf(dfn, 2)
+    with torch.no_grad():
+        ref = O.run_network(sd, 'nerf', ro[:, None] + rd[:, None] * z[:, :, None], vd, aud)
+    for prec, tol in ((dfn.PREC_FP32, 1e-5), (dfn.PREC_BF16X3, 1e-4)):
+        eng = dfn.RenderEngine(net, None, S, 0, precision=prec)
+        raw = eng.query_points(net, ro.to(DEV), rd.to(DEV), vd.to(DEV), z.to(DEV), None)
+        ew, ec = _alpha_err(raw, ref, z, rd)
+        assert ew < tol and ec < tol, (prec, ew, ec)
+
+
+def test_tc_matches_fp32_kernel_at_scale(dfn):
+    """Full-size cross-check on the device: 20k rays x 192 samples, bf16x3 vs the fp32 FFMA kernels."""
+    R, S = 20000, 192
+    ro, rd, vd, z, aud = _query_case(R, S, seed=3)
+    net = face(dfn, 1)
+    args = [t.to(DEV) for t in (ro, rd, vd, z, aud)]
+    e32 = dfn.RenderEngine(net, None, S, 0, precision=dfn.PREC_FP32)
+    ex3 = dfn.RenderEngine(net, None, S, 0, precision=dfn.PREC_BF16X3)
+    a = e32.query_points(net, *args)
+    b = ex3.query_points(net, *args)
+    wa = dfn.calc_volume_weights(args[3], args[1], a[..., 3].contiguous())
+    wb = dfn.calc_volume_weights(args[3], args[1], b[..., 3].contiguous())
+    assert maxerr(wa, wb) < 1e-4
+    assert maxerr(torch.sigmoid(a[..., :3]), torch.sigmoid(b[..., :3])) < 1e-4
