@@ -1,0 +1,272 @@
+#!/usr/bin/env python
+"""bench.py -- rendered rays/s of the hierarchical NeRF hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--precision bf16|bf16x3|fp32]
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+    python bench.py --impl reference            # CPU arm: the oracle port on the host cores
+
+One step = one 450x450 frame (202,500 rays) x (64 coarse + 128 fine samples) of the synthetic
+FaceNeRF field (configs[1] of BASELINE.json): get_rays -> z sampling -> PE + 8x256 skip-MLP ->
+compositing -> sample_pdf -> sort-merge -> fine MLP -> RGB.  With N > 1 the frame's rays are sharded
+contiguously over the ranks and the RGB tile is all-gathered (NCCL) inside the timed step.
+
+Printed JSON (rank 0): `value` = rays/s with inputs resident in HBM; `e2e` = the same through the
+public API with pinned-host inputs/outputs copied every step; `roofline` = tcgen05 MLP kernel against
+the measured bf16 peak; `cpu_baseline` = the oracle port on this box's host cores (bounded sample).
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = 'rendered rays/sec at 450x450x(64+128) samples; 1/2/4/8 B200 vs CPU ref'
+H = W = 450
+N_SAMPLES, N_IMPORTANCE = 64, 128
+FLOP_PER_RAY_FOLDED = 2 * 557184 * (N_SAMPLES + N_SAMPLES + N_IMPORTANCE)
+
+
+def peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(bf16_burst=d['bf16_tflops'], bf16_sustained=d.get('bf16_tflops_sustained', d['bf16_tflops']),
+                    hbm=d['hbm_gbs'], source='measured (MEASURED_PEAKS.json)')
+    return dict(bf16_burst=1590.0, bf16_sustained=1400.0, hbm=6650.0, source='fallback (B200_PROFILING.md)')
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled during the timed region."""
+    Q = 'clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
+        'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
+                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(',')])
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = float(r[1])
+            except Exception:
+                continue
+            for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), r[3:7]):
+                if v.lower().startswith('active'):
+                    reasons.add(name)
+        sm.sort()
+        return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': mx, 'reasons': sorted(reasons),
+                'samples': len(sm)}
+
+
+def cpu_arm(steps, warmup, rays_per_step, threads=None):
+    """The reference's arithmetic (oracle port: HELP.get_rays/Embedder/FaceNeRF/sample_pdf + MAIN.calc_volume_weights
+    composed in upstream render() order) on the host cores, fp32, chunk=2048, bounded ray sample per step."""
+    import torch
+    from oracle import nerf_oracle as O, synth
+    torch.set_num_threads(threads or os.cpu_count() or 1)
+    fr = synth.frame_inputs(H=H, W=W, seed=0)
+    sd_c, sd_f = synth.facenerf_state_dict(0), synth.facenerf_state_dict(1)
+    b = (H * W) // 2 - rays_per_step // 2          # centre of the image: foreground rays
+    times = []
+    with torch.no_grad():
+        for i in range(warmup + steps):
+            t0 = time.perf_counter()
+            O.render(H, W, fr['focal'], fr['cx'], fr['cy'], fr['c2w'], fr['bc_rgb'], fr['aud'], sd_c, sd_f,
+                     fr['near'], fr['far'], N_SAMPLES, N_IMPORTANCE, chunk=2048, ray_slice=(b, b + rays_per_step))
+            if i >= warmup:
+                times.append(time.perf_counter() - t0)
+    times.sort()
+    med = times[len(times) // 2]
+    return rays_per_step / med, med, torch.get_num_threads()
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    rays = 2048
+    value, sec, cores = cpu_arm(max(1, args.steps), max(1, min(args.warmup, 1)), rays)
+    sample = '%d rays (1 chunk of 2048, image centre) x (64+192) FaceNeRF evaluations per step, median of %d' % (rays, max(1, args.steps))
+    print(json.dumps({
+        'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': 'rays/s', 'n_gpus': args.gpus, 'steps': args.steps,
+        'warmup': args.warmup, 'ms_per_step': sec * 1e3, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None,
+        'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': 'FaceNeRF 450x450 x (64 coarse + 128 fine), synthetic seeded weights; CPU arm renders a bounded '
+                               'ray sample of the same frame', 'rays_per_frame': H * W, 'rays_per_step': rays},
+        'cpu_baseline': {'value': value, 'unit': 'rays/s', 'cores': cores, 'kind': 'port', 'sample': sample},
+        'e2e': {'value': value, 'unit': 'rays/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--precision', default='bf16', choices=['bf16', 'bf16x3', 'fp32'])
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        return run_reference(args)
+    args.warmup = max(args.warmup, 3)
+
+    import torch
+    import torch.distributed as dist
+    import dfa_nerf_b200 as dfn
+    from dfa_nerf_b200.distributed import shard_range, gather_rgb
+    from oracle import synth           # synthetic data generator only (no oracle arithmetic on this path)
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    assert torch.cuda.is_available(), 'bench.py needs a GPU (there is no CPU path)'
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    if world > 1:
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', device_id=dev)
+    prec = {'bf16': dfn.PREC_BF16, 'bf16x3': dfn.PREC_BF16X3, 'fp32': dfn.PREC_FP32}[args.precision]
+
+    fr = synth.frame_inputs(H=H, W=W, seed=0)
+
+    def mk(seed):
+        m = dfn.FaceNeRF(D=8, W=256, input_ch=63, input_ch_views=27, dim_aud=64, output_ch=4, skips=[4], use_viewdirs=True)
+        m.load_state_dict(synth.facenerf_state_dict(seed))
+        return m.to(dev)
+
+    eng = dfn.RenderEngine(mk(0), mk(1), N_SAMPLES, N_IMPORTANCE, precision=prec)
+    n_rays = H * W
+    b, e, per = shard_range(n_rays, rank, world)
+    bc_dev, aud_dev = fr['bc_rgb'].to(dev), fr['aud'].to(dev)
+    bc_host, aud_host = fr['bc_rgb'].pin_memory(), fr['aud'].pin_memory()
+    rgb_host = torch.empty((n_rays, 3), dtype=torch.float32).pin_memory()
+    launches = [0]
+
+    def step_resident():
+        out = eng.render_frame(H, W, fr['focal'], fr['c2w'], bc_dev, aud_dev, fr['near'], fr['far'], fr['cx'], fr['cy'],
+                               ray_range=(b, e), want=('rgb_map',))
+        launches[0] += eng.last_launches + 1            # + get_rays
+        return gather_rgb(out['rgb_map'], n_rays) if world > 1 else out['rgb_map']
+
+    def step_e2e():
+        bc = bc_host[b:e].to(dev, non_blocking=True)
+        aud = aud_host.to(dev, non_blocking=True)
+        bc_full = torch.empty((n_rays, 3), dtype=torch.float32, device=dev)
+        bc_full[b:e] = bc
+        out = eng.render_frame(H, W, fr['focal'], fr['c2w'], bc_full, aud, fr['near'], fr['far'], fr['cx'], fr['cy'],
+                               ray_range=(b, e), want=('rgb_map',))
+        full = gather_rgb(out['rgb_map'], n_rays) if world > 1 else out['rgb_map']
+        if rank == 0:
+            rgb_host.copy_(full, non_blocking=True)
+        torch.cuda.current_stream().synchronize()       # the caller consumes the frame
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        for _ in range(steps):
+            fn()
+        ev1.record()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms.item() / steps
+
+    # ---- device-resident throughput, with per-launch events around the tcgen05 kernel ---------------
+    sampler = ClockSampler(local_rank)
+    for _ in range(args.warmup):
+        step_resident()
+    torch.cuda.synchronize()
+    dfn.lib.dfn_profile_enable(1 if prec != dfn.PREC_FP32 else 0)
+    launches[0] = 0
+    sampler.start()
+    ms_step = timed(step_resident, args.steps, 0)
+    clocks = sampler.stop()
+    k_ms, k_n, k_macs = C.c_double(), C.c_int64(), C.c_double()
+    dfn.lib.dfn_profile_collect(C.byref(k_ms), C.byref(k_n), C.byref(k_macs))
+    dfn.lib.dfn_profile_enable(0)
+    n_launch = launches[0]
+    value = n_rays / (ms_step * 1e-3)
+
+    # ---- end to end through the public API with host buffers ------------------------------------------
+    ms_e2e = timed(step_e2e, args.steps, 2)
+    e2e = {'value': n_rays / (ms_e2e * 1e-3), 'unit': 'rays/s',
+           'h2d_bytes_per_step': int((e - b) * 12 + aud_host.numel() * 4 + 48),
+           'd2h_bytes_per_step': int(n_rays * 12) if rank == 0 else 0}
+
+    pk = peaks()
+    roofline = None
+    if k_n.value > 0:
+        achieved = 2.0 * k_macs.value / (k_ms.value * 1e-3) / 1e12
+        roofline = {'bound': 'tensor', 'achieved': achieved, 'peak': pk['bf16_sustained'], 'unit': 'TFLOP/s',
+                    'frac': achieved / pk['bf16_sustained'], 'traffic': None,
+                    'kernel': 'mlp_tc_kernel<%s>' % ('bf16x3' if prec == dfn.PREC_BF16X3 else 'bf16'),
+                    'launches': int(k_n.value), 'avg_launch_ms': k_ms.value / k_n.value,
+                    'kernel_share_of_step': k_ms.value / (ms_step * args.steps),
+                    'flops': 'algorithmic, latent/viewdir columns folded: 2*557,184 per MLP evaluation (BASELINE.md section 2)',
+                    'peak_source': 'bf16 dense sustained, ' + pk['source']}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        v, sec, cores = cpu_arm(3, 1, 2048)
+        cpu = {'value': v, 'unit': 'rays/s', 'cores': cores, 'kind': 'port',
+               'sample': '2048 rays (1 chunk, image centre) x (64+192) FaceNeRF evaluations, median of 3 (%.1f s each)' % sec}
+
+    if rank == 0:
+        print(json.dumps({
+            'metric': METRIC, 'value': value, 'unit': 'rays/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+            'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None,
+            'dtype': {'bf16': 'bf16', 'bf16x3': 'bf16x3 (split bf16, fp32-parity)', 'fp32': 'f32'}[args.precision],
+            'data': 'synthetic',
+            'config': {'workload': 'FaceNeRF 450x450 x (64 coarse + 128 fine samples), synthetic seeded weights/pose/latent '
+                                   '(BASELINE.json configs[1]); one step = one frame',
+                       'rays_per_step': n_rays, 'mlp_evals_per_ray': 256, 'precision': args.precision,
+                       'parallelism': 'rays sharded over %d GPU(s), one all-gather of the RGB tile' % world,
+                       'l2': 'per-step intermediates (~1.4 GB of raw/z buffers) exceed the 126 MB L2; no explicit flush'},
+            'e2e': e2e, 'gpu_launches': n_launch, 'clocks': clocks, 'roofline': roofline, 'cpu_baseline': cpu,
+        }))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

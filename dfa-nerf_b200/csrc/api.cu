@@ -35,6 +35,30 @@ int num_sms() {
 
 static inline int64_t align256(int64_t x) { return (x + 255) / 256 * 256; }
 
+// ---- measurement hook: CUDA events around the tcgen05 kernel launches ---------------------------
+static constexpr int kMaxProf = 4096;
+static bool g_prof_on = false;
+static std::vector<cudaEvent_t> g_prof_ev;
+static int g_prof_n = 0;
+static double g_prof_macs = 0.0;
+
+bool profile_begin(cudaStream_t st, double macs) {
+  if (!g_prof_on || g_prof_n >= kMaxProf) return false;
+  if ((int)g_prof_ev.size() < 2 * (g_prof_n + 1)) {
+    cudaEvent_t a, b;
+    if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b) != cudaSuccess) return false;
+    g_prof_ev.push_back(a);
+    g_prof_ev.push_back(b);
+  }
+  g_prof_macs += macs;
+  cudaEventRecord(g_prof_ev[2 * g_prof_n], st);
+  return true;
+}
+void profile_end(cudaStream_t st) {
+  cudaEventRecord(g_prof_ev[2 * g_prof_n + 1], st);
+  ++g_prof_n;
+}
+
 // x[p, :] = [PE(o + d*z) | latent | PE(viewdir)]  (upstream run_network; HELP:42-52, HELP:276)
 __global__ void build_inputs_kernel(int64_t P, int S, int64_t ray0_pt, int L, int Lv, int dim_aud,
                                     const float* __restrict__ rays_o, const float* __restrict__ rays_d,
@@ -55,7 +79,7 @@ __global__ void build_inputs_kernel(int64_t P, int S, int64_t ray0_pt, int L, in
         v = xc;
       } else {
         const int k = (j - 3) / 6, r = (j - 3) % 6;
-        const float a = __fmul_rn(xc, exp2f((float)k));
+        const float a = __fmul_rn(xc, pow2i(k));
         v = r < 3 ? sinf(a) : cosf(a);
       }
     } else if (j < d_pts + dim_aud) {
@@ -68,7 +92,7 @@ __global__ void build_inputs_kernel(int64_t P, int S, int64_t ray0_pt, int L, in
         v = xc;
       } else {
         const int k = (jj - 3) / 6, r = (jj - 3) % 6;
-        const float a = __fmul_rn(xc, exp2f((float)k));
+        const float a = __fmul_rn(xc, pow2i(k));
         v = r < 3 ? sinf(a) : cosf(a);
       }
     }
@@ -125,6 +149,29 @@ using namespace dfn;
 extern "C" int dfn_abi_version(void) { return DFN_ABI_VERSION; }
 extern "C" const char* dfn_last_error(void) { return g_err; }
 extern "C" int dfn_last_launch_count(void) { return g_launches; }
+
+extern "C" int dfn_profile_enable(int on) {
+  g_prof_on = on != 0;
+  g_prof_n = 0;
+  g_prof_macs = 0.0;
+  return 0;
+}
+
+extern "C" int dfn_profile_collect(double* kernel_ms, int64_t* launches, double* algorithmic_macs) {
+  double ms = 0.0;
+  for (int i = 0; i < g_prof_n; ++i) {
+    DFN_CUDA(cudaEventSynchronize(g_prof_ev[2 * i + 1]));
+    float t = 0.f;
+    DFN_CUDA(cudaEventElapsedTime(&t, g_prof_ev[2 * i], g_prof_ev[2 * i + 1]));
+    ms += t;
+  }
+  if (kernel_ms) *kernel_ms = ms;
+  if (launches) *launches = g_prof_n;
+  if (algorithmic_macs) *algorithmic_macs = g_prof_macs;
+  g_prof_n = 0;
+  g_prof_macs = 0.0;
+  return 0;
+}
 
 extern "C" int dfn_model_create(const dfn_model_desc* desc, dfn_model** out) {
   DFN_CHECK_ARG(desc && out, "dfn_model_create: null argument");

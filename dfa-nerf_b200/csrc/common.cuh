@@ -40,6 +40,12 @@ void reset_launch_count();
 static inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 
 int num_sms();
+// profiling hook (api.cu): returns false when disabled
+bool profile_begin(cudaStream_t st, double macs);
+void profile_end(cudaStream_t st);
+
+// exact 2^k (exp2f is not guaranteed exact); the reference's frequency bands are exact powers of two
+__device__ __forceinline__ float pow2i(int k) { return __int_as_float((127 + k) << 23); }
 
 int launch_raw2outputs(int R, int S, const float* raw, const float* z_vals, const float* rays_d,
                        const float* bc_rgb, int raw_is_feat, int white_bkgd, float last_dist, float* rgb_map,

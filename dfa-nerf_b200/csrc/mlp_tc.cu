@@ -511,7 +511,7 @@ __global__ void view_bias_kernel(int64_t R, int Wh, int ncol, int L, const float
         v = viewdirs[r * 3 + j];
       } else {
         const int k = (j - 3) / 6, q = (j - 3) % 6;
-        const float a = __fmul_rn(viewdirs[r * 3 + (q % 3)], exp2f((float)k));
+        const float a = __fmul_rn(viewdirs[r * 3 + (q % 3)], pow2i(k));
         v = q < 3 ? sinf(a) : cosf(a);
       }
       pe[j] = v;
@@ -788,6 +788,15 @@ int tc_query_points(const dfn_model* m, int64_t R, int S, const float* rays_o, c
   for (int i = 0; i < m->prog.n_layers; ++i) P.layers[i] = m->prog.layers[i];
 
   const int grid = P.n_tiles < num_sms() ? P.n_tiles : num_sms();
+  // algorithmic MACs per point with the latent / view-direction columns folded into biases
+  double macs_pt = 0.0;
+  for (int i = 0; i < d.D; ++i) {
+    const bool has_in = (i == 0) || (i - 1 == d.skip);
+    macs_pt += (double)d.W * ((i == 0 ? 0 : d.W) + (has_in ? d.input_ch : 0));
+  }
+  macs_pt += (double)d.W * Wh + d.W;                       // views_linears.0 (+ composed feature) and alpha
+  macs_pt += (double)(m->n_views - 1) * Wh * Wh + 3.0 * Wh;  // remaining view layers and rgb
+  const bool prof = profile_begin(st, macs_pt * (double)P.n_points);
   if (precision == DFN_PREC_BF16) {
     static bool attr_done = false;
     if (!attr_done) {
@@ -806,6 +815,7 @@ int tc_query_points(const dfn_model* m, int64_t R, int S, const float* rays_o, c
     set_error("tc_query_points: precision %d is not a tensor-core mode", precision);
     return DFN_E_ARG;
   }
+  if (prof) profile_end(st);
   DFN_LAUNCH_CHECK();
   return 0;
 }

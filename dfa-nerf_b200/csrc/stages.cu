@@ -106,13 +106,13 @@ __global__ void embed_kernel(int64_t P, const float* __restrict__ x, int L, int 
         v = x[p * 3 + j];
       } else {
         int k = (j - 3) / 6, r = (j - 3) % 6;
-        float a = __fmul_rn(x[p * 3 + (r % 3)], exp2f((float)k));
+        float a = __fmul_rn(x[p * 3 + (r % 3)], pow2i(k));
         v = r < 3 ? sinf(a) : cosf(a);
       }
     } else {
       int k = j / 6, r = j % 6;
       float ph = __fmul_rn(x[p * 3 + (r % 3)], 0.5f);
-      float a = __fmul_rn(__fmul_rn(exp2f((float)k), CUDART_PI_F), ph);
+      float a = __fmul_rn(__fmul_rn(pow2i(k), CUDART_PI_F), ph);
       v = r < 3 ? sinf(a) : cosf(a);
     }
     out[i] = v;

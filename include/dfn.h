@@ -185,6 +185,13 @@ int dfn_render_rays(const dfn_model* coarse, const dfn_model* fine, int64_t R, i
 /* Number of kernels the last dfn_render_rays / dfn_query_points call on this thread launched. */
 int dfn_last_launch_count(void);
 
+/* Measurement hook for bench.py: while enabled, every launch of the tcgen05 MLP kernel is bracketed
+ * by CUDA events on its own stream (up to 4096 launches).  dfn_profile_collect synchronises those
+ * events, returns the summed kernel time (ms), the number of launches and the algorithmic MACs they
+ * covered (constant-folded count), and resets the counters. */
+int dfn_profile_enable(int on);
+int dfn_profile_collect(double* kernel_ms, int64_t* launches, double* algorithmic_macs);
+
 #ifdef __cplusplus
 }
 #endif
