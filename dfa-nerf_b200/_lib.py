@@ -42,6 +42,8 @@ def _load():
         'dfn_last_error': (C.c_char_p, []),
         'dfn_last_launch_count': (i32, []),
         'dfn_profile_enable': (i32, [i32]),
+        'dfn_debug_trace': (i32, [vp, i32]),
+        'dfn_debug_set_impl': (i32, [i32]),
         'dfn_profile_collect': (i32, [C.POINTER(C.c_double), C.POINTER(i64), C.POINTER(C.c_double)]),
         'dfn_get_rays': (i32, [i32, i32, vp, vp, f32, f32, f32, C.POINTER(f32), vp, vp, vp, vp]),
         'dfn_z_vals': (i32, [i32, i32, vp, vp, vp, vp, vp, vp]),
@@ -73,7 +75,7 @@ def _load():
 
 
 lib = _load()
-EXPORTS = ['dfn_abi_version', 'dfn_last_error', 'dfn_last_launch_count', 'dfn_profile_enable', 'dfn_profile_collect', 'dfn_get_rays', 'dfn_z_vals', 'dfn_embed',
+EXPORTS = ['dfn_abi_version', 'dfn_last_error', 'dfn_last_launch_count', 'dfn_profile_enable', 'dfn_profile_collect', 'dfn_debug_trace', 'dfn_debug_set_impl', 'dfn_get_rays', 'dfn_z_vals', 'dfn_embed',
            'dfn_composite_fields', 'dfn_calc_volume_weights', 'dfn_raw2outputs', 'dfn_sample_pdf', 'dfn_invert_cdf',
            'dfn_sort_merge', 'dfn_model_create', 'dfn_model_destroy', 'dfn_model_num_tensors', 'dfn_model_load',
            'dfn_mlp_workspace_bytes', 'dfn_mlp_forward', 'dfn_query_workspace_bytes', 'dfn_query_points',

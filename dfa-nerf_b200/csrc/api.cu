@@ -150,6 +150,16 @@ extern "C" int dfn_abi_version(void) { return DFN_ABI_VERSION; }
 extern "C" const char* dfn_last_error(void) { return g_err; }
 extern "C" int dfn_last_launch_count(void) { return g_launches; }
 
+extern "C" int dfn_debug_set_impl(int impl) {
+  tc_set_impl(impl);
+  return 0;
+}
+
+extern "C" int dfn_debug_trace(void* dev_buffer, int tiles) {
+  tc_set_trace(dev_buffer, tiles);
+  return 0;
+}
+
 extern "C" int dfn_profile_enable(int on) {
   g_prof_on = on != 0;
   g_prof_n = 0;

@@ -25,14 +25,15 @@
 
 #include "common.cuh"
 #include "model.h"
+#include "tc_ptx.cuh"
 
 namespace dfn {
 namespace tc {
 
-static constexpr int TILE_M = 128;
 static constexpr int KB_BYTES = TILE_M * 128;      // one activation K-block: 128 rows x 64 bf16
 static constexpr int STAGE_BYTES = 128 * 128;      // one weight stage: <=128 rows x 64 bf16
 static constexpr int N_STAGES = 4;
+static constexpr int N_PAIRS = N_STAGES / 2;
 static constexpr int ARENA_BLOCKS = 2 * TC_KB_PER_TILE;
 static constexpr int SMEM_RING = ARENA_BLOCKS * KB_BYTES;
 static constexpr int SMEM_BIAS = SMEM_RING + N_STAGES * STAGE_BYTES;
@@ -55,137 +56,10 @@ struct Params {
   int n_layers;
   int multires;
   int view_w;  // W/2
+  unsigned long long* trace;  // debug: per-role clock64 records of CTA 0 (null in production)
+  int trace_tiles;            // local tiles per slot recorded
   TcLayer layers[TC_MAX_LAYERS];
 };
-
-// ------------------------------------------------------------------------------ PTX wrappers
-__device__ __forceinline__ uint32_t smem_u32(const void* p) {
-  return (uint32_t)__cvta_generic_to_shared(p);
-}
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok)
-      : "r"(bar), "r"(parity)
-      : "memory");
-  return ok;
-}
-// Bounded spin: a protocol bug must fault the launch (after ~2 s), never hang the GPU.
-__device__ __forceinline__ uint64_t globaltimer_ns() {
-  uint64_t t;
-  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-  return t;
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t spins = 0;
-  uint64_t t0 = 0;
-  while (!mbar_try_wait(bar, parity)) {
-    if ((++spins & 0x3FFu) == 0) {
-      const uint64_t t = globaltimer_ns();
-      if (t0 == 0) t0 = t;
-      else if (t - t0 > 2000000000ull) __trap();
-    }
-  }
-}
-__device__ __forceinline__ void fence_barrier_init() {
-  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void fence_proxy_async() {
-  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-}
-__device__ __forceinline__ void tcgen05_fence_before() {
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-}
-__device__ __forceinline__ void tcgen05_fence_after() {
-  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-}
-__device__ __forceinline__ void tma_bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-  asm volatile(
-      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-      "l"(src), "r"(bytes), "r"(bar)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols)
-               : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
-}
-__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
-                                          uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
-      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
-               : "memory");
-}
-__device__ __forceinline__ void tmem_ld_wait() {
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
-        "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
-        "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-      : "r"(taddr)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-      : "r"(taddr)
-      : "memory");
-}
-__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
-  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
-}
-
-// K-major, 128-byte swizzle, 8-row groups 1024 bytes apart (cute::UMMA::SmemDescriptor, version 1).
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
-  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
-}
-// kind::f16: D=f32, A=B=bf16, both K-major, M=128 (cute::UMMA::InstrDescriptor).
-__device__ __forceinline__ uint32_t make_idesc(uint32_t n) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((n >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
-}
-
-__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
-  __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
-  return *reinterpret_cast<uint32_t*>(&t);
-}
-__device__ __forceinline__ float bf16_lo_f(uint32_t p) { return __uint_as_float(p << 16); }
-__device__ __forceinline__ float bf16_hi_f(uint32_t p) { return __uint_as_float(p & 0xFFFF0000u); }
-
-// byte offset of 16-byte chunk `chunk` (0..7) of row `row` inside a swizzled K-block
-__device__ __forceinline__ uint32_t swz(uint32_t row, uint32_t chunk) {
-  return row * 128u + ((chunk ^ (row & 7u)) << 4);
-}
 
 // Writes 8 consecutive columns (one 16-byte chunk) of this thread's row.
 template <bool X3>
@@ -207,10 +81,58 @@ __device__ __forceinline__ void store_chunk(uint8_t* blk_hi, uint8_t* blk_lo, ui
   }
 }
 
+// One 32-column chunk of this thread's row: + bias, ReLU, bf16 (hi[/lo]) and four 16-byte stores into the
+// swizzled K-block.  `chunk32` = index of the 32-column chunk inside the layer output.
+template <bool X3, bool GLOBAL_BIAS>
+__device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[32], int chunk32, const float* gbias, uint32_t sbias,
+                                               uint8_t* arena_hi, uint8_t* arena_lo, uint32_t row) {
+  uint8_t* dst_hi = arena_hi + (size_t)(chunk32 >> 1) * KB_BYTES;
+  uint8_t* dst_lo = arena_lo + (size_t)(chunk32 >> 1) * KB_BYTES;
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    float b[8];
+    if (GLOBAL_BIAS) ldg_f32x8(gbias + chunk32 * 32 + g * 8, b);
+    else lds_f32x8(sbias + (uint32_t)(chunk32 * 32 + g * 8) * 4u, b);
+    const uint32_t c16 = (uint32_t)((chunk32 & 1) * 4 + g);
+    if (!X3) {
+      uint4 h;
+      h.x = add_relu_pack(v[g * 8 + 0], v[g * 8 + 1], b[0], b[1]);
+      h.y = add_relu_pack(v[g * 8 + 2], v[g * 8 + 3], b[2], b[3]);
+      h.z = add_relu_pack(v[g * 8 + 4], v[g * 8 + 5], b[4], b[5]);
+      h.w = add_relu_pack(v[g * 8 + 6], v[g * 8 + 7], b[6], b[7]);
+      *reinterpret_cast<uint4*>(dst_hi + swz(row, c16)) = h;
+    } else {
+      float o[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) o[e] = fmaxf(__uint_as_float(v[g * 8 + e]) + b[e], 0.f);
+      store_chunk<true>(dst_hi, dst_lo, row, c16, o);
+    }
+  }
+}
+
+// Accumulator columns [0, ncols) of this thread's row -> next layer's activation blocks.  The TMEM load of
+// chunk c+1 is in flight while chunk c is processed (tcgen05.wait::ld waits for all outstanding loads).
+template <bool X3, bool GLOBAL_BIAS>
+__device__ __forceinline__ void epilogue_relu(uint32_t acc, int ncols, const float* gbias, uint32_t sbias,
+                                              uint8_t* arena_hi, uint8_t* arena_lo, uint32_t row) {
+  uint32_t v0[32], v1[32];
+  const int nch = ncols >> 5;  // even
+  tmem_ld32(acc, v0);
+  for (int c = 0; c < nch; c += 2) {
+    tmem_ld_wait();
+    tmem_ld32(acc + (c + 1) * 32, v1);
+    epilogue_chunk<X3, GLOBAL_BIAS>(v0, c, gbias, sbias, arena_hi, arena_lo, row);
+    tmem_ld_wait();
+    if (c + 2 < nch) tmem_ld32(acc + (c + 2) * 32, v0);
+    epilogue_chunk<X3, GLOBAL_BIAS>(v1, c + 1, gbias, sbias, arena_hi, arena_lo, row);
+  }
+}
+
 // ------------------------------------------------------------------------------------ kernel
 // X3 = false: bf16, two tile slots (384 threads).  X3 = true: split-bf16, one slot (256 threads).
 template <bool X3>
-__global__ void __launch_bounds__(X3 ? 256 : 384, 1) mlp_tc_kernel(const __grid_constant__ Params P) {
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(X3 ? 256 : 384, 1)
+    mlp_tc_kernel(const __grid_constant__ Params P) {
   constexpr int NSLOT = X3 ? 1 : 2;
   constexpr int NPART = X3 ? 2 : 1;
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -228,7 +150,7 @@ __global__ void __launch_bounds__(X3 ? 256 : 384, 1) mlp_tc_kernel(const __grid_
   if (threadIdx.x == 0) {
     for (int i = 0; i < N_STAGES; ++i) {
       mbar_init(bar_full + 8 * i, 1);
-      mbar_init(bar_empty + 8 * i, 1);
+      mbar_init(bar_empty + 8 * i, 2);  // released by the MMA commits of both CTAs of the cluster
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(bar_acc + 8 * s, 1);
@@ -239,36 +161,53 @@ __global__ void __launch_bounds__(X3 ? 256 : 384, 1) mlp_tc_kernel(const __grid_
   if (warp == 2) tmem_alloc(smem_u32(tmem_ptr_smem), 512);
   tcgen05_fence_before();
   __syncthreads();
+  cluster_sync_all();  // both CTAs' barriers exist before any multicast copy or remote commit targets them
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
 
-  const int G = gridDim.x;
-  const int n_local = (int)blockIdx.x < P.n_tiles ? (P.n_tiles - (int)blockIdx.x + G - 1) / G : 0;
-  const int n_iter = (n_local + NSLOT - 1) / NSLOT;
+  // Cluster of two CTAs: every weight stage is fetched from L2 once and multicast into both CTAs' rings
+  // (the kernel is otherwise L2->SM bandwidth bound: each 128-point tile re-reads all 1.1 MB of weights).
+  // The two CTAs therefore walk the same (iteration, layer, slot) sequence; tile group g = (j*C + c)*NSLOT + s
+  // holds tiles 2g (rank 0) and 2g+1 (rank 1); a tile index past the end is computed on a clamped point
+  // and not stored.
+  const uint32_t crank = cluster_ctarank();
+  const int C = gridDim.x >> 1, c = (int)blockIdx.x >> 1;
+  const int n_groups = (P.n_tiles + 1) >> 1;
+  const int n_local = c * NSLOT < n_groups ? (n_groups - c * NSLOT + C * NSLOT - 1) / (C * NSLOT) * NSLOT : 0;  // slots incl. tail
+  const int n_iter = n_local / NSLOT;
+  auto group_of = [&](int j, int s) { return (j * C + c) * NSLOT + s; };
 
   if (warp == 0) {
     // ============================== weight producer (TMA) ===============================
-    if (lane == 0) {
+    {
       uint32_t cnt = 0;
       for (int j = 0; j < n_iter; ++j) {
         for (int l = 0; l < P.n_layers; ++l) {
           const TcLayer& L = P.layers[l];
           for (int s = 0; s < NSLOT; ++s) {
-            if (j * NSLOT + s >= n_local) continue;
+            if (group_of(j, s) >= n_groups) continue;
+            // One ring entry = one K-block of weights (all L.n rows x 64 K) as two [rows x 32 K] 64-byte-swizzled
+            // images in adjacent 16 KB slots, on ONE mbarrier: the issuing warp pays one barrier round trip per
+            // four MMAs instead of per two (its loop, not the tensor pipe, was the limiter).
             uint32_t off = L.woff;
+            const uint32_t bytes = (uint32_t)L.n * 64u;
             for (int kbi = 0; kbi < L.nkb; ++kbi) {
-              for (int c0 = 0; c0 < L.n; c0 += 128) {
-                const uint32_t bytes = (uint32_t)min(128, (int)L.n - c0) * 128u;
-                for (int part = 0; part < NPART; ++part) {
-                  const uint32_t slot = cnt % N_STAGES, par = (cnt / N_STAGES) & 1u;
-                  mbar_wait(bar_empty + 8 * slot, par ^ 1u);
-                  mbar_expect_tx(bar_full + 8 * slot, bytes);
-                  tma_bulk_load(sbase + SMEM_RING + slot * STAGE_BYTES, (part == 0 ? P.w_hi : P.w_lo) + off, bytes,
-                                bar_full + 8 * slot);
-                  ++cnt;
+              for (int part = 0; part < NPART; ++part) {
+                const uint32_t pair = cnt % N_PAIRS, par = (cnt / N_PAIRS) & 1u;
+                mbar_wait(bar_empty + 8 * pair, par ^ 1u);
+                if (elect_one_sync()) {
+                  mbar_expect_tx(bar_full + 8 * pair, 2u * bytes);  // both CTAs arm their own barrier ...
+                  if ((cnt & 1u) == crank) {                        // ... and take turns issuing the multicast copies
+                    const uint8_t* src = (part == 0 ? P.w_hi : P.w_lo) + off;
+                    const uint32_t dst = sbase + SMEM_RING + pair * 2u * STAGE_BYTES;
+                    tma_bulk_load_mc(dst, src, bytes, bar_full + 8 * pair, (uint16_t)3);
+                    tma_bulk_load_mc(dst + STAGE_BYTES, src + bytes, bytes, bar_full + 8 * pair, (uint16_t)3);
+                  }
                 }
-                off += bytes;
+                __syncwarp();
+                ++cnt;
               }
+              off += 2u * bytes;
             }
           }
         }
@@ -276,45 +215,59 @@ __global__ void __launch_bounds__(X3 ? 256 : 384, 1) mlp_tc_kernel(const __grid_
     }
   } else if (warp == 1) {
     // ================================= MMA issuer =========================================
-    if (lane == 0) {
+    {
       uint32_t cnt = 0;
       uint32_t apar[2] = {0u, 0u};
       for (int j = 0; j < n_iter; ++j) {
         for (int l = 0; l < P.n_layers; ++l) {
           const TcLayer& L = P.layers[l];
           for (int s = 0; s < NSLOT; ++s) {
-            if (j * NSLOT + s >= n_local) continue;
+            if (group_of(j, s) >= n_groups) continue;
+            const bool tr = P.trace != nullptr && blockIdx.x == 0 && j < P.trace_tiles;
+            long long t_w0 = 0, t_w1 = 0, t_full = 0;
+            if (tr) t_w0 = clock64();
             mbar_wait(bar_aready + 8 * s, apar[s]);
             apar[s] ^= 1u;
             tcgen05_fence_after();
+            if (tr) t_w1 = clock64();
             const uint32_t acc = tmem_base + (uint32_t)s * 256u;
+            const uint32_t idesc = make_idesc(L.n);
             for (int kbi = 0; kbi < L.nkb; ++kbi) {
               const uint32_t a_hi = sbase + (uint32_t)(s * TC_KB_PER_TILE + L.kb[kbi]) * KB_BYTES;
               const uint64_t adesc_hi = make_smem_desc(a_hi);
               const uint64_t adesc_lo = make_smem_desc(a_hi + TC_KB_PER_TILE * KB_BYTES);
-              for (int c0 = 0; c0 < L.n; c0 += 128) {
-                const uint32_t nn = (uint32_t)min(128, (int)L.n - c0);
-                const uint32_t idesc = make_idesc(nn);
-                for (int part = 0; part < NPART; ++part) {
-                  const uint32_t slot = cnt % N_STAGES, par = (cnt / N_STAGES) & 1u;
-                  mbar_wait(bar_full + 8 * slot, par);
-                  tcgen05_fence_after();
-                  const uint64_t bdesc = make_smem_desc(sbase + SMEM_RING + slot * STAGE_BYTES);
+              for (int part = 0; part < NPART; ++part) {
+                const uint32_t pair = cnt % N_PAIRS, par = (cnt / N_PAIRS) & 1u;
+                long long t_f0 = 0;
+                if (tr) t_f0 = clock64();
+                mbar_wait(bar_full + 8 * pair, par);
+                tcgen05_fence_after();
+                if (tr) t_full += clock64() - t_f0;
+                const uint64_t bdesc = make_smem_desc_sw64(sbase + SMEM_RING + pair * 2u * STAGE_BYTES);
 #pragma unroll
-                  for (int ks = 0; ks < 4; ++ks) {
-                    umma_bf16(acc + c0, adesc_hi + 2 * ks, bdesc + 2 * ks, idesc,
-                              (kbi | part | ks) != 0 ? 1u : 0u);
-                  }
-                  if (X3 && part == 0) {
-#pragma unroll
-                    for (int ks = 0; ks < 4; ++ks) umma_bf16(acc + c0, adesc_lo + 2 * ks, bdesc + 2 * ks, idesc, 1u);
-                  }
-                  umma_commit(bar_empty + 8 * slot);
-                  ++cnt;
+                for (int q = 0; q < 4; ++q) {  // q = 2*kh + ks: A advances 32 bytes per K-step, B 32 bytes inside a 16 KB image
+                  const uint64_t bd = bdesc + (uint64_t)((q >> 1) * (STAGE_BYTES >> 4) + (q & 1) * 2);
+                  umma_bf16(acc, adesc_hi + 2 * q, bd, idesc, (kbi | part | q) != 0 ? 1u : 0u);
                 }
+                if (X3 && part == 0) {
+#pragma unroll
+                  for (int q = 0; q < 4; ++q) {
+                    const uint64_t bd = bdesc + (uint64_t)((q >> 1) * (STAGE_BYTES >> 4) + (q & 1) * 2);
+                    umma_bf16(acc, adesc_lo + 2 * q, bd, idesc, 1u);
+                  }
+                }
+                umma_commit_mc(bar_empty + 8 * pair, (uint16_t)3);
+                ++cnt;
               }
             }
             umma_commit(bar_acc + 8 * s);
+            if (tr && lane == 0) {
+              unsigned long long* r = P.trace + ((size_t)(j * P.n_layers + l) * 2 + s) * 4;
+              r[0] = (unsigned long long)t_w0;
+              r[1] = (unsigned long long)t_w1;
+              r[2] = (unsigned long long)clock64();
+              r[3] = (unsigned long long)t_full;
+            }
           }
         }
       }
@@ -330,8 +283,11 @@ __global__ void __launch_bounds__(X3 ? 256 : 384, 1) mlp_tc_kernel(const __grid_
     const uint32_t acc = tmem_base + (uint32_t)s * 256u + ((uint32_t)((warp & 3) * 32) << 16);
     uint32_t acc_par = 0u;
 
-    for (int i = s; i < n_local; i += NSLOT) {
-      const int tile = (int)blockIdx.x + i * G;
+    for (int j = 0; j < n_iter; ++j) {
+      if (group_of(j, s) >= n_groups) break;
+      const int i = j * NSLOT + s;
+      const int tile = 2 * group_of(j, s) + (int)crank;
+      const long long t_tile0 = clock64();
       int64_t pt = (int64_t)tile * TILE_M + row;
       const bool valid = pt < P.n_points;
       if (!valid) pt = P.n_points - 1;
@@ -384,9 +340,13 @@ __global__ void __launch_bounds__(X3 ? 256 : 384, 1) mlp_tc_kernel(const __grid_
         float2 nb = make_float2(0.f, 0.f);
         if (l + 1 < P.n_layers) nb = reinterpret_cast<const float2*>(P.bias + (l + 1) * TC_BIAS_STRIDE)[tid_s];
 
+        const bool tr = P.trace != nullptr && blockIdx.x == 0 && tid_s == 0 && (i / NSLOT) < P.trace_tiles;
+        long long t_e0 = 0, t_e1 = 0;
+        if (tr) t_e0 = clock64();
         mbar_wait(bar_acc + 8 * s, acc_par);
         acc_par ^= 1u;
         tcgen05_fence_after();
+        if (tr) t_e1 = clock64();
 
         if (L.epi == TC_EPI_RGB) {
           uint32_t v[16];
@@ -402,48 +362,10 @@ __global__ void __launch_bounds__(X3 ? 256 : 384, 1) mlp_tc_kernel(const __grid_
           }
           tcgen05_fence_before();
         } else {
-          const bool per_ray = L.epi == TC_EPI_VIEW0;
-          const int n_relu = per_ray ? P.view_w : (int)L.n;
-          const float* rb = P.view_bias + ray * P.view_w;  // per-ray bias (TC_EPI_VIEW0 only)
-          for (int blk = 0; blk < n_relu / 64; ++blk) {
-            uint32_t va[32], vb[32];
-            tmem_ld32(acc + blk * 64, va);
-            tmem_ld32(acc + blk * 64 + 32, vb);
-            uint8_t* dst_hi = arena_hi + (size_t)blk * KB_BYTES;
-            uint8_t* dst_lo = arena_lo + (size_t)blk * KB_BYTES;
-            const float* bsrc = per_ray ? rb + blk * 64 : bias_s + blk * 64;
-#pragma unroll
-            for (int half = 0; half < 2; ++half) {
-              float4 pb[8];
-              if (per_ray) {
-#pragma unroll
-                for (int q = 0; q < 8; ++q) pb[q] = __ldg(reinterpret_cast<const float4*>(bsrc + half * 32) + q);
-              }
-              if (half == 0) tmem_ld_wait();
-#pragma unroll
-              for (int g = 0; g < 4; ++g) {
-                float4 b0, b1;
-                if (per_ray) {
-                  b0 = pb[2 * g];
-                  b1 = pb[2 * g + 1];
-                } else {
-                  b0 = reinterpret_cast<const float4*>(bsrc + half * 32)[2 * g];
-                  b1 = reinterpret_cast<const float4*>(bsrc + half * 32)[2 * g + 1];
-                }
-                const uint32_t* vv = half == 0 ? va : vb;
-                float o[8];
-                o[0] = fmaxf(__uint_as_float(vv[g * 8 + 0]) + b0.x, 0.f);
-                o[1] = fmaxf(__uint_as_float(vv[g * 8 + 1]) + b0.y, 0.f);
-                o[2] = fmaxf(__uint_as_float(vv[g * 8 + 2]) + b0.z, 0.f);
-                o[3] = fmaxf(__uint_as_float(vv[g * 8 + 3]) + b0.w, 0.f);
-                o[4] = fmaxf(__uint_as_float(vv[g * 8 + 4]) + b1.x, 0.f);
-                o[5] = fmaxf(__uint_as_float(vv[g * 8 + 5]) + b1.y, 0.f);
-                o[6] = fmaxf(__uint_as_float(vv[g * 8 + 6]) + b1.z, 0.f);
-                o[7] = fmaxf(__uint_as_float(vv[g * 8 + 7]) + b1.w, 0.f);
-                store_chunk<X3>(dst_hi, dst_lo, row, (uint32_t)(half * 4 + g), o);
-              }
-            }
-          }
+          if (L.epi == TC_EPI_VIEW0)
+            epilogue_relu<X3, true>(acc, P.view_w, P.view_bias + ray * P.view_w, 0u, arena_hi, arena_lo, row);
+          else
+            epilogue_relu<X3, false>(acc, (int)L.n, nullptr, smem_u32(bias_s), arena_hi, arena_lo, row);
           if (L.epi == TC_EPI_VIEW0) {
             uint32_t v[16];
             tmem_ld16(acc + P.view_w, v);
@@ -453,6 +375,14 @@ __global__ void __launch_bounds__(X3 ? 256 : 384, 1) mlp_tc_kernel(const __grid_
           tcgen05_fence_before();
           fence_proxy_async();
           mbar_arrive(bar_aready + 8 * s);
+        }
+        if (tr) {
+          unsigned long long* r = P.trace + (size_t)P.trace_tiles * P.n_layers * 8 +
+                                  ((size_t)((i / NSLOT) * P.n_layers + l) * 2 + s) * 4;
+          r[0] = (unsigned long long)t_e0;
+          r[1] = (unsigned long long)t_e1;
+          r[2] = (unsigned long long)clock64();
+          r[3] = (unsigned long long)t_tile0;
         }
         // swap in the next layer's bias
         if (l + 1 < P.n_layers) {
@@ -467,6 +397,7 @@ __global__ void __launch_bounds__(X3 ? 256 : 384, 1) mlp_tc_kernel(const __grid_
 
   tcgen05_fence_before();
   __syncthreads();
+  cluster_sync_all();  // the peer may still multicast into this CTA's ring / arrive on its barriers until it is done
   tcgen05_fence_after();
   if (warp == 2) tmem_dealloc(tmem_base, 512);
 }
@@ -542,7 +473,9 @@ static inline float bf2f(uint16_t h) {
 }
 
 struct Packer {
-  std::vector<uint8_t> hi, lo;
+  std::vector<uint8_t> hi, lo;       // [<=128 rows x 64 K] stages, 128-byte swizzle (mlp_ts.cu)
+  std::vector<uint8_t> hi32, lo32;   // [n rows x 32 K] stages, 64-byte swizzle (mlp_tc.cu)
+  uint32_t last32 = 0;               // offset of the last layer added to hi32
   // Appends the stages of one layer: for each K-block, for each chunk of <=128 output rows, a
   // [rows x 64] bf16 image in the swizzled K-major layout.  wfun(n, kbi, k) returns W[n][column
   // of K-block kbi, position k] or 0.
@@ -567,13 +500,38 @@ struct Packer {
         }
       }
     }
+    // K = 32 stages: for each K-block, for each half of it, all n_out rows x 32 K; 64-byte rows, 16-byte
+    // chunk index XORed with (row >> 1) & 3 (cute Swizzle<2,4,3>), 8-row groups 512 bytes apart.
+    last32 = (uint32_t)hi32.size();
+    for (int kbi = 0; kbi < nkb; ++kbi) {
+      for (int kh = 0; kh < 2; ++kh) {
+        const size_t base = hi32.size();
+        hi32.resize(base + (size_t)n_out * 64, 0);
+        lo32.resize(base + (size_t)n_out * 64, 0);
+        for (int r = 0; r < n_out; ++r) {
+          for (int k = 0; k < 32; ++k) {
+            const float w = wfun(r, kbi, kh * 32 + k);
+            const uint16_t h = f2bf(w);
+            const uint16_t l = f2bf(w - bf2f(h));
+            const size_t o = base + (size_t)r * 64 + ((((size_t)k >> 3) ^ (((size_t)r >> 1) & 3)) << 4) + ((size_t)k & 7) * 2;
+            memcpy(&hi32[o], &h, 2);
+            memcpy(&lo32[o], &l, 2);
+          }
+        }
+      }
+    }
     return start;
   }
 };
 
 }  // namespace tc
 
+int ts_pack_from_tc(dfn_model* m, const std::vector<uint8_t>& hi, const std::vector<uint8_t>& lo, cudaStream_t st);
+
 void tc_free_model(dfn_model* m) {
+  cudaFree(m->ts_hi);
+  cudaFree(m->ts_lo);
+  m->ts_hi = m->ts_lo = nullptr;
   cudaFree(m->tc_hi);
   cudaFree(m->tc_lo);
   cudaFree(m->tc_bias);
@@ -635,6 +593,7 @@ int tc_pack_model(dfn_model* m, const float* const* t, cudaStream_t st) {
           fold_w[((size_t)nfold * W + n) * d.dim_aud + j] = w[(size_t)n * ld + d.input_ch + j];
       pg.fold_layer[nfold++] = nl;
     }
+    m->tc32_woff[nl] = pk.last32;
     pg.layers[nl++] = L;
   }
   // views_linears.0 (+ alpha_linear as output row Wh).  NeRF applies feature_linear first
@@ -678,6 +637,7 @@ int tc_pack_model(dfn_model* m, const float* const* t, cudaStream_t st) {
       return 0.f;
     });
     bias[(size_t)nl * TC_BIAS_STRIDE + Wh] = Bt(i_alpha)[0];
+    m->tc32_woff[nl] = pk.last32;
     pg.layers[nl++] = L;
     // view-direction columns + composed bias for view_bias_kernel
     std::vector<float> vw((size_t)Wh * d.input_ch_views);
@@ -700,6 +660,7 @@ int tc_pack_model(dfn_model* m, const float* const* t, cudaStream_t st) {
     const float* w = Wt(i_views0 + i);
     L.woff = pk.add_layer(Wh, 2, [&](int n, int kbi, int k) -> float { return w[(size_t)n * Wh + kbi * 64 + k]; });
     for (int n = 0; n < Wh; ++n) bias[(size_t)nl * TC_BIAS_STRIDE + n] = Bt(i_views0 + i)[n];
+    m->tc32_woff[nl] = pk.last32;
     pg.layers[nl++] = L;
   }
   {
@@ -713,24 +674,39 @@ int tc_pack_model(dfn_model* m, const float* const* t, cudaStream_t st) {
     const float* w = Wt(i_rgb);
     L.woff = pk.add_layer(16, 2, [&](int n, int kbi, int k) -> float { return n < 3 ? w[(size_t)n * Wh + kbi * 64 + k] : 0.f; });
     for (int n = 0; n < 3; ++n) bias[(size_t)nl * TC_BIAS_STRIDE + n] = Bt(i_rgb)[n];
+    m->tc32_woff[nl] = pk.last32;
     pg.layers[nl++] = L;
   }
   pg.n_layers = nl;
-
-  m->tc_blob_bytes = (int64_t)pk.hi.size();
-  DFN_CUDA(cudaMalloc(&m->tc_hi, pk.hi.size()));
-  DFN_CUDA(cudaMalloc(&m->tc_lo, pk.lo.size()));
+  m->tc_blob_bytes = (int64_t)pk.hi32.size();
+  DFN_CUDA(cudaMalloc(&m->tc_hi, pk.hi32.size()));
+  DFN_CUDA(cudaMalloc(&m->tc_lo, pk.lo32.size()));
   DFN_CUDA(cudaMalloc(&m->tc_bias, bias.size() * 4));
   DFN_CUDA(cudaMalloc(&m->tc_fold_w, fold_w.size() * 4));
-  DFN_CUDA(cudaMemcpyAsync(m->tc_hi, pk.hi.data(), pk.hi.size(), cudaMemcpyHostToDevice, st));
-  DFN_CUDA(cudaMemcpyAsync(m->tc_lo, pk.lo.data(), pk.lo.size(), cudaMemcpyHostToDevice, st));
+  DFN_CUDA(cudaMemcpyAsync(m->tc_hi, pk.hi32.data(), pk.hi32.size(), cudaMemcpyHostToDevice, st));
+  DFN_CUDA(cudaMemcpyAsync(m->tc_lo, pk.lo32.data(), pk.lo32.size(), cudaMemcpyHostToDevice, st));
   DFN_CUDA(cudaMemcpyAsync(m->tc_bias, bias.data(), bias.size() * 4, cudaMemcpyHostToDevice, st));
   DFN_CUDA(cudaMemcpyAsync(m->tc_fold_w, fold_w.data(), fold_w.size() * 4, cudaMemcpyHostToDevice, st));
   DFN_CUDA(cudaStreamSynchronize(st));
-  return 0;
+  return ts_pack_from_tc(m, pk.hi, pk.lo, st);
 }
 
 static inline int64_t align256(int64_t x) { return (x + 255) / 256 * 256; }
+
+// debug timeline hook (dfn_debug_trace): device buffer of 2 * trace_tiles * n_layers * 8 uint64
+static int g_impl = 1;  // 1: activations in shared memory, two tiles in flight (fastest so far); 0: TMEM activations
+void tc_set_impl(int impl) { g_impl = impl; }
+static void* g_trace_ptr = nullptr;
+static int g_trace_tiles = 0;
+void tc_set_trace(void* dev_ptr, int tiles) {
+  g_trace_ptr = dev_ptr;
+  g_trace_tiles = dev_ptr ? tiles : 0;
+}
+
+void tc_get_trace(void** dev_ptr, int* tiles) {
+  *dev_ptr = g_trace_ptr;
+  *tiles = g_trace_tiles;
+}
 
 int64_t tc_query_workspace_bytes(const dfn_model* m, int64_t R, int S) {
   (void)S;
@@ -785,9 +761,15 @@ int tc_query_points(const dfn_model* m, int64_t R, int S, const float* rays_o, c
   P.n_layers = m->prog.n_layers;
   P.multires = d.multires;
   P.view_w = Wh;
-  for (int i = 0; i < m->prog.n_layers; ++i) P.layers[i] = m->prog.layers[i];
+  P.trace = reinterpret_cast<unsigned long long*>(g_trace_ptr);
+  P.trace_tiles = g_trace_tiles;
+  for (int i = 0; i < m->prog.n_layers; ++i) {
+    P.layers[i] = m->prog.layers[i];
+    P.layers[i].woff = m->tc32_woff[i];
+  }
 
-  const int grid = P.n_tiles < num_sms() ? P.n_tiles : num_sms();
+  int grid = P.n_tiles < num_sms() ? P.n_tiles : num_sms();
+  grid = (grid + 1) & ~1;  // clusters of two CTAs
   // algorithmic MACs per point with the latent / view-direction columns folded into biases
   double macs_pt = 0.0;
   for (int i = 0; i < d.D; ++i) {
@@ -797,7 +779,10 @@ int tc_query_points(const dfn_model* m, int64_t R, int S, const float* rays_o, c
   macs_pt += (double)d.W * Wh + d.W;                       // views_linears.0 (+ composed feature) and alpha
   macs_pt += (double)(m->n_views - 1) * Wh * Wh + 3.0 * Wh;  // remaining view layers and rgb
   const bool prof = profile_begin(st, macs_pt * (double)P.n_points);
-  if (precision == DFN_PREC_BF16) {
+  if (g_impl == 0 && (precision == DFN_PREC_BF16 || precision == DFN_PREC_BF16X3)) {
+    int rc = ts_launch(m, bias_ws, vbias_ws, R, S, rays_o, rays_d, z_vals, raw, precision, st);
+    if (rc) return rc;
+  } else if (precision == DFN_PREC_BF16) {
     static bool attr_done = false;
     if (!attr_done) {
       DFN_CUDA(cudaFuncSetAttribute(tc::mlp_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_TOTAL));

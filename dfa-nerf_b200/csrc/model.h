@@ -50,6 +50,7 @@ struct dfn_model {
   dfn::Fp32Layer feature, alpha, rgb;
   // tcgen05 path
   dfn::TcProgram prog;
+  uint32_t tc32_woff[dfn::TC_MAX_LAYERS] = {};  // per-layer offsets into tc_hi / tc_lo
   uint8_t* tc_hi = nullptr;     // packed bf16 (hi) weight stages
   uint8_t* tc_lo = nullptr;     // packed bf16 (lo = bf16(w - hi)) weight stages, same offsets
   int64_t tc_blob_bytes = 0;
@@ -57,6 +58,10 @@ struct dfn_model {
   float* tc_fold_w = nullptr;   // [2][W][dim_aud] latent columns of the two folding layers
   float* tc_view_w = nullptr;   // [W/2][input_ch_views] view-direction columns of views_linears.0
   float* tc_view_b = nullptr;   // [W/2] its (composed) bias
+  // TMEM-activation kernel (mlp_ts.cu): the same stage images in half-major order
+  uint8_t* ts_hi = nullptr;
+  uint8_t* ts_lo = nullptr;
+  uint32_t ts_woff[dfn::TC_MAX_LAYERS] = {};
 };
 
 namespace dfn {
@@ -64,6 +69,11 @@ int64_t mlp_fp32_workspace_bytes(const dfn_model* m, int64_t P);
 int mlp_fp32_forward(const dfn_model* m, int64_t P, const float* x, float* out, void* workspace,
                      int64_t workspace_bytes, cudaStream_t st);
 
+void tc_set_trace(void* dev_ptr, int tiles);
+void tc_get_trace(void** dev_ptr, int* tiles);
+void tc_set_impl(int impl);  // 0: activations in TMEM (mlp_ts.cu, default); 1: activations in shared memory (mlp_tc.cu)
+int ts_launch(const dfn_model* m, const float* bias_ws, const float* vbias_ws, int64_t R, int S, const float* rays_o,
+              const float* rays_d, const float* z_vals, float* raw, int precision, cudaStream_t st);
 int tc_pack_model(dfn_model* m, const float* const* t, cudaStream_t st);
 void tc_free_model(dfn_model* m);
 int64_t tc_query_workspace_bytes(const dfn_model* m, int64_t R, int S);

@@ -190,6 +190,15 @@ int dfn_last_launch_count(void);
  * events, returns the summed kernel time (ms), the number of launches and the algorithmic MACs they
  * covered (constant-folded count), and resets the counters. */
 int dfn_profile_enable(int on);
+
+/* Debug timeline of the tcgen05 kernel: while dev_buffer is non-null, CTA 0 records clock64 stamps for its
+ * first `tiles` tile iterations: [MMA issuer | epilogue] x [tile][layer][slot] x {wait begin, wait end,
+ * done, aux} (uint64 each; 2*tiles*14*2*4 entries at most).  Pass null to switch it off. */
+int dfn_debug_trace(void* dev_buffer, int tiles);
+
+/* Selects the tcgen05 kernel generation: 1 (default) activations in shared memory, two tiles in flight
+ * (mlp_tc.cu); 0 activations in tensor memory, one tile in flight (mlp_ts.cu; kept for A/B measurements). */
+int dfn_debug_set_impl(int impl);
 int dfn_profile_collect(double* kernel_ms, int64_t* launches, double* algorithmic_macs);
 
 #ifdef __cplusplus

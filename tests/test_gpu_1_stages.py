@@ -169,8 +169,10 @@ def check_against_plain_oracle(s, i, ref_s, ref_i):
     bad_i = i != ref_i
     bad_s = (s - ref_s).abs() > 1e-6
     assert bad_i.float().mean().item() < 0.01 and bad_s.float().mean().item() < 0.01
-    # interior samples that keep their index agree to rounding
-    assert ((s - ref_s).abs()[~bad_i]).max().item() < 1e-6
+    # samples that keep their index agree to the conditioning of the lerp: a 1-ulp cdf difference moves the
+    # sample by at most ulp/denom * bin width with denom >= 1e-5 (HELP:577) -> 6e-8/1e-5 * 0.0095 = 6e-5
+    assert ((s - ref_s).abs()[~bad_i]).max().item() < 1e-4
+    assert ((s - ref_s).abs()[~bad_i]).median().item() < 1e-7
 
 
 def test_sample_pdf_large(dfn):
