@@ -1,0 +1,587 @@
+// tcgen05 path, third generation ("pp"): ping-pong tiles with a cooperative epilogue.
+//
+// What the timelines of mlp_tc.cu showed (profiles/): with two 128-point tiles in flight the tensor pipe
+// waited on (1) the epilogue, 3.2k cycles per 256-wide layer when only the four warps of one tile work on
+// it, and (2) the single MMA-issuing warp's barrier round trips.  This kernel keeps the same data layout
+// (activations as 128-byte-swizzled K-major blocks in shared memory, accumulators in TMEM, weights
+// multicast to a 2-CTA cluster) and changes the schedule:
+//   * ALL EIGHT epilogue warps drain whichever tile's accumulator is ready (two warps per TMEM lane
+//     quarter, each thread owns half of the row's columns), so a layer's epilogue takes half as long and
+//     two warps per scheduler hide each other's TMEM / shared-memory latency;
+//   * one ring entry = one K-block of weights on one mbarrier (four MMAs per barrier round trip);
+//   * the positional-encoding K-block no longer owns shared memory for the whole tile: four dedicated warps
+//     compute PE rows one iteration ahead into an L2-resident scratch buffer, and the epilogue warps copy a
+//     tile's PE block into a *ring entry* right before the two layers that consume it (layer 0 and the skip
+//     layer).  The 32 KB this frees makes the weight ring three entries (96 KB) deep.
+// bf16x3 (A_hi*W_hi + A_lo*W_hi + A_hi*W_lo) runs one tile with hi/lo activation planes in the same arena.
+//
+// Warp roles (512 threads): 0 weight producer (TMA multicast), 1 MMA issuer, 2 TMEM allocator,
+// 4-11 epilogue, 12-15 positional encoding.
+// Reference arithmetic: HELP:21-52 (Embedder), HELP:275-299 (FaceNeRF.forward), HELP:372-396 (NeRF.forward).
+#include <string.h>
+
+#include <vector>
+
+#include "common.cuh"
+#include "model.h"
+#include "tc_ptx.cuh"
+
+namespace dfn {
+namespace pp {
+
+using namespace dfn::tc;
+
+static constexpr int KB_BYTES = TILE_M * 128;   // activation K-block [128 x 64] bf16
+static constexpr int SLOT_BYTES = 16384;        // half a ring entry
+static constexpr int N_ENTRIES = 3;             // ring entries (2 x 16 KB each)
+static constexpr int ARENA_BLOCKS = 8;          // bf16: 2 tiles x 4 blocks; bf16x3: hi 4 + lo 4
+static constexpr int SMEM_RING = ARENA_BLOCKS * KB_BYTES;
+static constexpr int SMEM_BIAS = SMEM_RING + N_ENTRIES * 2 * SLOT_BYTES;
+static constexpr int SMEM_BAR = SMEM_BIAS + 2 * TC_BIAS_STRIDE * 4;
+static constexpr int SMEM_TOTAL = SMEM_BAR + 256;
+static_assert(SMEM_TOTAL <= 227 * 1024, "shared memory budget");
+static constexpr int EPI_THREADS = 256;
+static constexpr int PE_THREADS = 128;
+
+struct Params {
+  const uint8_t* w_hi;
+  const uint8_t* w_lo;
+  const float* bias;       // [n_layers][256], latent already folded
+  const float* view_bias;  // [R][W/2]
+  const float* rays_o;
+  const float* rays_d;
+  const float* z_vals;
+  float* raw;
+  uint8_t* pe_scratch;     // [grid][2 buffers][2 slots][128 rows][row_bytes]
+  unsigned long long* trace;
+  int trace_tiles;
+  int64_t n_points;
+  int S;
+  int n_tiles;
+  int n_layers;
+  int multires;
+  int view_w;
+  TcLayer layers[TC_MAX_LAYERS];  // woff: offsets into the K=32 / 64-byte-swizzle blobs
+};
+
+__device__ __forceinline__ bool layer_has_pe(const TcLayer& L) {
+  for (int k = 0; k < L.nkb; ++k)
+    if (L.kb[k] == TC_KB_PE) return true;
+  return false;
+}
+template <int NPART>
+__device__ __forceinline__ uint32_t layer_entries(const TcLayer& L) {
+  return (uint32_t)L.nkb * NPART + (layer_has_pe(L) ? 1u : 0u);
+}
+
+// + bias, ReLU, bf16 (hi[/lo]) of one 32-column chunk -> four 16-byte stores into the swizzled K-block.
+template <bool X3, bool GLOBAL_BIAS>
+__device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[32], int chunk32, const float* gbias, uint32_t sbias,
+                                               uint8_t* arena_hi, uint8_t* arena_lo, uint32_t row) {
+  uint8_t* dst_hi = arena_hi + (size_t)(chunk32 >> 1) * KB_BYTES;
+  uint8_t* dst_lo = arena_lo + (size_t)(chunk32 >> 1) * KB_BYTES;
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    float b[8];
+    if (GLOBAL_BIAS) ldg_f32x8(gbias + chunk32 * 32 + g * 8, b);
+    else lds_f32x8(sbias + (uint32_t)(chunk32 * 32 + g * 8) * 4u, b);
+    const uint32_t c16 = (uint32_t)((chunk32 & 1) * 4 + g);
+    uint4 h;
+    if (!X3) {
+      h.x = add_relu_pack(v[g * 8 + 0], v[g * 8 + 1], b[0], b[1]);
+      h.y = add_relu_pack(v[g * 8 + 2], v[g * 8 + 3], b[2], b[3]);
+      h.z = add_relu_pack(v[g * 8 + 4], v[g * 8 + 5], b[4], b[5]);
+      h.w = add_relu_pack(v[g * 8 + 6], v[g * 8 + 7], b[6], b[7]);
+      *reinterpret_cast<uint4*>(dst_hi + swz(row, c16)) = h;
+    } else {
+      float o[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) o[e] = fmaxf(__uint_as_float(v[g * 8 + e]) + b[e], 0.f);
+      h.x = pack_bf16(o[0], o[1]);
+      h.y = pack_bf16(o[2], o[3]);
+      h.z = pack_bf16(o[4], o[5]);
+      h.w = pack_bf16(o[6], o[7]);
+      *reinterpret_cast<uint4*>(dst_hi + swz(row, c16)) = h;
+      uint4 l;
+      l.x = pack_bf16(o[0] - bf16_lo_f(h.x), o[1] - bf16_hi_f(h.x));
+      l.y = pack_bf16(o[2] - bf16_lo_f(h.y), o[3] - bf16_hi_f(h.y));
+      l.z = pack_bf16(o[4] - bf16_lo_f(h.z), o[5] - bf16_hi_f(h.z));
+      l.w = pack_bf16(o[6] - bf16_lo_f(h.w), o[7] - bf16_hi_f(h.w));
+      *reinterpret_cast<uint4*>(dst_lo + swz(row, c16)) = l;
+    }
+  }
+}
+
+// X3 = false: bf16, two tile slots.  X3 = true: split-bf16, one slot.
+template <bool X3>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(512, 1) mlp_pp_kernel(const __grid_constant__ Params P) {
+  constexpr int NSLOT = X3 ? 1 : 2;
+  constexpr int NPART = X3 ? 2 : 1;
+  constexpr int ROWB = X3 ? 256 : 128;  // scratch bytes per PE row
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const uint32_t sbase = smem_u32(smem);
+  if ((sbase & 1023u) != 0) __trap();
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t bar0 = sbase + SMEM_BAR;
+  const uint32_t bar_full = bar0;                 // [3]  ring entry filled (TMA bytes, or the PE copy)
+  const uint32_t bar_empty = bar0 + 8 * 4;        // [3]  ring entry consumed by both CTAs' MMAs
+  const uint32_t bar_acc = bar0 + 8 * 8;          // [2]  accumulator of slot s complete
+  const uint32_t bar_aready = bar0 + 8 * 10;      // [2]  activations of slot s written, accumulator drained
+  const uint32_t bar_pe_ready = bar0 + 8 * 12;    // [2]  scratch buffer b holds the PE rows of its iteration
+  const uint32_t bar_pe_free = bar0 + 8 * 14;     // [2]  scratch buffer b no longer needed
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + SMEM_BAR + 8 * 16);
+  float* bias_s = reinterpret_cast<float*>(smem + SMEM_BIAS);  // [2][256]
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < N_ENTRIES; ++i) {
+      mbar_init(bar_full + 8 * i, 1);
+      mbar_init(bar_empty + 8 * i, 2);  // MMA commits of both CTAs of the cluster
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(bar_acc + 8 * s, 1);
+      mbar_init(bar_aready + 8 * s, EPI_THREADS);
+      mbar_init(bar_pe_ready + 8 * s, PE_THREADS);
+      mbar_init(bar_pe_free + 8 * s, EPI_THREADS);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(smem_u32(tmem_ptr_smem), 512);
+  tcgen05_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  // tile group g = (j*C + c)*NSLOT + s holds tiles 2g (cluster rank 0) and 2g+1 (rank 1); both CTAs of a
+  // cluster walk the same (j, layer, slot) sequence because they share every multicast weight entry.
+  const uint32_t crank = cluster_ctarank();
+  const int C = gridDim.x >> 1, c = (int)blockIdx.x >> 1;
+  const int n_groups = (P.n_tiles + 1) >> 1;
+  const int n_iter = c * NSLOT < n_groups ? (n_groups - c * NSLOT + C * NSLOT - 1) / (C * NSLOT) : 0;
+  auto valid_slot = [&](int j, int s) { return (j * C + c) * NSLOT + s < n_groups; };
+  auto tile_of = [&](int j, int s) { return 2 * ((j * C + c) * NSLOT + s) + (int)crank; };
+  const int NL = P.n_layers;
+  uint8_t* scratch = P.pe_scratch + (size_t)blockIdx.x * 2 * 2 * TILE_M * ROWB;
+
+  if (warp == 0) {
+    // ============================== weight producer (TMA multicast) ==========================
+    uint32_t cnt = 0;
+    for (int j = 0; j < n_iter; ++j) {
+      for (int l = 0; l < NL; ++l) {
+        const TcLayer& L = P.layers[l];
+        for (int s = 0; s < NSLOT; ++s) {
+          if (!valid_slot(j, s)) continue;
+          uint32_t off = L.woff;
+          const uint32_t bytes = (uint32_t)L.n * 64u;
+          for (int kbi = 0; kbi < L.nkb; ++kbi) {
+            if (L.kb[kbi] == TC_KB_PE) ++cnt;  // the entry before this K-block's weights is filled by the epilogue warps
+            for (int part = 0; part < NPART; ++part) {
+              const uint32_t e = cnt % N_ENTRIES, par = (cnt / N_ENTRIES) & 1u;
+              mbar_wait(bar_empty + 8 * e, par ^ 1u);
+              if (elect_one_sync()) {
+                mbar_expect_tx(bar_full + 8 * e, 2u * bytes);
+                if ((cnt & 1u) == crank) {
+                  const uint8_t* src = (part == 0 ? P.w_hi : P.w_lo) + off;
+                  const uint32_t dst = sbase + SMEM_RING + e * 2u * SLOT_BYTES;
+                  tma_bulk_load_mc(dst, src, bytes, bar_full + 8 * e, (uint16_t)3);
+                  tma_bulk_load_mc(dst + SLOT_BYTES, src + bytes, bytes, bar_full + 8 * e, (uint16_t)3);
+                }
+              }
+              __syncwarp();
+              ++cnt;
+            }
+            off += 2u * bytes;
+          }
+        }
+      }
+    }
+    // tail: the peer CTA's last commits still target this CTA's barriers; do not run to the exit (and let the
+    // cluster retire) before every entry's final release, which needs both CTAs' arrivals, has landed here
+    for (uint32_t k = 0; k < (uint32_t)N_ENTRIES && k < cnt; ++k) {
+      const uint32_t u = cnt - 1u - k;
+      mbar_wait(bar_empty + 8 * (u % N_ENTRIES), (u / N_ENTRIES) & 1u);
+    }
+  } else if (warp == 1) {
+    // ================================= MMA issuer =========================================
+    uint32_t cnt = 0;
+    uint32_t apar[2] = {0u, 0u};
+    for (int j = 0; j < n_iter; ++j) {
+      for (int l = 0; l < NL; ++l) {
+        const TcLayer& L = P.layers[l];
+        const uint32_t idesc = make_idesc(L.n);
+        for (int s = 0; s < NSLOT; ++s) {
+          if (!valid_slot(j, s)) continue;
+          const bool tr = P.trace != nullptr && blockIdx.x == 0 && j < P.trace_tiles;
+          long long t_w0 = 0, t_w1 = 0, t_full = 0;
+          if (tr) t_w0 = clock64();
+          mbar_wait(bar_aready + 8 * s, apar[s]);
+          apar[s] ^= 1u;
+          tcgen05_fence_after();
+          if (tr) t_w1 = clock64();
+          const uint32_t acc = tmem_base + (uint32_t)s * 256u;
+          for (int kbi = 0; kbi < L.nkb; ++kbi) {
+            uint32_t a_hi, a_lo, pe_entry = 0;
+            const bool is_pe = L.kb[kbi] == TC_KB_PE;
+            if (is_pe) {
+              pe_entry = cnt % N_ENTRIES;
+              mbar_wait(bar_full + 8 * pe_entry, (cnt / N_ENTRIES) & 1u);
+              tcgen05_fence_after();
+              a_hi = sbase + SMEM_RING + pe_entry * 2u * SLOT_BYTES;
+              a_lo = a_hi + SLOT_BYTES;
+              ++cnt;
+            } else {
+              a_hi = sbase + (uint32_t)((X3 ? 0 : s * 4) + L.kb[kbi]) * KB_BYTES;
+              a_lo = a_hi + 4u * KB_BYTES;
+            }
+            const uint64_t adesc_hi = make_smem_desc(a_hi);
+            const uint64_t adesc_lo = make_smem_desc(a_lo);
+            for (int part = 0; part < NPART; ++part) {
+              const uint32_t e = cnt % N_ENTRIES, par = (cnt / N_ENTRIES) & 1u;
+              long long t_f0 = 0;
+              if (tr) t_f0 = clock64();
+              mbar_wait(bar_full + 8 * e, par);
+              tcgen05_fence_after();
+              if (tr) t_full += clock64() - t_f0;
+              const uint64_t bdesc = make_smem_desc_sw64(sbase + SMEM_RING + e * 2u * SLOT_BYTES);
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {  // q = 2*(K half) + K step
+                const uint64_t bd = bdesc + (uint64_t)((q >> 1) * (SLOT_BYTES >> 4) + (q & 1) * 2);
+                umma_bf16(acc, adesc_hi + 2 * q, bd, idesc, (kbi | part | q) != 0 ? 1u : 0u);
+              }
+              if (X3 && part == 0) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                  const uint64_t bd = bdesc + (uint64_t)((q >> 1) * (SLOT_BYTES >> 4) + (q & 1) * 2);
+                  umma_bf16(acc, adesc_lo + 2 * q, bd, idesc, 1u);
+                }
+              }
+              umma_commit_mc(bar_empty + 8 * e, (uint16_t)3);
+              ++cnt;
+            }
+            if (is_pe) umma_commit_mc(bar_empty + 8 * pe_entry, (uint16_t)3);
+          }
+          umma_commit(bar_acc + 8 * s);
+          if (tr && lane == 0) {
+            unsigned long long* r = P.trace + ((size_t)(j * NL + l) * 2 + s) * 4;
+            r[0] = (unsigned long long)t_w0;
+            r[1] = (unsigned long long)t_w1;
+            r[2] = (unsigned long long)clock64();
+            r[3] = (unsigned long long)t_full;
+          }
+        }
+      }
+    }
+  } else if (warp >= 4 && warp < 12) {
+    // ================================ epilogue warps =======================================
+    const int q = warp & 3;               // TMEM lane quarter
+    const int hf = (warp - 4) >> 2;       // which half of the layer's columns
+    const int et = (warp - 4) * 32 + lane;  // 0..255
+    const uint32_t row = (uint32_t)(q * 32 + lane);
+    const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
+    uint32_t acc_par[2] = {0u, 0u};
+    uint32_t cnt = 0;                     // ring entries before the current (j, l, s) in MMA order
+    float alpha[2] = {0.f, 0.f};
+    int pe_waited_j = -1;
+    int last_pe_layer = 0;
+    for (int l2 = 0; l2 < NL; ++l2)
+      if (layer_has_pe(P.layers[l2])) last_pe_layer = l2;
+    // the scratch buffer of iteration jj is dead once its last slot's copy for the last PE-consuming layer is made
+    auto maybe_free = [&](int jj, int layer, int s) {
+      if (layer != last_pe_layer) return;
+      for (int s2 = s + 1; s2 < NSLOT; ++s2)
+        if (valid_slot(jj, s2)) return;
+      mbar_arrive(bar_pe_free + 8 * (jj & 1));
+    };
+
+    // Copy of this thread's part of a PE row, scratch (L2) -> ring entry, in two halves: the loads are issued
+    // when the copy is scheduled, the stores when the ring entry is known to be drained.
+    // WAR on the ring entry is a LOCAL condition: every earlier entry has been consumed by this CTA's MMAs once
+    // the accumulator barrier of the layer-slot that precedes the consumer in MMA order has completed (no
+    // multicast write can target the entry before this CTA has released its PE use).  Waiting on the shared
+    // `empty` barrier here instead would alias phases when the peer CTA lags by more than one ring turn.
+    struct Pending {
+      bool on;
+      int jj, layer, s;
+      uint32_t cnt_e;
+      uint4 vh[4], vl[4];
+    } pend;
+    pend.on = false;
+    auto pe_load = [&](int jj, int layer, int s, uint32_t cnt_e) {
+      if (jj != pe_waited_j) {
+        mbar_wait(bar_pe_ready + 8 * (jj & 1), (uint32_t)(jj >> 1) & 1u);
+        pe_waited_j = jj;
+      }
+      const uint4* src = reinterpret_cast<const uint4*>(scratch + (size_t)((jj & 1) * 2 + s) * TILE_M * ROWB) + row;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) pend.vh[k] = src[(4 * hf + k) * TILE_M];
+      if (X3) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) pend.vl[k] = src[(8 + 4 * hf + k) * TILE_M];
+      }
+      pend.on = true;
+      pend.jj = jj;
+      pend.layer = layer;
+      pend.s = s;
+      pend.cnt_e = cnt_e;
+    };
+    auto pe_store = [&]() {
+      const uint32_t e = pend.cnt_e % N_ENTRIES;
+      uint8_t* dst = smem + SMEM_RING + (size_t)e * 2 * SLOT_BYTES;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) *reinterpret_cast<uint4*>(dst + swz(row, (uint32_t)(4 * hf + k))) = pend.vh[k];
+      if (X3) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) *reinterpret_cast<uint4*>(dst + SLOT_BYTES + swz(row, (uint32_t)(4 * hf + k))) = pend.vl[k];
+      }
+      fence_proxy_async();
+      if (et == 0) mbar_arrive(bar_full + 8 * e);  // phase bookkeeping; completeness is covered by a_ready
+      maybe_free(pend.jj, pend.layer, pend.s);
+      mbar_arrive(bar_aready + 8 * pend.s);
+      pend.on = false;
+    };
+
+    // first layer's bias + the PE blocks of iteration 0
+    bias_s[et] = P.bias[et];
+    {
+      uint32_t c0 = 0;
+      for (int s = 0; s < NSLOT; ++s) {
+        if (n_iter == 0 || !valid_slot(0, s)) continue;
+        pe_load(0, 0, s, c0);
+        pe_store();
+        c0 += layer_entries<NPART>(P.layers[0]);
+      }
+    }
+
+    for (int j = 0; j < n_iter; ++j) {
+      for (int l = 0; l < NL; ++l) {
+        const TcLayer& L = P.layers[l];
+        const uint32_t ents = layer_entries<NPART>(L);
+        const int gl = j * NL + l;
+        // per layer: everyone is done with the other bias buffer -> refill it with the next layer's bias
+        named_bar_sync(1, EPI_THREADS);
+        bias_s[((gl + 1) & 1) * TC_BIAS_STRIDE + et] = P.bias[((l + 1) % NL) * TC_BIAS_STRIDE + et];
+        const uint32_t sbias = smem_u32(bias_s + (gl & 1) * TC_BIAS_STRIDE);
+        const float* bl = bias_s + (gl & 1) * TC_BIAS_STRIDE;
+        const int ln = (l + 1) % NL, jn = j + (l + 1 == NL ? 1 : 0);
+        const bool next_has_pe = layer_has_pe(P.layers[ln]);
+        const uint32_t ents_next = layer_entries<NPART>(P.layers[ln]);
+
+        for (int s = 0; s < NSLOT; ++s) {
+          if (!valid_slot(j, s)) continue;
+          const int tile = tile_of(j, s);
+          int64_t pt = (int64_t)tile * TILE_M + row;
+          const bool valid = pt < P.n_points;
+          if (!valid) pt = P.n_points - 1;
+          const int64_t ray = pt / P.S;
+          uint8_t* arena_hi = smem + (size_t)(X3 ? 0 : s * 4) * KB_BYTES;
+          uint8_t* arena_lo = arena_hi + (size_t)4 * KB_BYTES;
+          const uint32_t acc = lane_base + (uint32_t)s * 256u;
+          const bool tr = P.trace != nullptr && blockIdx.x == 0 && et == 0 && j < P.trace_tiles;
+          long long t_e0 = 0, t_e1 = 0;
+          if (tr) t_e0 = clock64();
+
+          mbar_wait(bar_acc + 8 * s, acc_par[s]);
+          acc_par[s] ^= 1u;
+          tcgen05_fence_after();
+          if (tr) t_e1 = clock64();
+          if (pend.on) pe_store();  // every ring entry before the pending PE block has now been consumed
+
+          if (L.epi == TC_EPI_RGB) {
+            if (hf == 0) {
+              uint32_t v[16];
+              tmem_ld16(acc, v);
+              tmem_ld_wait();
+              if (valid) {
+                float4 o;
+                o.x = __uint_as_float(v[0]) + bl[0];
+                o.y = __uint_as_float(v[1]) + bl[1];
+                o.z = __uint_as_float(v[2]) + bl[2];
+                o.w = alpha[s];
+                reinterpret_cast<float4*>(P.raw)[pt] = o;
+              }
+            }
+          } else {
+            const bool per_ray = L.epi == TC_EPI_VIEW0;
+            const int n_relu = per_ray ? P.view_w : (int)L.n;
+            const int nch = n_relu >> 6;            // 32-column chunks per thread (4 or 2)
+            const int ch0 = hf * nch;               // first chunk of this thread
+            const float* rb = P.view_bias + ray * P.view_w;
+            uint32_t v0[32], v1[32];
+            tmem_ld32(acc + ch0 * 32, v0);
+            for (int cc = 0; cc < nch; cc += 2) {
+              tmem_ld_wait();
+              tmem_ld32(acc + (ch0 + cc + 1) * 32, v1);
+              if (per_ray) epilogue_chunk<X3, true>(v0, ch0 + cc, rb, 0u, arena_hi, arena_lo, row);
+              else epilogue_chunk<X3, false>(v0, ch0 + cc, nullptr, sbias, arena_hi, arena_lo, row);
+              tmem_ld_wait();
+              if (cc + 2 < nch) tmem_ld32(acc + (ch0 + cc + 2) * 32, v0);
+              if (per_ray) epilogue_chunk<X3, true>(v1, ch0 + cc + 1, rb, 0u, arena_hi, arena_lo, row);
+              else epilogue_chunk<X3, false>(v1, ch0 + cc + 1, nullptr, sbias, arena_hi, arena_lo, row);
+            }
+            if (per_ray && hf == 0) {  // density head: accumulator column view_w, no activation
+              uint32_t v[16];
+              tmem_ld16(acc + P.view_w, v);
+              tmem_ld_wait();
+              alpha[s] = __uint_as_float(v[0]) + bl[P.view_w];
+            }
+          }
+          tcgen05_fence_before();
+          fence_proxy_async();
+
+          // hand the slot back to the MMA issuer; if its next layer consumes the PE block, stage that first
+          const bool next_valid = jn < n_iter && valid_slot(jn, s);
+          if (next_valid) {
+            if (next_has_pe) {
+              // ring position of the next layer of this slot: the rest of this layer, then the earlier slots of the next
+              uint32_t cn = cnt + ents;
+              bool between = false;  // another layer-slot is issued between this one and the consumer
+              for (int s2 = s + 1; s2 < NSLOT; ++s2)
+                if (valid_slot(j, s2)) {
+                  cn += ents;
+                  between = true;
+                }
+              for (int s2 = 0; s2 < s; ++s2)
+                if (valid_slot(jn, s2)) {
+                  cn += ents_next;
+                  between = true;
+                }
+              pe_load(jn, ln, s, cn);
+              if (!between) pe_store();  // else: stored (and a_ready signalled) after that layer-slot's accumulator wait
+            } else {
+              mbar_arrive(bar_aready + 8 * s);
+            }
+          }
+          cnt += ents;
+          if (tr) {
+            unsigned long long* r = P.trace + (size_t)P.trace_tiles * NL * 8 + ((size_t)(j * NL + l) * 2 + s) * 4;
+            r[0] = (unsigned long long)t_e0;
+            r[1] = (unsigned long long)t_e1;
+            r[2] = (unsigned long long)clock64();
+            r[3] = 0;
+          }
+        }
+      }
+    }
+  } else if (warp >= 12) {
+    // ============================ positional-encoding warps ===================================
+    // One iteration ahead of the MLP: PE rows (bf16 hi [, lo]) of both slots' tiles -> L2-resident scratch,
+    // laid out [16-byte chunk][row] so that both these stores and the epilogue warps' loads are coalesced.
+    // sin/cos: the argument x*2^k is exact; two-constant Cody-Waite reduction to [-pi, pi] (error ~1e-8 for
+    // |x*2^k| < 1e3) and the MUFU sin/cos (abs error 2^-21.4 on that range) -- well below the bf16 (hi) and
+    // hi+lo (2^-17) resolution the MMA operands keep.
+    const uint32_t row = (uint32_t)((warp - 12) * 32 + lane);
+    for (int j = 0; j < n_iter; ++j) {
+      const int buf = j & 1;
+      mbar_wait(bar_pe_free + 8 * buf, ((uint32_t)(j >> 1) & 1u) ^ 1u);
+      for (int s = 0; s < NSLOT; ++s) {
+        if (!valid_slot(j, s)) continue;
+        int64_t pt = (int64_t)tile_of(j, s) * TILE_M + row;
+        if (pt >= P.n_points) pt = P.n_points - 1;
+        const int64_t ray = pt / P.S;
+        const float z = P.z_vals[pt];
+        float pe[64];
+#pragma unroll
+        for (int cidx = 0; cidx < 3; ++cidx)
+          pe[cidx] = __fadd_rn(P.rays_o[ray * 3 + cidx], __fmul_rn(P.rays_d[ray * 3 + cidx], z));
+#pragma unroll
+        for (int k = 0; k < 10; ++k) {
+#pragma unroll
+          for (int cidx = 0; cidx < 3; ++cidx) {
+            float sv = 0.f, cv = 0.f;
+            if (k < P.multires) {
+              const float t = __fmul_rn(pe[cidx], pow2i(k));
+              const float n = rintf(t * 0.15915494309189535f);
+              float r = fmaf(-n, 6.28125f, t);
+              r = fmaf(-n, 1.9353071795864769e-3f, r);
+              sv = __sinf(r);
+              cv = __cosf(r);
+            }
+            pe[3 + 6 * k + cidx] = sv;
+            pe[6 + 6 * k + cidx] = cv;
+          }
+        }
+        pe[63] = 0.f;
+        uint4* dst = reinterpret_cast<uint4*>(scratch + (size_t)(buf * 2 + s) * TILE_M * ROWB) + row;
+#pragma unroll
+        for (int ch = 0; ch < 8; ++ch) {
+          uint4 h;
+          h.x = pack_bf16(pe[ch * 8 + 0], pe[ch * 8 + 1]);
+          h.y = pack_bf16(pe[ch * 8 + 2], pe[ch * 8 + 3]);
+          h.z = pack_bf16(pe[ch * 8 + 4], pe[ch * 8 + 5]);
+          h.w = pack_bf16(pe[ch * 8 + 6], pe[ch * 8 + 7]);
+          dst[ch * TILE_M] = h;
+          if (X3) {
+            uint4 l;
+            l.x = pack_bf16(pe[ch * 8 + 0] - bf16_lo_f(h.x), pe[ch * 8 + 1] - bf16_hi_f(h.x));
+            l.y = pack_bf16(pe[ch * 8 + 2] - bf16_lo_f(h.y), pe[ch * 8 + 3] - bf16_hi_f(h.y));
+            l.z = pack_bf16(pe[ch * 8 + 4] - bf16_lo_f(h.z), pe[ch * 8 + 5] - bf16_hi_f(h.z));
+            l.w = pack_bf16(pe[ch * 8 + 6] - bf16_lo_f(h.w), pe[ch * 8 + 7] - bf16_hi_f(h.w));
+            dst[(8 + ch) * TILE_M] = l;
+          }
+        }
+      }
+      mbar_arrive(bar_pe_ready + 8 * buf);
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tcgen05_fence_after();
+  if (warp == 2) tmem_dealloc(tmem_base, 512);
+}
+
+}  // namespace pp
+
+int64_t pp_scratch_bytes() { return (int64_t)(num_sms() + 1) * 2 * 2 * tc::TILE_M * 256; }
+
+int pp_launch(const dfn_model* m, const float* bias_ws, const float* vbias_ws, void* scratch, int64_t R, int S,
+              const float* rays_o, const float* rays_d, const float* z_vals, float* raw, int precision,
+              cudaStream_t st) {
+  const dfn_model_desc& d = m->desc;
+  pp::Params P;
+  memset(&P, 0, sizeof(P));
+  P.w_hi = m->tc_hi;
+  P.w_lo = m->tc_lo;
+  P.bias = bias_ws;
+  P.view_bias = vbias_ws;
+  P.rays_o = rays_o;
+  P.rays_d = rays_d;
+  P.z_vals = z_vals;
+  P.raw = raw;
+  P.pe_scratch = reinterpret_cast<uint8_t*>(scratch);
+  tc_get_trace(reinterpret_cast<void**>(&P.trace), &P.trace_tiles);
+  P.n_points = R * S;
+  P.S = S;
+  P.n_tiles = (int)((P.n_points + tc::TILE_M - 1) / tc::TILE_M);
+  P.n_layers = m->prog.n_layers;
+  P.multires = d.multires;
+  P.view_w = d.W / 2;
+  for (int i = 0; i < m->prog.n_layers; ++i) {
+    P.layers[i] = m->prog.layers[i];
+    P.layers[i].woff = m->tc32_woff[i];
+  }
+  int grid = P.n_tiles < num_sms() ? P.n_tiles : num_sms();
+  grid = (grid + 1) & ~1;
+  if (grid > num_sms()) grid = num_sms() & ~1;
+  if (precision == DFN_PREC_BF16) {
+    static bool attr_done = false;
+    if (!attr_done) {
+      DFN_CUDA(cudaFuncSetAttribute(pp::mlp_pp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, pp::SMEM_TOTAL));
+      attr_done = true;
+    }
+    pp::mlp_pp_kernel<false><<<grid, 512, pp::SMEM_TOTAL, st>>>(P);
+  } else {
+    static bool attr_done = false;
+    if (!attr_done) {
+      DFN_CUDA(cudaFuncSetAttribute(pp::mlp_pp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, pp::SMEM_TOTAL));
+      attr_done = true;
+    }
+    pp::mlp_pp_kernel<true><<<grid, 512, pp::SMEM_TOTAL, st>>>(P);
+  }
+  return 0;
+}
+
+}  // namespace dfn

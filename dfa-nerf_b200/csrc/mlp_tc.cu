@@ -212,6 +212,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(X3 ? 256 : 384, 1)
           }
         }
       }
+      // tail: wait for the final release of every ring entry (it needs the peer CTA's remote arrival too)
+      for (uint32_t k = 0; k < (uint32_t)N_PAIRS && k < cnt; ++k) {
+        const uint32_t u = cnt - 1u - k;
+        mbar_wait(bar_empty + 8 * (u % N_PAIRS), (u / N_PAIRS) & 1u);
+      }
     }
   } else if (warp == 1) {
     // ================================= MMA issuer =========================================
@@ -694,7 +699,7 @@ int tc_pack_model(dfn_model* m, const float* const* t, cudaStream_t st) {
 static inline int64_t align256(int64_t x) { return (x + 255) / 256 * 256; }
 
 // debug timeline hook (dfn_debug_trace): device buffer of 2 * trace_tiles * n_layers * 8 uint64
-static int g_impl = 1;  // 1: activations in shared memory, two tiles in flight (fastest so far); 0: TMEM activations
+static int g_impl = -1;  // -1 auto: bf16 -> mlp_tc.cu (1), bf16x3 -> mlp_pp.cu (2); 0: mlp_ts.cu (TMEM activations)
 void tc_set_impl(int impl) { g_impl = impl; }
 static void* g_trace_ptr = nullptr;
 static int g_trace_tiles = 0;
@@ -710,7 +715,7 @@ void tc_get_trace(void** dev_ptr, int* tiles) {
 
 int64_t tc_query_workspace_bytes(const dfn_model* m, int64_t R, int S) {
   (void)S;
-  return align256((int64_t)TC_MAX_LAYERS * TC_BIAS_STRIDE * 4) + align256(R * (m->desc.W / 2) * 4);
+  return align256((int64_t)TC_MAX_LAYERS * TC_BIAS_STRIDE * 4) + align256(R * (m->desc.W / 2) * 4) + align256(pp_scratch_bytes());
 }
 
 int tc_query_points(const dfn_model* m, int64_t R, int S, const float* rays_o, const float* rays_d,
@@ -779,7 +784,12 @@ int tc_query_points(const dfn_model* m, int64_t R, int S, const float* rays_o, c
   macs_pt += (double)d.W * Wh + d.W;                       // views_linears.0 (+ composed feature) and alpha
   macs_pt += (double)(m->n_views - 1) * Wh * Wh + 3.0 * Wh;  // remaining view layers and rgb
   const bool prof = profile_begin(st, macs_pt * (double)P.n_points);
-  if (g_impl == 0 && (precision == DFN_PREC_BF16 || precision == DFN_PREC_BF16X3)) {
+  const int impl = g_impl >= 0 ? g_impl : (precision == DFN_PREC_BF16X3 ? 2 : 1);
+  if (impl == 2 && (precision == DFN_PREC_BF16 || precision == DFN_PREC_BF16X3)) {
+    void* scratch = reinterpret_cast<char*>(vbias_ws) + align256(R * (int64_t)Wh * 4);
+    int rc = pp_launch(m, bias_ws, vbias_ws, scratch, R, S, rays_o, rays_d, z_vals, raw, precision, st);
+    if (rc) return rc;
+  } else if (impl == 0 && (precision == DFN_PREC_BF16 || precision == DFN_PREC_BF16X3)) {
     int rc = ts_launch(m, bias_ws, vbias_ws, R, S, rays_o, rays_d, z_vals, raw, precision, st);
     if (rc) return rc;
   } else if (precision == DFN_PREC_BF16) {

@@ -71,7 +71,11 @@ int mlp_fp32_forward(const dfn_model* m, int64_t P, const float* x, float* out, 
 
 void tc_set_trace(void* dev_ptr, int tiles);
 void tc_get_trace(void** dev_ptr, int* tiles);
-void tc_set_impl(int impl);  // 0: activations in TMEM (mlp_ts.cu, default); 1: activations in shared memory (mlp_tc.cu)
+void tc_set_impl(int impl);  // 2: ping-pong + cooperative epilogue (mlp_pp.cu, default); 1: mlp_tc.cu; 0: mlp_ts.cu
+int64_t pp_scratch_bytes();
+int pp_launch(const dfn_model* m, const float* bias_ws, const float* vbias_ws, void* scratch, int64_t R, int S,
+              const float* rays_o, const float* rays_d, const float* z_vals, float* raw, int precision,
+              cudaStream_t st);
 int ts_launch(const dfn_model* m, const float* bias_ws, const float* vbias_ws, int64_t R, int S, const float* rays_o,
               const float* rays_d, const float* z_vals, float* raw, int precision, cudaStream_t st);
 int tc_pack_model(dfn_model* m, const float* const* t, cudaStream_t st);

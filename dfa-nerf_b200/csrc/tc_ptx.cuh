@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_bf16.h>
 #include <stdint.h>
+#include <stdio.h>
 
 namespace dfn {
 namespace tc {
@@ -38,6 +39,24 @@ __device__ __forceinline__ uint64_t globaltimer_ns() {
   asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
   return t;
 }
+#ifdef DFN_DEBUG_TIMEOUT
+// debug build: report the first stuck waits (thread, barrier offset inside the CTA, parity) and fall through
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t spins = 0;
+  uint64_t t0 = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if ((++spins & 0xFFu) == 0) {
+      const uint64_t t = globaltimer_ns();
+      if (t0 == 0) t0 = t;
+      else if (t - t0 > 100000000ull) {
+        if ((threadIdx.x & 31) == 0)
+          printf("TIMEOUT blk %d warp %d bar+0x%x parity %u\n", (int)blockIdx.x, (int)(threadIdx.x >> 5), bar & 0x3ffu, parity);
+        return;
+      }
+    }
+  }
+}
+#else
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t spins = 0;
   uint64_t t0 = 0;
@@ -49,6 +68,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     }
   }
 }
+#endif
 // One lane of a converged warp.  The MMA / TMA warps run their loops warp-uniformly (so descriptors and
 // barrier addresses stay in uniform registers) and only the tcgen05 / bulk-copy instruction is elected;
 // wrapping the whole loop in `if (lane == 0)` makes ptxas emit a per-lane R2UR waterfall around every UTCHMMA.

@@ -196,8 +196,9 @@ int dfn_profile_enable(int on);
  * done, aux} (uint64 each; 2*tiles*14*2*4 entries at most).  Pass null to switch it off. */
 int dfn_debug_trace(void* dev_buffer, int tiles);
 
-/* Selects the tcgen05 kernel generation: 1 (default) activations in shared memory, two tiles in flight
- * (mlp_tc.cu); 0 activations in tensor memory, one tile in flight (mlp_ts.cu; kept for A/B measurements). */
+/* Selects the tcgen05 kernel variant (A/B measurements): -1 (default) the fastest measured per precision
+ * (bf16 -> 1, bf16x3 -> 2); 1 two tiles in flight, per-tile epilogue warps (mlp_tc.cu); 2 cooperative
+ * epilogue + PE through the weight ring (mlp_pp.cu); 0 activations in tensor memory (mlp_ts.cu). */
 int dfn_debug_set_impl(int impl);
 int dfn_profile_collect(double* kernel_ms, int64_t* launches, double* algorithmic_macs);
 

@@ -22,7 +22,7 @@ aud = fr['aud'].to(dev)
 for mode, prec in (('bf16', dfn.PREC_BF16), ('bf16x3', dfn.PREC_BF16X3)):
     eng = dfn.RenderEngine(net, None, S, 0, precision=prec)
     outs = {}
-    for impl in (1, 0):
+    for impl in (1, 2):
         dfn.lib.dfn_debug_set_impl(impl)
         for _ in range(2):
             raw = eng.query_points(net, ro, rd, vd, z, aud)
@@ -34,7 +34,7 @@ for mode, prec in (('bf16', dfn.PREC_BF16), ('bf16x3', dfn.PREC_BF16X3)):
         torch.cuda.synchronize()
         ms = ev0.elapsed_time(ev1)
         outs[impl] = raw.clone()
-        print('%s impl=%s: %.3f ms -> %.1f TFLOP/s' % (mode, 'smem' if impl else 'tmem', ms, 2 * 557184 * R * S / ms / 1e9), flush=True)
-    d = (outs[0] - outs[1]).abs()
-    print('%s: max |tmem - smem| rgb %.3e sigma %.3e  finite=%s' % (mode, d[..., :3].max().item(), d[..., 3].max().item(), bool(torch.isfinite(outs[0]).all())), flush=True)
-dfn.lib.dfn_debug_set_impl(1)
+        print('%s impl=%s: %.3f ms -> %.1f TFLOP/s' % (mode, {0: 'ts', 1: 'tc', 2: 'pp'}[impl], ms, 2 * 557184 * R * S / ms / 1e9), flush=True)
+    d = (outs[2] - outs[1]).abs()
+    print('%s: max |pp - tc| rgb %.3e sigma %.3e  finite=%s' % (mode, d[..., :3].max().item(), d[..., 3].max().item(), bool(torch.isfinite(outs[2]).all())), flush=True)
+dfn.lib.dfn_debug_set_impl(-1)
