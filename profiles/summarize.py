@@ -1,0 +1,77 @@
+"""Turns gpurun_out/ ncu artefacts into the committed text summaries under profiles/.
+    python profiles/summarize.py r01
+Reads gpurun_out/launches_<round>.csv (ncu --metrics gpu__time_duration.sum of `bench.py --steps 2`) and
+gpurun_out/prof_<round>_*.ncu-rep (ncu --set full) with `ncu -i ... --page raw --csv`."""
+import collections
+import csv
+import io
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+rnd = sys.argv[1] if len(sys.argv) > 1 else 'r01'
+out = []
+
+
+def launches():
+    p = os.path.join(ROOT, 'gpurun_out', 'launches_%s.csv' % rnd)
+    if not os.path.exists(p):
+        return
+    rows = list(csv.DictReader(l for l in open(p) if l.startswith('"')))
+    agg = collections.OrderedDict()
+    for r in rows:
+        k = r['Kernel Name'].split('(')[0].replace('void ', '')
+        a = agg.setdefault(k, [0, 0.0])
+        a[0] += 1
+        a[1] += float(r['Metric Value'])
+    tot = sum(v[1] for v in agg.values())
+    out.append('## Launch list (%s): ncu --metrics gpu__time_duration.sum --clock-control none, `bench.py --steps 2 --warmup 3`' % rnd)
+    out.append('(cold-cache, serialised launches: compare SHARES, not absolutes; %d launches, %.1f ms total)\n' % (len(rows), tot / 1e6))
+    out.append('%-52s %6s %12s %12s %8s' % ('kernel', 'n', 'total ms', 'avg us', 'share'))
+    for k, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+        out.append('%-52s %6d %12.3f %12.2f %8.4f' % (k[:52], n, t / 1e6, t / n / 1e3, t / tot))
+    out.append('')
+
+
+WANT = ['gpu__time_duration.sum', 'sm__cycles_elapsed.max', 'dram__bytes_read.sum', 'dram__bytes_write.sum',
+        'sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed', 'launch__registers_per_thread',
+        'launch__grid_size', 'launch__block_size', 'launch__cluster_size', 'launch__shared_mem_per_block_dynamic',
+        'sm__warps_active.avg.pct_of_peak_sustained_active', 'smsp__issue_active.avg.pct_of_peak_sustained_active',
+        'smsp__inst_executed.sum', 'lts__t_sector_hit_rate.pct', 'lts__t_bytes.sum', 'l1tex__m_xbar2l1tex_read_bytes_mem_global_op_tma_ld.sum',
+        'l1tex__data_pipe_lsu_wavefronts_mem_shared.sum', 'l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum',
+        'smsp__sass_inst_executed_op_tmem_ldt.sum', 'sm__inst_executed_pipe_tensor_subpipe_hmma.sum',
+        'dram__throughput.avg.pct_of_peak_sustained_elapsed', 'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed']
+
+
+def report(tag, title):
+    p = os.path.join(ROOT, 'gpurun_out', 'prof_%s_%s.ncu-rep' % (rnd, tag))
+    if not os.path.exists(p):
+        return
+    txt = subprocess.run(['ncu', '-i', p, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(txt)))
+    hdr, units = rows[0], rows[1]
+    out.append('## %s  (ncu --set full --clock-control none; %s)' % (title, os.path.basename(p)))
+    for vals in rows[2:]:
+        d = {h: (u, v) for h, u, v in zip(hdr, units, vals)}
+        out.append('kernel: %s   grid %s block %s' % (d.get('Kernel Name', ('', '?'))[1], d.get('Grid Size', ('', '?'))[1], d.get('Block Size', ('', '?'))[1]))
+        for k in WANT:
+            if k in d and d[k][1] != '':
+                out.append('  %-82s %12s %s' % (k, d[k][1], d[k][0]))
+        try:
+            rd = float(d['dram__bytes_read.sum'][1].replace(',', ''))
+            wr = float(d['dram__bytes_write.sum'][1].replace(',', ''))
+            mult = {'byte': 1, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}
+            out.append('  DRAM traffic per launch: %.3f MB' % ((rd * mult[d['dram__bytes_read.sum'][0]] + wr * mult[d['dram__bytes_write.sum'][0]]) / 1e6))
+        except Exception:
+            pass
+    out.append('')
+
+
+launches()
+report('bf16', 'mlp_tc_kernel<bf16>: 20,000 rays x 192 samples (fine-pass sized network query)')
+report('x3', 'mlp_pp_kernel<bf16x3>: 20,000 rays x 192 samples')
+report('raw2outputs', 'volume_weights_kernel<1> (raw2outputs): 202,500 rays x 64 samples')
+path = os.path.join(ROOT, 'profiles', 'ncu_summary_%s.txt' % rnd)
+open(path, 'w').write('\n'.join(out) + '\n')
+print('\n'.join(out))
