@@ -5,14 +5,15 @@ libdfn.so (include/dfn.h).  There is NO CPU path: every function needs CUDA tens
 compiled extension, and fails loudly without them.
 """
 from ._lib import lib, DfnError, PREC_FP32, PREC_BF16, PREC_BF16X3  # noqa: F401
-from .functional import (get_rays, get_embedder, Embedder, decoder_transform_points, z_vals_uniform,  # noqa: F401
+from .functional import (get_rays, get_embedder, Embedder, decoder_transform_points, z_vals_uniform, make_points,  # noqa: F401
                          calc_volume_weights, composite_function, raw2outputs, sample_pdf, invert_cdf,
                          sort_merge)
 from .modules import NeRF, FaceNeRF  # noqa: F401
+from .decoder import Decoder, DeformationField_ori, render_head_torso  # noqa: F401
 from .render import render, render_rays, batchify_rays, run_network, RenderEngine  # noqa: F401
 from .distributed import render_sharded, shard_range  # noqa: F401
 
-__all__ = ['get_rays', 'get_embedder', 'Embedder', 'decoder_transform_points', 'z_vals_uniform',
+__all__ = ['get_rays', 'get_embedder', 'Embedder', 'decoder_transform_points', 'z_vals_uniform', 'make_points',
            'calc_volume_weights', 'composite_function', 'raw2outputs', 'sample_pdf', 'invert_cdf', 'sort_merge',
-           'NeRF', 'FaceNeRF', 'render', 'render_rays', 'batchify_rays', 'run_network', 'RenderEngine',
+           'NeRF', 'FaceNeRF', 'Decoder', 'DeformationField_ori', 'render_head_torso', 'render', 'render_rays', 'batchify_rays', 'run_network', 'RenderEngine',
            'render_sharded', 'shard_range', 'lib', 'DfnError', 'PREC_FP32', 'PREC_BF16', 'PREC_BF16X3']

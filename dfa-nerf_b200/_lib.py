@@ -47,10 +47,13 @@ def _load():
         'dfn_profile_collect': (i32, [C.POINTER(C.c_double), C.POINTER(i64), C.POINTER(C.c_double)]),
         'dfn_get_rays': (i32, [i32, i32, vp, vp, f32, f32, f32, C.POINTER(f32), vp, vp, vp, vp]),
         'dfn_z_vals': (i32, [i32, i32, vp, vp, vp, vp, vp, vp]),
+        'dfn_make_points': (i32, [i32, i32, vp, vp, vp, vp, vp, vp]),
         'dfn_embed': (i32, [i64, vp, i32, i32, vp, vp]),
         'dfn_composite_fields': (i32, [i32, i64, vp, vp, vp, vp, vp]),
         'dfn_calc_volume_weights': (i32, [i32, i32, vp, vp, vp, f32, vp, vp]),
         'dfn_raw2outputs': (i32, [i32, i32, vp, vp, vp, vp, i32, i32, f32, vp, vp, vp, vp, vp, vp]),
+        'dfn_composite_head_torso': (i32, [i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, f32, vp, vp, vp]),
+        'dfn_linear': (i32, [i64, i32, i32, vp, i64, i32, vp, i64, vp, vp, i32, vp, i64, vp, i64, vp]),
         'dfn_sample_pdf': (i32, [i32, i32, vp, vp, i64, i32, vp, i32, vp, vp, vp]),
         'dfn_invert_cdf': (i32, [i32, i32, vp, vp, i32, vp, i32, vp, vp, vp]),
         'dfn_sort_merge': (i32, [i32, i32, vp, i32, vp, vp, vp]),
@@ -75,8 +78,8 @@ def _load():
 
 
 lib = _load()
-EXPORTS = ['dfn_abi_version', 'dfn_last_error', 'dfn_last_launch_count', 'dfn_profile_enable', 'dfn_profile_collect', 'dfn_debug_trace', 'dfn_debug_set_impl', 'dfn_get_rays', 'dfn_z_vals', 'dfn_embed',
-           'dfn_composite_fields', 'dfn_calc_volume_weights', 'dfn_raw2outputs', 'dfn_sample_pdf', 'dfn_invert_cdf',
+EXPORTS = ['dfn_abi_version', 'dfn_last_error', 'dfn_last_launch_count', 'dfn_profile_enable', 'dfn_profile_collect', 'dfn_debug_trace', 'dfn_debug_set_impl', 'dfn_get_rays', 'dfn_z_vals', 'dfn_make_points', 'dfn_embed',
+           'dfn_composite_fields', 'dfn_composite_head_torso', 'dfn_linear', 'dfn_calc_volume_weights', 'dfn_raw2outputs', 'dfn_sample_pdf', 'dfn_invert_cdf',
            'dfn_sort_merge', 'dfn_model_create', 'dfn_model_destroy', 'dfn_model_num_tensors', 'dfn_model_load',
            'dfn_mlp_workspace_bytes', 'dfn_mlp_forward', 'dfn_query_workspace_bytes', 'dfn_query_points',
            'dfn_render_workspace_bytes', 'dfn_render_rays']

@@ -88,10 +88,26 @@ __global__ void z_vals_kernel(int R, int S, const float* __restrict__ t_vals,
   }
 }
 
+// ------------------------------------------------------------------------------- a3 points
+// MAIN:638-641: p = o + d*z (product and sum rounded separately) and the ray direction repeated per sample.
+__global__ void make_points_kernel(int R, int S, const float* __restrict__ rays_o, const float* __restrict__ rays_d,
+                                   const float* __restrict__ z_vals, float* __restrict__ pts, float* __restrict__ dirs) {
+  const int64_t n = (int64_t)R * S * 3;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t pt = i / 3;
+    const int c = (int)(i % 3);
+    const int64_t ray = pt / S;
+    const float d = rays_d[ray * 3 + c];
+    if (pts) pts[i] = __fadd_rn(rays_o[ray * 3 + c], __fmul_rn(d, z_vals[pt]));
+    if (dirs) dirs[i] = d;
+  }
+}
+
 // ------------------------------------------------------------------------- a4 / a4' encodings
 // One thread per output element so the [P, D] store is coalesced.
 // kind 0 (HELP:21-52): [x | sin(2^k x) | cos(2^k x)]_k, exact power-of-two scaling, no pi.
 // kind 1 (DEC:257-275): p/2 then [sin(2^k pi p) | cos(2^k pi p)]_k with fl32(2^k*pi) as in torch.
+// kind 2: kind 1 applied to x/||x|| (the view-direction branch, DEC:337-338).
 __global__ void embed_kernel(int64_t P, const float* __restrict__ x, int L, int kind,
                              float* __restrict__ out) {
   int D = kind == 0 ? 3 + 6 * L : 6 * L;
@@ -111,7 +127,12 @@ __global__ void embed_kernel(int64_t P, const float* __restrict__ x, int L, int 
       }
     } else {
       int k = j / 6, r = j % 6;
-      float ph = __fmul_rn(x[p * 3 + (r % 3)], 0.5f);
+      float xv = x[p * 3 + (r % 3)];
+      if (kind == 2) {
+        const float a0 = x[p * 3], a1 = x[p * 3 + 1], a2 = x[p * 3 + 2];
+        xv = __fdiv_rn(xv, sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(a0, a0), __fmul_rn(a1, a1)), __fmul_rn(a2, a2))));
+      }
+      float ph = __fmul_rn(xv, 0.5f);
       float a = __fmul_rn(__fmul_rn(pow2i(k), CUDART_PI_F), ph);
       v = r < 3 ? sinf(a) : cosf(a);
     }
@@ -282,6 +303,105 @@ __global__ void volume_weights_kernel(int R, int S, const float* __restrict__ sr
   }
 }
 
+// ------------------------------------------------ a6 + a7 + a8 + a9: live head + torso compositing
+// One warp per ray, MAIN:669-708 with concate_bg: head colour of the last sample <- background pixel; torso
+// sigma of the last sample <- 0; relu; +1e-6 on the last sample of the LAST field of each stack (head for the
+// head-only image, torso for the person image); two-field mix den = s_h + s_t (0 -> 1e-4),
+// feat = f_h*(s_h/den) + f_t*(s_t/den), sigma = s_h + s_t (MAIN:146-166); weights with the head rays' norm for
+// the head image and the torso rays' norm for the person image (MAIN:704-705); rgb = sum w*feat.
+__global__ void head_torso_kernel(int R, int S, const float* __restrict__ feat_h, const float* __restrict__ sig_h,
+                                  const float* __restrict__ feat_t, const float* __restrict__ sig_t,
+                                  const float* __restrict__ bc_rgb, const float* __restrict__ z_vals,
+                                  const float* __restrict__ rays_d_h, const float* __restrict__ rays_d_t,
+                                  float last_dist, float* __restrict__ rgb_head, float* __restrict__ rgb_person) {
+  const int lane = threadIdx.x & 31;
+  const int warps_per_block = blockDim.x >> 5;
+  const int seg = (S + 31) / 32;
+  for (int ray = blockIdx.x * warps_per_block + (threadIdx.x >> 5); ray < R; ray += gridDim.x * warps_per_block) {
+    float nrm[2];
+    {
+      const float* d0 = rays_d_h + ray * 3;
+      const float* d1 = rays_d_t + ray * 3;
+      nrm[0] = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(d0[0], d0[0]), __fmul_rn(d0[1], d0[1])), __fmul_rn(d0[2], d0[2])));
+      nrm[1] = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(d1[0], d1[0]), __fmul_rn(d1[1], d1[1])), __fmul_rn(d1[2], d1[2])));
+    }
+    const float* zr = z_vals + (int64_t)ray * S;
+    float alpha[2][kMaxSeg], col[2][kMaxSeg][3];
+    double local[2] = {1.0, 1.0};
+    const int s0 = lane * seg;
+#pragma unroll
+    for (int k = 0; k < kMaxSeg; ++k) {
+      const int s = s0 + k;
+      alpha[0][k] = alpha[1][k] = 0.f;
+      if (k < seg && s < S) {
+        const int64_t i = (int64_t)ray * S + s;
+        const bool last = s == S - 1;
+        float fh[3] = {feat_h[i * 3], feat_h[i * 3 + 1], feat_h[i * 3 + 2]};
+        if (last) {
+          fh[0] = bc_rgb[ray * 3];
+          fh[1] = bc_rgb[ray * 3 + 1];
+          fh[2] = bc_rgb[ray * 3 + 2];
+        }
+        const float ft[3] = {feat_t[i * 3], feat_t[i * 3 + 1], feat_t[i * 3 + 2]};
+        const float sh = fmaxf(sig_h[i], 0.f);
+        float st = last ? 0.f : fmaxf(sig_t[i], 0.f);
+        const float sh1 = last ? __fadd_rn(sh, 1e-6f) : sh;  // head-only stack: the head is the last field
+        if (last) st = __fadd_rn(st, 1e-6f);                  // two-field stack: the torso is the last field
+        float den = __fadd_rn(sh, st);
+        const float ssum = den;
+        if (den == 0.f) den = 1e-4f;
+        const float wh = __fdiv_rn(sh, den), wt = __fdiv_rn(st, den);
+        const float dz = last ? last_dist : __fsub_rn(zr[s + 1], zr[s]);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          col[0][k][c] = fh[c];
+          col[1][k][c] = __fadd_rn(__fmul_rn(fh[c], wh), __fmul_rn(ft[c], wt));
+        }
+        const float sg[2] = {sh1, ssum};
+#pragma unroll
+        for (int f = 0; f < 2; ++f) {
+          const float dist = __fmul_rn(dz, nrm[f]);
+          const float a = __fsub_rn(1.0f, expf(-__fmul_rn(__fadd_rn(fmaxf(sg[f], 0.f), 1e-6f), dist)));
+          alpha[f][k] = a;
+          local[f] *= (double)__fadd_rn(__fsub_rn(1.0f, a), 1e-10f);
+        }
+      }
+    }
+#pragma unroll
+    for (int f = 0; f < 2; ++f) {
+      double incl = local[f];
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        double up = shfl_up_f64(incl, d);
+        if (lane >= d) incl *= up;
+      }
+      double run = shfl_up_f64(incl, 1);
+      if (lane == 0) run = 1.0;
+      float acc[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+      for (int k = 0; k < kMaxSeg; ++k) {
+        const int s = s0 + k;
+        if (k < seg && s < S) {
+          const float w = __fmul_rn(alpha[f][k], (float)run);
+          run *= (double)__fadd_rn(__fsub_rn(1.0f, alpha[f][k]), 1e-10f);
+          acc[0] += w * col[f][k][0];
+          acc[1] += w * col[f][k][1];
+          acc[2] += w * col[f][k][2];
+        }
+      }
+      acc[0] = warp_sum(acc[0]);
+      acc[1] = warp_sum(acc[1]);
+      acc[2] = warp_sum(acc[2]);
+      float* out = f == 0 ? rgb_head : rgb_person;
+      if (lane == 0 && out) {
+        out[ray * 3 + 0] = acc[0];
+        out[ray * 3 + 1] = acc[1];
+        out[ray * 3 + 2] = acc[2];
+      }
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------- a10 sample_pdf
 static constexpr int kMaxBins = 256;
 
@@ -437,8 +557,16 @@ extern "C" int dfn_z_vals(int R, int S, const float* t_vals, const float* near, 
   return 0;
 }
 
+extern "C" int dfn_make_points(int R, int S, const float* rays_o, const float* rays_d, const float* z_vals, float* pts,
+                               float* dirs, void* stream) {
+  DFN_CHECK_ARG(R > 0 && S > 0 && rays_o && rays_d && z_vals && (pts || dirs), "dfn_make_points: bad argument");
+  make_points_kernel<<<grid_for((int64_t)R * S * 3), kThreads, 0, (cudaStream_t)stream>>>(R, S, rays_o, rays_d, z_vals, pts, dirs);
+  DFN_LAUNCH_CHECK();
+  return 0;
+}
+
 extern "C" int dfn_embed(int64_t P, const float* x, int L, int kind, float* out, void* stream) {
-  DFN_CHECK_ARG(P > 0 && x && out && L > 0 && L <= 16 && (kind == 0 || kind == 1), "dfn_embed: bad argument");
+  DFN_CHECK_ARG(P > 0 && x && out && L > 0 && L <= 16 && kind >= 0 && kind <= 2, "dfn_embed: bad argument");
   int D = kind == 0 ? 3 + 6 * L : 6 * L;
   embed_kernel<<<grid_for(P * D), kThreads, 0, (cudaStream_t)stream>>>(P, x, L, kind, out);
   DFN_LAUNCH_CHECK();
@@ -489,6 +617,20 @@ extern "C" int dfn_raw2outputs(int R, int S, const float* raw, const float* z_va
                                float* depth_map, void* stream) {
   return launch_raw2outputs(R, S, raw, z_vals, rays_d, bc_rgb, raw_is_feat, white_bkgd, last_dist, rgb_map, disp_map,
                             acc_map, weights, depth_map, nullptr, (cudaStream_t)stream);
+}
+
+extern "C" int dfn_composite_head_torso(int R, int S, const float* feat_head, const float* sigma_head,
+                                        const float* feat_torso, const float* sigma_torso, const float* bc_rgb,
+                                        const float* z_vals, const float* rays_d_head, const float* rays_d_torso,
+                                        float last_dist, float* rgb_head, float* rgb_person, void* stream) {
+  DFN_CHECK_ARG(R > 0 && S > 0 && S <= 32 * kMaxSeg && feat_head && sigma_head && feat_torso && sigma_torso && bc_rgb &&
+                    z_vals && rays_d_head && rays_d_torso,
+                "dfn_composite_head_torso: bad argument (S <= 256)");
+  head_torso_kernel<<<rays_grid(R, 8), 256, 0, (cudaStream_t)stream>>>(R, S, feat_head, sigma_head, feat_torso, sigma_torso,
+                                                                      bc_rgb, z_vals, rays_d_head, rays_d_torso, last_dist,
+                                                                      rgb_head, rgb_person);
+  DFN_LAUNCH_CHECK();
+  return 0;
 }
 
 extern "C" int dfn_sample_pdf(int R, int nb, const float* bins, const float* weights, int64_t w_stride,

@@ -114,9 +114,22 @@ def get_embedder(multires, i=0):
     return (lambda x, eo=eo: eo.embed(x)), eo.out_dim
 
 
-def decoder_transform_points(p, n_freq, views=False):
-    """DEC:257-275 ('normal' encoding, downscale_p_by=2)."""
-    return _embed(p, n_freq, 1)
+def decoder_transform_points(p, n_freq, views=False, normalize=False):
+    """DEC:257-275 ('normal' encoding, downscale_p_by=2); normalize=True encodes p/||p|| (DEC:337-338)."""
+    return _embed(p, n_freq, 2 if normalize else 1)
+
+
+def make_points(rays_o, rays_d, z_vals):
+    """MAIN:638-641: (p [R,S,3] = o + d*z, r [R,S,3] = d repeated per sample)."""
+    rays_o, po = dev(rays_o, 'rays_o')
+    rays_d, pd = dev(rays_d, 'rays_d')
+    z_vals, pz = dev(z_vals, 'z_vals')
+    R, S = z_vals.shape
+    pts = torch.empty((R, S, 3), dtype=torch.float32, device=z_vals.device)
+    dirs = torch.empty((R, S, 3), dtype=torch.float32, device=z_vals.device)
+    with torch.cuda.device(z_vals.device):
+        check(lib.dfn_make_points(R, S, po, pd, pz, ptr(pts), ptr(dirs), stream_ptr()), 'dfn_make_points')
+    return pts, dirs
 
 
 def calc_volume_weights(z_vals, ray_vector, sigma, last_dist=1e10):

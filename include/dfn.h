@@ -63,9 +63,16 @@ int dfn_get_rays(int n_rows, int n_cols, const float* xs, const float* ys, float
 int dfn_z_vals(int R, int S, const float* t_vals, const float* near, const float* far,
                const float* rand, float* z_out, void* stream);
 
+/* ---- a3  sample points  (MAIN:638-641) -----------------------------------------------------------------
+ * pts[r,s,:] = rays_o[r] + rays_d[r]*z_vals[r,s]; dirs[r,s,:] = rays_d[r].  Either output may be null.  Only the
+ * explicit-points interface of the Decoder needs these tensors; dfn_query_points never materialises them. */
+int dfn_make_points(int R, int S, const float* rays_o, const float* rays_d, const float* z_vals, float* pts,
+                    float* dirs, void* stream);
+
 /* ---- a4 / a4'  positional encodings  (HELP:21-70 Embedder; DEC:257-275 transform_points) ---
  * kind 0: [x, sin(2^k x), cos(2^k x)]_k  -> out [P, 3+6L];
- * kind 1: p/=2; [sin(2^k pi p), cos(2^k pi p)]_k -> out [P, 6L]. */
+ * kind 1: p/=2; [sin(2^k pi p), cos(2^k pi p)]_k -> out [P, 6L];
+ * kind 2: kind 1 of x/||x|| (view directions, DEC:337-338). */
 int dfn_embed(int64_t P, const float* x, int L, int kind, float* out, void* stream);
 
 /* ---- a7  composite_function  (MAIN:146-166) -------------------------------------------------
@@ -85,6 +92,15 @@ int dfn_raw2outputs(int R, int S, const float* raw, const float* z_vals, const f
                     const float* bc_rgb, int raw_is_feat, int white_bkgd, float last_dist,
                     float* rgb_map, float* disp_map, float* acc_map, float* weights,
                     float* depth_map, void* stream);
+
+/* ---- a6+a7+a8+a9  live two-field compositing of one chunk  (MAIN:669-708, concate_bg) ------------------
+ * feat_* [R,S,3] (sigmoid already applied, DEC:346), sigma_* [R,S] (raw, relu applied here, MAIN:688-689),
+ * bc_rgb [R,3], z_vals [R,S], rays_d_* [R,3] -> rgb_head [R,3] (head field alone), rgb_person [R,3]
+ * (density-weighted head+torso mix).  Either output may be null. */
+int dfn_composite_head_torso(int R, int S, const float* feat_head, const float* sigma_head,
+                             const float* feat_torso, const float* sigma_torso, const float* bc_rgb,
+                             const float* z_vals, const float* rays_d_head, const float* rays_d_torso,
+                             float last_dist, float* rgb_head, float* rgb_person, void* stream);
 
 /* ---- a10  sample_pdf  (HELP:537-581) --------------------------------------------------------
  * bins [R,nb], weights [R,nb-1] (row stride w_stride floats, so a [R,S] weights tensor can be
@@ -129,6 +145,15 @@ int dfn_model_num_tensors(const dfn_model* m);
  * (fp32 row-major for the FFMA path; bf16 hi/lo planes, K padded to 64, 128-byte swizzled
  * K-major tiles for the tcgen05 path) and uploads on `stream`. */
 int dfn_model_load(dfn_model* m, const float* const* tensors_host, int n_tensors, void* stream);
+
+/* One fused nn.Linear of the fp32 path: Y[p,n] = act(sum_k X(p,k) W[n,k] + bias[n]) (+ addend[p*ld_add + n]);
+ * X(p,k) = k < K1 ? X1[p*ld1 + k] : X2[p*ld2 + k-K1] (concatenated inputs are never materialised; a row
+ * stride of 0 broadcasts one row, e.g. the per-frame signal of DEC:293-295).  act & 3: 0 none, 1 relu,
+ * 2 sigmoid; act & 4: addend is added before the activation instead of after it.
+ * bias / X2 / addend may be null.  Building block of the Decoder / DeformationField_ori shim (DEC:109-349). */
+int dfn_linear(int64_t P, int N, int K1, const float* X1, int64_t ld1, int K2, const float* X2, int64_t ld2,
+               const float* W, const float* bias, int act, const float* addend, int64_t ld_add, float* Y,
+               int64_t ldy, void* stream);
 
 /* Module forward on explicit embedded inputs: x [P, input_ch+dim_aud+input_ch_views] -> out [P,4]
  * (HELP:275-299 / HELP:372-396).  fp32 FFMA path.  workspace: dfn_mlp_workspace_bytes(P) bytes. */

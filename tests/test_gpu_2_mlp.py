@@ -152,3 +152,30 @@ def test_tc_matches_fp32_kernel_at_scale(dfn):
     wb = dfn.calc_volume_weights(args[3], args[1], b[..., 3].contiguous())
     assert maxerr(wa, wb) < 1e-4
     assert maxerr(torch.sigmoid(a[..., :3]), torch.sigmoid(b[..., :3])) < 1e-4
+
+
+def test_kernel_variants_agree(dfn):
+    """The three tcgen05 kernel variants (dfn_debug_set_impl) compute the same function: activations in shared
+    memory (1) vs tensor memory (0) are bit-identical (same operands, same K order); the cooperative-epilogue
+    variant (2) uses its own sin/cos evaluation, so it agrees to the operand precision."""
+    R, S = 700, 192
+    ro, rd, vd, z, aud = _query_case(R, S, seed=9)
+    net = face(dfn, 1)
+    args = [t.to(DEV) for t in (ro, rd, vd, z, aud)]
+    try:
+        for prec in (dfn.PREC_BF16, dfn.PREC_BF16X3):
+            eng = dfn.RenderEngine(net, None, S, 0, precision=prec)
+            outs = {}
+            for impl in (0, 1, 2):
+                dfn.lib.dfn_debug_set_impl(impl)
+                outs[impl] = eng.query_points(net, *args).clone()
+                assert torch.isfinite(outs[impl]).all()
+            assert torch.equal(outs[0], outs[1]) or maxerr(outs[0], outs[1]) < 2e-3   # x3: K-half order differs
+            if prec == dfn.PREC_BF16:
+                assert torch.equal(outs[0], outs[1])
+            wa = dfn.calc_volume_weights(args[3], args[1], outs[1][..., 3].contiguous())
+            wb = dfn.calc_volume_weights(args[3], args[1], outs[2][..., 3].contiguous())
+            tol = 1e-4 if prec == dfn.PREC_BF16X3 else 5e-2
+            assert maxerr(wa, wb) < tol
+    finally:
+        dfn.lib.dfn_debug_set_impl(-1)
