@@ -378,32 +378,46 @@ __global__ void __launch_bounds__(512, 1) mlp_ts_kernel(const __grid_constant__ 
       if (pt >= P.n_points) pt = P.n_points - 1;
       const int64_t ray = pt / P.S;
       const float z = P.z_vals[pt];
-      float x[3];
+      float pe[64];
 #pragma unroll
-      for (int c = 0; c < 3; ++c) x[c] = __fadd_rn(P.rays_o[ray * 3 + c], __fmul_rn(P.rays_d[ray * 3 + c], z));
-      uint8_t* pe_hi = smem + C::SMEM_PE + (size_t)(buf * C::PE_PLANES) * PE_BYTES;
-      uint8_t* pe_lo = pe_hi + PE_BYTES;
-      auto put = [&](int e, float v) {
-        const uint32_t o = swz(row, (uint32_t)e >> 3) + ((uint32_t)e & 7u) * 2u;
-        const __nv_bfloat16 hb = __float2bfloat16_rn(v);
-        *reinterpret_cast<__nv_bfloat16*>(pe_hi + o) = hb;
-        if (X3) *reinterpret_cast<__nv_bfloat16*>(pe_lo + o) = __float2bfloat16_rn(v - __bfloat162float(hb));
-      };
-      put(0, x[0]);
-      put(1, x[1]);
-      put(2, x[2]);
-      float f = 1.0f;
-      for (int k = 0; k < P.multires; ++k) {
+      for (int c = 0; c < 3; ++c) pe[c] = __fadd_rn(P.rays_o[ray * 3 + c], __fmul_rn(P.rays_d[ray * 3 + c], z));
+#pragma unroll
+      for (int k = 0; k < 10; ++k) {   // same evaluation as mlp_tc.cu (exact 2^k scaling, Cody-Waite, MUFU)
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
-          float sv, cv;
-          sincosf(__fmul_rn(x[c], f), &sv, &cv);
-          put(3 + 6 * k + c, sv);
-          put(6 + 6 * k + c, cv);
+          float sv = 0.f, cv = 0.f;
+          if (k < P.multires) {
+            const float t = __fmul_rn(pe[c], pow2i(k));
+            const float n = rintf(t * 0.15915494309189535f);
+            float r = fmaf(-n, 6.28125f, t);
+            r = fmaf(-n, 1.9353071795864769e-3f, r);
+            sv = __sinf(r);
+            cv = __cosf(r);
+          }
+          pe[3 + 6 * k + c] = sv;
+          pe[6 + 6 * k + c] = cv;
         }
-        f *= 2.0f;
       }
-      for (int e = 3 + 6 * P.multires; e < 64; ++e) put(e, 0.0f);
+      pe[63] = 0.f;
+      uint8_t* pe_hi = smem + C::SMEM_PE + (size_t)(buf * C::PE_PLANES) * PE_BYTES;
+      uint8_t* pe_lo = pe_hi + PE_BYTES;
+#pragma unroll
+      for (int ch = 0; ch < 8; ++ch) {
+        uint4 h;
+        h.x = pack_bf16(pe[ch * 8 + 0], pe[ch * 8 + 1]);
+        h.y = pack_bf16(pe[ch * 8 + 2], pe[ch * 8 + 3]);
+        h.z = pack_bf16(pe[ch * 8 + 4], pe[ch * 8 + 5]);
+        h.w = pack_bf16(pe[ch * 8 + 6], pe[ch * 8 + 7]);
+        *reinterpret_cast<uint4*>(pe_hi + swz(row, (uint32_t)ch)) = h;
+        if (X3) {
+          uint4 l;
+          l.x = pack_bf16(pe[ch * 8 + 0] - bf16_lo_f(h.x), pe[ch * 8 + 1] - bf16_hi_f(h.x));
+          l.y = pack_bf16(pe[ch * 8 + 2] - bf16_lo_f(h.y), pe[ch * 8 + 3] - bf16_hi_f(h.y));
+          l.z = pack_bf16(pe[ch * 8 + 4] - bf16_lo_f(h.z), pe[ch * 8 + 5] - bf16_hi_f(h.z));
+          l.w = pack_bf16(pe[ch * 8 + 6] - bf16_lo_f(h.w), pe[ch * 8 + 7] - bf16_hi_f(h.w));
+          *reinterpret_cast<uint4*>(pe_lo + swz(row, (uint32_t)ch)) = l;
+        }
+      }
       fence_proxy_async();
       mbar_arrive(bar_pe_ready + 8 * buf);
     }

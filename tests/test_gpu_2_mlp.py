@@ -156,8 +156,8 @@ def test_tc_matches_fp32_kernel_at_scale(dfn):
 
 def test_kernel_variants_agree(dfn):
     """The three tcgen05 kernel variants (dfn_debug_set_impl) compute the same function: activations in shared
-    memory (1) vs tensor memory (0) are bit-identical (same operands, same K order); the cooperative-epilogue
-    variant (2) uses its own sin/cos evaluation, so it agrees to the operand precision."""
+    memory (1) vs tensor memory (0) are bit-identical in bf16 (same operands, same K order); in bf16x3 the hi/lo
+    products are accumulated in a different order, so all variants agree to the operand precision."""
     R, S = 700, 192
     ro, rd, vd, z, aud = _query_case(R, S, seed=9)
     net = face(dfn, 1)
