@@ -15,8 +15,8 @@
 //     layer).  The 32 KB this frees makes the weight ring three entries (96 KB) deep.
 // bf16x3 (A_hi*W_hi + A_lo*W_hi + A_hi*W_lo) runs one tile with hi/lo activation planes in the same arena.
 //
-// Warp roles (512 threads): 0 weight producer (TMA multicast), 1 MMA issuer, 2 TMEM allocator,
-// 4-11 epilogue, 12-15 positional encoding.
+// Warp roles (384 threads, 168 registers each): 0 weight producer (TMA multicast), 1 MMA issuer, 2-3 positional
+// encoding (warp 2 also allocates TMEM), 4-11 epilogue.
 // Reference arithmetic: HELP:21-52 (Embedder), HELP:275-299 (FaceNeRF.forward), HELP:372-396 (NeRF.forward).
 #include <string.h>
 
@@ -41,7 +41,7 @@ static constexpr int SMEM_BAR = SMEM_BIAS + 2 * TC_BIAS_STRIDE * 4;
 static constexpr int SMEM_TOTAL = SMEM_BAR + 256;
 static_assert(SMEM_TOTAL <= 227 * 1024, "shared memory budget");
 static constexpr int EPI_THREADS = 256;
-static constexpr int PE_THREADS = 128;
+static constexpr int PE_THREADS = 64;   // warps 2-3: two rows per thread and slot
 
 struct Params {
   const uint8_t* w_hi;
@@ -114,10 +114,14 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[32], int chun
 
 // X3 = false: bf16, two tile slots.  X3 = true: split-bf16, one slot.
 template <bool X3>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(512, 1) mlp_pp_kernel(const __grid_constant__ Params P) {
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1) mlp_pp_kernel(const __grid_constant__ Params P) {
   constexpr int NSLOT = X3 ? 1 : 2;
   constexpr int NPART = X3 ? 2 : 1;
   constexpr int ROWB = X3 ? 256 : 128;  // scratch bytes per PE row
+  // bf16x3 (one tile): all eight epilogue warps share the tile's columns.  bf16 (two tiles): four warps per tile,
+  // the two groups run concurrently (a cooperative, serialised epilogue of two tiles measured slower).
+  constexpr bool COOP = X3;
+  constexpr int EPI_GROUP = COOP ? EPI_THREADS : EPI_THREADS / 2;
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t sbase = smem_u32(smem);
   if ((sbase & 1023u) != 0) __trap();
@@ -141,9 +145,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(512, 1) mlp_pp_kerne
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(bar_acc + 8 * s, 1);
-      mbar_init(bar_aready + 8 * s, EPI_THREADS);
+      mbar_init(bar_aready + 8 * s, EPI_GROUP);
       mbar_init(bar_pe_ready + 8 * s, PE_THREADS);
-      mbar_init(bar_pe_free + 8 * s, EPI_THREADS);
+      mbar_init(bar_pe_free + 8 * s, EPI_GROUP);
     }
     fence_barrier_init();
   }
@@ -273,8 +277,159 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(512, 1) mlp_pp_kerne
         }
       }
     }
-  } else if (warp >= 4 && warp < 12) {
-    // ================================ epilogue warps =======================================
+  } else if (!COOP && warp >= 4 && warp < 12) {
+    // ===================== epilogue warps, one group of four per tile slot (bf16) =====================
+    const int s = (warp - 4) >> 2;        // this group's tile slot
+    const int o = 1 - s;                  // the other slot
+    const int q = warp & 3;               // TMEM lane quarter
+    const int et = (warp & 3) * 32 + lane;  // 0..127 within the group
+    const uint32_t row = (uint32_t)et;
+    const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
+    const uint32_t acc = lane_base + (uint32_t)s * 256u;
+    uint8_t* arena_hi = smem + (size_t)(s * 4) * KB_BYTES;
+    uint8_t* arena_lo = arena_hi;  // unused in bf16
+    float* bias_g = bias_s + s * TC_BIAS_STRIDE;
+    const uint32_t sbias = smem_u32(bias_g);
+    uint32_t acc_par = 0u;
+    int pe_waited_j = -1;
+    int last_pe_layer = 0;
+    for (int l2 = 0; l2 < NL; ++l2)
+      if (layer_has_pe(P.layers[l2])) last_pe_layer = l2;
+    uint4 vh[8];
+    // PE row of tile (jj, s): scratch (L2) -> registers
+    auto pe_load = [&](int jj) {
+      if (jj != pe_waited_j) {
+        mbar_wait(bar_pe_ready + 8 * (jj & 1), (uint32_t)(jj >> 1) & 1u);
+        pe_waited_j = jj;
+      }
+      const uint4* src = reinterpret_cast<const uint4*>(scratch + (size_t)((jj & 1) * 2 + s) * TILE_M * ROWB) + row;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) vh[k] = src[k * TILE_M];
+    };
+    // registers -> ring entry cnt_e, then hand the slot to the MMA issuer.  The entry is free once every earlier
+    // entry has been consumed by this CTA's MMAs, i.e. once the accumulator barrier of the layer-slot that precedes
+    // the consumer in MMA order has completed (see the note in the cooperative branch); the caller has waited.
+    auto pe_store = [&](int jj, int layer, uint32_t cnt_e) {
+      const uint32_t e = cnt_e % N_ENTRIES;
+      uint8_t* dst = smem + SMEM_RING + (size_t)e * 2 * SLOT_BYTES;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) *reinterpret_cast<uint4*>(dst + swz(row, (uint32_t)k)) = vh[k];
+      fence_proxy_async();
+      if (et == 0) mbar_arrive(bar_full + 8 * e);
+      if (layer == last_pe_layer) {   // scratch buffer of iteration jj is dead after its last slot's last copy
+        bool last_slot = true;
+        for (int s2 = s + 1; s2 < NSLOT; ++s2)
+          if (valid_slot(jj, s2)) last_slot = false;
+        if (last_slot) mbar_arrive(bar_pe_free + 8 * (jj & 1));
+      }
+      mbar_arrive(bar_aready + 8 * s);
+    };
+    // ring position of layer-slot (j, l, s): entries of all earlier layer-slots in MMA order
+    uint32_t base = 0;  // entries before (j, l, slot 0)
+    if (n_iter > 0 && valid_slot(0, s)) {
+      const uint32_t e0 = layer_entries<NPART>(P.layers[0]);
+      reinterpret_cast<float2*>(bias_g)[et] = reinterpret_cast<const float2*>(P.bias)[et];
+      pe_load(0);
+      pe_store(0, 0, s == 0 ? 0u : e0);   // nothing precedes the first layer-slots: the ring is empty
+      named_bar_sync(1 + s, EPI_GROUP);
+    }
+    float alpha = 0.f;
+    for (int j = 0; j < n_iter; ++j) {
+      if (!valid_slot(j, s)) break;
+      const uint32_t nv = valid_slot(j, 1) ? 2u : 1u;   // valid slots in this iteration (slot 0 always is)
+      const int tile = tile_of(j, s);
+      int64_t pt = (int64_t)tile * TILE_M + row;
+      const bool valid = pt < P.n_points;
+      if (!valid) pt = P.n_points - 1;
+      const int64_t ray = pt / P.S;
+      for (int l = 0; l < NL; ++l) {
+        const TcLayer& L = P.layers[l];
+        const uint32_t ents = layer_entries<NPART>(L);
+        const int ln = (l + 1) % NL, jn = j + (l + 1 == NL ? 1 : 0);
+        const bool next_has_pe = layer_has_pe(P.layers[ln]);
+        const bool next_valid = jn < n_iter && valid_slot(jn, s);
+        float2 nb = make_float2(0.f, 0.f);
+        nb = reinterpret_cast<const float2*>(P.bias + ln * TC_BIAS_STRIDE)[et];
+        if (next_valid && next_has_pe) pe_load(jn);   // L2 latency hidden behind the accumulator wait
+        const bool tr = P.trace != nullptr && blockIdx.x == 0 && et == 0 && j < P.trace_tiles;
+        long long t_e0 = 0, t_e1 = 0;
+        if (tr) t_e0 = clock64();
+        mbar_wait(bar_acc + 8 * s, acc_par);
+        acc_par ^= 1u;
+        tcgen05_fence_after();
+        if (tr) t_e1 = clock64();
+
+        if (L.epi == TC_EPI_RGB) {
+          uint32_t v[16];
+          tmem_ld16(acc, v);
+          tmem_ld_wait();
+          if (valid) {
+            float4 ov;
+            ov.x = __uint_as_float(v[0]) + bias_g[0];
+            ov.y = __uint_as_float(v[1]) + bias_g[1];
+            ov.z = __uint_as_float(v[2]) + bias_g[2];
+            ov.w = alpha;
+            reinterpret_cast<float4*>(P.raw)[pt] = ov;
+          }
+        } else {
+          const bool per_ray = L.epi == TC_EPI_VIEW0;
+          const int nch = (per_ray ? P.view_w : (int)L.n) >> 5;   // 32-column chunks: 8 or 4
+          const float* rb = P.view_bias + ray * P.view_w;
+          uint32_t v0[32], v1[32];
+          tmem_ld32(acc, v0);
+          for (int cc = 0; cc < nch; cc += 2) {
+            tmem_ld_wait();
+            tmem_ld32(acc + (cc + 1) * 32, v1);
+            if (per_ray) epilogue_chunk<X3, true>(v0, cc, rb, 0u, arena_hi, arena_lo, row);
+            else epilogue_chunk<X3, false>(v0, cc, nullptr, sbias, arena_hi, arena_lo, row);
+            tmem_ld_wait();
+            if (cc + 2 < nch) tmem_ld32(acc + (cc + 2) * 32, v0);
+            if (per_ray) epilogue_chunk<X3, true>(v1, cc + 1, rb, 0u, arena_hi, arena_lo, row);
+            else epilogue_chunk<X3, false>(v1, cc + 1, nullptr, sbias, arena_hi, arena_lo, row);
+          }
+          if (per_ray) {
+            uint32_t v[16];
+            tmem_ld16(acc + P.view_w, v);
+            tmem_ld_wait();
+            alpha = __uint_as_float(v[0]) + bias_g[P.view_w];
+          }
+        }
+        tcgen05_fence_before();
+        fence_proxy_async();
+
+        if (next_valid) {
+          if (next_has_pe) {
+            // consumer (jn, ln, s); the layer-slot issued just before it belongs to the other slot (if that is valid)
+            const uint32_t ents_n = layer_entries<NPART>(P.layers[ln]);
+            uint32_t cn;
+            if (s == 0) {
+              cn = base + ents * nv;                       // after both slots' layer l
+              if (nv == 2u) mbar_wait(bar_acc + 8 * o, (uint32_t)(j * NL + l) & 1u);            // acc of (j, l, 1)
+            } else {
+              cn = base + ents * nv + ents_n;              // after slot 0's next layer
+              mbar_wait(bar_acc + 8 * o, (uint32_t)(jn * NL + ln) & 1u);                          // acc of (jn, ln, 0)
+            }
+            pe_store(jn, ln, cn);
+          } else {
+            mbar_arrive(bar_aready + 8 * s);
+          }
+        }
+        // swap in the next layer's bias
+        named_bar_sync(1 + s, EPI_GROUP);
+        reinterpret_cast<float2*>(bias_g)[et] = nb;
+        named_bar_sync(1 + s, EPI_GROUP);
+        base += ents * nv;
+        if (tr) {
+          unsigned long long* r = P.trace + (size_t)P.trace_tiles * NL * 8 + ((size_t)(j * NL + l) * 2 + s) * 4;
+          r[0] = (unsigned long long)t_e0;
+          r[1] = (unsigned long long)t_e1;
+          r[2] = (unsigned long long)clock64();
+          r[3] = 0;
+        }
+      }
+    }
+  } else if (COOP && warp >= 4 && warp < 12) {
+    // ================================ epilogue warps (cooperative, bf16x3) ============================
     const int q = warp & 3;               // TMEM lane quarter
     const int hf = (warp - 4) >> 2;       // which half of the layer's columns
     const int et = (warp - 4) * 32 + lane;  // 0..255
@@ -464,18 +619,19 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(512, 1) mlp_pp_kerne
         }
       }
     }
-  } else if (warp >= 12) {
+  } else if (warp == 2 || warp == 3) {
     // ============================ positional-encoding warps ===================================
     // One iteration ahead of the MLP: PE rows (bf16 hi [, lo]) of both slots' tiles -> L2-resident scratch,
     // laid out [16-byte chunk][row] so that both these stores and the epilogue warps' loads are coalesced.
     // sin/cos: the argument x*2^k is exact; two-constant Cody-Waite reduction to [-pi, pi] (error ~1e-8 for
     // |x*2^k| < 1e3) and the MUFU sin/cos (abs error 2^-21.4 on that range) -- well below the bf16 (hi) and
     // hi+lo (2^-17) resolution the MMA operands keep.
-    const uint32_t row = (uint32_t)((warp - 12) * 32 + lane);
     for (int j = 0; j < n_iter; ++j) {
       const int buf = j & 1;
       mbar_wait(bar_pe_free + 8 * buf, ((uint32_t)(j >> 1) & 1u) ^ 1u);
-      for (int s = 0; s < NSLOT; ++s) {
+      for (int sr = 0; sr < 2 * NSLOT; ++sr) {
+        const int s = sr >> 1;
+        const uint32_t row = (uint32_t)((warp - 2) * 32 + lane + (sr & 1) * 64);
         if (!valid_slot(j, s)) continue;
         int64_t pt = (int64_t)tile_of(j, s) * TILE_M + row;
         if (pt >= P.n_points) pt = P.n_points - 1;
@@ -572,14 +728,14 @@ int pp_launch(const dfn_model* m, const float* bias_ws, const float* vbias_ws, v
       DFN_CUDA(cudaFuncSetAttribute(pp::mlp_pp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, pp::SMEM_TOTAL));
       attr_done = true;
     }
-    pp::mlp_pp_kernel<false><<<grid, 512, pp::SMEM_TOTAL, st>>>(P);
+    pp::mlp_pp_kernel<false><<<grid, 384, pp::SMEM_TOTAL, st>>>(P);
   } else {
     static bool attr_done = false;
     if (!attr_done) {
       DFN_CUDA(cudaFuncSetAttribute(pp::mlp_pp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, pp::SMEM_TOTAL));
       attr_done = true;
     }
-    pp::mlp_pp_kernel<true><<<grid, 512, pp::SMEM_TOTAL, st>>>(P);
+    pp::mlp_pp_kernel<true><<<grid, 384, pp::SMEM_TOTAL, st>>>(P);
   }
   return 0;
 }
