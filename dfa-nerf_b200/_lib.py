@@ -31,6 +31,17 @@ class RenderIO(C.Structure):
         [('u_per_ray', C.c_int64)]
 
 
+class DecoderDesc(C.Structure):
+    _fields_ = [(n, C.c_int) for n in ('hidden', 'z_dim', 'dim_signal', 'dim_et_embed', 'n_freq', 'n_freq_views',
+                                       'n_blocks', 'skip')]
+
+
+class HeadTorsoIO(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ('rays_o_head', 'rays_d_head', 'rays_o_torso', 'rays_d_torso', 'near', 'far',
+                                          't_vals', 'bc_rgb', 'z_shape', 'z_app', 'signal', 'signal_torso', 'rgb_head',
+                                          'rgb_person')] + [('last_dist', C.c_float)]
+
+
 def _load():
     if not os.path.exists(LIB_PATH):
         raise ImportError('dfa_nerf_b200: %s is missing -- run `python -c "import __graft_entry__ as g; g.build()"` '
@@ -67,6 +78,15 @@ def _load():
         'dfn_query_points': (i32, [vp, i64, i32, vp, vp, vp, vp, vp, vp, i32, vp, i64, vp]),
         'dfn_render_workspace_bytes': (i64, [vp, i64, i32, i32, i32]),
         'dfn_render_rays': (i32, [vp, vp, i64, i32, i32, C.POINTER(RenderIO), i32, i32, vp, i64, vp]),
+        'dfn_decoder_create': (i32, [C.POINTER(DecoderDesc), C.POINTER(vp)]),
+        'dfn_decoder_destroy': (None, [vp]),
+        'dfn_decoder_num_tensors': (i32, [vp]),
+        'dfn_decoder_load': (i32, [vp, C.POINTER(vp), i32, vp]),
+        'dfn_decoder_query_workspace_bytes': (i64, [vp, i64, i32]),
+        'dfn_decoder_query': (i32, [vp, i32, i64, i32, vp, vp, vp, vp, vp, vp, vp, i32, vp, i64, vp]),
+        'dfn_decoder_macs_per_sample': (C.c_double, [vp, i32]),
+        'dfn_render_head_torso_workspace_bytes': (i64, [vp, i64, i32]),
+        'dfn_render_head_torso': (i32, [vp, i64, i32, C.POINTER(HeadTorsoIO), i32, vp, i64, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib_, name)
@@ -82,7 +102,9 @@ EXPORTS = ['dfn_abi_version', 'dfn_last_error', 'dfn_last_launch_count', 'dfn_pr
            'dfn_composite_fields', 'dfn_composite_head_torso', 'dfn_linear', 'dfn_calc_volume_weights', 'dfn_raw2outputs', 'dfn_sample_pdf', 'dfn_invert_cdf',
            'dfn_sort_merge', 'dfn_model_create', 'dfn_model_destroy', 'dfn_model_num_tensors', 'dfn_model_load',
            'dfn_mlp_workspace_bytes', 'dfn_mlp_forward', 'dfn_query_workspace_bytes', 'dfn_query_points',
-           'dfn_render_workspace_bytes', 'dfn_render_rays']
+           'dfn_render_workspace_bytes', 'dfn_render_rays', 'dfn_decoder_create', 'dfn_decoder_destroy',
+           'dfn_decoder_num_tensors', 'dfn_decoder_load', 'dfn_decoder_query_workspace_bytes', 'dfn_decoder_query',
+           'dfn_decoder_macs_per_sample', 'dfn_render_head_torso_workspace_bytes', 'dfn_render_head_torso']
 
 
 def check(rc, what=''):

@@ -52,4 +52,9 @@ int launch_raw2outputs(int R, int S, const float* raw, const float* z_vals, cons
                        float* disp_map, float* acc_map, float* weights, float* depth_map, float* last_weight,
                        cudaStream_t st);
 
+int launch_head_torso(int R, int S, const float* feat_h, int fstride_h, const float* sig_h, int sstride_h,
+                      const float* feat_t, int fstride_t, const float* sig_t, int sstride_t, const float* bc_rgb,
+                      const float* z_vals, const float* rays_d_h, const float* rays_d_t, float last_dist, float* rgb_head,
+                      float* rgb_person, cudaStream_t st);
+
 }  // namespace dfn

@@ -18,6 +18,13 @@
 // Warp roles (384 threads, 168 registers each): 0 weight producer (TMA multicast), 1 MMA issuer, 2-3 positional
 // encoding (warp 2 also allocates TMEM), 4-11 epilogue.
 // Reference arithmetic: HELP:21-52 (Embedder), HELP:275-299 (FaceNeRF.forward), HELP:372-396 (NeRF.forward).
+//
+// DEC = true instantiates the same schedule for the reference's LIVE model, Decoder + DeformationField_ori
+// (DEC:77-349; layer programs built in mlp_dec.cu): the positional encoding of DEC:257-275, a density layer that
+// keeps its result in a register (TC_EPI_SIGMA), a 256-wide per-ray view bias, a sigmoid on the colours, a second
+// staged input block (the deformed per-sample signal of the torso field) whose layers are split in two
+// accumulate-chained halves (TC_EPI_CONT / TC_F_ACCUM), and the deformation output written back to the tile's
+// scratch blocks (TC_EPI_STAGE).
 #include <string.h>
 
 #include <vector>
@@ -52,7 +59,7 @@ struct Params {
   const float* rays_d;
   const float* z_vals;
   float* raw;
-  uint8_t* pe_scratch;     // [grid][2 buffers][2 slots][128 rows][row_bytes]
+  uint8_t* pe_scratch;     // [grid][2 buffers][2 slots][1|2 staged blocks][128 rows][row_bytes]
   unsigned long long* trace;
   int trace_tiles;
   int64_t n_points;
@@ -64,11 +71,13 @@ struct Params {
   TcLayer layers[TC_MAX_LAYERS];  // woff: offsets into the K=32 / 64-byte-swizzle blobs
 };
 
-__device__ __forceinline__ bool layer_has_pe(const TcLayer& L) {
+// staged input block of a layer (0: positional encoding, 1: deformed signal) or -1; at most one per layer
+__device__ __forceinline__ int layer_staged(const TcLayer& L) {
   for (int k = 0; k < L.nkb; ++k)
-    if (L.kb[k] == TC_KB_PE) return true;
-  return false;
+    if (L.kb[k] >= TC_KB_PE) return (int)L.kb[k] - TC_KB_PE;
+  return -1;
 }
+__device__ __forceinline__ bool layer_has_pe(const TcLayer& L) { return layer_staged(L) >= 0; }
 template <int NPART>
 __device__ __forceinline__ uint32_t layer_entries(const TcLayer& L) {
   return (uint32_t)L.nkb * NPART + (layer_has_pe(L) ? 1u : 0u);
@@ -112,12 +121,45 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[32], int chun
   }
 }
 
-// X3 = false: bf16, two tile slots.  X3 = true: split-bf16, one slot.
+// TC_EPI_STAGE: + bias (no activation), bf16 (hi[/lo]) of one 32-column chunk -> the tile's staged block in the
+// scratch ([16-byte chunk][row] layout, as the PE warps write it).  blk_base = staged block (chunk32 >> 1).
 template <bool X3>
+__device__ __forceinline__ void stage_chunk(const uint32_t (&v)[32], int chunk32, uint32_t sbias, uint8_t* blk_base,
+                                            uint32_t row) {
+  uint4* dst = reinterpret_cast<uint4*>(blk_base) + row;
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    float b[8], o[8];
+    lds_f32x8(sbias + (uint32_t)(chunk32 * 32 + g * 8) * 4u, b);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) o[e] = __uint_as_float(v[g * 8 + e]) + b[e];
+    const int c16 = (chunk32 & 1) * 4 + g;
+    uint4 h;
+    h.x = pack_bf16(o[0], o[1]);
+    h.y = pack_bf16(o[2], o[3]);
+    h.z = pack_bf16(o[4], o[5]);
+    h.w = pack_bf16(o[6], o[7]);
+    dst[c16 * TILE_M] = h;
+    if (X3) {
+      uint4 l;
+      l.x = pack_bf16(o[0] - bf16_lo_f(h.x), o[1] - bf16_hi_f(h.x));
+      l.y = pack_bf16(o[2] - bf16_lo_f(h.y), o[3] - bf16_hi_f(h.y));
+      l.z = pack_bf16(o[4] - bf16_lo_f(h.z), o[5] - bf16_hi_f(h.z));
+      l.w = pack_bf16(o[6] - bf16_lo_f(h.w), o[7] - bf16_hi_f(h.w));
+      dst[(8 + c16) * TILE_M] = l;
+    }
+  }
+}
+
+__device__ __forceinline__ float sigmoid_f(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
+
+// X3 = false: bf16, two tile slots.  X3 = true: split-bf16, one slot.  DEC: Decoder programs (see the header).
+template <bool X3, bool DEC>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1) mlp_pp_kernel(const __grid_constant__ Params P) {
   constexpr int NSLOT = X3 ? 1 : 2;
   constexpr int NPART = X3 ? 2 : 1;
-  constexpr int ROWB = X3 ? 256 : 128;  // scratch bytes per PE row
+  constexpr int ROWB = X3 ? 256 : 128;  // scratch bytes per row of a staged block
+  constexpr int NBLK = DEC ? 2 : 1;     // staged blocks per tile
   // bf16x3 (one tile): all eight epilogue warps share the tile's columns.  bf16 (two tiles): four warps per tile,
   // the two groups run concurrently (a cooperative, serialised epilogue of two tiles measured slower).
   constexpr bool COOP = X3;
@@ -167,7 +209,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1) mlp_pp_kerne
   auto valid_slot = [&](int j, int s) { return (j * C + c) * NSLOT + s < n_groups; };
   auto tile_of = [&](int j, int s) { return 2 * ((j * C + c) * NSLOT + s) + (int)crank; };
   const int NL = P.n_layers;
-  uint8_t* scratch = P.pe_scratch + (size_t)blockIdx.x * 2 * 2 * TILE_M * ROWB;
+  uint8_t* scratch = P.pe_scratch + (size_t)blockIdx.x * 2 * 2 * NBLK * TILE_M * ROWB;
+  // staged block `blk` of the tile in slot s of scratch buffer buf
+  auto scr = [&](int buf, int s, int blk) { return scratch + (size_t)((buf * 2 + s) * NBLK + blk) * TILE_M * ROWB; };
 
   if (warp == 0) {
     // ============================== weight producer (TMA multicast) ==========================
@@ -180,7 +224,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1) mlp_pp_kerne
           uint32_t off = L.woff;
           const uint32_t bytes = (uint32_t)L.n * 64u;
           for (int kbi = 0; kbi < L.nkb; ++kbi) {
-            if (L.kb[kbi] == TC_KB_PE) ++cnt;  // the entry before this K-block's weights is filled by the epilogue warps
+            if (L.kb[kbi] >= TC_KB_PE) ++cnt;  // the entry before this K-block's weights is filled by the epilogue warps
             for (int part = 0; part < NPART; ++part) {
               const uint32_t e = cnt % N_ENTRIES, par = (cnt / N_ENTRIES) & 1u;
               mbar_wait(bar_empty + 8 * e, par ^ 1u);
@@ -215,6 +259,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1) mlp_pp_kerne
       for (int l = 0; l < NL; ++l) {
         const TcLayer& L = P.layers[l];
         const uint32_t idesc = make_idesc(L.n);
+        const uint32_t acc0 = DEC && (L.flags & TC_F_ACCUM) ? 1u : 0u;  // continue the previous (TC_EPI_CONT) layer's sums
         for (int s = 0; s < NSLOT; ++s) {
           if (!valid_slot(j, s)) continue;
           const bool tr = P.trace != nullptr && blockIdx.x == 0 && j < P.trace_tiles;
@@ -227,7 +272,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1) mlp_pp_kerne
           const uint32_t acc = tmem_base + (uint32_t)s * 256u;
           for (int kbi = 0; kbi < L.nkb; ++kbi) {
             uint32_t a_hi, a_lo, pe_entry = 0;
-            const bool is_pe = L.kb[kbi] == TC_KB_PE;
+            const bool is_pe = L.kb[kbi] >= TC_KB_PE;
             if (is_pe) {
               pe_entry = cnt % N_ENTRIES;
               mbar_wait(bar_full + 8 * pe_entry, (cnt / N_ENTRIES) & 1u);
@@ -252,7 +297,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1) mlp_pp_kerne
 #pragma unroll
               for (int q = 0; q < 4; ++q) {  // q = 2*(K half) + K step
                 const uint64_t bd = bdesc + (uint64_t)((q >> 1) * (SLOT_BYTES >> 4) + (q & 1) * 2);
-                umma_bf16(acc, adesc_hi + 2 * q, bd, idesc, (kbi | part | q) != 0 ? 1u : 0u);
+                umma_bf16(acc, adesc_hi + 2 * q, bd, idesc, (kbi | part | q) != 0 ? 1u : acc0);
               }
               if (X3 && part == 0) {
 #pragma unroll
@@ -297,12 +342,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1) mlp_pp_kerne
       if (layer_has_pe(P.layers[l2])) last_pe_layer = l2;
     uint4 vh[8];
     // PE row of tile (jj, s): scratch (L2) -> registers
-    auto pe_load = [&](int jj) {
+    auto pe_load = [&](int jj, int blk) {
       if (jj != pe_waited_j) {
         mbar_wait(bar_pe_ready + 8 * (jj & 1), (uint32_t)(jj >> 1) & 1u);
         pe_waited_j = jj;
       }
-      const uint4* src = reinterpret_cast<const uint4*>(scratch + (size_t)((jj & 1) * 2 + s) * TILE_M * ROWB) + row;
+      const uint4* src = reinterpret_cast<const uint4*>(scr(jj & 1, s, blk)) + row;
 #pragma unroll
       for (int k = 0; k < 8; ++k) vh[k] = src[k * TILE_M];
     };
@@ -329,7 +374,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1) mlp_pp_kerne
     if (n_iter > 0 && valid_slot(0, s)) {
       const uint32_t e0 = layer_entries<NPART>(P.layers[0]);
       reinterpret_cast<float2*>(bias_g)[et] = reinterpret_cast<const float2*>(P.bias)[et];
-      pe_load(0);
+      pe_load(0, layer_staged(P.layers[0]));
       pe_store(0, 0, s == 0 ? 0u : e0);   // nothing precedes the first layer-slots: the ring is empty
       named_bar_sync(1 + s, EPI_GROUP);
     }
@@ -346,11 +391,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1) mlp_pp_kerne
         const TcLayer& L = P.layers[l];
         const uint32_t ents = layer_entries<NPART>(L);
         const int ln = (l + 1) % NL, jn = j + (l + 1 == NL ? 1 : 0);
-        const bool next_has_pe = layer_has_pe(P.layers[ln]);
+        const int st_next = layer_staged(P.layers[ln]);
+        const bool next_has_pe = st_next >= 0;
         const bool next_valid = jn < n_iter && valid_slot(jn, s);
+        // a TC_EPI_STAGE layer writes the block its successor stages: load that one after the epilogue
+        const bool late_load = DEC && L.epi == TC_EPI_STAGE;
         float2 nb = make_float2(0.f, 0.f);
         nb = reinterpret_cast<const float2*>(P.bias + ln * TC_BIAS_STRIDE)[et];
-        if (next_valid && next_has_pe) pe_load(jn);   // L2 latency hidden behind the accumulator wait
+        if (next_valid && next_has_pe && !late_load) pe_load(jn, st_next);   // L2 latency hidden behind the accumulator wait
         const bool tr = P.trace != nullptr && blockIdx.x == 0 && et == 0 && j < P.trace_tiles;
         long long t_e0 = 0, t_e1 = 0;
         if (tr) t_e0 = clock64();
@@ -368,8 +416,32 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1) mlp_pp_kerne
             ov.x = __uint_as_float(v[0]) + bias_g[0];
             ov.y = __uint_as_float(v[1]) + bias_g[1];
             ov.z = __uint_as_float(v[2]) + bias_g[2];
+            if (DEC) {  // DEC:346-347
+              ov.x = sigmoid_f(ov.x);
+              ov.y = sigmoid_f(ov.y);
+              ov.z = sigmoid_f(ov.z);
+            }
             ov.w = alpha;
             reinterpret_cast<float4*>(P.raw)[pt] = ov;
+          }
+        } else if (DEC && L.epi == TC_EPI_SIGMA) {
+          uint32_t v[16];
+          tmem_ld16(acc, v);
+          tmem_ld_wait();
+          alpha = __uint_as_float(v[0]) + bias_g[0];
+        } else if (DEC && L.epi == TC_EPI_CONT) {
+          // partial sums stay in the accumulator
+        } else if (DEC && L.epi == TC_EPI_STAGE) {
+          const int nch = (int)L.n >> 5;
+          uint32_t v0[32], v1[32];
+          tmem_ld32(acc, v0);
+          for (int cc = 0; cc < nch; cc += 2) {
+            tmem_ld_wait();
+            tmem_ld32(acc + (cc + 1) * 32, v1);
+            stage_chunk<X3>(v0, cc, sbias, scr(j & 1, s, cc >> 1), row);
+            tmem_ld_wait();
+            if (cc + 2 < nch) tmem_ld32(acc + (cc + 2) * 32, v0);
+            stage_chunk<X3>(v1, cc + 1, sbias, scr(j & 1, s, (cc + 1) >> 1), row);
           }
         } else {
           const bool per_ray = L.epi == TC_EPI_VIEW0;
@@ -387,7 +459,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1) mlp_pp_kerne
             if (per_ray) epilogue_chunk<X3, true>(v1, cc + 1, rb, 0u, arena_hi, arena_lo, row);
             else epilogue_chunk<X3, false>(v1, cc + 1, nullptr, sbias, arena_hi, arena_lo, row);
           }
-          if (per_ray) {
+          if (!DEC && per_ray) {
             uint32_t v[16];
             tmem_ld16(acc + P.view_w, v);
             tmem_ld_wait();
@@ -399,6 +471,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1) mlp_pp_kerne
 
         if (next_valid) {
           if (next_has_pe) {
+            if (late_load) pe_load(jn, st_next);
             // consumer (jn, ln, s); the layer-slot issued just before it belongs to the other slot (if that is valid)
             const uint32_t ents_n = layer_entries<NPART>(P.layers[ln]);
             uint32_t cn;
@@ -468,7 +541,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1) mlp_pp_kerne
         mbar_wait(bar_pe_ready + 8 * (jj & 1), (uint32_t)(jj >> 1) & 1u);
         pe_waited_j = jj;
       }
-      const uint4* src = reinterpret_cast<const uint4*>(scratch + (size_t)((jj & 1) * 2 + s) * TILE_M * ROWB) + row;
+      const uint4* src = reinterpret_cast<const uint4*>(scr(jj & 1, s, layer_staged(P.layers[layer]))) + row;
 #pragma unroll
       for (int k = 0; k < 4; ++k) pend.vh[k] = src[(4 * hf + k) * TILE_M];
       if (X3) {
@@ -553,9 +626,37 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1) mlp_pp_kerne
                 o.x = __uint_as_float(v[0]) + bl[0];
                 o.y = __uint_as_float(v[1]) + bl[1];
                 o.z = __uint_as_float(v[2]) + bl[2];
+                if (DEC) {  // DEC:346-347
+                  o.x = sigmoid_f(o.x);
+                  o.y = sigmoid_f(o.y);
+                  o.z = sigmoid_f(o.z);
+                }
                 o.w = alpha[s];
                 reinterpret_cast<float4*>(P.raw)[pt] = o;
               }
+            }
+          } else if (DEC && L.epi == TC_EPI_SIGMA) {
+            if (hf == 0) {
+              uint32_t v[16];
+              tmem_ld16(acc, v);
+              tmem_ld_wait();
+              alpha[s] = __uint_as_float(v[0]) + bl[0];
+            }
+          } else if (DEC && L.epi == TC_EPI_CONT) {
+            // partial sums stay in the accumulator
+          } else if (DEC && L.epi == TC_EPI_STAGE) {
+            // this thread's half of the columns is one whole staged block (N = 128: PE' | signal')
+            const int nch = (int)L.n >> 6;
+            const int ch0 = hf * nch;
+            uint32_t v0[32], v1[32];
+            tmem_ld32(acc + ch0 * 32, v0);
+            for (int cc = 0; cc < nch; cc += 2) {
+              tmem_ld_wait();
+              tmem_ld32(acc + (ch0 + cc + 1) * 32, v1);
+              stage_chunk<X3>(v0, ch0 + cc, sbias, scr(j & 1, s, (ch0 + cc) >> 1), row);
+              tmem_ld_wait();
+              if (cc + 2 < nch) tmem_ld32(acc + (ch0 + cc + 2) * 32, v0);
+              stage_chunk<X3>(v1, ch0 + cc + 1, sbias, scr(j & 1, s, (ch0 + cc + 1) >> 1), row);
             }
           } else {
             const bool per_ray = L.epi == TC_EPI_VIEW0;
@@ -575,7 +676,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1) mlp_pp_kerne
               if (per_ray) epilogue_chunk<X3, true>(v1, ch0 + cc + 1, rb, 0u, arena_hi, arena_lo, row);
               else epilogue_chunk<X3, false>(v1, ch0 + cc + 1, nullptr, sbias, arena_hi, arena_lo, row);
             }
-            if (per_ray && hf == 0) {  // density head: accumulator column view_w, no activation
+            if (!DEC && per_ray && hf == 0) {  // density head: accumulator column view_w, no activation
               uint32_t v[16];
               tmem_ld16(acc + P.view_w, v);
               tmem_ld_wait();
@@ -602,6 +703,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1) mlp_pp_kerne
                   cn += ents_next;
                   between = true;
                 }
+              // the staged block was written by other threads of the group in this layer's epilogue
+              if (DEC && L.epi == TC_EPI_STAGE) named_bar_sync(2, EPI_THREADS);
               pe_load(jn, ln, s, cn);
               if (!between) pe_store();  // else: stored (and a_ready signalled) after that layer-slot's accumulator wait
             } else {
@@ -638,28 +741,57 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1) mlp_pp_kerne
         const int64_t ray = pt / P.S;
         const float z = P.z_vals[pt];
         float pe[64];
+        if (!DEC) {
 #pragma unroll
-        for (int cidx = 0; cidx < 3; ++cidx)
-          pe[cidx] = __fadd_rn(P.rays_o[ray * 3 + cidx], __fmul_rn(P.rays_d[ray * 3 + cidx], z));
+          for (int cidx = 0; cidx < 3; ++cidx)
+            pe[cidx] = __fadd_rn(P.rays_o[ray * 3 + cidx], __fmul_rn(P.rays_d[ray * 3 + cidx], z));
 #pragma unroll
-        for (int k = 0; k < 10; ++k) {
+          for (int k = 0; k < 10; ++k) {
+#pragma unroll
+            for (int cidx = 0; cidx < 3; ++cidx) {
+              float sv = 0.f, cv = 0.f;
+              if (k < P.multires) {
+                const float t = __fmul_rn(pe[cidx], pow2i(k));
+                const float n = rintf(t * 0.15915494309189535f);
+                float r = fmaf(-n, 6.28125f, t);
+                r = fmaf(-n, 1.9353071795864769e-3f, r);
+                sv = __sinf(r);
+                cv = __cosf(r);
+              }
+              pe[3 + 6 * k + cidx] = sv;
+              pe[6 + 6 * k + cidx] = cv;
+            }
+          }
+          pe[63] = 0.f;
+        } else {
+          // DEC:257-275: p /= 2; [sin(2^k pi p) | cos(2^k pi p)]_k, no identity term.  torch multiplies the fp32 point by
+          // fl32(2^k pi) = 2^k fl32(pi), so the argument is exactly 2^k * fl32(fl32(pi) * p); same reduction as above.
+          float a0[3];
 #pragma unroll
           for (int cidx = 0; cidx < 3; ++cidx) {
-            float sv = 0.f, cv = 0.f;
-            if (k < P.multires) {
-              const float t = __fmul_rn(pe[cidx], pow2i(k));
-              const float n = rintf(t * 0.15915494309189535f);
-              float r = fmaf(-n, 6.28125f, t);
-              r = fmaf(-n, 1.9353071795864769e-3f, r);
-              sv = __sinf(r);
-              cv = __cosf(r);
-            }
-            pe[3 + 6 * k + cidx] = sv;
-            pe[6 + 6 * k + cidx] = cv;
+            const float x = __fadd_rn(P.rays_o[ray * 3 + cidx], __fmul_rn(P.rays_d[ray * 3 + cidx], z));
+            a0[cidx] = __fmul_rn(3.14159274101257324f, __fmul_rn(x, 0.5f));
           }
+#pragma unroll
+          for (int k = 0; k < 10; ++k) {
+#pragma unroll
+            for (int cidx = 0; cidx < 3; ++cidx) {
+              float sv = 0.f, cv = 0.f;
+              if (k < P.multires) {
+                const float t = __fmul_rn(a0[cidx], pow2i(k));
+                const float n = rintf(t * 0.15915494309189535f);
+                float r = fmaf(-n, 6.28125f, t);
+                r = fmaf(-n, 1.9353071795864769e-3f, r);
+                sv = __sinf(r);
+                cv = __cosf(r);
+              }
+              pe[6 * k + cidx] = sv;
+              pe[6 * k + 3 + cidx] = cv;
+            }
+          }
+          pe[60] = pe[61] = pe[62] = pe[63] = 0.f;
         }
-        pe[63] = 0.f;
-        uint4* dst = reinterpret_cast<uint4*>(scratch + (size_t)(buf * 2 + s) * TILE_M * ROWB) + row;
+        uint4* dst = reinterpret_cast<uint4*>(scr(buf, s, 0)) + row;
 #pragma unroll
         for (int ch = 0; ch < 8; ++ch) {
           uint4 h;
@@ -692,15 +824,29 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1) mlp_pp_kerne
 }  // namespace pp
 
 int64_t pp_scratch_bytes() { return (int64_t)(num_sms() + 1) * 2 * 2 * tc::TILE_M * 256; }
+int64_t pp_dec_scratch_bytes() { return 2 * pp_scratch_bytes(); }  // two staged blocks per tile
 
-int pp_launch(const dfn_model* m, const float* bias_ws, const float* vbias_ws, void* scratch, int64_t R, int S,
-              const float* rays_o, const float* rays_d, const float* z_vals, float* raw, int precision,
-              cudaStream_t st) {
-  const dfn_model_desc& d = m->desc;
+template <bool X3, bool DEC>
+static int pp_launch_t(const pp::Params& P, int grid, cudaStream_t st) {
+  static bool attr_done = false;
+  if (!attr_done) {
+    DFN_CUDA(cudaFuncSetAttribute(pp::mlp_pp_kernel<X3, DEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, pp::SMEM_TOTAL));
+    attr_done = true;
+  }
+  pp::mlp_pp_kernel<X3, DEC><<<grid, 384, pp::SMEM_TOTAL, st>>>(P);
+  return 0;
+}
+
+// prog: layer program (woff32: per-layer offsets into the K=32 stage blobs w_hi / w_lo); decoder: Decoder programs
+// (DEC kernel instantiation, 256-wide per-ray view bias, PE of DEC:257-275 with n_freq = multires).
+int pp_launch_prog(const TcProgram& prog, const uint32_t* woff32, const uint8_t* w_hi, const uint8_t* w_lo, bool decoder,
+                   int multires, int view_w, const float* bias_ws, const float* vbias_ws, void* scratch, int64_t R, int S,
+                   const float* rays_o, const float* rays_d, const float* z_vals, float* raw, int precision,
+                   cudaStream_t st) {
   pp::Params P;
   memset(&P, 0, sizeof(P));
-  P.w_hi = m->tc_hi;
-  P.w_lo = m->tc_lo;
+  P.w_hi = w_hi;
+  P.w_lo = w_lo;
   P.bias = bias_ws;
   P.view_bias = vbias_ws;
   P.rays_o = rays_o;
@@ -712,32 +858,26 @@ int pp_launch(const dfn_model* m, const float* bias_ws, const float* vbias_ws, v
   P.n_points = R * S;
   P.S = S;
   P.n_tiles = (int)((P.n_points + tc::TILE_M - 1) / tc::TILE_M);
-  P.n_layers = m->prog.n_layers;
-  P.multires = d.multires;
-  P.view_w = d.W / 2;
-  for (int i = 0; i < m->prog.n_layers; ++i) {
-    P.layers[i] = m->prog.layers[i];
-    P.layers[i].woff = m->tc32_woff[i];
+  P.n_layers = prog.n_layers;
+  P.multires = multires;
+  P.view_w = view_w;
+  for (int i = 0; i < prog.n_layers; ++i) {
+    P.layers[i] = prog.layers[i];
+    P.layers[i].woff = woff32[i];
   }
   int grid = P.n_tiles < num_sms() ? P.n_tiles : num_sms();
   grid = (grid + 1) & ~1;
   if (grid > num_sms()) grid = num_sms() & ~1;
-  if (precision == DFN_PREC_BF16) {
-    static bool attr_done = false;
-    if (!attr_done) {
-      DFN_CUDA(cudaFuncSetAttribute(pp::mlp_pp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, pp::SMEM_TOTAL));
-      attr_done = true;
-    }
-    pp::mlp_pp_kernel<false><<<grid, 384, pp::SMEM_TOTAL, st>>>(P);
-  } else {
-    static bool attr_done = false;
-    if (!attr_done) {
-      DFN_CUDA(cudaFuncSetAttribute(pp::mlp_pp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, pp::SMEM_TOTAL));
-      attr_done = true;
-    }
-    pp::mlp_pp_kernel<true><<<grid, 384, pp::SMEM_TOTAL, st>>>(P);
-  }
-  return 0;
+  const bool x3 = precision == DFN_PREC_BF16X3;
+  if (decoder) return x3 ? pp_launch_t<true, true>(P, grid, st) : pp_launch_t<false, true>(P, grid, st);
+  return x3 ? pp_launch_t<true, false>(P, grid, st) : pp_launch_t<false, false>(P, grid, st);
+}
+
+int pp_launch(const dfn_model* m, const float* bias_ws, const float* vbias_ws, void* scratch, int64_t R, int S,
+              const float* rays_o, const float* rays_d, const float* z_vals, float* raw, int precision,
+              cudaStream_t st) {
+  return pp_launch_prog(m->prog, m->tc32_woff, m->tc_hi, m->tc_lo, false, m->desc.multires, m->desc.W / 2, bias_ws, vbias_ws,
+                        scratch, R, S, rays_o, rays_d, z_vals, raw, precision, st);
 }
 
 }  // namespace dfn

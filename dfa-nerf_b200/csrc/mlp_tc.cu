@@ -26,6 +26,7 @@
 #include "common.cuh"
 #include "model.h"
 #include "tc_ptx.cuh"
+#include "tc_pack.h"
 
 namespace dfn {
 namespace tc {
@@ -468,73 +469,6 @@ __global__ void view_bias_kernel(int64_t R, int Wh, int ncol, int L, const float
     }
   }
 }
-
-// ------------------------------------------------------------------------ host: weight packing
-static inline uint16_t f2bf(float f) {  // round-to-nearest-even, as cvt.rn.bf16.f32
-  uint32_t u;
-  memcpy(&u, &f, 4);
-  if ((u & 0x7F800000u) == 0x7F800000u) return (uint16_t)(u >> 16);
-  u += 0x7FFFu + ((u >> 16) & 1u);
-  return (uint16_t)(u >> 16);
-}
-static inline float bf2f(uint16_t h) {
-  uint32_t u = (uint32_t)h << 16;
-  float f;
-  memcpy(&f, &u, 4);
-  return f;
-}
-
-struct Packer {
-  std::vector<uint8_t> hi, lo;       // [<=128 rows x 64 K] stages, 128-byte swizzle (mlp_ts.cu)
-  std::vector<uint8_t> hi32, lo32;   // [n rows x 32 K] stages, 64-byte swizzle (mlp_tc.cu)
-  uint32_t last32 = 0;               // offset of the last layer added to hi32
-  // Appends the stages of one layer: for each K-block, for each chunk of <=128 output rows, a
-  // [rows x 64] bf16 image in the swizzled K-major layout.  wfun(n, kbi, k) returns W[n][column
-  // of K-block kbi, position k] or 0.
-  template <class F>
-  uint32_t add_layer(int n_out, int nkb, F wfun) {
-    const uint32_t start = (uint32_t)hi.size();
-    for (int kbi = 0; kbi < nkb; ++kbi) {
-      for (int c0 = 0; c0 < n_out; c0 += 128) {
-        const int rows = n_out - c0 < 128 ? n_out - c0 : 128;
-        const size_t base = hi.size();
-        hi.resize(base + (size_t)rows * 128, 0);
-        lo.resize(base + (size_t)rows * 128, 0);
-        for (int r = 0; r < rows; ++r) {
-          for (int k = 0; k < 64; ++k) {
-            const float w = wfun(c0 + r, kbi, k);
-            const uint16_t h = f2bf(w);
-            const uint16_t l = f2bf(w - bf2f(h));
-            const size_t o = base + (size_t)r * 128 + ((((size_t)k >> 3) ^ ((size_t)r & 7)) << 4) + ((size_t)k & 7) * 2;
-            memcpy(&hi[o], &h, 2);
-            memcpy(&lo[o], &l, 2);
-          }
-        }
-      }
-    }
-    // K = 32 stages: for each K-block, for each half of it, all n_out rows x 32 K; 64-byte rows, 16-byte
-    // chunk index XORed with (row >> 1) & 3 (cute Swizzle<2,4,3>), 8-row groups 512 bytes apart.
-    last32 = (uint32_t)hi32.size();
-    for (int kbi = 0; kbi < nkb; ++kbi) {
-      for (int kh = 0; kh < 2; ++kh) {
-        const size_t base = hi32.size();
-        hi32.resize(base + (size_t)n_out * 64, 0);
-        lo32.resize(base + (size_t)n_out * 64, 0);
-        for (int r = 0; r < n_out; ++r) {
-          for (int k = 0; k < 32; ++k) {
-            const float w = wfun(r, kbi, kh * 32 + k);
-            const uint16_t h = f2bf(w);
-            const uint16_t l = f2bf(w - bf2f(h));
-            const size_t o = base + (size_t)r * 64 + ((((size_t)k >> 3) ^ (((size_t)r >> 1) & 3)) << 4) + ((size_t)k & 7) * 2;
-            memcpy(&hi32[o], &h, 2);
-            memcpy(&lo32[o], &l, 2);
-          }
-        }
-      }
-    }
-    return start;
-  }
-};
 
 }  // namespace tc
 

@@ -16,20 +16,33 @@ struct Fp32Layer {
 // ---- tcgen05 path: per-layer program -------------------------------------------------------
 // A operand blocks ("K-blocks") are [128 rows x 64 bf16] tiles in the 128-byte-swizzled K-major
 // layout.  Per tile slot: blocks 0..3 hold the 256-wide hidden state h, block 4 the positional
-// encoding of xyz (63 columns + one zero column).
-enum { TC_KB_H0 = 0, TC_KB_PE = 4, TC_KB_PER_TILE = 5 };
-enum { TC_EPI_RELU = 0, TC_EPI_VIEW0 = 1, TC_EPI_RGB = 2 };
-static constexpr int TC_MAX_LAYERS = 14;
+// encoding of xyz (63 columns + one zero column).  Block ids >= TC_KB_PE are "staged" inputs: in mlp_pp.cu
+// they live in an L2-resident scratch and pass through a weight-ring entry right before the layer that
+// consumes them (TC_KB_PE: the positional encoding; TC_KB_IN1: the deformed per-sample signal of the torso
+// field, DEC:297-299).  A layer has at most one staged input block.
+enum { TC_KB_H0 = 0, TC_KB_PE = 4, TC_KB_IN1 = 5, TC_KB_PER_TILE = 5 };
+enum {
+  TC_EPI_RELU = 0,   // + bias, relu -> hidden blocks H0..
+  TC_EPI_VIEW0 = 1,  // + per-ray bias, relu -> hidden blocks (FaceNeRF/NeRF: density rides as column view_w)
+  TC_EPI_RGB = 2,    // last layer: (rgb, density) -> raw[pt]
+  TC_EPI_SIGMA = 3,  // Decoder: column 0 + bias -> density register, nothing stored (DEC:329)
+  TC_EPI_CONT = 4,   // no epilogue: the next layer accumulates onto this one's partial sums (second staged input)
+  TC_EPI_STAGE = 5   // + bias, no activation -> staged blocks PE / IN1 of the tile (deformation output, DEC:299)
+};
+enum { TC_F_ACCUM = 1 };  // TcLayer.flags: the first MMA accumulates (layer continues a TC_EPI_CONT layer)
+static constexpr int TC_MAX_LAYERS = 20;
 static constexpr int TC_BIAS_STRIDE = 256;  // floats per layer in the bias blob
 
 struct TcLayer {
   uint32_t woff;     // byte offset of this layer's first weight stage in the (hi) blob
   uint16_t n;        // output columns computed by the MMAs (multiple of 16)
   uint8_t nkb;       // number of input K-blocks
-  uint8_t kb[5];     // their block ids, in weight order
+  uint8_t kb[6];     // their block ids, in weight order
   uint8_t epi;       // TC_EPI_*
-  uint8_t pad[3];
+  uint8_t flags;     // TC_F_*
+  uint8_t pad;
 };
+static_assert(sizeof(TcLayer) == 16, "TcLayer is passed by value in kernel parameters");
 
 struct TcProgram {
   int n_layers = 0;
@@ -73,6 +86,11 @@ void tc_set_trace(void* dev_ptr, int tiles);
 void tc_get_trace(void** dev_ptr, int* tiles);
 void tc_set_impl(int impl);  // 2: ping-pong + cooperative epilogue (mlp_pp.cu, default); 1: mlp_tc.cu; 0: mlp_ts.cu
 int64_t pp_scratch_bytes();
+int64_t pp_dec_scratch_bytes();
+int pp_launch_prog(const TcProgram& prog, const uint32_t* woff32, const uint8_t* w_hi, const uint8_t* w_lo, bool decoder,
+                   int multires, int view_w, const float* bias_ws, const float* vbias_ws, void* scratch, int64_t R, int S,
+                   const float* rays_o, const float* rays_d, const float* z_vals, float* raw, int precision,
+                   cudaStream_t st);
 int pp_launch(const dfn_model* m, const float* bias_ws, const float* vbias_ws, void* scratch, int64_t R, int S,
               const float* rays_o, const float* rays_d, const float* z_vals, float* raw, int precision,
               cudaStream_t st);

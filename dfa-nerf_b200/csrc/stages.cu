@@ -309,9 +309,11 @@ __global__ void volume_weights_kernel(int R, int S, const float* __restrict__ sr
 // head-only image, torso for the person image); two-field mix den = s_h + s_t (0 -> 1e-4),
 // feat = f_h*(s_h/den) + f_t*(s_t/den), sigma = s_h + s_t (MAIN:146-166); weights with the head rays' norm for
 // the head image and the torso rays' norm for the person image (MAIN:704-705); rgb = sum w*feat.
-__global__ void head_torso_kernel(int R, int S, const float* __restrict__ feat_h, const float* __restrict__ sig_h,
-                                  const float* __restrict__ feat_t, const float* __restrict__ sig_t,
-                                  const float* __restrict__ bc_rgb, const float* __restrict__ z_vals,
+// feat_* / sig_* are addressed with element strides (3 and 1 for separate tensors; 4 and 4 for the fused kernels'
+// interleaved raw [R,S,4] = (feat, sigma)).
+__global__ void head_torso_kernel(int R, int S, const float* __restrict__ feat_h, int fs_h, const float* __restrict__ sig_h,
+                                  int ss_h, const float* __restrict__ feat_t, int fs_t, const float* __restrict__ sig_t,
+                                  int ss_t, const float* __restrict__ bc_rgb, const float* __restrict__ z_vals,
                                   const float* __restrict__ rays_d_h, const float* __restrict__ rays_d_t,
                                   float last_dist, float* __restrict__ rgb_head, float* __restrict__ rgb_person) {
   const int lane = threadIdx.x & 31;
@@ -336,15 +338,15 @@ __global__ void head_torso_kernel(int R, int S, const float* __restrict__ feat_h
       if (k < seg && s < S) {
         const int64_t i = (int64_t)ray * S + s;
         const bool last = s == S - 1;
-        float fh[3] = {feat_h[i * 3], feat_h[i * 3 + 1], feat_h[i * 3 + 2]};
+        float fh[3] = {feat_h[i * fs_h], feat_h[i * fs_h + 1], feat_h[i * fs_h + 2]};
         if (last) {
           fh[0] = bc_rgb[ray * 3];
           fh[1] = bc_rgb[ray * 3 + 1];
           fh[2] = bc_rgb[ray * 3 + 2];
         }
-        const float ft[3] = {feat_t[i * 3], feat_t[i * 3 + 1], feat_t[i * 3 + 2]};
-        const float sh = fmaxf(sig_h[i], 0.f);
-        float st = last ? 0.f : fmaxf(sig_t[i], 0.f);
+        const float ft[3] = {feat_t[i * fs_t], feat_t[i * fs_t + 1], feat_t[i * fs_t + 2]};
+        const float sh = fmaxf(sig_h[i * ss_h], 0.f);
+        float st = last ? 0.f : fmaxf(sig_t[i * ss_t], 0.f);
         const float sh1 = last ? __fadd_rn(sh, 1e-6f) : sh;  // head-only stack: the head is the last field
         if (last) st = __fadd_rn(st, 1e-6f);                  // two-field stack: the torso is the last field
         float den = __fadd_rn(sh, st);
@@ -626,9 +628,17 @@ extern "C" int dfn_composite_head_torso(int R, int S, const float* feat_head, co
   DFN_CHECK_ARG(R > 0 && S > 0 && S <= 32 * kMaxSeg && feat_head && sigma_head && feat_torso && sigma_torso && bc_rgb &&
                     z_vals && rays_d_head && rays_d_torso,
                 "dfn_composite_head_torso: bad argument (S <= 256)");
-  head_torso_kernel<<<rays_grid(R, 8), 256, 0, (cudaStream_t)stream>>>(R, S, feat_head, sigma_head, feat_torso, sigma_torso,
-                                                                      bc_rgb, z_vals, rays_d_head, rays_d_torso, last_dist,
-                                                                      rgb_head, rgb_person);
+  return launch_head_torso(R, S, feat_head, 3, sigma_head, 1, feat_torso, 3, sigma_torso, 1, bc_rgb, z_vals, rays_d_head,
+                           rays_d_torso, last_dist, rgb_head, rgb_person, (cudaStream_t)stream);
+}
+
+int dfn::launch_head_torso(int R, int S, const float* feat_h, int fstride_h, const float* sig_h, int sstride_h,
+                           const float* feat_t, int fstride_t, const float* sig_t, int sstride_t, const float* bc_rgb,
+                           const float* z_vals, const float* rays_d_h, const float* rays_d_t, float last_dist,
+                           float* rgb_head, float* rgb_person, cudaStream_t st) {
+  head_torso_kernel<<<rays_grid(R, 8), 256, 0, st>>>(R, S, feat_h, fstride_h, sig_h, sstride_h, feat_t, fstride_t, sig_t,
+                                                    sstride_t, bc_rgb, z_vals, rays_d_h, rays_d_t, last_dist, rgb_head,
+                                                    rgb_person);
   DFN_LAUNCH_CHECK();
   return 0;
 }

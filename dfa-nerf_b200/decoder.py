@@ -1,18 +1,24 @@
 """The reference's live radiance model: ``Decoder`` + ``DeformationField_ori`` (DEC:77-134, DEC:137-349), with the
-reference's parameter names so ``load_state_dict`` of its checkpoints works.  ``forward`` composes the CUDA fp32
-building blocks of libdfn (dfn_embed for DEC:257-275, dfn_linear for every nn.Linear with the skip / latent / view
-terms fused as biases and addends); no torch arithmetic touches the per-point tensors.  Inference only.
+reference's parameter names so ``load_state_dict`` of its checkpoints works.  Inference only.  Two paths:
+
+* ``forward`` (explicit points, the reference's signature) composes the CUDA fp32 building blocks of libdfn
+  (dfn_embed for DEC:257-275, dfn_linear for every nn.Linear with the skip / latent / view terms fused as biases
+  and addends); no torch arithmetic touches the per-point tensors.
+* ``query_rays`` / ``render_head_torso`` (rays) run the fused tcgen05 kernel (dfn_decoder_query,
+  dfn_render_head_torso): encoding, deformation field, trunk, density and colour heads of a whole chunk in one
+  launch per field, nothing but raw [R,S,4] leaving the SMs.
 
 ``render_head_torso`` is one chunk of the live render loop (MAIN:633-708): head and torso fields, background
-splice, two-field density mix, weights and colour sums (dfn_composite_head_torso).
+splice, two-field density mix, weights and colour sums.
 """
 import ctypes as C
 
 import torch
 import torch.nn as nn
 
-from ._lib import lib, check, dev, ptr, stream_ptr, DfnError
-from .functional import decoder_transform_points, get_rays, z_vals_uniform, make_points
+from . import _lib
+from ._lib import lib, check, dev, ptr, stream_ptr, DfnError, DecoderDesc, HeadTorsoIO, Workspace
+from .functional import decoder_transform_points, get_rays, z_vals_uniform, make_points, linspace_table
 
 
 def _linear(P, N, X1, ld1, K1, W, bias, act=0, X2=None, ld2=0, K2=0, addend=None, ld_add=0, out=None, ldy=None):
@@ -106,6 +112,83 @@ class Decoder(nn.Module):
     def transform_points(self, p, views=False):
         return decoder_transform_points(p, self.n_freq_posenc_views if views else self.n_freq_posenc)
 
+    # -- libdfn handle of the fused tcgen05 path ------------------------------------------------------------
+    def _tensor_list(self):
+        """{weight, bias} in the load order of dfn_decoder_load (include/dfn.h)."""
+        if not self.use_deformation_field:
+            raise DfnError('Decoder: the fused path needs use_deformation_field=True (MAIN:518)')
+        dn = self.deform_net
+        mods = list(dn.blocks_embed) + [dn.out_embed] + list(dn.blocks_signal) + [dn.out_signal, dn.fc_embed_skips[0],
+                                                                                  dn.fc_signal_skips[0]]
+        mods += [self.fc_in, self.fc_in_torso, self.fc_z] + list(self.blocks)
+        mods += [self.fc_z_skips[0], self.fc_p_skips[0], self.fc_p_skips_torso[0], self.sigma_out, self.fc_z_view,
+                 self.feat_view, self.fc_view, self.feat_out]
+        out = []
+        for m in mods:
+            out += [m.weight, m.bias]
+        return out
+
+    def dfn_handle(self, device=None):
+        """Creates the native decoder on first use and re-uploads when parameters changed."""
+        params = self._tensor_list()
+        device = device or params[0].device
+        if torch.device(device).type != 'cuda':
+            raise DfnError('dfa_nerf_b200 has no CPU path: move the module to CUDA')
+        sig = (str(device),) + tuple((p.data_ptr(), p._version) for p in params)
+        if getattr(self, '_handle', None) is not None and sig == self._loaded_sig:
+            return self._handle
+        if getattr(self, '_handle', None) is None:
+            if list(self.skips) != [4]:
+                raise DfnError('Decoder: the fused path covers skips=[4]')
+            desc = DecoderDesc(self.hidden_size, self.z_dim, self.dim_signal, self.dim_et_embed, self.n_freq_posenc,
+                               self.n_freq_posenc_views, self.n_blocks, 4)
+            h = C.c_void_p()
+            check(lib.dfn_decoder_create(C.byref(desc), C.byref(h)), 'dfn_decoder_create')
+            self._handle = h
+        host = [p.detach().to('cpu', torch.float32).contiguous() for p in params]
+        arr = (C.c_void_p * len(host))(*[t.data_ptr() for t in host])
+        with torch.cuda.device(device):
+            check(lib.dfn_decoder_load(self._handle, arr, len(host), stream_ptr()), 'dfn_decoder_load')
+        self._loaded_sig = sig
+        return self._handle
+
+    def __del__(self):
+        h = getattr(self, '_handle', None)
+        if h is not None:
+            try:
+                lib.dfn_decoder_destroy(h)
+            except Exception:
+                pass
+
+    @torch.no_grad()
+    def query_rays(self, rays_o, rays_d, z_vals, z_shape, z_app, signal, head_or_torso, precision=_lib.PREC_BF16X3):
+        """Fused field query for pts = rays_o + rays_d*z (MAIN:638-641 + DEC:277-349): rays_o, rays_d [R,3] (rays_d
+        un-normalised), z_vals [R,S] -> (feat [R,S,3] after the sigmoid, sigma [R,S] before MAIN:688's relu)."""
+        if head_or_torso not in ('head', 'torso'):
+            raise Exception('Do not give head or torso!!')
+        if isinstance(signal, (list, tuple)):
+            signal = signal[0]
+        rays_o, p_o = dev(rays_o, 'rays_o')
+        rays_d, p_d = dev(rays_d, 'rays_d')
+        z_vals, p_z = dev(z_vals, 'z_vals')
+        z_shape, p_zs = dev(z_shape.reshape(-1), 'z_shape')
+        z_app, p_za = dev(z_app.reshape(-1), 'z_app')
+        signal, p_s = dev(signal.reshape(-1), 'signal')
+        field = 0 if head_or_torso == 'head' else 1
+        if z_shape.numel() != self.z_dim or z_app.numel() != self.z_dim or \
+                signal.numel() != (self.dim_signal if field == 0 else self.dim_et_embed):
+            raise DfnError('Decoder.query_rays: latent sizes do not match the module')
+        d = rays_o.device
+        R, S = z_vals.shape
+        h = self.dfn_handle(d)
+        raw = torch.empty((R, S, 4), dtype=torch.float32, device=d)
+        nbytes = lib.dfn_decoder_query_workspace_bytes(h, R, S)
+        ws = Workspace.get(nbytes, d, 'decoder')
+        with torch.cuda.device(d):
+            check(lib.dfn_decoder_query(h, field, R, S, p_o, p_d, p_z, p_zs, p_za, p_s, ptr(raw), int(precision), ptr(ws),
+                                        nbytes, stream_ptr()), 'dfn_decoder_query')
+        return raw[..., :3], raw[..., 3]
+
     @torch.no_grad()
     def forward(self, p_in, ray_d, z_shape=None, z_app=None, signal=None, head_or_torso=None):
         """p_in, ray_d [1,P,3]; z_shape, z_app [1,z_dim]; signal [1,dim_signal] (head; a [signal, None] list as the
@@ -158,15 +241,42 @@ class Decoder(nn.Module):
 
 @torch.no_grad()
 def render_head_torso(decoder, H, W, focal, c2w_head, c2w_torso, bc_rgb, z_shape, z_app, signal, signal_torso, near, far,
-                      cx=None, cy=None, N_samples=64, ray_range=None, last_dist=1e10):
+                      cx=None, cy=None, N_samples=64, ray_range=None, last_dist=1e10, precision=_lib.PREC_BF16X3):
     """One frame (or ray range) of the reference's live loop MAIN:633-708: returns (rgb_head, rgb_person) [R,3].
-    z_shape / z_app: [1,2,z_dim] (index 0 head, 1 torso, MAIN:664-674)."""
+    z_shape / z_app: [1,2,z_dim] (index 0 head, 1 torso, MAIN:664-674).
+    precision PREC_BF16 / PREC_BF16X3: the fused tcgen05 path (dfn_render_head_torso, 5 launches per call);
+    PREC_FP32: the explicit-points Decoder.forward built from the fp32 FFMA blocks."""
     device = bc_rgb.device
     ro, rd = get_rays(H, W, focal, c2w_head, cx, cy, device=device)
     rot, rdt = get_rays(H, W, focal, c2w_torso, cx, cy, device=device)
     b, e = ray_range if ray_range is not None else (0, H * W)
     ro, rd, rot, rdt = [t.reshape(-1, 3)[b:e].contiguous() for t in (ro, rd, rot, rdt)]
     R = e - b
+    if precision != _lib.PREC_FP32:
+        if isinstance(signal, (list, tuple)):
+            signal = signal[0]
+        io = HeadTorsoIO()
+        nr = torch.full((R,), float(near), device=device)
+        fr = torch.full((R,), float(far), device=device)
+        t_vals = linspace_table(N_samples, device)
+        bc, io.bc_rgb = dev(bc_rgb.reshape(-1, 3)[b:e], 'bc_rgb')
+        zs, io.z_shape = dev(z_shape.reshape(2, -1), 'z_shape')
+        za, io.z_app = dev(z_app.reshape(2, -1), 'z_app')
+        sg, io.signal = dev(signal.reshape(-1), 'signal')
+        sgt, io.signal_torso = dev(signal_torso.reshape(-1), 'signal_torso')
+        io.rays_o_head, io.rays_d_head, io.rays_o_torso, io.rays_d_torso = ptr(ro), ptr(rd), ptr(rot), ptr(rdt)
+        io.near, io.far, io.t_vals = ptr(nr), ptr(fr), ptr(t_vals)
+        rgb_head = torch.empty((R, 3), dtype=torch.float32, device=device)
+        rgb_person = torch.empty((R, 3), dtype=torch.float32, device=device)
+        io.rgb_head, io.rgb_person, io.last_dist = ptr(rgb_head), ptr(rgb_person), float(last_dist)
+        h = decoder.dfn_handle(device)
+        nbytes = lib.dfn_render_head_torso_workspace_bytes(h, R, N_samples)
+        ws = Workspace.get(nbytes, device, 'head_torso')
+        with torch.cuda.device(device):
+            check(lib.dfn_render_head_torso(h, R, N_samples, C.byref(io), int(precision), ptr(ws), nbytes, stream_ptr()),
+                  'dfn_render_head_torso')
+        render_head_torso.last_launches = lib.dfn_last_launch_count() + 2       # + the two get_rays
+        return rgb_head, rgb_person
     z = z_vals_uniform(torch.full((R,), float(near), device=device), torch.full((R,), float(far), device=device), N_samples)
     # points: o + d*z (MAIN:638-651); the Decoder takes explicit points, so they are materialised here
     p, r = [t.reshape(1, -1, 3) for t in make_points(ro, rd, z)]

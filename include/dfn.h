@@ -169,6 +169,70 @@ int dfn_query_points(const dfn_model* m, int64_t R, int S, const float* rays_o, 
                      const float* viewdirs, const float* z_vals, const float* latent, float* raw,
                      int precision, void* workspace, int64_t workspace_bytes, void* stream);
 
+/* ---- a5''  Decoder + DeformationField_ori on the tensor cores  (DEC:77-134, DEC:137-349) ---------------
+ * The reference's LIVE model (MAIN:518: Decoder(z_dim=256, hidden_size=256, dim_signal=96, use_deformation_field)).
+ * dfn_decoder_query is the fused network query of one field for pts = rays_o + rays_d*z: positional encoding of
+ * DEC:257-275, per-frame latents (signal, z_shape, z_app) and the per-ray view term folded into biases, the torso's
+ * deformation field in front of its trunk; raw [R,S,4] = (feat after the sigmoid of DEC:346-347, sigma before the relu
+ * of MAIN:688).  rays_d is NOT normalised by the caller (DEC:337 normalises the view direction itself). */
+typedef struct dfn_decoder dfn_decoder;
+
+typedef struct {
+  int hidden;        /* 256 */
+  int z_dim;         /* 256 */
+  int dim_signal;    /* 96  head signal (scripts/test_obama.sh:8) */
+  int dim_et_embed;  /* 42  torso signal */
+  int n_freq;        /* 10  n_freq_posenc */
+  int n_freq_views;  /* 4   n_freq_posenc_views */
+  int n_blocks;      /* 8 */
+  int skip;          /* 4   skips=[4] */
+} dfn_decoder_desc;
+
+int dfn_decoder_create(const dfn_decoder_desc* desc, dfn_decoder** out);
+void dfn_decoder_destroy(dfn_decoder* m);
+
+/* 64 HOST fp32 tensors, {weight, bias} of the reference's modules in this order:
+ * deform_net.blocks_embed.{0..4}, deform_net.out_embed, deform_net.blocks_signal.{0..4}, deform_net.out_signal,
+ * deform_net.fc_embed_skips.0, deform_net.fc_signal_skips.0, fc_in, fc_in_torso, fc_z, blocks.{0..6}, fc_z_skips.0,
+ * fc_p_skips.0, fc_p_skips_torso.0, sigma_out, fc_z_view, feat_view, fc_view, feat_out. */
+int dfn_decoder_num_tensors(const dfn_decoder* m);
+int dfn_decoder_load(dfn_decoder* m, const float* const* tensors_host, int n_tensors, void* stream);
+
+/* field: 0 head (signal [dim_signal]), 1 torso (signal [dim_et_embed]); z_shape, z_app [z_dim];
+ * precision: DFN_PREC_BF16 or DFN_PREC_BF16X3. */
+int64_t dfn_decoder_query_workspace_bytes(const dfn_decoder* m, int64_t R, int S);
+int dfn_decoder_query(const dfn_decoder* m, int field, int64_t R, int S, const float* rays_o, const float* rays_d,
+                      const float* z_vals, const float* z_shape, const float* z_app, const float* signal, float* raw,
+                      int precision, void* workspace, int64_t workspace_bytes, void* stream);
+/* algorithmic MACs per sample of a field with the per-frame and per-ray terms folded (roofline accounting) */
+double dfn_decoder_macs_per_sample(const dfn_decoder* m, int field);
+
+/* ---- one chunk of the live render loop  (MAIN:617-619, MAIN:633-708) ----------------------------------
+ * z sampling -> head field on the head-pose rays, torso field (with deformation) on the body-pose rays ->
+ * background splice, two-field density mix, weights, colour sums.  z_shape / z_app: [2, z_dim] (row 0 head,
+ * row 1 torso, MAIN:664-674).  Outputs (each nullable): rgb_head [R,3], rgb_person [R,3]. */
+typedef struct {
+  const float* rays_o_head;
+  const float* rays_d_head;
+  const float* rays_o_torso;
+  const float* rays_d_torso;
+  const float* near;
+  const float* far;
+  const float* t_vals;
+  const float* bc_rgb;
+  const float* z_shape;
+  const float* z_app;
+  const float* signal;
+  const float* signal_torso;
+  float* rgb_head;
+  float* rgb_person;
+  float last_dist; /* <= 0: 1e10 (MAIN:169) */
+} dfn_head_torso_io;
+
+int64_t dfn_render_head_torso_workspace_bytes(const dfn_decoder* m, int64_t R, int S);
+int dfn_render_head_torso(const dfn_decoder* m, int64_t R, int S, const dfn_head_torso_io* io, int precision,
+                          void* workspace, int64_t workspace_bytes, void* stream);
+
 /* ---- render_rays  (upstream name; MAIN:114 is the reference's dead stub) -----------------------
  * coarse pass (N_samples) -> raw2outputs -> sample_pdf(z_mid, w[1:-1], N_importance) -> sort-merge
  * -> fine pass (N_samples+N_importance) with `fine` (or `coarse` when null) -> raw2outputs.
@@ -218,7 +282,7 @@ int dfn_profile_enable(int on);
 
 /* Debug timeline of the tcgen05 kernel: while dev_buffer is non-null, CTA 0 records clock64 stamps for its
  * first `tiles` tile iterations: [MMA issuer | epilogue] x [tile][layer][slot] x {wait begin, wait end,
- * done, aux} (uint64 each; 2*tiles*14*2*4 entries at most).  Pass null to switch it off. */
+ * done, aux} (uint64 each; 2*tiles*20*2*4 entries at most).  Pass null to switch it off. */
 int dfn_debug_trace(void* dev_buffer, int tiles);
 
 /* Selects the tcgen05 kernel variant (A/B measurements): -1 (default) the fastest measured per precision

@@ -81,7 +81,8 @@ def test_head_torso_frame_golden(dfn, golden):
     dec = make_decoder(dfn, g['seed'])
     rgb_head, rgb_person = dfn.render_head_torso(
         dec, g['H'], g['W'], g['focal'], g['c2w'], g['c2w_torso'], g['bc_rgb'].to(DEV), g['z_shape'].to(DEV),
-        g['z_app'].to(DEV), g['signal'].to(DEV), g['signal_torso'].to(DEV), g['near'], g['far'], g['cx'], g['cy'])
+        g['z_app'].to(DEV), g['signal'].to(DEV), g['signal_torso'].to(DEV), g['near'], g['far'], g['cx'], g['cy'],
+        precision=dfn.PREC_FP32)
     assert maxerr(rgb_head, g['rgb_head']) < 1e-5
     assert maxerr(rgb_person, g['rgb_person']) < 1e-5
 

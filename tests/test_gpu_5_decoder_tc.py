@@ -1,0 +1,121 @@
+"""GPU parity of the reference's LIVE model on the tensor cores: Decoder + DeformationField_ori (DEC:77-349) as
+layer programs of the tcgen05 kernel (dfn_decoder_query), and the fused live chunk of MAIN:633-708
+(dfn_render_head_torso).  bf16x3 is gated against the fp32 oracle at the north star's 1e-4 on what compositing
+consumes (weights, colours) and on the rendered pixels; bf16 (throughput mode) is reported and loosely gated."""
+import pytest
+import torch
+
+from oracle import nerf_oracle as O
+from oracle import synth
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda'
+
+
+def maxerr(a, b):
+    return (a.detach().cpu().double() - b.detach().cpu().double()).abs().max().item()
+
+
+@pytest.fixture(scope='module')
+def dfn():
+    import dfa_nerf_b200
+    return dfa_nerf_b200
+
+
+def make_decoder(dfn, seed):
+    m = dfn.Decoder(z_dim=256, hidden_size=256, dim_signal=96, use_deformation_field=True)
+    m.load_state_dict(synth.decoder_state_dict(seed))
+    return m.to(DEV)
+
+
+def _case(R, S, seed):
+    g = torch.Generator().manual_seed(seed)
+    fr = synth.frame_inputs(H=R, W=1, seed=seed)
+    ro = fr['c2w'][:3, -1].expand(R, 3).contiguous()
+    rd = torch.randn(R, 3, generator=g) * 0.2 + torch.tensor([0., 0., -1.])
+    z, _ = torch.sort(torch.rand(R, S, generator=g) * 0.6 + 0.4, -1)
+    zs, za = torch.randn(1, 256, generator=g), torch.randn(1, 256, generator=g)
+    return ro, rd, z, zs, za, torch.randn(1, 96, generator=g), torch.randn(1, 42, generator=g)
+
+
+def _oracle(sd, ro, rd, z, zs, za, sig, which):
+    R, S = z.shape
+    p = (ro[:, None, :] + rd[:, None, :] * z[:, :, None]).reshape(1, -1, 3)
+    r = rd[:, None, :].expand(R, S, 3).reshape(1, -1, 3)
+    with torch.no_grad():
+        f, s = O.decoder_forward(sd, p, r, zs, za, sig, which)
+    return f.reshape(R, S, 3), s.reshape(R, S)
+
+
+def _weights_err(sig, ref, z, rd):
+    w = O.calc_volume_weights(z[None], rd[None], torch.relu(sig.cpu())[None])
+    wr = O.calc_volume_weights(z[None], rd[None], torch.relu(ref)[None])
+    return maxerr(w, wr)
+
+
+@pytest.mark.parametrize('which', ['head', 'torso'])
+@pytest.mark.parametrize('R,S', [(1, 64), (37, 64), (300, 64), (21, 192)])
+def test_decoder_query_bf16x3_vs_fp32_oracle(dfn, which, R, S):
+    seed = 3
+    sd = synth.decoder_state_dict(seed)
+    dec = make_decoder(dfn, seed)
+    ro, rd, z, zs, za, sg_h, sg_t = _case(R, S, seed + R)
+    sig = sg_h if which == 'head' else sg_t
+    rf, rs = _oracle(sd, ro, rd, z, zs, za, sig, which)
+    f, s = dec.query_rays(ro.to(DEV), rd.to(DEV), z.to(DEV), zs.to(DEV), za.to(DEV), sig.to(DEV), which,
+                          precision=dfn.PREC_BF16X3)
+    assert f.shape == (R, S, 3) and s.shape == (R, S) and torch.isfinite(f).all() and torch.isfinite(s).all()
+    ef, ew, es = maxerr(f, rf), _weights_err(s, rs, z, rd), maxerr(s, rs)
+    print('decoder %s bf16x3 R=%d S=%d: feat err %.2e, weights err %.2e, raw sigma err %.2e (|sigma| max %.1f)'
+          % (which, R, S, ef, ew, es, rs.abs().max().item()))
+    assert ef < 1e-4 and ew < 1e-4, (ef, ew)      # north-star tolerance: 1e-4 max-abs
+
+
+@pytest.mark.parametrize('which', ['head', 'torso'])
+def test_decoder_query_bf16_reported(dfn, which):
+    """Throughput mode: 8-bit mantissas on every operand; gated loosely, error printed."""
+    R, S, seed = 200, 64, 4
+    sd = synth.decoder_state_dict(seed)
+    dec = make_decoder(dfn, seed)
+    ro, rd, z, zs, za, sg_h, sg_t = _case(R, S, seed)
+    sig = sg_h if which == 'head' else sg_t
+    rf, rs = _oracle(sd, ro, rd, z, zs, za, sig, which)
+    f, s = dec.query_rays(ro.to(DEV), rd.to(DEV), z.to(DEV), zs.to(DEV), za.to(DEV), sig.to(DEV), which,
+                          precision=dfn.PREC_BF16)
+    assert torch.isfinite(f).all() and torch.isfinite(s).all()
+    ef, es = maxerr(f, rf), maxerr(s, rs)
+    rel = es / rs.abs().max().item()
+    print('decoder %s bf16: feat err %.2e, sigma err %.2e (%.2e of max |sigma|)' % (which, ef, es, rel))
+    assert ef < 5e-2 and rel < 5e-2
+
+
+def test_decoder_query_matches_fp32_blocks_at_scale(dfn):
+    """Chunk-sized cross-check on the device: 2,048 rays x 64 samples (the reference's chunk, scripts/test_obama.sh:5),
+    fused bf16x3 against the explicit-points fp32 FFMA Decoder.forward, both fields."""
+    R, S, seed = 2048, 64, 5
+    dec = make_decoder(dfn, seed)
+    ro, rd, z, zs, za, sg_h, sg_t = [t.to(DEV) for t in _case(R, S, seed)]
+    p, r = dfn.make_points(ro, rd, z)
+    for which, sig in (('head', sg_h), ('torso', sg_t)):
+        f32, s32 = dec(p.reshape(1, -1, 3), r.reshape(1, -1, 3), zs, za, sig, which)
+        f, s = dec.query_rays(ro, rd, z, zs, za, sig, which, precision=dfn.PREC_BF16X3)
+        wa = dfn.calc_volume_weights(z[None], rd[None], torch.relu(s32.reshape(1, R, S)).contiguous())
+        wb = dfn.calc_volume_weights(z[None], rd[None], torch.relu(s)[None].contiguous())
+        assert maxerr(f, f32.reshape(R, S, 3)) < 1e-4 and maxerr(wa, wb) < 1e-4, which
+
+
+def test_render_head_torso_fused_golden(dfn, golden):
+    """The whole live chunk through dfn_render_head_torso (bf16x3) against the reference's own output."""
+    g = golden('head_torso')
+    dec = make_decoder(dfn, g['seed'])
+    args = (dec, g['H'], g['W'], g['focal'], g['c2w'], g['c2w_torso'], g['bc_rgb'].to(DEV), g['z_shape'].to(DEV),
+            g['z_app'].to(DEV), g['signal'].to(DEV), g['signal_torso'].to(DEV), g['near'], g['far'], g['cx'], g['cy'])
+    rh, rp = dfn.render_head_torso(*args, precision=dfn.PREC_BF16X3)
+    eh, ep = maxerr(rh, g['rgb_head']), maxerr(rp, g['rgb_person'])
+    print('fused head+torso bf16x3 vs reference: rgb_head %.2e rgb_person %.2e (%d launches)'
+          % (eh, ep, dfn.render_head_torso.last_launches))
+    assert eh < 1e-4 and ep < 1e-4
+    rh16, rp16 = dfn.render_head_torso(*args, precision=dfn.PREC_BF16)
+    print('fused head+torso bf16  vs reference: rgb_head %.2e rgb_person %.2e'
+          % (maxerr(rh16, g['rgb_head']), maxerr(rp16, g['rgb_person'])))
+    assert maxerr(rh16, g['rgb_head']) < 0.1 and maxerr(rp16, g['rgb_person']) < 0.1
