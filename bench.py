@@ -4,6 +4,7 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--precision bf16|bf16x3|fp32]
     python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
     python bench.py --impl reference            # CPU arm: the oracle port on the host cores
+    python bench.py --workload head_torso       # BASELINE.json configs[2]: the reference's live two-field frame
 
 One step = one 450x450 frame (202,500 rays) x (64 coarse + 128 fine samples) of the synthetic
 FaceNeRF field (configs[1] of BASELINE.json): get_rays -> z sampling -> PE + 8x256 skip-MLP ->
@@ -29,7 +30,6 @@ sys.path.insert(0, ROOT)
 METRIC = 'rendered rays/sec at 450x450x(64+128) samples; 1/2/4/8 B200 vs CPU ref'
 H = W = 450
 N_SAMPLES, N_IMPORTANCE = 64, 128
-FLOP_PER_RAY_FOLDED = 2 * 557184 * (N_SAMPLES + N_SAMPLES + N_IMPORTANCE)
 
 
 def peaks():
@@ -87,6 +87,35 @@ class ClockSampler:
                 'samples': len(sm)}
 
 
+def cpu_arm_head_torso(steps, warmup, rays_per_step, threads=None):
+    """The reference's live chunk (MAIN:633-708: Decoder head + torso with deformation, two-field compositing) on the
+    host cores: oracle port, fp32, 64 samples, chunk=2048."""
+    import torch
+    from oracle import nerf_oracle as O, synth
+    torch.set_num_threads(threads or os.cpu_count() or 1)
+    fr, fr_t = synth.frame_inputs(H=H, W=W, seed=0), synth.frame_inputs(H=H, W=W, seed=7)
+    sd = synth.decoder_state_dict(0)
+    g = torch.Generator().manual_seed(0)
+    zs, za = torch.randn(1, 2, 256, generator=g), torch.randn(1, 2, 256, generator=g)
+    sig, sig_t = torch.randn(1, 96, generator=g), torch.randn(1, 42, generator=g)
+    b = (H * W) // 2 - rays_per_step // 2
+    ro, rd = [t.reshape(-1, 3) for t in O.get_rays(H, W, fr['focal'], fr['c2w'], fr['cx'], fr['cy'])]
+    rot, rdt = [t.reshape(-1, 3) for t in O.get_rays(H, W, fr['focal'], fr_t['c2w'], fr['cx'], fr['cy'])]
+    times = []
+    with torch.no_grad():
+        for i in range(warmup + steps):
+            t0 = time.perf_counter()
+            for c0 in range(b, b + rays_per_step, 2048):
+                c1 = min(c0 + 2048, b + rays_per_step)
+                z = O.z_vals_uniform(torch.full((c1 - c0, 1), fr['near']), torch.full((c1 - c0, 1), fr['far']), N_SAMPLES)
+                O.render_head_torso_chunk(sd, ro[c0:c1], rd[c0:c1], rot[c0:c1], rdt[c0:c1], z, fr['bc_rgb'][c0:c1], zs, za, sig, sig_t)
+            if i >= warmup:
+                times.append(time.perf_counter() - t0)
+    times.sort()
+    med = times[len(times) // 2]
+    return rays_per_step / med, med, torch.get_num_threads()
+
+
 def cpu_arm(steps, warmup, rays_per_step, threads=None):
     """The reference's arithmetic (oracle port: HELP.get_rays/Embedder/FaceNeRF/sample_pdf + MAIN.calc_volume_weights
     composed in upstream render() order) on the host cores, fp32, chunk=2048, bounded ray sample per step."""
@@ -109,19 +138,30 @@ def cpu_arm(steps, warmup, rays_per_step, threads=None):
     return rays_per_step / med, med, torch.get_num_threads()
 
 
+WORKLOADS = {
+    'facenerf': 'FaceNeRF 450x450 x (64 coarse + 128 fine samples), synthetic seeded weights/pose/latent '
+                '(BASELINE.json configs[1]); one step = one frame',
+    'head_torso': 'Decoder head + torso (DeformationField_ori) two-field frame, 450x450 x 64 samples, synthetic seeded '
+                  'weights/poses/latents (BASELINE.json configs[2], the path scripts/test_obama.sh runs); one step = one frame',
+}
+CPU_RAYS = 8192   # bounded CPU sample per step (four chunks of 2048 at the image centre; ~4 s on 16 cores)
+
+
 def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    rays = 2048
-    value, sec, cores = cpu_arm(max(1, args.steps), max(1, min(args.warmup, 1)), rays)
-    sample = '%d rays (1 chunk of 2048, image centre) x (64+192) FaceNeRF evaluations per step, median of %d' % (rays, max(1, args.steps))
+    rays = CPU_RAYS
+    arm = cpu_arm if args.workload == 'facenerf' else cpu_arm_head_torso
+    value, sec, cores = arm(max(1, args.steps), max(1, min(args.warmup, 1)), rays)
+    evals = '(64+192) FaceNeRF' if args.workload == 'facenerf' else '(64 head + 64 torso) Decoder'
+    sample = '%d rays (4 chunks of 2048, image centre) x %s evaluations per step, median of %d' % (rays, evals, max(1, args.steps))
     print(json.dumps({
         'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': 'rays/s', 'n_gpus': args.gpus, 'steps': args.steps,
         'warmup': args.warmup, 'ms_per_step': sec * 1e3, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None,
         'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': 'FaceNeRF 450x450 x (64 coarse + 128 fine), synthetic seeded weights; CPU arm renders a bounded '
-                               'ray sample of the same frame', 'rays_per_frame': H * W, 'rays_per_step': rays},
+        'config': {'workload': WORKLOADS[args.workload] + '; CPU arm renders a bounded ray sample of the same frame',
+                   'rays_per_frame': H * W, 'rays_per_step': rays},
         'cpu_baseline': {'value': value, 'unit': 'rays/s', 'cores': cores, 'kind': 'port', 'sample': sample},
         'e2e': {'value': value, 'unit': 'rays/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
     }))
@@ -134,6 +174,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--precision', default='bf16', choices=['bf16', 'bf16x3', 'fp32'])
+    ap.add_argument('--workload', default='facenerf', choices=sorted(WORKLOADS))
     ap.add_argument('--no-cpu-baseline', action='store_true')
     args = ap.parse_args()
     if args.impl == 'reference':
@@ -158,34 +199,65 @@ def main():
     prec = {'bf16': dfn.PREC_BF16, 'bf16x3': dfn.PREC_BF16X3, 'fp32': dfn.PREC_FP32}[args.precision]
 
     fr = synth.frame_inputs(H=H, W=W, seed=0)
-
-    def mk(seed):
-        m = dfn.FaceNeRF(D=8, W=256, input_ch=63, input_ch_views=27, dim_aud=64, output_ch=4, skips=[4], use_viewdirs=True)
-        m.load_state_dict(synth.facenerf_state_dict(seed))
-        return m.to(dev)
-
-    eng = dfn.RenderEngine(mk(0), mk(1), N_SAMPLES, N_IMPORTANCE, precision=prec)
     n_rays = H * W
     b, e, per = shard_range(n_rays, rank, world)
-    bc_dev, aud_dev = fr['bc_rgb'].to(dev), fr['aud'].to(dev)
-    bc_host, aud_host = fr['bc_rgb'].pin_memory(), fr['aud'].pin_memory()
+    bc_dev = fr['bc_rgb'].to(dev)
+    bc_host = fr['bc_rgb'].pin_memory()
     rgb_host = torch.empty((n_rays, 3), dtype=torch.float32).pin_memory()
     launches = [0]
 
+    if args.workload == 'facenerf':
+        def mk(seed):
+            m = dfn.FaceNeRF(D=8, W=256, input_ch=63, input_ch_views=27, dim_aud=64, output_ch=4, skips=[4], use_viewdirs=True)
+            m.load_state_dict(synth.facenerf_state_dict(seed))
+            return m.to(dev)
+
+        eng = dfn.RenderEngine(mk(0), mk(1), N_SAMPLES, N_IMPORTANCE, precision=prec)
+        aud_dev = fr['aud'].to(dev)
+        lat_host = fr['aud'].pin_memory()
+        evals_per_ray = N_SAMPLES + N_SAMPLES + N_IMPORTANCE
+        kernel_name = 'mlp_tc_kernel<bf16>' if prec == dfn.PREC_BF16 else 'mlp_pp_kernel<bf16x3>'
+        flops_note = 'algorithmic, latent/viewdir columns folded: 2*557,184 per MLP evaluation (BASELINE.md section 2)'
+
+        def render(bc_full, lat):
+            out = eng.render_frame(H, W, fr['focal'], fr['c2w'], bc_full, lat, fr['near'], fr['far'], fr['cx'], fr['cy'],
+                                   ray_range=(b, e), want=('rgb_map',))
+            launches[0] += eng.last_launches + 1            # + get_rays
+            return out['rgb_map']
+    else:
+        if prec == dfn.PREC_FP32:
+            raise SystemExit('--workload head_torso runs on the tensor-core path: --precision bf16 | bf16x3')
+        dec = dfn.Decoder(z_dim=256, hidden_size=256, dim_signal=96, use_deformation_field=True)
+        dec.load_state_dict(synth.decoder_state_dict(0))
+        dec = dec.to(dev)
+        c2w_torso = synth.frame_inputs(H=H, W=W, seed=7)['c2w']        # fixed body pose (MAIN:644)
+        g = torch.Generator().manual_seed(0)
+        zs, za = torch.randn(1, 2, 256, generator=g).to(dev), torch.randn(1, 2, 256, generator=g).to(dev)
+        lat = torch.cat([torch.randn(96, generator=g), torch.randn(42, generator=g)])   # head signal | torso signal
+        aud_dev, lat_host = lat.to(dev), lat.pin_memory()
+        evals_per_ray = 2 * N_SAMPLES
+        kernel_name = 'mlp_pp_kernel<%s, Decoder>' % args.precision
+        flops_note = 'algorithmic, per-frame latents and per-ray view term folded: 2*556,032 (head) + 2*628,352 (torso incl. ' \
+                     'deformation field) per sample (SURVEY.md section 8d, appendix A)'
+
+        def render(bc_full, lat):
+            _, rgb = dfn.render_head_torso(dec, H, W, fr['focal'], fr['c2w'], c2w_torso, bc_full, zs, za, lat[:96], lat[96:],
+                                           fr['near'], fr['far'], fr['cx'], fr['cy'], N_samples=N_SAMPLES, ray_range=(b, e),
+                                           precision=prec)
+            launches[0] += dfn.render_head_torso.last_launches
+            return rgb
+
     def step_resident():
-        out = eng.render_frame(H, W, fr['focal'], fr['c2w'], bc_dev, aud_dev, fr['near'], fr['far'], fr['cx'], fr['cy'],
-                               ray_range=(b, e), want=('rgb_map',))
-        launches[0] += eng.last_launches + 1            # + get_rays
-        return gather_rgb(out['rgb_map'], n_rays) if world > 1 else out['rgb_map']
+        rgb = render(bc_dev, aud_dev)
+        return gather_rgb(rgb, n_rays) if world > 1 else rgb
 
     def step_e2e():
         bc = bc_host[b:e].to(dev, non_blocking=True)
-        aud = aud_host.to(dev, non_blocking=True)
+        lat = lat_host.to(dev, non_blocking=True)
         bc_full = torch.empty((n_rays, 3), dtype=torch.float32, device=dev)
         bc_full[b:e] = bc
-        out = eng.render_frame(H, W, fr['focal'], fr['c2w'], bc_full, aud, fr['near'], fr['far'], fr['cx'], fr['cy'],
-                               ray_range=(b, e), want=('rgb_map',))
-        full = gather_rgb(out['rgb_map'], n_rays) if world > 1 else out['rgb_map']
+        rgb = render(bc_full, lat)
+        full = gather_rgb(rgb, n_rays) if world > 1 else rgb
         if rank == 0:
             rgb_host.copy_(full, non_blocking=True)
         torch.cuda.current_stream().synchronize()       # the caller consumes the frame
@@ -230,7 +302,7 @@ def main():
     # ---- end to end through the public API with host buffers ------------------------------------------
     ms_e2e = timed(step_e2e, args.steps, 2)
     e2e = {'value': n_rays / (ms_e2e * 1e-3), 'unit': 'rays/s',
-           'h2d_bytes_per_step': int((e - b) * 12 + aud_host.numel() * 4 + 48),
+           'h2d_bytes_per_step': int((e - b) * 12 + lat_host.numel() * 4 + 48),
            'd2h_bytes_per_step': int(n_rays * 12) if rank == 0 else 0}
 
     pk = peaks()
@@ -239,17 +311,18 @@ def main():
         achieved = 2.0 * k_macs.value / (k_ms.value * 1e-3) / 1e12
         roofline = {'bound': 'tensor', 'achieved': achieved, 'peak': pk['bf16_sustained'], 'unit': 'TFLOP/s',
                     'frac': achieved / pk['bf16_sustained'], 'traffic': None,
-                    'kernel': 'mlp_tc_kernel<%s>' % ('bf16x3' if prec == dfn.PREC_BF16X3 else 'bf16'),
+                    'kernel': kernel_name,
                     'launches': int(k_n.value), 'avg_launch_ms': k_ms.value / k_n.value,
                     'kernel_share_of_step': k_ms.value / (ms_step * args.steps),
-                    'flops': 'algorithmic, latent/viewdir columns folded: 2*557,184 per MLP evaluation (BASELINE.md section 2)',
+                    'flops': flops_note,
                     'peak_source': 'bf16 dense sustained, ' + pk['source']}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        v, sec, cores = cpu_arm(3, 1, 2048)
+        v, sec, cores = (cpu_arm if args.workload == 'facenerf' else cpu_arm_head_torso)(3, 1, CPU_RAYS)
         cpu = {'value': v, 'unit': 'rays/s', 'cores': cores, 'kind': 'port',
-               'sample': '2048 rays (1 chunk, image centre) x (64+192) FaceNeRF evaluations, median of 3 (%.1f s each)' % sec}
+               'sample': '%d rays (4 chunks of 2048, image centre) x %d network evaluations per ray, median of 3 (%.1f s each)'
+                         % (CPU_RAYS, evals_per_ray, sec)}
 
     if rank == 0:
         print(json.dumps({
@@ -257,9 +330,8 @@ def main():
             'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None,
             'dtype': {'bf16': 'bf16', 'bf16x3': 'bf16x3 (split bf16, fp32-parity)', 'fp32': 'f32'}[args.precision],
             'data': 'synthetic',
-            'config': {'workload': 'FaceNeRF 450x450 x (64 coarse + 128 fine samples), synthetic seeded weights/pose/latent '
-                                   '(BASELINE.json configs[1]); one step = one frame',
-                       'rays_per_step': n_rays, 'mlp_evals_per_ray': 256, 'precision': args.precision,
+            'config': {'workload': WORKLOADS[args.workload],
+                       'rays_per_step': n_rays, 'mlp_evals_per_ray': evals_per_ray, 'precision': args.precision,
                        'parallelism': 'rays sharded over %d GPU(s), one all-gather of the RGB tile' % world,
                        'l2': 'per-step intermediates (~1.4 GB of raw/z buffers) exceed the 126 MB L2; no explicit flush'},
             'e2e': e2e, 'gpu_launches': n_launch, 'clocks': clocks, 'roofline': roofline, 'cpu_baseline': cpu,
