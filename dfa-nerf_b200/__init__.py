@@ -7,13 +7,14 @@ compiled extension, and fails loudly without them.
 from ._lib import lib, DfnError, PREC_FP32, PREC_BF16, PREC_BF16X3  # noqa: F401
 from .functional import (get_rays, get_embedder, Embedder, decoder_transform_points, z_vals_uniform, make_points,  # noqa: F401
                          calc_volume_weights, composite_function, raw2outputs, sample_pdf, invert_cdf,
-                         sort_merge)
+                         sort_merge, to8b)
 from .modules import NeRF, FaceNeRF  # noqa: F401
 from .decoder import Decoder, DeformationField_ori, render_head_torso  # noqa: F401
 from .render import render, render_rays, batchify_rays, run_network, RenderEngine  # noqa: F401
 from .distributed import render_sharded, shard_range  # noqa: F401
+from .sequence import render_sequence, render_sequence_head_torso, shard_frames, FrameSink  # noqa: F401
 
 __all__ = ['get_rays', 'get_embedder', 'Embedder', 'decoder_transform_points', 'z_vals_uniform', 'make_points',
            'calc_volume_weights', 'composite_function', 'raw2outputs', 'sample_pdf', 'invert_cdf', 'sort_merge',
            'NeRF', 'FaceNeRF', 'Decoder', 'DeformationField_ori', 'render_head_torso', 'render', 'render_rays', 'batchify_rays', 'run_network', 'RenderEngine',
-           'render_sharded', 'shard_range', 'lib', 'DfnError', 'PREC_FP32', 'PREC_BF16', 'PREC_BF16X3']
+           'render_sharded', 'shard_range', 'render_sequence', 'render_sequence_head_torso', 'shard_frames', 'FrameSink', 'to8b', 'lib', 'DfnError', 'PREC_FP32', 'PREC_BF16', 'PREC_BF16X3']

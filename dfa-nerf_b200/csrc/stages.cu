@@ -534,9 +534,36 @@ __global__ void sort_merge_kernel(int R, int na, const float* __restrict__ a, in
   }
 }
 
+// ---------------------------------------------------------------------------- to8b (HELP:17)
+// (255 * clip(x, 0, 1)).astype(uint8): fp32 product, truncation.  Four values per thread (one 32-bit store).
+__global__ void to8b_kernel(int64_t n, const float* __restrict__ x, uint8_t* __restrict__ out) {
+  const int64_t n4 = n >> 2;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    const float4 v = reinterpret_cast<const float4*>(x)[i];
+    const uint32_t b0 = (uint32_t)__fmul_rn(255.f, fminf(fmaxf(v.x, 0.f), 1.f));
+    const uint32_t b1 = (uint32_t)__fmul_rn(255.f, fminf(fmaxf(v.y, 0.f), 1.f));
+    const uint32_t b2 = (uint32_t)__fmul_rn(255.f, fminf(fmaxf(v.z, 0.f), 1.f));
+    const uint32_t b3 = (uint32_t)__fmul_rn(255.f, fminf(fmaxf(v.w, 0.f), 1.f));
+    reinterpret_cast<uint32_t*>(out)[i] = b0 | (b1 << 8) | (b2 << 16) | (b3 << 24);
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
+    const int64_t i = (n4 << 2) + threadIdx.x;
+    out[i] = (uint8_t)__fmul_rn(255.f, fminf(fmaxf(x[i], 0.f), 1.f));
+  }
+}
+
 }  // namespace dfn
 
 using namespace dfn;
+
+extern "C" int dfn_to8b(int64_t n, const float* x, uint8_t* out, void* stream) {
+  DFN_CHECK_ARG(n > 0 && x && out, "dfn_to8b: bad argument");
+  DFN_CHECK_ARG((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 3) == 0,
+                "dfn_to8b: x must be 16-byte and out 4-byte aligned");
+  to8b_kernel<<<grid_for((n + 3) / 4), kThreads, 0, (cudaStream_t)stream>>>(n, x, out);
+  DFN_LAUNCH_CHECK();
+  return 0;
+}
 
 extern "C" int dfn_get_rays(int n_rows, int n_cols, const float* xs, const float* ys, float focal,
                             float cx, float cy, const float* c2w_host, float* rays_o, float* rays_d,

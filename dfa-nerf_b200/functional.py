@@ -242,3 +242,13 @@ def sort_merge(a, b):
     with torch.cuda.device(a.device):
         check(lib.dfn_sort_merge(R, a.shape[1], pa, b.shape[1], pb_, ptr(out), stream_ptr()), 'dfn_sort_merge')
     return out
+
+
+def to8b(x):
+    """HELP:17 on the device: uint8(255 * clip(x, 0, 1)), same shape (numpy's fp32 product and truncation)."""
+    x, px = dev(x, 'x')
+    out = torch.empty(x.shape, dtype=torch.uint8, device=x.device)
+    if x.numel():
+        with torch.cuda.device(x.device):
+            check(lib.dfn_to8b(x.numel(), px, ptr(out), stream_ptr()), 'dfn_to8b')
+    return out

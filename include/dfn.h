@@ -117,6 +117,10 @@ int dfn_invert_cdf(int R, int nb, const float* bins, const float* cdf, int N, co
 /* ---- a11  merge  (upstream: z_vals,_ = sort(cat([z_vals, z_samples]))) ------------------------ */
 int dfn_sort_merge(int R, int na, const float* a, int nb, const float* b, float* out, void* stream);
 
+/* ---- output side  to8b  (HELP:17; MAIN:714-715) ---------------------------------------------
+ * out[i] = uint8(255 * clip(x[i], 0, 1)) (fp32 product, truncation) -- the frame leaves the device as 3 bytes/pixel. */
+int dfn_to8b(int64_t n, const float* x, uint8_t* out, void* stream);
+
 /* ---- a5 / a5'  the 8x256 skip-MLP  (HELP:242-299 FaceNeRF, HELP:342-396 NeRF) ------------------ */
 typedef struct dfn_model dfn_model;
 

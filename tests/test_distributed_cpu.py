@@ -62,3 +62,16 @@ def test_gather_rgb_single_process():
     from dfa_nerf_b200.distributed import gather_rgb
     x = torch.rand(10, 3)
     assert torch.equal(gather_rgb(x, 10), x)
+
+
+def test_shard_frames_partition():
+    """Frame sharding of the sequence loop: contiguous, disjoint, complete, balanced to within one frame."""
+    from dfa_nerf_b200.sequence import shard_frames
+    for n in (0, 1, 7, 300):
+        for world in (1, 2, 3, 8):
+            blocks = [shard_frames(n, r, world) for r in range(world)]
+            assert blocks[0][0] == 0 and blocks[-1][1] == n
+            assert all(blocks[r][1] == blocks[r + 1][0] for r in range(world - 1))
+            sizes = [e - b for b, e in blocks]
+            assert max(sizes) - min(sizes) <= 1 and sum(sizes) == n
+    assert shard_frames(300, 7, 8) == (263, 300) and shard_frames(300, 0, 8) == (0, 38)

@@ -128,3 +128,41 @@ def test_full_frame_properties(dfn):
     assert maxerr(sub['rgb0'], sub3['rgb0']) < 1e-4
     e = (sub['rgb_map'] - sub3['rgb_map']).abs()
     assert e.median() < 1e-5
+
+
+def test_to8b_bit_exact(dfn):
+    """HELP:17 on the device against numpy's (255*clip(x,0,1)).astype(uint8), ragged length, edge values."""
+    g = torch.Generator().manual_seed(0)
+    x = torch.cat([torch.rand(4099, generator=g) * 1.4 - 0.2, torch.tensor([0., 1., -0., 0.999999, 1 / 255., 254.5 / 255., 2., -3.])])
+    ref = torch.from_numpy(O.to8b(x.numpy()))
+    assert torch.equal(dfn.to8b(x.to(DEV)).cpu(), ref)
+    y = torch.rand(5, 7, 3, generator=g)
+    assert torch.equal(dfn.to8b(y.to(DEV)).cpu(), torch.from_numpy(O.to8b(y.numpy())))
+
+
+def test_render_sequence_matches_per_frame(dfn):
+    """Sequence loop (device-side to8b + double-buffered D2H) == frame-by-frame render + to8b, FaceNeRF and live model."""
+    H = W = 12
+    n = 5
+    fr = synth.frame_inputs(H=H, W=W, seed=2, n_frames=n)
+    net_c, net_f = nets(dfn, 0, 1)
+    eng = dfn.RenderEngine(net_c, net_f, 64, 128, precision=dfn.PREC_BF16X3)
+    bc = fr['bc_rgb'].to(DEV)
+    frames = dfn.render_sequence(eng, H, W, fr['focal'], fr['c2w_seq'], fr['aud'], bc, fr['near'], fr['far'], fr['cx'], fr['cy'])
+    assert frames.shape == (n, H, W, 3) and frames.dtype == torch.uint8 and not frames.is_cuda
+    for i in range(n):
+        one = eng.render_frame(H, W, fr['focal'], fr['c2w_seq'][i], bc, fr['aud'][i].to(DEV), fr['near'], fr['far'], fr['cx'], fr['cy'])
+        assert torch.equal(frames[i], dfn.to8b(one['rgb_map']).reshape(H, W, 3).cpu())
+    dec = dfn.Decoder(z_dim=256, hidden_size=256, dim_signal=96, use_deformation_field=True)
+    dec.load_state_dict(synth.decoder_state_dict(1))
+    dec = dec.to(DEV)
+    g = torch.Generator().manual_seed(5)
+    zs, za = torch.randn(1, 2, 256, generator=g).to(DEV), torch.randn(1, 2, 256, generator=g).to(DEV)
+    sig, sig_t = torch.randn(n, 96, generator=g), torch.randn(n, 42, generator=g)
+    body = synth.camera_pose(9)
+    fr2 = dfn.render_sequence_head_torso(dec, H, W, fr['focal'], fr['c2w_seq'], body, bc, zs, za, sig, sig_t, fr['near'], fr['far'],
+                                         fr['cx'], fr['cy'])
+    for i in (0, n - 1):
+        _, person = dfn.render_head_torso(dec, H, W, fr['focal'], fr['c2w_seq'][i], body, bc, zs, za, sig[i].to(DEV), sig_t[i].to(DEV),
+                                          fr['near'], fr['far'], fr['cx'], fr['cy'])
+        assert torch.equal(fr2[i], dfn.to8b(person).reshape(H, W, 3).cpu())
