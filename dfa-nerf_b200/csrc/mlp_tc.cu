@@ -27,11 +27,11 @@
 #include "model.h"
 #include "tc_ptx.cuh"
 #include "tc_pack.h"
+#include "tc_epi.cuh"
 
 namespace dfn {
 namespace tc {
 
-static constexpr int KB_BYTES = TILE_M * 128;      // one activation K-block: 128 rows x 64 bf16
 static constexpr int STAGE_BYTES = 128 * 128;      // one weight stage: <=128 rows x 64 bf16
 static constexpr int N_STAGES = 4;
 static constexpr int N_PAIRS = N_STAGES / 2;
@@ -61,73 +61,6 @@ struct Params {
   int trace_tiles;            // local tiles per slot recorded
   TcLayer layers[TC_MAX_LAYERS];
 };
-
-// Writes 8 consecutive columns (one 16-byte chunk) of this thread's row.
-template <bool X3>
-__device__ __forceinline__ void store_chunk(uint8_t* blk_hi, uint8_t* blk_lo, uint32_t row, uint32_t chunk,
-                                            const float (&v)[8]) {
-  uint4 h;
-  h.x = pack_bf16(v[0], v[1]);
-  h.y = pack_bf16(v[2], v[3]);
-  h.z = pack_bf16(v[4], v[5]);
-  h.w = pack_bf16(v[6], v[7]);
-  *reinterpret_cast<uint4*>(blk_hi + swz(row, chunk)) = h;
-  if (X3) {
-    uint4 l;
-    l.x = pack_bf16(v[0] - bf16_lo_f(h.x), v[1] - bf16_hi_f(h.x));
-    l.y = pack_bf16(v[2] - bf16_lo_f(h.y), v[3] - bf16_hi_f(h.y));
-    l.z = pack_bf16(v[4] - bf16_lo_f(h.z), v[5] - bf16_hi_f(h.z));
-    l.w = pack_bf16(v[6] - bf16_lo_f(h.w), v[7] - bf16_hi_f(h.w));
-    *reinterpret_cast<uint4*>(blk_lo + swz(row, chunk)) = l;
-  }
-}
-
-// One 32-column chunk of this thread's row: + bias, ReLU, bf16 (hi[/lo]) and four 16-byte stores into the
-// swizzled K-block.  `chunk32` = index of the 32-column chunk inside the layer output.
-template <bool X3, bool GLOBAL_BIAS>
-__device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[32], int chunk32, const float* gbias, uint32_t sbias,
-                                               uint8_t* arena_hi, uint8_t* arena_lo, uint32_t row) {
-  uint8_t* dst_hi = arena_hi + (size_t)(chunk32 >> 1) * KB_BYTES;
-  uint8_t* dst_lo = arena_lo + (size_t)(chunk32 >> 1) * KB_BYTES;
-#pragma unroll
-  for (int g = 0; g < 4; ++g) {
-    float b[8];
-    if (GLOBAL_BIAS) ldg_f32x8(gbias + chunk32 * 32 + g * 8, b);
-    else lds_f32x8(sbias + (uint32_t)(chunk32 * 32 + g * 8) * 4u, b);
-    const uint32_t c16 = (uint32_t)((chunk32 & 1) * 4 + g);
-    if (!X3) {
-      uint4 h;
-      h.x = add_relu_pack(v[g * 8 + 0], v[g * 8 + 1], b[0], b[1]);
-      h.y = add_relu_pack(v[g * 8 + 2], v[g * 8 + 3], b[2], b[3]);
-      h.z = add_relu_pack(v[g * 8 + 4], v[g * 8 + 5], b[4], b[5]);
-      h.w = add_relu_pack(v[g * 8 + 6], v[g * 8 + 7], b[6], b[7]);
-      *reinterpret_cast<uint4*>(dst_hi + swz(row, c16)) = h;
-    } else {
-      float o[8];
-#pragma unroll
-      for (int e = 0; e < 8; ++e) o[e] = fmaxf(__uint_as_float(v[g * 8 + e]) + b[e], 0.f);
-      store_chunk<true>(dst_hi, dst_lo, row, c16, o);
-    }
-  }
-}
-
-// Accumulator columns [0, ncols) of this thread's row -> next layer's activation blocks.  The TMEM load of
-// chunk c+1 is in flight while chunk c is processed (tcgen05.wait::ld waits for all outstanding loads).
-template <bool X3, bool GLOBAL_BIAS>
-__device__ __forceinline__ void epilogue_relu(uint32_t acc, int ncols, const float* gbias, uint32_t sbias,
-                                              uint8_t* arena_hi, uint8_t* arena_lo, uint32_t row) {
-  uint32_t v0[32], v1[32];
-  const int nch = ncols >> 5;  // even
-  tmem_ld32(acc, v0);
-  for (int c = 0; c < nch; c += 2) {
-    tmem_ld_wait();
-    tmem_ld32(acc + (c + 1) * 32, v1);
-    epilogue_chunk<X3, GLOBAL_BIAS>(v0, c, gbias, sbias, arena_hi, arena_lo, row);
-    tmem_ld_wait();
-    if (c + 2 < nch) tmem_ld32(acc + (c + 2) * 32, v0);
-    epilogue_chunk<X3, GLOBAL_BIAS>(v1, c + 1, gbias, sbias, arena_hi, arena_lo, row);
-  }
-}
 
 // ------------------------------------------------------------------------------------ kernel
 // X3 = false: bf16, two tile slots (384 threads).  X3 = true: split-bf16, one slot (256 threads).
@@ -478,6 +411,9 @@ void tc_free_model(dfn_model* m) {
   cudaFree(m->ts_hi);
   cudaFree(m->ts_lo);
   m->ts_hi = m->ts_lo = nullptr;
+  cudaFree(m->tc2_hi);
+  cudaFree(m->tc2_lo);
+  m->tc2_hi = m->tc2_lo = nullptr;
   cudaFree(m->tc_hi);
   cudaFree(m->tc_lo);
   cudaFree(m->tc_bias);
@@ -540,6 +476,7 @@ int tc_pack_model(dfn_model* m, const float* const* t, cudaStream_t st) {
       pg.fold_layer[nfold++] = nl;
     }
     m->tc32_woff[nl] = pk.last32;
+    m->tc2_woff[nl] = pk.last2;
     pg.layers[nl++] = L;
   }
   // views_linears.0 (+ alpha_linear as output row Wh).  NeRF applies feature_linear first
@@ -584,6 +521,7 @@ int tc_pack_model(dfn_model* m, const float* const* t, cudaStream_t st) {
     });
     bias[(size_t)nl * TC_BIAS_STRIDE + Wh] = Bt(i_alpha)[0];
     m->tc32_woff[nl] = pk.last32;
+    m->tc2_woff[nl] = pk.last2;
     pg.layers[nl++] = L;
     // view-direction columns + composed bias for view_bias_kernel
     std::vector<float> vw((size_t)Wh * d.input_ch_views);
@@ -607,6 +545,7 @@ int tc_pack_model(dfn_model* m, const float* const* t, cudaStream_t st) {
     L.woff = pk.add_layer(Wh, 2, [&](int n, int kbi, int k) -> float { return w[(size_t)n * Wh + kbi * 64 + k]; });
     for (int n = 0; n < Wh; ++n) bias[(size_t)nl * TC_BIAS_STRIDE + n] = Bt(i_views0 + i)[n];
     m->tc32_woff[nl] = pk.last32;
+    m->tc2_woff[nl] = pk.last2;
     pg.layers[nl++] = L;
   }
   {
@@ -621,10 +560,15 @@ int tc_pack_model(dfn_model* m, const float* const* t, cudaStream_t st) {
     L.woff = pk.add_layer(16, 2, [&](int n, int kbi, int k) -> float { return n < 3 ? w[(size_t)n * Wh + kbi * 64 + k] : 0.f; });
     for (int n = 0; n < 3; ++n) bias[(size_t)nl * TC_BIAS_STRIDE + n] = Bt(i_rgb)[n];
     m->tc32_woff[nl] = pk.last32;
+    m->tc2_woff[nl] = pk.last2;
     pg.layers[nl++] = L;
   }
   pg.n_layers = nl;
   m->tc_blob_bytes = (int64_t)pk.hi32.size();
+  DFN_CUDA(cudaMalloc(&m->tc2_hi, pk.hi2.size()));
+  DFN_CUDA(cudaMalloc(&m->tc2_lo, pk.lo2.size()));
+  DFN_CUDA(cudaMemcpyAsync(m->tc2_hi, pk.hi2.data(), pk.hi2.size(), cudaMemcpyHostToDevice, st));
+  DFN_CUDA(cudaMemcpyAsync(m->tc2_lo, pk.lo2.data(), pk.lo2.size(), cudaMemcpyHostToDevice, st));
   DFN_CUDA(cudaMalloc(&m->tc_hi, pk.hi32.size()));
   DFN_CUDA(cudaMalloc(&m->tc_lo, pk.lo32.size()));
   DFN_CUDA(cudaMalloc(&m->tc_bias, bias.size() * 4));
@@ -729,6 +673,9 @@ int tc_query_points(const dfn_model* m, int64_t R, int S, const float* rays_o, c
   if (impl == 2 && (precision == DFN_PREC_BF16 || precision == DFN_PREC_BF16X3)) {
     void* scratch = reinterpret_cast<char*>(vbias_ws) + align256(R * (int64_t)Wh * 4);
     int rc = pp_launch(m, bias_ws, vbias_ws, scratch, R, S, rays_o, rays_d, z_vals, raw, precision, st);
+    if (rc) return rc;
+  } else if (impl == 3 && precision == DFN_PREC_BF16) {
+    int rc = tc2_launch(m, bias_ws, vbias_ws, R, S, rays_o, rays_d, z_vals, raw, precision, st);
     if (rc) return rc;
   } else if (impl == 0 && (precision == DFN_PREC_BF16 || precision == DFN_PREC_BF16X3)) {
     int rc = ts_launch(m, bias_ws, vbias_ws, R, S, rays_o, rays_d, z_vals, raw, precision, st);

@@ -71,6 +71,10 @@ struct dfn_model {
   float* tc_fold_w = nullptr;   // [2][W][dim_aud] latent columns of the two folding layers
   float* tc_view_w = nullptr;   // [W/2][input_ch_views] view-direction columns of views_linears.0
   float* tc_view_b = nullptr;   // [W/2] its (composed) bias
+  // cta_group::2 kernel (mlp_tc2.cu): per K-block, per CTA of the pair, [n/2 rows x 64 K] stages
+  uint8_t* tc2_hi = nullptr;
+  uint8_t* tc2_lo = nullptr;
+  uint32_t tc2_woff[dfn::TC_MAX_LAYERS] = {};
   // TMEM-activation kernel (mlp_ts.cu): the same stage images in half-major order
   uint8_t* ts_hi = nullptr;
   uint8_t* ts_lo = nullptr;
@@ -94,6 +98,8 @@ int pp_launch_prog(const TcProgram& prog, const uint32_t* woff32, const uint8_t*
 int pp_launch(const dfn_model* m, const float* bias_ws, const float* vbias_ws, void* scratch, int64_t R, int S,
               const float* rays_o, const float* rays_d, const float* z_vals, float* raw, int precision,
               cudaStream_t st);
+int tc2_launch(const dfn_model* m, const float* bias_ws, const float* vbias_ws, int64_t R, int S, const float* rays_o,
+               const float* rays_d, const float* z_vals, float* raw, int precision, cudaStream_t st);
 int ts_launch(const dfn_model* m, const float* bias_ws, const float* vbias_ws, int64_t R, int S, const float* rays_o,
               const float* rays_d, const float* z_vals, float* raw, int precision, cudaStream_t st);
 int tc_pack_model(dfn_model* m, const float* const* t, cudaStream_t st);

@@ -1,0 +1,80 @@
+// Epilogue building blocks shared by mlp_tc.cu and mlp_tc2.cu: accumulator (TMEM) -> + bias -> ReLU -> bf16 (hi[/lo])
+// -> 128-byte-swizzled K-major activation blocks in shared memory.
+#pragma once
+#include "tc_ptx.cuh"
+
+namespace dfn {
+namespace tc {
+
+static constexpr int KB_BYTES = TILE_M * 128;      // one activation K-block: 128 rows x 64 bf16
+
+// Writes 8 consecutive columns (one 16-byte chunk) of this thread's row.
+template <bool X3>
+__device__ __forceinline__ void store_chunk(uint8_t* blk_hi, uint8_t* blk_lo, uint32_t row, uint32_t chunk,
+                                            const float (&v)[8]) {
+  uint4 h;
+  h.x = pack_bf16(v[0], v[1]);
+  h.y = pack_bf16(v[2], v[3]);
+  h.z = pack_bf16(v[4], v[5]);
+  h.w = pack_bf16(v[6], v[7]);
+  *reinterpret_cast<uint4*>(blk_hi + swz(row, chunk)) = h;
+  if (X3) {
+    uint4 l;
+    l.x = pack_bf16(v[0] - bf16_lo_f(h.x), v[1] - bf16_hi_f(h.x));
+    l.y = pack_bf16(v[2] - bf16_lo_f(h.y), v[3] - bf16_hi_f(h.y));
+    l.z = pack_bf16(v[4] - bf16_lo_f(h.z), v[5] - bf16_hi_f(h.z));
+    l.w = pack_bf16(v[6] - bf16_lo_f(h.w), v[7] - bf16_hi_f(h.w));
+    *reinterpret_cast<uint4*>(blk_lo + swz(row, chunk)) = l;
+  }
+}
+
+// One 32-column chunk of this thread's row: + bias, ReLU, bf16 (hi[/lo]) and four 16-byte stores into the
+// swizzled K-block.  `chunk32` = index of the 32-column chunk inside the layer output.
+template <bool X3, bool GLOBAL_BIAS>
+__device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[32], int chunk32, const float* gbias, uint32_t sbias,
+                                               uint8_t* arena_hi, uint8_t* arena_lo, uint32_t row) {
+  uint8_t* dst_hi = arena_hi + (size_t)(chunk32 >> 1) * KB_BYTES;
+  uint8_t* dst_lo = arena_lo + (size_t)(chunk32 >> 1) * KB_BYTES;
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    float b[8];
+    if (GLOBAL_BIAS) ldg_f32x8(gbias + chunk32 * 32 + g * 8, b);
+    else lds_f32x8(sbias + (uint32_t)(chunk32 * 32 + g * 8) * 4u, b);
+    const uint32_t c16 = (uint32_t)((chunk32 & 1) * 4 + g);
+    if (!X3) {
+      uint4 h;
+      h.x = add_relu_pack(v[g * 8 + 0], v[g * 8 + 1], b[0], b[1]);
+      h.y = add_relu_pack(v[g * 8 + 2], v[g * 8 + 3], b[2], b[3]);
+      h.z = add_relu_pack(v[g * 8 + 4], v[g * 8 + 5], b[4], b[5]);
+      h.w = add_relu_pack(v[g * 8 + 6], v[g * 8 + 7], b[6], b[7]);
+      *reinterpret_cast<uint4*>(dst_hi + swz(row, c16)) = h;
+    } else {
+      float o[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) o[e] = fmaxf(__uint_as_float(v[g * 8 + e]) + b[e], 0.f);
+      store_chunk<true>(dst_hi, dst_lo, row, c16, o);
+    }
+  }
+}
+
+// Accumulator columns [0, ncols) of this thread's row -> next layer's activation blocks.  The TMEM load of
+// chunk c+1 is in flight while chunk c is processed (tcgen05.wait::ld waits for all outstanding loads).
+template <bool X3, bool GLOBAL_BIAS>
+__device__ __forceinline__ void epilogue_relu(uint32_t acc, int ncols, const float* gbias, uint32_t sbias,
+                                              uint8_t* arena_hi, uint8_t* arena_lo, uint32_t row) {
+  uint32_t v0[32], v1[32];
+  const int nch = ncols >> 5;  // even
+  tmem_ld32(acc, v0);
+  for (int c = 0; c < nch; c += 2) {
+    tmem_ld_wait();
+    tmem_ld32(acc + (c + 1) * 32, v1);
+    epilogue_chunk<X3, GLOBAL_BIAS>(v0, c, gbias, sbias, arena_hi, arena_lo, row);
+    tmem_ld_wait();
+    if (c + 2 < nch) tmem_ld32(acc + (c + 2) * 32, v0);
+    epilogue_chunk<X3, GLOBAL_BIAS>(v1, c + 1, gbias, sbias, arena_hi, arena_lo, row);
+  }
+}
+
+
+}  // namespace tc
+}  // namespace dfn

@@ -26,7 +26,10 @@ static inline float bf2f(uint16_t h) {
 struct Packer {
   std::vector<uint8_t> hi, lo;       // [<=128 rows x 64 K] stages, 128-byte swizzle (mlp_ts.cu)
   std::vector<uint8_t> hi32, lo32;   // [n rows x 32 K] stages, 64-byte swizzle (mlp_tc.cu)
+  std::vector<uint8_t> hi2, lo2;     // [n/2 rows x 64 K] per CTA of a pair, 128-byte swizzle (mlp_tc2.cu)
   uint32_t last32 = 0;               // offset of the last layer added to hi32
+  uint32_t last2 = 0;                // offset of the last layer added to hi2
+  bool want2 = true;                 // build the cta_group::2 images
   bool want64 = true;                // also build the 128-byte-swizzle images (only mlp_ts.cu reads them)
   // Appends the stages of one layer: for each K-block, for each chunk of <=128 output rows, a
   // [rows x 64] bf16 image in the swizzled K-major layout.  wfun(n, kbi, k) returns W[n][column
@@ -68,6 +71,29 @@ struct Packer {
             const size_t o = base + (size_t)r * 64 + ((((size_t)k >> 3) ^ (((size_t)r >> 1) & 3)) << 4) + ((size_t)k & 7) * 2;
             memcpy(&hi32[o], &h, 2);
             memcpy(&lo32[o], &l, 2);
+          }
+        }
+      }
+    }
+    // cta_group::2 stages: for each K-block, for each CTA rank of the pair, rows [rank*n/2, (rank+1)*n/2) x 64 K in the
+    // 128-byte-swizzled K-major layout (the pair's MMA takes half of B's N rows from each CTA's shared memory).
+    last2 = (uint32_t)hi2.size();
+    if (want2 && n_out % 16 == 0) {
+      const int half = n_out / 2;
+      for (int kbi = 0; kbi < nkb; ++kbi) {
+        for (int rank = 0; rank < 2; ++rank) {
+          const size_t base = hi2.size();
+          hi2.resize(base + (size_t)half * 128, 0);
+          lo2.resize(base + (size_t)half * 128, 0);
+          for (int r = 0; r < half; ++r) {
+            for (int k = 0; k < 64; ++k) {
+              const float w = wfun(rank * half + r, kbi, k);
+              const uint16_t h = f2bf(w);
+              const uint16_t l = f2bf(w - bf2f(h));
+              const size_t o = base + (size_t)r * 128 + ((((size_t)k >> 3) ^ ((size_t)r & 7)) << 4) + ((size_t)k & 7) * 2;
+              memcpy(&hi2[o], &h, 2);
+              memcpy(&lo2[o], &l, 2);
+            }
           }
         }
       }

@@ -291,7 +291,8 @@ int dfn_debug_trace(void* dev_buffer, int tiles);
 
 /* Selects the tcgen05 kernel variant (A/B measurements): -1 (default) the fastest measured per precision
  * (bf16 -> 1, bf16x3 -> 2); 1 two tiles in flight, per-tile epilogue warps (mlp_tc.cu); 2 cooperative
- * epilogue + PE through the weight ring (mlp_pp.cu); 0 activations in tensor memory (mlp_ts.cu). */
+ * epilogue + PE through the weight ring (mlp_pp.cu); 0 activations in tensor memory (mlp_ts.cu); 3 (bf16 only) CTA-pair
+ * cta_group::2 MMAs (mlp_tc2.cu; measured slower, kept as an experiment). */
 int dfn_debug_set_impl(int impl);
 int dfn_profile_collect(double* kernel_ms, int64_t* launches, double* algorithmic_macs);
 

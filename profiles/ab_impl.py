@@ -1,4 +1,5 @@
-"""A/B of the two tcgen05 kernel generations on the same query: max |diff| and timing."""
+"""A/B of the tcgen05 kernel generations on the same query: max |diff| against impl 1 and timing.
+    python profiles/ab_impl.py [R] [impls, e.g. 1,2,3]"""
 import os
 import sys
 
@@ -9,7 +10,9 @@ import dfa_nerf_b200 as dfn  # noqa: E402
 from oracle import synth  # noqa: E402
 
 R = int(sys.argv[1]) if len(sys.argv) > 1 else 4000
+impls = [int(x) for x in sys.argv[2].split(',')] if len(sys.argv) > 2 else [1, 2, 3]
 S = 192
+NAMES = {0: 'ts', 1: 'tc', 2: 'pp', 3: 'tc2'}
 dev = torch.device('cuda', 0)
 net = dfn.FaceNeRF(D=8, W=256, input_ch=63, input_ch_views=27, dim_aud=64, output_ch=4, skips=[4], use_viewdirs=True)
 net.load_state_dict(synth.facenerf_state_dict(1))
@@ -22,7 +25,9 @@ aud = fr['aud'].to(dev)
 for mode, prec in (('bf16', dfn.PREC_BF16), ('bf16x3', dfn.PREC_BF16X3)):
     eng = dfn.RenderEngine(net, None, S, 0, precision=prec)
     outs = {}
-    for impl in (1, 2):
+    for impl in impls:
+        if impl == 3 and mode != 'bf16':
+            continue
         dfn.lib.dfn_debug_set_impl(impl)
         for _ in range(2):
             raw = eng.query_points(net, ro, rd, vd, z, aud)
@@ -34,7 +39,10 @@ for mode, prec in (('bf16', dfn.PREC_BF16), ('bf16x3', dfn.PREC_BF16X3)):
         torch.cuda.synchronize()
         ms = ev0.elapsed_time(ev1)
         outs[impl] = raw.clone()
-        print('%s impl=%s: %.3f ms -> %.1f TFLOP/s' % (mode, {0: 'ts', 1: 'tc', 2: 'pp'}[impl], ms, 2 * 557184 * R * S / ms / 1e9), flush=True)
-    d = (outs[2] - outs[1]).abs()
-    print('%s: max |pp - tc| rgb %.3e sigma %.3e  finite=%s' % (mode, d[..., :3].max().item(), d[..., 3].max().item(), bool(torch.isfinite(outs[2]).all())), flush=True)
+        msg = ''
+        if impls[0] in outs and impl != impls[0]:
+            d = (outs[impl] - outs[impls[0]]).abs()
+            msg = '  max|diff vs %s| rgb %.3e sigma %.3e finite=%s' % (NAMES[impls[0]], d[..., :3].max().item(), d[..., 3].max().item(),
+                                                                      bool(torch.isfinite(outs[impl]).all()))
+        print('%s impl=%s: %.3f ms -> %.1f TFLOP/s%s' % (mode, NAMES[impl], ms, 2 * 557184 * R * S / ms / 1e9, msg), flush=True)
 dfn.lib.dfn_debug_set_impl(-1)

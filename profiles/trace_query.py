@@ -37,7 +37,7 @@ for j in range(2, 4):
     for l in range(NL):
         for s in range(nslot):
             w0, w1, e, fw = [int(x) for x in b[0, j, l, s]]
-            print('  j=%d l=%2d s=%d  start %8d  wait_aready %6d  issue %6d  (full-wait %6d)' % (j, l, s, w0 - t0, w1 - w0, e - w1, fw))
+            print('  j=%d l=%2d s=%d  start %8d  wait_aready %6d  issue %6d  (full-wait %6d, peer-full-wait %6d)' % (j, l, s, w0 - t0, w1 - w0, e - w1, fw & 0xFFFFFFFF, fw >> 32))
 print('EPILOGUE: tile layer slot | wait_acc  work')
 for j in range(2, 4):
     for l in range(NL):

@@ -173,6 +173,9 @@ def test_kernel_variants_agree(dfn):
             assert torch.equal(outs[0], outs[1]) or maxerr(outs[0], outs[1]) < 2e-3   # x3: K-half order differs
             if prec == dfn.PREC_BF16:
                 assert torch.equal(outs[0], outs[1])
+            if prec == dfn.PREC_BF16:      # CTA-pair kernel (cta_group::2 MMAs): same operands, same K order
+                dfn.lib.dfn_debug_set_impl(3)
+                assert torch.equal(eng.query_points(net, *args), outs[1])
             wa = dfn.calc_volume_weights(args[3], args[1], outs[1][..., 3].contiguous())
             wb = dfn.calc_volume_weights(args[3], args[1], outs[2][..., 3].contiguous())
             tol = 1e-4 if prec == dfn.PREC_BF16X3 else 5e-2
