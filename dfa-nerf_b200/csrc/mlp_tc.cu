@@ -126,6 +126,21 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(X3 ? 256 : 384, 1)
             uint32_t off = L.woff;
             const uint32_t bytes = (uint32_t)L.n * 64u;
             for (int kbi = 0; kbi < L.nkb; ++kbi) {
+              if (!X3) {   // bf16: four single-stage entries ([n rows x 32 K], 16 KB), each refilled as soon as its two MMAs
+                           // retire (+2.5 % over two 32 KB entries; the issuer is otherwise paced by the tensor pipe's
+                           // operand fetch, not by its barrier waits -- a look-ahead barrier test changed nothing)
+                for (int kh = 0; kh < 2; ++kh) {
+                  const uint32_t e = cnt % N_STAGES, par = (cnt / N_STAGES) & 1u;
+                  mbar_wait(bar_empty + 8 * e, par ^ 1u);
+                  if (elect_one_sync()) {
+                    mbar_expect_tx(bar_full + 8 * e, bytes);
+                    if ((cnt & 1u) == crank)
+                      tma_bulk_load_mc(sbase + SMEM_RING + e * STAGE_BYTES, P.w_hi + off + kh * bytes, bytes, bar_full + 8 * e, (uint16_t)3);
+                  }
+                  __syncwarp();
+                  ++cnt;
+                }
+              } else
               for (int part = 0; part < NPART; ++part) {
                 const uint32_t pair = cnt % N_PAIRS, par = (cnt / N_PAIRS) & 1u;
                 mbar_wait(bar_empty + 8 * pair, par ^ 1u);
@@ -147,9 +162,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(X3 ? 256 : 384, 1)
         }
       }
       // tail: wait for the final release of every ring entry (it needs the peer CTA's remote arrival too)
-      for (uint32_t k = 0; k < (uint32_t)N_PAIRS && k < cnt; ++k) {
+      const uint32_t n_ent = X3 ? N_PAIRS : N_STAGES;
+      for (uint32_t k = 0; k < n_ent && k < cnt; ++k) {
         const uint32_t u = cnt - 1u - k;
-        mbar_wait(bar_empty + 8 * (u % N_PAIRS), (u / N_PAIRS) & 1u);
+        mbar_wait(bar_empty + 8 * (u % n_ent), (u / n_ent) & 1u);
       }
     }
   } else if (warp == 1) {
@@ -175,6 +191,23 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(X3 ? 256 : 384, 1)
               const uint32_t a_hi = sbase + (uint32_t)(s * TC_KB_PER_TILE + L.kb[kbi]) * KB_BYTES;
               const uint64_t adesc_hi = make_smem_desc(a_hi);
               const uint64_t adesc_lo = make_smem_desc(a_hi + TC_KB_PER_TILE * KB_BYTES);
+              if (!X3) {
+#pragma unroll
+                for (int kh = 0; kh < 2; ++kh) {
+                  const uint32_t e = cnt % N_STAGES, par = (cnt / N_STAGES) & 1u;
+                  long long t_f0 = 0;
+                  if (tr) t_f0 = clock64();
+                  mbar_wait(bar_full + 8 * e, par);
+                  tcgen05_fence_after();
+                  if (tr) t_full += clock64() - t_f0;
+                  const uint64_t bdesc = make_smem_desc_sw64(sbase + SMEM_RING + e * STAGE_BYTES);
+#pragma unroll
+                  for (int ks = 0; ks < 2; ++ks)
+                    umma_bf16(acc, adesc_hi + 2 * (2 * kh + ks), bdesc + (uint64_t)(ks * 2), idesc, (kbi | kh | ks) != 0 ? 1u : 0u);
+                  umma_commit_mc(bar_empty + 8 * e, (uint16_t)3);
+                  ++cnt;
+                }
+              } else
               for (int part = 0; part < NPART; ++part) {
                 const uint32_t pair = cnt % N_PAIRS, par = (cnt / N_PAIRS) & 1u;
                 long long t_f0 = 0;
