@@ -14,8 +14,8 @@ rnd = sys.argv[1] if len(sys.argv) > 1 else 'r01'
 out = []
 
 
-def launches():
-    p = os.path.join(ROOT, 'gpurun_out', 'launches_%s.csv' % rnd)
+def launches(suffix='', cmd='bench.py --steps 2 --warmup 3'):
+    p = os.path.join(ROOT, 'gpurun_out', 'launches_%s%s.csv' % (rnd, suffix))
     if not os.path.exists(p):
         return
     rows = list(csv.DictReader(l for l in open(p) if l.startswith('"')))
@@ -26,7 +26,7 @@ def launches():
         a[0] += 1
         a[1] += float(r['Metric Value'])
     tot = sum(v[1] for v in agg.values())
-    out.append('## Launch list (%s): ncu --metrics gpu__time_duration.sum --clock-control none, `bench.py --steps 2 --warmup 3`' % rnd)
+    out.append('## Launch list (%s): ncu --metrics gpu__time_duration.sum --clock-control none, `%s`' % (rnd, cmd))
     out.append('(cold-cache, serialised launches: compare SHARES, not absolutes; %d launches, %.1f ms total)\n' % (len(rows), tot / 1e6))
     out.append('%-52s %6s %12s %12s %8s' % ('kernel', 'n', 'total ms', 'avg us', 'share'))
     for k, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
@@ -69,9 +69,12 @@ def report(tag, title):
 
 
 launches()
+launches('_ht', 'bench.py --workload head_torso --steps 2 --warmup 3')
 report('bf16', 'mlp_tc_kernel<bf16>: 20,000 rays x 192 samples (fine-pass sized network query)')
 report('x3', 'mlp_pp_kernel<bf16x3>: 20,000 rays x 192 samples')
+report('dec_all', 'mlp_pp_kernel<bf16, Decoder>: 60,000 rays x 64 samples, head field then torso field (live model)')
 report('raw2outputs', 'volume_weights_kernel<1> (raw2outputs): 202,500 rays x 64 samples')
+report('headtorso', 'head_torso_kernel (live two-field compositing): 202,500 rays x 64 samples')
 path = os.path.join(ROOT, 'profiles', 'ncu_summary_%s.txt' % rnd)
 open(path, 'w').write('\n'.join(out) + '\n')
 print('\n'.join(out))
