@@ -119,3 +119,29 @@ def test_render_head_torso_fused_golden(dfn, golden):
     print('fused head+torso bf16  vs reference: rgb_head %.2e rgb_person %.2e'
           % (maxerr(rh16, g['rgb_head']), maxerr(rp16, g['rgb_person'])))
     assert maxerr(rh16, g['rgb_head']) < 0.1 and maxerr(rp16, g['rgb_person']) < 0.1
+
+
+def test_head_torso_full_frame_properties(dfn):
+    """BASELINE size (450x450 x 64, both fields, bf16): rays are independent, so any sharding of the frame into ray ranges
+    (the N-GPU split, a ragged 2048-ray chunking like MAIN:655) reproduces the whole-frame render bit for bit; the output
+    is finite and inside [0, 1] (a convex combination of sigmoid colours and the background)."""
+    H = W = 450
+    dec = make_decoder(dfn, 0)
+    fr, fr_t = synth.frame_inputs(H=H, W=W, seed=0), synth.frame_inputs(H=H, W=W, seed=7)
+    g = torch.Generator().manual_seed(0)
+    zs, za = torch.randn(1, 2, 256, generator=g).to(DEV), torch.randn(1, 2, 256, generator=g).to(DEV)
+    sig, sig_t = torch.randn(1, 96, generator=g).to(DEV), torch.randn(1, 42, generator=g).to(DEV)
+    bc = fr['bc_rgb'].to(DEV)
+
+    def run(rng=None):
+        return dfn.render_head_torso(dec, H, W, fr['focal'], fr['c2w'], fr_t['c2w'], bc, zs, za, sig, sig_t, fr['near'], fr['far'],
+                                     fr['cx'], fr['cy'], N_samples=64, ray_range=rng, precision=dfn.PREC_BF16)
+    head, person = run()
+    assert person.shape == (H * W, 3) and torch.isfinite(person).all() and torch.isfinite(head).all()
+    assert person.min().item() >= -1e-6 and person.max().item() <= 1 + 1e-5
+    from dfa_nerf_b200.distributed import shard_range
+    parts = [run(shard_range(H * W, r, 8)[:2])[1] for r in range(8)]
+    assert torch.equal(torch.cat(parts, 0), person)
+    n = H * W
+    tail = run((n - 1796, n))[1]            # the reference's short last chunk (202,500 = 98 x 2048 + 1796)
+    assert torch.equal(tail, person[n - 1796:])
