@@ -36,6 +36,10 @@ class DecoderDesc(C.Structure):
                                        'n_blocks', 'skip')]
 
 
+class ConvStack(C.Structure):
+    _fields_ = [('n', C.c_int), ('ch', C.c_int * 7), ('stride', C.c_int), ('w', C.c_void_p * 6), ('b', C.c_void_p * 6)]
+
+
 class HeadTorsoIO(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ('rays_o_head', 'rays_d_head', 'rays_o_torso', 'rays_d_torso', 'near', 'far',
                                           't_vals', 'bc_rgb', 'z_shape', 'z_app', 'signal', 'signal_torso', 'rgb_head',
@@ -69,6 +73,9 @@ def _load():
         'dfn_invert_cdf': (i32, [i32, i32, vp, vp, i32, vp, i32, vp, vp, vp]),
         'dfn_sort_merge': (i32, [i32, i32, vp, i32, vp, vp, vp]),
         'dfn_to8b': (i32, [i64, vp, vp, vp]),
+        'dfn_audionet_forward': (i32, [i32, i32, vp, C.POINTER(ConvStack), vp, vp, vp, vp, vp, vp]),
+        'dfn_att_smooth': (i32, [i32, i32, i32, i32, vp, vp, C.POINTER(ConvStack), vp, vp, vp, vp]),
+        'dfn_pose_signal': (i32, [i32, vp, i32, i32, vp, vp, vp]),
         'dfn_model_create': (i32, [C.POINTER(ModelDesc), C.POINTER(vp)]),
         'dfn_model_destroy': (None, [vp]),
         'dfn_model_num_tensors': (i32, [vp]),
@@ -101,7 +108,7 @@ def _load():
 lib = _load()
 EXPORTS = ['dfn_abi_version', 'dfn_last_error', 'dfn_last_launch_count', 'dfn_profile_enable', 'dfn_profile_collect', 'dfn_debug_trace', 'dfn_debug_set_impl', 'dfn_get_rays', 'dfn_z_vals', 'dfn_make_points', 'dfn_embed',
            'dfn_composite_fields', 'dfn_composite_head_torso', 'dfn_linear', 'dfn_calc_volume_weights', 'dfn_raw2outputs', 'dfn_sample_pdf', 'dfn_invert_cdf',
-           'dfn_sort_merge', 'dfn_to8b', 'dfn_model_create', 'dfn_model_destroy', 'dfn_model_num_tensors', 'dfn_model_load',
+           'dfn_sort_merge', 'dfn_to8b', 'dfn_audionet_forward', 'dfn_att_smooth', 'dfn_pose_signal', 'dfn_model_create', 'dfn_model_destroy', 'dfn_model_num_tensors', 'dfn_model_load',
            'dfn_mlp_workspace_bytes', 'dfn_mlp_forward', 'dfn_query_workspace_bytes', 'dfn_query_points',
            'dfn_render_workspace_bytes', 'dfn_render_rays', 'dfn_decoder_create', 'dfn_decoder_destroy',
            'dfn_decoder_num_tensors', 'dfn_decoder_load', 'dfn_decoder_query_workspace_bytes', 'dfn_decoder_query',

@@ -11,7 +11,7 @@ namespace dfn {
 static constexpr int BM = 64, BN = 64, BK = 16;
 
 // Y[p, n] = act(sum_k X(p,k) * W[n,k] + b[n]) (+ A[p*ld_add + n]),  X(p,k) = k<K1 ? X1[p*ld1+k] : X2[p*ld2+k-K1]
-// act & 3: 0 none, 1 relu, 2 sigmoid; act & 4: the addend is added BEFORE the activation (DEC:331-340) instead
+// act & 3: 0 none, 1 relu, 2 sigmoid, 3 LeakyReLU(0.02) (HELP:171); act & 4: the addend is added BEFORE the activation (DEC:331-340) instead
 // of after it (DEC:316-325).  A row stride of 0 broadcasts one row (per-frame latent terms, DEC:311,319).
 __global__ void __launch_bounds__(256)
 linear_fp32_kernel(int64_t P, int N, int K1, int K2, const float* __restrict__ X1, int64_t ld1,
@@ -74,6 +74,7 @@ linear_fp32_kernel(int64_t P, int N, int K1, int K2, const float* __restrict__ X
       if (addend && (relu & 4)) v += addend[p * ld_add + n];
       if ((relu & 3) == 1) v = fmaxf(v, 0.f);
       else if ((relu & 3) == 2) v = __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-v)));
+      else if ((relu & 3) == 3) v = v > 0.f ? v : __fmul_rn(0.02f, v);   // nn.LeakyReLU(0.02) of the latent encoders
       if (addend && !(relu & 4)) v += addend[p * ld_add + n];
       Y[p * ldy + n] = v;
     }
@@ -100,7 +101,7 @@ extern "C" int dfn_linear(int64_t P, int N, int K1, const float* X1, int64_t ld1
                           const float* W, const float* bias, int act, const float* addend, int64_t ld_add, float* Y,
                           int64_t ldy, void* stream) {
   using namespace dfn;
-  DFN_CHECK_ARG(P > 0 && N > 0 && K1 > 0 && K2 >= 0 && X1 && W && Y && (K2 == 0 || X2) && act >= 0 && act <= 7 && (act & 3) != 3 && ldy >= N,
+  DFN_CHECK_ARG(P > 0 && N > 0 && K1 > 0 && K2 >= 0 && X1 && W && Y && (K2 == 0 || X2) && act >= 0 && act <= 7 && ldy >= N,
                 "dfn_linear: bad argument");
   dim3 grid(ceil_div(P, BM), ceil_div(N, BN));
   linear_fp32_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(P, N, K1, K2, X1, ld1, X2, ld2, W, bias, act, Y, ldy, addend,

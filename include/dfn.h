@@ -153,7 +153,7 @@ int dfn_model_load(dfn_model* m, const float* const* tensors_host, int n_tensors
 /* One fused nn.Linear of the fp32 path: Y[p,n] = act(sum_k X(p,k) W[n,k] + bias[n]) (+ addend[p*ld_add + n]);
  * X(p,k) = k < K1 ? X1[p*ld1 + k] : X2[p*ld2 + k-K1] (concatenated inputs are never materialised; a row
  * stride of 0 broadcasts one row, e.g. the per-frame signal of DEC:293-295).  act & 3: 0 none, 1 relu,
- * 2 sigmoid; act & 4: addend is added before the activation instead of after it.
+ * 2 sigmoid, 3 LeakyReLU(0.02); act & 4: addend is added before the activation instead of after it.
  * bias / X2 / addend may be null.  Building block of the Decoder / DeformationField_ori shim (DEC:109-349). */
 int dfn_linear(int64_t P, int N, int K1, const float* X1, int64_t ld1, int K2, const float* X2, int64_t ld2,
                const float* W, const float* bias, int act, const float* addend, int64_t ld_add, float* Y,
@@ -236,6 +236,35 @@ typedef struct {
 int64_t dfn_render_head_torso_workspace_bytes(const dfn_decoder* m, int64_t R, int S);
 int dfn_render_head_torso(const dfn_decoder* m, int64_t R, int S, const dfn_head_torso_io* io, int precision,
                           void* workspace, int64_t workspace_bytes, void* stream);
+
+/* ---- latent encoders: the callers of the path  (HELP:109-240, MAIN:28-111) -----------
+ * The MLP encoders (AudioNet_W2L HELP:165, ExpressionEnc HELP:182) are chains of dfn_linear with act = 3.
+ * A conv stack is `n` Conv1d(kernel 3, padding 1, one common stride) layers, each followed by LeakyReLU(0.02);
+ * w[i] is [ch[i+1], ch[i], 3], b[i] is [ch[i+1]]; all DEVICE pointers. */
+typedef struct {
+  int n;             /* number of conv layers (<= 6) */
+  int ch[7];         /* channels: ch[0] input ... ch[n] output */
+  int stride;        /* 2 (AudioNet) or 1 (AudioAttNet) */
+  const float* w[6];
+  const float* b[6];
+} dfn_conv_stack;
+
+/* AudioNet.forward (HELP:133-141): x [N,16,29] (DeepSpeech windows) -> out [N,dim_aud]; four stride-2 convs
+ * (29->32->32->64->64 over 16->8->4->2->1 steps), Linear(64,64)+LeakyReLU, Linear(64,dim_aud).  win_size must be 16. */
+int dfn_audionet_forward(int N, int dim_aud, const float* x, const dfn_conv_stack* convs, const float* fc1_w,
+                         const float* fc1_b, const float* fc2_w, const float* fc2_b, float* out, void* stream);
+
+/* AudioAttNet.forward over a whole sequence (HELP:232-240 with the window logic of MAIN:35-61 / MAIN:85-101):
+ * feats [N,D] per-frame features; for frame i the window is rows [i-seq_len/2, i+seq_len/2), rows outside [0,N)
+ * replaced by pad_row [D] (the features of an all-zero input, as the reference pads before encoding); attention
+ * weights from the first dim_att columns (five stride-1 convs, Linear(seq,seq), softmax) applied to all D columns.
+ * out [N,D].  seq_len even, <= 16; D <= 128. */
+int dfn_att_smooth(int N, int D, int dim_att, int seq_len, const float* feats, const float* pad_row,
+                   const dfn_conv_stack* convs, const float* lin_w, const float* lin_b, float* out, void* stream);
+
+/* pose_to_euler_trans + Embedder (MAIN:182-205, MAIN:106-109): poses [N, pose_stride floats] row-major 3x4 or 4x4
+ * (pose_stride 12 or 16) -> out [N, 2*(3+6L)] = [embed_L(euler) | embed_L(trans)]; et_out (nullable) [N,6] = euler|trans. */
+int dfn_pose_signal(int N, const float* poses, int pose_stride, int L, float* out, float* et_out, void* stream);
 
 /* ---- render_rays  (upstream name; MAIN:114 is the reference's dead stub) -----------------------
  * coarse pass (N_samples) -> raw2outputs -> sample_pdf(z_mid, w[1:-1], N_importance) -> sort-merge

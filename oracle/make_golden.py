@@ -300,6 +300,45 @@ def main():
     save('head_torso', H=fr2['H'], W=fr2['W'], focal=fr2['focal'], cx=fr2['cx'], cy=fr2['cy'], near=fr2['near'], far=fr2['far'],
          c2w=fr2['c2w'], c2w_torso=synth.camera_pose(10), bc_rgb=fr2['bc_rgb'], z_shape=z_shape, z_app=z_app,
          signal=sig_h, signal_torso=sig_t, rgb_head=rgb_head, rgb_person=rgb_person, seed=5)
+    # ---- latent encoders, the callers of the path -----------------------------
+    print('encoders (HELP:109-240) + encode_signal / encode_signal_torso (MAIN:28-111)')
+    ge = torch.Generator().manual_seed(77)
+    sd_an = synth.audionet_state_dict(0)
+    x_an = torch.randn(5, 16, 29, generator=ge)
+    y_an = ref_module(HELP.AudioNet, sd_an, dim_aud=76, win_size=16)(x_an)
+    same(O.audionet_forward(sd_an, x_an), y_an, 'AudioNet')
+    sd_w2l, sd_exp = synth.mlp_encoder_state_dict(1), synth.mlp_encoder_state_dict(2, (64, 32, 32))
+    m_w2l, m_exp = ref_module(HELP.AudioNet_W2L, sd_w2l), ref_module(HELP.ExpressionEnc, sd_exp)
+    n_fr = 20
+    auds, exps = torch.randn(n_fr, 512, generator=ge), torch.randn(n_fr, 64, generator=ge)
+    same(O.mlp_encoder_forward(sd_w2l, auds), m_w2l(auds), 'AudioNet_W2L')
+    same(O.mlp_encoder_forward(sd_exp, exps), m_exp(exps), 'ExpressionEnc')
+    sd_att = synth.audio_att_state_dict(3, 96, 4)          # scripts/test_obama.sh: --dim_aud=96 --smo_size=4
+    m_att = ref_module(HELP.AudioAttNet, sd_att, dim_aud=96, seq_len=4)
+    sd_patt = synth.audio_att_state_dict(4, 42, 8)         # --smo_torse_size 8, dim_torso_signal = 42 (MAIN:515-516)
+    m_patt = ref_module(HELP.AudioAttNet, sd_patt, dim_aud=42, seq_len=8)
+    args = types.SimpleNamespace(nosmo_iters=10, smo_size=4, smo_torse_size=8)
+    ds = [{'auds': auds, 'exp': exps}]
+    sig_plain = torch.cat([MAIN.encode_signal(ds, 0, i, 96, m_w2l, m_exp, m_att, 0, args, n_fr)[0] for i in range(n_fr)], 0)
+    sig_smooth = torch.cat([MAIN.encode_signal(ds, 0, i, 96, m_w2l, m_exp, m_att, 20, args, n_fr)[0] for i in range(n_fr)], 0)
+    same(torch.cat([O.encode_signal(auds, exps, i, sd_w2l, sd_exp) for i in range(n_fr)], 0), sig_plain, 'encode_signal (no smoothing)')
+    same(torch.cat([O.encode_signal(auds, exps, i, sd_w2l, sd_exp, sd_att, 4, 96) for i in range(n_fr)], 0), sig_smooth,
+         'encode_signal (AudioAttNet window)')
+    # rot_to_euler hard-codes .cuda() (MAIN:184): run it on the CPU by making .cuda() the identity for this call
+    poses = synth.pose_sequence(12, 0)
+    embed_fn, _ = HELP.get_embedder(3, 0)
+    dsp = [{'poses': poses}]
+    cuda_attr = torch.Tensor.cuda
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    try:
+        t_plain = torch.cat([MAIN.encode_signal_torso(dsp, 0, i, m_patt, 0, args, 12, embed_fn=embed_fn).reshape(1, -1) for i in range(12)], 0)
+        t_smooth = torch.cat([MAIN.encode_signal_torso(dsp, 0, i, m_patt, 20, args, 12, embed_fn=embed_fn).reshape(1, -1) for i in range(12)], 0)
+    finally:
+        torch.Tensor.cuda = cuda_attr
+    same(torch.cat([O.encode_signal_torso(poses, i) for i in range(12)], 0), t_plain, 'encode_signal_torso (no smoothing)')
+    same(torch.cat([O.encode_signal_torso(poses, i, sd_patt, 8, 3) for i in range(12)], 0), t_smooth, 'encode_signal_torso (pose AudioAttNet)')
+    save('encoders', x_audionet=x_an, y_audionet=y_an, auds=auds, exps=exps, sig_plain=sig_plain, sig_smooth=sig_smooth,
+         poses=poses, torso_plain=t_plain, torso_smooth=t_smooth)
     print('golden vectors written to', OUT)
 
 

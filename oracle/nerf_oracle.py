@@ -410,6 +410,107 @@ def facenerf_forward_bf16(sd, x, **kw):
     return torch.cat([rgb, alpha], -1)
 
 
+# --------------------------------------------- latent encoders (callers of the path)
+
+
+def _leaky(x):
+    return F.leaky_relu(x, 0.02)
+
+
+def audionet_forward(sd, x, win_size=16):
+    """HELP:109-141 AudioNet: x [N,16,29] -> [N,dim_aud] (four stride-2 Conv1d + two Linear, LeakyReLU(0.02))."""
+    half_w = int(win_size / 2)
+    x = x[:, 8 - half_w:8 + half_w, :].permute(0, 2, 1)
+    for i in (0, 2, 4, 6):
+        x = _leaky(F.conv1d(x, sd['encoder_conv.%d.weight' % i], sd['encoder_conv.%d.bias' % i], stride=2, padding=1))
+    x = x.squeeze(-1)
+    x = _leaky(F.linear(x, sd['encoder_fc1.0.weight'], sd['encoder_fc1.0.bias']))
+    return F.linear(x, sd['encoder_fc1.2.weight'], sd['encoder_fc1.2.bias'])
+
+
+def mlp_encoder_forward(sd, x):
+    """HELP:165-178 AudioNet_W2L (512->256->128->64) / HELP:182-193 ExpressionEnc (64->32->32): Linear + LeakyReLU(0.02)
+    chain over `encoder.{0,2,..}`, no activation after the last layer."""
+    idx = sorted(int(k.split('.')[1]) for k in sd if k.endswith('.weight'))
+    for j, i in enumerate(idx):
+        x = F.linear(x, sd['encoder.%d.weight' % i], sd['encoder.%d.bias' % i])
+        if j + 1 < len(idx):
+            x = _leaky(x)
+    return x
+
+
+def audio_att_forward(sd, x, dim_aud, seq_len):
+    """HELP:210-240 AudioAttNet: x [seq_len, D] -> [D]: attention weights from the first dim_aud columns (five Conv1d k=3
+    + LeakyReLU, Linear(seq,seq), softmax) applied to ALL D columns."""
+    y = x[..., :dim_aud].permute(1, 0).unsqueeze(0)
+    for i in (0, 2, 4, 6, 8):
+        y = _leaky(F.conv1d(y, sd['attentionConvNet.%d.weight' % i], sd['attentionConvNet.%d.bias' % i], stride=1, padding=1))
+    y = F.linear(y.view(1, seq_len), sd['attentionNet.0.weight'], sd['attentionNet.0.bias'])
+    y = torch.softmax(y, dim=1).view(seq_len, 1)
+    return torch.sum(y * x, dim=0)
+
+
+def _window(x, img_i, half, n):
+    """MAIN:36-61 / MAIN:86-101: rows [img_i-half, img_i+half) of x, zero rows where the window leaves [0, n)."""
+    left_i, right_i = img_i - half, img_i + half
+    pad_left, pad_right = 0, 0
+    if left_i < 0:
+        pad_left, left_i = -left_i, 0
+    if right_i > n:
+        pad_right, right_i = right_i - n, n
+    win = x[left_i:right_i]
+    if pad_left > 0:
+        win = torch.cat((torch.zeros_like(win)[:pad_left], win), dim=0)
+    if pad_right > 0:
+        win = torch.cat((win, torch.zeros_like(win)[:pad_right]), dim=0)
+    return win
+
+
+def encode_signal(auds, exps, img_i, sd_aud, sd_exp, sd_att=None, smo_size=8, dim_aud=64, n=None):
+    """MAIN:28-68, itr_obj == 0: the head's per-frame signal [1, 64+32].  sd_att=None is the global_step < nosmo_iters
+    branch (MAIN:63-66); otherwise the smoothing window + AudioAttNet of MAIN:35-61."""
+    n = auds.shape[0] if n is None else n
+    if sd_att is None:
+        return torch.cat([mlp_encoder_forward(sd_aud, auds[img_i:img_i + 1]), mlp_encoder_forward(sd_exp, exps[img_i:img_i + 1])], 1)
+    half = int(smo_size / 2)
+    win = torch.cat([mlp_encoder_forward(sd_aud, _window(auds, img_i, half, n)),
+                     mlp_encoder_forward(sd_exp, _window(exps, img_i, half, n))], 1)
+    return audio_att_forward(sd_att, win, dim_aud, smo_size).unsqueeze(0)
+
+
+def rot_to_euler(R):
+    """MAIN:182-199."""
+    e = torch.ones((R.shape[0], 3))
+    e[:, 2] = torch.atan2(R[:, 0, 0], -R[:, 0, 1])
+    e[:, 1] = torch.asin(-R[:, 0, 2])
+    e[:, 0] = torch.atan2(R[:, 2, 2], R[:, 1, 2])
+    return e
+
+
+def pose_to_euler_trans(poses):
+    """MAIN:202-205."""
+    return torch.cat((rot_to_euler(poses), poses[:, :3, 3]), dim=1)
+
+
+def encode_signal_torso(poses, img_i, sd_att=None, smo_size=4, multires=3, n=None):
+    """MAIN:78-111: the torso signal [1, 42] = Embedder_3(euler) | Embedder_3(trans) of the head pose (optionally
+    smoothed by the pose AudioAttNet over a window of euler/trans rows, zero rows outside the sequence)."""
+    n = poses.shape[0] if n is None else n
+    if sd_att is None:
+        et = pose_to_euler_trans(poses[img_i].unsqueeze(0))
+        return torch.cat((embed(et[:, :3], multires), embed(et[:, 3:], multires)), dim=1)
+    half = int(smo_size / 2)
+    left_i, right_i = max(img_i - half, 0), min(img_i + half, n)
+    et = pose_to_euler_trans(poses[left_i:right_i])
+    pad_left, pad_right = max(half - img_i, 0), max(img_i + half - n, 0)
+    if pad_left > 0:
+        et = torch.cat((torch.zeros_like(et)[:pad_left], et), dim=0)
+    if pad_right > 0:
+        et = torch.cat((et, torch.zeros_like(et)[:pad_right]), dim=0)
+    et_embed = torch.cat((embed(et[:, :3], multires), embed(et[:, 3:], multires)), dim=1)
+    return audio_att_forward(sd_att, et_embed, et_embed.shape[1], smo_size).unsqueeze(0)
+
+
 def to8b(x):
     """HELP:17."""
     return (255 * np.clip(x, 0, 1)).astype(np.uint8)

@@ -111,6 +111,49 @@ def decoder_state_dict(seed=0, hidden=256, z_dim=256, dim_signal=96, dim_et=42, 
     return sd
 
 
+def _conv1d(gen, sd, name, c_in, c_out, k=3):
+    b = 1. / math.sqrt(c_in * k)       # nn.Conv1d default init
+    sd[name + '.weight'] = _uniform(gen, (c_out, c_in, k), b)
+    sd[name + '.bias'] = _uniform(gen, (c_out,), b)
+
+
+def audionet_state_dict(seed=0, dim_aud=76):
+    """HELP:109-132 AudioNet."""
+    g, sd = torch.Generator().manual_seed(seed), {}
+    for i, (ci, co) in zip((0, 2, 4, 6), ((29, 32), (32, 32), (32, 64), (64, 64))):
+        _conv1d(g, sd, 'encoder_conv.%d' % i, ci, co)
+    _linear(g, sd, 'encoder_fc1.0', 64, 64)
+    _linear(g, sd, 'encoder_fc1.2', 64, dim_aud)
+    return sd
+
+
+def mlp_encoder_state_dict(seed=0, dims=(512, 256, 128, 64)):
+    """HELP:165-178 AudioNet_W2L (default dims) / HELP:182-193 ExpressionEnc (dims=(64, 32, 32))."""
+    g, sd = torch.Generator().manual_seed(seed), {}
+    for j in range(len(dims) - 1):
+        _linear(g, sd, 'encoder.%d' % (2 * j), dims[j], dims[j + 1])
+    return sd
+
+
+def audio_att_state_dict(seed=0, dim_aud=64, seq_len=8):
+    """HELP:210-231 AudioAttNet."""
+    g, sd = torch.Generator().manual_seed(seed), {}
+    ch = (dim_aud, 16, 8, 4, 2, 1)
+    for j in range(5):
+        _conv1d(g, sd, 'attentionConvNet.%d' % (2 * j), ch[j], ch[j + 1])
+    _linear(g, sd, 'attentionNet.0', seq_len, seq_len)
+    return sd
+
+
+def pose_sequence(n, seed=0):
+    """[n,4,4] head poses with the synthetic camera statistics (camera_pose per frame)."""
+    out = torch.zeros(n, 4, 4)
+    for i in range(n):
+        out[i, :3] = camera_pose(seed + i)
+        out[i, 3, 3] = 1.
+    return out
+
+
 def euler_to_rot(e):
     """Rx(theta) Ry(phi) Rz(psi) rotation for synthetic head poses."""
     t, p, s = [float(v) for v in e]

@@ -134,5 +134,23 @@ def test_bf16_restatement_is_close_to_fp32(golden):
     assert (y[:, :3] - g['y_face'][:, :3]).abs().max() < 5e-2
 
 
+def test_encoders(golden):
+    """Latent encoders and the per-frame signal assembly (HELP:109-240, MAIN:28-111) against the reference's outputs."""
+    g = golden('encoders')
+    with torch.no_grad():
+        close(O.audionet_forward(synth.audionet_state_dict(0), g['x_audionet']), g['y_audionet'], 1e-6)
+        sd_a, sd_e = synth.mlp_encoder_state_dict(1), synth.mlp_encoder_state_dict(2, (64, 32, 32))
+        n = g['auds'].shape[0]
+        plain = torch.cat([O.encode_signal(g['auds'], g['exps'], i, sd_a, sd_e) for i in range(n)], 0)
+        smooth = torch.cat([O.encode_signal(g['auds'], g['exps'], i, sd_a, sd_e, synth.audio_att_state_dict(3, 96, 4), 4, 96)
+                            for i in range(n)], 0)
+        close(plain, g['sig_plain'], 1e-6)
+        close(smooth, g['sig_smooth'], 1e-6)
+        m = g['poses'].shape[0]
+        close(torch.cat([O.encode_signal_torso(g['poses'], i) for i in range(m)], 0), g['torso_plain'], 1e-6)
+        close(torch.cat([O.encode_signal_torso(g['poses'], i, synth.audio_att_state_dict(4, 42, 8), 8, 3) for i in range(m)], 0),
+              g['torso_smooth'], 1e-6)
+
+
 def test_to8b():
     assert np.array_equal(O.to8b(np.array([-1., 0., 0.5, 1., 2.])), np.array([0, 0, 127, 255, 255], np.uint8))
