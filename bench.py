@@ -5,6 +5,8 @@
     python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
     python bench.py --impl reference            # CPU arm: the oracle port on the host cores
     python bench.py --workload head_torso       # BASELINE.json configs[2]: the reference's live two-field frame
+    python bench.py --workload mlp_1m           # configs[3]: flat 8x256 NeRF query, 2^20 rays x 192 samples (roofline sweep)
+    python bench.py --workload sequence --steps 1   # configs[4]: driven sequence (--frames N, default 300), frames sharded
 
 One step = one 450x450 frame (202,500 rays) x (64 coarse + 128 fine samples) of the synthetic
 FaceNeRF field (configs[1] of BASELINE.json): get_rays -> z sampling -> PE + 8x256 skip-MLP ->
@@ -144,6 +146,10 @@ WORKLOADS = {
     'head_torso': 'Decoder head + torso (DeformationField_ori) two-field frame, 450x450 x 64 samples, synthetic seeded '
                   'weights/poses/latents (BASELINE.json configs[2], the path scripts/test_obama.sh runs); one step = one frame',
 }
+WORKLOADS['mlp_1m'] = 'Synthetic random-weight 8x256 NeRF (no latent), 2^20 rays x 192 samples, flat network query + compositing ' \
+                      '(BASELINE.json configs[3]); one step = all rays'
+WORKLOADS['sequence'] = 'Audio-driven FaceNeRF sequence, 450x450 x (64+128) per frame, per-frame pose + latent tables, uint8 frames ' \
+                        'copied out double-buffered, FRAMES sharded over the GPUs (BASELINE.json configs[4]); one step = the sequence'
 CPU_RAYS = 8192   # bounded CPU sample per step (four chunks of 2048 at the image centre; ~4 s on 16 cores)
 
 
@@ -152,7 +158,7 @@ def run_reference(args):
     if rank != 0:
         return
     rays = CPU_RAYS
-    arm = cpu_arm if args.workload == 'facenerf' else cpu_arm_head_torso
+    arm = cpu_arm_head_torso if args.workload == 'head_torso' else cpu_arm
     value, sec, cores = arm(max(1, args.steps), max(1, min(args.warmup, 1)), rays)
     evals = '(64+192) FaceNeRF' if args.workload == 'facenerf' else '(64 head + 64 torso) Decoder'
     sample = '%d rays (4 chunks of 2048, image centre) x %s evaluations per step, median of %d' % (rays, evals, max(1, args.steps))
@@ -175,6 +181,7 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--precision', default='bf16', choices=['bf16', 'bf16x3', 'fp32'])
     ap.add_argument('--workload', default='facenerf', choices=sorted(WORKLOADS))
+    ap.add_argument('--frames', type=int, default=300, help='sequence workload: frames per step')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     args = ap.parse_args()
     if args.impl == 'reference':
@@ -224,6 +231,47 @@ def main():
                                    ray_range=(b, e), want=('rgb_map',))
             launches[0] += eng.last_launches + 1            # + get_rays
             return out['rgb_map']
+    elif args.workload == 'mlp_1m':
+        n_rays = 1 << 20
+        b, e, per = shard_range(n_rays, rank, world)
+        S = N_SAMPLES + N_IMPORTANCE
+        net = dfn.NeRF(D=8, W=256, input_ch=63, input_ch_views=27, output_ch=4, skips=[4], use_viewdirs=True)
+        net.load_state_dict(synth.nerf_state_dict(0))
+        net = net.to(dev)
+        eng = dfn.RenderEngine(net, None, S, 0, precision=prec)
+        g = torch.Generator().manual_seed(0)
+        n_loc = e - b
+        ro = fr['c2w'][:3, -1].expand(n_loc, 3).contiguous().to(dev)
+        rd = (torch.randn(n_loc, 3, generator=g) * 0.2 + torch.tensor([0., 0., -1.])).to(dev)
+        vd = rd / torch.norm(rd, dim=-1, keepdim=True)
+        z, _ = torch.sort(torch.rand(n_loc, S, generator=g) * 0.6 + 0.4, -1)
+        z = z.to(dev)
+        bc_dev = torch.rand(n_rays, 3, generator=g).to(dev)
+        bc_host = bc_dev.cpu().pin_memory()
+        rgb_host = torch.empty((n_rays, 3), dtype=torch.float32).pin_memory()
+        aud_dev, lat_host = torch.zeros(1, device=dev), torch.zeros(1).pin_memory()
+        evals_per_ray = S
+        kernel_name = 'mlp_tc_kernel<bf16>' if prec == dfn.PREC_BF16 else 'mlp_pp_kernel<bf16x3>'
+        flops_note = 'algorithmic, viewdir columns folded: 2*557,184 per MLP evaluation (NeRF and FaceNeRF coincide, SURVEY 8d)'
+
+        def render(bc_full, lat):
+            raw = eng.query_points(net, ro, rd, vd, z, None)
+            launches[0] += eng.last_launches + 1
+            return dfn.raw2outputs(raw, z, rd, bc_full[b:e])[0]
+    elif args.workload == 'sequence':
+        def mk(seed):
+            m = dfn.FaceNeRF(D=8, W=256, input_ch=63, input_ch_views=27, dim_aud=64, output_ch=4, skips=[4], use_viewdirs=True)
+            m.load_state_dict(synth.facenerf_state_dict(seed))
+            return m.to(dev)
+        eng = dfn.RenderEngine(mk(0), mk(1), N_SAMPLES, N_IMPORTANCE, precision=prec)
+        seq = synth.frame_inputs(H=H, W=W, seed=0, n_frames=args.frames)
+        evals_per_ray = N_SAMPLES + N_SAMPLES + N_IMPORTANCE
+        kernel_name = 'mlp_tc_kernel<bf16>' if prec == dfn.PREC_BF16 else 'mlp_pp_kernel<bf16x3>'
+        flops_note = 'algorithmic, latent/viewdir columns folded: 2*557,184 per MLP evaluation (BASELINE.md section 2)'
+        n_rays = H * W * args.frames            # rays per step: the whole sequence
+        b, e = 0, n_rays
+        lat_host = seq['aud'].pin_memory()
+        aud_dev = None
     else:
         if prec == dfn.PREC_FP32:
             raise SystemExit('--workload head_torso runs on the tensor-core path: --precision bf16 | bf16x3')
@@ -247,11 +295,23 @@ def main():
             launches[0] += dfn.render_head_torso.last_launches
             return rgb
 
+    def step_sequence(n=None):
+        # pose / latent tables from (pinned) host memory, uint8 frames back to pinned host memory: this IS the end-to-end path
+        n = args.frames if n is None else n
+        frames = dfn.render_sequence(eng, H, W, seq['focal'], seq['c2w_seq'][:n], lat_host[:n], bc_dev, seq['near'], seq['far'],
+                                     seq['cx'], seq['cy'])
+        launches[0] += (eng.last_launches + 2) * ((n + world - 1) // world)
+        return frames
+
     def step_resident():
+        if args.workload == 'sequence':
+            return step_sequence()
         rgb = render(bc_dev, aud_dev)
         return gather_rgb(rgb, n_rays) if world > 1 else rgb
 
     def step_e2e():
+        if args.workload == 'sequence':
+            return step_sequence()
         bc = bc_host[b:e].to(dev, non_blocking=True)
         lat = lat_host.to(dev, non_blocking=True)
         bc_full = torch.empty((n_rays, 3), dtype=torch.float32, device=dev)
@@ -286,7 +346,10 @@ def main():
     # ---- device-resident throughput, with per-launch events around the tcgen05 kernel ---------------
     sampler = ClockSampler(local_rank)
     for _ in range(args.warmup):
-        step_resident()
+        if args.workload == 'sequence':
+            step_sequence(min(args.frames, 2 * world))     # warm-up on a short prefix of the sequence
+        else:
+            step_resident()
     torch.cuda.synchronize()
     dfn.lib.dfn_profile_enable(1 if prec != dfn.PREC_FP32 else 0)
     launches[0] = 0
@@ -300,10 +363,12 @@ def main():
     value = n_rays / (ms_step * 1e-3)
 
     # ---- end to end through the public API with host buffers ------------------------------------------
-    ms_e2e = timed(step_e2e, args.steps, 2)
+    ms_e2e = ms_step if args.workload == 'sequence' else timed(step_e2e, args.steps, 2)   # the sequence step IS end to end
     e2e = {'value': n_rays / (ms_e2e * 1e-3), 'unit': 'rays/s',
            'h2d_bytes_per_step': int((e - b) * 12 + lat_host.numel() * 4 + 48),
            'd2h_bytes_per_step': int(n_rays * 12) if rank == 0 else 0}
+    if args.workload == 'sequence':
+        e2e.update(h2d_bytes_per_step=int(lat_host.numel() * 4 + args.frames * 48), d2h_bytes_per_step=int(n_rays * 3))
 
     pk = peaks()
     roofline = None
@@ -318,7 +383,7 @@ def main():
                     'peak_source': 'bf16 dense sustained, ' + pk['source']}
 
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and args.workload in ('facenerf', 'head_torso'):
         v, sec, cores = (cpu_arm if args.workload == 'facenerf' else cpu_arm_head_torso)(3, 1, CPU_RAYS)
         cpu = {'value': v, 'unit': 'rays/s', 'cores': cores, 'kind': 'port',
                'sample': '%d rays (4 chunks of 2048, image centre) x %d network evaluations per ray, median of 3 (%.1f s each)'
@@ -332,7 +397,8 @@ def main():
             'data': 'synthetic',
             'config': {'workload': WORKLOADS[args.workload],
                        'rays_per_step': n_rays, 'mlp_evals_per_ray': evals_per_ray, 'precision': args.precision,
-                       'parallelism': 'rays sharded over %d GPU(s), one all-gather of the RGB tile' % world,
+                       'parallelism': ('frames sharded over %d GPU(s), one all-gather of the uint8 frames at the end' % world)
+                       if args.workload == 'sequence' else 'rays sharded over %d GPU(s), one all-gather of the RGB tile' % world,
                        'l2': 'per-step intermediates (~1.4 GB of raw/z buffers) exceed the 126 MB L2; no explicit flush'},
             'e2e': e2e, 'gpu_launches': n_launch, 'clocks': clocks, 'roofline': roofline, 'cpu_baseline': cpu,
         }))
