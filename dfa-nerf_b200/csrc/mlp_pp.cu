@@ -78,6 +78,16 @@ __device__ __forceinline__ int layer_staged(const TcLayer& L) {
   return -1;
 }
 __device__ __forceinline__ bool layer_has_pe(const TcLayer& L) { return layer_staged(L) >= 0; }
+// bf16x3 (one tile, cooperative epilogue): the epilogue signals every finished 64-column activation block -- blocks
+// before the last on `kready[k]`, the last one (or an epilogue that writes none) on `aready` -- so the next layer's MMAs
+// start on block 0 while blocks 1.. are still being drained from the OTHER accumulator buffer (one tile leaves TMEM
+// columns 256..511 free for double buffering by layer).  One barrier per block: a single multi-phase barrier would
+// run two phases ahead of its waiter and alias parities.  Number of signals of a layer's epilogue:
+__device__ __forceinline__ int layer_phases(const TcLayer& L, int view_w) {
+  if (L.epi == TC_EPI_RELU) return L.n >= 64 ? (int)L.n >> 6 : 1;
+  if (L.epi == TC_EPI_VIEW0) return view_w >> 6;
+  return 1;
+}
 template <int NPART>
 __device__ __forceinline__ uint32_t layer_entries(const TcLayer& L) {
   return (uint32_t)L.nkb * NPART + (layer_has_pe(L) ? 1u : 0u);
@@ -177,6 +187,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1) mlp_pp_kerne
   const uint32_t bar_aready = bar0 + 8 * 10;      // [2]  activations of slot s written, accumulator drained
   const uint32_t bar_pe_ready = bar0 + 8 * 12;    // [2]  scratch buffer b holds the PE rows of its iteration
   const uint32_t bar_pe_free = bar0 + 8 * 14;     // [2]  scratch buffer b no longer needed
+  const uint32_t bar_kready = bar0 + 8 * 20;      // [3]  bf16x3: hidden block k of the tile written (blocks before the last)
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + SMEM_BAR + 8 * 16);
   float* bias_s = reinterpret_cast<float*>(smem + SMEM_BIAS);  // [2][256]
 
@@ -191,6 +202,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1) mlp_pp_kerne
       mbar_init(bar_pe_ready + 8 * s, PE_THREADS);
       mbar_init(bar_pe_free + 8 * s, EPI_GROUP);
     }
+    for (int k = 0; k < 3; ++k) mbar_init(bar_kready + 8 * k, EPI_THREADS);
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(smem_u32(tmem_ptr_smem), 512);
@@ -255,6 +267,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1) mlp_pp_kerne
     // ================================= MMA issuer =========================================
     uint32_t cnt = 0;
     uint32_t apar[2] = {0u, 0u};
+    uint32_t abuf = 0u;    // bf16x3: accumulator buffer of the current layer (toggles per layer, not across CONT -> ACCUM)
+    uint32_t kpar = 0u;    // bf16x3: phase parities of kready[0..2]
+    int nph_prev = 1;      // bf16x3: `aready` phases the previous layer's epilogue signals (first: the initial PE store)
     for (int j = 0; j < n_iter; ++j) {
       for (int l = 0; l < NL; ++l) {
         const TcLayer& L = P.layers[l];
@@ -265,14 +280,41 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1) mlp_pp_kerne
           const bool tr = P.trace != nullptr && blockIdx.x == 0 && j < P.trace_tiles;
           long long t_w0 = 0, t_w1 = 0, t_full = 0;
           if (tr) t_w0 = clock64();
-          mbar_wait(bar_aready + 8 * s, apar[s]);
-          apar[s] ^= 1u;
-          tcgen05_fence_after();
+          const int nk = X3 ? nph_prev - 1 : 0;   // block signals of the previous epilogue that precede its final one
+          int kw = 0;                              // ... consumed so far
+          bool fin = false;                        // final signal consumed
+          auto wait_block = [&](int k) {
+            mbar_wait(bar_kready + 8 * k, (kpar >> k) & 1u);
+            kpar ^= 1u << k;
+            tcgen05_fence_after();
+          };
+          auto wait_final = [&]() {
+            mbar_wait(bar_aready + 8 * s, apar[s]);
+            apar[s] ^= 1u;
+            tcgen05_fence_after();
+            fin = true;
+          };
+          const bool staged_layer = layer_has_pe(L);
+          if (X3 && !(L.flags & TC_F_ACCUM)) abuf ^= 1u;
+          if (!X3 || staged_layer) {
+            // (bf16x3: a staged input is copied at the very end of the previous epilogue -- no overlap for those layers)
+            for (; kw < nk; ++kw) wait_block(kw);
+            wait_final();
+          }
           if (tr) t_w1 = clock64();
-          const uint32_t acc = tmem_base + (uint32_t)s * 256u;
+          const uint32_t acc = tmem_base + (X3 ? abuf : (uint32_t)s) * 256u;
           for (int kbi = 0; kbi < L.nkb; ++kbi) {
             uint32_t a_hi, a_lo, pe_entry = 0;
             const bool is_pe = L.kb[kbi] >= TC_KB_PE;
+            // bf16x3: hidden block kbi is complete once phase kbi+1 of the previous epilogue has been signalled
+            if (X3 && !fin) {
+              if (kbi < nk) {
+                wait_block(kbi);
+                kw = kbi + 1;
+              } else {
+                wait_final();
+              }
+            }
             if (is_pe) {
               pe_entry = cnt % N_ENTRIES;
               mbar_wait(bar_full + 8 * pe_entry, (cnt / N_ENTRIES) & 1u);
@@ -310,6 +352,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1) mlp_pp_kerne
               ++cnt;
             }
             if (is_pe) umma_commit_mc(bar_empty + 8 * pe_entry, (uint16_t)3);
+          }
+          if (X3) {
+            for (; kw < nk; ++kw) wait_block(kw);   // (a layer that reads fewer blocks than its predecessor wrote)
+            if (!fin) wait_final();
+            nph_prev = layer_phases(L, P.view_w);
           }
           umma_commit(bar_acc + 8 * s);
           if (tr && lane == 0) {
@@ -509,6 +556,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1) mlp_pp_kerne
     const uint32_t row = (uint32_t)(q * 32 + lane);
     const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
     uint32_t acc_par[2] = {0u, 0u};
+    uint32_t abuf = 0u;                   // accumulator buffer of the current layer (mirrors the MMA issuer)
     uint32_t cnt = 0;                     // ring entries before the current (j, l, s) in MMA order
     float alpha[2] = {0.f, 0.f};
     int pe_waited_j = -1;
@@ -605,7 +653,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1) mlp_pp_kerne
           const int64_t ray = pt / P.S;
           uint8_t* arena_hi = smem + (size_t)(X3 ? 0 : s * 4) * KB_BYTES;
           uint8_t* arena_lo = arena_hi + (size_t)4 * KB_BYTES;
-          const uint32_t acc = lane_base + (uint32_t)s * 256u;
+          if (X3 && !(L.flags & TC_F_ACCUM)) abuf ^= 1u;
+          const uint32_t acc = lane_base + (X3 ? abuf : (uint32_t)s) * 256u;
           const bool tr = P.trace != nullptr && blockIdx.x == 0 && et == 0 && j < P.trace_tiles;
           long long t_e0 = 0, t_e1 = 0;
           if (tr) t_e0 = clock64();
@@ -662,19 +711,31 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1) mlp_pp_kerne
             const bool per_ray = L.epi == TC_EPI_VIEW0;
             const int n_relu = per_ray ? P.view_w : (int)L.n;
             const int nch = n_relu >> 6;            // 32-column chunks per thread (4 or 2)
-            const int ch0 = hf * nch;               // first chunk of this thread
+            // this thread's k-th chunk is 2k + hf: the two column halves of 64-column block k belong to the two warps of
+            // a lane quarter, so block k is complete -- and signalled to the MMA issuer, which may start the next
+            // layer on it -- after everybody's k-th chunk (the last block is signalled by the hand-back below)
             const float* rb = P.view_bias + ray * P.view_w;
             uint32_t v0[32], v1[32];
-            tmem_ld32(acc + ch0 * 32, v0);
+            auto block_done = [&](int k) {
+              if (k + 1 < nch) {
+                tcgen05_fence_before();
+                fence_proxy_async();
+                mbar_arrive(bar_kready + 8 * k);
+              }
+            };
+            tmem_ld32(acc + hf * 32, v0);
             for (int cc = 0; cc < nch; cc += 2) {
+              const int c0 = 2 * cc + hf, c1 = c0 + 2;
               tmem_ld_wait();
-              tmem_ld32(acc + (ch0 + cc + 1) * 32, v1);
-              if (per_ray) epilogue_chunk<X3, true>(v0, ch0 + cc, rb, 0u, arena_hi, arena_lo, row);
-              else epilogue_chunk<X3, false>(v0, ch0 + cc, nullptr, sbias, arena_hi, arena_lo, row);
+              tmem_ld32(acc + c1 * 32, v1);
+              if (per_ray) epilogue_chunk<X3, true>(v0, c0, rb, 0u, arena_hi, arena_lo, row);
+              else epilogue_chunk<X3, false>(v0, c0, nullptr, sbias, arena_hi, arena_lo, row);
+              block_done(cc);
               tmem_ld_wait();
-              if (cc + 2 < nch) tmem_ld32(acc + (ch0 + cc + 2) * 32, v0);
-              if (per_ray) epilogue_chunk<X3, true>(v1, ch0 + cc + 1, rb, 0u, arena_hi, arena_lo, row);
-              else epilogue_chunk<X3, false>(v1, ch0 + cc + 1, nullptr, sbias, arena_hi, arena_lo, row);
+              if (cc + 2 < nch) tmem_ld32(acc + (c1 + 2) * 32, v0);
+              if (per_ray) epilogue_chunk<X3, true>(v1, c1, rb, 0u, arena_hi, arena_lo, row);
+              else epilogue_chunk<X3, false>(v1, c1, nullptr, sbias, arena_hi, arena_lo, row);
+              block_done(cc + 1);
             }
             if (!DEC && per_ray && hf == 0) {  // density head: accumulator column view_w, no activation
               uint32_t v[16];
