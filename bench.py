@@ -192,7 +192,7 @@ def main():
     import torch.distributed as dist
     import dfa_nerf_b200 as dfn
     from dfa_nerf_b200.distributed import shard_range, gather_rgb
-    from oracle import synth           # synthetic data generator only (no oracle arithmetic on this path)
+    import synth                       # seeded synthetic data (repo root; nothing under oracle/ is touched on this path)
 
     world = int(os.environ.get('WORLD_SIZE', '1'))
     rank = int(os.environ.get('RANK', '0'))

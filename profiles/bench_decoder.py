@@ -10,7 +10,7 @@ import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import dfa_nerf_b200 as dfn  # noqa: E402
-from oracle import synth  # noqa: E402
+import synth  # noqa: E402
 
 H = W = int(sys.argv[1]) if len(sys.argv) > 1 else 450
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 5

@@ -1,7 +1,7 @@
 import torch, sys
 sys.path.insert(0, ".")
 import dfa_nerf_b200 as dfn
-from oracle import synth
+import synth
 dev = torch.device("cuda", 0)
 net = dfn.FaceNeRF(D=8, W=256, input_ch=63, input_ch_views=27, dim_aud=64, output_ch=4, skips=[4], use_viewdirs=True)
 net.load_state_dict(synth.facenerf_state_dict(1)); net = net.to(dev)

@@ -8,7 +8,7 @@ import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import dfa_nerf_b200 as dfn  # noqa: E402
-from oracle import synth  # noqa: E402
+import synth  # noqa: E402
 
 R, S = 40000, 192
 mode = sys.argv[1] if len(sys.argv) > 1 else 'bf16'
