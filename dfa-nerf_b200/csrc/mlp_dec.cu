@@ -88,32 +88,43 @@ __global__ void dec_fold_kernel(int n_layers, int dimL, const float* __restrict_
 }
 
 // out[r][n] = bias_row[n] + sum_j fc_view.W[n][j] * PE(ray_d_r / |ray_d_r|)[j]  (DEC:337-339; PE of DEC:257-275 with
-// n_freq_views frequencies: d/2, then [sin(2^k pi d) | cos(2^k pi d)]_k).  One block walks rays; thread n owns output n.
+// n_freq_views frequencies: d/2, then [sin(2^k pi d) | cos(2^k pi d)]_k).  A block walks rays eight at a time; thread n
+// owns output n of each.
+static constexpr int DVB_RAYS = 8;
 __global__ void dec_view_bias_kernel(int64_t R, int Hd, int Lv, const float* __restrict__ rays_d,
                                      const float* __restrict__ vw, const float* __restrict__ bias_row,
                                      float* __restrict__ out) {
   extern __shared__ float sm[];
   const int ncol = 6 * Lv;
   float* w_s = sm;                      // [Hd][ncol + 1]
-  float* pe = sm + Hd * (ncol + 1);     // [ncol]
+  float* pe = sm + Hd * (ncol + 1);     // [DVB_RAYS][ncol]
   for (int i = threadIdx.x; i < Hd * ncol; i += blockDim.x) w_s[(i / ncol) * (ncol + 1) + (i % ncol)] = vw[i];
   const float bn = (int)threadIdx.x < Hd ? bias_row[threadIdx.x] : 0.f;
-  for (int64_t r = blockIdx.x; r < R; r += gridDim.x) {
+  for (int64_t r0 = (int64_t)blockIdx.x * DVB_RAYS; r0 < R; r0 += (int64_t)gridDim.x * DVB_RAYS) {
     __syncthreads();
-    if ((int)threadIdx.x < ncol) {
-      const int j = threadIdx.x, k = j / 6, q = j % 6;
+    for (int i = threadIdx.x; i < DVB_RAYS * ncol; i += blockDim.x) {
+      const int q = i / ncol, j = i % ncol, k = j / 6, c = j % 6;
+      const int64_t r = r0 + q < R ? r0 + q : R - 1;
       const float a0 = rays_d[r * 3], a1 = rays_d[r * 3 + 1], a2 = rays_d[r * 3 + 2];
       const float nrm = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(a0, a0), __fmul_rn(a1, a1)), __fmul_rn(a2, a2)));
-      const float xv = __fdiv_rn(rays_d[r * 3 + (q % 3)], nrm);
+      const float xv = __fdiv_rn(rays_d[r * 3 + (c % 3)], nrm);
       const float a = __fmul_rn(__fmul_rn(pow2i(k), 3.14159274101257324f), __fmul_rn(xv, 0.5f));
-      pe[j] = q < 3 ? sinf(a) : cosf(a);
+      pe[i] = c < 3 ? sinf(a) : cosf(a);
     }
     __syncthreads();
     if ((int)threadIdx.x < Hd) {
-      float acc = 0.f;
+      float acc[DVB_RAYS];
+#pragma unroll
+      for (int q = 0; q < DVB_RAYS; ++q) acc[q] = 0.f;
       const float* w = w_s + threadIdx.x * (ncol + 1);
-      for (int j = 0; j < ncol; ++j) acc = fmaf(w[j], pe[j], acc);
-      out[r * Hd + threadIdx.x] = bn + acc;
+      for (int j = 0; j < ncol; ++j) {
+        const float wj = w[j];
+#pragma unroll
+        for (int q = 0; q < DVB_RAYS; ++q) acc[q] = fmaf(wj, pe[q * ncol + j], acc[q]);
+      }
+#pragma unroll
+      for (int q = 0; q < DVB_RAYS; ++q)
+        if (r0 + q < R) out[(r0 + q) * Hd + threadIdx.x] = bn + acc[q];
     }
   }
 }
@@ -424,9 +435,10 @@ static int dec_query(const dfn_decoder* m, int field, int64_t R, int S, const fl
   dec_fold_kernel<<<F.prog.n_layers, TC_BIAS_STRIDE, 0, st>>>(F.prog.n_layers, F.dimL, F.bias, F.fold_w, fa, bias_ws);
   DFN_LAUNCH_CHECK();
   {
-    int64_t blocks = R < (int64_t)num_sms() * 8 ? R : (int64_t)num_sms() * 8;
+    int64_t blocks = (R + DVB_RAYS - 1) / DVB_RAYS;
+    if (blocks > (int64_t)num_sms() * 8) blocks = (int64_t)num_sms() * 8;
     const int ncol = 6 * d.n_freq_views;
-    const size_t sm = ((size_t)d.hidden * (ncol + 1) + ncol) * sizeof(float);
+    const size_t sm = ((size_t)d.hidden * (ncol + 1) + DVB_RAYS * ncol) * sizeof(float);
     dec_view_bias_kernel<<<(int)blocks, 256, sm, st>>>(R, d.hidden, d.n_freq_views, rays_d, m->view_w,
                                                        bias_ws + (size_t)F.view_layer * TC_BIAS_STRIDE, vbias_ws);
     DFN_LAUNCH_CHECK();

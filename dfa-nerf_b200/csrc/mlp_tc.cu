@@ -402,36 +402,46 @@ __global__ void fold_latent_kernel(int n_layers, int W, int dim_aud, const float
 }
 
 // view_bias[r][n] = b[n] + sum_j Wv[n][j] * PE(viewdir_r)[j]: the view-direction columns of
-// views_linears.0 (HELP:288-292) are constant along a ray.  One block walks rays; thread n owns
-// output n.  PE layout as HELP:42-52 with multires_views frequencies.
+// views_linears.0 (HELP:288-292) are constant along a ray.  A block walks rays four at a time; thread n owns
+// output n of each.  PE layout as HELP:42-52 with multires_views frequencies.
+static constexpr int VB_RAYS = 4;
 __global__ void view_bias_kernel(int64_t R, int Wh, int ncol, int L, const float* __restrict__ viewdirs,
                                  const float* __restrict__ vw, const float* __restrict__ vb,
                                  float* __restrict__ out) {
   extern __shared__ float sm[];
   float* w_s = sm;                 // [Wh][ncol]
-  float* pe = sm + Wh * ncol;      // [ncol]
+  float* pe = sm + Wh * ncol;      // [VB_RAYS][ncol]
   for (int i = threadIdx.x; i < Wh * ncol; i += blockDim.x) w_s[i] = vw[i];
-  const float bn = threadIdx.x < Wh ? vb[threadIdx.x] : 0.f;
-  for (int64_t r = blockIdx.x; r < R; r += gridDim.x) {
+  const float bn = (int)threadIdx.x < Wh ? vb[threadIdx.x] : 0.f;
+  for (int64_t r0 = (int64_t)blockIdx.x * VB_RAYS; r0 < R; r0 += (int64_t)gridDim.x * VB_RAYS) {
     __syncthreads();
-    if ((int)threadIdx.x < ncol) {
-      const int j = threadIdx.x;
+    for (int i = threadIdx.x; i < VB_RAYS * ncol; i += blockDim.x) {
+      const int q = i / ncol, j = i % ncol;
+      const int64_t r = r0 + q < R ? r0 + q : R - 1;
       float v;
       if (j < 3) {
         v = viewdirs[r * 3 + j];
       } else {
-        const int k = (j - 3) / 6, q = (j - 3) % 6;
-        const float a = __fmul_rn(viewdirs[r * 3 + (q % 3)], pow2i(k));
-        v = q < 3 ? sinf(a) : cosf(a);
+        const int k = (j - 3) / 6, c = (j - 3) % 6;
+        const float a = __fmul_rn(viewdirs[r * 3 + (c % 3)], pow2i(k));
+        v = c < 3 ? sinf(a) : cosf(a);
       }
-      pe[j] = v;
+      pe[i] = v;
     }
     __syncthreads();
     if ((int)threadIdx.x < Wh) {
-      float acc = 0.f;
+      float acc[VB_RAYS];
+#pragma unroll
+      for (int q = 0; q < VB_RAYS; ++q) acc[q] = 0.f;
       const float* w = w_s + threadIdx.x * ncol;
-      for (int j = 0; j < ncol; ++j) acc = fmaf(w[j], pe[j], acc);
-      out[r * Wh + threadIdx.x] = bn + acc;
+      for (int j = 0; j < ncol; ++j) {
+        const float wj = w[j];
+#pragma unroll
+        for (int q = 0; q < VB_RAYS; ++q) acc[q] = fmaf(wj, pe[q * ncol + j], acc[q]);
+      }
+#pragma unroll
+      for (int q = 0; q < VB_RAYS; ++q)
+        if (r0 + q < R) out[(r0 + q) * Wh + threadIdx.x] = bn + acc[q];
     }
   }
 }
@@ -661,8 +671,9 @@ int tc_query_points(const dfn_model* m, int64_t R, int S, const float* rays_o, c
       m->prog.n_layers, d.W, d.dim_aud, m->tc_bias, m->tc_fold_w, latent, m->prog.fold_layer[0], m->prog.fold_layer[1], bias_ws);
   DFN_LAUNCH_CHECK();
   {
-    int64_t blocks = R < (int64_t)num_sms() * 8 ? R : (int64_t)num_sms() * 8;
-    size_t sm = ((size_t)Wh * d.input_ch_views + d.input_ch_views) * sizeof(float);
+    int64_t blocks = (R + tc::VB_RAYS - 1) / tc::VB_RAYS;
+    if (blocks > (int64_t)num_sms() * 8) blocks = (int64_t)num_sms() * 8;
+    size_t sm = ((size_t)Wh * d.input_ch_views + tc::VB_RAYS * d.input_ch_views) * sizeof(float);
     tc::view_bias_kernel<<<(int)blocks, 128, sm, st>>>(R, Wh, d.input_ch_views, d.multires_views, viewdirs, m->tc_view_w,
                                                         m->tc_view_b, vbias_ws);
     DFN_LAUNCH_CHECK();

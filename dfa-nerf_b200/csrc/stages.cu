@@ -496,15 +496,18 @@ __global__ void sample_pdf_kernel(int R, int nb, const float* __restrict__ bins,
 }
 
 // ----------------------------------------------------------------------------- a11 sort-merge
-// out = sort(cat(a, b)) per ray (upstream render_rays).  Bitonic network in shared memory over the
-// next power of two (padding +inf); values only, so the result equals torch.sort's.
+// out = sort(cat(a, b)) per ray (upstream render_rays); values only, so the result equals torch.sort's.
+// Fast path: at render time both runs are already ascending (uniform z_vals; sample_pdf of a sorted u is monotone), so
+// every element's output position is its own index plus its rank in the other run (two binary searches in shared
+// memory) -- checked per ray, warp-uniformly.  Otherwise (stratified / random u, NaNs): bitonic network over the next
+// power of two (padding +inf).
 __global__ void sort_merge_kernel(int R, int na, const float* __restrict__ a, int nb,
                                   const float* __restrict__ b, float* __restrict__ out, int npow2) {
   extern __shared__ float sm[];
   const int lane = threadIdx.x & 31;
   const int wib = threadIdx.x >> 5;
   const int warps_per_block = blockDim.x >> 5;
-  float* v = sm + (size_t)wib * npow2;
+  float* v = sm + (size_t)wib * 2 * npow2;
   const int n = na + nb;
   for (int ray = blockIdx.x * warps_per_block + wib; ray < R; ray += gridDim.x * warps_per_block) {
     __syncwarp();
@@ -515,6 +518,30 @@ __global__ void sort_merge_kernel(int R, int na, const float* __restrict__ a, in
       v[i] = x;
     }
     __syncwarp();
+    {
+      bool sorted = true;
+      for (int i = lane; i < n; i += 32)
+        if (i != 0 && i != na) sorted = sorted && (v[i - 1] <= v[i]);
+      if (__all_sync(0xFFFFFFFFu, sorted)) {
+        float* w = v + npow2;   // second buffer: merged run, stored coalesced afterwards
+        for (int i = lane; i < n; i += 32) {
+          const float x = v[i];
+          const bool from_a = i < na;
+          const float* other = from_a ? v + na : v;
+          int lo = 0, hi = from_a ? nb : na;
+          while (lo < hi) {   // from a: #{b < x} (lower bound); from b: #{a <= x} (upper bound) -> distinct positions on ties
+            const int mid = (lo + hi) >> 1;
+            const float y = other[mid];
+            if (from_a ? (y < x) : (y <= x)) lo = mid + 1;
+            else hi = mid;
+          }
+          w[(from_a ? i : i - na) + lo] = x;
+        }
+        __syncwarp();
+        for (int i = lane; i < n; i += 32) out[(int64_t)ray * n + i] = w[i];
+        continue;
+      }
+    }
     for (int k = 2; k <= npow2; k <<= 1) {
       for (int j = k >> 1; j > 0; j >>= 1) {
         for (int t = lane; t < (npow2 >> 1); t += 32) {
@@ -700,8 +727,9 @@ extern "C" int dfn_sort_merge(int R, int na, const float* a, int nb, const float
                 "dfn_sort_merge: bad argument (na+nb <= 1024)");
   int npow2 = 2;
   while (npow2 < na + nb) npow2 <<= 1;
-  const int wpb = 8;
-  size_t smem = (size_t)wpb * npow2 * sizeof(float);
+  int wpb = 8;
+  while (wpb > 1 && (size_t)wpb * 2 * npow2 * sizeof(float) > 48 * 1024) wpb >>= 1;
+  size_t smem = (size_t)wpb * 2 * npow2 * sizeof(float);
   sort_merge_kernel<<<rays_grid(R, wpb), wpb * 32, smem, (cudaStream_t)stream>>>(R, na, a, nb, b, out, npow2);
   DFN_LAUNCH_CHECK();
   return 0;

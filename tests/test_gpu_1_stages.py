@@ -76,7 +76,7 @@ def test_calc_volume_weights(dfn, golden):
     rd = torch.randn(R, 3)
     sg = torch.randn(R, S) * 12 + 2
     w = dfn.calc_volume_weights(z.to(DEV), rd.to(DEV), sg.to(DEV))
-    assert maxerr(w, O.calc_volume_weights(z, rd, sg)) < 1e-6
+    assert maxerr(w, O.calc_volume_weights(z, rd, sg)) < 2e-6    # expf: 2 ulp (CUDA) vs 1 ulp (host libm) on values <= 1
 
 
 def test_composite_function(dfn, golden):
@@ -169,9 +169,10 @@ def check_against_plain_oracle(s, i, ref_s, ref_i):
     bad_i = i != ref_i
     bad_s = (s - ref_s).abs() > 1e-6
     assert bad_i.float().mean().item() < 0.01 and bad_s.float().mean().item() < 0.01
-    # samples that keep their index agree to the conditioning of the lerp: a 1-ulp cdf difference moves the
-    # sample by at most ulp/denom * bin width with denom >= 1e-5 (HELP:577) -> 6e-8/1e-5 * 0.0095 = 6e-5
-    assert ((s - ref_s).abs()[~bad_i]).max().item() < 1e-4
+    # samples that keep their index agree to the conditioning of the lerp: the two cdf knots of a bin each differ by up
+    # to one ulp between the two row-sum orders, which moves the sample by at most 2 ulp/denom * bin width with
+    # denom >= 1e-5 (HELP:577) -> 1.2e-7/1e-5 * 0.0095 = 1.1e-4
+    assert ((s - ref_s).abs()[~bad_i]).max().item() < 2e-4
     assert ((s - ref_s).abs()[~bad_i]).median().item() < 1e-7
 
 
@@ -197,3 +198,15 @@ def test_sort_merge_bit_exact(dfn):
     assert torch.equal(out.cpu(), ref)
     out = dfn.sort_merge(a[:5, :7].contiguous().to(DEV), b[:5, :3].contiguous().to(DEV))
     assert torch.equal(out.cpu(), torch.sort(torch.cat([a[:5, :7], b[:5, :3]], -1), -1)[0])
+    # render-time case: both runs ascending (merge-by-rank fast path), with ties inside and across the runs, mixed per
+    # ray with unsorted rows (bitonic fallback), and the largest supported width
+    bs, _ = torch.sort(b, -1)
+    bs[::3, 5] = bs[::3, 4]
+    bs[::5, :64:7] = a[::5, :64:7]
+    bs, _ = torch.sort(bs, -1)
+    mixed = bs.clone()
+    mixed[1::2] = b[1::2]
+    for bb in (bs, mixed):
+        assert torch.equal(dfn.sort_merge(a.to(DEV), bb.to(DEV)).cpu(), torch.sort(torch.cat([a, bb], -1), -1)[0])
+    big_a, big_b = torch.sort(torch.rand(33, 500), -1)[0], torch.sort(torch.rand(33, 524), -1)[0]
+    assert torch.equal(dfn.sort_merge(big_a.to(DEV), big_b.to(DEV)).cpu(), torch.sort(torch.cat([big_a, big_b], -1), -1)[0])
