@@ -49,12 +49,12 @@ class ClockSampler:
         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.t0 = index, [], None, 0.0
 
     def start(self):
         try:
             self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
-                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                          '--format=csv,noheader,nounits', '-lms', '25'],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -63,7 +63,11 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(',')])
+            self.rows.append((time.time(), [x.strip() for x in line.split(',')]))
+
+    def mark(self):
+        """Samples before this point (sampler start-up, idle GPU) are not part of the record."""
+        self.t0 = time.time()
 
     def stop(self):
         if self.proc is None:
@@ -75,7 +79,8 @@ class ClockSampler:
         except Exception:
             self.proc.kill()
         sm, mx, reasons = [], None, set()
-        for r in self.rows:
+        rows = [r for t, r in self.rows if t >= self.t0] or [r for _, r in self.rows]
+        for r in rows:
             try:
                 sm.append(float(r[0]))
                 mx = float(r[1])
@@ -344,7 +349,12 @@ def main():
         return ms.item() / steps
 
     # ---- device-resident throughput, with per-launch events around the tcgen05 kernel ---------------
+    # clocks are sampled from the warm-up through both timed regions (the GPU is under this load throughout; a
+    # multi-GPU step is a few milliseconds, shorter than nvidia-smi's start-up)
     sampler = ClockSampler(local_rank)
+    sampler.start()
+    time.sleep(0.3)
+    sampler.mark()
     for _ in range(args.warmup):
         if args.workload == 'sequence':
             step_sequence(min(args.frames, 2 * world))     # warm-up on a short prefix of the sequence
@@ -353,9 +363,7 @@ def main():
     torch.cuda.synchronize()
     dfn.lib.dfn_profile_enable(1 if prec != dfn.PREC_FP32 else 0)
     launches[0] = 0
-    sampler.start()
     ms_step = timed(step_resident, args.steps, 0)
-    clocks = sampler.stop()
     k_ms, k_n, k_macs = C.c_double(), C.c_int64(), C.c_double()
     dfn.lib.dfn_profile_collect(C.byref(k_ms), C.byref(k_n), C.byref(k_macs))
     dfn.lib.dfn_profile_enable(0)
@@ -364,6 +372,7 @@ def main():
 
     # ---- end to end through the public API with host buffers ------------------------------------------
     ms_e2e = ms_step if args.workload == 'sequence' else timed(step_e2e, args.steps, 2)   # the sequence step IS end to end
+    clocks = sampler.stop()
     e2e = {'value': n_rays / (ms_e2e * 1e-3), 'unit': 'rays/s',
            'h2d_bytes_per_step': int((e - b) * 12 + lat_host.numel() * 4 + 48),
            'd2h_bytes_per_step': int(n_rays * 12) if rank == 0 else 0}
