@@ -200,7 +200,9 @@ static constexpr int kMaxSeg = 8;  // samples per lane: S <= 256
 // The running product is carried in fp64 and rounded per element, as torch's CPU cumprod does;
 // a warp-shuffle exclusive scan combines the per-lane segment products.
 // MODE 0: sigma [R,S] -> weights.  MODE 1: raw [R,S,4] -> maps (raw2outputs).
-template <int MODE>
+// SEG = samples per lane (compile-time, >= ceil(S/32)): the per-lane arrays live in registers, so a 64-sample ray (SEG 2)
+// does not pay the register footprint -- and the occupancy -- of a 256-sample one.
+template <int MODE, int SEG>
 __global__ void volume_weights_kernel(int R, int S, const float* __restrict__ src,
                                       const float* __restrict__ z_vals,
                                       const float* __restrict__ rays_d,
@@ -217,11 +219,11 @@ __global__ void volume_weights_kernel(int R, int S, const float* __restrict__ sr
     const float dx = rays_d[ray * 3 + 0], dy = rays_d[ray * 3 + 1], dz = rays_d[ray * 3 + 2];
     const float nrm = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)));
     const float* zr = z_vals + (int64_t)ray * S;
-    float alpha[kMaxSeg], zv[kMaxSeg], col[kMaxSeg][3];
+    float alpha[SEG], zv[SEG], col[SEG][3];
     double local = 1.0;
     const int s0 = lane * seg;
 #pragma unroll
-    for (int k = 0; k < kMaxSeg; ++k) {
+    for (int k = 0; k < SEG; ++k) {
       int s = s0 + k;
       alpha[k] = 0.f;
       zv[k] = 0.f;
@@ -264,7 +266,7 @@ __global__ void volume_weights_kernel(int R, int S, const float* __restrict__ sr
     if (lane == 0) run = 1.0;
     float acc_rgb[3] = {0.f, 0.f, 0.f}, acc_w = 0.f, acc_d = 0.f;
 #pragma unroll
-    for (int k = 0; k < kMaxSeg; ++k) {
+    for (int k = 0; k < SEG; ++k) {
       int s = s0 + k;
       if (k < seg && s < S) {
         float T = (float)run;
@@ -311,6 +313,7 @@ __global__ void volume_weights_kernel(int R, int S, const float* __restrict__ sr
 // the head image and the torso rays' norm for the person image (MAIN:704-705); rgb = sum w*feat.
 // feat_* / sig_* are addressed with element strides (3 and 1 for separate tensors; 4 and 4 for the fused kernels'
 // interleaved raw [R,S,4] = (feat, sigma)).
+template <int SEG>
 __global__ void head_torso_kernel(int R, int S, const float* __restrict__ feat_h, int fs_h, const float* __restrict__ sig_h,
                                   int ss_h, const float* __restrict__ feat_t, int fs_t, const float* __restrict__ sig_t,
                                   int ss_t, const float* __restrict__ bc_rgb, const float* __restrict__ z_vals,
@@ -328,11 +331,11 @@ __global__ void head_torso_kernel(int R, int S, const float* __restrict__ feat_h
       nrm[1] = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(d1[0], d1[0]), __fmul_rn(d1[1], d1[1])), __fmul_rn(d1[2], d1[2])));
     }
     const float* zr = z_vals + (int64_t)ray * S;
-    float alpha[2][kMaxSeg], col[2][kMaxSeg][3];
+    float alpha[2][SEG], col[2][SEG][3];
     double local[2] = {1.0, 1.0};
     const int s0 = lane * seg;
 #pragma unroll
-    for (int k = 0; k < kMaxSeg; ++k) {
+    for (int k = 0; k < SEG; ++k) {
       const int s = s0 + k;
       alpha[0][k] = alpha[1][k] = 0.f;
       if (k < seg && s < S) {
@@ -381,7 +384,7 @@ __global__ void head_torso_kernel(int R, int S, const float* __restrict__ feat_h
       if (lane == 0) run = 1.0;
       float acc[3] = {0.f, 0.f, 0.f};
 #pragma unroll
-      for (int k = 0; k < kMaxSeg; ++k) {
+      for (int k = 0; k < SEG; ++k) {
         const int s = s0 + k;
         if (k < seg && s < S) {
           const float w = __fmul_rn(alpha[f][k], (float)run);
@@ -637,6 +640,17 @@ extern "C" int dfn_composite_fields(int n_box, int64_t n, const float* sigma, co
   return 0;
 }
 
+// instantiate KERNEL<..., SEG> for the smallest SEG in {1, 2, 4, 6, 8} that covers ceil(S/32)
+#define DFN_SEG_DISPATCH(S, CALL)          \
+  do {                                     \
+    const int seg__ = ((S) + 31) / 32;     \
+    if (seg__ <= 1) { CALL(1); }           \
+    else if (seg__ <= 2) { CALL(2); }      \
+    else if (seg__ <= 4) { CALL(4); }      \
+    else if (seg__ <= 6) { CALL(6); }      \
+    else { CALL(8); }                      \
+  } while (0)
+
 static int rays_grid(int R, int warps_per_block) {
   int64_t blocks = ((int64_t)R + warps_per_block - 1) / warps_per_block;
   int64_t cap = (int64_t)num_sms() * 16;
@@ -647,8 +661,11 @@ extern "C" int dfn_calc_volume_weights(int R, int S, const float* z_vals, const 
                                        const float* sigma, float last_dist, float* weights, void* stream) {
   DFN_CHECK_ARG(R > 0 && S > 0 && S <= 32 * kMaxSeg && z_vals && ray_vector && sigma && weights,
                 "dfn_calc_volume_weights: bad argument (S <= 256)");
-  volume_weights_kernel<0><<<rays_grid(R, 8), 256, 0, (cudaStream_t)stream>>>(
-      R, S, sigma, z_vals, ray_vector, nullptr, 0, 0, last_dist, nullptr, nullptr, nullptr, weights, nullptr, nullptr);
+#define CALL_VW0(SEG)                                                                                     \
+  volume_weights_kernel<0, SEG><<<rays_grid(R, 8), 256, 0, (cudaStream_t)stream>>>(                       \
+      R, S, sigma, z_vals, ray_vector, nullptr, 0, 0, last_dist, nullptr, nullptr, nullptr, weights, nullptr, nullptr)
+  DFN_SEG_DISPATCH(S, CALL_VW0);
+#undef CALL_VW0
   DFN_LAUNCH_CHECK();
   return 0;
 }
@@ -660,9 +677,12 @@ int dfn::launch_raw2outputs(int R, int S, const float* raw, const float* z_vals,
   DFN_CHECK_ARG(R > 0 && S > 0 && S <= 32 * kMaxSeg && raw && z_vals && rays_d,
                 "dfn_raw2outputs: bad argument (S <= 256)");
   DFN_CHECK_ARG((reinterpret_cast<uintptr_t>(raw) & 15) == 0, "dfn_raw2outputs: raw must be 16-byte aligned");
-  volume_weights_kernel<1><<<rays_grid(R, 8), 256, 0, st>>>(R, S, raw, z_vals, rays_d, bc_rgb, raw_is_feat, white_bkgd,
-                                                           last_dist, rgb_map, disp_map, acc_map, weights, depth_map,
-                                                           last_weight);
+#define CALL_VW1(SEG)                                                                                          \
+  volume_weights_kernel<1, SEG><<<rays_grid(R, 8), 256, 0, st>>>(R, S, raw, z_vals, rays_d, bc_rgb, raw_is_feat,       \
+                                                                white_bkgd, last_dist, rgb_map, disp_map, acc_map,    \
+                                                                weights, depth_map, last_weight)
+  DFN_SEG_DISPATCH(S, CALL_VW1);
+#undef CALL_VW1
   DFN_LAUNCH_CHECK();
   return 0;
 }
@@ -690,9 +710,12 @@ int dfn::launch_head_torso(int R, int S, const float* feat_h, int fstride_h, con
                            const float* feat_t, int fstride_t, const float* sig_t, int sstride_t, const float* bc_rgb,
                            const float* z_vals, const float* rays_d_h, const float* rays_d_t, float last_dist,
                            float* rgb_head, float* rgb_person, cudaStream_t st) {
-  head_torso_kernel<<<rays_grid(R, 8), 256, 0, st>>>(R, S, feat_h, fstride_h, sig_h, sstride_h, feat_t, fstride_t, sig_t,
-                                                    sstride_t, bc_rgb, z_vals, rays_d_h, rays_d_t, last_dist, rgb_head,
-                                                    rgb_person);
+#define CALL_HT(SEG)                                                                                             \
+  head_torso_kernel<SEG><<<rays_grid(R, 8), 256, 0, st>>>(R, S, feat_h, fstride_h, sig_h, sstride_h, feat_t, fstride_t, \
+                                                         sig_t, sstride_t, bc_rgb, z_vals, rays_d_h, rays_d_t,         \
+                                                         last_dist, rgb_head, rgb_person)
+  DFN_SEG_DISPATCH(S, CALL_HT);
+#undef CALL_HT
   DFN_LAUNCH_CHECK();
   return 0;
 }
