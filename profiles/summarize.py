@@ -77,8 +77,10 @@ launches('_ht', 'bench.py --workload head_torso --steps 2 --warmup 3')
 report('bf16', 'mlp_tc_kernel<bf16>: 20,000 rays x 192 samples (fine-pass sized network query)')
 report('x3', 'mlp_pp_kernel<bf16x3>: 20,000 rays x 192 samples')
 report('dec_all', 'mlp_pp_kernel<bf16, Decoder>: 60,000 rays x 64 samples, head field then torso field (live model)')
-report('raw2outputs', 'volume_weights_kernel<1> (raw2outputs): 202,500 rays x 64 samples')
+report('vw', 'volume_weights_kernel<1> (raw2outputs): 202,500 rays x 64 samples (coarse), then x 192 (fine)')
 report('headtorso', 'head_torso_kernel (live two-field compositing): 202,500 rays x 64 samples')
+report('sortmerge', 'sort_merge_kernel: 202,500 rays x (64 + 128)')
+report('samplepdf', 'sample_pdf_kernel: 202,500 rays, 63 bins -> 128 samples')
 path = os.path.join(ROOT, 'profiles', 'ncu_summary_%s.txt' % rnd)
 open(path, 'w').write('\n'.join(out) + '\n')
 print('\n'.join(out))
