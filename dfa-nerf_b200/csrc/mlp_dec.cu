@@ -163,6 +163,7 @@ struct Builder {
   DecField* F;
   std::vector<float> bias;                 // [TC_MAX_LAYERS][256]
   std::vector<std::vector<float>> folds;   // each [dimL][256]
+  std::vector<float>* dense = nullptr;     // host-only introspection: fp32 weights [layer][256][6*64], see dfn_decoder_program_host
   int nl = 0;
   explicit Builder(DecField* f, int dimL) : F(f), bias((size_t)TC_MAX_LAYERS * TC_BIAS_STRIDE, 0.f) {
     pk.want64 = false;
@@ -179,6 +180,12 @@ struct Builder {
     L.epi = (uint8_t)epi;
     L.flags = (uint8_t)flags;
     for (int kb : kbs) L.kb[L.nkb++] = (uint8_t)kb;
+    if (dense) {
+      float* d = dense->data() + (size_t)nl * TC_BIAS_STRIDE * 6 * 64;
+      for (int r = 0; r < n; ++r)
+        for (int kbi = 0; kbi < L.nkb; ++kbi)
+          for (int k = 0; k < 64; ++k) d[((size_t)r * 6 + kbi) * 64 + k] = wfun(r, kbi, k);
+    }
     pk.add_layer(n, L.nkb, wfun);
     F->woff32[nl] = pk.last32;
     F->prog.layers[nl] = L;
@@ -396,6 +403,37 @@ static void build_deform(Builder& B, const std::vector<Lin>& T, const dfn_decode
   B.F->macs_pt += (double)HD * (de + dt);
 }
 
+// {weight, bias} pointers + shapes of the reference's modules in load order
+static std::vector<Lin> tensor_table(const dfn_decoder_desc& d, const float* const* t) {
+  const int H = d.hidden, de = 6 * d.n_freq, dv = 6 * d.n_freq_views, dt = d.dim_et_embed;
+  std::vector<Lin> T(T_COUNT);
+  auto set = [&](int i, int in, int out) { T[i] = Lin{t[2 * i], t[2 * i + 1], in, out}; };
+  set(T_DE0, de + dt, 64);
+  set(T_DS0, de + dt, 64);
+  for (int i = 1; i < 5; ++i) {
+    set(T_DE0 + i, 64, 64);
+    set(T_DS0 + i, 64, 64);
+  }
+  set(T_DEOUT, 64, de);
+  set(T_DSOUT, 64, dt);
+  set(T_DESKIP, de, 64);
+  set(T_DSSKIP, dt, 64);
+  set(T_FCIN, de + d.dim_signal, H);
+  set(T_FCIN_TORSO, de + dt, H);
+  set(T_FCZ, d.z_dim, H);
+  for (int i = 0; i < 7; ++i) set(T_BLOCK0 + i, H, H);
+  set(T_FCZSKIP, d.z_dim, H);
+  set(T_FCPSKIP, de + d.dim_signal, H);
+  set(T_FCPSKIP_TORSO, de + dt, H);
+  set(T_SIGMA, H, 1);
+  set(T_FCZVIEW, d.z_dim, H);
+  set(T_FEATVIEW, H, H);
+  set(T_FCVIEW, dv, H);
+  set(T_FEATOUT, H, 3);
+
+  return T;
+}
+
 static int64_t dec_workspace_bytes(const dfn_decoder* m, int64_t R) {
   return align256((int64_t)TC_MAX_LAYERS * TC_BIAS_STRIDE * 4) + align256(R * m->desc.hidden * 4) + align256(pp_dec_scratch_bytes());
 }
@@ -491,31 +529,8 @@ extern "C" int dfn_decoder_load(dfn_decoder* m, const float* const* t, int n_ten
   for (int i = 0; i < n_tensors; ++i) DFN_CHECK_ARG(t[i] != nullptr, "dfn_decoder_load: tensor %d is null", i);
   cudaStream_t st = (cudaStream_t)stream;
   const dfn_decoder_desc& d = m->desc;
-  const int H = d.hidden, de = 6 * d.n_freq, dv = 6 * d.n_freq_views, dt = d.dim_et_embed;
-  std::vector<Lin> T(T_COUNT);
-  auto set = [&](int i, int in, int out) { T[i] = Lin{t[2 * i], t[2 * i + 1], in, out}; };
-  set(T_DE0, de + dt, 64);
-  set(T_DS0, de + dt, 64);
-  for (int i = 1; i < 5; ++i) {
-    set(T_DE0 + i, 64, 64);
-    set(T_DS0 + i, 64, 64);
-  }
-  set(T_DEOUT, 64, de);
-  set(T_DSOUT, 64, dt);
-  set(T_DESKIP, de, 64);
-  set(T_DSSKIP, dt, 64);
-  set(T_FCIN, de + d.dim_signal, H);
-  set(T_FCIN_TORSO, de + dt, H);
-  set(T_FCZ, d.z_dim, H);
-  for (int i = 0; i < 7; ++i) set(T_BLOCK0 + i, H, H);
-  set(T_FCZSKIP, d.z_dim, H);
-  set(T_FCPSKIP, de + d.dim_signal, H);
-  set(T_FCPSKIP_TORSO, de + dt, H);
-  set(T_SIGMA, H, 1);
-  set(T_FCZVIEW, d.z_dim, H);
-  set(T_FEATVIEW, H, H);
-  set(T_FCVIEW, dv, H);
-  set(T_FEATOUT, H, 3);
+  const int H = d.hidden, dv = 6 * d.n_freq_views, dt = d.dim_et_embed;
+  const std::vector<Lin> T = tensor_table(d, t);
 
   free_field(m->f[0]);
   free_field(m->f[1]);
@@ -539,6 +554,46 @@ extern "C" int dfn_decoder_load(dfn_decoder* m, const float* const* t, int n_ten
   DFN_CUDA(cudaMemcpyAsync(m->view_w, T[T_FCVIEW].w, (size_t)H * dv * 4, cudaMemcpyHostToDevice, st));
   DFN_CUDA(cudaStreamSynchronize(st));
   m->loaded = true;
+  return 0;
+}
+
+// Host-only: the layer program dfn_decoder_load builds for one field, as dense fp32 (no CUDA calls).
+extern "C" int dfn_decoder_program_host(const dfn_decoder_desc* desc, const float* const* t, int n_tensors, int field,
+                                        int max_layers, dfn_layer_info* layers, int* n_layers, float* weights, float* bias,
+                                        int* n_fold, int* fold_layer, float* fold_w, int* dimL, int* view_layer) {
+  DFN_CHECK_ARG(desc && t && layers && n_layers && weights && bias && n_fold && fold_layer && fold_w && dimL && view_layer,
+                "dfn_decoder_program_host: null argument");
+  DFN_CHECK_ARG(n_tensors == 2 * T_COUNT && (field == 0 || field == 1) && max_layers >= TC_MAX_LAYERS,
+                "dfn_decoder_program_host: expected %d tensors, field 0|1, max_layers >= %d", 2 * T_COUNT, TC_MAX_LAYERS);
+  DFN_CHECK_ARG(desc->hidden == 256 && desc->n_blocks == 8 && desc->skip == 4 && desc->n_freq >= 1 && desc->n_freq <= 10 &&
+                    desc->dim_et_embed >= 1 && desc->dim_et_embed <= 64,
+                "dfn_decoder_program_host: unsupported decoder shape");
+  const std::vector<Lin> T = tensor_table(*desc, t);
+  DecField F;
+  const int dsig = field == 0 ? desc->dim_signal : desc->dim_et_embed;
+  Builder B(&F, dsig + 2 * desc->z_dim);
+  std::vector<float> dense((size_t)TC_MAX_LAYERS * TC_BIAS_STRIDE * 6 * 64, 0.f);
+  B.dense = &dense;
+  if (field == 1) build_deform(B, T, *desc);
+  build_trunk(B, T, *desc, field == 1, dsig, dsig + desc->z_dim);
+  *n_layers = B.nl;
+  for (int l = 0; l < B.nl; ++l) {
+    const TcLayer& L = F.prog.layers[l];
+    layers[l].n = L.n;
+    layers[l].nkb = L.nkb;
+    layers[l].epi = L.epi;
+    layers[l].flags = L.flags;
+    for (int k = 0; k < 6; ++k) layers[l].kb[k] = L.kb[k];
+  }
+  memcpy(weights, dense.data(), dense.size() * 4);
+  memcpy(bias, B.bias.data(), B.bias.size() * 4);
+  *n_fold = F.n_fold;
+  *dimL = F.dimL;
+  *view_layer = F.view_layer;
+  for (int i = 0; i < F.n_fold; ++i) {
+    fold_layer[i] = F.fold_layer[i];
+    memcpy(fold_w + (size_t)i * F.dimL * TC_BIAS_STRIDE, B.folds[i].data(), (size_t)F.dimL * TC_BIAS_STRIDE * 4);
+  }
   return 0;
 }
 

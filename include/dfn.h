@@ -211,6 +211,21 @@ int dfn_decoder_query(const dfn_decoder* m, int field, int64_t R, int S, const f
 /* algorithmic MACs per sample of a field with the per-frame and per-ray terms folded (roofline accounting) */
 double dfn_decoder_macs_per_sample(const dfn_decoder* m, int field);
 
+/* Host-only introspection (no CUDA calls; used by the CPU tests): the layer program dfn_decoder_load compiles for one
+ * field.  layers[l]: output columns n, input K-blocks kb[0..nkb) (0..3 hidden blocks, 4 = positional encoding / deformed
+ * encoding, 5 = deformed signal), epilogue (0 relu, 1 per-ray-bias relu, 2 rgb+sigmoid, 3 sigma, 4 continue, 5 write
+ * staged blocks) and flags (1 = accumulates onto the previous layer).  weights: dense fp32 [max_layers][256][6*64]
+ * (row n, input block slot i, position k), bias [max_layers][256], fold_w [n_fold][dimL][256] with
+ * bias[fold_layer[i]][n] += sum_j fold_w[i][j][n] * latent[j], latent = [signal | z_shape | z_app].
+ * max_layers >= 20; fold_layer has 8 entries; fold_w holds 8*dimL*256 floats (dimL <= 1024). */
+typedef struct {
+  int n, nkb, epi, flags;
+  int kb[6];
+} dfn_layer_info;
+int dfn_decoder_program_host(const dfn_decoder_desc* desc, const float* const* tensors_host, int n_tensors, int field,
+                             int max_layers, dfn_layer_info* layers, int* n_layers, float* weights, float* bias,
+                             int* n_fold, int* fold_layer, float* fold_w, int* dimL, int* view_layer);
+
 /* ---- one chunk of the live render loop  (MAIN:617-619, MAIN:633-708) ----------------------------------
  * z sampling -> head field on the head-pose rays, torso field (with deformation) on the body-pose rays ->
  * background splice, two-field density mix, weights, colour sums.  z_shape / z_app: [2, z_dim] (row 0 head,
