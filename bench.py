@@ -184,7 +184,7 @@ def main():
     ap.add_argument('--steps', type=int, default=10)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--precision', default='bf16', choices=['bf16', 'bf16x3', 'fp32'])
+    ap.add_argument('--precision', default='bf16', choices=['bf16', 'fp16', 'bf16x3', 'fp32'])
     ap.add_argument('--workload', default='facenerf', choices=sorted(WORKLOADS))
     ap.add_argument('--frames', type=int, default=300, help='sequence workload: frames per step')
     ap.add_argument('--no-cpu-baseline', action='store_true')
@@ -208,7 +208,7 @@ def main():
     if world > 1:
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
         dist.init_process_group('nccl', device_id=dev)
-    prec = {'bf16': dfn.PREC_BF16, 'bf16x3': dfn.PREC_BF16X3, 'fp32': dfn.PREC_FP32}[args.precision]
+    prec = {'bf16': dfn.PREC_BF16, 'fp16': dfn.PREC_FP16, 'bf16x3': dfn.PREC_BF16X3, 'fp32': dfn.PREC_FP32}[args.precision]
 
     fr = synth.frame_inputs(H=H, W=W, seed=0)
     n_rays = H * W
@@ -228,7 +228,7 @@ def main():
         aud_dev = fr['aud'].to(dev)
         lat_host = fr['aud'].pin_memory()
         evals_per_ray = N_SAMPLES + N_SAMPLES + N_IMPORTANCE
-        kernel_name = 'mlp_tc_kernel<bf16>' if prec == dfn.PREC_BF16 else 'mlp_pp_kernel<bf16x3>'
+        kernel_name = 'mlp_pp_kernel<bf16x3>' if prec == dfn.PREC_BF16X3 else 'mlp_tc_kernel<%s>' % args.precision
         flops_note = 'algorithmic, latent/viewdir columns folded: 2*557,184 per MLP evaluation (BASELINE.md section 2)'
 
         def render(bc_full, lat):
@@ -256,7 +256,7 @@ def main():
         rgb_host = torch.empty((n_rays, 3), dtype=torch.float32).pin_memory()
         aud_dev, lat_host = torch.zeros(1, device=dev), torch.zeros(1).pin_memory()
         evals_per_ray = S
-        kernel_name = 'mlp_tc_kernel<bf16>' if prec == dfn.PREC_BF16 else 'mlp_pp_kernel<bf16x3>'
+        kernel_name = 'mlp_pp_kernel<bf16x3>' if prec == dfn.PREC_BF16X3 else 'mlp_tc_kernel<%s>' % args.precision
         flops_note = 'algorithmic, viewdir columns folded: 2*557,184 per MLP evaluation (NeRF and FaceNeRF coincide, SURVEY 8d)'
 
         def render(bc_full, lat):
@@ -271,7 +271,7 @@ def main():
         eng = dfn.RenderEngine(mk(0), mk(1), N_SAMPLES, N_IMPORTANCE, precision=prec)
         seq = synth.frame_inputs(H=H, W=W, seed=0, n_frames=args.frames)
         evals_per_ray = N_SAMPLES + N_SAMPLES + N_IMPORTANCE
-        kernel_name = 'mlp_tc_kernel<bf16>' if prec == dfn.PREC_BF16 else 'mlp_pp_kernel<bf16x3>'
+        kernel_name = 'mlp_pp_kernel<bf16x3>' if prec == dfn.PREC_BF16X3 else 'mlp_tc_kernel<%s>' % args.precision
         flops_note = 'algorithmic, latent/viewdir columns folded: 2*557,184 per MLP evaluation (BASELINE.md section 2)'
         n_rays = H * W * args.frames            # rays per step: the whole sequence
         b, e = 0, n_rays
@@ -402,7 +402,7 @@ def main():
         print(json.dumps({
             'metric': METRIC, 'value': value, 'unit': 'rays/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
             'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None,
-            'dtype': {'bf16': 'bf16', 'bf16x3': 'bf16x3 (split bf16, fp32-parity)', 'fp32': 'f32'}[args.precision],
+            'dtype': {'bf16': 'bf16', 'fp16': 'fp16', 'bf16x3': 'bf16x3 (split bf16, fp32-parity)', 'fp32': 'f32'}[args.precision],
             'data': 'synthetic',
             'config': {'workload': WORKLOADS[args.workload],
                        'rays_per_step': n_rays, 'mlp_evals_per_ray': evals_per_ray, 'precision': args.precision,

@@ -64,9 +64,11 @@ struct Params {
 
 // ------------------------------------------------------------------------------------ kernel
 // X3 = false: bf16, two tile slots (384 threads).  X3 = true: split-bf16, one slot (256 threads).
-template <bool X3>
+// F16 (bf16-mode schedule only): fp16 operands -- P.w_hi then points at the fp16 weight stages.
+template <bool X3, bool F16 = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(X3 ? 256 : 384, 1)
     mlp_tc_kernel(const __grid_constant__ Params P) {
+  static_assert(!(X3 && F16), "fp16 operands run in the single-pass schedule");
   constexpr int NSLOT = X3 ? 1 : 2;
   constexpr int NPART = X3 ? 2 : 1;
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -186,7 +188,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(X3 ? 256 : 384, 1)
             tcgen05_fence_after();
             if (tr) t_w1 = clock64();
             const uint32_t acc = tmem_base + (uint32_t)s * 256u;
-            const uint32_t idesc = make_idesc(L.n);
+            const uint32_t idesc = F16 ? make_idesc_f16(L.n) : make_idesc(L.n);
             for (int kbi = 0; kbi < L.nkb; ++kbi) {
               const uint32_t a_hi = sbase + (uint32_t)(s * TC_KB_PER_TILE + L.kb[kbi]) * KB_BYTES;
               const uint64_t adesc_hi = make_smem_desc(a_hi);
@@ -305,7 +307,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(X3 ? 256 : 384, 1)
           float o[8];
 #pragma unroll
           for (int e = 0; e < 8; ++e) o[e] = pe[ch * 8 + e];
-          store_chunk<X3>(pe_hi, pe_lo, row, (uint32_t)ch, o);
+          store_chunk<X3, F16>(pe_hi, pe_lo, row, (uint32_t)ch, o);
         }
       }
       fence_proxy_async();
@@ -342,9 +344,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(X3 ? 256 : 384, 1)
           tcgen05_fence_before();
         } else {
           if (L.epi == TC_EPI_VIEW0)
-            epilogue_relu<X3, true>(acc, P.view_w, P.view_bias + ray * P.view_w, 0u, arena_hi, arena_lo, row);
+            epilogue_relu<X3, true, F16>(acc, P.view_w, P.view_bias + ray * P.view_w, 0u, arena_hi, arena_lo, row);
           else
-            epilogue_relu<X3, false>(acc, (int)L.n, nullptr, smem_u32(bias_s), arena_hi, arena_lo, row);
+            epilogue_relu<X3, false, F16>(acc, (int)L.n, nullptr, smem_u32(bias_s), arena_hi, arena_lo, row);
           if (L.epi == TC_EPI_VIEW0) {
             uint32_t v[16];
             tmem_ld16(acc + P.view_w, v);
@@ -459,6 +461,8 @@ void tc_free_model(dfn_model* m) {
   m->tc2_hi = m->tc2_lo = nullptr;
   cudaFree(m->tc_hi);
   cudaFree(m->tc_lo);
+  cudaFree(m->tc_h16);
+  m->tc_h16 = nullptr;
   cudaFree(m->tc_bias);
   cudaFree(m->tc_fold_w);
   cudaFree(m->tc_view_w);
@@ -614,6 +618,8 @@ int tc_pack_model(dfn_model* m, const float* const* t, cudaStream_t st) {
   DFN_CUDA(cudaMemcpyAsync(m->tc2_lo, pk.lo2.data(), pk.lo2.size(), cudaMemcpyHostToDevice, st));
   DFN_CUDA(cudaMalloc(&m->tc_hi, pk.hi32.size()));
   DFN_CUDA(cudaMalloc(&m->tc_lo, pk.lo32.size()));
+  DFN_CUDA(cudaMalloc(&m->tc_h16, pk.h16.size()));
+  DFN_CUDA(cudaMemcpyAsync(m->tc_h16, pk.h16.data(), pk.h16.size(), cudaMemcpyHostToDevice, st));
   DFN_CUDA(cudaMalloc(&m->tc_bias, bias.size() * 4));
   DFN_CUDA(cudaMalloc(&m->tc_fold_w, fold_w.size() * 4));
   DFN_CUDA(cudaMemcpyAsync(m->tc_hi, pk.hi32.data(), pk.hi32.size(), cudaMemcpyHostToDevice, st));
@@ -731,6 +737,14 @@ int tc_query_points(const dfn_model* m, int64_t R, int S, const float* rays_o, c
       attr_done = true;
     }
     tc::mlp_tc_kernel<false><<<grid, 384, tc::SMEM_TOTAL, st>>>(P);
+  } else if (precision == DFN_PREC_FP16) {
+    static bool attr_done = false;
+    if (!attr_done) {
+      DFN_CUDA(cudaFuncSetAttribute(tc::mlp_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_TOTAL));
+      attr_done = true;
+    }
+    P.w_hi = m->tc_h16;
+    tc::mlp_tc_kernel<false, true><<<grid, 384, tc::SMEM_TOTAL, st>>>(P);
   } else if (precision == DFN_PREC_BF16X3) {
     static bool attr_done = false;
     if (!attr_done) {

@@ -66,6 +66,7 @@ struct dfn_model {
   uint32_t tc32_woff[dfn::TC_MAX_LAYERS] = {};  // per-layer offsets into tc_hi / tc_lo
   uint8_t* tc_hi = nullptr;     // packed bf16 (hi) weight stages
   uint8_t* tc_lo = nullptr;     // packed bf16 (lo = bf16(w - hi)) weight stages, same offsets
+  uint8_t* tc_h16 = nullptr;    // packed fp16 weight stages (DFN_PREC_FP16), same offsets
   int64_t tc_blob_bytes = 0;
   float* tc_bias = nullptr;     // [n_layers][256] static biases
   float* tc_fold_w = nullptr;   // [2][W][dim_aud] latent columns of the two folding layers

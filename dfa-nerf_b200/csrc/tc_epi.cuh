@@ -9,14 +9,21 @@ namespace tc {
 static constexpr int KB_BYTES = TILE_M * 128;      // one activation K-block: 128 rows x 64 bf16
 
 // Writes 8 consecutive columns (one 16-byte chunk) of this thread's row.
-template <bool X3>
+template <bool X3, bool F16 = false>
 __device__ __forceinline__ void store_chunk(uint8_t* blk_hi, uint8_t* blk_lo, uint32_t row, uint32_t chunk,
                                             const float (&v)[8]) {
   uint4 h;
-  h.x = pack_bf16(v[0], v[1]);
-  h.y = pack_bf16(v[2], v[3]);
-  h.z = pack_bf16(v[4], v[5]);
-  h.w = pack_bf16(v[6], v[7]);
+  if (F16) {
+    h.x = pack_f16(v[0], v[1]);
+    h.y = pack_f16(v[2], v[3]);
+    h.z = pack_f16(v[4], v[5]);
+    h.w = pack_f16(v[6], v[7]);
+  } else {
+    h.x = pack_bf16(v[0], v[1]);
+    h.y = pack_bf16(v[2], v[3]);
+    h.z = pack_bf16(v[4], v[5]);
+    h.w = pack_bf16(v[6], v[7]);
+  }
   *reinterpret_cast<uint4*>(blk_hi + swz(row, chunk)) = h;
   if (X3) {
     uint4 l;
@@ -30,7 +37,7 @@ __device__ __forceinline__ void store_chunk(uint8_t* blk_hi, uint8_t* blk_lo, ui
 
 // One 32-column chunk of this thread's row: + bias, ReLU, bf16 (hi[/lo]) and four 16-byte stores into the
 // swizzled K-block.  `chunk32` = index of the 32-column chunk inside the layer output.
-template <bool X3, bool GLOBAL_BIAS>
+template <bool X3, bool GLOBAL_BIAS, bool F16 = false>
 __device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[32], int chunk32, const float* gbias, uint32_t sbias,
                                                uint8_t* arena_hi, uint8_t* arena_lo, uint32_t row) {
   uint8_t* dst_hi = arena_hi + (size_t)(chunk32 >> 1) * KB_BYTES;
@@ -43,10 +50,17 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[32], int chun
     const uint32_t c16 = (uint32_t)((chunk32 & 1) * 4 + g);
     if (!X3) {
       uint4 h;
-      h.x = add_relu_pack(v[g * 8 + 0], v[g * 8 + 1], b[0], b[1]);
-      h.y = add_relu_pack(v[g * 8 + 2], v[g * 8 + 3], b[2], b[3]);
-      h.z = add_relu_pack(v[g * 8 + 4], v[g * 8 + 5], b[4], b[5]);
-      h.w = add_relu_pack(v[g * 8 + 6], v[g * 8 + 7], b[6], b[7]);
+      if (F16) {
+        h.x = add_relu_pack_f16(v[g * 8 + 0], v[g * 8 + 1], b[0], b[1]);
+        h.y = add_relu_pack_f16(v[g * 8 + 2], v[g * 8 + 3], b[2], b[3]);
+        h.z = add_relu_pack_f16(v[g * 8 + 4], v[g * 8 + 5], b[4], b[5]);
+        h.w = add_relu_pack_f16(v[g * 8 + 6], v[g * 8 + 7], b[6], b[7]);
+      } else {
+        h.x = add_relu_pack(v[g * 8 + 0], v[g * 8 + 1], b[0], b[1]);
+        h.y = add_relu_pack(v[g * 8 + 2], v[g * 8 + 3], b[2], b[3]);
+        h.z = add_relu_pack(v[g * 8 + 4], v[g * 8 + 5], b[4], b[5]);
+        h.w = add_relu_pack(v[g * 8 + 6], v[g * 8 + 7], b[6], b[7]);
+      }
       *reinterpret_cast<uint4*>(dst_hi + swz(row, c16)) = h;
     } else {
       float o[8];
@@ -59,7 +73,7 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[32], int chun
 
 // Accumulator columns [0, ncols) of this thread's row -> next layer's activation blocks.  The TMEM load of
 // chunk c+1 is in flight while chunk c is processed (tcgen05.wait::ld waits for all outstanding loads).
-template <bool X3, bool GLOBAL_BIAS>
+template <bool X3, bool GLOBAL_BIAS, bool F16 = false>
 __device__ __forceinline__ void epilogue_relu(uint32_t acc, int ncols, const float* gbias, uint32_t sbias,
                                               uint8_t* arena_hi, uint8_t* arena_lo, uint32_t row) {
   uint32_t v0[32], v1[32];
@@ -68,10 +82,10 @@ __device__ __forceinline__ void epilogue_relu(uint32_t acc, int ncols, const flo
   for (int c = 0; c < nch; c += 2) {
     tmem_ld_wait();
     tmem_ld32(acc + (c + 1) * 32, v1);
-    epilogue_chunk<X3, GLOBAL_BIAS>(v0, c, gbias, sbias, arena_hi, arena_lo, row);
+    epilogue_chunk<X3, GLOBAL_BIAS, F16>(v0, c, gbias, sbias, arena_hi, arena_lo, row);
     tmem_ld_wait();
     if (c + 2 < nch) tmem_ld32(acc + (c + 2) * 32, v0);
-    epilogue_chunk<X3, GLOBAL_BIAS>(v1, c + 1, gbias, sbias, arena_hi, arena_lo, row);
+    epilogue_chunk<X3, GLOBAL_BIAS, F16>(v1, c + 1, gbias, sbias, arena_hi, arena_lo, row);
   }
 }
 

@@ -4,6 +4,8 @@
 #include <stdint.h>
 #include <string.h>
 
+#include <cuda_fp16.h>
+
 #include <vector>
 
 namespace dfn {
@@ -26,6 +28,7 @@ static inline float bf2f(uint16_t h) {
 struct Packer {
   std::vector<uint8_t> hi, lo;       // [<=128 rows x 64 K] stages, 128-byte swizzle (mlp_ts.cu)
   std::vector<uint8_t> hi32, lo32;   // [n rows x 32 K] stages, 64-byte swizzle (mlp_tc.cu)
+  std::vector<uint8_t> h16;          // the hi32 images with fp16 instead of bf16 values (DFN_PREC_FP16), same offsets
   std::vector<uint8_t> hi2, lo2;     // [n/2 rows x 64 K] per CTA of a pair, 128-byte swizzle (mlp_tc2.cu)
   uint32_t last32 = 0;               // offset of the last layer added to hi32
   uint32_t last2 = 0;                // offset of the last layer added to hi2
@@ -63,6 +66,7 @@ struct Packer {
         const size_t base = hi32.size();
         hi32.resize(base + (size_t)n_out * 64, 0);
         lo32.resize(base + (size_t)n_out * 64, 0);
+        h16.resize(base + (size_t)n_out * 64, 0);
         for (int r = 0; r < n_out; ++r) {
           for (int k = 0; k < 32; ++k) {
             const float w = wfun(r, kbi, kh * 32 + k);
@@ -71,6 +75,8 @@ struct Packer {
             const size_t o = base + (size_t)r * 64 + ((((size_t)k >> 3) ^ (((size_t)r >> 1) & 3)) << 4) + ((size_t)k & 7) * 2;
             memcpy(&hi32[o], &h, 2);
             memcpy(&lo32[o], &l, 2);
+            const __half hh = __float2half_rn(w);
+            memcpy(&h16[o], &hh, 2);
           }
         }
       }

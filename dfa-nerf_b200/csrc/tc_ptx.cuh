@@ -190,6 +190,11 @@ __device__ __forceinline__ uint32_t make_idesc(uint32_t n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((n >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
 }
 
+// same with fp16 operands (a_format = b_format = 0)
+__device__ __forceinline__ uint32_t make_idesc_f16(uint32_t n) {
+  return (1u << 4) | ((n >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
+}
+
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&t);
@@ -219,6 +224,24 @@ __device__ __forceinline__ uint32_t add_relu_pack(uint32_t a0, uint32_t a1, floa
   return r;
 }
 
+
+// fp16 variants (DFN_PREC_FP16: 11-bit significands instead of 8; saturating, so an activation beyond 65504 cannot
+// become inf)
+__device__ __forceinline__ uint32_t pack_f16(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+__device__ __forceinline__ uint32_t add_relu_pack_f16(uint32_t a0, uint32_t a1, float b0, float b1) {
+  uint64_t a, b, c;
+  uint32_t c0, c1, r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(a) : "r"(a0), "r"(a1));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(b) : "f"(b0), "f"(b1));
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(c) : "l"(a), "l"(b));
+  asm("mov.b64 {%0, %1}, %2;" : "=r"(c0), "=r"(c1) : "l"(c));
+  asm("cvt.rn.relu.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(__uint_as_float(c1)), "f"(__uint_as_float(c0)));
+  return r;
+}
 
 // A operand from TMEM (rows = lanes, two bf16 per 32-bit column), B from shared memory.
 __device__ __forceinline__ void umma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,

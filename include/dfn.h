@@ -39,6 +39,8 @@ enum {
 enum {
   DFN_PREC_FP32 = 0,   /* fp32 FFMA kernels (no tensor cores), reference-exact up to summation order */
   DFN_PREC_BF16 = 1,   /* tcgen05 kind::f16 bf16 operands, fp32 accumulate in TMEM (throughput mode) */
+  DFN_PREC_FP16 = 2,   /* same kernel and speed with fp16 operands (11-bit significands, saturating): ~10x closer to
+                          fp32 than bf16; FaceNeRF / NeRF models */
   DFN_PREC_BF16X3 = 3  /* tcgen05 split-bf16: A_hi*W_hi + A_lo*W_hi + A_hi*W_lo (fp32-parity mode) */
 };
 

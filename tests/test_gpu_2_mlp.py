@@ -124,6 +124,26 @@ def test_query_points_bf16_vs_bf16_oracle(dfn, R, S):
     assert e16 < e32 + 1e-3 and s16 < s32 + 0.05
 
 
+@pytest.mark.parametrize('R,S', [(37, 64), (300, 64), (21, 192)])
+def test_query_points_fp16_between_bf16_and_fp32(dfn, R, S):
+    """DFN_PREC_FP16: the bf16 kernel and schedule with fp16 operands (11-bit significands).  Same speed, several times
+    closer to the fp32 oracle than bf16 on everything compositing consumes; reported, and gated on that ordering."""
+    ro, rd, vd, z, aud = _query_case(R, S)
+    sd = synth.facenerf_state_dict(0)
+    net = face(dfn, 0)
+    with torch.no_grad():
+        ref = O.run_network(sd, 'facenerf', ro[:, None] + rd[:, None] * z[:, :, None], vd, aud)
+    err = {}
+    for name, prec in (('bf16', dfn.PREC_BF16), ('fp16', dfn.PREC_FP16)):
+        eng = dfn.RenderEngine(net, None, S, 0, precision=prec)
+        raw = eng.query_points(net, ro.to(DEV), rd.to(DEV), vd.to(DEV), z.to(DEV), aud.to(DEV))
+        assert torch.isfinite(raw).all()
+        err[name] = _alpha_err(raw, ref, z, rd) + (maxerr(raw[..., 3], ref[..., 3]),)
+    print('R=%d S=%d  weights / colour / raw sigma error: bf16 %.2e %.2e %.2e | fp16 %.2e %.2e %.2e' % ((R, S) + err['bf16'] + err['fp16']))
+    assert err['fp16'][0] < 0.5 * err['bf16'][0] and err['fp16'][2] < 0.5 * err['bf16'][2]
+    assert err['fp16'][0] < 5e-3 and err['fp16'][1] < 5e-5
+
+
 def test_query_points_nerf_model(dfn):
     R, S = 19, 64
     ro, rd, vd, z, aud = _query_case(R, S, seed=5)
