@@ -33,6 +33,7 @@ struct DecField {
   uint32_t woff32[TC_MAX_LAYERS] = {};
   uint8_t* w_hi = nullptr;
   uint8_t* w_lo = nullptr;
+  uint8_t* w_h16 = nullptr;  // fp16 stages (DFN_PREC_FP16), same offsets
   float* bias = nullptr;     // [n_layers][256] static part
   int n_fold = 0;
   int fold_layer[8] = {};
@@ -204,6 +205,8 @@ struct Builder {
     F->prog.n_layers = nl;
     DFN_CUDA(cudaMalloc(&F->w_hi, pk.hi32.size()));
     DFN_CUDA(cudaMalloc(&F->w_lo, pk.lo32.size()));
+    DFN_CUDA(cudaMalloc(&F->w_h16, pk.h16.size()));
+    DFN_CUDA(cudaMemcpyAsync(F->w_h16, pk.h16.data(), pk.h16.size(), cudaMemcpyHostToDevice, st));
     DFN_CUDA(cudaMalloc(&F->bias, bias.size() * 4));
     std::vector<float> fw;
     for (auto& f : folds) fw.insert(fw.end(), f.begin(), f.end());
@@ -229,6 +232,8 @@ enum {  // load order (dfn.h)
 static void free_field(DecField& F) {
   cudaFree(F.w_hi);
   cudaFree(F.w_lo);
+  cudaFree(F.w_h16);
+  F.w_h16 = nullptr;
   cudaFree(F.bias);
   cudaFree(F.fold_w);
   F.w_hi = F.w_lo = nullptr;
@@ -448,8 +453,8 @@ static int dec_query(const dfn_decoder* m, int field, int64_t R, int S, const fl
     set_error("dfn_decoder_query: decoder has no weights");
     return DFN_E_STATE;
   }
-  DFN_CHECK_ARG(precision == DFN_PREC_BF16 || precision == DFN_PREC_BF16X3,
-                "dfn_decoder_query: precision must be DFN_PREC_BF16 or DFN_PREC_BF16X3 (the fp32 path is dfn_linear)");
+  DFN_CHECK_ARG(precision == DFN_PREC_BF16 || precision == DFN_PREC_FP16 || precision == DFN_PREC_BF16X3,
+                "dfn_decoder_query: precision must be DFN_PREC_BF16, DFN_PREC_FP16 or DFN_PREC_BF16X3 (the fp32 path is dfn_linear)");
   DFN_CHECK_ARG((reinterpret_cast<uintptr_t>(raw) & 15) == 0, "dfn_decoder_query: raw must be 16-byte aligned");
   if (workspace_bytes < dec_workspace_bytes(m, R)) {
     set_error("dfn_decoder_query: workspace %lld < %lld bytes", (long long)workspace_bytes, (long long)dec_workspace_bytes(m, R));
@@ -482,7 +487,7 @@ static int dec_query(const dfn_decoder* m, int field, int64_t R, int S, const fl
     DFN_LAUNCH_CHECK();
   }
   const bool prof = profile_begin(st, F.macs_pt * (double)R * S);
-  int rc = pp_launch_prog(F.prog, F.woff32, F.w_hi, F.w_lo, true, d.n_freq, d.hidden, bias_ws, vbias_ws, scratch, R, S, rays_o,
+  int rc = pp_launch_prog(F.prog, F.woff32, precision == DFN_PREC_FP16 ? F.w_h16 : F.w_hi, F.w_lo, true, d.n_freq, d.hidden, bias_ws, vbias_ws, scratch, R, S, rays_o,
                           rays_d, z_vals, raw, precision, st);
   if (prof) profile_end(st);
   if (rc) return rc;

@@ -32,13 +32,13 @@
 #include "common.cuh"
 #include "model.h"
 #include "tc_ptx.cuh"
+#include "tc_epi.cuh"
 
 namespace dfn {
 namespace pp {
 
 using namespace dfn::tc;
 
-static constexpr int KB_BYTES = TILE_M * 128;   // activation K-block [128 x 64] bf16
 static constexpr int SLOT_BYTES = 16384;        // half a ring entry
 static constexpr int N_ENTRIES = 3;             // ring entries (2 x 16 KB each)
 static constexpr int ARENA_BLOCKS = 8;          // bf16: 2 tiles x 4 blocks; bf16x3: hi 4 + lo 4
@@ -93,47 +93,9 @@ __device__ __forceinline__ uint32_t layer_entries(const TcLayer& L) {
   return (uint32_t)L.nkb * NPART + (layer_has_pe(L) ? 1u : 0u);
 }
 
-// + bias, ReLU, bf16 (hi[/lo]) of one 32-column chunk -> four 16-byte stores into the swizzled K-block.
-template <bool X3, bool GLOBAL_BIAS>
-__device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[32], int chunk32, const float* gbias, uint32_t sbias,
-                                               uint8_t* arena_hi, uint8_t* arena_lo, uint32_t row) {
-  uint8_t* dst_hi = arena_hi + (size_t)(chunk32 >> 1) * KB_BYTES;
-  uint8_t* dst_lo = arena_lo + (size_t)(chunk32 >> 1) * KB_BYTES;
-#pragma unroll
-  for (int g = 0; g < 4; ++g) {
-    float b[8];
-    if (GLOBAL_BIAS) ldg_f32x8(gbias + chunk32 * 32 + g * 8, b);
-    else lds_f32x8(sbias + (uint32_t)(chunk32 * 32 + g * 8) * 4u, b);
-    const uint32_t c16 = (uint32_t)((chunk32 & 1) * 4 + g);
-    uint4 h;
-    if (!X3) {
-      h.x = add_relu_pack(v[g * 8 + 0], v[g * 8 + 1], b[0], b[1]);
-      h.y = add_relu_pack(v[g * 8 + 2], v[g * 8 + 3], b[2], b[3]);
-      h.z = add_relu_pack(v[g * 8 + 4], v[g * 8 + 5], b[4], b[5]);
-      h.w = add_relu_pack(v[g * 8 + 6], v[g * 8 + 7], b[6], b[7]);
-      *reinterpret_cast<uint4*>(dst_hi + swz(row, c16)) = h;
-    } else {
-      float o[8];
-#pragma unroll
-      for (int e = 0; e < 8; ++e) o[e] = fmaxf(__uint_as_float(v[g * 8 + e]) + b[e], 0.f);
-      h.x = pack_bf16(o[0], o[1]);
-      h.y = pack_bf16(o[2], o[3]);
-      h.z = pack_bf16(o[4], o[5]);
-      h.w = pack_bf16(o[6], o[7]);
-      *reinterpret_cast<uint4*>(dst_hi + swz(row, c16)) = h;
-      uint4 l;
-      l.x = pack_bf16(o[0] - bf16_lo_f(h.x), o[1] - bf16_hi_f(h.x));
-      l.y = pack_bf16(o[2] - bf16_lo_f(h.y), o[3] - bf16_hi_f(h.y));
-      l.z = pack_bf16(o[4] - bf16_lo_f(h.z), o[5] - bf16_hi_f(h.z));
-      l.w = pack_bf16(o[6] - bf16_lo_f(h.w), o[7] - bf16_hi_f(h.w));
-      *reinterpret_cast<uint4*>(dst_lo + swz(row, c16)) = l;
-    }
-  }
-}
-
 // TC_EPI_STAGE: + bias (no activation), bf16 (hi[/lo]) of one 32-column chunk -> the tile's staged block in the
 // scratch ([16-byte chunk][row] layout, as the PE warps write it).  blk_base = staged block (chunk32 >> 1).
-template <bool X3>
+template <bool X3, bool F16>
 __device__ __forceinline__ void stage_chunk(const uint32_t (&v)[32], int chunk32, uint32_t sbias, uint8_t* blk_base,
                                             uint32_t row) {
   uint4* dst = reinterpret_cast<uint4*>(blk_base) + row;
@@ -145,10 +107,17 @@ __device__ __forceinline__ void stage_chunk(const uint32_t (&v)[32], int chunk32
     for (int e = 0; e < 8; ++e) o[e] = __uint_as_float(v[g * 8 + e]) + b[e];
     const int c16 = (chunk32 & 1) * 4 + g;
     uint4 h;
-    h.x = pack_bf16(o[0], o[1]);
-    h.y = pack_bf16(o[2], o[3]);
-    h.z = pack_bf16(o[4], o[5]);
-    h.w = pack_bf16(o[6], o[7]);
+    if (F16) {
+      h.x = pack_f16(o[0], o[1]);
+      h.y = pack_f16(o[2], o[3]);
+      h.z = pack_f16(o[4], o[5]);
+      h.w = pack_f16(o[6], o[7]);
+    } else {
+      h.x = pack_bf16(o[0], o[1]);
+      h.y = pack_bf16(o[2], o[3]);
+      h.z = pack_bf16(o[4], o[5]);
+      h.w = pack_bf16(o[6], o[7]);
+    }
     dst[c16 * TILE_M] = h;
     if (X3) {
       uint4 l;
@@ -164,8 +133,10 @@ __device__ __forceinline__ void stage_chunk(const uint32_t (&v)[32], int chunk32
 __device__ __forceinline__ float sigmoid_f(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
 
 // X3 = false: bf16, two tile slots.  X3 = true: split-bf16, one slot.  DEC: Decoder programs (see the header).
-template <bool X3, bool DEC>
+// F16 (single-pass schedule only): fp16 operands -- P.w_hi then points at the fp16 weight stages (DFN_PREC_FP16).
+template <bool X3, bool DEC, bool F16 = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1) mlp_pp_kernel(const __grid_constant__ Params P) {
+  static_assert(!(X3 && F16), "fp16 operands run in the single-pass schedule");
   constexpr int NSLOT = X3 ? 1 : 2;
   constexpr int NPART = X3 ? 2 : 1;
   constexpr int ROWB = X3 ? 256 : 128;  // scratch bytes per row of a staged block
@@ -273,7 +244,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1) mlp_pp_kerne
     for (int j = 0; j < n_iter; ++j) {
       for (int l = 0; l < NL; ++l) {
         const TcLayer& L = P.layers[l];
-        const uint32_t idesc = make_idesc(L.n);
+        const uint32_t idesc = F16 ? make_idesc_f16(L.n) : make_idesc(L.n);
         const uint32_t acc0 = DEC && (L.flags & TC_F_ACCUM) ? 1u : 0u;  // continue the previous (TC_EPI_CONT) layer's sums
         for (int s = 0; s < NSLOT; ++s) {
           if (!valid_slot(j, s)) continue;
@@ -485,10 +456,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1) mlp_pp_kerne
           for (int cc = 0; cc < nch; cc += 2) {
             tmem_ld_wait();
             tmem_ld32(acc + (cc + 1) * 32, v1);
-            stage_chunk<X3>(v0, cc, sbias, scr(j & 1, s, cc >> 1), row);
+            stage_chunk<X3, F16>(v0, cc, sbias, scr(j & 1, s, cc >> 1), row);
             tmem_ld_wait();
             if (cc + 2 < nch) tmem_ld32(acc + (cc + 2) * 32, v0);
-            stage_chunk<X3>(v1, cc + 1, sbias, scr(j & 1, s, (cc + 1) >> 1), row);
+            stage_chunk<X3, F16>(v1, cc + 1, sbias, scr(j & 1, s, (cc + 1) >> 1), row);
           }
         } else {
           const bool per_ray = L.epi == TC_EPI_VIEW0;
@@ -499,12 +470,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1) mlp_pp_kerne
           for (int cc = 0; cc < nch; cc += 2) {
             tmem_ld_wait();
             tmem_ld32(acc + (cc + 1) * 32, v1);
-            if (per_ray) epilogue_chunk<X3, true>(v0, cc, rb, 0u, arena_hi, arena_lo, row);
-            else epilogue_chunk<X3, false>(v0, cc, nullptr, sbias, arena_hi, arena_lo, row);
+            if (per_ray) epilogue_chunk<X3, true, F16>(v0, cc, rb, 0u, arena_hi, arena_lo, row);
+            else epilogue_chunk<X3, false, F16>(v0, cc, nullptr, sbias, arena_hi, arena_lo, row);
             tmem_ld_wait();
             if (cc + 2 < nch) tmem_ld32(acc + (cc + 2) * 32, v0);
-            if (per_ray) epilogue_chunk<X3, true>(v1, cc + 1, rb, 0u, arena_hi, arena_lo, row);
-            else epilogue_chunk<X3, false>(v1, cc + 1, nullptr, sbias, arena_hi, arena_lo, row);
+            if (per_ray) epilogue_chunk<X3, true, F16>(v1, cc + 1, rb, 0u, arena_hi, arena_lo, row);
+            else epilogue_chunk<X3, false, F16>(v1, cc + 1, nullptr, sbias, arena_hi, arena_lo, row);
           }
           if (!DEC && per_ray) {
             uint32_t v[16];
@@ -702,10 +673,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1) mlp_pp_kerne
             for (int cc = 0; cc < nch; cc += 2) {
               tmem_ld_wait();
               tmem_ld32(acc + (ch0 + cc + 1) * 32, v1);
-              stage_chunk<X3>(v0, ch0 + cc, sbias, scr(j & 1, s, (ch0 + cc) >> 1), row);
+              stage_chunk<X3, F16>(v0, ch0 + cc, sbias, scr(j & 1, s, (ch0 + cc) >> 1), row);
               tmem_ld_wait();
               if (cc + 2 < nch) tmem_ld32(acc + (ch0 + cc + 2) * 32, v0);
-              stage_chunk<X3>(v1, ch0 + cc + 1, sbias, scr(j & 1, s, (ch0 + cc + 1) >> 1), row);
+              stage_chunk<X3, F16>(v1, ch0 + cc + 1, sbias, scr(j & 1, s, (ch0 + cc + 1) >> 1), row);
             }
           } else {
             const bool per_ray = L.epi == TC_EPI_VIEW0;
@@ -728,13 +699,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1) mlp_pp_kerne
               const int c0 = 2 * cc + hf, c1 = c0 + 2;
               tmem_ld_wait();
               tmem_ld32(acc + c1 * 32, v1);
-              if (per_ray) epilogue_chunk<X3, true>(v0, c0, rb, 0u, arena_hi, arena_lo, row);
-              else epilogue_chunk<X3, false>(v0, c0, nullptr, sbias, arena_hi, arena_lo, row);
+              if (per_ray) epilogue_chunk<X3, true, F16>(v0, c0, rb, 0u, arena_hi, arena_lo, row);
+              else epilogue_chunk<X3, false, F16>(v0, c0, nullptr, sbias, arena_hi, arena_lo, row);
               block_done(cc);
               tmem_ld_wait();
               if (cc + 2 < nch) tmem_ld32(acc + (c1 + 2) * 32, v0);
-              if (per_ray) epilogue_chunk<X3, true>(v1, c1, rb, 0u, arena_hi, arena_lo, row);
-              else epilogue_chunk<X3, false>(v1, c1, nullptr, sbias, arena_hi, arena_lo, row);
+              if (per_ray) epilogue_chunk<X3, true, F16>(v1, c1, rb, 0u, arena_hi, arena_lo, row);
+              else epilogue_chunk<X3, false, F16>(v1, c1, nullptr, sbias, arena_hi, arena_lo, row);
               block_done(cc + 1);
             }
             if (!DEC && per_ray && hf == 0) {  // density head: accumulator column view_w, no activation
@@ -856,10 +827,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1) mlp_pp_kerne
 #pragma unroll
         for (int ch = 0; ch < 8; ++ch) {
           uint4 h;
-          h.x = pack_bf16(pe[ch * 8 + 0], pe[ch * 8 + 1]);
-          h.y = pack_bf16(pe[ch * 8 + 2], pe[ch * 8 + 3]);
-          h.z = pack_bf16(pe[ch * 8 + 4], pe[ch * 8 + 5]);
-          h.w = pack_bf16(pe[ch * 8 + 6], pe[ch * 8 + 7]);
+          if (F16) {
+            h.x = pack_f16(pe[ch * 8 + 0], pe[ch * 8 + 1]);
+            h.y = pack_f16(pe[ch * 8 + 2], pe[ch * 8 + 3]);
+            h.z = pack_f16(pe[ch * 8 + 4], pe[ch * 8 + 5]);
+            h.w = pack_f16(pe[ch * 8 + 6], pe[ch * 8 + 7]);
+          } else {
+            h.x = pack_bf16(pe[ch * 8 + 0], pe[ch * 8 + 1]);
+            h.y = pack_bf16(pe[ch * 8 + 2], pe[ch * 8 + 3]);
+            h.z = pack_bf16(pe[ch * 8 + 4], pe[ch * 8 + 5]);
+            h.w = pack_bf16(pe[ch * 8 + 6], pe[ch * 8 + 7]);
+          }
           dst[ch * TILE_M] = h;
           if (X3) {
             uint4 l;
@@ -887,14 +865,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1) mlp_pp_kerne
 int64_t pp_scratch_bytes() { return (int64_t)(num_sms() + 1) * 2 * 2 * tc::TILE_M * 256; }
 int64_t pp_dec_scratch_bytes() { return 2 * pp_scratch_bytes(); }  // two staged blocks per tile
 
-template <bool X3, bool DEC>
+template <bool X3, bool DEC, bool F16 = false>
 static int pp_launch_t(const pp::Params& P, int grid, cudaStream_t st) {
   static bool attr_done = false;
   if (!attr_done) {
-    DFN_CUDA(cudaFuncSetAttribute(pp::mlp_pp_kernel<X3, DEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, pp::SMEM_TOTAL));
+    DFN_CUDA(cudaFuncSetAttribute(pp::mlp_pp_kernel<X3, DEC, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, pp::SMEM_TOTAL));
     attr_done = true;
   }
-  pp::mlp_pp_kernel<X3, DEC><<<grid, 384, pp::SMEM_TOTAL, st>>>(P);
+  pp::mlp_pp_kernel<X3, DEC, F16><<<grid, 384, pp::SMEM_TOTAL, st>>>(P);
   return 0;
 }
 
@@ -930,6 +908,13 @@ int pp_launch_prog(const TcProgram& prog, const uint32_t* woff32, const uint8_t*
   grid = (grid + 1) & ~1;
   if (grid > num_sms()) grid = num_sms() & ~1;
   const bool x3 = precision == DFN_PREC_BF16X3;
+  if (precision == DFN_PREC_FP16) {   // w_hi: the fp16 stages (Decoder programs; FaceNeRF / NeRF use mlp_tc.cu)
+    if (!decoder) {
+      set_error("pp_launch_prog: DFN_PREC_FP16 is wired for the Decoder programs only");
+      return DFN_E_UNSUPPORTED;
+    }
+    return pp_launch_t<false, true, true>(P, grid, st);
+  }
   if (decoder) return x3 ? pp_launch_t<true, true>(P, grid, st) : pp_launch_t<false, true>(P, grid, st);
   return x3 ? pp_launch_t<true, false>(P, grid, st) : pp_launch_t<false, false>(P, grid, st);
 }

@@ -40,7 +40,7 @@ enum {
   DFN_PREC_FP32 = 0,   /* fp32 FFMA kernels (no tensor cores), reference-exact up to summation order */
   DFN_PREC_BF16 = 1,   /* tcgen05 kind::f16 bf16 operands, fp32 accumulate in TMEM (throughput mode) */
   DFN_PREC_FP16 = 2,   /* same kernel and speed with fp16 operands (11-bit significands, saturating): ~10x closer to
-                          fp32 than bf16; FaceNeRF / NeRF models */
+                          fp32 than bf16 */
   DFN_PREC_BF16X3 = 3  /* tcgen05 split-bf16: A_hi*W_hi + A_lo*W_hi + A_hi*W_lo (fp32-parity mode) */
 };
 
@@ -205,7 +205,7 @@ int dfn_decoder_num_tensors(const dfn_decoder* m);
 int dfn_decoder_load(dfn_decoder* m, const float* const* tensors_host, int n_tensors, void* stream);
 
 /* field: 0 head (signal [dim_signal]), 1 torso (signal [dim_et_embed]); z_shape, z_app [z_dim];
- * precision: DFN_PREC_BF16 or DFN_PREC_BF16X3. */
+ * precision: DFN_PREC_BF16, DFN_PREC_FP16 or DFN_PREC_BF16X3. */
 int64_t dfn_decoder_query_workspace_bytes(const dfn_decoder* m, int64_t R, int S);
 int dfn_decoder_query(const dfn_decoder* m, int field, int64_t R, int S, const float* rays_o, const float* rays_d,
                       const float* z_vals, const float* z_shape, const float* z_app, const float* signal, float* raw,

@@ -119,6 +119,11 @@ def test_render_head_torso_fused_golden(dfn, golden):
     print('fused head+torso bf16  vs reference: rgb_head %.2e rgb_person %.2e'
           % (maxerr(rh16, g['rgb_head']), maxerr(rp16, g['rgb_person'])))
     assert maxerr(rh16, g['rgb_head']) < 0.1 and maxerr(rp16, g['rgb_person']) < 0.1
+    rhf, rpf = dfn.render_head_torso(*args, precision=dfn.PREC_FP16)
+    print('fused head+torso fp16  vs reference: rgb_head %.2e rgb_person %.2e'
+          % (maxerr(rhf, g['rgb_head']), maxerr(rpf, g['rgb_person'])))
+    # fp16 operands: several times closer to the reference than bf16 on the rendered pixels
+    assert maxerr(rpf, g['rgb_person']) < 0.5 * maxerr(rp16, g['rgb_person']) and maxerr(rpf, g['rgb_person']) < 5e-4
 
 
 def test_head_torso_full_frame_properties(dfn):
