@@ -240,7 +240,7 @@ static void free_field(DecField& F) {
   F.bias = F.fold_w = nullptr;
 }
 
-// Layers shared by both fields from blocks[0] on.  `in_blocks`: staged blocks the field's point input occupies
+// Layers shared by both fields from fc_in on.  The field's point input occupies the staged blocks
 // (head: PE; torso: PE', signal').  lat offsets: z_shape at zs0, z_app at za0 inside the latent vector.
 static void build_trunk(Builder& B, const std::vector<Lin>& T, const dfn_decoder_desc& d, bool torso, int zs0, int za0) {
   const int H = d.hidden, de = 6 * d.n_freq;
