@@ -190,15 +190,23 @@ class Decoder(nn.Module):
         return raw[..., :3], raw[..., 3]
 
     @torch.no_grad()
-    def forward(self, p_in, ray_d, z_shape=None, z_app=None, signal=None, head_or_torso=None):
+    def forward(self, p_in, ray_d, z_shape=None, z_app=None, signal=None, head_or_torso=None, precision=_lib.PREC_FP32):
         """p_in, ray_d [1,P,3]; z_shape, z_app [1,z_dim]; signal [1,dim_signal] (head; a [signal, None] list as the
-        reference passes is accepted) or [1,dim_et_embed] (torso) -> (feat [1,P,3], sigma [1,P])."""
+        reference passes is accepted) or [1,dim_et_embed] (torso) -> (feat [1,P,3], sigma [1,P]).
+        precision PREC_FP32 (default): the fp32 FFMA building blocks; PREC_BF16 / PREC_FP16 / PREC_BF16X3: the fused tcgen05
+        kernel on the explicit points (every point is a one-sample ray: origin p, depth 0, its own view direction)."""
         if head_or_torso not in ('head', 'torso'):
             raise Exception('Do not give head or torso!!')
         if isinstance(signal, (list, tuple)):
             signal = signal[0]
         if z_shape is None or z_app is None or signal is None:
             raise DfnError('Decoder.forward: z_shape, z_app and signal are required (as in MAIN:666,675)')
+        if precision != _lib.PREC_FP32:
+            pts = p_in.reshape(-1, 3)
+            n = pts.shape[0]
+            feat, sigma = self.query_rays(pts, ray_d.reshape(-1, 3), torch.zeros((n, 1), dtype=torch.float32, device=pts.device),
+                                          z_shape, z_app, signal, head_or_torso, precision=precision)
+            return feat.reshape(1, n, 3), sigma.reshape(1, n)
         p_in, _ = dev(p_in.reshape(-1, 3), 'p_in')
         ray_d, _ = dev(ray_d.reshape(-1, 3), 'ray_d')
         z_shape, _ = dev(z_shape.reshape(1, -1), 'z_shape')

@@ -104,6 +104,20 @@ def test_decoder_query_matches_fp32_blocks_at_scale(dfn):
         assert maxerr(f, f32.reshape(R, S, 3)) < 1e-4 and maxerr(wa, wb) < 1e-4, which
 
 
+def test_decoder_forward_explicit_points_on_tensor_cores(dfn, golden):
+    """The reference's own call, decoder(p_in, ray_d, z_shape, z_app, signal, 'head'|'torso') on explicit points with
+    per-point directions (MAIN:666, MAIN:675), through the fused kernel: golden vectors of the reference."""
+    g = golden('decoder')
+    dec = make_decoder(dfn, g['seed'])
+    zs, za = g['z_shape'].to(DEV), g['z_app'].to(DEV)
+    for prec, tf, ts in ((dfn.PREC_BF16X3, 1e-5, 1e-3), (dfn.PREC_FP16, 1e-4, 0.1)):
+        fh, sh = dec(g['p'].to(DEV), g['ray_d'].to(DEV), zs[:, 0], za[:, 0], [g['signal'].to(DEV), None], 'head', precision=prec)
+        ft, st = dec(g['p'].to(DEV), g['ray_d'].to(DEV), zs[:, 1], za[:, 1], g['signal_torso'].to(DEV), 'torso', precision=prec)
+        assert fh.shape == (1, 40, 3) and sh.shape == (1, 40)
+        assert maxerr(fh, g['feat_head']) < tf and maxerr(ft, g['feat_torso']) < tf
+        assert maxerr(sh, g['sigma_head']) < ts and maxerr(st, g['sigma_torso']) < ts
+
+
 def test_render_head_torso_fused_golden(dfn, golden):
     """The whole live chunk through dfn_render_head_torso (bf16x3) against the reference's own output."""
     g = golden('head_torso')
