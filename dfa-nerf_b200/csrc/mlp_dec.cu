@@ -5,7 +5,9 @@
 // What the programs fold away (all exact in real arithmetic; products formed on the host in fp64):
 //   * per-frame inputs -- the head's audio/expression signal (DEC:293-295), z_shape (fc_z, fc_z_skips) and z_app
 //     (fc_z_view) -- become fp32 bias terms (fold_kernel);
-//   * fc_view(PE(ray_d / |ray_d|)) (DEC:337-339) is constant along a ray: a per-ray bias (dec_view_bias_kernel);
+//   * fc_view(PE(ray_d / |ray_d|)) (DEC:337-339) is constant along a ray, but stays a K-block of the view layer's MMA
+//     (staged block TC_KB_DIR): a per-ray bias row read in that layer's epilogue measured 2.5x the cost of any other
+//     epilogue (global broadcast loads), one extra K-block is 4 of ~180 MMA instructions per tile;
 //   * the additive skips (DEC:317-325, DEC:118-121) are applied AFTER the relu and feed a linear layer, so
 //     blocks[4](relu + skip(p)) = blocks[4](relu) + (W4 Wskip) p + W4 b_skip: the skip becomes extra input K-blocks of
 //     blocks[4] with composed weights, exactly the [input | h] form the FaceNeRF skip layer already has;
@@ -49,7 +51,6 @@ struct dfn_decoder {
   dfn_decoder_desc desc;
   bool loaded = false;
   dfn::DecField f[2];        // 0 head, 1 torso
-  float* view_w = nullptr;   // fc_view.weight [hidden][6*n_freq_views]
 };
 
 namespace dfn {
@@ -86,48 +87,6 @@ __global__ void dec_fold_kernel(int n_layers, int dimL, const float* __restrict_
     v += acc;
   }
   bias_out[l * TC_BIAS_STRIDE + n] = v;
-}
-
-// out[r][n] = bias_row[n] + sum_j fc_view.W[n][j] * PE(ray_d_r / |ray_d_r|)[j]  (DEC:337-339; PE of DEC:257-275 with
-// n_freq_views frequencies: d/2, then [sin(2^k pi d) | cos(2^k pi d)]_k).  A block walks rays eight at a time; thread n
-// owns output n of each.
-static constexpr int DVB_RAYS = 8;
-__global__ void dec_view_bias_kernel(int64_t R, int Hd, int Lv, const float* __restrict__ rays_d,
-                                     const float* __restrict__ vw, const float* __restrict__ bias_row,
-                                     float* __restrict__ out) {
-  extern __shared__ float sm[];
-  const int ncol = 6 * Lv;
-  float* w_s = sm;                      // [Hd][ncol + 1]
-  float* pe = sm + Hd * (ncol + 1);     // [DVB_RAYS][ncol]
-  for (int i = threadIdx.x; i < Hd * ncol; i += blockDim.x) w_s[(i / ncol) * (ncol + 1) + (i % ncol)] = vw[i];
-  const float bn = (int)threadIdx.x < Hd ? bias_row[threadIdx.x] : 0.f;
-  for (int64_t r0 = (int64_t)blockIdx.x * DVB_RAYS; r0 < R; r0 += (int64_t)gridDim.x * DVB_RAYS) {
-    __syncthreads();
-    for (int i = threadIdx.x; i < DVB_RAYS * ncol; i += blockDim.x) {
-      const int q = i / ncol, j = i % ncol, k = j / 6, c = j % 6;
-      const int64_t r = r0 + q < R ? r0 + q : R - 1;
-      const float a0 = rays_d[r * 3], a1 = rays_d[r * 3 + 1], a2 = rays_d[r * 3 + 2];
-      const float nrm = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(a0, a0), __fmul_rn(a1, a1)), __fmul_rn(a2, a2)));
-      const float xv = __fdiv_rn(rays_d[r * 3 + (c % 3)], nrm);
-      const float a = __fmul_rn(__fmul_rn(pow2i(k), 3.14159274101257324f), __fmul_rn(xv, 0.5f));
-      pe[i] = c < 3 ? sinf(a) : cosf(a);
-    }
-    __syncthreads();
-    if ((int)threadIdx.x < Hd) {
-      float acc[DVB_RAYS];
-#pragma unroll
-      for (int q = 0; q < DVB_RAYS; ++q) acc[q] = 0.f;
-      const float* w = w_s + threadIdx.x * (ncol + 1);
-      for (int j = 0; j < ncol; ++j) {
-        const float wj = w[j];
-#pragma unroll
-        for (int q = 0; q < DVB_RAYS; ++q) acc[q] = fmaf(wj, pe[q * ncol + j], acc[q]);
-      }
-#pragma unroll
-      for (int q = 0; q < DVB_RAYS; ++q)
-        if (r0 + q < R) out[(r0 + q) * Hd + threadIdx.x] = bn + acc[q];
-    }
-  }
 }
 
 // ------------------------------------------------------------------------------- host: programs
@@ -318,7 +277,12 @@ static void build_trunk(Builder& B, const std::vector<Lin>& T, const dfn_decoder
     const Lin& fv = T[T_FEATVIEW];
     const Lin& zv = T[T_FCZVIEW];
     const Lin& vw = T[T_FCVIEW];
-    l = B.layer(H, TC_EPI_VIEW0, 0, {0, 1, 2, 3}, [&](int n, int kbi, int k) { return fv.W(n, kbi * 64 + k); });
+    const int dv = 6 * d.n_freq_views;
+    // the view-direction encoding is a staged input block of this layer (TC_KB_DIR), fc_view its weights
+    l = B.layer(H, TC_EPI_RELU, 0, {TC_KB_DIR, 0, 1, 2, 3}, [&](int n, int kbi, int k) {
+      if (kbi == 0) return k < dv ? vw.W(n, k) : 0.f;
+      return fv.W(n, (kbi - 1) * 64 + k);
+    });
     float* fw = B.fold(l);
     for (int n = 0; n < H; ++n) {
       B.b(l, n) = fv.b[n] + zv.b[n] + vw.b[n];
@@ -440,7 +404,9 @@ static std::vector<Lin> tensor_table(const dfn_decoder_desc& d, const float* con
 }
 
 static int64_t dec_workspace_bytes(const dfn_decoder* m, int64_t R) {
-  return align256((int64_t)TC_MAX_LAYERS * TC_BIAS_STRIDE * 4) + align256(R * m->desc.hidden * 4) + align256(pp_dec_scratch_bytes());
+  (void)m;
+  (void)R;
+  return align256((int64_t)TC_MAX_LAYERS * TC_BIAS_STRIDE * 4) + align256(pp_dec_scratch_bytes());
 }
 
 static int dec_query(const dfn_decoder* m, int field, int64_t R, int S, const float* rays_o, const float* rays_d,
@@ -463,8 +429,7 @@ static int dec_query(const dfn_decoder* m, int field, int64_t R, int S, const fl
   const DecField& F = m->f[field];
   const dfn_decoder_desc& d = m->desc;
   float* bias_ws = reinterpret_cast<float*>(workspace);
-  float* vbias_ws = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + align256((int64_t)TC_MAX_LAYERS * TC_BIAS_STRIDE * 4));
-  void* scratch = reinterpret_cast<char*>(vbias_ws) + align256(R * (int64_t)d.hidden * 4);
+  void* scratch = reinterpret_cast<char*>(workspace) + align256((int64_t)TC_MAX_LAYERS * TC_BIAS_STRIDE * 4);
 
   FoldArgs fa;
   memset(&fa, 0, sizeof(fa));
@@ -477,17 +442,8 @@ static int dec_query(const dfn_decoder* m, int field, int64_t R, int S, const fl
   fa.lat[2] = z_app;
   dec_fold_kernel<<<F.prog.n_layers, TC_BIAS_STRIDE, 0, st>>>(F.prog.n_layers, F.dimL, F.bias, F.fold_w, fa, bias_ws);
   DFN_LAUNCH_CHECK();
-  {
-    int64_t blocks = (R + DVB_RAYS - 1) / DVB_RAYS;
-    if (blocks > (int64_t)num_sms() * 8) blocks = (int64_t)num_sms() * 8;
-    const int ncol = 6 * d.n_freq_views;
-    const size_t sm = ((size_t)d.hidden * (ncol + 1) + DVB_RAYS * ncol) * sizeof(float);
-    dec_view_bias_kernel<<<(int)blocks, 256, sm, st>>>(R, d.hidden, d.n_freq_views, rays_d, m->view_w,
-                                                       bias_ws + (size_t)F.view_layer * TC_BIAS_STRIDE, vbias_ws);
-    DFN_LAUNCH_CHECK();
-  }
   const bool prof = profile_begin(st, F.macs_pt * (double)R * S);
-  int rc = pp_launch_prog(F.prog, F.woff32, precision == DFN_PREC_FP16 ? F.w_h16 : F.w_hi, F.w_lo, true, d.n_freq, d.hidden, bias_ws, vbias_ws, scratch, R, S, rays_o,
+  int rc = pp_launch_prog(F.prog, F.woff32, precision == DFN_PREC_FP16 ? F.w_h16 : F.w_hi, F.w_lo, true, d.n_freq, d.n_freq_views, d.hidden, bias_ws, nullptr, scratch, R, S, rays_o,
                           rays_d, z_vals, raw, precision, st);
   if (prof) profile_end(st);
   if (rc) return rc;
@@ -522,7 +478,6 @@ extern "C" void dfn_decoder_destroy(dfn_decoder* m) {
   if (!m) return;
   free_field(m->f[0]);
   free_field(m->f[1]);
-  cudaFree(m->view_w);
   delete m;
 }
 
@@ -534,13 +489,11 @@ extern "C" int dfn_decoder_load(dfn_decoder* m, const float* const* t, int n_ten
   for (int i = 0; i < n_tensors; ++i) DFN_CHECK_ARG(t[i] != nullptr, "dfn_decoder_load: tensor %d is null", i);
   cudaStream_t st = (cudaStream_t)stream;
   const dfn_decoder_desc& d = m->desc;
-  const int H = d.hidden, dv = 6 * d.n_freq_views, dt = d.dim_et_embed;
+  const int dt = d.dim_et_embed;
   const std::vector<Lin> T = tensor_table(d, t);
 
   free_field(m->f[0]);
   free_field(m->f[1]);
-  cudaFree(m->view_w);
-  m->view_w = nullptr;
   m->loaded = false;
   {
     Builder B(&m->f[0], d.dim_signal + 2 * d.z_dim);
@@ -555,9 +508,6 @@ extern "C" int dfn_decoder_load(dfn_decoder* m, const float* const* t, int n_ten
     int rc = B.upload(st);
     if (rc) return rc;
   }
-  DFN_CUDA(cudaMalloc(&m->view_w, (size_t)H * dv * 4));
-  DFN_CUDA(cudaMemcpyAsync(m->view_w, T[T_FCVIEW].w, (size_t)H * dv * 4, cudaMemcpyHostToDevice, st));
-  DFN_CUDA(cudaStreamSynchronize(st));
   m->loaded = true;
   return 0;
 }

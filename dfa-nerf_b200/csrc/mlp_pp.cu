@@ -67,6 +67,7 @@ struct Params {
   int n_tiles;
   int n_layers;
   int multires;
+  int multires_views;      // Decoder: frequencies of the view-direction encoding (staged block TC_KB_DIR)
   int view_w;
   TcLayer layers[TC_MAX_LAYERS];  // woff: offsets into the K=32 / 64-byte-swizzle blobs
 };
@@ -140,7 +141,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1) mlp_pp_kerne
   constexpr int NSLOT = X3 ? 1 : 2;
   constexpr int NPART = X3 ? 2 : 1;
   constexpr int ROWB = X3 ? 256 : 128;  // scratch bytes per row of a staged block
-  constexpr int NBLK = DEC ? 2 : 1;     // staged blocks per tile
+  constexpr int NBLK = DEC ? 3 : 1;     // staged blocks per tile (Decoder: PE | deformed signal | view-direction PE)
   // bf16x3 (one tile): all eight epilogue warps share the tile's columns.  bf16 (two tiles): four warps per tile,
   // the two groups run concurrently (a cooperative, serialised epilogue of two tiles measured slower).
   constexpr bool COOP = X3;
@@ -420,6 +421,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1) mlp_pp_kerne
         const bool tr = P.trace != nullptr && blockIdx.x == 0 && et == 0 && j < P.trace_tiles;
         long long t_e0 = 0, t_e1 = 0;
         if (tr) t_e0 = clock64();
+        if (L.epi == TC_EPI_VIEW0) prefetch_row_l1(P.view_bias + ray * P.view_w, P.view_w);   // hidden behind the wait
         mbar_wait(bar_acc + 8 * s, acc_par);
         acc_par ^= 1u;
         tcgen05_fence_after();
@@ -630,6 +632,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1) mlp_pp_kerne
           long long t_e0 = 0, t_e1 = 0;
           if (tr) t_e0 = clock64();
 
+          if (L.epi == TC_EPI_VIEW0) prefetch_row_l1(P.view_bias + ray * P.view_w, P.view_w);   // hidden behind the wait
           mbar_wait(bar_acc + 8 * s, acc_par[s]);
           acc_par[s] ^= 1u;
           tcgen05_fence_after();
@@ -848,6 +851,55 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1) mlp_pp_kerne
             dst[(8 + ch) * TILE_M] = l;
           }
         }
+        if (DEC) {
+          // view-direction encoding (DEC:337-338): d / |d|, halved, [sin(2^k pi d) | cos(2^k pi d)]_k -- constant along a
+          // ray, but a K-block of the view layer's MMA is cheaper than a per-ray bias row read per eight columns in its
+          // epilogue (global broadcast loads made that epilogue 2.5x longer than any other)
+          const float dx = P.rays_d[ray * 3], dy = P.rays_d[ray * 3 + 1], dz = P.rays_d[ray * 3 + 2];
+          const float nrm = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)));
+          const float dn[3] = {__fdiv_rn(dx, nrm), __fdiv_rn(dy, nrm), __fdiv_rn(dz, nrm)};
+#pragma unroll
+          for (int i = 0; i < 64; ++i) pe[i] = 0.f;
+#pragma unroll
+          for (int k = 0; k < 10; ++k) {
+#pragma unroll
+            for (int cidx = 0; cidx < 3; ++cidx) {
+              if (k < P.multires_views) {
+                const float t = __fmul_rn(__fmul_rn(pow2i(k), 3.14159274101257324f), __fmul_rn(dn[cidx], 0.5f));
+                const float n = rintf(t * 0.15915494309189535f);
+                float r = fmaf(-n, 6.28125f, t);
+                r = fmaf(-n, 1.9353071795864769e-3f, r);
+                pe[6 * k + cidx] = __sinf(r);
+                pe[6 * k + 3 + cidx] = __cosf(r);
+              }
+            }
+          }
+          uint4* dd = reinterpret_cast<uint4*>(scr(buf, s, 2)) + row;
+#pragma unroll
+          for (int ch = 0; ch < 8; ++ch) {
+            uint4 h;
+            if (F16) {
+              h.x = pack_f16(pe[ch * 8 + 0], pe[ch * 8 + 1]);
+              h.y = pack_f16(pe[ch * 8 + 2], pe[ch * 8 + 3]);
+              h.z = pack_f16(pe[ch * 8 + 4], pe[ch * 8 + 5]);
+              h.w = pack_f16(pe[ch * 8 + 6], pe[ch * 8 + 7]);
+            } else {
+              h.x = pack_bf16(pe[ch * 8 + 0], pe[ch * 8 + 1]);
+              h.y = pack_bf16(pe[ch * 8 + 2], pe[ch * 8 + 3]);
+              h.z = pack_bf16(pe[ch * 8 + 4], pe[ch * 8 + 5]);
+              h.w = pack_bf16(pe[ch * 8 + 6], pe[ch * 8 + 7]);
+            }
+            dd[ch * TILE_M] = h;
+            if (X3) {
+              uint4 l;
+              l.x = pack_bf16(pe[ch * 8 + 0] - bf16_lo_f(h.x), pe[ch * 8 + 1] - bf16_hi_f(h.x));
+              l.y = pack_bf16(pe[ch * 8 + 2] - bf16_lo_f(h.y), pe[ch * 8 + 3] - bf16_hi_f(h.y));
+              l.z = pack_bf16(pe[ch * 8 + 4] - bf16_lo_f(h.z), pe[ch * 8 + 5] - bf16_hi_f(h.z));
+              l.w = pack_bf16(pe[ch * 8 + 6] - bf16_lo_f(h.w), pe[ch * 8 + 7] - bf16_hi_f(h.w));
+              dd[(8 + ch) * TILE_M] = l;
+            }
+          }
+        }
       }
       mbar_arrive(bar_pe_ready + 8 * buf);
     }
@@ -863,7 +915,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1) mlp_pp_kerne
 }  // namespace pp
 
 int64_t pp_scratch_bytes() { return (int64_t)(num_sms() + 1) * 2 * 2 * tc::TILE_M * 256; }
-int64_t pp_dec_scratch_bytes() { return 2 * pp_scratch_bytes(); }  // two staged blocks per tile
+int64_t pp_dec_scratch_bytes() { return 3 * pp_scratch_bytes(); }  // three staged blocks per tile
 
 template <bool X3, bool DEC, bool F16 = false>
 static int pp_launch_t(const pp::Params& P, int grid, cudaStream_t st) {
@@ -879,7 +931,7 @@ static int pp_launch_t(const pp::Params& P, int grid, cudaStream_t st) {
 // prog: layer program (woff32: per-layer offsets into the K=32 stage blobs w_hi / w_lo); decoder: Decoder programs
 // (DEC kernel instantiation, 256-wide per-ray view bias, PE of DEC:257-275 with n_freq = multires).
 int pp_launch_prog(const TcProgram& prog, const uint32_t* woff32, const uint8_t* w_hi, const uint8_t* w_lo, bool decoder,
-                   int multires, int view_w, const float* bias_ws, const float* vbias_ws, void* scratch, int64_t R, int S,
+                   int multires, int multires_views, int view_w, const float* bias_ws, const float* vbias_ws, void* scratch, int64_t R, int S,
                    const float* rays_o, const float* rays_d, const float* z_vals, float* raw, int precision,
                    cudaStream_t st) {
   pp::Params P;
@@ -899,6 +951,7 @@ int pp_launch_prog(const TcProgram& prog, const uint32_t* woff32, const uint8_t*
   P.n_tiles = (int)((P.n_points + tc::TILE_M - 1) / tc::TILE_M);
   P.n_layers = prog.n_layers;
   P.multires = multires;
+  P.multires_views = multires_views;
   P.view_w = view_w;
   for (int i = 0; i < prog.n_layers; ++i) {
     P.layers[i] = prog.layers[i];
@@ -922,7 +975,8 @@ int pp_launch_prog(const TcProgram& prog, const uint32_t* woff32, const uint8_t*
 int pp_launch(const dfn_model* m, const float* bias_ws, const float* vbias_ws, void* scratch, int64_t R, int S,
               const float* rays_o, const float* rays_d, const float* z_vals, float* raw, int precision,
               cudaStream_t st) {
-  return pp_launch_prog(m->prog, m->tc32_woff, m->tc_hi, m->tc_lo, false, m->desc.multires, m->desc.W / 2, bias_ws, vbias_ws,
+  return pp_launch_prog(m->prog, m->tc32_woff, m->tc_hi, m->tc_lo, false, m->desc.multires, m->desc.multires_views, m->desc.W / 2,
+                        bias_ws, vbias_ws,
                         scratch, R, S, rays_o, rays_d, z_vals, raw, precision, st);
 }
 

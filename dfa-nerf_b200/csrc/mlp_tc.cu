@@ -324,6 +324,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(X3 ? 256 : 384, 1)
         const bool tr = P.trace != nullptr && blockIdx.x == 0 && tid_s == 0 && (i / NSLOT) < P.trace_tiles;
         long long t_e0 = 0, t_e1 = 0;
         if (tr) t_e0 = clock64();
+        if (L.epi == TC_EPI_VIEW0) prefetch_row_l1(P.view_bias + ray * P.view_w, P.view_w);   // hidden behind the wait
         mbar_wait(bar_acc + 8 * s, acc_par);
         acc_par ^= 1u;
         tcgen05_fence_after();

@@ -19,8 +19,9 @@ struct Fp32Layer {
 // encoding of xyz (63 columns + one zero column).  Block ids >= TC_KB_PE are "staged" inputs: in mlp_pp.cu
 // they live in an L2-resident scratch and pass through a weight-ring entry right before the layer that
 // consumes them (TC_KB_PE: the positional encoding; TC_KB_IN1: the deformed per-sample signal of the torso
-// field, DEC:297-299).  A layer has at most one staged input block.
-enum { TC_KB_H0 = 0, TC_KB_PE = 4, TC_KB_IN1 = 5, TC_KB_PER_TILE = 5 };
+// field, DEC:297-299; TC_KB_DIR: the Decoder's view-direction encoding, DEC:337-338).  A layer has at most one staged
+// input block.
+enum { TC_KB_H0 = 0, TC_KB_PE = 4, TC_KB_IN1 = 5, TC_KB_DIR = 6, TC_KB_PER_TILE = 5 };
 enum {
   TC_EPI_RELU = 0,   // + bias, relu -> hidden blocks H0..
   TC_EPI_VIEW0 = 1,  // + per-ray bias, relu -> hidden blocks (FaceNeRF/NeRF: density rides as column view_w)
@@ -93,7 +94,7 @@ void tc_set_impl(int impl);  // 2: ping-pong + cooperative epilogue (mlp_pp.cu, 
 int64_t pp_scratch_bytes();
 int64_t pp_dec_scratch_bytes();
 int pp_launch_prog(const TcProgram& prog, const uint32_t* woff32, const uint8_t* w_hi, const uint8_t* w_lo, bool decoder,
-                   int multires, int view_w, const float* bias_ws, const float* vbias_ws, void* scratch, int64_t R, int S,
+                   int multires, int multires_views, int view_w, const float* bias_ws, const float* vbias_ws, void* scratch, int64_t R, int S,
                    const float* rays_o, const float* rays_d, const float* z_vals, float* raw, int precision,
                    cudaStream_t st);
 int pp_launch(const dfn_model* m, const float* bias_ws, const float* vbias_ws, void* scratch, int64_t R, int S,

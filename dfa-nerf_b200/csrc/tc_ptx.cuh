@@ -346,6 +346,12 @@ __device__ __forceinline__ void fence_proxy_async_all() {
   asm volatile("fence.proxy.async;" ::: "memory");
 }
 
+// Pull `n_floats` consecutive floats (a per-ray bias row, read once per tile and otherwise a DRAM round trip per eight
+// columns in the middle of the epilogue) into L1 ahead of use.
+__device__ __forceinline__ void prefetch_row_l1(const float* p, int n_floats) {
+  for (int i = 0; i < n_floats; i += 32) asm volatile("prefetch.global.L1 [%0];" ::"l"(p + i));
+}
+
 // byte offset of 16-byte chunk `chunk` (0..7) of row `row` inside a 128-byte-swizzled K-block
 __device__ __forceinline__ uint32_t swz(uint32_t row, uint32_t chunk) {
   return row * 128u + ((chunk ^ (row & 7u)) << 4);

@@ -178,7 +178,7 @@ int dfn_query_points(const dfn_model* m, int64_t R, int S, const float* rays_o, 
 /* ---- a5''  Decoder + DeformationField_ori on the tensor cores  (DEC:77-134, DEC:137-349) ---------------
  * The reference's LIVE model (MAIN:518: Decoder(z_dim=256, hidden_size=256, dim_signal=96, use_deformation_field)).
  * dfn_decoder_query is the fused network query of one field for pts = rays_o + rays_d*z: positional encoding of
- * DEC:257-275, per-frame latents (signal, z_shape, z_app) and the per-ray view term folded into biases, the torso's
+ * DEC:257-275, per-frame latents (signal, z_shape, z_app) folded into biases, the view-direction encoding as an input block, the torso's
  * deformation field in front of its trunk; raw [R,S,4] = (feat after the sigmoid of DEC:346-347, sigma before the relu
  * of MAIN:688).  rays_d is NOT normalised by the caller (DEC:337 normalises the view direction itself). */
 typedef struct dfn_decoder dfn_decoder;
@@ -215,7 +215,7 @@ double dfn_decoder_macs_per_sample(const dfn_decoder* m, int field);
 
 /* Host-only introspection (no CUDA calls; used by the CPU tests): the layer program dfn_decoder_load compiles for one
  * field.  layers[l]: output columns n, input K-blocks kb[0..nkb) (0..3 hidden blocks, 4 = positional encoding / deformed
- * encoding, 5 = deformed signal), epilogue (0 relu, 1 per-ray-bias relu, 2 rgb+sigmoid, 3 sigma, 4 continue, 5 write
+ * encoding, 5 = deformed signal, 6 = view-direction encoding), epilogue (0 relu, 1 per-ray-bias relu, 2 rgb+sigmoid, 3 sigma, 4 continue, 5 write
  * staged blocks) and flags (1 = accumulates onto the previous layer).  weights: dense fp32 [max_layers][256][6*64]
  * (row n, input block slot i, position k), bias [max_layers][256], fold_w [n_fold][dimL][256] with
  * bias[fold_layer[i]][n] += sum_j fold_w[i][j][n] * latent[j], latent = [signal | z_shape | z_app].

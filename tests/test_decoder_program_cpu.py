@@ -11,7 +11,7 @@ from oracle import nerf_oracle as O
 from oracle import synth
 
 EPI_RELU, EPI_VIEW0, EPI_RGB, EPI_SIGMA, EPI_CONT, EPI_STAGE = range(6)
-KB_PE, KB_IN1 = 4, 5
+KB_PE, KB_IN1, KB_DIR = 4, 5, 6
 ORDER = (['deform_net.blocks_embed.%d' % i for i in range(5)] + ['deform_net.out_embed'] +
          ['deform_net.blocks_signal.%d' % i for i in range(5)] + ['deform_net.out_signal', 'deform_net.fc_embed_skips.0',
                                                                   'deform_net.fc_signal_skips.0', 'fc_in', 'fc_in_torso', 'fc_z'] +
@@ -42,12 +42,13 @@ def dump_program(sd, field):
     return [layers[i] for i in range(n_layers.value)], weights, bias, folds, dl, view_layer.value
 
 
-def run_program(prog, pe, latent, view_term):
-    """pe [P,60] fp64, latent [dimL], view_term [P,256] = fc_view(PE(dir)) without bias -> (feat [P,3], sigma [P])."""
+def run_program(prog, pe, latent, pe_dir):
+    """pe [P,60] fp64, latent [dimL], pe_dir [P,24] = PE(dir/|dir|) (staged block TC_KB_DIR) -> (feat [P,3], sigma [P])."""
     layers, weights, bias, folds, dimL, view_layer = prog
     P = pe.shape[0]
-    blocks = {k: np.zeros((P, 64)) for k in range(6)}
+    blocks = {k: np.zeros((P, 64)) for k in range(7)}
     blocks[KB_PE][:, :60] = pe
+    blocks[KB_DIR][:, :pe_dir.shape[1]] = pe_dir
     acc, sigma, feat = None, None, None
     for l, L in enumerate(layers):
         n, kbs = L.n, [L.kb[i] for i in range(L.nkb)]
@@ -63,8 +64,7 @@ def run_program(prog, pe, latent, view_term):
         if L.epi == EPI_RELU:
             h = np.maximum(acc + b, 0.)
         elif L.epi == EPI_VIEW0:
-            assert l == view_layer
-            h = np.maximum(acc + b + view_term, 0.)
+            raise AssertionError('the Decoder programs carry the view term as a K-block, not as a per-ray bias')
         elif L.epi == EPI_SIGMA:
             sigma = acc[:, 0] + b[0]
             continue
@@ -92,14 +92,15 @@ def test_decoder_layer_programs_compute_the_reference_forward():
     with torch.no_grad():
         pe = O.decoder_transform_points(p.double(), 10)[0].numpy()
         d = rd.double() / torch.norm(rd.double(), dim=-1, keepdim=True)
-        view_term = (O.decoder_transform_points(d, 4)[0] @ sd64['fc_view.weight'].t()).numpy()
+        pe_dir = O.decoder_transform_points(d, 4)[0].numpy()
         for field, which in ((0, 'head'), (1, 'torso')):
             prog = dump_program(sd, field)
             n_layers = len(prog[0])
             assert n_layers == (11 if field == 0 else 19)
             latent = torch.cat([sig[field].reshape(-1), zs.reshape(-1), za.reshape(-1)]).double().numpy()
             assert prog[4] == latent.shape[0]
-            feat, sigma = run_program(prog, pe, latent, view_term)
+            assert prog[0][prog[5]].kb[0] == KB_DIR          # the view layer stages the direction encoding
+            feat, sigma = run_program(prog, pe, latent, pe_dir)
             rf, rs = O.decoder_forward(sd64, p.double(), rd.double(), zs.double(), za.double(), sig[field].double(), which)
             ef = np.abs(feat - rf[0].numpy()).max()
             es = np.abs(sigma - rs[0].numpy()).max() / np.abs(rs[0].numpy()).max()
