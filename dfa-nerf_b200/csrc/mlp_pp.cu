@@ -33,6 +33,7 @@
 #include "model.h"
 #include "tc_ptx.cuh"
 #include "tc_epi.cuh"
+#include "pe.cuh"
 
 namespace dfn {
 namespace pp {
@@ -775,57 +776,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1) mlp_pp_kerne
         if (pt >= P.n_points) pt = P.n_points - 1;
         const int64_t ray = pt / P.S;
         const float z = P.z_vals[pt];
-        float pe[64];
-        if (!DEC) {
-#pragma unroll
-          for (int cidx = 0; cidx < 3; ++cidx)
-            pe[cidx] = __fadd_rn(P.rays_o[ray * 3 + cidx], __fmul_rn(P.rays_d[ray * 3 + cidx], z));
-#pragma unroll
-          for (int k = 0; k < 10; ++k) {
-#pragma unroll
-            for (int cidx = 0; cidx < 3; ++cidx) {
-              float sv = 0.f, cv = 0.f;
-              if (k < P.multires) {
-                const float t = __fmul_rn(pe[cidx], pow2i(k));
-                const float n = rintf(t * 0.15915494309189535f);
-                float r = fmaf(-n, 6.28125f, t);
-                r = fmaf(-n, 1.9353071795864769e-3f, r);
-                sv = __sinf(r);
-                cv = __cosf(r);
-              }
-              pe[3 + 6 * k + cidx] = sv;
-              pe[6 + 6 * k + cidx] = cv;
-            }
-          }
-          pe[63] = 0.f;
-        } else {
-          // DEC:257-275: p /= 2; [sin(2^k pi p) | cos(2^k pi p)]_k, no identity term.  torch multiplies the fp32 point by
-          // fl32(2^k pi) = 2^k fl32(pi), so the argument is exactly 2^k * fl32(fl32(pi) * p); same reduction as above.
-          float a0[3];
-#pragma unroll
-          for (int cidx = 0; cidx < 3; ++cidx) {
-            const float x = __fadd_rn(P.rays_o[ray * 3 + cidx], __fmul_rn(P.rays_d[ray * 3 + cidx], z));
-            a0[cidx] = __fmul_rn(3.14159274101257324f, __fmul_rn(x, 0.5f));
-          }
-#pragma unroll
-          for (int k = 0; k < 10; ++k) {
-#pragma unroll
-            for (int cidx = 0; cidx < 3; ++cidx) {
-              float sv = 0.f, cv = 0.f;
-              if (k < P.multires) {
-                const float t = __fmul_rn(a0[cidx], pow2i(k));
-                const float n = rintf(t * 0.15915494309189535f);
-                float r = fmaf(-n, 6.28125f, t);
-                r = fmaf(-n, 1.9353071795864769e-3f, r);
-                sv = __sinf(r);
-                cv = __cosf(r);
-              }
-              pe[6 * k + cidx] = sv;
-              pe[6 * k + 3 + cidx] = cv;
-            }
-          }
-          pe[60] = pe[61] = pe[62] = pe[63] = 0.f;
-        }
+        float pe[64], x[3];
+        sample_point(P.rays_o, P.rays_d, ray, z, x);
+        if (!DEC) pe_embedder(x, P.multires, pe);
+        else pe_decoder(x, P.multires, pe);
         uint4* dst = reinterpret_cast<uint4*>(scr(buf, s, 0)) + row;
 #pragma unroll
         for (int ch = 0; ch < 8; ++ch) {
@@ -855,25 +809,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1) mlp_pp_kerne
           // view-direction encoding (DEC:337-338): d / |d|, halved, [sin(2^k pi d) | cos(2^k pi d)]_k -- constant along a
           // ray, but a K-block of the view layer's MMA is cheaper than a per-ray bias row read per eight columns in its
           // epilogue (global broadcast loads made that epilogue 2.5x longer than any other)
-          const float dx = P.rays_d[ray * 3], dy = P.rays_d[ray * 3 + 1], dz = P.rays_d[ray * 3 + 2];
-          const float nrm = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)));
-          const float dn[3] = {__fdiv_rn(dx, nrm), __fdiv_rn(dy, nrm), __fdiv_rn(dz, nrm)};
-#pragma unroll
-          for (int i = 0; i < 64; ++i) pe[i] = 0.f;
-#pragma unroll
-          for (int k = 0; k < 10; ++k) {
-#pragma unroll
-            for (int cidx = 0; cidx < 3; ++cidx) {
-              if (k < P.multires_views) {
-                const float t = __fmul_rn(__fmul_rn(pow2i(k), 3.14159274101257324f), __fmul_rn(dn[cidx], 0.5f));
-                const float n = rintf(t * 0.15915494309189535f);
-                float r = fmaf(-n, 6.28125f, t);
-                r = fmaf(-n, 1.9353071795864769e-3f, r);
-                pe[6 * k + cidx] = __sinf(r);
-                pe[6 * k + 3 + cidx] = __cosf(r);
-              }
-            }
-          }
+          pe_decoder_viewdir(P.rays_d, ray, P.multires_views, pe);
           uint4* dd = reinterpret_cast<uint4*>(scr(buf, s, 2)) + row;
 #pragma unroll
           for (int ch = 0; ch < 8; ++ch) {

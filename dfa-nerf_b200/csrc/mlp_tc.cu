@@ -28,6 +28,7 @@
 #include "tc_ptx.cuh"
 #include "tc_pack.h"
 #include "tc_epi.cuh"
+#include "pe.cuh"
 
 namespace dfn {
 namespace tc {
@@ -277,29 +278,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(X3 ? 256 : 384, 1)
       // and the MUFU sin/cos (abs error 2^-21.4 there): below the bf16 / hi+lo resolution of the MMA operands, and
       // four times shorter than sincosf on the tile's critical path.  Eight 16-byte swizzled stores per row.
       {
-        const float z = P.z_vals[pt];
-        float pe[64];
-#pragma unroll
-        for (int c = 0; c < 3; ++c)
-          pe[c] = __fadd_rn(P.rays_o[ray * 3 + c], __fmul_rn(P.rays_d[ray * 3 + c], z));
-#pragma unroll
-        for (int k = 0; k < 10; ++k) {
-#pragma unroll
-          for (int c = 0; c < 3; ++c) {
-            float sv = 0.f, cv = 0.f;
-            if (k < P.multires) {
-              const float t = __fmul_rn(pe[c], pow2i(k));
-              const float n = rintf(t * 0.15915494309189535f);
-              float r = fmaf(-n, 6.28125f, t);
-              r = fmaf(-n, 1.9353071795864769e-3f, r);
-              sv = __sinf(r);
-              cv = __cosf(r);
-            }
-            pe[3 + 6 * k + c] = sv;
-            pe[6 + 6 * k + c] = cv;
-          }
-        }
-        pe[63] = 0.f;
+        float pe[64], x[3];
+        sample_point(P.rays_o, P.rays_d, ray, P.z_vals[pt], x);
+        pe_embedder(x, P.multires, pe);
         uint8_t* pe_hi = arena_hi + TC_KB_PE * KB_BYTES;
         uint8_t* pe_lo = arena_lo + TC_KB_PE * KB_BYTES;
 #pragma unroll

@@ -35,6 +35,7 @@
 #include "model.h"
 #include "tc_ptx.cuh"
 #include "tc_epi.cuh"
+#include "pe.cuh"
 
 namespace dfn {
 namespace tc2 {
@@ -252,29 +253,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1) mlp_tc2_kern
       bias_s[((j * NL) & 1) * TC_BIAS_STRIDE + et] = P.bias[et];
       // ---- positional encoding (HELP:42-52): warps 4-7 encode slot 0's rows, warps 8-11 slot 1's ----
       if (live[hf]) {
-        const float z = P.z_vals[pt[hf]];
-        float pe[64];
-#pragma unroll
-        for (int cc = 0; cc < 3; ++cc)
-          pe[cc] = __fadd_rn(P.rays_o[ray[hf] * 3 + cc], __fmul_rn(P.rays_d[ray[hf] * 3 + cc], z));
-#pragma unroll
-        for (int k = 0; k < 10; ++k) {
-#pragma unroll
-          for (int cc = 0; cc < 3; ++cc) {
-            float sv = 0.f, cv = 0.f;
-            if (k < P.multires) {
-              const float t = __fmul_rn(pe[cc], pow2i(k));
-              const float n = rintf(t * 0.15915494309189535f);
-              float r = fmaf(-n, 6.28125f, t);
-              r = fmaf(-n, 1.9353071795864769e-3f, r);
-              sv = __sinf(r);
-              cv = __cosf(r);
-            }
-            pe[3 + 6 * k + cc] = sv;
-            pe[6 + 6 * k + cc] = cv;
-          }
-        }
-        pe[63] = 0.f;
+        float pe[64], x[3];
+        sample_point(P.rays_o, P.rays_d, ray[hf], P.z_vals[pt[hf]], x);
+        pe_embedder(x, P.multires, pe);
         uint8_t* pe_hi = smem + (size_t)(hf * TC_KB_PER_TILE + TC_KB_PE) * KB_BYTES;
 #pragma unroll
         for (int ch = 0; ch < 8; ++ch) {

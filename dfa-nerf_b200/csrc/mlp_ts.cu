@@ -25,6 +25,7 @@
 #include "common.cuh"
 #include "model.h"
 #include "tc_ptx.cuh"
+#include "pe.cuh"
 
 namespace dfn {
 namespace ts {
@@ -377,28 +378,9 @@ __global__ void __launch_bounds__(512, 1) mlp_ts_kernel(const __grid_constant__ 
       int64_t pt = (int64_t)tile * TILE_M + row;
       if (pt >= P.n_points) pt = P.n_points - 1;
       const int64_t ray = pt / P.S;
-      const float z = P.z_vals[pt];
-      float pe[64];
-#pragma unroll
-      for (int c = 0; c < 3; ++c) pe[c] = __fadd_rn(P.rays_o[ray * 3 + c], __fmul_rn(P.rays_d[ray * 3 + c], z));
-#pragma unroll
-      for (int k = 0; k < 10; ++k) {   // same evaluation as mlp_tc.cu (exact 2^k scaling, Cody-Waite, MUFU)
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-          float sv = 0.f, cv = 0.f;
-          if (k < P.multires) {
-            const float t = __fmul_rn(pe[c], pow2i(k));
-            const float n = rintf(t * 0.15915494309189535f);
-            float r = fmaf(-n, 6.28125f, t);
-            r = fmaf(-n, 1.9353071795864769e-3f, r);
-            sv = __sinf(r);
-            cv = __cosf(r);
-          }
-          pe[3 + 6 * k + c] = sv;
-          pe[6 + 6 * k + c] = cv;
-        }
-      }
-      pe[63] = 0.f;
+      float pe[64], x[3];   // same evaluation as mlp_tc.cu (pe.cuh)
+      sample_point(P.rays_o, P.rays_d, ray, P.z_vals[pt], x);
+      pe_embedder(x, P.multires, pe);
       uint8_t* pe_hi = smem + C::SMEM_PE + (size_t)(buf * C::PE_PLANES) * PE_BYTES;
       uint8_t* pe_lo = pe_hi + PE_BYTES;
 #pragma unroll
