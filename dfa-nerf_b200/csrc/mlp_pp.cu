@@ -95,6 +95,37 @@ __device__ __forceinline__ uint32_t layer_entries(const TcLayer& L) {
   return (uint32_t)L.nkb * NPART + (layer_has_pe(L) ? 1u : 0u);
 }
 
+// One 64-column row of a staged block -> scratch, bf16 / fp16 (hi [, lo = bf16(v - hi)]) in the [16-byte chunk][row]
+// layout (coalesced for these stores and for the epilogue warps' loads).
+template <bool X3, bool F16>
+__device__ __forceinline__ void scratch_row(uint8_t* blk_base, uint32_t row, const float (&v)[64]) {
+  uint4* dst = reinterpret_cast<uint4*>(blk_base) + row;
+#pragma unroll
+  for (int ch = 0; ch < 8; ++ch) {
+    uint4 h;
+    if (F16) {
+      h.x = pack_f16(v[ch * 8 + 0], v[ch * 8 + 1]);
+      h.y = pack_f16(v[ch * 8 + 2], v[ch * 8 + 3]);
+      h.z = pack_f16(v[ch * 8 + 4], v[ch * 8 + 5]);
+      h.w = pack_f16(v[ch * 8 + 6], v[ch * 8 + 7]);
+    } else {
+      h.x = pack_bf16(v[ch * 8 + 0], v[ch * 8 + 1]);
+      h.y = pack_bf16(v[ch * 8 + 2], v[ch * 8 + 3]);
+      h.z = pack_bf16(v[ch * 8 + 4], v[ch * 8 + 5]);
+      h.w = pack_bf16(v[ch * 8 + 6], v[ch * 8 + 7]);
+    }
+    dst[ch * TILE_M] = h;
+    if (X3) {
+      uint4 l;
+      l.x = pack_bf16(v[ch * 8 + 0] - bf16_lo_f(h.x), v[ch * 8 + 1] - bf16_hi_f(h.x));
+      l.y = pack_bf16(v[ch * 8 + 2] - bf16_lo_f(h.y), v[ch * 8 + 3] - bf16_hi_f(h.y));
+      l.z = pack_bf16(v[ch * 8 + 4] - bf16_lo_f(h.z), v[ch * 8 + 5] - bf16_hi_f(h.z));
+      l.w = pack_bf16(v[ch * 8 + 6] - bf16_lo_f(h.w), v[ch * 8 + 7] - bf16_hi_f(h.w));
+      dst[(8 + ch) * TILE_M] = l;
+    }
+  }
+}
+
 // TC_EPI_STAGE: + bias (no activation), bf16 (hi[/lo]) of one 32-column chunk -> the tile's staged block in the
 // scratch ([16-byte chunk][row] layout, as the PE warps write it).  blk_base = staged block (chunk32 >> 1).
 template <bool X3, bool F16>
@@ -780,61 +811,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1) mlp_pp_kerne
         sample_point(P.rays_o, P.rays_d, ray, z, x);
         if (!DEC) pe_embedder(x, P.multires, pe);
         else pe_decoder(x, P.multires, pe);
-        uint4* dst = reinterpret_cast<uint4*>(scr(buf, s, 0)) + row;
-#pragma unroll
-        for (int ch = 0; ch < 8; ++ch) {
-          uint4 h;
-          if (F16) {
-            h.x = pack_f16(pe[ch * 8 + 0], pe[ch * 8 + 1]);
-            h.y = pack_f16(pe[ch * 8 + 2], pe[ch * 8 + 3]);
-            h.z = pack_f16(pe[ch * 8 + 4], pe[ch * 8 + 5]);
-            h.w = pack_f16(pe[ch * 8 + 6], pe[ch * 8 + 7]);
-          } else {
-            h.x = pack_bf16(pe[ch * 8 + 0], pe[ch * 8 + 1]);
-            h.y = pack_bf16(pe[ch * 8 + 2], pe[ch * 8 + 3]);
-            h.z = pack_bf16(pe[ch * 8 + 4], pe[ch * 8 + 5]);
-            h.w = pack_bf16(pe[ch * 8 + 6], pe[ch * 8 + 7]);
-          }
-          dst[ch * TILE_M] = h;
-          if (X3) {
-            uint4 l;
-            l.x = pack_bf16(pe[ch * 8 + 0] - bf16_lo_f(h.x), pe[ch * 8 + 1] - bf16_hi_f(h.x));
-            l.y = pack_bf16(pe[ch * 8 + 2] - bf16_lo_f(h.y), pe[ch * 8 + 3] - bf16_hi_f(h.y));
-            l.z = pack_bf16(pe[ch * 8 + 4] - bf16_lo_f(h.z), pe[ch * 8 + 5] - bf16_hi_f(h.z));
-            l.w = pack_bf16(pe[ch * 8 + 6] - bf16_lo_f(h.w), pe[ch * 8 + 7] - bf16_hi_f(h.w));
-            dst[(8 + ch) * TILE_M] = l;
-          }
-        }
+        scratch_row<X3, F16>(scr(buf, s, 0), row, pe);
         if (DEC) {
           // view-direction encoding (DEC:337-338): d / |d|, halved, [sin(2^k pi d) | cos(2^k pi d)]_k -- constant along a
           // ray, but a K-block of the view layer's MMA is cheaper than a per-ray bias row read per eight columns in its
           // epilogue (global broadcast loads made that epilogue 2.5x longer than any other)
           pe_decoder_viewdir(P.rays_d, ray, P.multires_views, pe);
-          uint4* dd = reinterpret_cast<uint4*>(scr(buf, s, 2)) + row;
-#pragma unroll
-          for (int ch = 0; ch < 8; ++ch) {
-            uint4 h;
-            if (F16) {
-              h.x = pack_f16(pe[ch * 8 + 0], pe[ch * 8 + 1]);
-              h.y = pack_f16(pe[ch * 8 + 2], pe[ch * 8 + 3]);
-              h.z = pack_f16(pe[ch * 8 + 4], pe[ch * 8 + 5]);
-              h.w = pack_f16(pe[ch * 8 + 6], pe[ch * 8 + 7]);
-            } else {
-              h.x = pack_bf16(pe[ch * 8 + 0], pe[ch * 8 + 1]);
-              h.y = pack_bf16(pe[ch * 8 + 2], pe[ch * 8 + 3]);
-              h.z = pack_bf16(pe[ch * 8 + 4], pe[ch * 8 + 5]);
-              h.w = pack_bf16(pe[ch * 8 + 6], pe[ch * 8 + 7]);
-            }
-            dd[ch * TILE_M] = h;
-            if (X3) {
-              uint4 l;
-              l.x = pack_bf16(pe[ch * 8 + 0] - bf16_lo_f(h.x), pe[ch * 8 + 1] - bf16_hi_f(h.x));
-              l.y = pack_bf16(pe[ch * 8 + 2] - bf16_lo_f(h.y), pe[ch * 8 + 3] - bf16_hi_f(h.y));
-              l.z = pack_bf16(pe[ch * 8 + 4] - bf16_lo_f(h.z), pe[ch * 8 + 5] - bf16_hi_f(h.z));
-              l.w = pack_bf16(pe[ch * 8 + 6] - bf16_lo_f(h.w), pe[ch * 8 + 7] - bf16_hi_f(h.w));
-              dd[(8 + ch) * TILE_M] = l;
-            }
-          }
+          scratch_row<X3, F16>(scr(buf, s, 2), row, pe);
         }
       }
       mbar_arrive(bar_pe_ready + 8 * buf);
