@@ -97,6 +97,8 @@ def _load():
         'dfn_decoder_query_workspace_bytes': (i64, [vp, i64, i32]),
         'dfn_decoder_query': (i32, [vp, i32, i64, i32, vp, vp, vp, vp, vp, vp, vp, i32, vp, i64, vp]),
         'dfn_decoder_macs_per_sample': (C.c_double, [vp, i32]),
+        'dfn_model_program_host': (i32, [vp, C.POINTER(vp), i32, i32, C.POINTER(LayerInfo), C.POINTER(i32), vp, vp,
+                                         C.POINTER(i32), vp, vp, vp]),
         'dfn_decoder_program_host': (i32, [C.POINTER(DecoderDesc), C.POINTER(vp), i32, i32, i32, C.POINTER(LayerInfo),
                                            C.POINTER(i32), vp, vp, C.POINTER(i32), C.POINTER(i32), vp, C.POINTER(i32),
                                            C.POINTER(i32)]),
@@ -119,7 +121,7 @@ EXPORTS = ['dfn_abi_version', 'dfn_last_error', 'dfn_last_launch_count', 'dfn_pr
            'dfn_mlp_workspace_bytes', 'dfn_mlp_forward', 'dfn_query_workspace_bytes', 'dfn_query_points',
            'dfn_render_workspace_bytes', 'dfn_render_rays', 'dfn_decoder_create', 'dfn_decoder_destroy',
            'dfn_decoder_num_tensors', 'dfn_decoder_load', 'dfn_decoder_query_workspace_bytes', 'dfn_decoder_query',
-           'dfn_decoder_macs_per_sample', 'dfn_decoder_program_host', 'dfn_render_head_torso_workspace_bytes', 'dfn_render_head_torso']
+           'dfn_decoder_macs_per_sample', 'dfn_decoder_program_host', 'dfn_model_program_host', 'dfn_render_head_torso_workspace_bytes', 'dfn_render_head_torso']
 
 
 def check(rc, what=''):

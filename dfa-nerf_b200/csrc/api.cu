@@ -265,6 +265,40 @@ extern "C" int dfn_model_load(dfn_model* m, const float* const* t, int n_tensors
   return 0;
 }
 
+// Host-only: the layer program dfn_model_load builds for the tcgen05 kernels, as dense fp32 (no CUDA calls).
+extern "C" int dfn_model_program_host(const dfn_model* m, const float* const* t, int n_tensors, int max_layers,
+                                      dfn_layer_info* layers, int* n_layers, float* weights, float* bias, int* fold_layer,
+                                      float* fold_w, float* view_w, float* view_b) {
+  DFN_CHECK_ARG(m && t && layers && n_layers && weights && bias && fold_layer && fold_w && view_w && view_b,
+                "dfn_model_program_host: null argument");
+  DFN_CHECK_ARG(n_tensors == dfn_model_num_tensors(m) && max_layers >= TC_MAX_LAYERS,
+                "dfn_model_program_host: expected %d tensors and max_layers >= %d", dfn_model_num_tensors(m), TC_MAX_LAYERS);
+  dfn_model tmp;
+  tmp.desc = m->desc;
+  tmp.n_views = m->n_views;
+  TcHostDump dump;
+  int rc = tc_pack_model(&tmp, t, nullptr, &dump);
+  if (rc) return rc;
+  *n_layers = tmp.prog.n_layers;
+  for (int l = 0; l < tmp.prog.n_layers; ++l) {
+    const TcLayer& L = tmp.prog.layers[l];
+    layers[l].n = L.n;
+    layers[l].nkb = L.nkb;
+    layers[l].epi = L.epi;
+    layers[l].flags = L.flags;
+    for (int k = 0; k < 6; ++k) layers[l].kb[k] = L.kb[k];
+  }
+  memset(weights, 0, (size_t)max_layers * TC_BIAS_STRIDE * 6 * 64 * 4);
+  memcpy(weights, dump.dense.data(), dump.dense.size() * 4);
+  memcpy(bias, dump.bias.data(), dump.bias.size() * 4);
+  fold_layer[0] = tmp.prog.fold_layer[0];
+  fold_layer[1] = tmp.prog.fold_layer[1];
+  memcpy(fold_w, dump.fold_w.data(), dump.fold_w.size() * 4);
+  memcpy(view_w, dump.view_w.data(), dump.view_w.size() * 4);
+  memcpy(view_b, dump.view_b.data(), dump.view_b.size() * 4);
+  return 0;
+}
+
 extern "C" int64_t dfn_mlp_workspace_bytes(const dfn_model* m, int64_t P) {
   return m ? mlp_fp32_workspace_bytes(m, P) : 0;
 }

@@ -123,7 +123,6 @@ struct Builder {
   DecField* F;
   std::vector<float> bias;                 // [TC_MAX_LAYERS][256]
   std::vector<std::vector<float>> folds;   // each [dimL][256]
-  std::vector<float>* dense = nullptr;     // host-only introspection: fp32 weights [layer][256][6*64], see dfn_decoder_program_host
   int nl = 0;
   explicit Builder(DecField* f, int dimL) : F(f), bias((size_t)TC_MAX_LAYERS * TC_BIAS_STRIDE, 0.f) {
     pk.want64 = false;
@@ -140,12 +139,6 @@ struct Builder {
     L.epi = (uint8_t)epi;
     L.flags = (uint8_t)flags;
     for (int kb : kbs) L.kb[L.nkb++] = (uint8_t)kb;
-    if (dense) {
-      float* d = dense->data() + (size_t)nl * TC_BIAS_STRIDE * 6 * 64;
-      for (int r = 0; r < n; ++r)
-        for (int kbi = 0; kbi < L.nkb; ++kbi)
-          for (int k = 0; k < 64; ++k) d[((size_t)r * 6 + kbi) * 64 + k] = wfun(r, kbi, k);
-    }
     pk.add_layer(n, L.nkb, wfun);
     F->woff32[nl] = pk.last32;
     F->prog.layers[nl] = L;
@@ -527,8 +520,8 @@ extern "C" int dfn_decoder_program_host(const dfn_decoder_desc* desc, const floa
   DecField F;
   const int dsig = field == 0 ? desc->dim_signal : desc->dim_et_embed;
   Builder B(&F, dsig + 2 * desc->z_dim);
-  std::vector<float> dense((size_t)TC_MAX_LAYERS * TC_BIAS_STRIDE * 6 * 64, 0.f);
-  B.dense = &dense;
+  std::vector<float> dense;
+  B.pk.dense = &dense;
   if (field == 1) build_deform(B, T, *desc);
   build_trunk(B, T, *desc, field == 1, dsig, dsig + desc->z_dim);
   *n_layers = B.nl;
@@ -540,6 +533,7 @@ extern "C" int dfn_decoder_program_host(const dfn_decoder_desc* desc, const floa
     layers[l].flags = L.flags;
     for (int k = 0; k < 6; ++k) layers[l].kb[k] = L.kb[k];
   }
+  memset(weights, 0, (size_t)max_layers * tc::Packer::kDenseLayer * 4);
   memcpy(weights, dense.data(), dense.size() * 4);
   memcpy(bias, B.bias.data(), B.bias.size() * 4);
   *n_fold = F.n_fold;

@@ -454,7 +454,9 @@ void tc_free_model(dfn_model* m) {
 }
 
 // Builds the layer program and the packed blobs from the reference tensors (order of dfn.h).
-int tc_pack_model(dfn_model* m, const float* const* t, cudaStream_t st) {
+// dump != nullptr: host-only dry run for dfn_model_program_host (no CUDA calls; the program, biases and fold / view
+// matrices are returned in *dump).
+int tc_pack_model(dfn_model* m, const float* const* t, cudaStream_t st, TcHostDump* dump) {
   const dfn_model_desc& d = m->desc;
   if (d.W != 256 || d.input_ch > 63 || d.input_ch != 3 + 6 * d.multires || d.D < 2 || d.D + m->n_views + 1 > TC_MAX_LAYERS ||
       d.skip < 0 || d.skip >= d.D - 1) {
@@ -467,6 +469,7 @@ int tc_pack_model(dfn_model* m, const float* const* t, cudaStream_t st) {
   const int i_views0 = d.D, i_feature = d.D + m->n_views, i_alpha = i_feature + 1, i_rgb = i_feature + 2;
 
   tc::Packer pk;
+  if (dump) pk.dense = &dump->dense;
   TcProgram& pg = m->prog;
   pg = TcProgram();
   std::vector<float> bias((size_t)TC_MAX_LAYERS * TC_BIAS_STRIDE, 0.f);
@@ -556,11 +559,16 @@ int tc_pack_model(dfn_model* m, const float* const* t, cudaStream_t st) {
     std::vector<float> vw((size_t)Wh * d.input_ch_views);
     for (int n = 0; n < Wh; ++n)
       for (int j = 0; j < d.input_ch_views; ++j) vw[(size_t)n * d.input_ch_views + j] = wv[(size_t)n * ldv + W + j];
-    DFN_CUDA(cudaMalloc(&m->tc_view_w, vw.size() * 4));
-    DFN_CUDA(cudaMalloc(&m->tc_view_b, bc.size() * 4));
-    DFN_CUDA(cudaMemcpyAsync(m->tc_view_w, vw.data(), vw.size() * 4, cudaMemcpyHostToDevice, st));
-    DFN_CUDA(cudaMemcpyAsync(m->tc_view_b, bc.data(), bc.size() * 4, cudaMemcpyHostToDevice, st));
-    DFN_CUDA(cudaStreamSynchronize(st));
+    if (dump) {
+      dump->view_w = vw;
+      dump->view_b = bc;
+    } else {
+      DFN_CUDA(cudaMalloc(&m->tc_view_w, vw.size() * 4));
+      DFN_CUDA(cudaMalloc(&m->tc_view_b, bc.size() * 4));
+      DFN_CUDA(cudaMemcpyAsync(m->tc_view_w, vw.data(), vw.size() * 4, cudaMemcpyHostToDevice, st));
+      DFN_CUDA(cudaMemcpyAsync(m->tc_view_b, bc.data(), bc.size() * 4, cudaMemcpyHostToDevice, st));
+      DFN_CUDA(cudaStreamSynchronize(st));
+    }
   }
   for (int i = 1; i < m->n_views; ++i) {
     TcLayer L;
@@ -594,6 +602,11 @@ int tc_pack_model(dfn_model* m, const float* const* t, cudaStream_t st) {
   }
   pg.n_layers = nl;
   m->tc_blob_bytes = (int64_t)pk.hi32.size();
+  if (dump) {
+    dump->bias = bias;
+    dump->fold_w = fold_w;
+    return 0;
+  }
   DFN_CUDA(cudaMalloc(&m->tc2_hi, pk.hi2.size()));
   DFN_CUDA(cudaMalloc(&m->tc2_lo, pk.lo2.size()));
   DFN_CUDA(cudaMemcpyAsync(m->tc2_hi, pk.hi2.data(), pk.hi2.size(), cudaMemcpyHostToDevice, st));

@@ -3,6 +3,8 @@
 #include <stdint.h>
 #include <cuda_runtime.h>
 
+#include <vector>
+
 #include "../../include/dfn.h"
 
 namespace dfn {
@@ -104,7 +106,14 @@ int tc2_launch(const dfn_model* m, const float* bias_ws, const float* vbias_ws, 
                const float* rays_d, const float* z_vals, float* raw, int precision, cudaStream_t st);
 int ts_launch(const dfn_model* m, const float* bias_ws, const float* vbias_ws, int64_t R, int S, const float* rays_o,
               const float* rays_d, const float* z_vals, float* raw, int precision, cudaStream_t st);
-int tc_pack_model(dfn_model* m, const float* const* t, cudaStream_t st);
+struct TcHostDump {   // host-only view of a packed model (dfn_model_program_host)
+  std::vector<float> dense;    // [layer][256][6][64]
+  std::vector<float> bias;     // [TC_MAX_LAYERS][256]
+  std::vector<float> fold_w;   // [2][W][dim_aud]
+  std::vector<float> view_w;   // [W/2][input_ch_views]
+  std::vector<float> view_b;   // [W/2]
+};
+int tc_pack_model(dfn_model* m, const float* const* t, cudaStream_t st, TcHostDump* dump = nullptr);
 void tc_free_model(dfn_model* m);
 int64_t tc_query_workspace_bytes(const dfn_model* m, int64_t R, int S);
 int tc_query_points(const dfn_model* m, int64_t R, int S, const float* rays_o, const float* rays_d,

@@ -33,6 +33,10 @@ struct Packer {
   uint32_t last32 = 0;               // offset of the last layer added to hi32
   uint32_t last2 = 0;                // offset of the last layer added to hi2
   bool want2 = true;                 // build the cta_group::2 images
+  // host-only introspection (dfn_*_program_host): dense fp32 weights, [layer][256 rows][6 input-block slots][64]
+  static constexpr size_t kDenseLayer = (size_t)256 * 6 * 64;
+  std::vector<float>* dense = nullptr;
+  int n_dense = 0;
   bool want64 = true;                // also build the 128-byte-swizzle images (only mlp_ts.cu reads them)
   // Appends the stages of one layer: for each K-block, for each chunk of <=128 output rows, a
   // [rows x 64] bf16 image in the swizzled K-major layout.  wfun(n, kbi, k) returns W[n][column
@@ -40,6 +44,14 @@ struct Packer {
   template <class F>
   uint32_t add_layer(int n_out, int nkb, F wfun) {
     const uint32_t start = (uint32_t)hi.size();
+    if (dense) {
+      dense->resize((size_t)(n_dense + 1) * kDenseLayer, 0.f);
+      float* d = dense->data() + (size_t)n_dense * kDenseLayer;
+      for (int r = 0; r < n_out; ++r)
+        for (int kbi = 0; kbi < nkb; ++kbi)
+          for (int k = 0; k < 64; ++k) d[((size_t)r * 6 + kbi) * 64 + k] = wfun(r, kbi, k);
+      ++n_dense;
+    }
     for (int kbi = 0; want64 && kbi < nkb; ++kbi) {
       for (int c0 = 0; c0 < n_out; c0 += 128) {
         const int rows = n_out - c0 < 128 ? n_out - c0 : 128;

@@ -228,6 +228,14 @@ int dfn_decoder_program_host(const dfn_decoder_desc* desc, const float* const* t
                              int max_layers, dfn_layer_info* layers, int* n_layers, float* weights, float* bias,
                              int* n_fold, int* fold_layer, float* fold_w, int* dimL, int* view_layer);
 
+/* The same for a FaceNeRF / NeRF model (m: created, weights not needed): layers as above (epilogue 1 = views_linears.0
+ * with the density head as column W/2 and the per-ray view term as bias); fold_layer[2] / fold_w [2][W][dim_aud]: the
+ * latent columns of the two layers that read the input (bias[fold_layer[i]][n] += fold_w[i][n][:] . latent); view_w
+ * [W/2][input_ch_views], view_b [W/2]: the per-ray term of views_linears.0 (for NeRF with feature_linear composed in). */
+int dfn_model_program_host(const dfn_model* m, const float* const* tensors_host, int n_tensors, int max_layers,
+                           dfn_layer_info* layers, int* n_layers, float* weights, float* bias, int* fold_layer,
+                           float* fold_w, float* view_w, float* view_b);
+
 /* ---- one chunk of the live render loop  (MAIN:617-619, MAIN:633-708) ----------------------------------
  * z sampling -> head field on the head-pose rays, torso field (with deformation) on the body-pose rays ->
  * background splice, two-field density mix, weights, colour sums.  z_shape / z_app: [2, z_dim] (row 0 head,

@@ -118,3 +118,90 @@ def test_program_host_argument_checks():
     assert _lib.lib.dfn_decoder_num_tensors(h) == 64
     assert _lib.lib.dfn_decoder_macs_per_sample(h, 0) == 0.0          # nothing loaded yet
     _lib.lib.dfn_decoder_destroy(h)
+
+
+def _dump_model_program(dfn, kind, sd, names):
+    from dfa_nerf_b200 import _lib
+    dim_aud = 64 if kind == _lib.MODEL_FACENERF else 0
+    desc = _lib.ModelDesc(kind, 8, 256, 63, 27, dim_aud, 4, 10, 4)
+    h = C.c_void_p()
+    assert _lib.lib.dfn_model_create(C.byref(desc), C.byref(h)) == 0
+    host = []
+    for n in names:
+        host += [sd[n + '.weight'].contiguous().float(), sd[n + '.bias'].contiguous().float()]
+    assert _lib.lib.dfn_model_num_tensors(h) == len(host)
+    arr = (C.c_void_p * len(host))(*[t.data_ptr() for t in host])
+    ML = 20
+    layers = (_lib.LayerInfo * ML)()
+    n_layers = C.c_int()
+    weights = np.zeros((ML, 256, 6, 64), np.float32)
+    bias = np.zeros((ML, 256), np.float32)
+    fold_layer = (C.c_int * 2)()
+    fold_w = np.zeros((2, 256, max(dim_aud, 1)), np.float32)
+    view_w, view_b = np.zeros((128, 27), np.float32), np.zeros(128, np.float32)
+    rc = _lib.lib.dfn_model_program_host(h, arr, len(host), ML, layers, C.byref(n_layers), weights.ctypes.data_as(C.c_void_p),
+                                         bias.ctypes.data_as(C.c_void_p), fold_layer, fold_w.ctypes.data_as(C.c_void_p),
+                                         view_w.ctypes.data_as(C.c_void_p), view_b.ctypes.data_as(C.c_void_p))
+    assert rc == 0, _lib.lib.dfn_last_error()
+    _lib.lib.dfn_model_destroy(h)
+    return [layers[i] for i in range(n_layers.value)], weights, bias, [fold_layer[0], fold_layer[1]], fold_w, view_w, view_b
+
+
+def _run_model_program(prog, pe, latent, pe_view):
+    layers, weights, bias, fold_layer, fold_w, view_w, view_b = prog
+    P = pe.shape[0]
+    blocks = {k: np.zeros((P, 64)) for k in range(5)}
+    blocks[KB_PE][:, :63] = pe
+    alpha, rgb = None, None
+    for l, L in enumerate(layers):
+        n = L.n
+        x = np.concatenate([blocks[L.kb[i]] for i in range(L.nkb)], 1)
+        acc = x @ weights[l, :n, :L.nkb].reshape(n, -1).astype(np.float64).T
+        b = bias[l, :n].astype(np.float64)
+        if latent is not None and l in fold_layer:
+            b = b + np.pad(fold_w[fold_layer.index(l)].astype(np.float64) @ latent, (0, 0))[:n]
+        if L.epi == EPI_RGB:
+            rgb = acc[:, :3] + b[:3]
+            continue
+        if L.epi == EPI_VIEW0:
+            wh = view_w.shape[0]
+            alpha = acc[:, wh] + b[wh]
+            h = np.maximum(acc[:, :wh] + view_b.astype(np.float64) + pe_view @ view_w.astype(np.float64).T, 0.)
+            n = wh
+        else:
+            h = np.maximum(acc + b, 0.)
+        for i in range(n // 64):
+            blocks[i] = h[:, 64 * i:64 * (i + 1)]
+    return np.concatenate([rgb, alpha[:, None]], 1)
+
+
+def test_facenerf_and_nerf_layer_programs_compute_the_reference_forward():
+    """FaceNeRF (HELP:275-299: latent columns folded into biases, view columns into a per-ray term, alpha riding the first
+    view layer) and NeRF (HELP:372-396: feature_linear composed into views_linears.0) as compiled by tc_pack_model."""
+    import dfa_nerf_b200 as dfn
+    from dfa_nerf_b200 import _lib
+    g = torch.Generator().manual_seed(1)
+    P = 61
+    pts = (torch.rand(P, 3, generator=g) * 2 - 1).double()
+    vd = torch.randn(P, 3, generator=g).double()
+    vd = vd / torch.norm(vd, dim=-1, keepdim=True)
+    aud = torch.randn(64, generator=g).double()
+    pe, pev = O.embed(pts, 10), O.embed(vd, 4)
+    trunk = ['pts_linears.%d' % i for i in range(8)]
+    cases = ((_lib.MODEL_FACENERF, synth.facenerf_state_dict(2), trunk + ['views_linears.%d' % i for i in range(3)] +
+              ['feature_linear', 'alpha_linear', 'rgb_linear'], 12),
+             (_lib.MODEL_NERF, synth.nerf_state_dict(2), trunk + ['views_linears.0', 'feature_linear', 'alpha_linear', 'rgb_linear'], 10))
+    with torch.no_grad():
+        for kind, sd, names, nl in cases:
+            prog = _dump_model_program(dfn, kind, sd, names)
+            assert len(prog[0]) == nl
+            sd64 = {k: v.double() for k, v in sd.items()}
+            if kind == _lib.MODEL_FACENERF:
+                ref = O.facenerf_forward(sd64, torch.cat([pe, aud[None].expand(P, -1), pev], -1))
+                out = _run_model_program(prog, pe.numpy(), aud.numpy(), pev.numpy())
+            else:
+                ref = O.nerf_forward(sd64, torch.cat([pe, pev], -1))
+                out = _run_model_program(prog, pe.numpy(), None, pev.numpy())
+            scale = np.abs(ref.numpy()).max(0)
+            err = (np.abs(out - ref.numpy()) / scale).max()
+            assert err < 2e-6, (kind, err)
