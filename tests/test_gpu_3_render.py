@@ -168,3 +168,28 @@ def test_render_sequence_matches_per_frame(dfn):
         _, person = dfn.render_head_torso(dec, H, W, fr['focal'], fr['c2w_seq'][i], body, bc, zs, za, sig[i].to(DEV), sig_t[i].to(DEV),
                                           fr['near'], fr['far'], fr['cx'], fr['cy'])
         assert torch.equal(fr2[i], dfn.to8b(person).reshape(H, W, 3).cpu())
+
+
+def test_render_rays_maximum_samples_and_limits(dfn):
+    """The largest supported ray (128 coarse + 128 fine = 256 samples, eight per lane in the compositing kernels, the
+    512-wide padded merge) teacher-forced against the oracle; one sample more is refused with an error, not truncated."""
+    R, Nc, Nf = 24, 128, 128
+    fr = synth.frame_inputs(H=R, W=1, seed=6)
+    sd_c, sd_f = synth.facenerf_state_dict(0), synth.facenerf_state_dict(1)
+    nc, nf = nets(dfn, 0, 1)
+    ro, rd = O.get_rays(R, 1, fr['focal'], fr['c2w'], fr['cx'], fr['cy'])
+    ro, rd = ro.reshape(-1, 3).contiguous(), rd.reshape(-1, 3)
+    vd = rd / torch.norm(rd, dim=-1, keepdim=True)
+    near, far = torch.full((R,), fr['near']), torch.full((R,), fr['far'])
+    rays = torch.cat([ro, rd, near[:, None], far[:, None], vd], -1)
+    with torch.no_grad():
+        ref = O.render_rays(rays, fr['bc_rgb'], fr['aud'], sd_c, sd_f, Nc, Nf)
+    eng = dfn.RenderEngine(nc, nf, Nc, Nf, precision=dfn.PREC_BF16X3)
+    out = eng.render_rays(ro.to(DEV), rd.to(DEV), vd.to(DEV), near.to(DEV), far.to(DEV), fr['bc_rgb'].to(DEV), fr['aud'].to(DEV),
+                          z_samples=ref['z_samples'].to(DEV), want=('rgb_map', 'rgb0', 'acc_map', 'z_vals'))
+    assert torch.equal(out['z_vals'].cpu(), ref['z_vals'])
+    assert maxerr(out['rgb0'], ref['rgb0']) < 1e-4 and maxerr(out['rgb_map'], ref['rgb_map']) < 1e-4
+    assert maxerr(out['acc_map'], ref['acc_map']) < 1e-4
+    with pytest.raises(dfn.DfnError):
+        dfn.RenderEngine(nc, nf, 129, 128, precision=dfn.PREC_BF16X3).render_rays(
+            ro.to(DEV), rd.to(DEV), vd.to(DEV), near.to(DEV), far.to(DEV), fr['bc_rgb'].to(DEV), fr['aud'].to(DEV))
