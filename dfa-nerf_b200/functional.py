@@ -12,7 +12,6 @@ import ctypes as C
 import numpy as np
 import torch
 
-from . import _lib
 from ._lib import lib, check, dev, ptr, stream_ptr, DfnError
 
 _tables = {}

@@ -1,6 +1,5 @@
 """GPU parity of the stage kernels (through the C ABI) against the oracle and the golden vectors.
 Bars: rays / depths / merged depths / searchsorted indices bit-exact; floats to the stated tolerance."""
-import numpy as np
 import pytest
 import torch
 

@@ -114,7 +114,6 @@ def test_composite_head_torso_edge_cases(dfn):
     w2 = O.calc_volume_weights(z[None], rdt[None], ss2)
     ref_h = torch.sum(w1.unsqueeze(-1) * fw1, dim=-2)[0]
     ref_p = torch.sum(w2.unsqueeze(-1) * fw2, dim=-2)[0]
-    import ctypes as C
     from dfa_nerf_b200._lib import lib, ptr, stream_ptr
     t = [x.contiguous().to(DEV) for x in (fh, sh, ft, st, bc, z, rd, rdt)]
     oh, op = torch.empty(R, 3, device=DEV), torch.empty(R, 3, device=DEV)
