@@ -93,18 +93,18 @@ def _run(render_one, H, W, n_frames, bc_rgb, latents, group, gather):
     f0, f1 = shard_frames(n_frames, rank, world)
     lat_dev = latents.to(device, torch.float32).contiguous() if latents is not None else None   # one upload for the sequence
     bc = bc_rgb.reshape(-1, 3)
+    if world > 1 and gather:
+        # frames stay on the device until the one all-gather at the end (uint8: 3 bytes per pixel on the wire); ragged
+        # blocks are padded to the largest and trimmed afterwards
+        per = (n_frames + world - 1) // world
+        tile = torch.zeros((per, H, W, 3), dtype=torch.uint8, device=device)
+        for i in range(f0, f1):
+            tile[i - f0].copy_(to8b(render_one(i, bc, lat_dev[i] if lat_dev is not None else None)).reshape(H, W, 3))
+        full = torch.empty((world * per, H, W, 3), dtype=torch.uint8, device=device)
+        dist.all_gather_into_tensor(full, tile, group=group)
+        blocks = [shard_frames(n_frames, r, world) for r in range(world)]
+        return torch.cat([full[r * per:r * per + (e - b)] for r, (b, e) in enumerate(blocks)], 0).cpu()
     sink = FrameSink(max(f1 - f0, 1), H, W, device)
     for i in range(f0, f1):
         sink.push(render_one(i, bc, lat_dev[i] if lat_dev is not None else None))
-    local = sink.finish()[:f1 - f0]
-    if world == 1 or not gather:
-        return local
-    # ragged blocks: pad to the largest, all_gather, trim (uint8 frames: 3 bytes per pixel on the wire)
-    per = (n_frames + world - 1) // world
-    tile = torch.zeros((per, H, W, 3), dtype=torch.uint8, device=device)
-    tile[:f1 - f0].copy_(local, non_blocking=True)
-    full = torch.empty((world * per, H, W, 3), dtype=torch.uint8, device=device)
-    dist.all_gather_into_tensor(full, tile, group=group)
-    out = [full[r * per:r * per + (shard_frames(n_frames, r, world)[1] - shard_frames(n_frames, r, world)[0])]
-           for r in range(world)]
-    return torch.cat(out, 0).cpu()
+    return sink.finish()[:f1 - f0]
