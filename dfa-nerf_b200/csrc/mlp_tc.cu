@@ -35,12 +35,13 @@ namespace tc {
 
 static constexpr int STAGE_BYTES = 128 * 128;      // one weight stage: <=128 rows x 64 bf16
 static constexpr int N_STAGES = 4;
+static constexpr int PE_HELPERS = 64;   // warps 2-3 encode the next tile while the current one is in its last layers
 static constexpr int N_PAIRS = N_STAGES / 2;
 static constexpr int ARENA_BLOCKS = 2 * TC_KB_PER_TILE;
 static constexpr int SMEM_RING = ARENA_BLOCKS * KB_BYTES;
 static constexpr int SMEM_BIAS = SMEM_RING + N_STAGES * STAGE_BYTES;
 static constexpr int SMEM_BAR = SMEM_BIAS + 2 * TC_BIAS_STRIDE * 4;
-static constexpr int SMEM_TOTAL = SMEM_BAR + 128;
+static constexpr int SMEM_TOTAL = SMEM_BAR + 192;
 static_assert(SMEM_TOTAL <= 227 * 1024, "shared memory budget");
 
 struct Params {
@@ -83,6 +84,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(X3 ? 256 : 384, 1)
   const uint32_t bar_acc = sbase + SMEM_BAR + 64;      // [2] accumulator of slot s complete
   const uint32_t bar_aready = sbase + SMEM_BAR + 80;   // [2] activations of slot s written
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + SMEM_BAR + 96);
+  const uint32_t bar_pefree = sbase + SMEM_BAR + 112;  // [2] the PE block of slot s is no longer read (last PE layer's MMAs done)
+  const uint32_t bar_peready = sbase + SMEM_BAR + 128; // [2] the PE block of slot s holds the next tile's encoding
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < N_STAGES; ++i) {
@@ -92,6 +95,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(X3 ? 256 : 384, 1)
     for (int s = 0; s < 2; ++s) {
       mbar_init(bar_acc + 8 * s, 1);
       mbar_init(bar_aready + 8 * s, TILE_M);
+      mbar_init(bar_pefree + 8 * s, TILE_M);
+      mbar_init(bar_peready + 8 * s, PE_HELPERS);
     }
     fence_barrier_init();
   }
@@ -257,6 +262,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(X3 ? 256 : 384, 1)
     float* bias_s = reinterpret_cast<float*>(smem + SMEM_BIAS) + s * TC_BIAS_STRIDE;
     const uint32_t acc = tmem_base + (uint32_t)s * 256u + ((uint32_t)((warp & 3) * 32) << 16);
     uint32_t acc_par = 0u;
+    int last_pe_layer = 0;
+    for (int l2 = 0; l2 < P.n_layers; ++l2)
+      for (int k = 0; k < P.layers[l2].nkb; ++k)
+        if (P.layers[l2].kb[k] == TC_KB_PE) last_pe_layer = l2;
 
     for (int j = 0; j < n_iter; ++j) {
       if (group_of(j, s) >= n_groups) break;
@@ -273,24 +282,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(X3 ? 256 : 384, 1)
         const float2 b2 = reinterpret_cast<const float2*>(P.bias)[tid_s];
         reinterpret_cast<float2*>(bias_s)[tid_s] = b2;
       }
-      // ---- positional encoding of x = o + d*z into the PE K-block (HELP:42-52) ----
-      // The argument x*2^k is exact; two-constant Cody-Waite reduction to [-pi, pi] (error ~1e-8 for |x*2^k| < 1e3)
-      // and the MUFU sin/cos (abs error 2^-21.4 there): below the bf16 / hi+lo resolution of the MMA operands, and
-      // four times shorter than sincosf on the tile's critical path.  Eight 16-byte swizzled stores per row.
-      {
-        float pe[64], x[3];
-        sample_point(P.rays_o, P.rays_d, ray, P.z_vals[pt], x);
-        pe_embedder(x, P.multires, pe);
-        uint8_t* pe_hi = arena_hi + TC_KB_PE * KB_BYTES;
-        uint8_t* pe_lo = arena_lo + TC_KB_PE * KB_BYTES;
-#pragma unroll
-        for (int ch = 0; ch < 8; ++ch) {
-          float o[8];
-#pragma unroll
-          for (int e = 0; e < 8; ++e) o[e] = pe[ch * 8 + e];
-          store_chunk<X3, F16>(pe_hi, pe_lo, row, (uint32_t)ch, o);
-        }
-      }
+      // the tile's positional encoding was written into the PE K-block by the helper warps (below), one tile ahead
+      mbar_wait(bar_peready + 8 * s, (uint32_t)j & 1u);
       fence_proxy_async();
       mbar_arrive(bar_aready + 8 * s);
       named_bar_sync(1 + s, TILE_M);  // bias_s visible to the slot's four warps
@@ -310,6 +303,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(X3 ? 256 : 384, 1)
         acc_par ^= 1u;
         tcgen05_fence_after();
         if (tr) t_e1 = clock64();
+        if (l == last_pe_layer) mbar_arrive(bar_pefree + 8 * s);   // its MMAs were the last readers of the PE block
 
         if (L.epi == TC_EPI_RGB) {
           uint32_t v[16];
@@ -355,6 +349,42 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(X3 ? 256 : 384, 1)
         }
       }
       named_bar_sync(1 + s, TILE_M);  // everyone done with bias_s before the next tile restages it
+    }
+  }
+
+  if (warp == 2 || warp == 3) {
+    // ============================ positional-encoding helper warps ==============================
+    // x = o + d*z -> [x | sin(2^k x) | cos(2^k x)] (HELP:42-52, pe.cuh) for the NEXT tile of each slot, written straight
+    // into the slot's PE K-block as soon as the last layer that reads it (the skip layer) has finished its MMAs: the
+    // ~2,800 cycles of encoding leave the slot's dependency chain.  Two rows per thread and slot.
+    const int t = (warp - 2) * 32 + lane;
+    for (int j = 0; j < n_iter; ++j) {
+      for (int s = 0; s < NSLOT; ++s) {
+        if (group_of(j, s) >= n_groups) continue;
+        if (j > 0) mbar_wait(bar_pefree + 8 * s, (uint32_t)(j - 1) & 1u);
+        uint8_t* pe_hi = smem + (size_t)(s * TC_KB_PER_TILE + TC_KB_PE) * KB_BYTES;
+        uint8_t* pe_lo = pe_hi + (size_t)TC_KB_PER_TILE * KB_BYTES;
+        const int tile = 2 * group_of(j, s) + (int)crank;
+#pragma unroll 1
+        for (int h = 0; h < 2; ++h) {
+          const uint32_t row = (uint32_t)(t + 64 * h);
+          int64_t pt = (int64_t)tile * TILE_M + row;
+          if (pt >= P.n_points) pt = P.n_points - 1;
+          const int64_t ray = pt / P.S;
+          float pe[64], x[3];
+          sample_point(P.rays_o, P.rays_d, ray, P.z_vals[pt], x);
+          pe_embedder(x, P.multires, pe);
+#pragma unroll
+          for (int ch = 0; ch < 8; ++ch) {
+            float o[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) o[e] = pe[ch * 8 + e];
+            store_chunk<X3, F16>(pe_hi, pe_lo, row, (uint32_t)ch, o);
+          }
+        }
+        fence_proxy_async();
+        mbar_arrive(bar_peready + 8 * s);
+      }
     }
   }
 
