@@ -28,21 +28,31 @@ def shard_frames(n_frames, rank, world_size):
 
 
 class FrameSink:
-    """Double-buffered device->host path for rendered frames: to8b on the render stream, copy on a side stream."""
+    """Double-buffered device->host path for rendered frames: to8b on the render stream, copy on a side stream.
+    `planes` images per frame (render_person keeps head and person).  `on_frame(k, u8[planes,H,W,3] numpy view)` is
+    called on the host, in order, as soon as local frame k's copy has landed -- i.e. while later frames render."""
 
-    def __init__(self, n_frames, H, W, device, depth=2):
-        self.host = torch.empty((n_frames, H, W, 3), dtype=torch.uint8).pin_memory()
-        self.dev = [torch.empty((H, W, 3), dtype=torch.uint8, device=device) for _ in range(depth)]
+    def __init__(self, n_frames, H, W, device, depth=2, planes=1, on_frame=None):
+        self.host = torch.empty((n_frames, planes, H, W, 3), dtype=torch.uint8).pin_memory()
+        self.dev = [torch.empty((planes, H, W, 3), dtype=torch.uint8, device=device) for _ in range(depth)]
         self.copied = [None] * depth
         self.stream = torch.cuda.Stream(device=device)
-        self.H, self.W, self.i = H, W, 0
+        self.shape, self.i, self.delivered, self.on_frame = (planes, H, W, 3), 0, 0, on_frame
+
+    def _deliver(self, upto):
+        while self.on_frame is not None and self.delivered < upto:
+            self.on_frame(self.delivered, self.host[self.delivered].numpy())
+            self.delivered += 1
 
     def push(self, rgb_map):
         k = self.i % len(self.dev)
         cur = torch.cuda.current_stream()
         if self.copied[k] is not None:
             cur.wait_event(self.copied[k])          # the previous copy out of this buffer has finished
-        self.dev[k].copy_(to8b(rgb_map).reshape(self.H, self.W, 3))
+            if self.on_frame is not None:
+                self.copied[k].synchronize()        # frame i-depth is in host memory: hand it on while frame i renders
+                self._deliver(self.i - len(self.dev) + 1)
+        self.dev[k].copy_(to8b(rgb_map).reshape(self.shape))
         ready = torch.cuda.Event()
         ready.record(cur)
         with torch.cuda.stream(self.stream):
@@ -55,22 +65,28 @@ class FrameSink:
 
     def finish(self):
         self.stream.synchronize()
-        return self.host[:self.i]
+        self._deliver(self.i)
+        out = self.host[:self.i]
+        return out[:, 0] if self.shape[0] == 1 else out
 
 
 @torch.no_grad()
-def render_sequence(engine, H, W, focal, poses, auds, bc_rgb, near, far, cx=None, cy=None, group=None, gather=True):
+def render_sequence(engine, H, W, focal, poses, auds, bc_rgb, near, far, cx=None, cy=None, group=None, gather=True,
+                    on_frame=None):
     """FaceNeRF / NeRF sequence: poses [N,3,4] (or [N,4,4]), auds [N,dim_aud] (None for NeRF), one background.
-    Returns uint8 frames [N,H,W,3] in pinned host memory (this rank's block [n_local,H,W,3] when gather=False)."""
+    Returns uint8 frames [N,H,W,3] in pinned host memory (this rank's block [n_local,H,W,3] when gather=False).
+    on_frame(i, u8[1,H,W,3]): called per finished frame of THIS rank with its global index (e.g. a FrameWriter)."""
     return _run(lambda i, bc, lat: engine.render_frame(H, W, focal, poses[i, :3, :4], bc, lat, near, far, cx, cy)['rgb_map'],
-                H, W, poses.shape[0], bc_rgb, auds, group, gather)
+                H, W, poses.shape[0], bc_rgb, auds, group, gather, on_frame=on_frame)
 
 
 @torch.no_grad()
 def render_sequence_head_torso(decoder, H, W, focal, poses, pose_torso, bc_rgb, z_shape, z_app, signals, signals_torso,
-                               near, far, cx=None, cy=None, N_samples=64, precision=None, group=None, gather=True):
+                               near, far, cx=None, cy=None, N_samples=64, precision=None, group=None, gather=True,
+                               on_frame=None, with_head=False):
     """The reference's live loop MAIN:624-733: head poses [N,3,4], one fixed body pose (MAIN:644), per-frame head
-    signals [N,dim_signal] and torso signals [N,dim_et_embed].  Returns the `person` frames (MAIN:712-715) as uint8."""
+    signals [N,dim_signal] and torso signals [N,dim_et_embed].  Returns the `person` frames (MAIN:712-715) as uint8
+    [N,H,W,3]; with_head=True keeps both images of a frame, [N,2,H,W,3] = (head, person) (MAIN:712-722 writes both)."""
     from .decoder import render_head_torso
     from . import _lib
     precision = _lib.PREC_BF16X3 if precision is None else precision
@@ -78,12 +94,13 @@ def render_sequence_head_torso(decoder, H, W, focal, poses, pose_torso, bc_rgb, 
     ds = signals.shape[1]
 
     def frame(i, bc, l):
-        return render_head_torso(decoder, H, W, focal, poses[i, :3, :4], pose_torso[:3, :4], bc, z_shape, z_app, l[:ds], l[ds:],
-                                 near, far, cx, cy, N_samples=N_samples, precision=precision)[1]
-    return _run(frame, H, W, poses.shape[0], bc_rgb, lat, group, gather)
+        both = render_head_torso(decoder, H, W, focal, poses[i, :3, :4], pose_torso[:3, :4], bc, z_shape, z_app, l[:ds], l[ds:],
+                                 near, far, cx, cy, N_samples=N_samples, precision=precision)
+        return torch.cat(both, 0) if with_head else both[1]
+    return _run(frame, H, W, poses.shape[0], bc_rgb, lat, group, gather, planes=2 if with_head else 1, on_frame=on_frame)
 
 
-def _run(render_one, H, W, n_frames, bc_rgb, latents, group, gather):
+def _run(render_one, H, W, n_frames, bc_rgb, latents, group, gather, planes=1, on_frame=None):
     if not bc_rgb.is_cuda:
         raise DfnError('dfa_nerf_b200 has no CPU path: bc_rgb must be a CUDA tensor')
     device = bc_rgb.device
@@ -93,18 +110,24 @@ def _run(render_one, H, W, n_frames, bc_rgb, latents, group, gather):
     f0, f1 = shard_frames(n_frames, rank, world)
     lat_dev = latents.to(device, torch.float32).contiguous() if latents is not None else None   # one upload for the sequence
     bc = bc_rgb.reshape(-1, 3)
+    squeeze = (lambda t: t[:, 0]) if planes == 1 else (lambda t: t)
     if world > 1 and gather:
         # frames stay on the device until the one all-gather at the end (uint8: 3 bytes per pixel on the wire); ragged
         # blocks are padded to the largest and trimmed afterwards
         per = (n_frames + world - 1) // world
-        tile = torch.zeros((per, H, W, 3), dtype=torch.uint8, device=device)
+        tile = torch.zeros((per, planes, H, W, 3), dtype=torch.uint8, device=device)
         for i in range(f0, f1):
-            tile[i - f0].copy_(to8b(render_one(i, bc, lat_dev[i] if lat_dev is not None else None)).reshape(H, W, 3))
-        full = torch.empty((world * per, H, W, 3), dtype=torch.uint8, device=device)
+            tile[i - f0].copy_(to8b(render_one(i, bc, lat_dev[i] if lat_dev is not None else None)).reshape(planes, H, W, 3))
+        full = torch.empty((world * per, planes, H, W, 3), dtype=torch.uint8, device=device)
         dist.all_gather_into_tensor(full, tile, group=group)
         blocks = [shard_frames(n_frames, r, world) for r in range(world)]
-        return torch.cat([full[r * per:r * per + (e - b)] for r, (b, e) in enumerate(blocks)], 0).cpu()
-    sink = FrameSink(max(f1 - f0, 1), H, W, device)
+        out = torch.cat([full[r * per:r * per + (e - b)] for r, (b, e) in enumerate(blocks)], 0).cpu()
+        if on_frame is not None:
+            for i in range(f0, f1):
+                on_frame(i, out[i].numpy())
+        return squeeze(out)
+    sink = FrameSink(max(f1 - f0, 1), H, W, device, planes=planes,
+                     on_frame=(lambda k, fr: on_frame(f0 + k, fr)) if on_frame is not None else None)
     for i in range(f0, f1):
         sink.push(render_one(i, bc, lat_dev[i] if lat_dev is not None else None))
     return sink.finish()[:f1 - f0]
