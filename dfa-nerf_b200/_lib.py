@@ -151,12 +151,13 @@ def ptr(t):
 
 
 class Workspace:
-    """Grow-only device scratch buffer per (device, tag); avoids allocator traffic per call."""
+    """Grow-only device scratch buffer per (device, stream, tag); avoids allocator traffic per call.  Keyed by the
+    current stream as well, so calls issued on different streams never share scratch memory."""
     _bufs = {}
 
     @classmethod
     def get(cls, nbytes, device, tag='default'):
-        key = (str(device), tag)
+        key = (str(device), torch.cuda.current_stream(device).cuda_stream, tag)
         buf = cls._bufs.get(key)
         if buf is None or buf.numel() < nbytes:
             buf = torch.empty(int(nbytes) + 256, dtype=torch.uint8, device=device)

@@ -329,6 +329,8 @@ static int query_points_impl(const dfn_model* m, int64_t R, int S, const float* 
     set_error("dfn_query_points: model has no weights");
     return DFN_E_STATE;
   }
+  DFN_CHECK_ARG(m->desc.dim_aud == 0 || latent != nullptr, "dfn_query_points: this model needs a latent of %d floats",
+                m->desc.dim_aud);
   if (precision == DFN_PREC_FP32)
     return fp32_query_points(m, R, S, rays_o, rays_d, viewdirs, z_vals, latent, raw, workspace, workspace_bytes, st);
   if (precision != DFN_PREC_BF16 && precision != DFN_PREC_BF16X3 && precision != DFN_PREC_FP16) {
