@@ -122,7 +122,7 @@ def dataset_to_device(data, device, near=None, far=None):
     for k in ('poses', 'auds', 'exp'):
         if out.get(k) is not None:
             out[k] = torch.from_numpy(np.ascontiguousarray(out[k])).to(device, torch.float32)
-    out['bc_img'] = torch.from_numpy(np.ascontiguousarray(data['bc_img'])).to(device).float() / 255.0
+    out['bc_img'] = torch.from_numpy(np.array(data['bc_img'])).to(device).float() / 255.0    # copy: Pillow's array is read-only
     if near is not None:
         out['near'], out['far'] = near, far
     return out
