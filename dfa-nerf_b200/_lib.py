@@ -99,9 +99,9 @@ def _load():
         'dfn_decoder_macs_per_sample': (C.c_double, [vp, i32]),
         'dfn_model_program_host': (i32, [vp, C.POINTER(vp), i32, i32, C.POINTER(LayerInfo), C.POINTER(i32), vp, vp,
                                          C.POINTER(i32), vp, vp, vp]),
-        'dfn_decoder_program_host': (i32, [C.POINTER(DecoderDesc), C.POINTER(vp), i32, i32, i32, C.POINTER(LayerInfo),
+        'dfn_decoder_program_host': (i32, [C.POINTER(DecoderDesc), C.POINTER(vp), i32, i32, i32, i32, C.POINTER(LayerInfo),
                                            C.POINTER(i32), vp, vp, C.POINTER(i32), C.POINTER(i32), vp, C.POINTER(i32),
-                                           C.POINTER(i32)]),
+                                           C.POINTER(i32), vp]),
         'dfn_render_head_torso_workspace_bytes': (i64, [vp, i64, i32]),
         'dfn_render_head_torso': (i32, [vp, i64, i32, C.POINTER(HeadTorsoIO), i32, vp, i64, vp]),
     }

@@ -15,6 +15,9 @@
 //     output `deform_net(p) + p` (DEC:299) is an identity block in the output layer's weights.
 // The torso's deformed signal is per-sample, so it is a real (staged) input block: layers that read both staged
 // blocks are split in two accumulate-chained halves (TC_EPI_CONT, TC_F_ACCUM).
+// Each field is compiled twice: the plain program (bf16x3 kernel) keeps sigma_out as a 16-column MMA layer; the
+// "folded-head" program of the single-pass kernels evaluates it on the CUDA cores inside the epilogue of blocks[6]
+// (TC_F_DOT_SIGMA) -- one layer fewer on every tile's dependency chain.
 #include <math.h>
 #include <string.h>
 
@@ -42,6 +45,7 @@ struct DecField {
   float* fold_w = nullptr;   // [n_fold][dimL][256]: bias[layer][n] += sum_j fold_w[f][j][n] * latent[j]
   int dimL = 0;              // latent = [signal | z_shape | z_app]
   int view_layer = -1;
+  float* dot_w = nullptr;    // folded-head program: sigma_out row [256] + its bias (TC_DOT_FLOATS)
   double macs_pt = 0.0;      // algorithmic MACs per sample with the per-frame / per-ray terms folded
 };
 
@@ -50,7 +54,8 @@ struct DecField {
 struct dfn_decoder {
   dfn_decoder_desc desc;
   bool loaded = false;
-  dfn::DecField f[2];        // 0 head, 1 torso
+  dfn::DecField f[2];        // 0 head, 1 torso: plain programs (bf16x3)
+  dfn::DecField g[2];        // the same fields with sigma_out folded into an epilogue (bf16 / fp16)
 };
 
 namespace dfn {
@@ -123,6 +128,7 @@ struct Builder {
   DecField* F;
   std::vector<float> bias;                 // [TC_MAX_LAYERS][256]
   std::vector<std::vector<float>> folds;   // each [dimL][256]
+  std::vector<float> dot;                  // folded heads (TC_DOT_FLOATS) or empty
   int nl = 0;
   explicit Builder(DecField* f, int dimL) : F(f), bias((size_t)TC_MAX_LAYERS * TC_BIAS_STRIDE, 0.f) {
     pk.want64 = false;
@@ -168,6 +174,10 @@ struct Builder {
     DFN_CUDA(cudaMemcpyAsync(F->w_lo, pk.lo32.data(), pk.lo32.size(), cudaMemcpyHostToDevice, st));
     DFN_CUDA(cudaMemcpyAsync(F->bias, bias.data(), bias.size() * 4, cudaMemcpyHostToDevice, st));
     DFN_CUDA(cudaMemcpyAsync(F->fold_w, fw.data(), fw.size() * 4, cudaMemcpyHostToDevice, st));
+    if (!dot.empty()) {
+      DFN_CUDA(cudaMalloc(&F->dot_w, dot.size() * 4));
+      DFN_CUDA(cudaMemcpyAsync(F->dot_w, dot.data(), dot.size() * 4, cudaMemcpyHostToDevice, st));
+    }
     DFN_CUDA(cudaStreamSynchronize(st));
     return 0;
   }
@@ -188,13 +198,15 @@ static void free_field(DecField& F) {
   F.w_h16 = nullptr;
   cudaFree(F.bias);
   cudaFree(F.fold_w);
+  cudaFree(F.dot_w);
   F.w_hi = F.w_lo = nullptr;
-  F.bias = F.fold_w = nullptr;
+  F.bias = F.fold_w = F.dot_w = nullptr;
 }
 
 // Layers shared by both fields from fc_in on.  The field's point input occupies the staged blocks
 // (head: PE; torso: PE', signal').  lat offsets: z_shape at zs0, z_app at za0 inside the latent vector.
-static void build_trunk(Builder& B, const std::vector<Lin>& T, const dfn_decoder_desc& d, bool torso, int zs0, int za0) {
+static void build_trunk(Builder& B, const std::vector<Lin>& T, const dfn_decoder_desc& d, bool torso, int zs0, int za0,
+                        bool fold_heads) {
   const int H = d.hidden, de = 6 * d.n_freq;
   const Lin& fcin = T[torso ? T_FCIN_TORSO : T_FCIN];
   const Lin& pskip = T[torso ? T_FCPSKIP_TORSO : T_FCPSKIP];
@@ -224,7 +236,9 @@ static void build_trunk(Builder& B, const std::vector<Lin>& T, const dfn_decoder
   for (int i = 0; i < nb; ++i) {
     const Lin& blk = T[T_BLOCK0 + i];
     if (i != d.skip) {
-      l = B.layer(H, TC_EPI_RELU, 0, {0, 1, 2, 3}, [&](int n, int kbi, int k) { return blk.W(n, kbi * 64 + k); });
+      // folded head: the last block's epilogue also forms sigma_out . relu(out)
+      l = B.layer(H, TC_EPI_RELU, (fold_heads && i == nb - 1) ? TC_F_DOT_SIGMA : 0, {0, 1, 2, 3},
+                  [&](int n, int kbi, int k) { return blk.W(n, kbi * 64 + k); });
       for (int n = 0; n < H; ++n) B.b(l, n) = blk.b[n];
       B.F->macs_pt += (double)H * H;
       continue;
@@ -258,8 +272,14 @@ static void build_trunk(Builder& B, const std::vector<Lin>& T, const dfn_decoder
     }
     B.F->macs_pt += (double)H * H + (double)H * (de + (torso ? dsig : 0));
   }
-  // ---- sigma_out (DEC:329): 16-column layer, column 0 kept in a register
-  {
+  if (fold_heads) {   // sigma_out (DEC:329) rides the epilogue of the last block: its row and bias
+    const Lin& sg = T[T_SIGMA];
+    B.dot.assign(TC_DOT_FLOATS, 0.f);
+    for (int k = 0; k < H; ++k) B.dot[k] = sg.W(0, k);
+    B.dot[TC_BIAS_STRIDE] = sg.b[0];
+    B.F->macs_pt += H;
+  } else {
+    // ---- sigma_out (DEC:329): 16-column layer, column 0 kept in a register
     const Lin& sg = T[T_SIGMA];
     l = B.layer(16, TC_EPI_SIGMA, 0, {0, 1, 2, 3}, [&](int n, int kbi, int k) { return n == 0 ? sg.W(0, kbi * 64 + k) : 0.f; });
     B.b(l, 0) = sg.b[0];
@@ -419,7 +439,7 @@ static int dec_query(const dfn_decoder* m, int field, int64_t R, int S, const fl
     set_error("dfn_decoder_query: workspace %lld < %lld bytes", (long long)workspace_bytes, (long long)dec_workspace_bytes(m, R));
     return DFN_E_WORKSPACE;
   }
-  const DecField& F = m->f[field];
+  const DecField& F = precision == DFN_PREC_BF16X3 ? m->f[field] : m->g[field];   // single-pass kernels: folded heads
   const dfn_decoder_desc& d = m->desc;
   float* bias_ws = reinterpret_cast<float*>(workspace);
   void* scratch = reinterpret_cast<char*>(workspace) + align256((int64_t)TC_MAX_LAYERS * TC_BIAS_STRIDE * 4);
@@ -436,7 +456,7 @@ static int dec_query(const dfn_decoder* m, int field, int64_t R, int S, const fl
   dec_fold_kernel<<<F.prog.n_layers, TC_BIAS_STRIDE, 0, st>>>(F.prog.n_layers, F.dimL, F.bias, F.fold_w, fa, bias_ws);
   DFN_LAUNCH_CHECK();
   const bool prof = profile_begin(st, F.macs_pt * (double)R * S);
-  int rc = pp_launch_prog(F.prog, F.woff32, precision == DFN_PREC_FP16 ? F.w_h16 : F.w_hi, F.w_lo, true, d.n_freq, d.n_freq_views, d.hidden, bias_ws, nullptr, scratch, R, S, rays_o,
+  int rc = pp_launch_prog(F.prog, F.woff32, precision == DFN_PREC_FP16 ? F.w_h16 : F.w_hi, F.w_lo, F.dot_w, true, d.n_freq, d.n_freq_views, d.hidden, bias_ws, nullptr, scratch, R, S, rays_o,
                           rays_d, z_vals, raw, precision, st);
   if (prof) profile_end(st);
   if (rc) return rc;
@@ -469,8 +489,10 @@ extern "C" int dfn_decoder_create(const dfn_decoder_desc* desc, dfn_decoder** ou
 
 extern "C" void dfn_decoder_destroy(dfn_decoder* m) {
   if (!m) return;
-  free_field(m->f[0]);
-  free_field(m->f[1]);
+  for (int i = 0; i < 2; ++i) {
+    free_field(m->f[i]);
+    free_field(m->g[i]);
+  }
   delete m;
 }
 
@@ -485,21 +507,26 @@ extern "C" int dfn_decoder_load(dfn_decoder* m, const float* const* t, int n_ten
   const int dt = d.dim_et_embed;
   const std::vector<Lin> T = tensor_table(d, t);
 
-  free_field(m->f[0]);
-  free_field(m->f[1]);
-  m->loaded = false;
-  {
-    Builder B(&m->f[0], d.dim_signal + 2 * d.z_dim);
-    build_trunk(B, T, d, false, d.dim_signal, d.dim_signal + d.z_dim);
-    int rc = B.upload(st);
-    if (rc) return rc;
+  for (int i = 0; i < 2; ++i) {
+    free_field(m->f[i]);
+    free_field(m->g[i]);
   }
-  {
-    Builder B(&m->f[1], dt + 2 * d.z_dim);
-    build_deform(B, T, d);
-    build_trunk(B, T, d, true, dt, dt + d.z_dim);
-    int rc = B.upload(st);
-    if (rc) return rc;
+  m->loaded = false;
+  for (int folded = 0; folded < 2; ++folded) {
+    DecField* F = folded ? m->g : m->f;
+    {
+      Builder B(&F[0], d.dim_signal + 2 * d.z_dim);
+      build_trunk(B, T, d, false, d.dim_signal, d.dim_signal + d.z_dim, folded != 0);
+      int rc = B.upload(st);
+      if (rc) return rc;
+    }
+    {
+      Builder B(&F[1], dt + 2 * d.z_dim);
+      build_deform(B, T, d);
+      build_trunk(B, T, d, true, dt, dt + d.z_dim, folded != 0);
+      int rc = B.upload(st);
+      if (rc) return rc;
+    }
   }
   m->loaded = true;
   return 0;
@@ -507,12 +534,14 @@ extern "C" int dfn_decoder_load(dfn_decoder* m, const float* const* t, int n_ten
 
 // Host-only: the layer program dfn_decoder_load builds for one field, as dense fp32 (no CUDA calls).
 extern "C" int dfn_decoder_program_host(const dfn_decoder_desc* desc, const float* const* t, int n_tensors, int field,
-                                        int max_layers, dfn_layer_info* layers, int* n_layers, float* weights, float* bias,
-                                        int* n_fold, int* fold_layer, float* fold_w, int* dimL, int* view_layer) {
+                                        int folded_heads, int max_layers, dfn_layer_info* layers, int* n_layers, float* weights,
+                                        float* bias, int* n_fold, int* fold_layer, float* fold_w, int* dimL, int* view_layer,
+                                        float* dot_w) {
   DFN_CHECK_ARG(desc && t && layers && n_layers && weights && bias && n_fold && fold_layer && fold_w && dimL && view_layer,
                 "dfn_decoder_program_host: null argument");
   DFN_CHECK_ARG(n_tensors == 2 * T_COUNT && (field == 0 || field == 1) && max_layers >= TC_MAX_LAYERS,
                 "dfn_decoder_program_host: expected %d tensors, field 0|1, max_layers >= %d", 2 * T_COUNT, TC_MAX_LAYERS);
+  DFN_CHECK_ARG(!folded_heads || dot_w, "dfn_decoder_program_host: dot_w is required for the folded-head program");
   DFN_CHECK_ARG(desc->hidden == 256 && desc->n_blocks == 8 && desc->skip == 4 && desc->n_freq >= 1 && desc->n_freq <= 10 &&
                     desc->dim_et_embed >= 1 && desc->dim_et_embed <= 64,
                 "dfn_decoder_program_host: unsupported decoder shape");
@@ -523,7 +552,8 @@ extern "C" int dfn_decoder_program_host(const dfn_decoder_desc* desc, const floa
   std::vector<float> dense;
   B.pk.dense = &dense;
   if (field == 1) build_deform(B, T, *desc);
-  build_trunk(B, T, *desc, field == 1, dsig, dsig + desc->z_dim);
+  build_trunk(B, T, *desc, field == 1, dsig, dsig + desc->z_dim, folded_heads != 0);
+  if (folded_heads) memcpy(dot_w, B.dot.data(), B.dot.size() * 4);
   *n_layers = B.nl;
   for (int l = 0; l < B.nl; ++l) {
     const TcLayer& L = F.prog.layers[l];

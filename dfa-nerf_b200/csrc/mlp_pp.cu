@@ -46,7 +46,8 @@ static constexpr int ARENA_BLOCKS = 8;          // bf16: 2 tiles x 4 blocks; bf1
 static constexpr int SMEM_RING = ARENA_BLOCKS * KB_BYTES;
 static constexpr int SMEM_BIAS = SMEM_RING + N_ENTRIES * 2 * SLOT_BYTES;
 static constexpr int SMEM_BAR = SMEM_BIAS + 2 * TC_BIAS_STRIDE * 4;
-static constexpr int SMEM_TOTAL = SMEM_BAR + 256;
+static constexpr int SMEM_DOT = SMEM_BAR + 256;   // density-head row as packed 16-bit pairs (TC_F_DOT_SIGMA), 512 bytes
+static constexpr int SMEM_TOTAL = SMEM_DOT + 512;
 static_assert(SMEM_TOTAL <= 227 * 1024, "shared memory budget");
 static constexpr int EPI_THREADS = 256;
 static constexpr int PE_THREADS = 64;   // warps 2-3: two rows per thread and slot
@@ -56,6 +57,7 @@ struct Params {
   const uint8_t* w_lo;
   const float* bias;       // [n_layers][256], latent already folded
   const float* view_bias;  // [R][W/2]
+  const float* dot_w;      // Decoder density head folded into an epilogue (TC_F_DOT_SIGMA): row [256] + bias, or null
   const float* rays_o;
   const float* rays_d;
   const float* z_vals;
@@ -386,6 +388,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1) mlp_pp_kerne
     uint8_t* arena_lo = arena_hi;  // unused in bf16
     float* bias_g = bias_s + s * TC_BIAS_STRIDE;
     const uint32_t sbias = smem_u32(bias_g);
+    const uint32_t sdot = sbase + SMEM_DOT;
+    if (DEC && !X3 && P.dot_w != nullptr) {
+      // each slot group writes the whole row (identical values), so its own barrier below orders it before its reads
+      const float2 w2 = reinterpret_cast<const float2*>(P.dot_w)[et];
+      reinterpret_cast<uint32_t*>(smem + SMEM_DOT)[et] = F16 ? pack_f16(w2.x, w2.y) : pack_bf16(w2.x, w2.y);
+    }
     uint32_t acc_par = 0u;
     int pe_waited_j = -1;
     int last_pe_layer = 0;
@@ -495,6 +503,21 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1) mlp_pp_kerne
             if (cc + 2 < nch) tmem_ld32(acc + (cc + 2) * 32, v0);
             stage_chunk<X3, F16>(v1, cc + 1, sbias, scr(j & 1, s, (cc + 1) >> 1), row);
           }
+        } else if (DEC && !X3 && (L.flags & TC_F_DOT_SIGMA)) {
+          // last trunk block + sigma_out (DEC:329): the usual epilogue, and the density from its fp32 activations
+          const int nch = (int)L.n >> 5;
+          float d4[4] = {0.f, 0.f, 0.f, 0.f};
+          uint32_t v0[32], v1[32];
+          tmem_ld32(acc, v0);
+          for (int cc = 0; cc < nch; cc += 2) {
+            tmem_ld_wait();
+            tmem_ld32(acc + (cc + 1) * 32, v1);
+            epilogue_chunk_dot1<F16>(v0, cc, sbias, sdot, arena_hi, row, d4);
+            tmem_ld_wait();
+            if (cc + 2 < nch) tmem_ld32(acc + (cc + 2) * 32, v0);
+            epilogue_chunk_dot1<F16>(v1, cc + 1, sbias, sdot, arena_hi, row, d4);
+          }
+          alpha = (d4[0] + d4[1]) + (d4[2] + d4[3]) + P.dot_w[TC_BIAS_STRIDE];
         } else {
           const bool per_ray = L.epi == TC_EPI_VIEW0;
           const int nch = (per_ray ? P.view_w : (int)L.n) >> 5;   // 32-column chunks: 8 or 4
@@ -849,8 +872,8 @@ static int pp_launch_t(const pp::Params& P, int grid, cudaStream_t st) {
 
 // prog: layer program (woff32: per-layer offsets into the K=32 stage blobs w_hi / w_lo); decoder: Decoder programs
 // (DEC kernel instantiation, 256-wide per-ray view bias, PE of DEC:257-275 with n_freq = multires).
-int pp_launch_prog(const TcProgram& prog, const uint32_t* woff32, const uint8_t* w_hi, const uint8_t* w_lo, bool decoder,
-                   int multires, int multires_views, int view_w, const float* bias_ws, const float* vbias_ws, void* scratch, int64_t R, int S,
+int pp_launch_prog(const TcProgram& prog, const uint32_t* woff32, const uint8_t* w_hi, const uint8_t* w_lo, const float* dot_w,
+                   bool decoder, int multires, int multires_views, int view_w, const float* bias_ws, const float* vbias_ws, void* scratch, int64_t R, int S,
                    const float* rays_o, const float* rays_d, const float* z_vals, float* raw, int precision,
                    cudaStream_t st) {
   pp::Params P;
@@ -859,6 +882,7 @@ int pp_launch_prog(const TcProgram& prog, const uint32_t* woff32, const uint8_t*
   P.w_lo = w_lo;
   P.bias = bias_ws;
   P.view_bias = vbias_ws;
+  P.dot_w = dot_w;
   P.rays_o = rays_o;
   P.rays_d = rays_d;
   P.z_vals = z_vals;
@@ -880,6 +904,11 @@ int pp_launch_prog(const TcProgram& prog, const uint32_t* woff32, const uint8_t*
   grid = (grid + 1) & ~1;
   if (grid > num_sms()) grid = num_sms() & ~1;
   const bool x3 = precision == DFN_PREC_BF16X3;
+  for (int i = 0; i < prog.n_layers; ++i)
+    if ((prog.layers[i].flags & TC_F_DOT_SIGMA) && (x3 || !decoder || dot_w == nullptr)) {
+      set_error("pp_launch_prog: a program with a folded density head runs on the single-pass Decoder kernels only");
+      return DFN_E_STATE;
+    }
   if (precision == DFN_PREC_FP16) {   // w_hi: the fp16 stages (Decoder programs; FaceNeRF / NeRF use mlp_tc.cu)
     if (!decoder) {
       set_error("pp_launch_prog: DFN_PREC_FP16 is wired for the Decoder programs only");
@@ -894,7 +923,7 @@ int pp_launch_prog(const TcProgram& prog, const uint32_t* woff32, const uint8_t*
 int pp_launch(const dfn_model* m, const float* bias_ws, const float* vbias_ws, void* scratch, int64_t R, int S,
               const float* rays_o, const float* rays_d, const float* z_vals, float* raw, int precision,
               cudaStream_t st) {
-  return pp_launch_prog(m->prog, m->tc32_woff, m->tc_hi, m->tc_lo, false, m->desc.multires, m->desc.multires_views, m->desc.W / 2,
+  return pp_launch_prog(m->prog, m->tc32_woff, m->tc_hi, m->tc_lo, nullptr, false, m->desc.multires, m->desc.multires_views, m->desc.W / 2,
                         bias_ws, vbias_ws,
                         scratch, R, S, rays_o, rays_d, z_vals, raw, precision, st);
 }

@@ -32,7 +32,14 @@ enum {
   TC_EPI_CONT = 4,   // no epilogue: the next layer accumulates onto this one's partial sums (second staged input)
   TC_EPI_STAGE = 5   // + bias, no activation -> staged blocks PE / IN1 of the tile (deformation output, DEC:299)
 };
-enum { TC_F_ACCUM = 1 };  // TcLayer.flags: the first MMA accumulates (layer continues a TC_EPI_CONT layer)
+enum {
+  TC_F_ACCUM = 1,      // TcLayer.flags: the first MMA accumulates (layer continues a TC_EPI_CONT layer)
+  // Decoder, single-pass precisions: sigma_out (DEC:329) is evaluated on the CUDA cores inside the epilogue of the block
+  // that produces its input -- an M=128 x K=16 MMA costs the same for N=16 as for N=256, and every layer is one more
+  // MMA -> epilogue -> barrier step on the tile's dependency chain.  dot_w = the head row [256] + its bias.
+  TC_F_DOT_SIGMA = 2   // TC_EPI_RELU layer: density register = dot_w[0..255] . relu(out) + dot_w[256]
+};
+static constexpr int TC_DOT_FLOATS = 256 + 4;
 static constexpr int TC_MAX_LAYERS = 20;
 static constexpr int TC_BIAS_STRIDE = 256;  // floats per layer in the bias blob
 
@@ -95,7 +102,7 @@ void tc_get_trace(void** dev_ptr, int* tiles);
 void tc_set_impl(int impl);  // 2: ping-pong + cooperative epilogue (mlp_pp.cu, default); 1: mlp_tc.cu; 0: mlp_ts.cu
 int64_t pp_scratch_bytes();
 int64_t pp_dec_scratch_bytes();
-int pp_launch_prog(const TcProgram& prog, const uint32_t* woff32, const uint8_t* w_hi, const uint8_t* w_lo, bool decoder,
+int pp_launch_prog(const TcProgram& prog, const uint32_t* woff32, const uint8_t* w_hi, const uint8_t* w_lo, const float* dot_w, bool decoder,
                    int multires, int multires_views, int view_w, const float* bias_ws, const float* vbias_ws, void* scratch, int64_t R, int S,
                    const float* rays_o, const float* rays_d, const float* z_vals, float* raw, int precision,
                    cudaStream_t st);

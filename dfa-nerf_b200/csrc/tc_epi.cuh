@@ -71,6 +71,31 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[32], int chun
   }
 }
 
+// Decoder density head on the CUDA cores (TC_F_DOT_SIGMA, single-pass precisions): epilogue_chunk with one extra FMA
+// per element, dot[] += relu(v + bias) * w[column] on the fp32 activations, four partial sums.  sdot: the head row in
+// shared memory as packed bf16 / fp16 pairs (the precision the MMA path gives its weights; 512 bytes is what is left).
+template <bool F16>
+__device__ __forceinline__ void epilogue_chunk_dot1(const uint32_t (&v)[32], int chunk32, uint32_t sbias, uint32_t sdot,
+                                                    uint8_t* arena_hi, uint32_t row, float (&dot)[4]) {
+  uint8_t* dst_hi = arena_hi + (size_t)(chunk32 >> 1) * KB_BYTES;
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    const int c = chunk32 * 32 + g * 8;
+    float b[8], w[8], x[8];
+    uint32_t wp[4];
+    lds_f32x8(sbias + (uint32_t)c * 4u, b);
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(wp[0]), "=r"(wp[1]), "=r"(wp[2]), "=r"(wp[3]) : "r"(sdot + (uint32_t)c * 2u));
+#pragma unroll
+    for (int q = 0; q < 4; ++q) unpack_h2<F16>(wp[q], w[2 * q], w[2 * q + 1]);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      x[e] = fmaxf(__uint_as_float(v[g * 8 + e]) + b[e], 0.f);
+      dot[e & 3] = fmaf(x[e], w[e], dot[e & 3]);
+    }
+    store_chunk<false, F16>(dst_hi, dst_hi, row, (uint32_t)((chunk32 & 1) * 4 + g), x);
+  }
+}
+
 // Accumulator columns [0, ncols) of this thread's row -> next layer's activation blocks.  The TMEM load of
 // chunk c+1 is in flight while chunk c is processed (tcgen05.wait::ld waits for all outstanding loads).
 template <bool X3, bool GLOBAL_BIAS, bool F16 = false>

@@ -212,6 +212,16 @@ __device__ __forceinline__ void ldg_f32x8(const float* g, float (&b)[8]) {
   asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(b[0]), "=f"(b[1]), "=f"(b[2]), "=f"(b[3]) : "l"(g));
   asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(b[4]), "=f"(b[5]), "=f"(b[6]), "=f"(b[7]) : "l"(g + 4));
 }
+// two packed 16-bit floats (bf16 or fp16) -> fp32
+template <bool F16>
+__device__ __forceinline__ void unpack_h2(uint32_t u, float& lo, float& hi) {
+  if (F16) {
+    asm("{.reg .f16 l, h; mov.b32 {l, h}, %2; cvt.f32.f16 %0, l; cvt.f32.f16 %1, h;}" : "=f"(lo), "=f"(hi) : "r"(u));
+  } else {
+    lo = __uint_as_float(u << 16);
+    hi = __uint_as_float(u & 0xffff0000u);
+  }
+}
 // relu(a + b) for two adjacent columns -> packed bf16x2 (FADD2 + F2FP.RELU.BF16.PACK_AB: one instruction per element)
 __device__ __forceinline__ uint32_t add_relu_pack(uint32_t a0, uint32_t a1, float b0, float b1) {
   uint64_t a, b, c;

@@ -216,7 +216,9 @@ double dfn_decoder_macs_per_sample(const dfn_decoder* m, int field);
 /* Host-only introspection (no CUDA calls; used by the CPU tests): the layer program dfn_decoder_load compiles for one
  * field.  layers[l]: output columns n, input K-blocks kb[0..nkb) (0..3 hidden blocks, 4 = positional encoding / deformed
  * encoding, 5 = deformed signal, 6 = view-direction encoding), epilogue (0 relu, 1 per-ray-bias relu, 2 rgb+sigmoid, 3 sigma, 4 continue, 5 write
- * staged blocks) and flags (1 = accumulates onto the previous layer).  weights: dense fp32 [max_layers][256][6*64]
+ * staged blocks) and flags (1 = accumulates onto the previous layer; 2 = folded-head program: the epilogue also forms the
+ * density dot_w[0..255] . relu(out) + dot_w[256]).  folded_heads = 0: the program of DFN_PREC_BF16X3 (sigma_out as a
+ * 16-column layer); 1: the program of DFN_PREC_BF16 / DFN_PREC_FP16, with dot_w [260] filled.  weights: dense fp32 [max_layers][256][6*64]
  * (row n, input block slot i, position k), bias [max_layers][256], fold_w [n_fold][dimL][256] with
  * bias[fold_layer[i]][n] += sum_j fold_w[i][j][n] * latent[j], latent = [signal | z_shape | z_app].
  * max_layers >= 20; fold_layer has 8 entries; fold_w holds 8*dimL*256 floats (dimL <= 1024). */
@@ -225,8 +227,9 @@ typedef struct {
   int kb[6];
 } dfn_layer_info;
 int dfn_decoder_program_host(const dfn_decoder_desc* desc, const float* const* tensors_host, int n_tensors, int field,
-                             int max_layers, dfn_layer_info* layers, int* n_layers, float* weights, float* bias,
-                             int* n_fold, int* fold_layer, float* fold_w, int* dimL, int* view_layer);
+                             int folded_heads, int max_layers, dfn_layer_info* layers, int* n_layers, float* weights,
+                             float* bias, int* n_fold, int* fold_layer, float* fold_w, int* dimL, int* view_layer,
+                             float* dot_w);
 
 /* The same for a FaceNeRF / NeRF model (m: created, weights not needed): layers as above (epilogue 1 = views_linears.0
  * with the density head as column W/2 and the per-ray view term as bias); fold_layer[2] / fold_w [2][W][dim_aud]: the

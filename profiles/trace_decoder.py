@@ -26,7 +26,7 @@ zs, za = torch.randn(1, 256, generator=g).to(dev), torch.randn(1, 256, generator
 sig = (torch.randn(1, 96, generator=g) if which == 'head' else torch.randn(1, 42, generator=g)).to(dev)
 prec = {'bf16': dfn.PREC_BF16, 'bf16x3': dfn.PREC_BF16X3, 'fp16': dfn.PREC_FP16}[mode]
 dec.query_rays(ro, rd, z, zs, za, sig, which, precision=prec)
-T, NL = 5, 11 if which == 'head' else 19
+T, NL = 5, (11 if which == "head" else 19) - (0 if mode == "bf16x3" else 1)   # single-pass programs: sigma_out folded
 buf = torch.zeros(2 * T * NL * 8, dtype=torch.int64, device=dev)
 dfn.lib.dfn_debug_trace(C.c_void_p(buf.data_ptr()), T)
 dec.query_rays(ro, rd, z, zs, za, sig, which, precision=prec)

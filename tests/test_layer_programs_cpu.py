@@ -12,6 +12,7 @@ from oracle import synth
 
 EPI_RELU, EPI_VIEW0, EPI_RGB, EPI_SIGMA, EPI_CONT, EPI_STAGE = range(6)
 KB_PE, KB_IN1, KB_DIR = 4, 5, 6
+F_ACCUM, F_DOT_SIGMA = 1, 2
 ORDER = (['deform_net.blocks_embed.%d' % i for i in range(5)] + ['deform_net.out_embed'] +
          ['deform_net.blocks_signal.%d' % i for i in range(5)] + ['deform_net.out_signal', 'deform_net.fc_embed_skips.0',
                                                                   'deform_net.fc_signal_skips.0', 'fc_in', 'fc_in_torso', 'fc_z'] +
@@ -19,7 +20,7 @@ ORDER = (['deform_net.blocks_embed.%d' % i for i in range(5)] + ['deform_net.out
                                                 'feat_view', 'fc_view', 'feat_out'])
 
 
-def dump_program(sd, field):
+def dump_program(sd, field, folded=0):
     from dfa_nerf_b200 import _lib
     host = []
     for name in ORDER:
@@ -33,18 +34,20 @@ def dump_program(sd, field):
     bias = np.zeros((ML, 256), np.float32)
     fold_layer = (C.c_int * 8)()
     fold_w = np.zeros((8, 1024 * 256), np.float32)
-    rc = _lib.lib.dfn_decoder_program_host(C.byref(desc), arr, len(host), field, ML, layers, C.byref(n_layers),
+    dot_w = np.zeros(256 + 4, np.float32)
+    rc = _lib.lib.dfn_decoder_program_host(C.byref(desc), arr, len(host), field, folded, ML, layers, C.byref(n_layers),
                                            weights.ctypes.data_as(C.c_void_p), bias.ctypes.data_as(C.c_void_p), C.byref(n_fold),
-                                           fold_layer, fold_w.ctypes.data_as(C.c_void_p), C.byref(dimL), C.byref(view_layer))
+                                           fold_layer, fold_w.ctypes.data_as(C.c_void_p), C.byref(dimL), C.byref(view_layer),
+                                           dot_w.ctypes.data_as(C.c_void_p))
     assert rc == 0, _lib.lib.dfn_last_error()
     dl = dimL.value
     folds = {fold_layer[i]: fold_w.reshape(-1)[i * dl * 256:(i + 1) * dl * 256].reshape(dl, 256) for i in range(n_fold.value)}
-    return [layers[i] for i in range(n_layers.value)], weights, bias, folds, dl, view_layer.value
+    return [layers[i] for i in range(n_layers.value)], weights, bias, folds, dl, view_layer.value, dot_w.astype(np.float64)
 
 
 def run_program(prog, pe, latent, pe_dir):
     """pe [P,60] fp64, latent [dimL], pe_dir [P,24] = PE(dir/|dir|) (staged block TC_KB_DIR) -> (feat [P,3], sigma [P])."""
-    layers, weights, bias, folds, dimL, view_layer = prog
+    layers, weights, bias, folds, dimL, view_layer, dot_w = prog
     P = pe.shape[0]
     blocks = {k: np.zeros((P, 64)) for k in range(7)}
     blocks[KB_PE][:, :60] = pe
@@ -58,11 +61,13 @@ def run_program(prog, pe, latent, pe_dir):
         if l in folds:
             b = b + folds[l][:, :n].astype(np.float64).T @ latent
         out = x @ W.T
-        acc = acc + out if (L.flags & 1) else out
+        acc = acc + out if (L.flags & F_ACCUM) else out
         if L.epi == EPI_CONT:
             continue
         if L.epi == EPI_RELU:
             h = np.maximum(acc + b, 0.)
+            if L.flags & F_DOT_SIGMA:        # folded head: density from this layer's activations
+                sigma = h @ dot_w[:256] + dot_w[256]
         elif L.epi == EPI_VIEW0:
             raise AssertionError('the Decoder programs carry the view term as a K-block, not as a per-ray bias')
         elif L.epi == EPI_SIGMA:
@@ -93,10 +98,12 @@ def test_decoder_layer_programs_compute_the_reference_forward():
         pe = O.decoder_transform_points(p.double(), 10)[0].numpy()
         d = rd.double() / torch.norm(rd.double(), dim=-1, keepdim=True)
         pe_dir = O.decoder_transform_points(d, 4)[0].numpy()
-        for field, which in ((0, 'head'), (1, 'torso')):
-            prog = dump_program(sd, field)
+        for field, which, folded in ((0, 'head', 0), (1, 'torso', 0), (0, 'head', 1), (1, 'torso', 1)):
+            prog = dump_program(sd, field, folded)
             n_layers = len(prog[0])
-            assert n_layers == (11 if field == 0 else 19)
+            assert n_layers == (11 if field == 0 else 19) - folded
+            assert [L.flags & F_DOT_SIGMA for L in prog[0]].count(F_DOT_SIGMA) == folded
+            assert all(L.epi != EPI_SIGMA for L in prog[0]) == bool(folded)
             latent = torch.cat([sig[field].reshape(-1), zs.reshape(-1), za.reshape(-1)]).double().numpy()
             assert prog[4] == latent.shape[0]
             assert prog[0][prog[5]].kb[0] == KB_DIR          # the view layer stages the direction encoding
