@@ -37,7 +37,7 @@ def test_render_person_directory_to_jpegs(tmp_path):
     assert os.path.getsize(tmp_path / 'person.mp4') > 0
 
     H, W, focal, cx, cy = data['hwfcxy']
-    bc = torch.from_numpy(data['bc_img']).float().reshape(-1, 3) / 255.0
+    bc = torch.from_numpy(np.array(data['bc_img'])).float().reshape(-1, 3) / 255.0
     poses, auds, exps = [torch.from_numpy(data[k]) for k in ('poses', 'auds', 'exp')]
     rot, rdt = [t.reshape(-1, 3) for t in O.get_rays(H, W, focal, body[:3, :4], cx, cy)]
     z = O.z_vals_uniform(torch.full((H * W, 1), near), torch.full((H * W, 1), far), 64)

@@ -117,6 +117,22 @@ def test_decoder_layer_programs_compute_the_reference_forward():
 
 def test_program_host_argument_checks():
     from dfa_nerf_b200 import _lib
+    # the folded-head program needs somewhere to put the head row
+    sd = synth.decoder_state_dict(3)
+    host = []
+    for name in ORDER:
+        host += [sd[name + '.weight'].contiguous().float(), sd[name + '.bias'].contiguous().float()]
+    arr = (C.c_void_p * len(host))(*[t.data_ptr() for t in host])
+    d0 = _lib.DecoderDesc(256, 256, 96, 42, 10, 4, 8, 4)
+    layers = (_lib.LayerInfo * 20)()
+    n = C.c_int()
+    w, b, fw = np.zeros((20, 256, 6, 64), np.float32), np.zeros((20, 256), np.float32), np.zeros((8, 1024 * 256), np.float32)
+    fl = (C.c_int * 8)()
+    args = [C.byref(d0), arr, len(host), 0, 1, 20, layers, C.byref(n), w.ctypes.data_as(C.c_void_p), b.ctypes.data_as(C.c_void_p),
+            C.byref(C.c_int()), fl, fw.ctypes.data_as(C.c_void_p), C.byref(C.c_int()), C.byref(C.c_int())]
+    assert _lib.lib.dfn_decoder_program_host(*args, None) == -1 and b'dot_w' in _lib.lib.dfn_last_error()
+    assert _lib.lib.dfn_decoder_program_host(*args[:4], 0, *args[5:], None) == 0       # plain program: dot_w not needed
+    assert n.value == 11
     desc = _lib.DecoderDesc(128, 256, 96, 42, 10, 4, 8, 4)      # hidden 128: outside the tcgen05 coverage
     h = C.c_void_p()
     assert _lib.lib.dfn_decoder_create(C.byref(desc), C.byref(h)) == -1
