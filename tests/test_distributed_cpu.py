@@ -75,3 +75,48 @@ def test_shard_frames_partition():
             sizes = [e - b for b, e in blocks]
             assert max(sizes) - min(sizes) <= 1 and sum(sizes) == n
     assert shard_frames(300, 7, 8) == (263, 300) and shard_frames(300, 0, 8) == (0, 38)
+
+
+def _frame(i, H=12, W=10):
+    import numpy as np
+    y, x = np.mgrid[0:H, 0:W]
+    return np.stack([(x * 20 + i) % 256, (y * 15 + 2 * i) % 256, np.full_like(x, (40 * i) % 256)], -1).astype(np.uint8)
+
+
+def _writer_worker(rank, world, port, n_frames, out_dir):
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        from dfa_nerf_b200.sequence import shard_frames
+        from dfa_nerf_b200.frame_io import FrameWriter
+        b, e = shard_frames(n_frames, dist.get_rank(), dist.get_world_size())
+        w = FrameWriter(os.path.join(out_dir, 'render_com'), workers=2)
+        for i in range(b, e):                 # what sequence._run's on_frame hands over: the GLOBAL frame index
+            w.write(i, _frame(i))
+        paths = w.close()
+        assert len(paths) == e - b
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_frame_sharded_ranks_fill_one_directory(tmp_path):
+    """Output side of the frame-sharded sequence (render_person with several ranks): every rank writes its own block of
+    frames under their global numbers -- one directory, no collisions, no gather."""
+    import numpy as np
+    from PIL import Image
+    n = 7                                      # ragged: 4 + 3
+    ctx = mp.get_context('spawn')
+    port = _free_port()
+    procs = [ctx.Process(target=_writer_worker, args=(r, 2, port, n, str(tmp_path))) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=180)
+        assert p.exitcode == 0
+    names = sorted(os.listdir(tmp_path / 'render_com'))
+    assert names == ['test_%06d.jpg' % i for i in range(n)]
+    for i, name in enumerate(names):
+        back = np.asarray(Image.open(tmp_path / 'render_com' / name)).astype(np.int32)
+        assert back.shape == (12, 10, 3) and np.abs(back - _frame(i)).mean() < 12.0      # the right frame under each number
