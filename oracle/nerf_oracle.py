@@ -347,9 +347,11 @@ def render_head_torso_chunk(sd, rays_o, rays_d, rays_o_t, rays_d_t, z_vals, bc_r
     sig_t = sig_t.reshape(1, R, S).clone()
     feat_t = feat_t.reshape(1, R, S, 3)
     sig_t[:, :, -1] = 0
-    s1 = F.relu(torch.stack([sig_h], 0))
+    # .clone(): the reference writes the +1e-6 into the ReLU output in place (MAIN:692-694, 884-886), which autograd of
+    # current PyTorch rejects when this chunk is differentiated (oracle/train_oracle.py); same arithmetic
+    s1 = F.relu(torch.stack([sig_h], 0)).clone()
     f1 = torch.stack([feat_h], 0)
-    s2 = F.relu(torch.stack([sig_h, sig_t], 0))
+    s2 = F.relu(torch.stack([sig_h, sig_t], 0)).clone()
     f2 = torch.stack([feat_h, feat_t], 0)
     s1[-1, :, :, -1] = s1[-1, :, :, -1] + 1e-6
     s2[-1, :, :, -1] = s2[-1, :, :, -1] + 1e-6
