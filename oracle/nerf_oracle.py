@@ -167,7 +167,7 @@ def decoder_forward(sd, p_in, ray_d, z_shape, z_app, signal, head_or_torso,
     p = decoder_transform_points(p_in, n_freq)
     p = torch.cat((p, signal.expand(p.shape[1], -1).unsqueeze(0)), -1)
     if head_or_torso == 'torso':
-        p = deformation_forward(sd, p) + p
+        p = deformation_forward(sd, p, dim_embed=6 * n_freq, dim_signal=signal.shape[-1]) + p
         net = _lin(sd, 'fc_in_torso', p)
         pskip = 'fc_p_skips_torso.0'
     elif head_or_torso == 'head':

@@ -20,13 +20,13 @@ ORDER = (['deform_net.blocks_embed.%d' % i for i in range(5)] + ['deform_net.out
                                                 'feat_view', 'fc_view', 'feat_out'])
 
 
-def dump_program(sd, field, folded=0):
+def dump_program(sd, field, folded=0, shape=(256, 256, 96, 42, 10, 4)):
     from dfa_nerf_b200 import _lib
     host = []
     for name in ORDER:
         host += [sd[name + '.weight'].contiguous().float(), sd[name + '.bias'].contiguous().float()]
     arr = (C.c_void_p * len(host))(*[t.data_ptr() for t in host])
-    desc = _lib.DecoderDesc(256, 256, 96, 42, 10, 4, 8, 4)
+    desc = _lib.DecoderDesc(*shape, 8, 4)
     ML = 20
     layers = (_lib.LayerInfo * ML)()
     n_layers, n_fold, dimL, view_layer = C.c_int(), C.c_int(), C.c_int(), C.c_int()
@@ -46,11 +46,11 @@ def dump_program(sd, field, folded=0):
 
 
 def run_program(prog, pe, latent, pe_dir):
-    """pe [P,60] fp64, latent [dimL], pe_dir [P,24] = PE(dir/|dir|) (staged block TC_KB_DIR) -> (feat [P,3], sigma [P])."""
+    """pe [P,6*n_freq] fp64, latent [dimL], pe_dir [P,24] = PE(dir/|dir|) (staged block TC_KB_DIR) -> (feat [P,3], sigma [P])."""
     layers, weights, bias, folds, dimL, view_layer, dot_w = prog
     P = pe.shape[0]
     blocks = {k: np.zeros((P, 64)) for k in range(7)}
-    blocks[KB_PE][:, :60] = pe
+    blocks[KB_PE][:, :pe.shape[1]] = pe
     blocks[KB_DIR][:, :pe_dir.shape[1]] = pe_dir
     acc, sigma, feat = None, None, None
     for l, L in enumerate(layers):
@@ -113,6 +113,36 @@ def test_decoder_layer_programs_compute_the_reference_forward():
             es = np.abs(sigma - rs[0].numpy()).max() / np.abs(rs[0].numpy()).max()
             # the compiled program stores fp32 weights (products composed in fp64, rounded once): 1e-6 relative
             assert ef < 2e-6 and es < 2e-6, (which, ef, es)
+
+
+def test_decoder_layer_programs_other_shapes():
+    """The program compiler for non-default module sizes the C ABI accepts (fewer PE frequencies, other latent widths):
+    (hidden, z_dim, dim_signal, dim_et_embed, n_freq, n_freq_views)."""
+    for shape in ((256, 64, 64, 30, 6, 2), (256, 128, 32, 18, 10, 1)):
+        _, zd, ds, dt, nf, nfv = shape
+        sd = synth.decoder_state_dict(9, z_dim=zd, dim_signal=ds, dim_et=dt, n_freq=nf, n_freq_views=nfv)
+        g = torch.Generator().manual_seed(2)
+        P = 33
+        p = (torch.rand(1, P, 3, generator=g) * 2 - 1) * 0.7
+        rd = torch.randn(1, P, 3, generator=g)
+        zs, za = torch.randn(1, zd, generator=g), torch.randn(1, zd, generator=g)
+        sig = {0: torch.randn(1, ds, generator=g), 1: torch.randn(1, dt, generator=g)}
+        sd64 = {k: v.double() for k, v in sd.items()}
+        with torch.no_grad():
+            pe = O.decoder_transform_points(p.double(), nf)[0].numpy()
+            d = rd.double() / torch.norm(rd.double(), dim=-1, keepdim=True)
+            pe_dir = O.decoder_transform_points(d, nfv)[0].numpy()
+            for field, which in ((0, 'head'), (1, 'torso')):
+                for folded in (0, 1):
+                    prog = dump_program(sd, field, folded, shape)
+                    latent = torch.cat([sig[field].reshape(-1), zs.reshape(-1), za.reshape(-1)]).double().numpy()
+                    assert prog[4] == latent.shape[0]
+                    feat, sigma = run_program(prog, pe, latent, pe_dir)
+                    rf, rs = O.decoder_forward(sd64, p.double(), rd.double(), zs.double(), za.double(), sig[field].double(), which,
+                                               n_freq=nf, n_freq_views=nfv)
+                    ef = np.abs(feat - rf[0].numpy()).max()
+                    es = np.abs(sigma - rs[0].numpy()).max() / np.abs(rs[0].numpy()).max()
+                    assert ef < 2e-6 and es < 2e-6, (shape, which, folded, ef, es)
 
 
 def test_program_host_argument_checks():
