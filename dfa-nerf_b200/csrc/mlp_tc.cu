@@ -462,7 +462,9 @@ __global__ void view_bias_kernel(int64_t R, int Wh, int ncol, int L, const float
 
 }  // namespace tc
 
+#ifdef DFN_EXPERIMENTS
 int ts_pack_from_tc(dfn_model* m, const std::vector<uint8_t>& hi, const std::vector<uint8_t>& lo, cudaStream_t st);
+#endif
 
 void tc_free_model(dfn_model* m) {
   cudaFree(m->ts_hi);
@@ -499,6 +501,9 @@ int tc_pack_model(dfn_model* m, const float* const* t, cudaStream_t st, TcHostDu
   const int i_views0 = d.D, i_feature = d.D + m->n_views, i_alpha = i_feature + 1, i_rgb = i_feature + 2;
 
   tc::Packer pk;
+#ifndef DFN_EXPERIMENTS
+  pk.want64 = pk.want2 = false;   // stage images of the experimental kernels (mlp_ts.cu, mlp_tc2.cu; make EXPERIMENTS=1)
+#endif
   if (dump) pk.dense = &dump->dense;
   TcProgram& pg = m->prog;
   pg = TcProgram();
@@ -637,10 +642,12 @@ int tc_pack_model(dfn_model* m, const float* const* t, cudaStream_t st, TcHostDu
     dump->fold_w = fold_w;
     return 0;
   }
+#ifdef DFN_EXPERIMENTS
   DFN_CUDA(cudaMalloc(&m->tc2_hi, pk.hi2.size()));
   DFN_CUDA(cudaMalloc(&m->tc2_lo, pk.lo2.size()));
   DFN_CUDA(cudaMemcpyAsync(m->tc2_hi, pk.hi2.data(), pk.hi2.size(), cudaMemcpyHostToDevice, st));
   DFN_CUDA(cudaMemcpyAsync(m->tc2_lo, pk.lo2.data(), pk.lo2.size(), cudaMemcpyHostToDevice, st));
+#endif
   DFN_CUDA(cudaMalloc(&m->tc_hi, pk.hi32.size()));
   DFN_CUDA(cudaMalloc(&m->tc_lo, pk.lo32.size()));
   DFN_CUDA(cudaMalloc(&m->tc_h16, pk.h16.size()));
@@ -652,13 +659,17 @@ int tc_pack_model(dfn_model* m, const float* const* t, cudaStream_t st, TcHostDu
   DFN_CUDA(cudaMemcpyAsync(m->tc_bias, bias.data(), bias.size() * 4, cudaMemcpyHostToDevice, st));
   DFN_CUDA(cudaMemcpyAsync(m->tc_fold_w, fold_w.data(), fold_w.size() * 4, cudaMemcpyHostToDevice, st));
   DFN_CUDA(cudaStreamSynchronize(st));
+#ifdef DFN_EXPERIMENTS
   return ts_pack_from_tc(m, pk.hi, pk.lo, st);
+#else
+  return 0;
+#endif
 }
 
 static inline int64_t align256(int64_t x) { return (x + 255) / 256 * 256; }
 
 // debug timeline hook (dfn_debug_trace): device buffer of 2 * trace_tiles * n_layers * 8 uint64
-static int g_impl = -1;  // -1 auto: bf16 -> mlp_tc.cu (1), bf16x3 -> mlp_pp.cu (2); 0: mlp_ts.cu (TMEM activations)
+static int g_impl = -1;  // -1 auto: bf16 -> mlp_tc.cu (1), bf16x3 -> mlp_pp.cu (2); with EXPERIMENTS=1 also 0: mlp_ts.cu, 3: mlp_tc2.cu
 void tc_set_impl(int impl) { g_impl = impl; }
 static void* g_trace_ptr = nullptr;
 static int g_trace_tiles = 0;
@@ -749,12 +760,18 @@ int tc_query_points(const dfn_model* m, int64_t R, int S, const float* rays_o, c
     void* scratch = reinterpret_cast<char*>(vbias_ws) + align256(R * (int64_t)Wh * 4);
     int rc = pp_launch(m, bias_ws, vbias_ws, scratch, R, S, rays_o, rays_d, z_vals, raw, precision, st);
     if (rc) return rc;
+#ifdef DFN_EXPERIMENTS
   } else if (impl == 3 && precision == DFN_PREC_BF16) {
     int rc = tc2_launch(m, bias_ws, vbias_ws, R, S, rays_o, rays_d, z_vals, raw, precision, st);
     if (rc) return rc;
   } else if (impl == 0 && (precision == DFN_PREC_BF16 || precision == DFN_PREC_BF16X3)) {
     int rc = ts_launch(m, bias_ws, vbias_ws, R, S, rays_o, rays_d, z_vals, raw, precision, st);
     if (rc) return rc;
+#else
+  } else if (impl == 0 || impl == 3) {
+    set_error("dfn_debug_set_impl(%d): the experimental kernels (mlp_ts.cu, mlp_tc2.cu) are not in this build (make EXPERIMENTS=1)", impl);
+    return DFN_E_UNSUPPORTED;
+#endif
   } else if (precision == DFN_PREC_BF16) {
     static bool attr_done = false;
     if (!attr_done) {

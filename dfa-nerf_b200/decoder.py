@@ -40,6 +40,8 @@ class DeformationField_ori(nn.Module):
 
     def __init__(self, dim_embed, dim_signal, hidden_size=64, n_blocks=7, skips=[4]):
         super().__init__()
+        if hidden_size != 64 or n_blocks != 7 or list(skips) != [4]:
+            raise DfnError('DeformationField_ori: only hidden_size=64, n_blocks=7, skips=[4] are built (what DEC:208 constructs)')
         self.dim_embed, self.dim_signal, self.skips = dim_embed, dim_signal, skips
         self.blocks_embed = nn.ModuleList([nn.Linear(dim_embed + dim_signal, hidden_size)] +
                                           [nn.Linear(hidden_size, hidden_size) for _ in range(n_blocks - 3)])
@@ -85,8 +87,10 @@ class Decoder(nn.Module):
                  use_deformation_field=False, use_expression=False, **kwargs):
         super().__init__()
         if positional_encoding != 'normal' or not use_viewdirs or n_blocks_view != 1 or downscale_p_by != 2. or \
-                use_expression or use_wav2lip or not final_sigmoid_activation or z_dim <= 0 or rgb_out_dim != 3:
-            raise DfnError('Decoder: only the configuration of MAIN:518 is built')
+                use_expression or use_wav2lip or not final_sigmoid_activation or z_dim <= 0 or rgb_out_dim != 3 or \
+                list(skips) != [4] or n_blocks != 8:
+            raise DfnError('Decoder: only the configuration of MAIN:518 is built (n_blocks=8, skips=[4], one view block, '
+                           "'normal' encoding, final sigmoid)")
         self.n_freq_posenc, self.n_freq_posenc_views, self.skips = n_freq_posenc, n_freq_posenc_views, skips
         self.z_dim, self.hidden_size, self.n_blocks, self.dim_signal = z_dim, hidden_size, n_blocks, dim_signal
         self.dim_et_embed, self.use_deformation_field = dim_et_embed, use_deformation_field
@@ -249,14 +253,17 @@ class Decoder(nn.Module):
 
 @torch.no_grad()
 def render_head_torso(decoder, H, W, focal, c2w_head, c2w_torso, bc_rgb, z_shape, z_app, signal, signal_torso, near, far,
-                      cx=None, cy=None, N_samples=64, ray_range=None, last_dist=1e10, precision=_lib.PREC_BF16X3):
+                      cx=None, cy=None, N_samples=64, ray_range=None, last_dist=1e10, precision=_lib.PREC_BF16X3,
+                      rays_torso=None):
     """One frame (or ray range) of the reference's live loop MAIN:633-708: returns (rgb_head, rgb_person) [R,3].
     z_shape / z_app: [1,2,z_dim] (index 0 head, 1 torso, MAIN:664-674).
     precision PREC_BF16 / PREC_BF16X3: the fused tcgen05 path (dfn_render_head_torso, 5 launches per call);
-    PREC_FP32: the explicit-points Decoder.forward built from the fp32 FFMA blocks."""
+    PREC_FP32: the explicit-points Decoder.forward built from the fp32 FFMA blocks.
+    rays_torso = (rays_o, rays_d) [H*W,3] of the body pose, which is fixed over a sequence (MAIN:644): a frame loop computes
+    them once and passes them instead of c2w_torso."""
     device = bc_rgb.device
     ro, rd = get_rays(H, W, focal, c2w_head, cx, cy, device=device)
-    rot, rdt = get_rays(H, W, focal, c2w_torso, cx, cy, device=device)
+    rot, rdt = rays_torso if rays_torso is not None else get_rays(H, W, focal, c2w_torso, cx, cy, device=device)
     b, e = ray_range if ray_range is not None else (0, H * W)
     ro, rd, rot, rdt = [t.reshape(-1, 3)[b:e].contiguous() for t in (ro, rd, rot, rdt)]
     R = e - b

@@ -74,7 +74,12 @@ class RenderEngine:
             io.perturb_rand = ptr(rnd)
         if Nf > 0:
             if self.perturb > 0.:
-                u = torch.rand((R, Nf), device=d)
+                if pytest:      # upstream sample_pdf(pytest=True): np.random.seed(0); u = np.random.rand(R, N) (HELP:553-561)
+                    import numpy as np
+                    np.random.seed(0)
+                    u = torch.Tensor(np.random.rand(R, Nf)).to(d)
+                else:
+                    u = torch.rand((R, Nf), device=d)
                 io.u_per_ray = 1
             else:
                 u = linspace_table(Nf, d)
@@ -97,7 +102,8 @@ class RenderEngine:
                 raise DfnError('output %r must be contiguous fp32 of shape %s' % (name, shapes[key]))
             setattr(io, key, ptr(t))
             res[name] = t
-        nbytes = lib.dfn_render_workspace_bytes(hc, R, Nc, Nf, self.precision)
+        nbytes = max(lib.dfn_render_workspace_bytes(hc, R, Nc, Nf, self.precision),
+                     lib.dfn_render_workspace_bytes(hf, R, Nc, Nf, self.precision) if hf is not None else 0)
         ws = Workspace.get(nbytes, d, 'render')
         with torch.cuda.device(d):
             check(lib.dfn_render_rays(hc, hf, R, Nc, Nf, C.byref(io), int(self.white_bkgd), self.precision, ptr(ws),

@@ -41,6 +41,6 @@ def render_person(decoder, data, pose_body, z_shape, z_app, AudNet, ExpNet, out_
 
     render_sequence_head_torso(decoder, H, W, focal, poses, pose_body.to(poses.device), data['bc_img'], z_shape, z_app, signals,
                                signals_torso, near, far, cx, cy, N_samples=N_samples, precision=precision, group=group,
-                               gather=False, on_frame=on_frame, with_head=True)
+                               gather=False, on_frame=on_frame, with_head=True, keep=False)
     head.close()
     return com.close()

@@ -308,7 +308,8 @@ def render_rays(ray_batch, bc_rgb, aud, sd_coarse, sd_fine, N_samples, N_importa
 
 
 def render(H, W, focal, cx, cy, c2w, bc_rgb, aud, sd_coarse, sd_fine, near, far,
-           N_samples=64, N_importance=128, chunk=2048, model='facenerf', ray_slice=None):
+           N_samples=64, N_importance=128, chunk=2048, model='facenerf', ray_slice=None,
+           keys=('rgb_map', 'disp_map', 'acc_map', 'last_weight')):
     """Upstream render(): get_rays -> viewdirs -> batchify(render_rays).  bc_rgb [H*W,3].
     ray_slice=(begin,end) renders a contiguous ray range only (bounded CPU samples)."""
     rays_o, rays_d = get_rays(H, W, focal, c2w, cx, cy)
@@ -323,7 +324,6 @@ def render(H, W, focal, cx, cy, c2w, bc_rgb, aud, sd_coarse, sd_fine, near, far,
         j = min(i + chunk, e)
         outs.append(render_rays(rays[i:j], bc_rgb[i:j], aud, sd_coarse, sd_fine,
                                 N_samples, N_importance, model=model))
-    keys = ('rgb_map', 'disp_map', 'acc_map', 'last_weight')
     return {k: torch.cat([o[k] for o in outs], 0) for k in keys}
 
 

@@ -120,3 +120,44 @@ def test_frame_sharded_ranks_fill_one_directory(tmp_path):
     for i, name in enumerate(names):
         back = np.asarray(Image.open(tmp_path / 'render_com' / name)).astype(np.int32)
         assert back.shape == (12, 10, 3) and np.abs(back - _frame(i)).mean() < 12.0      # the right frame under each number
+
+
+def _gather_worker(rank, world, port, n_frames, q):
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        from dfa_nerf_b200.sequence import shard_frames, FrameGather
+        seen = []
+        fg = FrameGather(n_frames, 12, 10, 'cpu', planes=1, on_frame=lambda i, fr: seen.append((i, int(fr.sum()))))
+        b, e = shard_frames(n_frames, rank, world)
+        assert fg.per == -(-n_frames // world)
+        for k in range(fg.per):                     # every rank makes the same number of collective calls
+            i = b + k
+            fg.push(torch.from_numpy(_frame(i))[None] if i < e else None)
+        out = fg.finish()
+        if rank == 0:
+            q.put((tuple(out.shape), [int(out[i].sum()) for i in range(n_frames)], sorted(seen)))
+        else:
+            assert out is None and seen == []
+    finally:
+        dist.destroy_process_group()
+
+
+def test_frame_gather_to_rank0_two_ranks_gloo():
+    """The world>1 sequence path (sequence.FrameGather): frames sharded in contiguous blocks, local frame k of every rank
+    gathered to rank 0 as uint8 per step, ragged blocks (4 + 3) padded with a step whose stale buffer is ignored."""
+    n = 7
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_gather_worker, args=(r, 2, port, n, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=180)
+        assert p.exitcode == 0
+    shape, sums, seen = q.get(timeout=10)
+    want = [int(_frame(i).sum()) for i in range(n)]
+    assert shape == (n, 1, 12, 10, 3) and sums == want
+    assert seen == [(i, want[i]) for i in range(n)]          # on_frame saw every global frame exactly once, on rank 0

@@ -101,27 +101,92 @@ def test_query_points_bf16x3_vs_fp32_oracle(dfn, R, S):
     assert ew < 1e-4 and ec < 1e-4, (ew, ec)      # north-star tolerance: 1e-4 max-abs
 
 
-@pytest.mark.parametrize('R,S', [(37, 64), (21, 192)])
-def test_query_points_bf16_vs_bf16_oracle(dfn, R, S):
+# Gates of the single-pass kernels against the reduced-precision restatement (oracle/quantized.py: same operands rounded
+# at the same places, exact products, one fp32 rounding per accumulator).  What is left between the two is the tensor
+# cores' own accumulation (order, truncated alignment: ~1e-6 relative on a pre-activation) and the MUFU sin/cos of the
+# fused encoding -- either can flip the 16-bit rounding of an activation that sits on a rounding boundary, and ONE flip
+# in the last trunk layer moves sigma by gain x |w| x ulp ~ 3e-3 |sigma|max in bf16 (tests/test_quantized_cpu.py).  So the
+# max is gated at a few flips, p99 and the median far below, and everything is printed.
+#                 colours(sigmoid) max, sigma max / p99 / median as fractions of |sigma|max
+Q_GATE = {'bf16': (5e-5, 1e-2, 3e-3, 5e-4), 'fp16': (1e-5, 1.5e-3, 4e-4, 6e-5)}
+
+
+def _gate_quantized(tag, prec_name, raw, refq, ref32):
+    from oracle import quantized as Q
+    raw = raw.detach().cpu()
+    smax = ref32[..., 3].abs().max().item()
+    ec = maxerr(torch.sigmoid(raw[..., :3]), torch.sigmoid(refq[..., :3]))
+    mx, p99, med = Q.stats(raw[..., 3] - refq[..., 3])
+    mx32, p9932, med32 = Q.stats(raw[..., 3] - ref32[..., 3])
+    print('%s %s vs %s-operand restatement: colours %.2e | sigma max %.2e p99 %.2e median %.2e of |sigma|max=%.1f  '
+          '(vs fp32 oracle: max %.2e p99 %.2e median %.2e)'
+          % (tag, prec_name, prec_name, ec, mx / smax, p99 / smax, med / smax, smax, mx32 / smax, p9932 / smax, med32 / smax))
+    gc, gm, g99, gmed = Q_GATE[prec_name]
+    assert torch.isfinite(raw).all()
+    assert ec <= gc and mx <= gm * smax and p99 <= g99 * smax and med <= gmed * smax, (tag, ec, mx / smax, p99 / smax, med / smax)
+    # the restatement explains the kernel: far closer to it than to the fp32 forward
+    assert med < 0.2 * med32 and p99 < 0.5 * p9932, (tag, med, med32, p99, p9932)
+
+
+def _face_x(ro, rd, vd, z, aud):
+    R, S = z.shape
+    pts = (ro[:, None] + rd[:, None] * z[:, :, None]).reshape(-1, 3)
+    return torch.cat([O.embed(pts, 10), aud[None].expand(pts.shape[0], -1), O.embed(vd[:, None].expand(R, S, 3).reshape(-1, 3), 4)], -1)
+
+
+@pytest.mark.parametrize('prec_name', ['bf16', 'fp16'])
+@pytest.mark.parametrize('R,S', [(37, 64), (600, 64), (20000, 8)])
+def test_query_points_single_pass_vs_quantized_oracle(dfn, prec_name, R, S):
+    """mlp_tc_kernel<bf16> / <fp16> (the benchmarked kernels) against the bf16- / fp16-operand restatement of HELP:275-299."""
+    from oracle import quantized as Q
+    ro, rd, vd, z, aud = _query_case(R, S)
+    sd = synth.facenerf_state_dict(0)
+    prec, dt = {'bf16': (dfn.PREC_BF16, torch.bfloat16), 'fp16': (dfn.PREC_FP16, torch.float16)}[prec_name]
+    eng = dfn.RenderEngine(face(dfn, 0), None, S, 0, precision=prec)
+    raw = eng.query_points(eng.network_fn, ro.to(DEV), rd.to(DEV), vd.to(DEV), z.to(DEV), aud.to(DEV))
+    x = _face_x(ro, rd, vd, z, aud)
+    with torch.no_grad():
+        refq = Q.facenerf_forward_q(sd, x, dt).reshape(R, S, 4)
+        ref32 = O.facenerf_forward(sd, x).reshape(R, S, 4)
+    _gate_quantized('FaceNeRF R=%d S=%d' % (R, S), prec_name, raw, refq, ref32)
+
+
+@pytest.mark.parametrize('prec_name', ['bf16', 'fp16'])
+def test_query_points_nerf_single_pass_vs_quantized_oracle(dfn, prec_name):
+    """NeRF (HELP:372-396; feature_linear composed into views_linears.0 before rounding) on the same kernels."""
+    from oracle import quantized as Q
+    R, S = 300, 64
+    ro, rd, vd, z, aud = _query_case(R, S, seed=5)
+    sd = synth.nerf_state_dict(2)
+    prec, dt = {'bf16': (dfn.PREC_BF16, torch.bfloat16), 'fp16': (dfn.PREC_FP16, torch.float16)}[prec_name]
+    net = nerf(dfn, 2)
+    eng = dfn.RenderEngine(net, None, S, 0, precision=prec)
+    raw = eng.query_points(net, ro.to(DEV), rd.to(DEV), vd.to(DEV), z.to(DEV), None)
+    pts = (ro[:, None] + rd[:, None] * z[:, :, None]).reshape(-1, 3)
+    x = torch.cat([O.embed(pts, 10), O.embed(vd[:, None].expand(R, S, 3).reshape(-1, 3), 4)], -1)
+    with torch.no_grad():
+        refq = Q.nerf_forward_q(sd, x, dt).reshape(R, S, 4)
+        ref32 = O.nerf_forward(sd, x).reshape(R, S, 4)
+    _gate_quantized('NeRF R=%d S=%d' % (R, S), prec_name, raw, refq, ref32)
+
+
+def test_query_points_pp_kernel_bf16_vs_quantized_oracle(dfn):
+    """The ping-pong kernel (mlp_pp_kernel<bf16>, dfn_debug_set_impl(2)) in its single-pass instantiation: same gate."""
+    from oracle import quantized as Q
+    R, S = 600, 64
     ro, rd, vd, z, aud = _query_case(R, S)
     sd = synth.facenerf_state_dict(0)
     eng = dfn.RenderEngine(face(dfn, 0), None, S, 0, precision=dfn.PREC_BF16)
-    raw = eng.query_points(eng.network_fn, ro.to(DEV), rd.to(DEV), vd.to(DEV), z.to(DEV), aud.to(DEV))
-    pts = (ro[:, None] + rd[:, None] * z[:, :, None]).reshape(-1, 3)
-    x = torch.cat([O.embed(pts, 10), aud[None].expand(pts.shape[0], -1), O.embed(vd[:, None].expand(R, S, 3).reshape(-1, 3), 4)], -1)
+    try:
+        dfn.lib.dfn_debug_set_impl(2)
+        raw = eng.query_points(eng.network_fn, ro.to(DEV), rd.to(DEV), vd.to(DEV), z.to(DEV), aud.to(DEV))
+    finally:
+        dfn.lib.dfn_debug_set_impl(-1)
+    x = _face_x(ro, rd, vd, z, aud)
     with torch.no_grad():
-        ref16 = O.facenerf_forward_bf16(sd, x).reshape(R, S, 4)
+        refq = Q.facenerf_forward_q(sd, x, torch.bfloat16).reshape(R, S, 4)
         ref32 = O.facenerf_forward(sd, x).reshape(R, S, 4)
-    assert torch.isfinite(raw).all()
-    # same operand rounding, different accumulation order -> close to the bf16 restatement ...
-    e16 = maxerr(raw[..., :3], ref16[..., :3])
-    s16 = maxerr(raw[..., 3], ref16[..., 3])
-    # ... and the bf16 rounding itself is what separates it from fp32
-    e32 = maxerr(raw[..., :3], ref32[..., :3])
-    s32 = maxerr(raw[..., 3], ref32[..., 3])
-    print('bf16 R=%d S=%d: vs bf16-oracle rgb %.2e sigma %.2e | vs fp32 rgb %.2e sigma %.2e' % (R, S, e16, s16, e32, s32))
-    # (loose: a 1-ulp libm difference in a PE input can flip its bf16 rounding)
-    assert e16 < e32 + 1e-3 and s16 < s32 + 0.05
+    _gate_quantized('FaceNeRF (mlp_pp) R=%d S=%d' % (R, S), 'bf16', raw, refq, ref32)
 
 
 @pytest.mark.parametrize('R,S', [(37, 64), (300, 64), (21, 192)])
@@ -175,9 +240,10 @@ def test_tc_matches_fp32_kernel_at_scale(dfn):
 
 
 def test_kernel_variants_agree(dfn):
-    """The three tcgen05 kernel variants (dfn_debug_set_impl) compute the same function: activations in shared
-    memory (1) vs tensor memory (0) are bit-identical in bf16 (same operands, same K order); in bf16x3 the hi/lo
-    products are accumulated in a different order, so all variants agree to the operand precision."""
+    """The two tcgen05 kernel generations of the product build (dfn_debug_set_impl: 1 = mlp_tc.cu, 2 = mlp_pp.cu) compute
+    the same function: bit-identical in bf16 (same operands, same K order); in bf16x3 the hi/lo products are accumulated
+    in a different order, so they agree to the operand precision.  The experimental generations (0 = TMEM activations,
+    3 = CTA pairs) are only in `make EXPERIMENTS=1` builds and are compared when present."""
     R, S = 700, 192
     ro, rd, vd, z, aud = _query_case(R, S, seed=9)
     net = face(dfn, 1)
@@ -186,16 +252,22 @@ def test_kernel_variants_agree(dfn):
         for prec in (dfn.PREC_BF16, dfn.PREC_BF16X3):
             eng = dfn.RenderEngine(net, None, S, 0, precision=prec)
             outs = {}
-            for impl in (0, 1, 2):
+            for impl in (1, 2, 0, 3):
+                if impl == 3 and prec != dfn.PREC_BF16:
+                    continue
                 dfn.lib.dfn_debug_set_impl(impl)
-                outs[impl] = eng.query_points(net, *args).clone()
+                try:
+                    outs[impl] = eng.query_points(net, *args).clone()
+                except dfn.DfnError as ex:
+                    assert impl in (0, 3) and 'EXPERIMENTS' in str(ex)
+                    continue
                 assert torch.isfinite(outs[impl]).all()
-            assert torch.equal(outs[0], outs[1]) or maxerr(outs[0], outs[1]) < 2e-3   # x3: K-half order differs
             if prec == dfn.PREC_BF16:
-                assert torch.equal(outs[0], outs[1])
-            if prec == dfn.PREC_BF16:      # CTA-pair kernel (cta_group::2 MMAs): same operands, same K order
-                dfn.lib.dfn_debug_set_impl(3)
-                assert torch.equal(eng.query_points(net, *args), outs[1])
+                for impl in outs:
+                    assert torch.equal(outs[impl], outs[1]), impl
+            else:
+                for impl in outs:
+                    assert maxerr(outs[impl], outs[1]) < 2e-3, impl      # x3: K-half order differs
             wa = dfn.calc_volume_weights(args[3], args[1], outs[1][..., 3].contiguous())
             wb = dfn.calc_volume_weights(args[3], args[1], outs[2][..., 3].contiguous())
             tol = 1e-4 if prec == dfn.PREC_BF16X3 else 5e-2

@@ -71,22 +71,53 @@ def test_decoder_query_bf16x3_vs_fp32_oracle(dfn, which, R, S):
     assert ef < 1e-4 and ew < 1e-4, (ef, ew)      # north-star tolerance: 1e-4 max-abs
 
 
+# Single-pass Decoder kernels (mlp_pp_kernel<bf16|fp16, Decoder> running the folded-head programs) against the
+# reduced-precision interpretation of the SAME program (oracle/quantized.run_program_q: operands rounded where the kernel
+# rounds them -- staged encodings, activations after bias + ReLU, the deformation output, the 16-bit density row --,
+# exact products, fp32 accumulators); tests/test_layer_programs_cpu.py + test_quantized_cpu.py show that the program
+# without rounding IS the reference's Decoder.forward.  Gates as in test_gpu_2_mlp.py (one flipped 16-bit rounding of a
+# last-block activation moves sigma by gain 400 x |w| x ulp ~ 1e-3 |sigma|max in bf16).
+#                 colours max, sigma max / p99 / median as fractions of |sigma|max
+Q_GATE = {'bf16': (3e-4, 1e-2, 3e-3, 5e-4), 'fp16': (4e-5, 1.5e-3, 4e-4, 6e-5)}
+
+
+@pytest.mark.parametrize('prec_name', ['bf16', 'fp16'])
 @pytest.mark.parametrize('which', ['head', 'torso'])
-def test_decoder_query_bf16_reported(dfn, which):
-    """Throughput mode: 8-bit mantissas on every operand; gated loosely, error printed."""
-    R, S, seed = 200, 64, 4
+@pytest.mark.parametrize('R,S', [(37, 64), (600, 64), (20000, 4)])
+def test_decoder_query_single_pass_vs_quantized_program(dfn, prec_name, which, R, S):
+    from oracle import quantized as Q
+    from program_dump import dump_program, KB_PE, KB_DIR
+    seed = 4
     sd = synth.decoder_state_dict(seed)
     dec = make_decoder(dfn, seed)
-    ro, rd, z, zs, za, sg_h, sg_t = _case(R, S, seed)
+    ro, rd, z, zs, za, sg_h, sg_t = _case(R, S, seed + R)
     sig = sg_h if which == 'head' else sg_t
-    rf, rs = _oracle(sd, ro, rd, z, zs, za, sig, which)
-    f, s = dec.query_rays(ro.to(DEV), rd.to(DEV), z.to(DEV), zs.to(DEV), za.to(DEV), sig.to(DEV), which,
-                          precision=dfn.PREC_BF16)
+    prec, dt = {'bf16': (dfn.PREC_BF16, torch.bfloat16), 'fp16': (dfn.PREC_FP16, torch.float16)}[prec_name]
+    f, s = dec.query_rays(ro.to(DEV), rd.to(DEV), z.to(DEV), zs.to(DEV), za.to(DEV), sig.to(DEV), which, precision=prec)
     assert torch.isfinite(f).all() and torch.isfinite(s).all()
-    ef, es = maxerr(f, rf), maxerr(s, rs)
-    rel = es / rs.abs().max().item()
-    print('decoder %s bf16: feat err %.2e, sigma err %.2e (%.2e of max |sigma|)' % (which, ef, es, rel))
-    assert ef < 5e-2 and rel < 5e-2
+    rf, rs = _oracle(sd, ro, rd, z, zs, za, sig, which)
+    layers, weights, bias, folds, dimL, view_layer, dot_w = dump_program(sd, 0 if which == 'head' else 1, 1)
+    latent = torch.cat([sig.reshape(-1), zs.reshape(-1), za.reshape(-1)])
+    fold = {l: (torch.as_tensor(fw).double().t() @ latent.double()).float() for l, fw in folds.items()}
+    p = (ro[:, None, :] + rd[:, None, :] * z[:, :, None]).reshape(1, -1, 3)
+    dn = (rd / torch.norm(rd, dim=-1, keepdim=True))[:, None, :].expand(R, S, 3).reshape(1, -1, 3)
+    pe, ped = torch.zeros(R * S, 64), torch.zeros(R * S, 64)
+    pe[:, :60] = O.decoder_transform_points(p, 10)[0]
+    ped[:, :24] = O.decoder_transform_points(dn, 4)[0]
+    with torch.no_grad():
+        qf, qs = Q.run_program_q(layers, weights, bias, {KB_PE: pe, KB_DIR: ped}, dt, fold_bias=fold, dot_w=dot_w)
+    qf, qs = qf.reshape(R, S, 3), qs.reshape(R, S)
+    smax = rs.abs().max().item()
+    ec = maxerr(f, qf)
+    mx, p99, med = Q.stats(s.cpu() - qs)
+    mx32, p9932, med32 = Q.stats(s.cpu() - rs)
+    print('decoder %s %s R=%d S=%d vs %s-operand program: colours %.2e (vs fp32 %.2e) | sigma max %.2e p99 %.2e median %.2e of '
+          '|sigma|max=%.1f (vs fp32 oracle: max %.2e p99 %.2e median %.2e)'
+          % (which, prec_name, R, S, prec_name, ec, maxerr(f, rf), mx / smax, p99 / smax, med / smax, smax, mx32 / smax,
+             p9932 / smax, med32 / smax))
+    gc, gm, g99, gmed = Q_GATE[prec_name]
+    assert ec <= gc and mx <= gm * smax and p99 <= g99 * smax and med <= gmed * smax, (ec, mx / smax, p99 / smax, med / smax)
+    assert med < 0.2 * med32 and p99 < 0.5 * p9932, (med, med32, p99, p9932)
 
 
 def test_decoder_query_matches_fp32_blocks_at_scale(dfn):
