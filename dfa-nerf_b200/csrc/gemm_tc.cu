@@ -1,0 +1,276 @@
+// Strided tcgen05 GEMM with in-kernel fp32 -> split-bf16 operand conversion: the workhorse of the training step
+// (what `loss.backward()` at MAIN:923 and every nn.Linear forward of MAIN:855-880 spend their time in).
+//
+//   C[m, n] = act( sum_k A(m, k) * B(n, k) + bias[n] (+ addend[m, n]) ) (+ addend[m, n]) (+ C[m, n])
+//   A(m, k) = A[m * a_ld_r + k * a_ld_k] (* mask'(A_mask[same index])),   B(n, k) = B[n * b_ld_r + k * b_ld_k]
+//
+// Both operands are addressed with a (row, k) stride pair, one of which is 1, so the three GEMMs of a layer need no
+// transposed copies of anything:
+//   forward      Y  = X W^T        A = X  (ld, 1)        B = W      (K, 1)
+//   data grad    dX = dA W         A = dH (ld, 1) masked B = W^T    (1, K)      dA = dH * act'(Y), formed by the loader
+//   weight grad  dW = dA^T X       A = dH^T (1, ld) masked, B = X^T (1, ld)     split over the batch, fp32 atomics
+// Per CTA: one 128 x N (N <= 256) output tile; K walked in chunks of 64 through a two-stage shared-memory pipeline.
+//   warps 0-3   A loaders (thread = tile row): 64 fp32 from global, optional activation-derivative mask, split into bf16
+//               hi / lo = bf16(v - hi), 16-byte stores into the 128-byte-swizzled K-major operand block; then the epilogue
+//   warps 4-11  B loaders (thread = output column n)
+//   warp 12     TMEM allocation + MMA issue: tcgen05.mma.kind::f16, A_hi B_hi + A_lo B_hi + A_hi B_lo (bf16x3, fp32-level
+//               products; DFN_PREC_BF16 issues the first term only), fp32 accumulator in tensor memory
+// The kernel is bound by the loaders' conversion work, not by the tensor pipe (a training step is ~1 TFLOP: milliseconds).
+#include <string.h>
+
+#include "common.cuh"
+#include "tc_ptx.cuh"
+#include "tc_epi.cuh"
+
+namespace dfn {
+namespace gemm {
+
+using namespace dfn::tc;
+
+static constexpr int BM = 128, BK = 64, BN_MAX = 256;
+static constexpr int A_BYTES = BM * 128;        // one bf16 plane of the A tile
+static constexpr int B_BYTES = BN_MAX * 128;
+static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;   // hi + lo of both operands: 96 KB
+static constexpr int N_STAGE = 2;
+static constexpr int SMEM_BAR = N_STAGE * STAGE_BYTES;
+static constexpr int SMEM_TOTAL = SMEM_BAR + 128;
+static constexpr int A_THREADS = 128, B_THREADS = 256, LOADERS = A_THREADS + B_THREADS, THREADS = LOADERS + 32;
+static_assert(SMEM_TOTAL <= 227 * 1024, "shared memory budget");
+
+struct Params {
+  dfn_gemm_desc d;
+  int n_pad;       // N rounded up to 16 (MMA granularity)
+  int m_tiles;
+  int chunks;      // ceil(K / 64)
+  int per_split;   // chunks per K split
+};
+
+__device__ __forceinline__ float mask_factor(int mode, float y) {
+  if (mode == DFN_MASK_RELU) return y > 0.f ? 1.f : 0.f;
+  if (mode == DFN_MASK_LEAKY) return y > 0.f ? 1.f : 0.02f;
+  return y * (1.f - y);   // DFN_MASK_SIGMOID: y is the sigmoid's output
+}
+
+// 32 consecutive k of one operand row -> registers (zero outside the matrix), optionally times act'(mask)
+__device__ __forceinline__ void fetch32(const float* __restrict__ src, const float* __restrict__ msk, int mmode, int64_t row_off,
+                                        int64_t ld_k, int k0, int K, bool row_ok, float (&v)[32]) {
+  if (!row_ok) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = 0.f;
+    return;
+  }
+  const float* p = src + row_off;
+  if (ld_k == 1 && k0 + 32 <= K && ((reinterpret_cast<uintptr_t>(p + k0) & 15) == 0)) {
+    const float4* q = reinterpret_cast<const float4*>(p + k0);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float4 t = __ldg(q + j);
+      v[4 * j] = t.x; v[4 * j + 1] = t.y; v[4 * j + 2] = t.z; v[4 * j + 3] = t.w;
+    }
+    if (msk) {
+      const float4* qm = reinterpret_cast<const float4*>(msk + row_off + k0);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4 t = __ldg(qm + j);
+        v[4 * j] *= mask_factor(mmode, t.x); v[4 * j + 1] *= mask_factor(mmode, t.y);
+        v[4 * j + 2] *= mask_factor(mmode, t.z); v[4 * j + 3] *= mask_factor(mmode, t.w);
+      }
+    }
+    return;
+  }
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    const int k = k0 + j;
+    v[j] = k < K ? __ldg(p + (int64_t)k * ld_k) : 0.f;
+  }
+  if (msk) {
+    const float* pm = msk + row_off;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const int k = k0 + j;
+      if (k < K) v[j] *= mask_factor(mmode, __ldg(pm + (int64_t)k * ld_k));
+    }
+  }
+}
+
+// one tile row, one 64-wide K chunk: global fp32 -> bf16 hi [/ lo] planes in the swizzled K-major block
+template <bool X3>
+__device__ __forceinline__ void load_row(const float* __restrict__ src, const float* __restrict__ msk, int mmode, int64_t ld_r,
+                                         int64_t ld_k, int64_t row_g, bool row_ok, int k0, int K, uint8_t* hi, uint8_t* lo,
+                                         uint32_t row) {
+  float v[32];
+#pragma unroll 1
+  for (int h = 0; h < 2; ++h) {
+    fetch32(src, msk, mmode, row_g * ld_r, ld_k, k0 + 32 * h, K, row_ok, v);
+#pragma unroll
+    for (int ch = 0; ch < 4; ++ch) {
+      float o[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) o[e] = v[ch * 8 + e];
+      store_chunk<X3>(hi, lo, row, (uint32_t)(4 * h + ch), o);
+    }
+  }
+}
+
+template <bool X3>
+__global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const __grid_constant__ Params P) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const uint32_t sbase = smem_u32(smem);
+  if ((sbase & 1023u) != 0) __trap();
+  const dfn_gemm_desc& d = P.d;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t bar_full = sbase + SMEM_BAR;        // [2] stage filled by all loader threads
+  const uint32_t bar_empty = sbase + SMEM_BAR + 16;  // [2] stage consumed by the MMAs
+  const uint32_t bar_acc = sbase + SMEM_BAR + 32;    // accumulator complete
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + SMEM_BAR + 48);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < N_STAGE; ++s) {
+      mbar_init(bar_full + 8 * s, LOADERS);
+      mbar_init(bar_empty + 8 * s, 1);
+    }
+    mbar_init(bar_acc, 1);
+    fence_barrier_init();
+  }
+  if (warp == 12) tmem_alloc(smem_u32(tmem_ptr_smem), 256);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  const int mt = (int)blockIdx.x % P.m_tiles, ks = (int)blockIdx.x / P.m_tiles;
+  const int kc0 = ks * P.per_split;
+  const int kc1 = min(P.chunks, kc0 + P.per_split);
+  const int n_it = kc1 - kc0;     // >= 1 (host guarantees)
+  const int64_t m0 = (int64_t)mt * BM;
+
+  if (warp < 12) {
+    // =========================================== operand loaders ===========================================
+    const bool is_a = warp < 4;
+    const uint32_t row = is_a ? (uint32_t)threadIdx.x : (uint32_t)(threadIdx.x - A_THREADS);
+    const int64_t row_g = is_a ? m0 + row : (int64_t)row;
+    const bool row_ok = is_a ? row_g < d.M : (int)row < d.N;
+    const bool row_used = is_a || (int)row < P.n_pad;
+    const float* src = is_a ? d.A : d.B;
+    const float* msk = is_a ? d.A_mask : nullptr;
+    const int64_t ld_r = is_a ? d.a_ld_r : d.b_ld_r, ld_k = is_a ? d.a_ld_k : d.b_ld_k;
+    for (int it = 0; it < n_it; ++it) {
+      const int s = it % N_STAGE;
+      const uint32_t par = (uint32_t)(it / N_STAGE) & 1u;
+      mbar_wait(bar_empty + 8 * s, par ^ 1u);
+      uint8_t* st = smem + (size_t)s * STAGE_BYTES;
+      uint8_t* hi = is_a ? st : st + 2 * A_BYTES;
+      uint8_t* lo = is_a ? st + A_BYTES : st + 2 * A_BYTES + B_BYTES;
+      if (row_used) load_row<X3>(src, msk, d.a_mask_mode, ld_r, ld_k, row_g, row_ok, (kc0 + it) * BK, d.K, hi, lo, row);
+      fence_proxy_async();
+      mbar_arrive(bar_full + 8 * s);
+    }
+  } else {
+    // ============================================= MMA issuer ==============================================
+    const uint32_t idesc = make_idesc((uint32_t)P.n_pad);
+    for (int it = 0; it < n_it; ++it) {
+      const int s = it % N_STAGE;
+      const uint32_t par = (uint32_t)(it / N_STAGE) & 1u;
+      mbar_wait(bar_full + 8 * s, par);
+      tcgen05_fence_after();
+      const uint32_t st = sbase + (uint32_t)s * STAGE_BYTES;
+      const uint64_t a_hi = make_smem_desc(st), a_lo = make_smem_desc(st + A_BYTES);
+      const uint64_t b_hi = make_smem_desc(st + 2 * A_BYTES), b_lo = make_smem_desc(st + 2 * A_BYTES + B_BYTES);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) umma_bf16(tmem_base, a_hi + 2 * q, b_hi + 2 * q, idesc, (it | q) != 0 ? 1u : 0u);
+      if (X3) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) umma_bf16(tmem_base, a_lo + 2 * q, b_hi + 2 * q, idesc, 1u);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) umma_bf16(tmem_base, a_hi + 2 * q, b_lo + 2 * q, idesc, 1u);
+      }
+      umma_commit(bar_empty + 8 * s);
+    }
+    umma_commit(bar_acc);
+  }
+
+  if (warp < 4) {
+    // ================================================ epilogue ================================================
+    mbar_wait(bar_acc, 0u);
+    tcgen05_fence_after();
+    const uint32_t row = (uint32_t)threadIdx.x;
+    const int64_t m = m0 + row;
+    const uint32_t acc = tmem_base + ((uint32_t)(warp * 32) << 16);
+    const bool atomic = d.k_splits > 1;
+    const int act = d.act & 3;
+    const bool pre_add = (d.act & 4) != 0;
+    for (int c0 = 0; c0 < P.n_pad; c0 += 16) {
+      uint32_t v[16];
+      tmem_ld16(acc + (uint32_t)c0, v);
+      tmem_ld_wait();
+      if (m < d.M) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const int n = c0 + j;
+          if (n >= d.N) continue;
+          float x = __uint_as_float(v[j]);
+          if (d.bias != nullptr && ks == 0) x += d.bias[n];
+          const float add = d.addend != nullptr && ks == 0 ? d.addend[m * d.add_ld_r + (int64_t)n * d.add_ld_c] : 0.f;
+          if (pre_add) x += add;
+          if (act == 1) x = fmaxf(x, 0.f);
+          else if (act == 2) x = __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-x)));
+          else if (act == 3) x = x > 0.f ? x : __fmul_rn(0.02f, x);
+          if (!pre_add) x += add;
+          float* dst = d.C + m * d.c_ld_r + (int64_t)n * d.c_ld_c;
+          if (atomic) atomicAdd(dst, x);
+          else *dst = d.beta ? *dst + x : x;
+        }
+      }
+    }
+    tcgen05_fence_before();
+  }
+  __syncthreads();
+  tcgen05_fence_after();
+  if (warp == 12) tmem_dealloc(tmem_base, 256);
+}
+
+}  // namespace gemm
+}  // namespace dfn
+
+using namespace dfn;
+
+extern "C" int dfn_gemm(const dfn_gemm_desc* d, void* stream) {
+  DFN_CHECK_ARG(d && d->A && d->B && d->C && d->M > 0 && d->N > 0 && d->K > 0, "dfn_gemm: null operand or empty shape");
+  DFN_CHECK_ARG(d->N <= gemm::BN_MAX, "dfn_gemm: N = %d > %d output columns per call", d->N, gemm::BN_MAX);
+  DFN_CHECK_ARG(d->precision == DFN_PREC_BF16X3 || d->precision == DFN_PREC_BF16, "dfn_gemm: precision must be BF16X3 or BF16");
+  DFN_CHECK_ARG(d->act >= 0 && d->act <= 7 && d->a_mask_mode >= 0 && d->a_mask_mode <= 3, "dfn_gemm: bad act / mask mode");
+  DFN_CHECK_ARG(d->A_mask == nullptr || d->a_mask_mode != 0, "dfn_gemm: A_mask given without a mask mode");
+  gemm::Params P;
+  memset(&P, 0, sizeof(P));
+  P.d = *d;
+  if (P.d.A_mask == nullptr) P.d.a_mask_mode = 0;
+  P.n_pad = (d->N + 15) / 16 * 16;
+  P.m_tiles = (d->M + gemm::BM - 1) / gemm::BM;
+  P.chunks = (d->K + gemm::BK - 1) / gemm::BK;
+  int splits = d->k_splits < 1 ? 1 : d->k_splits;
+  if (splits > P.chunks) splits = P.chunks;
+  P.per_split = (P.chunks + splits - 1) / splits;
+  splits = (P.chunks + P.per_split - 1) / P.per_split;   // no empty split
+  P.d.k_splits = splits;
+  DFN_CHECK_ARG(splits == 1 || ((d->act & 3) == 0 && d->beta == 1),
+                "dfn_gemm: a split-K call accumulates into C with atomics: it needs act = 0 and beta = 1 (C zeroed or running)");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t grid = (int64_t)P.m_tiles * splits;
+  DFN_CHECK_ARG(grid < (1ll << 31), "dfn_gemm: grid too large");
+  static bool attr_done[2] = {false, false};
+  if (d->precision == DFN_PREC_BF16X3) {
+    if (!attr_done[0]) {
+      DFN_CUDA(cudaFuncSetAttribute(gemm::gemm_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm::SMEM_TOTAL));
+      attr_done[0] = true;
+    }
+    gemm::gemm_tc_kernel<true><<<(int)grid, gemm::THREADS, gemm::SMEM_TOTAL, st>>>(P);
+  } else {
+    if (!attr_done[1]) {
+      DFN_CUDA(cudaFuncSetAttribute(gemm::gemm_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm::SMEM_TOTAL));
+      attr_done[1] = true;
+    }
+    gemm::gemm_tc_kernel<false><<<(int)grid, gemm::THREADS, gemm::SMEM_TOTAL, st>>>(P);
+  }
+  DFN_LAUNCH_CHECK();
+  return 0;
+}

@@ -353,6 +353,51 @@ int dfn_debug_trace(void* dev_buffer, int tiles);
 int dfn_debug_set_impl(int impl);
 int dfn_profile_collect(double* kernel_ms, int64_t* launches, double* algorithmic_macs);
 
+/* ---- f-3  training step  (MAIN:855-931: two-field forward on N_rand rays, img2mse x2, loss.backward(), Adam) ---------
+ * The three GEMMs of every nn.Linear -- forward, data gradient, weight gradient (what torch.autograd runs inside
+ * MAIN:923's loss.backward()) -- are ONE strided tcgen05 kernel: both operands carry a (row, k) stride pair, so no
+ * transposed copy of an activation, gradient or weight is ever made; operands are converted fp32 -> split bf16 in the
+ * kernel's loaders; the activation derivative is applied while the gradient operand is loaded.
+ *   C[m,n] = act( sum_k A(m,k) B(n,k) + bias[n] (+ addend[m,n] if act & 4) ) (+ addend[m,n] otherwise) (+ C[m,n] if beta)
+ *   A(m,k) = A[m*a_ld_r + k*a_ld_k] * mask'(A_mask[same index]);   B(n,k) = B[n*b_ld_r + k*b_ld_k];  N <= 256 per call.
+ * act & 3 as dfn_linear (0 none, 1 relu, 2 sigmoid, 3 LeakyReLU(0.02)).  k_splits > 1 splits the contraction over CTAs
+ * and accumulates with fp32 atomics into C (zeroed or running sums; needs act = 0, beta = 1).
+ * precision: DFN_PREC_BF16X3 (A_hi B_hi + A_lo B_hi + A_hi B_lo, fp32-level) or DFN_PREC_BF16. */
+enum { DFN_MASK_NONE = 0, DFN_MASK_RELU = 1, DFN_MASK_LEAKY = 2, DFN_MASK_SIGMOID = 3 };  /* act'(y) from the OUTPUT y */
+typedef struct {
+  const float* A; int64_t a_ld_r, a_ld_k;
+  const float* A_mask; int a_mask_mode;       /* nullable; same strides as A */
+  const float* B; int64_t b_ld_r, b_ld_k;
+  float* C; int64_t c_ld_r, c_ld_c;
+  const float* bias;                          /* [N], nullable */
+  const float* addend; int64_t add_ld_r, add_ld_c;   /* nullable; a row stride of 0 broadcasts one row */
+  int act;
+  int M, N, K;
+  int beta;
+  int k_splits;
+  int precision;
+} dfn_gemm_desc;
+int dfn_gemm(const dfn_gemm_desc* d, void* stream);
+
+/* Bias gradient: out[n] += sum_m X[m*ld + n] * act'(Y[m*ld + n]) (Y nullable / mask_mode 0: plain column sums). */
+int dfn_colsum(int64_t M, int N, const float* X, int64_t ld, const float* Y, int mask_mode, float* out, void* stream);
+
+/* MAIN:884-907 and its backward: the live two-field compositing of dfn_composite_head_torso, the two image losses
+ * loss2[0] += img2mse(rgb_head, target_head), loss2[1] += img2mse(rgb_person, target_person) (HELP:11; loss2 is
+ * accumulated into, zero it first), and the gradient of their sum with respect to the fields' outputs:
+ * dpre_* [R,S,3] = d loss / d (colour BEFORE the final sigmoid of DEC:346-347), dsigma_* [R,S] = d loss / d (raw density
+ * before MAIN:688's relu).  rgb_head / rgb_person (nullable) receive the rendered pixels.  S <= 128. */
+int dfn_head_torso_loss_bwd(int R, int S, const float* feat_head, const float* sigma_head, const float* feat_torso,
+                            const float* sigma_torso, const float* bc_rgb, const float* z_vals, const float* rays_d_head,
+                            const float* rays_d_torso, float last_dist, const float* target_head, const float* target_person,
+                            float* loss2, float* rgb_head, float* rgb_person, float* dpre_head, float* dsigma_head,
+                            float* dpre_torso, float* dsigma_torso, void* stream);
+
+/* torch.optim.Adam(lr, betas, eps) step number `step` (1-based) over one flat parameter group (MAIN:522-535, 924-931):
+ * parameters whose gradient is zero and whose moments are zero do not move, like parameters torch skips for grad=None. */
+int dfn_adam_step(int64_t n, float* params, const float* grads, float* exp_avg, float* exp_avg_sq, float lr, float beta1,
+                  float beta2, float eps, int step, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

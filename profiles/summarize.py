@@ -72,15 +72,68 @@ def report(tag, title):
     out.append('')
 
 
-launches()
-launches('_ht', 'bench.py --workload head_torso --steps 2 --warmup 3')
-report('bf16', 'mlp_tc_kernel<bf16>: 20,000 rays x 192 samples (fine-pass sized network query)')
-report('x3', 'mlp_pp_kernel<bf16x3>: 20,000 rays x 192 samples')
-report('dec_all', 'mlp_pp_kernel<bf16, Decoder>: 60,000 rays x 64 samples, head field then torso field (live model)')
-report('vw', 'volume_weights_kernel<1> (raw2outputs): 202,500 rays x 64 samples (coarse), then x 192 (fine)')
-report('headtorso', 'head_torso_kernel (live two-field compositing): 202,500 rays x 64 samples')
-report('sortmerge', 'sort_merge_kernel: 202,500 rays x (64 + 128)')
-report('samplepdf', 'sample_pdf_kernel: 202,500 rays, 63 bins -> 128 samples')
+TRAFFIC = {}
+
+
+def traffic(tag, kernel_name, points_per_launch, also=()):
+    """Per-point DRAM and L2->SM (TMA) bytes of a tcgen05 kernel from its ncu --set full capture of the bench's own launches
+    -> profiles/traffic.json (read by bench.py for roofline.traffic / l2_to_sm_bytes)."""
+    p = os.path.join(ROOT, 'gpurun_out', 'prof_%s_%s.ncu-rep' % (rnd, tag))
+    if not os.path.exists(p):
+        return
+    txt = subprocess.run(['ncu', '-i', p, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(txt)))
+    hdr, units = rows[0], rows[1]
+    mult = {'byte': 1, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9, 'Tbyte': 1e12}
+    dram = l2 = 0.0
+    for vals in rows[2:]:
+        d = {h: (u, v) for h, u, v in zip(hdr, units, vals)}
+        g = lambda k: float(d[k][1].replace(',', '')) * mult[d[k][0]]          # noqa: E731
+        dram += g('dram__bytes_read.sum') + g('dram__bytes_write.sum')
+        l2 += g('l1tex__m_xbar2l1tex_read_bytes_mem_global_op_tma_ld.sum')
+    pts = float(sum(points_per_launch))
+    rec = {'dram_bytes_per_point': dram / pts, 'l2_to_sm_bytes_per_point': l2 / pts,
+           'source': 'ncu --set full --clock-control none of the bench\'s own launches (profiles/ncu_summary_%s.txt, %s): %d launches, '
+                     '%.0f points' % (rnd, os.path.basename(p), len(rows) - 2, pts)}
+    TRAFFIC[kernel_name] = rec
+    for other in also:
+        TRAFFIC[other] = dict(rec, source=rec['source'] + '; same kernel schedule and data movement as ' + kernel_name)
+
+
+if rnd == 'r01':
+    launches()
+    launches('_ht', 'bench.py --workload head_torso --steps 2 --warmup 3')
+    report('bf16', 'mlp_tc_kernel<bf16>: 20,000 rays x 192 samples (fine-pass sized network query)')
+    report('x3', 'mlp_pp_kernel<bf16x3>: 20,000 rays x 192 samples')
+    report('dec_all', 'mlp_pp_kernel<bf16, Decoder>: 60,000 rays x 64 samples, head field then torso field (live model)')
+    report('vw', 'volume_weights_kernel<1> (raw2outputs): 202,500 rays x 64 samples (coarse), then x 192 (fine)')
+    report('headtorso', 'head_torso_kernel (live two-field compositing): 202,500 rays x 64 samples')
+    report('sortmerge', 'sort_merge_kernel: 202,500 rays x (64 + 128)')
+    report('samplepdf', 'sample_pdf_kernel: 202,500 rays, 63 bins -> 128 samples')
+else:
+    launches('', 'bench.py --steps 2 --warmup 3 --no-extras --no-cpu-baseline')
+    launches('_ht', 'bench.py --workload head_torso --steps 2 --warmup 3 --no-extras --no-cpu-baseline')
+    launches('_fused', 'bench.py --steps 2 --warmup 3 --no-extras --no-cpu-baseline (fused stage kernels)')
+    launches('_train', 'bench.py --workload train_step --steps 2 --warmup 3 --no-extras --no-cpu-baseline')
+    frame = 202500
+    report('bench_bf16', 'mlp_tc_kernel<bf16>: the bench frame\'s coarse (202,500 x 64) and fine (202,500 x 192) launches')
+    report('bench_x3', 'mlp_pp_kernel<bf16x3>: the bench frame\'s coarse and fine launches')
+    report('bench_dec', 'mlp_pp_kernel<bf16, Decoder>: the head_torso frame\'s head and torso launches (202,500 x 64 each)')
+    report('embed', 'embed_kernel (dfn_embed, HELP:21-52): 12.96 M points -> [P,63] (12 B in + 252 B out per point)')
+    report('stages', 'HBM-bound stage kernels of the bench frame')
+    report('gemm', 'gemm_tc_kernel (training step GEMMs)')
+    traffic('bench_bf16', 'mlp_tc_kernel<bf16>', [frame * 64, frame * 192], also=('mlp_tc_kernel<fp16>',))
+    traffic('bench_x3', 'mlp_pp_kernel<bf16x3>', [frame * 64, frame * 192])
+    traffic('bench_dec', 'mlp_pp_kernel<bf16, Decoder>', [frame * 64, frame * 64],
+            also=('mlp_pp_kernel<fp16, Decoder>', 'mlp_pp_kernel<bf16x3, Decoder>'))
+    if TRAFFIC:
+        import json
+        old = {}
+        tp = os.path.join(ROOT, 'profiles', 'traffic.json')
+        if os.path.exists(tp):
+            old = json.load(open(tp))
+        old.update(TRAFFIC)
+        json.dump(old, open(tp, 'w'), indent=1)
 path = os.path.join(ROOT, 'profiles', 'ncu_summary_%s.txt' % rnd)
 open(path, 'w').write('\n'.join(out) + '\n')
 print('\n'.join(out))

@@ -108,7 +108,7 @@ def test_query_points_bf16x3_vs_fp32_oracle(dfn, R, S):
 # in the last trunk layer moves sigma by gain x |w| x ulp ~ 3e-3 |sigma|max in bf16 (tests/test_quantized_cpu.py).  So the
 # max is gated at a few flips, p99 and the median far below, and everything is printed.
 #                 colours(sigmoid) max, sigma max / p99 / median as fractions of |sigma|max
-Q_GATE = {'bf16': (5e-5, 1e-2, 3e-3, 5e-4), 'fp16': (1e-5, 1.5e-3, 4e-4, 6e-5)}
+Q_GATE = {'bf16': (1.5e-4, 2e-2, 4e-3, 1e-5), 'fp16': (1e-4, 4e-3, 1e-3, 2e-6)}
 
 
 def _gate_quantized(tag, prec_name, raw, refq, ref32):
@@ -125,7 +125,7 @@ def _gate_quantized(tag, prec_name, raw, refq, ref32):
     assert torch.isfinite(raw).all()
     assert ec <= gc and mx <= gm * smax and p99 <= g99 * smax and med <= gmed * smax, (tag, ec, mx / smax, p99 / smax, med / smax)
     # the restatement explains the kernel: far closer to it than to the fp32 forward
-    assert med < 0.2 * med32 and p99 < 0.5 * p9932, (tag, med, med32, p99, p9932)
+    assert med < 0.02 * med32 and p99 < p9932, (tag, med, med32, p99, p9932)
 
 
 def _face_x(ro, rd, vd, z, aud):
