@@ -8,6 +8,8 @@
     python bench.py --workload coarse64         # configs[0]: 64x64 rays x 64 coarse samples (the reference's CPU-sized case)
     python bench.py --workload mlp_1m           # configs[3]: flat 8x256 NeRF query, 2^20 rays x 192 samples (roofline sweep)
     python bench.py --workload sequence --steps 1   # configs[4]: driven sequence (--frames N, default 300), frames sharded
+    python bench.py --workload train_step       # the reference's training step (2048 rays x 64 samples x 2 fields,
+                                                # forward + backward + Adam), value = training rays/s
 
 One step = one 450x450 frame (202,500 rays) x (64 coarse + 128 fine samples) of the synthetic
 FaceNeRF field (configs[1] of BASELINE.json): get_rays -> z sampling -> PE + 8x256 skip-MLP ->
@@ -203,6 +205,9 @@ WORKLOADS = {
     'sequence': 'Audio-driven FaceNeRF sequence, 450x450 x (64+128) per frame, per-frame pose + latent tables, uint8 frames '
                 'copied out double-buffered, FRAMES sharded over the GPUs (BASELINE.json configs[4]); one step = the sequence',
 }
+WORKLOADS['train_step'] = 'Training step of the live model (MAIN:764-931): 2048 random rays x 64 samples x (head + torso) Decoder fields, ' \
+                          'two-field compositing, two MSE losses, backward, Adam on decoder + AudNet + ExpNet; synthetic 450x450 targets; ' \
+                          'one step = one optimiser step (single GPU: the reference trains on one)'
 EVALS = {'facenerf': '(64+192) FaceNeRF', 'head_torso': '(64 head + 64 torso) Decoder', 'coarse64': '64 FaceNeRF'}
 
 
@@ -282,6 +287,34 @@ class Job:
             self.evals_per_ray = S
             self.kernel_name = tc_name
             self.flops_note = 'algorithmic, viewdir columns folded: 2*557,184 per MLP evaluation (NeRF and FaceNeRF coincide, SURVEY 8d)'
+        elif workload == 'train_step':
+            from dfa_nerf_b200.train import Trainer, select_coords
+            import numpy as np
+            if world > 1:
+                raise SystemExit('--workload train_step is single-GPU (the reference trains on one GPU; no gradient exchange is built)')
+            dec = dfn.Decoder(z_dim=256, hidden_size=256, dim_signal=96, use_deformation_field=True)
+            dec.load_state_dict(synth.decoder_state_dict(0))
+            aud, exp = dfn.AudioNet_W2L(), dfn.ExpressionEnc()
+            aud.load_state_dict(synth.mlp_encoder_state_dict(7))
+            exp.load_state_dict(synth.mlp_encoder_state_dict(8, (64, 32, 32)))
+            tprec = dfn.PREC_BF16X3 if precision in ('bf16x3', 'fp32') else dfn.PREC_BF16
+            self.trainer = Trainer(dec, aud, exp, lrate=5e-4, N_samples=N_SAMPLES, precision=tprec, device=dev)
+            g = torch.Generator().manual_seed(3)
+            poses = torch.cat([synth.pose_sequence(8, 0), torch.tensor([0., 0., 0., 1.]).expand(8, 1, 4)], 1)
+            self.host_imgs = [torch.rand(H, W, 3, generator=g).pin_memory() for _ in range(3)]     # target_com, target_head_neck, bc
+            np.random.seed(0)
+            self.batch = dict(H=H, W=W, focal=fr['focal'], cx=fr['cx'], cy=fr['cy'], near=fr['near'], far=fr['far'], poses=poses, img_i=3,
+                              pose=poses[3, :3, :4], pose_torso=poses[0, :3, :4], auds=torch.randn(8, 512, generator=g).to(dev),
+                              exps=torch.randn(8, 64, generator=g).to(dev), coords=select_coords(H, W, [100, 125, 200, 200], 2048, 0.95).to(dev),
+                              target_com=self.host_imgs[0].to(dev), target_head_neck=self.host_imgs[1].to(dev), bc_img=self.host_imgs[2].to(dev),
+                              z_shape=torch.randn(1, 2, 256, generator=g).to(dev), z_app=torch.randn(1, 2, 256, generator=g).to(dev))
+            self.n_rays, self.b, self.e = 2048, 0, 2048
+            self.evals_per_ray = 2 * N_SAMPLES
+            self.kernel_name = 'gemm_tc_kernel<%s>' % ('bf16x3' if tprec == dfn.PREC_BF16X3 else 'bf16')
+            self.flops_note = 'algorithmic 2*M*N*K of every GEMM launch of the step (forward, data and weight gradients, per-frame ' \
+                              'vector products); bf16x3 issues three MMAs per product and counts once'
+            self.gstep = 0
+            self.lat_host = torch.zeros(1).pin_memory()
         elif workload == 'sequence':
             self.eng = dfn.RenderEngine(mk(0), mk(1), N_SAMPLES, N_IMPORTANCE, precision=prec)
             self.seq = synth.frame_inputs(H=H, W=W, seed=0, n_frames=args.frames)
@@ -308,7 +341,7 @@ class Job:
             self.kernel_name = 'mlp_pp_kernel<%s, Decoder>' % precision
             self.flops_note = 'algorithmic, per-frame latents and per-ray view term folded: 2*556,032 (head) + 2*628,352 (torso ' \
                               'incl. deformation field) per sample (SURVEY.md section 8d, appendix A)'
-        if workload != 'sequence':
+        if workload not in ('sequence', 'train_step'):
             self.rgb_host = torch.empty((self.n_rays, 3), dtype=torch.float32).pin_memory()
 
     # -- one frame on this rank's ray range
@@ -338,8 +371,21 @@ class Job:
         self.launches += (self.eng.last_launches + 2) * ((n + world - 1) // world)
         return frames
 
+    def step_train(self, e2e=False):
+        b = self.batch
+        if e2e:     # the step's images come from the host (the reference reads three JPEGs per step, MAIN:771-774); the loss goes back
+            b = dict(b, target_com=self.host_imgs[0].to(self.ctx['dev'], non_blocking=True),
+                     target_head_neck=self.host_imgs[1].to(self.ctx['dev'], non_blocking=True),
+                     bc_img=self.host_imgs[2].to(self.ctx['dev'], non_blocking=True))
+        loss = self.trainer.step(b, global_step=self.gstep)
+        self.gstep += 1
+        self.launches += self.trainer.last_launches
+        return float(loss) if e2e else loss
+
     def step_resident(self):
         from dfa_nerf_b200.distributed import gather_rgb
+        if self.workload == 'train_step':
+            return self.step_train()
         if self.workload == 'sequence':
             return self.step_sequence()
         rgb = self.render(self.bc_dev, self.aud_dev)
@@ -348,6 +394,8 @@ class Job:
     def step_e2e(self):
         from dfa_nerf_b200.distributed import gather_rgb
         torch, dev = self.torch, self.ctx['dev']
+        if self.workload == 'train_step':
+            return self.step_train(e2e=True)
         if self.workload == 'sequence':
             return self.step_sequence()
         bc = self.bc_host[self.b:self.e].to(dev, non_blocking=True)
@@ -369,6 +417,8 @@ class Job:
         return (self.e - self.b) * self.evals_per_ray
 
     def bytes_per_step(self):
+        if self.workload == 'train_step':
+            return int(3 * H * W * 3 * 4), 4
         if self.workload == 'sequence':
             return int(self.lat_host.numel() * 4 + self.frames * 48), int(self.n_rays * 3)
         return int((self.e - self.b) * 12 + self.lat_host.numel() * 4 + 48), (int(self.n_rays * 12) if self.ctx['rank'] == 0 else 0)
@@ -540,14 +590,20 @@ def main():
                            'frac': r['roofline']['frac'] if r['roofline'] else None,
                            'kernel': r['roofline']['kernel'] if r['roofline'] else None}
     if extras and args.workload == 'facenerf':
-        for wl, key, steps in (('head_torso', 'head_torso', max(3, min(args.steps, 5))), ('coarse64', 'coarse64', 10),
-                               ('sequence', 'sequence_%d' % args.frames, 1)):
-            j = Job(wl, args.precision, args, ctx)
+        plan = [('head_torso', 'head_torso', max(3, min(args.steps, 5))), ('coarse64', 'coarse64', 10),
+                ('sequence', 'sequence_%d' % args.frames, 1)]
+        if world == 1:
+            plan.append(('train_step', 'train_step', 10))
+        for wl, key, steps in plan:
+            j = Job(wl, 'bf16x3' if wl == 'train_step' else args.precision, args, ctx)
             r = measure(ctx, j, steps, 3)
             extra[key] = {'workload': WORKLOADS[wl], 'value': r['value'], 'unit': 'rays/s', 'ms_per_step': r['ms_per_step'],
                           'rays_per_step': j.n_rays, 'e2e': r['e2e'], 'gpu_launches': r['gpu_launches'], 'steps': steps,
                           'frac': r['roofline']['frac'] if r['roofline'] else None,
                           'kernel_share_of_step': r['roofline']['kernel_share_of_step'] if r['roofline'] else None}
+            if wl == 'train_step':
+                extra[key]['precision'] = 'bf16x3'
+                extra[key]['points_per_step'] = j.points_per_step()
             if wl == 'sequence':
                 extra[key]['frames'] = args.frames
                 extra[key]['ms_per_frame'] = r['ms_per_step'] / args.frames
@@ -580,7 +636,7 @@ def main():
             'config': {'workload': WORKLOADS[args.workload],
                        'rays_per_step': job.n_rays, 'mlp_evals_per_ray': job.evals_per_ray, 'precision': args.precision,
                        'parallelism': ('frames sharded over %d GPU(s), uint8 frames gathered to rank 0 per frame' % world)
-                       if args.workload == 'sequence' else 'rays sharded over %d GPU(s), one all-gather of the RGB tile' % world,
+                       if args.workload == 'sequence' else 'single GPU' if args.workload == 'train_step' else 'rays sharded over %d GPU(s), one all-gather of the RGB tile' % world,
                        'l2': 'per-step intermediates (~1.4 GB of raw/z buffers) exceed the 126 MB L2; no explicit flush'},
             'e2e': main_res['e2e'], 'gpu_launches': main_res['gpu_launches'], 'clocks': clocks, 'roofline': main_res['roofline'],
             'cpu_baseline': cpu, 'modes': modes or None, 'parity': parity, 'extra': extra or None,

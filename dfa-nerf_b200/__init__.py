@@ -18,8 +18,9 @@ from .sequence import render_sequence, render_sequence_head_torso, shard_frames,
 from .load_audface import load_audface_data_split, dataset_to_device, pose_body  # noqa: F401
 from .frame_io import FrameWriter, write_video  # noqa: F401
 from .render_person import render_person  # noqa: F401
+from .train import Trainer, select_coords  # noqa: F401
 
 __all__ = ['get_rays', 'get_embedder', 'Embedder', 'decoder_transform_points', 'z_vals_uniform', 'make_points',
            'calc_volume_weights', 'composite_function', 'raw2outputs', 'sample_pdf', 'invert_cdf', 'sort_merge',
            'NeRF', 'FaceNeRF', 'Decoder', 'DeformationField_ori', 'render_head_torso', 'render', 'render_rays', 'batchify_rays', 'run_network', 'RenderEngine',
-           'render_sharded', 'shard_range', 'AudioNet', 'AudioNet_W2L', 'ExpressionEnc', 'AudioAttNet', 'encode_signal', 'encode_signal_torso', 'encode_signal_sequence', 'encode_signal_torso_sequence', 'pose_to_euler_trans', 'render_sequence', 'render_sequence_head_torso', 'shard_frames', 'FrameSink', 'to8b', 'load_audface_data_split', 'dataset_to_device', 'pose_body', 'FrameWriter', 'write_video', 'render_person', 'lib', 'DfnError', 'PREC_FP32', 'PREC_BF16', 'PREC_FP16', 'PREC_BF16X3']
+           'render_sharded', 'shard_range', 'AudioNet', 'AudioNet_W2L', 'ExpressionEnc', 'AudioAttNet', 'encode_signal', 'encode_signal_torso', 'encode_signal_sequence', 'encode_signal_torso_sequence', 'pose_to_euler_trans', 'render_sequence', 'render_sequence_head_torso', 'shard_frames', 'FrameSink', 'to8b', 'load_audface_data_split', 'dataset_to_device', 'pose_body', 'FrameWriter', 'write_video', 'render_person', 'Trainer', 'select_coords', 'lib', 'DfnError', 'PREC_FP32', 'PREC_BF16', 'PREC_FP16', 'PREC_BF16X3']

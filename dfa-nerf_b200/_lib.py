@@ -50,6 +50,15 @@ class HeadTorsoIO(C.Structure):
                                           'rgb_person')] + [('last_dist', C.c_float)]
 
 
+class GemmDesc(C.Structure):
+    _fields_ = [('A', C.c_void_p), ('a_ld_r', C.c_int64), ('a_ld_k', C.c_int64), ('A_mask', C.c_void_p), ('a_mask_mode', C.c_int),
+                ('B', C.c_void_p), ('b_ld_r', C.c_int64), ('b_ld_k', C.c_int64),
+                ('C', C.c_void_p), ('c_ld_r', C.c_int64), ('c_ld_c', C.c_int64),
+                ('bias', C.c_void_p), ('addend', C.c_void_p), ('add_ld_r', C.c_int64), ('add_ld_c', C.c_int64),
+                ('act', C.c_int), ('M', C.c_int), ('N', C.c_int), ('K', C.c_int), ('beta', C.c_int), ('k_splits', C.c_int),
+                ('precision', C.c_int)]
+
+
 def _load():
     if not os.path.exists(LIB_PATH):
         raise ImportError('dfa_nerf_b200: %s is missing -- run `python -c "import __graft_entry__ as g; g.build()"` '
@@ -102,6 +111,10 @@ def _load():
         'dfn_decoder_program_host': (i32, [C.POINTER(DecoderDesc), C.POINTER(vp), i32, i32, i32, i32, C.POINTER(LayerInfo),
                                            C.POINTER(i32), vp, vp, C.POINTER(i32), C.POINTER(i32), vp, C.POINTER(i32),
                                            C.POINTER(i32), vp]),
+        'dfn_gemm': (i32, [C.POINTER(GemmDesc), vp]),
+        'dfn_colsum': (i32, [i64, i32, vp, i64, vp, i32, vp, vp]),
+        'dfn_head_torso_loss_bwd': (i32, [i32, i32] + [vp] * 8 + [f32] + [vp] * 9 + [vp]),
+        'dfn_adam_step': (i32, [i64, vp, vp, vp, vp, f32, f32, f32, f32, i32, vp]),
         'dfn_render_head_torso_workspace_bytes': (i64, [vp, i64, i32]),
         'dfn_render_head_torso': (i32, [vp, i64, i32, C.POINTER(HeadTorsoIO), i32, vp, i64, vp]),
     }
@@ -121,7 +134,8 @@ EXPORTS = ['dfn_abi_version', 'dfn_last_error', 'dfn_last_launch_count', 'dfn_pr
            'dfn_mlp_workspace_bytes', 'dfn_mlp_forward', 'dfn_query_workspace_bytes', 'dfn_query_points',
            'dfn_render_workspace_bytes', 'dfn_render_rays', 'dfn_decoder_create', 'dfn_decoder_destroy',
            'dfn_decoder_num_tensors', 'dfn_decoder_load', 'dfn_decoder_query_workspace_bytes', 'dfn_decoder_query',
-           'dfn_decoder_macs_per_sample', 'dfn_decoder_program_host', 'dfn_model_program_host', 'dfn_render_head_torso_workspace_bytes', 'dfn_render_head_torso']
+           'dfn_decoder_macs_per_sample', 'dfn_decoder_program_host', 'dfn_model_program_host', 'dfn_render_head_torso_workspace_bytes', 'dfn_render_head_torso',
+           'dfn_gemm', 'dfn_colsum', 'dfn_head_torso_loss_bwd', 'dfn_adam_step']
 
 
 def check(rc, what=''):

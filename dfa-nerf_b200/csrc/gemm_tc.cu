@@ -258,6 +258,7 @@ extern "C" int dfn_gemm(const dfn_gemm_desc* d, void* stream) {
   const int64_t grid = (int64_t)P.m_tiles * splits;
   DFN_CHECK_ARG(grid < (1ll << 31), "dfn_gemm: grid too large");
   static bool attr_done[2] = {false, false};
+  const bool prof = profile_begin(st, (double)d->M * (double)d->N * (double)d->K);
   if (d->precision == DFN_PREC_BF16X3) {
     if (!attr_done[0]) {
       DFN_CUDA(cudaFuncSetAttribute(gemm::gemm_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm::SMEM_TOTAL));
@@ -271,6 +272,7 @@ extern "C" int dfn_gemm(const dfn_gemm_desc* d, void* stream) {
     }
     gemm::gemm_tc_kernel<false><<<(int)grid, gemm::THREADS, gemm::SMEM_TOTAL, st>>>(P);
   }
+  if (prof) profile_end(st);
   DFN_LAUNCH_CHECK();
   return 0;
 }

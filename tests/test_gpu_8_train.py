@@ -1,0 +1,254 @@
+"""GPU parity of the training step (MAIN:764-931): the strided tcgen05 GEMM against fp64 matmuls over every
+stride / mask / epilogue combination the tape uses, the bias-gradient, compositing-loss-backward and Adam kernels against
+the torch statements of their contracts (tests/test_train_tape_cpu.py), and two whole steps against the reference's golden
+vectors (tests/golden/train_step.npz: loss, gradients, updated parameters) and against torch.autograd over the oracle for all
+74 gradient tensors.  Tolerance: 1e-4 relative (bf16x3 products are fp32-level; the batch reduction order differs)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import synth
+from oracle import train_oracle as TO
+
+from test_train_oracle_golden import make_batch, GOLD, NS, LRATE
+from test_train_tape_cpu import ref_mm, ref_colsum, ref_loss_bwd, ref_adam
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda'
+
+
+@pytest.fixture(scope='module')
+def train():
+    from dfa_nerf_b200 import train
+    return train
+
+
+def rel(a, b):
+    b = b.double()
+    return ((a.detach().cpu().double() - b).abs().max() / (b.abs().max() + 1e-30)).item()
+
+
+CASES = [
+    # M, N, K, A layout, B layout, kwargs
+    (300, 256, 256, 'rk', 'rk', {}),                                          # forward: X [P,K] row-major, W [N,K]
+    (1000, 256, 60, 'rk', 'rk', dict(bias=True, act=1)),                      # K < 64, bias + relu
+    (257, 64, 102, 'rk', 'rk', dict(bias=True, act=3)),                       # unaligned leading dimension -> scalar loads; leaky
+    (129, 3, 256, 'rk', 'rk', dict(bias=True, act=2)),                        # N = 3 (feat_out), sigmoid
+    (777, 1, 256, 'rk', 'rk', dict(bias=True)),                               # N = 1 (sigma_out)
+    (500, 256, 256, 'rk', 'kr', dict(mask=1)),                                # data grad: B = W^T view, relu mask on A
+    (500, 156, 256, 'rk', 'kr', dict(mask=2, beta=1)),                        # accumulate into an existing dX, leaky mask
+    (256, 256, 5000, 'kr', 'kr', dict(mask=1, beta=1, k_splits=40)),          # weight grad: A = dH^T, B = X^T, split-K atomics
+    (64, 102, 3000, 'kr', 'kr', dict(beta=1, k_splits=7)),                    # ragged M and N tiles
+    (3, 256, 2000, 'kr', 'kr', dict(mask=3, beta=1, k_splits=200)),           # more splits than chunks
+    (1, 64, 512, 'rk', 'rk', dict(bias=True, act=3)),                         # per-frame vectors: M = 1
+    (256, 512, 1, 'kr', 'kr', dict(beta=1)),                                  # outer product, N > 256 (two launches)
+    (1, 96, 256, 'rk', 'kr', dict(beta=1, mask=2)),
+    (400, 128, 128, 'rk', 'rk', dict(bias=True, addend='post')),              # additive skip after the (absent) activation
+    (400, 256, 24, 'rk', 'rk', dict(addend='pre', act=1)),                    # view layer: addend before the relu
+    (400, 42, 64, 'rk', 'rk', dict(bias=True, addend='bcast', strided_out=True)),   # broadcast-row addend, column-slice output
+]
+
+
+def build_case(case):
+    """Host tensors of one GEMM case with the strides the tape produces (.t() views, column slices, broadcast rows)."""
+    M, N, K, la, lb, kw = CASES[case]
+    g = torch.Generator().manual_seed(case)
+
+    def mat(r, c, layout, pad=0):
+        if layout == 'rk':                                   # (row, k) strides (ld, 1)
+            return torch.randn(r, c + pad, generator=g)[:, :c]
+        return torch.randn(c, r + pad, generator=g)[:, :r].t()    # (1, ld)
+    A, B = mat(M, K, la, 1 if case == 2 else 0), mat(N, K, lb)
+    mask_mode = kw.get('mask', 0)
+    mask = None
+    if mask_mode:
+        mask = torch.empty_strided(A.shape, A.stride())
+        mask.copy_(torch.rand(A.shape, generator=g) - (0. if mask_mode == 3 else 0.4))
+    bias = torch.randn(N, generator=g) if kw.get('bias') else None
+    addend, pre = None, False
+    if kw.get('addend') == 'post':
+        addend = torch.randn(M, N, generator=g)
+    elif kw.get('addend') == 'pre':
+        addend, pre = torch.randn(M, N, generator=g), True
+    elif kw.get('addend') == 'bcast':
+        addend = torch.randn(N, generator=g)[None, :].expand(M, N)
+    Cfull = torch.randn(M, N + 60, generator=g) if kw.get('strided_out') else torch.randn(M, N, generator=g)
+    return A, B, mask, mask_mode, bias, addend, pre, Cfull
+
+
+@pytest.mark.parametrize('case', range(len(CASES)))
+@pytest.mark.parametrize('precision', ['bf16x3', 'bf16'])
+def test_gemm_against_fp64(train, case, precision):
+    import dfa_nerf_b200 as dfn
+    M, N, K, la, lb, kw = CASES[case]
+    A, B, mask, mask_mode, bias, addend, pre, Cfull = build_case(case)
+    so = bool(kw.get('strided_out'))
+    ref = (Cfull[:, 60:] if so else Cfull).clone()
+    ref_mm(A, B, ref, bias=bias, addend=addend, pre_add=pre, act=kw.get('act', 0), mask=mask, mask_mode=mask_mode, beta=kw.get('beta', 0),
+           k_splits=kw.get('k_splits', 1))
+
+    def to_dev(t):
+        if t is None:
+            return None
+        if t.dim() == 2 and t.stride(0) == 0:
+            return t[:1].contiguous().to(DEV).expand(t.shape)
+        d = torch.empty_strided(t.shape, t.stride(), device=DEV)
+        d.copy_(t)
+        return d
+    Cd_full = Cfull.to(DEV)
+    Cd = Cd_full[:, 60:] if so else Cd_full
+    prec = dfn.PREC_BF16X3 if precision == 'bf16x3' else dfn.PREC_BF16
+    train.mm(to_dev(A), to_dev(B), Cd, bias=to_dev(bias), addend=to_dev(addend), pre_add=pre, act=kw.get('act', 0), mask=to_dev(mask),
+             mask_mode=mask_mode, beta=kw.get('beta', 0), k_splits=kw.get('k_splits', 1), precision=prec)
+    torch.cuda.synchronize()
+    e = rel(Cd, ref)
+    print('gemm case %d %s: M=%d N=%d K=%d %s/%s %s -> rel err %.2e' % (case, precision, M, N, K, la, lb, kw, e))
+    assert torch.isfinite(Cd).all()
+    assert e < (2e-5 if precision == 'bf16x3' else 2e-2), e
+    if so:
+        assert torch.equal(Cd_full[:, :60].cpu(), Cfull[:, :60])          # the columns next to the output view are untouched
+
+
+def test_colsum(train):
+    g = torch.Generator().manual_seed(0)
+    for M, N, mode in ((5000, 256, 1), (1, 64, 2), (777, 3, 0), (1300, 102, 3)):
+        X = torch.randn(M, N + 4, generator=g)[:, :N]
+        Y = (torch.rand(M, N + 4, generator=g) - (0.5 if mode != 3 else 0.))[:, :N]
+        out = torch.randn(N, generator=g)
+        ref = out.clone()
+        ref_colsum(X, Y, mode, ref)
+        Xd, Yd = torch.empty_strided(X.shape, X.stride(), device=DEV), torch.empty_strided(Y.shape, Y.stride(), device=DEV)
+        Xd.copy_(X)
+        Yd.copy_(Y)
+        od = out.to(DEV)
+        train.colsum(Xd, Yd, mode, od)
+        assert rel(od, ref) < 1e-5, (M, N, mode)
+
+
+@pytest.mark.parametrize('R,S', [(96, 16), (300, 64), (37, 100)])
+def test_loss_backward_kernel(train, R, S):
+    g = torch.Generator().manual_seed(R)
+    feat_h, feat_t = torch.rand(R * S, 3, generator=g), torch.rand(R * S, 3, generator=g)
+    sig_h = torch.randn(R * S, 1, generator=g) * 8
+    sig_t = torch.randn(R * S, 1, generator=g) * 8
+    sig_h[:7] = 0.                                  # den == 0 entries (both fields empty) and relu'(0) = 0
+    sig_t[:9] = -1.
+    z, _ = torch.sort(torch.rand(R, S, generator=g) * 0.6 + 0.4, -1)
+    rd_h = torch.randn(R, 3, generator=g) * 0.2 + torch.tensor([0., 0., -1.])
+    rd_t = torch.randn(R, 3, generator=g) * 0.2 + torch.tensor([0., 0., -1.])
+    bc, t0, t1 = [torch.rand(R, 3, generator=g) for _ in range(3)]
+    outs = dict(loss2=torch.zeros(2), rgb_head=torch.zeros(R, 3), rgb_person=torch.zeros(R, 3), g_feat_h=torch.zeros(R * S, 3),
+                g_sig_h=torch.zeros(R * S, 1), g_feat_t=torch.zeros(R * S, 3), g_sig_t=torch.zeros(R * S, 1))
+    ref = {k: v.clone() for k, v in outs.items()}
+    ref_loss_bwd(R, S, feat_h, sig_h, feat_t, sig_t, bc, z, rd_h, rd_t, t0, t1, **ref)
+    d = {k: v.to(DEV) for k, v in outs.items()}
+    train.loss_bwd(R, S, *[t.to(DEV) for t in (feat_h, sig_h, feat_t, sig_t, bc, z, rd_h, rd_t, t0, t1)], **d)
+    torch.cuda.synchronize()
+    for k in outs:
+        e = rel(d[k], ref[k])
+        print('loss_bwd R=%d S=%d %-10s rel err %.2e (|ref|max %.2e)' % (R, S, k, e, ref[k].abs().max().item()))
+        assert e < 5e-5, (k, e)
+
+
+def test_adam_kernel(train):
+    g = torch.Generator().manual_seed(1)
+    n = 100003
+    p, m, v = torch.randn(n, generator=g), torch.zeros(n), torch.zeros(n)
+    pd, md, vd = p.to(DEV), m.to(DEV), v.to(DEV)
+    for step in range(1, 4):
+        grad = torch.randn(n, generator=g) * 10 ** float(torch.randint(-6, 1, (1,), generator=g))
+        grad[::7] = 0.
+        ref_adam(p, grad, m, v, 5e-4, (0.9, 0.999), 1e-8, step)
+        train.adam_step(pd, grad.to(DEV), md, vd, 5e-4, (0.9, 0.999), 1e-8, step)
+        assert (pd.cpu() - p).abs().max().item() < 1e-6 and rel(md, m) < 1e-5 and rel(vd, v) < 1e-5
+
+
+def _modules():
+    import dfa_nerf_b200 as dfn
+    sds = {'dec': synth.decoder_state_dict(6), 'aud': synth.mlp_encoder_state_dict(7), 'exp': synth.mlp_encoder_state_dict(8, (64, 32, 32))}
+    dec = dfn.Decoder(z_dim=256, hidden_size=256, dim_signal=96, use_deformation_field=True)
+    dec.load_state_dict(sds['dec'])
+    aud, exp = dfn.AudioNet_W2L(), dfn.ExpressionEnc()
+    aud.load_state_dict(sds['aud'])
+    exp.load_state_dict(sds['exp'])
+    return sds, dec, aud, exp
+
+
+def test_two_training_steps_match_the_reference(train):
+    """Golden vectors of the REFERENCE's own modules (oracle/make_golden_train.py) + every gradient tensor against autograd
+    over the oracle on the CPU."""
+    gold = np.load(GOLD)
+    b = make_batch()
+    sds, dec, aud, exp = _modules()
+    params = {k: {n: v.clone().requires_grad_(True) for n, v in sd.items()} for k, sd in sds.items()}
+    opt = {k: torch.optim.Adam(params=list(params[k].values()), lr=LRATE, betas=(0.9, 0.999)) for k in params}
+    bd = {k: (v.to(DEV) if torch.is_tensor(v) and k in ('target_com', 'target_head_neck', 'bc_img') else v) for k, v in b.items()}
+    tr = train.Trainer(dec, aud, exp, lrate=LRATE, N_samples=NS)
+    picks = [k for k in gold.files if k.startswith('grad0/')]
+    for step in range(2):
+        loss_ref = TO.train_step(params, b, opt, global_step=step, noexp_iters=0, N_samples=NS)
+        loss = tr.step(bd, global_step=step, noexp_iters=0)
+        torch.cuda.synchronize()
+        assert abs(float(loss) - float(gold['loss%d' % step])) <= 1e-4 * float(gold['loss%d' % step]), (step, float(loss))
+        assert abs(float(loss) - float(loss_ref)) <= 1e-4 * float(loss_ref)
+        worst = 0.
+        n_checked = 0
+        for k in params:
+            for n, q in params[k].items():
+                gq = tr.grads[k][n].cpu()
+                if q.grad is None:
+                    assert not gq.any(), (k, n)
+                    continue
+                e = rel(gq, q.grad)
+                worst = max(worst, e)
+                assert e <= 1e-4, (step, k, n, e)
+                n_checked += 1
+                assert (tr.params[k][n].cpu() - q.detach()).abs().max().item() <= 0.05 * LRATE, (step, k, n)
+        assert n_checked == 74
+        for key in picks:
+            _, k, n = key.split('/')
+            gq = tr.grads[k][n].cpu()
+            gn = float(gold['gradnorm%d/%s/%s' % (step, k, n)])
+            assert abs(float(gq.double().norm()) - gn) <= 1e-4 * gn + 1e-9, (step, k, n)
+            refs = gold['grad%d/%s/%s' % (step, k, n)]
+            assert np.abs(gq.reshape(-1)[:64].numpy() - refs).max() <= 1e-4 * np.abs(refs).max() + 1e-9, (step, k, n)
+            pref = gold['param%d/%s/%s' % (step, k, n)]
+            assert np.abs(tr.params[k][n].cpu().reshape(-1)[:64].numpy() - pref).max() <= 0.05 * LRATE, (step, k, n)
+        print('training step %d: loss %.9f (golden %.9f), worst relative gradient error over 74 tensors %.2e, %d launches'
+              % (step, float(loss), float(gold['loss%d' % step]), worst, tr.last_launches))
+    # the trained weights are what the render path now sees
+    assert dec.fc_in.weight.data_ptr() == tr.params['dec']['fc_in.weight'].data_ptr()
+
+
+def test_training_step_full_size_properties(train):
+    """The reference's batch size (N_rand 2048 x 64 samples x 2 fields, scripts/train_obama.sh): finite loss and gradients, the
+    loss decreases over a few Adam steps on a fixed batch, bf16 single-pass gradients agree with bf16x3 to operand precision."""
+    import dfa_nerf_b200 as dfn
+    import synth as S
+    Hh = Ww = 128
+    g = torch.Generator().manual_seed(5)
+    fr = S.frame_inputs(H=Hh, W=Ww, seed=1)
+    poses = torch.cat([S.pose_sequence(4, 3), torch.tensor([0., 0., 0., 1.]).expand(4, 1, 4)], 1)
+    np.random.seed(0)
+    batch = dict(H=Hh, W=Ww, focal=fr['focal'], cx=fr['cx'], cy=fr['cy'], near=fr['near'], far=fr['far'], poses=poses, img_i=1,
+                 pose=poses[1, :3, :4], pose_torso=poses[0, :3, :4], auds=torch.randn(4, 512, generator=g), exps=torch.randn(4, 64, generator=g),
+                 coords=train.select_coords(Hh, Ww, [30, 30, 60, 60], 2048, 0.95),
+                 target_com=torch.rand(Hh, Ww, 3, generator=g).to(DEV), target_head_neck=torch.rand(Hh, Ww, 3, generator=g).to(DEV),
+                 bc_img=torch.rand(Hh, Ww, 3, generator=g).to(DEV), z_shape=torch.randn(1, 2, 256, generator=g),
+                 z_app=torch.randn(1, 2, 256, generator=g))
+    grads = {}
+    for name, prec in (('bf16x3', dfn.PREC_BF16X3), ('bf16', dfn.PREC_BF16)):
+        _, dec, aud, exp = _modules()
+        tr = train.Trainer(dec, aud, exp, lrate=5e-4, N_samples=64, precision=prec)
+        l0 = float(tr.losses_and_grads(batch))
+        assert np.isfinite(l0)
+        grads[name] = {k: {n: t.clone() for n, t in tr.grads[k].items()} for k in tr.grads}
+        for k in tr.grads:
+            assert all(torch.isfinite(t).all() for t in tr.grads[k].values())
+        if name == 'bf16x3':
+            losses = [float(tr.step(batch, global_step=i)) for i in range(6)]
+            assert losses[-1] < losses[0], losses
+            print('2048 rays x 64 x 2 fields: loss over 6 Adam steps on a fixed batch %s; %d launches per step' %
+                  (['%.5f' % v for v in losses], tr.last_launches))
+    a, c = grads['bf16x3']['dec']['blocks.3.weight'], grads['bf16']['dec']['blocks.3.weight']
+    assert rel(c, a.cpu()) < 0.2
