@@ -85,6 +85,7 @@ def _load():
         'dfn_sample_pdf': (i32, [i32, i32, vp, vp, i64, i32, vp, i32, vp, vp, vp]),
         'dfn_invert_cdf': (i32, [i32, i32, vp, vp, i32, vp, i32, vp, vp, vp]),
         'dfn_sort_merge': (i32, [i32, i32, vp, i32, vp, vp, vp]),
+        'dfn_coarse_to_fine': (i32, [i32, i32, i32, vp, vp, vp, vp, i32, f32, vp, i32, vp, vp, vp, vp, vp]),
         'dfn_to8b': (i32, [i64, vp, vp, vp]),
         'dfn_audionet_forward': (i32, [i32, i32, vp, C.POINTER(ConvStack), vp, vp, vp, vp, vp, vp]),
         'dfn_att_smooth': (i32, [i32, i32, i32, i32, vp, vp, C.POINTER(ConvStack), vp, vp, vp, vp]),
@@ -135,7 +136,7 @@ EXPORTS = ['dfn_abi_version', 'dfn_last_error', 'dfn_last_launch_count', 'dfn_pr
            'dfn_render_workspace_bytes', 'dfn_render_rays', 'dfn_decoder_create', 'dfn_decoder_destroy',
            'dfn_decoder_num_tensors', 'dfn_decoder_load', 'dfn_decoder_query_workspace_bytes', 'dfn_decoder_query',
            'dfn_decoder_macs_per_sample', 'dfn_decoder_program_host', 'dfn_model_program_host', 'dfn_render_head_torso_workspace_bytes', 'dfn_render_head_torso',
-           'dfn_gemm', 'dfn_colsum', 'dfn_head_torso_loss_bwd', 'dfn_adam_step']
+           'dfn_coarse_to_fine', 'dfn_gemm', 'dfn_colsum', 'dfn_head_torso_loss_bwd', 'dfn_adam_step']
 
 
 def check(rc, what=''):

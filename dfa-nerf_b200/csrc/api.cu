@@ -322,7 +322,7 @@ extern "C" int64_t dfn_query_workspace_bytes(const dfn_model* m, int64_t R, int 
 
 static int query_points_impl(const dfn_model* m, int64_t R, int S, const float* rays_o, const float* rays_d,
                              const float* viewdirs, const float* z_vals, const float* latent, float* raw,
-                             int precision, void* workspace, int64_t workspace_bytes, cudaStream_t st) {
+                             int precision, void* workspace, int64_t workspace_bytes, cudaStream_t st, const void* pre = nullptr) {
   DFN_CHECK_ARG(m && R > 0 && S > 0 && rays_o && rays_d && viewdirs && z_vals && raw && workspace,
                 "dfn_query_points: bad argument");
   if (!m->loaded) {
@@ -341,7 +341,7 @@ static int query_points_impl(const dfn_model* m, int64_t R, int S, const float* 
     set_error("dfn_query_points: this model shape has no tcgen05 path; use DFN_PREC_FP32");
     return DFN_E_UNSUPPORTED;
   }
-  return tc_query_points(m, R, S, rays_o, rays_d, viewdirs, z_vals, latent, raw, precision, workspace, workspace_bytes, st);
+  return tc_query_points(m, R, S, rays_o, rays_d, viewdirs, z_vals, latent, raw, precision, workspace, workspace_bytes, st, pre);
 }
 
 extern "C" int dfn_query_points(const dfn_model* m, int64_t R, int S, const float* rays_o, const float* rays_d,
@@ -354,7 +354,7 @@ extern "C" int dfn_query_points(const dfn_model* m, int64_t R, int S, const floa
 
 // --------------------------------------------------------------------------- render_rays
 struct RenderWs {
-  int64_t z0, raw0, w0, zmid, zs, zall, raw1, query, total;
+  int64_t z0, raw0, w0, zmid, zs, zall, raw1, query, pre_a, pre_b, total;
 };
 
 static RenderWs render_layout(const dfn_model* m, int64_t R, int Nc, int Nf, int precision) {
@@ -376,6 +376,9 @@ static RenderWs render_layout(const dfn_model* m, int64_t R, int Nc, int Nf, int
   int64_t q = dfn_query_workspace_bytes(m, R, Nf > 0 ? Nt : Nc, precision);
   int64_t q0 = dfn_query_workspace_bytes(m, R, Nc, precision);
   w.query = take(q > q0 ? q : q0);
+  const int64_t pb = precision == DFN_PREC_FP32 ? 16 : tc_prep_bytes(m, R);   // both networks' prepared biases (tc_prep_launch)
+  w.pre_a = take(pb);
+  w.pre_b = take(pb);
   w.total = o;
   return w;
 }
@@ -413,7 +416,7 @@ extern "C" int dfn_render_rays(const dfn_model* coarse, const dfn_model* fine, i
   float* zall = io->z_vals_out && Nf > 0 ? io->z_vals_out : reinterpret_cast<float*>(ws + L.zall);
   float* raw1 = reinterpret_cast<float*>(ws + L.raw1);
   void* qws = ws + L.query;
-  const int64_t qbytes = L.total - L.query;
+  const int64_t qbytes = L.pre_a - L.query;
   const int Ri = (int)R;
   int rc;
 #define STEP(call)        \
@@ -422,31 +425,52 @@ extern "C" int dfn_render_rays(const dfn_model* coarse, const dfn_model* fine, i
     if (rc) return rc;    \
   } while (0)
 
-  STEP(dfn_z_vals(Ri, Nc, io->t_vals, io->near, io->far, io->perturb_rand, z0, st));
+  // one preparation launch for the frame: both networks' folded biases and per-ray view-bias rows + the coarse depths
+  const void* pre_c = nullptr;
+  const void* pre_f = nullptr;
+  rc = DFN_E_UNSUPPORTED;
+  if (precision != DFN_PREC_FP32 && Nf > 0 && coarse->loaded && fine->loaded)
+    rc = tc_prep_launch(coarse, fine, R, Nc, io->viewdirs, io->latent, io->t_vals, io->near, io->far, io->perturb_rand, z0, ws + L.pre_a,
+                        ws + L.pre_b, st);
+  if (rc == 0) {
+    pre_c = ws + L.pre_a;
+    pre_f = ws + L.pre_b;
+  } else if (rc != DFN_E_UNSUPPORTED) {
+    return rc;
+  } else {
+    STEP(dfn_z_vals(Ri, Nc, io->t_vals, io->near, io->far, io->perturb_rand, z0, st));
+  }
   STEP(query_points_impl(coarse, R, Nc, io->rays_o, io->rays_d, io->viewdirs, z0, io->latent, raw0, precision, qws,
-                         qbytes, st));
+                         qbytes, st, pre_c));
   if (Nf == 0) {
     STEP(launch_raw2outputs(Ri, Nc, raw0, z0, io->rays_d, io->bc_rgb, 0, white_bkgd, 1e10f, io->rgb_map, io->disp_map,
                             io->acc_map, nullptr, nullptr, io->last_weight, st));
     if (io->z_vals_out) DFN_CUDA(cudaMemcpyAsync(io->z_vals_out, z0, (size_t)R * Nc * 4, cudaMemcpyDeviceToDevice, st));
   } else {
-    STEP(launch_raw2outputs(Ri, Nc, raw0, z0, io->rays_d, io->bc_rgb, 0, white_bkgd, 1e10f, io->rgb0, nullptr, nullptr, w0,
-                            nullptr, nullptr, st));
-    const float* zsamp = io->z_samples_in;
-    if (zsamp == nullptr) {
-      int64_t blocks = ((int64_t)R * (Nc - 1) + 255) / 256;
-      if (blocks > (int64_t)num_sms() * 32) blocks = (int64_t)num_sms() * 32;
-      z_mid_kernel<<<(int)blocks, 256, 0, st>>>(Ri, Nc, z0, zmid);
-      DFN_LAUNCH_CHECK();
-      float* zs_out = io->z_samples_out ? io->z_samples_out : zs;
-      STEP(dfn_sample_pdf(Ri, Nc - 1, zmid, w0 + 1, Nc, Nf, io->u_vals, io->u_per_ray ? 1 : 0, zs_out, nullptr, st));
-      zsamp = zs_out;
-    } else if (io->z_samples_out && io->z_samples_out != zsamp) {
-      DFN_CUDA(cudaMemcpyAsync(io->z_samples_out, zsamp, (size_t)R * Nf * 4, cudaMemcpyDeviceToDevice, st));
+    if (Nc >= 3 && Nc <= 128) {
+      // raw2outputs(coarse) -> z_mid -> sample_pdf -> sort-merge in ONE launch; weights, midpoints, cdf and the new samples stay
+      // in shared memory (stages.cu: coarse_to_fine_kernel, bit-identical to the chain below)
+      STEP(dfn_coarse_to_fine(Ri, Nc, Nf, raw0, z0, io->rays_d, io->bc_rgb, white_bkgd, 1e10f, io->u_vals, io->u_per_ray ? 1 : 0,
+                              io->z_samples_in, io->rgb0, io->z_samples_out, zall, st));
+    } else {
+      STEP(launch_raw2outputs(Ri, Nc, raw0, z0, io->rays_d, io->bc_rgb, 0, white_bkgd, 1e10f, io->rgb0, nullptr, nullptr, w0,
+                              nullptr, nullptr, st));
+      const float* zsamp = io->z_samples_in;
+      if (zsamp == nullptr) {
+        int64_t blocks = ((int64_t)R * (Nc - 1) + 255) / 256;
+        if (blocks > (int64_t)num_sms() * 32) blocks = (int64_t)num_sms() * 32;
+        z_mid_kernel<<<(int)blocks, 256, 0, st>>>(Ri, Nc, z0, zmid);
+        DFN_LAUNCH_CHECK();
+        float* zs_out = io->z_samples_out ? io->z_samples_out : zs;
+        STEP(dfn_sample_pdf(Ri, Nc - 1, zmid, w0 + 1, Nc, Nf, io->u_vals, io->u_per_ray ? 1 : 0, zs_out, nullptr, st));
+        zsamp = zs_out;
+      } else if (io->z_samples_out && io->z_samples_out != zsamp) {
+        DFN_CUDA(cudaMemcpyAsync(io->z_samples_out, zsamp, (size_t)R * Nf * 4, cudaMemcpyDeviceToDevice, st));
+      }
+      STEP(dfn_sort_merge(Ri, Nc, z0, Nf, zsamp, zall, st));
     }
-    STEP(dfn_sort_merge(Ri, Nc, z0, Nf, zsamp, zall, st));
     STEP(query_points_impl(fine, R, Nt, io->rays_o, io->rays_d, io->viewdirs, zall, io->latent, raw1, precision, qws,
-                           qbytes, st));
+                           qbytes, st, pre_f));
     STEP(launch_raw2outputs(Ri, Nt, raw1, zall, io->rays_d, io->bc_rgb, 0, white_bkgd, 1e10f, io->rgb_map, io->disp_map,
                             io->acc_map, nullptr, nullptr, io->last_weight, st));
   }

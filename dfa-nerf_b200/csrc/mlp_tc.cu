@@ -460,6 +460,106 @@ __global__ void view_bias_kernel(int64_t R, int Wh, int ncol, int L, const float
   }
 }
 
+
+// One launch in front of a hierarchical render (dfn_render_rays): the per-call preparation of BOTH networks and the coarse
+// depths -- fold_latent_kernel x 2, view_bias_kernel x 2 and z_vals_kernel in one grid.  Blocks [0, nl_a + nl_b) fold the
+// per-frame latent into the layer biases of network a / b; the other blocks walk the rays VB_RAYS at a time: the view
+// direction is encoded once, threads [0, Wh) form network a's per-ray bias row, threads [Wh, 2 Wh) network b's, and the
+// block writes the rays' coarse depth rows (MAIN:617-619 + optional stratified jitter), with the arithmetic of the three
+// kernels it replaces.
+struct PrepNet {
+  const float* bias;     // [n_layers][256]
+  const float* fold_w;   // [2][W][dim_aud]
+  const float* view_w;   // [Wh][ncol]
+  const float* view_b;   // [Wh]
+  float* bias_out;       // [n_layers][256]
+  float* vbias_out;      // [R][Wh]
+  int n_layers, fold0, fold1;
+};
+
+__global__ void render_prep_kernel(PrepNet A, PrepNet B, int W, int dim_aud, const float* __restrict__ latent, int64_t R, int Wh,
+                                   int ncol, const float* __restrict__ viewdirs, int Nc, const float* __restrict__ t_vals,
+                                   const float* __restrict__ near, const float* __restrict__ far,
+                                   const float* __restrict__ rnd, float* __restrict__ z_out) {
+  const int n_fold_blocks = A.n_layers + B.n_layers;
+  if ((int)blockIdx.x < n_fold_blocks) {
+    const bool second = (int)blockIdx.x >= A.n_layers;
+    const PrepNet& N = second ? B : A;
+    const int l = second ? (int)blockIdx.x - A.n_layers : (int)blockIdx.x, n = threadIdx.x;
+    if (n >= TC_BIAS_STRIDE) return;
+    float v = N.bias[l * TC_BIAS_STRIDE + n];
+    const int which = l == N.fold0 ? 0 : (l == N.fold1 ? 1 : -1);
+    if (which >= 0 && latent != nullptr && n < W) {
+      const float* w = N.fold_w + ((size_t)which * W + n) * dim_aud;
+      float acc = 0.f;
+      for (int j = 0; j < dim_aud; ++j) acc = fmaf(w[j], latent[j], acc);
+      v += acc;
+    }
+    N.bias_out[l * TC_BIAS_STRIDE + n] = v;
+    return;
+  }
+  extern __shared__ float sm[];
+  float* w_s = sm;                       // [2][Wh][ncol]
+  float* pe = sm + 2 * Wh * ncol;        // [VB_RAYS][ncol]
+  for (int i = threadIdx.x; i < Wh * ncol; i += blockDim.x) {
+    w_s[i] = A.view_w[i];
+    w_s[Wh * ncol + i] = B.view_w[i];
+  }
+  const int net = (int)threadIdx.x / Wh, nn = (int)threadIdx.x % Wh;      // blockDim = 2 * Wh
+  const PrepNet& N = net == 0 ? A : B;
+  const float bn = N.view_b[nn];
+  const int ray_blocks = (int)gridDim.x - n_fold_blocks;
+  for (int64_t r0 = (int64_t)((int)blockIdx.x - n_fold_blocks) * VB_RAYS; r0 < R; r0 += (int64_t)ray_blocks * VB_RAYS) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < VB_RAYS * ncol; i += blockDim.x) {
+      const int q = i / ncol, j = i % ncol;
+      const int64_t r = r0 + q < R ? r0 + q : R - 1;
+      float v;
+      if (j < 3) {
+        v = viewdirs[r * 3 + j];
+      } else {
+        const int k = (j - 3) / 6, c = (j - 3) % 6;
+        const float a = __fmul_rn(viewdirs[r * 3 + (c % 3)], pow2i(k));
+        v = c < 3 ? sinf(a) : cosf(a);
+      }
+      pe[i] = v;
+    }
+    __syncthreads();
+    {
+      float acc[VB_RAYS];
+#pragma unroll
+      for (int q = 0; q < VB_RAYS; ++q) acc[q] = 0.f;
+      const float* w = w_s + (size_t)net * Wh * ncol + nn * ncol;
+      for (int j = 0; j < ncol; ++j) {
+        const float wj = w[j];
+#pragma unroll
+        for (int q = 0; q < VB_RAYS; ++q) acc[q] = fmaf(wj, pe[q * ncol + j], acc[q]);
+      }
+#pragma unroll
+      for (int q = 0; q < VB_RAYS; ++q)
+        if (r0 + q < R) N.vbias_out[(r0 + q) * Wh + nn] = bn + acc[q];
+    }
+    // coarse depths of these rays (z_vals_kernel)
+    for (int i = threadIdx.x; i < VB_RAYS * Nc; i += blockDim.x) {
+      const int q = i / Nc, sidx = i % Nc;
+      const int64_t r = r0 + q;
+      if (r >= R) break;
+      const float nr = near[r], fr = far[r];
+      auto zf = [&](int k) {
+        const float t = t_vals[k];
+        return __fadd_rn(__fmul_rn(nr, __fsub_rn(1.0f, t)), __fmul_rn(fr, t));
+      };
+      float z = zf(sidx);
+      if (rnd) {
+        const float lower = sidx == 0 ? z : __fmul_rn(0.5f, __fadd_rn(z, zf(sidx - 1)));
+        const float upper = sidx == Nc - 1 ? z : __fmul_rn(0.5f, __fadd_rn(zf(sidx + 1), z));
+        z = __fadd_rn(lower, __fmul_rn(__fsub_rn(upper, lower), rnd[r * Nc + sidx]));
+      }
+      z_out[r * Nc + sidx] = z;
+    }
+  }
+}
+
 }  // namespace tc
 
 #ifdef DFN_EXPERIMENTS
@@ -688,9 +788,47 @@ int64_t tc_query_workspace_bytes(const dfn_model* m, int64_t R, int S) {
   return align256((int64_t)TC_MAX_LAYERS * TC_BIAS_STRIDE * 4) + align256(R * (m->desc.W / 2) * 4) + align256(pp_scratch_bytes());
 }
 
+// The preparation launch of a hierarchical render: biases (latent folded) and per-ray view-bias rows of both networks + the
+// coarse depth rows.  pre_a / pre_b: tc_prep_bytes(R) each.  Returns DFN_E_UNSUPPORTED when the two networks cannot share it.
+int64_t tc_prep_bytes(const dfn_model* m, int64_t R) {
+  return align256((int64_t)TC_MAX_LAYERS * TC_BIAS_STRIDE * 4) + align256(R * (m->desc.W / 2) * 4);
+}
+
+int tc_prep_launch(const dfn_model* a, const dfn_model* b, int64_t R, int Nc, const float* viewdirs, const float* latent,
+                   const float* t_vals, const float* near, const float* far, const float* rnd, float* z0, void* pre_a, void* pre_b,
+                   cudaStream_t st) {
+  const dfn_model_desc& da = a->desc;
+  const dfn_model_desc& db = b->desc;
+  if (a->tc_hi == nullptr || b->tc_hi == nullptr || da.W != db.W || da.input_ch_views != db.input_ch_views || da.dim_aud != db.dim_aud ||
+      da.multires_views != db.multires_views || da.W / 2 > 128 || (da.dim_aud > 0 && latent == nullptr))
+    return DFN_E_UNSUPPORTED;
+  const int Wh = da.W / 2;
+  auto net = [&](const dfn_model* m, void* pre) {
+    tc::PrepNet n;
+    n.bias = m->tc_bias;
+    n.fold_w = m->tc_fold_w;
+    n.view_w = m->tc_view_w;
+    n.view_b = m->tc_view_b;
+    n.bias_out = reinterpret_cast<float*>(pre);
+    n.vbias_out = reinterpret_cast<float*>(reinterpret_cast<char*>(pre) + align256((int64_t)TC_MAX_LAYERS * TC_BIAS_STRIDE * 4));
+    n.n_layers = m->prog.n_layers;
+    n.fold0 = m->prog.fold_layer[0];
+    n.fold1 = m->prog.fold_layer[1];
+    return n;
+  };
+  int64_t ray_blocks = (R + tc::VB_RAYS - 1) / tc::VB_RAYS;
+  if (ray_blocks > (int64_t)num_sms() * 8) ray_blocks = (int64_t)num_sms() * 8;
+  const int grid = a->prog.n_layers + b->prog.n_layers + (int)ray_blocks;
+  const size_t sm = ((size_t)2 * Wh * da.input_ch_views + tc::VB_RAYS * da.input_ch_views) * sizeof(float);
+  tc::render_prep_kernel<<<grid, 2 * Wh, sm, st>>>(net(a, pre_a), net(b, pre_b), da.W, da.dim_aud, latent, R, Wh, da.input_ch_views,
+                                                  viewdirs, Nc, t_vals, near, far, rnd, z0);
+  DFN_LAUNCH_CHECK();
+  return 0;
+}
+
 int tc_query_points(const dfn_model* m, int64_t R, int S, const float* rays_o, const float* rays_d,
                     const float* viewdirs, const float* z_vals, const float* latent, float* raw,
-                    int precision, void* workspace, int64_t workspace_bytes, cudaStream_t st) {
+                    int precision, void* workspace, int64_t workspace_bytes, cudaStream_t st, const void* pre) {
   const dfn_model_desc& d = m->desc;
   if (workspace_bytes < tc_query_workspace_bytes(m, R, S)) {
     set_error("dfn_query_points: workspace %lld < %lld bytes", (long long)workspace_bytes,
@@ -708,7 +846,12 @@ int tc_query_points(const dfn_model* m, int64_t R, int S, const float* rays_o, c
   float* bias_ws = reinterpret_cast<float*>(workspace);
   float* vbias_ws = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + align256((int64_t)TC_MAX_LAYERS * TC_BIAS_STRIDE * 4));
   const int Wh = d.W / 2;
+  void* const scratch_ws = reinterpret_cast<char*>(vbias_ws) + align256(R * (int64_t)Wh * 4);
 
+  if (pre != nullptr) {       // biases and view-bias rows already formed by tc_prep_launch
+    bias_ws = reinterpret_cast<float*>(const_cast<void*>(pre));
+    vbias_ws = reinterpret_cast<float*>(reinterpret_cast<char*>(const_cast<void*>(pre)) + align256((int64_t)TC_MAX_LAYERS * TC_BIAS_STRIDE * 4));
+  } else {
   tc::fold_latent_kernel<<<m->prog.n_layers, TC_BIAS_STRIDE, 0, st>>>(
       m->prog.n_layers, d.W, d.dim_aud, m->tc_bias, m->tc_fold_w, latent, m->prog.fold_layer[0], m->prog.fold_layer[1], bias_ws);
   DFN_LAUNCH_CHECK();
@@ -719,6 +862,7 @@ int tc_query_points(const dfn_model* m, int64_t R, int S, const float* rays_o, c
     tc::view_bias_kernel<<<(int)blocks, 128, sm, st>>>(R, Wh, d.input_ch_views, d.multires_views, viewdirs, m->tc_view_w,
                                                         m->tc_view_b, vbias_ws);
     DFN_LAUNCH_CHECK();
+  }
   }
 
   tc::Params P;
@@ -757,8 +901,7 @@ int tc_query_points(const dfn_model* m, int64_t R, int S, const float* rays_o, c
   const bool prof = profile_begin(st, macs_pt * (double)P.n_points);
   const int impl = g_impl >= 0 ? g_impl : (precision == DFN_PREC_BF16X3 ? 2 : 1);
   if (impl == 2 && (precision == DFN_PREC_BF16 || precision == DFN_PREC_BF16X3)) {
-    void* scratch = reinterpret_cast<char*>(vbias_ws) + align256(R * (int64_t)Wh * 4);
-    int rc = pp_launch(m, bias_ws, vbias_ws, scratch, R, S, rays_o, rays_d, z_vals, raw, precision, st);
+    int rc = pp_launch(m, bias_ws, vbias_ws, scratch_ws, R, S, rays_o, rays_d, z_vals, raw, precision, st);
     if (rc) return rc;
 #ifdef DFN_EXPERIMENTS
   } else if (impl == 3 && precision == DFN_PREC_BF16) {

@@ -125,5 +125,9 @@ void tc_free_model(dfn_model* m);
 int64_t tc_query_workspace_bytes(const dfn_model* m, int64_t R, int S);
 int tc_query_points(const dfn_model* m, int64_t R, int S, const float* rays_o, const float* rays_d,
                     const float* viewdirs, const float* z_vals, const float* latent, float* raw,
-                    int precision, void* workspace, int64_t workspace_bytes, cudaStream_t st);
+                    int precision, void* workspace, int64_t workspace_bytes, cudaStream_t st, const void* pre = nullptr);
+int64_t tc_prep_bytes(const dfn_model* m, int64_t R);
+int tc_prep_launch(const dfn_model* a, const dfn_model* b, int64_t R, int Nc, const float* viewdirs, const float* latent,
+                   const float* t_vals, const float* near, const float* far, const float* rnd, float* z0, void* pre_a, void* pre_b,
+                   cudaStream_t st);
 }  // namespace dfn

@@ -564,6 +564,236 @@ __global__ void sort_merge_kernel(int R, int na, const float* __restrict__ a, in
   }
 }
 
+// ------------------------------------------------- coarse pass -> fine depths, one kernel (a8 + a9 + a10 + a11)
+// raw2outputs(coarse) -> z_mid -> sample_pdf -> sort(cat(z, z_samples)) of upstream render_rays for one
+// ray per warp, with the arithmetic of volume_weights_kernel<1>, sample_pdf_kernel<false> and sort_merge_kernel above -- the
+// same operations in the same order, so the merged depths are bit-identical to the chain of separate launches -- but the
+// weights, the bin midpoints, the cdf and the new samples live in shared memory instead of making five round trips
+// through HBM (w0, z_mid, z_samples written and re-read), and the frame needs one launch instead of four.
+// Per warp: the ray's raw row [Nc,4] and depth row [Nc] are fetched with coalesced loads into shared memory (lane l then
+// owns the contiguous samples [l*seg, (l+1)*seg) for the fp64 transmittance scan); rgb0 is formed only when requested.
+struct C2FSmem {   // floats per warp
+  static __host__ __device__ int raw(int Nc) { return 4 * Nc; }
+  static __host__ __device__ int total(int Nc, int npow2) { return 4 * Nc + 4 * Nc + 2 * npow2; }   // raw | w, zmid, cdf, pad | v, merged
+};
+
+template <int SEG>
+__global__ void coarse_to_fine_kernel(int R, int Nc, int Nf, const float* __restrict__ raw0, const float* __restrict__ z0,
+                                      const float* __restrict__ rays_d, const float* __restrict__ bc_rgb, int white_bkgd,
+                                      float last_dist, const float* __restrict__ u, int u_per_ray,
+                                      const float* __restrict__ zs_in, float* __restrict__ rgb0, float* __restrict__ zs_out,
+                                      float* __restrict__ zall, int npow2) {
+  extern __shared__ float sm[];
+  const int lane = threadIdx.x & 31;
+  const int wib = threadIdx.x >> 5;
+  const int warps_per_block = blockDim.x >> 5;
+  float* base = sm + (size_t)wib * C2FSmem::total(Nc, npow2);
+  float4* rawS = reinterpret_cast<float4*>(base);
+  float* wgt = base + 4 * Nc;          // [Nc] weights
+  float* zmid = wgt + Nc;              // [Nc-1]
+  float* cdf = zmid + Nc;              // [Nc-1]
+  float* v = cdf + 2 * Nc;             // [npow2]: z (Nc) | samples (Nf) | +inf
+  float* mrg = v + npow2;              // [npow2] merged run
+  const int seg = (Nc + 31) / 32;
+  const int n = Nc + Nf;
+  const int nb = Nc - 1, nw = Nc - 2;  // bins = z_mid, weights[..., 1:-1]
+  for (int ray = blockIdx.x * warps_per_block + wib; ray < R; ray += gridDim.x * warps_per_block) {
+    __syncwarp();
+    // ---- coalesced fetch of the ray's rows
+    const float4* rsrc = reinterpret_cast<const float4*>(raw0) + (int64_t)ray * Nc;
+    for (int i = lane; i < Nc; i += 32) {
+      rawS[i] = rsrc[i];
+      v[i] = z0[(int64_t)ray * Nc + i];
+    }
+    const float dx = rays_d[ray * 3 + 0], dy = rays_d[ray * 3 + 1], dz = rays_d[ray * 3 + 2];
+    const float nrm = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)));
+    __syncwarp();
+    // ---- weights (MAIN:169-179) [+ colour sum, MAIN:706] exactly as volume_weights_kernel<1, SEG>
+    float alpha[SEG], col[SEG][3];
+    double local = 1.0;
+    const int s0 = lane * seg;
+#pragma unroll
+    for (int k = 0; k < SEG; ++k) {
+      const int s = s0 + k;
+      alpha[k] = 0.f;
+      if (k < seg && s < Nc) {
+        const float4 rv = rawS[s];
+        if (rgb0) {
+          col[k][0] = __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-rv.x)));
+          col[k][1] = __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-rv.y)));
+          col[k][2] = __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-rv.z)));
+          if (s == Nc - 1 && bc_rgb) {
+            col[k][0] = bc_rgb[ray * 3 + 0]; col[k][1] = bc_rgb[ray * 3 + 1]; col[k][2] = bc_rgb[ray * 3 + 2];
+          }
+        }
+        const float z = v[s];
+        float dist = s == Nc - 1 ? last_dist : __fsub_rn(v[s + 1], z);
+        dist = __fmul_rn(dist, nrm);
+        const float t = __fadd_rn(fmaxf(rv.w, 0.f), 1e-6f);
+        const float a = __fsub_rn(1.0f, expf(-__fmul_rn(t, dist)));
+        alpha[k] = a;
+        local *= (double)__fadd_rn(__fsub_rn(1.0f, a), 1e-10f);
+      }
+    }
+    double incl = local;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      double up = shfl_up_f64(incl, d);
+      if (lane >= d) incl *= up;
+    }
+    double run = shfl_up_f64(incl, 1);
+    if (lane == 0) run = 1.0;
+    float acc_rgb[3] = {0.f, 0.f, 0.f}, acc_w = 0.f;
+#pragma unroll
+    for (int k = 0; k < SEG; ++k) {
+      const int s = s0 + k;
+      if (k < seg && s < Nc) {
+        const float T = (float)run;
+        const float w = __fmul_rn(alpha[k], T);
+        run *= (double)__fadd_rn(__fsub_rn(1.0f, alpha[k]), 1e-10f);
+        wgt[s] = w;
+        if (rgb0) {
+          acc_rgb[0] += w * col[k][0];
+          acc_rgb[1] += w * col[k][1];
+          acc_rgb[2] += w * col[k][2];
+          acc_w += w;
+        }
+      }
+    }
+    if (rgb0) {
+      acc_rgb[0] = warp_sum(acc_rgb[0]);
+      acc_rgb[1] = warp_sum(acc_rgb[1]);
+      acc_rgb[2] = warp_sum(acc_rgb[2]);
+      acc_w = warp_sum(acc_w);
+      if (lane == 0) {
+        if (white_bkgd) {
+          const float bgw = 1.0f - acc_w;
+          acc_rgb[0] += bgw; acc_rgb[1] += bgw; acc_rgb[2] += bgw;
+        }
+        rgb0[ray * 3 + 0] = acc_rgb[0]; rgb0[ray * 3 + 1] = acc_rgb[1]; rgb0[ray * 3 + 2] = acc_rgb[2];
+      }
+    }
+    __syncwarp();
+    if (zs_in == nullptr) {
+      // ---- z_mid and the cdf of weights[..., 1:-1] + 1e-5 (HELP:539-544), as sample_pdf_kernel<false>
+      for (int i = lane; i < nb; i += 32) zmid[i] = __fmul_rn(0.5f, __fadd_rn(v[i + 1], v[i]));
+      {
+        const int sg = (nw + 31) / 32;
+        float wv[kMaxBins / 32];
+        double part = 0.0;
+#pragma unroll
+        for (int k = 0; k < kMaxBins / 32; ++k) {
+          const int i = lane * sg + k;
+          wv[k] = 0.f;
+          if (k < sg && i < nw) {
+            wv[k] = __fadd_rn(wgt[1 + i], 1e-5f);
+            part += (double)wv[k];
+          }
+        }
+        double tot = part;
+#pragma unroll
+        for (int m = 16; m > 0; m >>= 1) tot += shfl_xor_f64(tot, m);
+        const float total = (float)tot;
+        double lsum = 0.0;
+#pragma unroll
+        for (int k = 0; k < kMaxBins / 32; ++k) {
+          const int i = lane * sg + k;
+          if (k < sg && i < nw) {
+            wv[k] = __fdiv_rn(wv[k], total);
+            lsum += (double)wv[k];
+          }
+        }
+        double inc2 = lsum;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+          double up = shfl_up_f64(inc2, d);
+          if (lane >= d) inc2 += up;
+        }
+        double r2 = shfl_up_f64(inc2, 1);
+        if (lane == 0) {
+          r2 = 0.0;
+          cdf[0] = 0.f;
+        }
+#pragma unroll
+        for (int k = 0; k < kMaxBins / 32; ++k) {
+          const int i = lane * sg + k;
+          if (k < sg && i < nw) {
+            r2 += (double)wv[k];
+            cdf[i + 1] = (float)r2;
+          }
+        }
+      }
+      __syncwarp();
+      // ---- inverse-cdf samples (HELP:563-579)
+      for (int j = lane; j < Nf; j += 32) {
+        const float uu = u_per_ray ? u[(int64_t)ray * Nf + j] : u[j];
+        int lo = 0, hi = nb;
+        while (lo < hi) {
+          const int mid = (lo + hi) >> 1;
+          if (cdf[mid] <= uu) lo = mid + 1; else hi = mid;
+        }
+        const int below = max(0, lo - 1), above = min(nb - 1, lo);
+        const float cb = cdf[below], ca = cdf[above];
+        float den = __fsub_rn(ca, cb);
+        if (den < 1e-5f) den = 1.0f;
+        const float t = __fdiv_rn(__fsub_rn(uu, cb), den);
+        const float bb = zmid[below], ba = zmid[above];
+        const float smp = __fadd_rn(bb, __fmul_rn(t, __fsub_rn(ba, bb)));
+        v[Nc + j] = smp;
+        if (zs_out) zs_out[(int64_t)ray * Nf + j] = smp;
+      }
+    } else {
+      for (int j = lane; j < Nf; j += 32) {
+        const float smp = zs_in[(int64_t)ray * Nf + j];
+        v[Nc + j] = smp;
+        if (zs_out && zs_out != zs_in) zs_out[(int64_t)ray * Nf + j] = smp;
+      }
+    }
+    for (int i = n + lane; i < npow2; i += 32) v[i] = CUDART_INF_F;
+    __syncwarp();
+    // ---- sort(cat(z, z_samples)) as sort_merge_kernel: merge by rank when both runs ascend, bitonic network otherwise
+    {
+      bool sorted = true;
+      for (int i = lane; i < n; i += 32)
+        if (i != 0 && i != Nc) sorted = sorted && (v[i - 1] <= v[i]);
+      if (__all_sync(0xFFFFFFFFu, sorted)) {
+        for (int i = lane; i < n; i += 32) {
+          const float x = v[i];
+          const bool from_a = i < Nc;
+          const float* other = from_a ? v + Nc : v;
+          int lo = 0, hi = from_a ? Nf : Nc;
+          while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            const float y = other[mid];
+            if (from_a ? (y < x) : (y <= x)) lo = mid + 1;
+            else hi = mid;
+          }
+          mrg[(from_a ? i : i - Nc) + lo] = x;
+        }
+        __syncwarp();
+        for (int i = lane; i < n; i += 32) zall[(int64_t)ray * n + i] = mrg[i];
+        continue;
+      }
+    }
+    for (int k = 2; k <= npow2; k <<= 1) {
+      for (int j = k >> 1; j > 0; j >>= 1) {
+        for (int t = lane; t < (npow2 >> 1); t += 32) {
+          const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+          const int p = i | j;
+          const bool up = (i & k) == 0;
+          const float x = v[i], y = v[p];
+          if ((x > y) == up) {
+            v[i] = y;
+            v[p] = x;
+          }
+        }
+        __syncwarp();
+      }
+    }
+    for (int i = lane; i < n; i += 32) zall[(int64_t)ray * n + i] = v[i];
+  }
+}
+
 // ---------------------------------------------------------------------------- to8b (HELP:17)
 // (255 * clip(x, 0, 1)).astype(uint8): fp32 product, truncation.  Four values per thread (one 32-bit store).
 __global__ void to8b_kernel(int64_t n, const float* __restrict__ x, uint8_t* __restrict__ out) {
@@ -741,6 +971,32 @@ extern "C" int dfn_invert_cdf(int R, int nb, const float* bins, const float* cdf
   size_t smem = (size_t)wpb * 2 * kMaxBins * sizeof(float);
   sample_pdf_kernel<true><<<rays_grid(R, wpb), wpb * 32, smem, (cudaStream_t)stream>>>(
       R, nb, bins, cdf, nb, N, u, u_per_ray, samples, inds);
+  DFN_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int dfn_coarse_to_fine(int R, int N_samples, int N_importance, const float* raw0, const float* z_vals, const float* rays_d,
+                                  const float* bc_rgb, int white_bkgd, float last_dist, const float* u, int u_per_ray,
+                                  const float* z_samples_in, float* rgb0, float* z_samples_out, float* z_all, void* stream) {
+  DFN_CHECK_ARG(R > 0 && N_samples >= 3 && N_samples <= 32 * 4 && N_importance > 0 && N_samples + N_importance <= 512 && raw0 &&
+                    z_vals && rays_d && z_all && (u || z_samples_in),
+                "dfn_coarse_to_fine: bad argument (3 <= N_samples <= 128, N_samples + N_importance <= 512)");
+  DFN_CHECK_ARG((reinterpret_cast<uintptr_t>(raw0) & 15) == 0, "dfn_coarse_to_fine: raw0 must be 16-byte aligned");
+  int npow2 = 2;
+  while (npow2 < N_samples + N_importance) npow2 <<= 1;
+  const int per_warp = C2FSmem::total(N_samples, npow2);
+  int wpb = 8;
+  while (wpb > 1 && (size_t)wpb * per_warp * sizeof(float) > 48 * 1024) wpb >>= 1;
+  const size_t smem = (size_t)wpb * per_warp * sizeof(float);
+  const int seg = (N_samples + 31) / 32;
+#define CALL_C2F(SEG)                                                                                                     \
+  coarse_to_fine_kernel<SEG><<<rays_grid(R, wpb), wpb * 32, smem, (cudaStream_t)stream>>>(                                \
+      R, N_samples, N_importance, raw0, z_vals, rays_d, bc_rgb, white_bkgd, last_dist, u, u_per_ray, z_samples_in, rgb0,  \
+      z_samples_out, z_all, npow2)
+  if (seg <= 1) CALL_C2F(1);
+  else if (seg <= 2) CALL_C2F(2);
+  else CALL_C2F(4);
+#undef CALL_C2F
   DFN_LAUNCH_CHECK();
   return 0;
 }

@@ -243,6 +243,38 @@ def sort_merge(a, b):
     return out
 
 
+def coarse_to_fine(raw0, z_vals, rays_d, N_importance, bc_rgb=None, u=None, z_samples=None, white_bkgd=False, want_rgb0=True,
+                   last_dist=1e10):
+    """The coarse half of upstream render_rays after the network query, fused (dfn_coarse_to_fine): raw2outputs(raw0) ->
+    z_mid -> sample_pdf(z_mid, weights[..., 1:-1], N_importance, det) -> sort(cat(z_vals, z_samples)).
+    Returns (z_all [R, S+N_importance], z_samples [R, N_importance], rgb0 [R,3] or None); `u` as sample_pdf, `z_samples` injects
+    the new depths (teacher forcing)."""
+    raw0, pr = dev(raw0, 'raw0')
+    z_vals, pz = dev(z_vals, 'z_vals')
+    rays_d, pd = dev(rays_d, 'rays_d')
+    R, S = z_vals.shape
+    d = raw0.device
+    pb = C.c_void_p(0)
+    if bc_rgb is not None:
+        bc_rgb, pb = dev(bc_rgb, 'bc_rgb')
+    if u is None and z_samples is None:
+        u = linspace_table(N_importance, d)
+    pu, per_ray = C.c_void_p(0), 0
+    if u is not None:
+        u, pu = dev(u, 'u')
+        per_ray = 1 if u.dim() == 2 else 0
+    pzs = C.c_void_p(0)
+    if z_samples is not None:
+        z_samples, pzs = dev(z_samples, 'z_samples')
+    z_all = torch.empty((R, S + N_importance), dtype=torch.float32, device=d)
+    zs = torch.empty((R, N_importance), dtype=torch.float32, device=d)
+    rgb0 = torch.empty((R, 3), dtype=torch.float32, device=d) if want_rgb0 else None
+    with torch.cuda.device(d):
+        check(lib.dfn_coarse_to_fine(R, S, N_importance, pr, pz, pd, pb, int(bool(white_bkgd)), float(last_dist), pu, per_ray, pzs,
+                                     ptr(rgb0), ptr(zs), ptr(z_all), stream_ptr()), 'dfn_coarse_to_fine')
+    return z_all, zs, rgb0
+
+
 def to8b(x):
     """HELP:17 on the device: uint8(255 * clip(x, 0, 1)), same shape (numpy's fp32 product and truncation)."""
     x, px = dev(x, 'x')

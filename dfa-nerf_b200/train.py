@@ -433,7 +433,7 @@ class Trainer:
         aud = self._encoder(tape, 'aud', batch['auds'][i].to(dev).float().contiguous())
         exp = self._encoder(tape, 'exp', batch['exps'][i].to(dev).float().contiguous())
         n_aud = aud.n
-        sig_torso = encode_signal_torso_sequence(batch['poses'][i:i + 1].to(dev).float())[0].contiguous()   # MAIN:78-84, no parameters
+        sig_torso = encode_signal_torso_sequence(batch['poses'][i:i + 1, :3, :4].to(dev).float().contiguous())[0].contiguous()   # MAIN:78-84, no parameters
         zs, za = batch['z_shape'].to(dev).float(), batch['z_app'].to(dev).float()
 
         def head_signal(Wfull, gWfull, de):      # [aud (64) | exp (32)] columns of a weight that reads [PE | signal] (DEC:293-295)

@@ -119,6 +119,17 @@ int dfn_invert_cdf(int R, int nb, const float* bins, const float* cdf, int N, co
 /* ---- a11  merge  (upstream: z_vals,_ = sort(cat([z_vals, z_samples]))) ------------------------ */
 int dfn_sort_merge(int R, int na, const float* a, int nb, const float* b, float* out, void* stream);
 
+/* ---- a8+a9+a10+a11 fused: coarse pass -> fine depths  (upstream render_rays) ------------
+ * raw2outputs(raw0) -> z_mid = .5 (z[1:] + z[:-1]) -> sample_pdf(z_mid, weights[..., 1:-1], N_importance, u) ->
+ * z_all = sort(cat(z_vals, z_samples)) in ONE launch; weights, midpoints, cdf and samples stay in shared memory.  The
+ * arithmetic is that of dfn_raw2outputs / dfn_sample_pdf / dfn_sort_merge, operation for operation: z_all is bit-identical
+ * to the chain of the three.  rgb0 [R,3] (coarse image) and z_samples_out [R,N_importance] are optional outputs;
+ * z_samples_in (nullable) injects the new depths instead of sampling them (teacher forcing).  u: [N_importance]
+ * (u_per_ray 0) or [R,N_importance]. */
+int dfn_coarse_to_fine(int R, int N_samples, int N_importance, const float* raw0, const float* z_vals, const float* rays_d,
+                       const float* bc_rgb, int white_bkgd, float last_dist, const float* u, int u_per_ray,
+                       const float* z_samples_in, float* rgb0, float* z_samples_out, float* z_all, void* stream);
+
 /* ---- output side  to8b  (HELP:17; MAIN:714-715) ---------------------------------------------
  * out[i] = uint8(255 * clip(x[i], 0, 1)) (fp32 product, truncation) -- the frame leaves the device as 3 bytes/pixel. */
 int dfn_to8b(int64_t n, const float* x, uint8_t* out, void* stream);

@@ -209,3 +209,42 @@ def test_sort_merge_bit_exact(dfn):
         assert torch.equal(dfn.sort_merge(a.to(DEV), bb.to(DEV)).cpu(), torch.sort(torch.cat([a, bb], -1), -1)[0])
     big_a, big_b = torch.sort(torch.rand(33, 500), -1)[0], torch.sort(torch.rand(33, 524), -1)[0]
     assert torch.equal(dfn.sort_merge(big_a.to(DEV), big_b.to(DEV)).cpu(), torch.sort(torch.cat([big_a, big_b], -1), -1)[0])
+
+
+@pytest.mark.parametrize('R,Nc,Nf', [(1, 64, 128), (777, 64, 128), (50, 16, 16), (33, 100, 60), (20000, 64, 128)])
+def test_coarse_to_fine_bit_identical_to_the_stage_chain(dfn, R, Nc, Nf):
+    """The fused coarse -> fine kernel (dfn_coarse_to_fine: raw2outputs -> z_mid -> sample_pdf -> sort-merge in one launch,
+    intermediates in shared memory) against the chain of the separately tested stage kernels: same operations in the same
+    order, so the coarse image, the new samples and the merged depths must be bit-identical -- for the deterministic u table
+    (merge-by-rank path), for random per-ray u (unsorted samples: bitonic path) and with injected samples (teacher forcing)."""
+    g = torch.Generator().manual_seed(R + Nc)
+    raw = torch.randn(R, Nc, 4, generator=g)
+    raw[..., 3] = raw[..., 3] * 12 + 2
+    raw[: max(1, R // 10), :, 3] = -1.                         # empty rays: uniform pdf
+    z0, _ = torch.sort(torch.rand(R, Nc, generator=g) * 0.6 + 0.4, -1)
+    rd = torch.randn(R, 3, generator=g) * 0.2 + torch.tensor([0., 0., -1.])
+    bc = torch.rand(R, 3, generator=g)
+    raw, z0, rd, bc = [t.to(DEV) for t in (raw, z0, rd, bc)]
+
+    def chain(u, zs_in=None):
+        rgb0, _, _, w, _ = dfn.raw2outputs(raw, z0, rd, bc)
+        if zs_in is None:
+            zmid = (0.5 * (z0[:, 1:] + z0[:, :-1])).contiguous()
+            zs = dfn.sample_pdf(zmid, w[:, 1:-1].contiguous(), Nf, u=u)
+        else:
+            zs = zs_in
+        return dfn.sort_merge(z0, zs), zs, rgb0
+
+    u_det = torch.linspace(0., 1., Nf).to(DEV)
+    u_rand = torch.rand(R, Nf, generator=g).to(DEV)
+    for u in (u_det, u_rand):
+        za, zs, rgb0 = dfn.coarse_to_fine(raw, z0, rd, Nf, bc, u=u)
+        ra, rs, r0 = chain(u)
+        assert torch.equal(zs, rs) and torch.equal(za, ra) and torch.equal(rgb0, r0)
+        assert (za[:, 1:] >= za[:, :-1]).all()
+    inj = (torch.rand(R, Nf, generator=g) * 0.6 + 0.4).to(DEV)
+    za, zs, rgb0 = dfn.coarse_to_fine(raw, z0, rd, Nf, bc, z_samples=inj)
+    ra, rs, r0 = chain(None, inj)
+    assert torch.equal(za, ra) and torch.equal(zs, inj) and torch.equal(rgb0, r0)
+    za2, _, none = dfn.coarse_to_fine(raw, z0, rd, Nf, bc, u=u_det, want_rgb0=False)
+    assert none is None and torch.equal(za2, chain(u_det)[0])

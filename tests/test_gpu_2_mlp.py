@@ -106,9 +106,11 @@ def test_query_points_bf16x3_vs_fp32_oracle(dfn, R, S):
 # cores' own accumulation (order, truncated alignment: ~1e-6 relative on a pre-activation) and the MUFU sin/cos of the
 # fused encoding -- either can flip the 16-bit rounding of an activation that sits on a rounding boundary, and ONE flip
 # in the last trunk layer moves sigma by gain x |w| x ulp ~ 3e-3 |sigma|max in bf16 (tests/test_quantized_cpu.py).  So the
-# max is gated at a few flips, p99 and the median far below, and everything is printed.
+# max is gated at a few flips, p99 and the median far below, and everything is printed.  Measured on the B200 (round 2):
+# bf16 colours <= 6.5e-5, sigma max <= 7.5e-3, p99 <= 1.2e-3, median ~1e-7 of |sigma|max; fp16 9e-6 / 1.1e-3 / 4.6e-4 / 4e-7 --
+# i.e. at the median the restatement reproduces the kernel to fp32 rounding, 10^4 times closer than the fp32 forward is.
 #                 colours(sigmoid) max, sigma max / p99 / median as fractions of |sigma|max
-Q_GATE = {'bf16': (1.5e-4, 2e-2, 4e-3, 1e-5), 'fp16': (1e-4, 4e-3, 1e-3, 2e-6)}
+Q_GATE = {'bf16': (1.3e-4, 1.5e-2, 2.5e-3, 1e-6), 'fp16': (2e-5, 2.5e-3, 1e-3, 2e-6)}
 
 
 def _gate_quantized(tag, prec_name, raw, refq, ref32):

@@ -119,7 +119,7 @@ def cpu_train(monkeypatch):
             p = p / torch.norm(p, dim=-1, keepdim=True)
         return O.decoder_transform_points(p, n_freq).contiguous()
     monkeypatch.setattr(train, 'decoder_transform_points', tp)
-    monkeypatch.setattr(train, 'encode_signal_torso_sequence', lambda poses: O.encode_signal_torso(poses, 0))
+    monkeypatch.setattr(train, 'encode_signal_torso_sequence', lambda poses: O.encode_signal_torso(poses, 0))     # poses [1,3,4]
     return train
 
 
