@@ -1,0 +1,435 @@
+// tcgen05 path of network_query_fn for the single-pass precisions (bf16 / fp16), CTA-pair generation: the schedule of
+// mlp_tc.cu (two 128-point tiles per CTA in flight, activations as 128-byte-swizzled K-major blocks in shared memory,
+// accumulators in TMEM, per-slot epilogue warps, positional encoding one tile ahead by helper warps) with the MMAs issued
+// as cta_group::2 by the leader CTA of a 2-CTA cluster: one instruction covers M = 256 points (128 per CTA) and takes HALF
+// of the weight rows from each CTA's shared memory.
+//
+// Why (profiles/microbench/): the 1-CTA kernel sits at its shared-memory bandwidth roofline.  Per
+// 256x256 layer and 128-point tile an SM moves A reads 64 KB + B reads 128 KB + TMA weight writes 128 KB + epilogue stores
+// 64 KB = 384 KB = 3,072 cycles at 128 B/clk against 2,048 tensor-pipe cycles, and the timeline shows exactly that (3,100
+// cycles per tile-layer with the MMA issuer never waiting for activations).  With the pair sharing B each SM stores and reads
+// only its half of every weight K-block: 64 + 64 + 64 + 64 = 256 KB = 2,048 cycles, and the 64 KB ring holds a whole layer.
+// The first CTA-pair experiment (round 1, mlp_tc2.cu) lost to the 1-CTA kernel because its per-slot dependency chain
+// (MMA -> accumulator readout + repack -> cross-CTA signal) was longer than the other slot's MMAs; what changed is the
+// epilogue: the column-distributed readout (tc_epi.cuh, epilogue_relu_cd) takes half the time of the row-per-thread one,
+// whose warp-broadcast bias loads were more than half of it.
+//
+// Roles per CTA (384 threads): warp 0 weight producer (cp.async.bulk of this CTA's half stage, local `full` barrier);
+// warp 1: leader = MMA issuer, peer = relay (forwards its `full` completions to the leader's `pfull` barriers);
+// warps 2-3 positional encoding of each slot's NEXT tile (warp 2 also allocates TMEM); warps 4-7 / 8-11 epilogue of
+// tile slot 0 / 1.  Cross-CTA signalling: one lane per epilogue warp of both CTAs arrives on the LEADER's `aready`
+// barrier (the peer's with a cluster-scope release); the leader's tcgen05.commit multicasts to both CTAs' `empty` and
+// `acc` barriers.
+//
+// Reference arithmetic: HELP:21-52 (Embedder), HELP:275-299 (FaceNeRF.forward), HELP:372-396 (NeRF.forward); output
+// bit-identical to mlp_tc.cu (same operands, same fp32 bias add and rounding; the accumulation order inside an MMA is
+// the hardware's in both).
+#include <string.h>
+
+#include "common.cuh"
+#include "model.h"
+#include "tc_ptx.cuh"
+#include "tc_epi.cuh"
+#include "pe.cuh"
+
+namespace dfn {
+namespace tcp {
+
+using namespace dfn::tc;
+
+static constexpr int STAGE_BYTES = 128 * 128;      // one ring entry: this CTA's <=128 weight rows x 64 K
+static constexpr int N_STAGES = 4;
+static constexpr int PE_HELPERS = 64;
+static constexpr int ARENA_BLOCKS = 2 * TC_KB_PER_TILE;
+static constexpr int SMEM_RING = ARENA_BLOCKS * KB_BYTES;
+static constexpr int SMEM_BIAS = SMEM_RING + N_STAGES * STAGE_BYTES;
+static constexpr int SMEM_BAR = SMEM_BIAS + 2 * TC_BIAS_STRIDE * 4;
+static constexpr int SMEM_TOTAL = SMEM_BAR + 256;
+static_assert(SMEM_TOTAL <= 227 * 1024, "shared memory budget");
+
+struct Params {
+  const uint8_t* w;        // cta-pair stage images (tc_pack.h: hi2 / h16_2)
+  const float* bias;       // [n_layers][256], latent already folded
+  const float* view_bias;  // [R][W/2]
+  const float* rays_o;
+  const float* rays_d;
+  const float* z_vals;
+  float* raw;
+  int64_t n_points;
+  int S;
+  int n_tiles;
+  int n_layers;
+  int multires;
+  int view_w;
+  unsigned long long* trace;  // debug: per-role clock64 records of CTA 0 (null in production), format of mlp_tc.cu
+  int trace_tiles;
+  TcLayer layers[TC_MAX_LAYERS];
+};
+
+// kind::f16, M = 256 across the pair, D = f32, both operands K-major; bf16 or fp16 operands
+template <bool F16>
+__device__ __forceinline__ uint32_t make_idesc_pair(uint32_t n) {
+  return (1u << 4) | (F16 ? 0u : ((1u << 7) | (1u << 10))) | ((n >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+}
+
+// EW: epilogue warps per tile slot -- 4 (one per TMEM lane quarter, 384 threads) or 8 (two per quarter, each half of the columns; 640
+// threads, 96 registers).
+template <bool F16, int EW>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((4 + 2 * EW) * 32, 1) mlp_pair_kernel(const __grid_constant__ Params P) {
+  constexpr int NSLOT = 2;
+  constexpr int NH = EW / 4;          // column halves per row
+  constexpr int ETH = EW * 32;        // epilogue threads per slot
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const uint32_t sbase = smem_u32(smem);
+  if ((sbase & 1023u) != 0) __trap();
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t bar_full = sbase + SMEM_BAR;           // [4] this CTA's half of ring entry e has landed
+  const uint32_t bar_empty = sbase + SMEM_BAR + 32;     // [4] ring entry e consumed by the pair's MMAs
+  const uint32_t bar_pfull = sbase + SMEM_BAR + 64;     // [4] leader only: the PEER's half of entry e has landed
+  const uint32_t bar_acc = sbase + SMEM_BAR + 96;       // [2] accumulator of slot s complete
+  const uint32_t bar_aready = sbase + SMEM_BAR + 112;   // [2] leader only: both CTAs' activations of slot s written
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + SMEM_BAR + 128);
+  const uint32_t bar_pefree = sbase + SMEM_BAR + 144;   // [2] the PE block of slot s is no longer read
+  const uint32_t bar_peready = sbase + SMEM_BAR + 160;  // [2] the PE block of slot s holds the next tile's encoding
+  const uint32_t crank = cluster_ctarank();
+  const bool leader = crank == 0;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < N_STAGES; ++i) {
+      mbar_init(bar_full + 8 * i, 1);
+      mbar_init(bar_empty + 8 * i, 1);
+      mbar_init(bar_pfull + 8 * i, 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(bar_acc + 8 * s, 1);
+      mbar_init(bar_aready + 8 * s, 2 * EW);  // the epilogue warps of both CTAs
+      mbar_init(bar_pefree + 8 * s, ETH);
+      mbar_init(bar_peready + 8 * s, PE_HELPERS);
+    }
+    fence_barrier_init();
+  }
+  __syncthreads();
+  cluster_sync_all();   // both CTAs' barriers exist before the pair allocates TMEM / anything remote targets them
+  if (warp == 2) tmem_alloc2(smem_u32(tmem_ptr_smem), 512);
+  tcgen05_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  // tile group g = (j*C + c)*NSLOT + s holds tiles 2g (leader) and 2g+1 (peer); a tile index past the end is computed
+  // on a clamped point and not stored.
+  const int C = gridDim.x >> 1, c = (int)blockIdx.x >> 1;
+  const int n_groups = (P.n_tiles + 1) >> 1;
+  const int n_local = c * NSLOT < n_groups ? (n_groups - c * NSLOT + C * NSLOT - 1) / (C * NSLOT) * NSLOT : 0;
+  const int n_iter = n_local / NSLOT;
+  auto group_of = [&](int j, int s) { return (j * C + c) * NSLOT + s; };
+
+  if (warp == 0) {
+    // ============================== weight producer: this CTA's half of every K-block ===================
+    uint32_t cnt = 0;
+    for (int j = 0; j < n_iter; ++j) {
+      for (int l = 0; l < P.n_layers; ++l) {
+        const TcLayer& L = P.layers[l];
+        const uint32_t bytes = (uint32_t)L.n * 64u;   // n/2 rows x 128 bytes
+        for (int s = 0; s < NSLOT; ++s) {
+          if (group_of(j, s) >= n_groups) continue;
+          const uint8_t* src = P.w + L.woff + crank * bytes;
+          for (int kbi = 0; kbi < L.nkb; ++kbi) {
+            const uint32_t e = cnt % N_STAGES, par = (cnt / N_STAGES) & 1u;
+            mbar_wait(bar_empty + 8 * e, par ^ 1u);
+            if (P.trace != nullptr && blockIdx.x == 0 && j < P.trace_tiles && lane == 0 && kbi < 4)
+              P.trace[(size_t)P.trace_tiles * P.n_layers * 16 + ((size_t)(j * P.n_layers + l) * 2 + s) * 16 + kbi] = (unsigned long long)clock64();
+            if (elect_one_sync()) {
+              mbar_expect_tx(bar_full + 8 * e, bytes);
+              tma_bulk_load(sbase + SMEM_RING + e * STAGE_BYTES, src, bytes, bar_full + 8 * e);
+            }
+            __syncwarp();
+            src += 2u * bytes;
+            ++cnt;
+          }
+        }
+      }
+    }
+    // the leader's last commits still target this CTA's `empty` barriers: wait for the final release of every entry
+    for (uint32_t k = 0; k < (uint32_t)N_STAGES && k < cnt; ++k) {
+      const uint32_t u = cnt - 1u - k;
+      mbar_wait(bar_empty + 8 * (u % N_STAGES), (u / N_STAGES) & 1u);
+    }
+  } else if (warp == 1 && !leader) {
+    // ============================== relay (peer CTA): local `full` -> leader's `pfull` ==================
+    uint32_t cnt = 0;
+    for (int j = 0; j < n_iter; ++j) {
+      for (int l = 0; l < P.n_layers; ++l) {
+        const int nkb = P.layers[l].nkb;
+        for (int s = 0; s < NSLOT; ++s) {
+          if (group_of(j, s) >= n_groups) continue;
+          for (int kbi = 0; kbi < nkb; ++kbi) {
+            const uint32_t e = cnt % N_STAGES, par = (cnt / N_STAGES) & 1u;
+            mbar_wait(bar_full + 8 * e, par);
+            if (elect_one_sync()) mbar_arrive_remote_light(bar_pfull + 8 * e, 0u);
+            __syncwarp();
+            ++cnt;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================= MMA issuer (leader CTA) ==================================
+    uint32_t cnt = 0;
+    uint32_t apar[2] = {0u, 0u};
+    for (int j = 0; j < n_iter; ++j) {
+      for (int l = 0; l < P.n_layers; ++l) {
+        const TcLayer& L = P.layers[l];
+        const uint32_t idesc = make_idesc_pair<F16>(L.n);
+        for (int s = 0; s < NSLOT; ++s) {
+          if (group_of(j, s) >= n_groups) continue;
+          const bool tr = P.trace != nullptr && blockIdx.x == 0 && j < P.trace_tiles;
+          long long t_w0 = 0, t_w1 = 0, t_full = 0, t_pfull = 0;
+          if (tr) t_w0 = clock64();
+          mbar_wait_cluster(bar_aready + 8 * s, apar[s]);
+          apar[s] ^= 1u;
+          tcgen05_fence_after();
+          if (tr) t_w1 = clock64();
+          const uint32_t acc = tmem_base + (uint32_t)s * 256u;
+          for (int kbi = 0; kbi < L.nkb; ++kbi) {
+            const uint64_t adesc = make_smem_desc(sbase + (uint32_t)(s * TC_KB_PER_TILE + L.kb[kbi]) * KB_BYTES);
+            const uint32_t e = cnt % N_STAGES, par = (cnt / N_STAGES) & 1u;
+            long long t_f0 = 0;
+            if (tr) t_f0 = clock64();
+            mbar_wait(bar_full + 8 * e, par);
+            long long t_f1 = 0;
+            if (tr) t_f1 = clock64();
+            mbar_wait_cluster(bar_pfull + 8 * e, par);
+            tcgen05_fence_after();
+            if (tr) {
+              t_full += t_f1 - t_f0;
+              t_pfull += clock64() - t_f1;
+              if (lane == 0 && kbi < 4) {
+                unsigned long long* d = P.trace + (size_t)P.trace_tiles * P.n_layers * 16 + ((size_t)(j * P.n_layers + l) * 2 + s) * 16;
+                d[4 + kbi] = (unsigned long long)t_f0;
+                d[8 + kbi] = (unsigned long long)t_f1;
+                d[12 + kbi] = (unsigned long long)clock64();
+              }
+            }
+            const uint64_t bdesc = make_smem_desc(sbase + SMEM_RING + e * STAGE_BYTES);
+#pragma unroll
+            for (int q = 0; q < 4; ++q)   // K = 16 per instruction: both operands advance 32 bytes inside the swizzle atom
+              umma_bf16_2cta(acc, adesc + 2 * q, bdesc + 2 * q, idesc, (kbi | q) != 0 ? 1u : 0u);
+            umma_commit2_mc(bar_empty + 8 * e, (uint16_t)3);
+            ++cnt;
+          }
+          umma_commit2_mc(bar_acc + 8 * s, (uint16_t)3);
+          if (tr && lane == 0) {
+            unsigned long long* r = P.trace + ((size_t)(j * P.n_layers + l) * 2 + s) * 4;
+            r[0] = (unsigned long long)t_w0;
+            r[1] = (unsigned long long)t_w1;
+            r[2] = (unsigned long long)clock64();
+            r[3] = (unsigned long long)t_full | ((unsigned long long)t_pfull << 32);
+          }
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ================================ epilogue warps (EW per tile slot) =======================================
+    const int ew = warp - 4;
+    const int s = ew / EW;                            // tile slot
+    const int hf = (ew % EW) >> 2;                    // which part of the columns (NH parts)
+    const uint32_t row = (uint32_t)((warp & 3) * 32 + lane);
+    const int tid_s = (ew % EW) * 32 + lane;          // 0..ETH-1 within the slot
+    uint8_t* arena = smem + (size_t)s * TC_KB_PER_TILE * KB_BYTES;
+    float* bias_s = reinterpret_cast<float*>(smem + SMEM_BIAS) + s * TC_BIAS_STRIDE;
+    const uint32_t acc = tmem_base + (uint32_t)s * 256u + ((uint32_t)((warp & 3) * 32) << 16);
+    uint32_t acc_par = 0u;
+    int last_pe_layer = 0;
+    for (int l2 = 0; l2 < P.n_layers; ++l2)
+      for (int k = 0; k < P.layers[l2].nkb; ++k)
+        if (P.layers[l2].kb[k] == TC_KB_PE) last_pe_layer = l2;
+    // this warp's writes to the slot are done and its accumulator reads have completed: tell the leader's MMA issuer
+    auto signal_ready = [&]() {
+      tcgen05_fence_before();
+      fence_proxy_async();     // this CTA's tensor core reads this CTA's rows: the cross-CTA part is the barrier below
+      __syncwarp();
+      if (lane == 0) {
+        if (leader) mbar_arrive(bar_aready + 8 * s);
+        else mbar_arrive_remote(bar_aready + 8 * s, 0u);
+      }
+    };
+    auto stage_bias = [&](const float* src) {   // 256 floats
+      if (ETH == 256) bias_s[tid_s] = src[tid_s];
+      else reinterpret_cast<float2*>(bias_s)[tid_s] = reinterpret_cast<const float2*>(src)[tid_s];
+    };
+
+    for (int j = 0; j < n_iter; ++j) {
+      if (group_of(j, s) >= n_groups) break;
+      const int tile = 2 * group_of(j, s) + (int)crank;
+      const long long t_tile0 = clock64();
+      int64_t pt = (int64_t)tile * TILE_M + row;
+      const bool valid = pt < P.n_points;
+      if (!valid) pt = P.n_points - 1;
+      const int64_t ray = pt / P.S;
+
+      stage_bias(P.bias);   // the first layer's bias
+      // the tile's positional encoding was written into the PE K-block by the helper warps (below), one tile ahead
+      mbar_wait(bar_peready + 8 * s, (uint32_t)j & 1u);
+      signal_ready();
+      named_bar_sync(1 + s, ETH);  // bias_s visible to the slot's warps
+
+      float alpha = 0.f;
+      for (int l = 0; l < P.n_layers; ++l) {
+        const TcLayer& L = P.layers[l];
+        const bool tr = P.trace != nullptr && blockIdx.x == 0 && tid_s == 0 && j < P.trace_tiles;
+        long long t_e0 = 0, t_e1 = 0;
+        if (tr) t_e0 = clock64();
+        if (L.epi == TC_EPI_VIEW0) prefetch_row_l1(P.view_bias + ray * P.view_w + hf * (P.view_w / NH), P.view_w / NH);   // hidden behind the wait
+        mbar_wait(bar_acc + 8 * s, acc_par);
+        acc_par ^= 1u;
+        tcgen05_fence_after();
+        if (tr) t_e1 = clock64();
+        if (l == last_pe_layer) mbar_arrive(bar_pefree + 8 * s);   // its MMAs were the last readers of the PE block
+
+        if (L.epi == TC_EPI_RGB) {
+          if (hf == 0) {
+            uint32_t v[16];
+            tmem_ld16(acc, v);
+            tmem_ld_wait();
+            if (valid) {
+              float4 o;
+              o.x = __uint_as_float(v[0]) + bias_s[0];
+              o.y = __uint_as_float(v[1]) + bias_s[1];
+              o.z = __uint_as_float(v[2]) + bias_s[2];
+              o.w = alpha;
+              reinterpret_cast<float4*>(P.raw)[pt] = o;
+            }
+          }
+          tcgen05_fence_before();
+        } else {
+          if (L.epi == TC_EPI_VIEW0) {
+            const int per = P.view_w / NH;
+            epilogue_relu_rows16<true, F16>(acc, hf * per, (hf + 1) * per, P.view_bias + ray * P.view_w, 0u, arena, row);
+            if (hf == 0) {
+              uint32_t v[16];
+              tmem_ld16(acc + P.view_w, v);
+              tmem_ld_wait();
+              alpha = __uint_as_float(v[0]) + bias_s[P.view_w];
+            }
+          } else if ((L.n % (64 * NH)) == 0) {
+            const int per = ((int)L.n >> 6) / NH;
+            epilogue_relu_cd<F16, EW == 4>(acc, hf * per, (hf + 1) * per, smem_u32(bias_s), arena, (uint32_t)((warp & 3) * 32), (uint32_t)lane);
+          } else {
+            const int per = (int)L.n / NH;
+            epilogue_relu_rows16<false, F16>(acc, hf * per, (hf + 1) * per, nullptr, smem_u32(bias_s), arena, row);
+          }
+          signal_ready();
+        }
+        if (tr) {
+          unsigned long long* r = P.trace + (size_t)P.trace_tiles * P.n_layers * 8 + ((size_t)(j * P.n_layers + l) * 2 + s) * 4;
+          r[0] = (unsigned long long)t_e0;
+          r[1] = (unsigned long long)t_e1;
+          r[2] = (unsigned long long)clock64();
+          r[3] = (unsigned long long)t_tile0;
+        }
+        // swap in the next layer's bias
+        if (l + 1 < P.n_layers) {
+          named_bar_sync(1 + s, ETH);
+          stage_bias(P.bias + (l + 1) * TC_BIAS_STRIDE);
+          named_bar_sync(1 + s, ETH);
+        }
+      }
+      named_bar_sync(1 + s, ETH);  // everyone done with bias_s before the next tile restages it
+    }
+  }
+
+  if (warp == 2 || warp == 3) {
+    // ============================ positional-encoding helper warps ==============================
+    // x = o + d*z -> [x | sin(2^k x) | cos(2^k x)] (HELP:42-52, pe.cuh) for the NEXT tile of each slot, written straight
+    // into the slot's PE K-block as soon as the last layer that reads it (the skip layer) has finished its MMAs.
+    const int t = (warp - 2) * 32 + lane;
+    for (int j = 0; j < n_iter; ++j) {
+      for (int s = 0; s < NSLOT; ++s) {
+        if (group_of(j, s) >= n_groups) continue;
+        if (j > 0) mbar_wait(bar_pefree + 8 * s, (uint32_t)(j - 1) & 1u);
+        uint8_t* pe_blk = smem + (size_t)(s * TC_KB_PER_TILE + TC_KB_PE) * KB_BYTES;
+        const int tile = 2 * group_of(j, s) + (int)crank;
+#pragma unroll 1
+        for (int h = 0; h < 2; ++h) {
+          const uint32_t row = (uint32_t)(t + 64 * h);
+          int64_t pt = (int64_t)tile * TILE_M + row;
+          if (pt >= P.n_points) pt = P.n_points - 1;
+          const int64_t ray = pt / P.S;
+          float pe[64], x[3];
+          sample_point(P.rays_o, P.rays_d, ray, P.z_vals[pt], x);
+          pe_embedder(x, P.multires, pe);
+#pragma unroll
+          for (int ch = 0; ch < 8; ++ch) {
+            float o[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) o[e] = pe[ch * 8 + e];
+            store_chunk<false, F16>(pe_blk, pe_blk, row, (uint32_t)ch, o);
+          }
+        }
+        fence_proxy_async();
+        mbar_arrive(bar_peready + 8 * s);
+      }
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // the pair's MMAs read both CTAs' shared memory and TMEM until the leader is done
+  tcgen05_fence_after();
+  if (warp == 2) tmem_dealloc2(tmem_base, 512);
+}
+
+}  // namespace tcp
+
+static int g_pair_ew = 8;   // epilogue warps per slot (debug: dfn_debug_set_impl(3) -> 8, (8) -> 4)
+void pair_set_epilogue_warps(int ew) { g_pair_ew = ew == 4 ? 4 : 8; }
+
+int pair_launch(const dfn_model* m, const float* bias_ws, const float* vbias_ws, int64_t R, int S, const float* rays_o,
+                const float* rays_d, const float* z_vals, float* raw, int precision, cudaStream_t st) {
+  const bool f16 = precision == DFN_PREC_FP16;
+  if ((precision != DFN_PREC_BF16 && !f16) || m->tc2_hi == nullptr || m->tc2_h16 == nullptr) {
+    set_error("pair_launch: the cta_group::2 kernel covers DFN_PREC_BF16 / DFN_PREC_FP16");
+    return DFN_E_UNSUPPORTED;
+  }
+  const dfn_model_desc& d = m->desc;
+  tcp::Params P;
+  memset(&P, 0, sizeof(P));
+  P.w = f16 ? m->tc2_h16 : m->tc2_hi;
+  P.bias = bias_ws;
+  P.view_bias = vbias_ws;
+  P.rays_o = rays_o;
+  P.rays_d = rays_d;
+  P.z_vals = z_vals;
+  P.raw = raw;
+  P.n_points = R * S;
+  P.S = S;
+  P.n_tiles = (int)((P.n_points + tc::TILE_M - 1) / tc::TILE_M);
+  P.n_layers = m->prog.n_layers;
+  P.multires = d.multires;
+  P.view_w = d.W / 2;
+  tc_get_trace(reinterpret_cast<void**>(&P.trace), &P.trace_tiles);
+  for (int i = 0; i < m->prog.n_layers; ++i) {
+    P.layers[i] = m->prog.layers[i];
+    P.layers[i].woff = m->tc2_woff[i];
+  }
+  int grid = P.n_tiles < num_sms() ? P.n_tiles : num_sms();
+  grid = (grid + 1) & ~1;
+  if (grid > num_sms()) grid = num_sms() & ~1;
+  const int ew = g_pair_ew;
+  auto launch = [&](auto kernel, int threads) -> int {
+    DFN_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tcp::SMEM_TOTAL));
+    kernel<<<grid, threads, tcp::SMEM_TOTAL, st>>>(P);
+    return 0;
+  };
+  int rc;
+  if (ew == 8) rc = f16 ? launch(tcp::mlp_pair_kernel<true, 8>, 640) : launch(tcp::mlp_pair_kernel<false, 8>, 640);
+  else rc = f16 ? launch(tcp::mlp_pair_kernel<true, 4>, 384) : launch(tcp::mlp_pair_kernel<false, 4>, 384);
+  if (rc) return rc;
+  return 0;
+}
+
+}  // namespace dfn

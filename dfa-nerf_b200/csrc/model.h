@@ -85,6 +85,7 @@ struct dfn_model {
   // cta_group::2 kernel (mlp_tc2.cu): per K-block, per CTA of the pair, [n/2 rows x 64 K] stages
   uint8_t* tc2_hi = nullptr;
   uint8_t* tc2_lo = nullptr;
+  uint8_t* tc2_h16 = nullptr;   // fp16 images, same offsets
   uint32_t tc2_woff[dfn::TC_MAX_LAYERS] = {};
   // TMEM-activation kernel (mlp_ts.cu): the same stage images in half-major order
   uint8_t* ts_hi = nullptr;
@@ -109,6 +110,9 @@ int pp_launch_prog(const TcProgram& prog, const uint32_t* woff32, const uint8_t*
 int pp_launch(const dfn_model* m, const float* bias_ws, const float* vbias_ws, void* scratch, int64_t R, int S,
               const float* rays_o, const float* rays_d, const float* z_vals, float* raw, int precision,
               cudaStream_t st);
+int pair_launch(const dfn_model* m, const float* bias_ws, const float* vbias_ws, int64_t R, int S, const float* rays_o,
+                const float* rays_d, const float* z_vals, float* raw, int precision, cudaStream_t st);
+void pair_set_epilogue_warps(int ew);
 int tc2_launch(const dfn_model* m, const float* bias_ws, const float* vbias_ws, int64_t R, int S, const float* rays_o,
                const float* rays_d, const float* z_vals, float* raw, int precision, cudaStream_t st);
 int ts_launch(const dfn_model* m, const float* bias_ws, const float* vbias_ws, int64_t R, int S, const float* rays_o,

@@ -115,5 +115,127 @@ __device__ __forceinline__ void epilogue_relu(uint32_t acc, int ncols, const flo
 }
 
 
+// ---- column-distributed epilogue (single-pass precisions) ----
+// tcgen05.ld.16x256b hands thread t of a warp rows t/4 and t/4 + 8 of a 16-lane group and columns 8g + 2(t%4) + {0, 1} of every
+// 8-column group g: a thread then needs only 16 of a K-block's 64 biases (eight 8-byte loads that are conflict-free across the warp: one
+// wavefront each) instead of all of them through warp-broadcast LDS.128 (four wavefronts per 16 bytes -- 1,024 of the ~2,840 shared-memory
+// wavefronts of a 256-wide tile-layer, and more than half of this epilogue's time when it runs alone: profiles/microbench/epilogue.cu).
+// The packed pair goes out as one 4-byte store; the eight rows of a store instruction land in eight different 16-byte chunks of the
+// 128-byte swizzle, i.e. 32 distinct banks.  Results are bit-identical to epilogue_relu (same fp32 add, same rounding).
+__device__ __forceinline__ void tmem_ld_16x256b_x8(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.16x256b.x8.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+        "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+        "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+
+// one 16-row x 64-column piece: v as loaded by tmem_ld_16x256b_x8, b = this thread's 16 biases of the K-block
+template <bool F16>
+__device__ __forceinline__ void epilogue_piece_cd(const uint32_t (&v)[32], const float (&b)[16], uint8_t* blk, uint32_t row_lo, uint32_t lane) {
+  const uint32_t sub = (lane & 3u) * 4u;
+#pragma unroll
+  for (int g = 0; g < 8; ++g) {
+    uint32_t p0, p1;
+    if (F16) {
+      p0 = add_relu_pack_f16(v[4 * g + 0], v[4 * g + 1], b[2 * g], b[2 * g + 1]);
+      p1 = add_relu_pack_f16(v[4 * g + 2], v[4 * g + 3], b[2 * g], b[2 * g + 1]);
+    } else {
+      p0 = add_relu_pack(v[4 * g + 0], v[4 * g + 1], b[2 * g], b[2 * g + 1]);
+      p1 = add_relu_pack(v[4 * g + 2], v[4 * g + 3], b[2 * g], b[2 * g + 1]);
+    }
+    *reinterpret_cast<uint32_t*>(blk + swz(row_lo, (uint32_t)g) + sub) = p0;
+    *reinterpret_cast<uint32_t*>(blk + swz(row_lo + 8u, (uint32_t)g) + sub) = p1;
+  }
+}
+
+// K-blocks [kb_begin, kb_end) of the accumulator (64 columns each) of this warp's 32 lanes -> the next layer's activation blocks.
+// acc: TMEM address of the warp's lane quarter (lane field = 32 * (warp % 4)) and the slot's first column; row0 = 32 * (warp % 4).
+// DB: the next 16-lane piece is in flight while the current one is processed (64 data registers); !DB: one piece at a time, for
+// kernels with two warps per lane quarter and a 96-register budget (the two warps overlap each other).
+template <bool F16, bool DB = true>
+__device__ __forceinline__ void epilogue_relu_cd(uint32_t acc, int kb_begin, int kb_end, uint32_t sbias, uint8_t* arena_hi, uint32_t row0,
+                                                 uint32_t lane) {
+  const uint32_t r = row0 + (lane >> 2);
+  if (DB) {
+    uint32_t v0[32], v1[32];
+    tmem_ld_16x256b_x8(acc + (uint32_t)kb_begin * 64u, v0);
+    for (int kb = kb_begin; kb < kb_end; ++kb) {
+      float b[16];
+      const uint32_t ba = sbias + (uint32_t)(kb * 64 + 2 * (int)(lane & 3u)) * 4u;
+#pragma unroll
+      for (int g = 0; g < 8; ++g)
+        asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(b[2 * g]), "=f"(b[2 * g + 1]) : "r"(ba + (uint32_t)g * 32u));
+      uint8_t* blk = arena_hi + (size_t)kb * KB_BYTES;
+      tmem_ld_wait();
+      tmem_ld_16x256b_x8(acc + (16u << 16) + (uint32_t)kb * 64u, v1);
+      epilogue_piece_cd<F16>(v0, b, blk, r, lane);
+      tmem_ld_wait();
+      if (kb + 1 < kb_end) tmem_ld_16x256b_x8(acc + (uint32_t)(kb + 1) * 64u, v0);
+      epilogue_piece_cd<F16>(v1, b, blk, r + 16u, lane);
+    }
+  } else {
+    uint32_t v[32];
+    for (int kb = kb_begin; kb < kb_end; ++kb) {
+      tmem_ld_16x256b_x8(acc + (uint32_t)kb * 64u, v);
+      float b[16];
+      const uint32_t ba = sbias + (uint32_t)(kb * 64 + 2 * (int)(lane & 3u)) * 4u;
+#pragma unroll
+      for (int g = 0; g < 8; ++g)
+        asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(b[2 * g]), "=f"(b[2 * g + 1]) : "r"(ba + (uint32_t)g * 32u));
+      uint8_t* blk = arena_hi + (size_t)kb * KB_BYTES;
+      tmem_ld_wait();
+      epilogue_piece_cd<F16>(v, b, blk, r, lane);
+      tmem_ld_16x256b_x8(acc + (16u << 16) + (uint32_t)kb * 64u, v);
+      tmem_ld_wait();
+      epilogue_piece_cd<F16>(v, b, blk, r + 16u, lane);
+    }
+  }
+}
+
+// Row-per-thread epilogue over columns [c_begin, c_end) (multiples of 32) with 16-column TMEM loads, the next one in flight (32 data
+// registers): the per-ray-bias layer (GLOBAL_BIAS: every row has its own bias row in global memory) in the 96-register kernels.
+template <bool GLOBAL_BIAS, bool F16>
+__device__ __forceinline__ void epilogue_relu_rows16(uint32_t acc, int c_begin, int c_end, const float* gbias, uint32_t sbias,
+                                                     uint8_t* arena_hi, uint32_t row) {
+  uint32_t v0[16], v1[16];
+  auto piece = [&](const uint32_t (&v)[16], int c) {
+#pragma unroll
+    for (int g = 0; g < 2; ++g) {
+      float b[8];
+      if (GLOBAL_BIAS) ldg_f32x8(gbias + c + g * 8, b);
+      else lds_f32x8(sbias + (uint32_t)(c + g * 8) * 4u, b);
+      uint4 h;
+      if (F16) {
+        h.x = add_relu_pack_f16(v[g * 8 + 0], v[g * 8 + 1], b[0], b[1]);
+        h.y = add_relu_pack_f16(v[g * 8 + 2], v[g * 8 + 3], b[2], b[3]);
+        h.z = add_relu_pack_f16(v[g * 8 + 4], v[g * 8 + 5], b[4], b[5]);
+        h.w = add_relu_pack_f16(v[g * 8 + 6], v[g * 8 + 7], b[6], b[7]);
+      } else {
+        h.x = add_relu_pack(v[g * 8 + 0], v[g * 8 + 1], b[0], b[1]);
+        h.y = add_relu_pack(v[g * 8 + 2], v[g * 8 + 3], b[2], b[3]);
+        h.z = add_relu_pack(v[g * 8 + 4], v[g * 8 + 5], b[4], b[5]);
+        h.w = add_relu_pack(v[g * 8 + 6], v[g * 8 + 7], b[6], b[7]);
+      }
+      const int cc = c + g * 8;
+      *reinterpret_cast<uint4*>(arena_hi + (size_t)(cc >> 6) * KB_BYTES + swz(row, (uint32_t)((cc & 63) >> 3))) = h;
+    }
+  };
+  tmem_ld16(acc + (uint32_t)c_begin, v0);
+  for (int c = c_begin; c < c_end; c += 32) {
+    tmem_ld_wait();
+    tmem_ld16(acc + (uint32_t)(c + 16), v1);
+    piece(v0, c);
+    tmem_ld_wait();
+    if (c + 32 < c_end) tmem_ld16(acc + (uint32_t)(c + 32), v0);
+    piece(v1, c + 16);
+  }
+}
+
 }  // namespace tc
 }  // namespace dfn

@@ -29,7 +29,8 @@ struct Packer {
   std::vector<uint8_t> hi, lo;       // [<=128 rows x 64 K] stages, 128-byte swizzle (mlp_ts.cu)
   std::vector<uint8_t> hi32, lo32;   // [n rows x 32 K] stages, 64-byte swizzle (mlp_tc.cu)
   std::vector<uint8_t> h16;          // the hi32 images with fp16 instead of bf16 values (DFN_PREC_FP16), same offsets
-  std::vector<uint8_t> hi2, lo2;     // [n/2 rows x 64 K] per CTA of a pair, 128-byte swizzle (mlp_tc2.cu)
+  std::vector<uint8_t> hi2, lo2;     // [n/2 rows x 64 K] per CTA of a pair, 128-byte swizzle (mlp_pair.cu; lo2: experiments only)
+  std::vector<uint8_t> h16_2;        // the hi2 images with fp16 values (DFN_PREC_FP16), same offsets
   uint32_t last32 = 0;               // offset of the last layer added to hi32
   uint32_t last2 = 0;                // offset of the last layer added to hi2
   bool want2 = true;                 // build the cta_group::2 images
@@ -103,6 +104,7 @@ struct Packer {
           const size_t base = hi2.size();
           hi2.resize(base + (size_t)half * 128, 0);
           lo2.resize(base + (size_t)half * 128, 0);
+          h16_2.resize(base + (size_t)half * 128, 0);
           for (int r = 0; r < half; ++r) {
             for (int k = 0; k < 64; ++k) {
               const float w = wfun(rank * half + r, kbi, k);
@@ -111,6 +113,8 @@ struct Packer {
               const size_t o = base + (size_t)r * 128 + ((((size_t)k >> 3) ^ ((size_t)r & 7)) << 4) + ((size_t)k & 7) * 2;
               memcpy(&hi2[o], &h, 2);
               memcpy(&lo2[o], &l, 2);
+              const __half hh = __float2half_rn(w);
+              memcpy(&h16_2[o], &hh, 2);
             }
           }
         }

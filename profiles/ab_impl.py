@@ -12,7 +12,7 @@ import synth  # noqa: E402
 R = int(sys.argv[1]) if len(sys.argv) > 1 else 4000
 impls = [int(x) for x in sys.argv[2].split(',')] if len(sys.argv) > 2 else [1, 2, 3]
 S = 192
-NAMES = {0: 'ts', 1: 'tc', 2: 'pp', 3: 'tc2'}
+NAMES = {0: 'ts', 1: 'tc', 2: 'pp', 3: 'pair-ew8', 7: 'tc2', 8: 'pair-ew4', 4: 'tc-unicast', 5: 'tc-unicast-cd', 6: 'tc-cd'}
 dev = torch.device('cuda', 0)
 net = dfn.FaceNeRF(D=8, W=256, input_ch=63, input_ch_views=27, dim_aud=64, output_ch=4, skips=[4], use_viewdirs=True)
 net.load_state_dict(synth.facenerf_state_dict(1))
@@ -26,7 +26,7 @@ for mode, prec in (('bf16', dfn.PREC_BF16), ('bf16x3', dfn.PREC_BF16X3)):
     eng = dfn.RenderEngine(net, None, S, 0, precision=prec)
     outs = {}
     for impl in impls:
-        if impl == 3 and mode != 'bf16':
+        if impl >= 3 and mode != 'bf16':
             continue
         dfn.lib.dfn_debug_set_impl(impl)
         for _ in range(2):

@@ -24,12 +24,13 @@ aud = fr['aud'].to(dev)
 eng = dfn.RenderEngine(net, None, S, 0, precision={'bf16': dfn.PREC_BF16, 'bf16x3': dfn.PREC_BF16X3}[mode])
 eng.query_points(net, ro, rd, vd, z, aud)
 T, NL = 6, 12
-buf = torch.zeros(2 * T * NL * 8, dtype=torch.int64, device=dev)
+buf = torch.zeros(2 * T * NL * 8 + T * NL * 2 * 16, dtype=torch.int64, device=dev)
 dfn.lib.dfn_debug_trace(C.c_void_p(buf.data_ptr()), T)
 eng.query_points(net, ro, rd, vd, z, aud)
 torch.cuda.synchronize()
 dfn.lib.dfn_debug_trace(None, 0)
-b = buf.cpu().reshape(2, T, NL, 2, 4)
+detail = buf.cpu()[2 * T * NL * 8:].reshape(T, NL, 2, 4, 4)
+b = buf.cpu()[:2 * T * NL * 8].reshape(2, T, NL, 2, 4)
 t0 = int(b[0, 0, 0, 0, 0])
 nslot = 2 if mode == 'bf16' else 1
 print('MMA issuer (cycles rel. to start): tile layer slot | wait_aready  issue(incl. full waits)  full_wait')
@@ -45,3 +46,11 @@ for j in range(2, 4):
             w0, w1, e, tt = [int(x) for x in b[1, j, l, s]]
             extra = ' (tile start->first wait: %d = PE)' % (w0 - tt) if l == 0 else ''
             print('  j=%d l=%2d s=%d  start %8d  wait_acc %6d  work %6d%s' % (j, l, s, w0 - t0, w1 - w0, e - w1, extra))
+
+if int(detail.abs().sum()) != 0:
+    print('PAIR kernel, per K-block of (j=3; l=2,3): producer saw the entry empty | issuer began waiting | own half landed | peer half landed')
+    for l in (2, 3):
+        for s in range(nslot):
+            for k in range(4):
+                pe, f0, f1, f2 = [int(x) - t0 for x in detail[3, l, s, :, k]]
+                print('  l=%d s=%d kb=%d  empty %8d  wait-begin %8d  full %8d  pfull %8d' % (l, s, k, pe, f0, f1, f2))

@@ -196,6 +196,7 @@ def test_two_training_steps_match_the_reference(train):
         assert abs(float(loss) - float(loss_ref)) <= 1e-4 * float(loss_ref)
         worst = 0.
         n_checked = 0
+        errs = []
         for k in params:
             for n, q in params[k].items():
                 gq = tr.grads[k][n].cpu()
@@ -204,10 +205,12 @@ def test_two_training_steps_match_the_reference(train):
                     continue
                 e = rel(gq, q.grad)
                 worst = max(worst, e)
-                assert e <= 1e-4, (step, k, n, e)
+                errs.append((e, k, n))
                 n_checked += 1
                 assert (tr.params[k][n].cpu() - q.detach()).abs().max().item() <= 0.05 * LRATE, (step, k, n)
         assert n_checked == 74
+        print('step %d, largest relative gradient errors: %s' % (step, ', '.join('%s/%s %.1e' % (k, n, e) for e, k, n in sorted(errs, reverse=True)[:12])))
+        assert worst <= 1e-4, sorted(errs, reverse=True)[:5]
         for key in picks:
             _, k, n = key.split('/')
             gq = tr.grads[k][n].cpu()
