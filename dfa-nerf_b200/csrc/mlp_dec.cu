@@ -131,7 +131,7 @@ struct Builder {
   std::vector<float> dot;                  // folded heads (TC_DOT_FLOATS) or empty
   int nl = 0;
   explicit Builder(DecField* f, int dimL) : F(f), bias((size_t)TC_MAX_LAYERS * TC_BIAS_STRIDE, 0.f) {
-    pk.want64 = false;
+    pk.want2 = false;   // the Decoder programs run on mlp_pp.cu
     F->prog = TcProgram();
     F->dimL = dimL;
     F->n_fold = 0;

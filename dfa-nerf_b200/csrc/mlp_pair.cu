@@ -37,12 +37,12 @@ namespace tcp {
 
 using namespace dfn::tc;
 
-static constexpr int STAGE_BYTES = 128 * 128;      // one ring entry: this CTA's <=128 weight rows x 64 K
-static constexpr int N_STAGES = 4;
+static constexpr int ENT_BYTES = 2 * 128 * 128;    // one ring entry: two K-blocks of this CTA's <=128 weight rows x 64 K
+static constexpr int N_ENT = 2;
 static constexpr int PE_HELPERS = 64;
 static constexpr int ARENA_BLOCKS = 2 * TC_KB_PER_TILE;
 static constexpr int SMEM_RING = ARENA_BLOCKS * KB_BYTES;
-static constexpr int SMEM_BIAS = SMEM_RING + N_STAGES * STAGE_BYTES;
+static constexpr int SMEM_BIAS = SMEM_RING + N_ENT * ENT_BYTES;
 static constexpr int SMEM_BAR = SMEM_BIAS + 2 * TC_BIAS_STRIDE * 4;
 static constexpr int SMEM_TOTAL = SMEM_BAR + 256;
 static_assert(SMEM_TOTAL <= 227 * 1024, "shared memory budget");
@@ -63,6 +63,7 @@ struct Params {
   int view_w;
   unsigned long long* trace;  // debug: per-role clock64 records of CTA 0 (null in production), format of mlp_tc.cu
   int trace_tiles;
+  int flags;                  // bit 0: a layer's weights stay in the ring for both slots; bit 1: CTA-scope release on the peer's `aready` arrivals
   TcLayer layers[TC_MAX_LAYERS];
 };
 
@@ -85,9 +86,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((4 + 2 * EW) * 32, 1
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const uint32_t bar_full = sbase + SMEM_BAR;           // [4] this CTA's half of ring entry e has landed
-  const uint32_t bar_empty = sbase + SMEM_BAR + 32;     // [4] ring entry e consumed by the pair's MMAs
-  const uint32_t bar_pfull = sbase + SMEM_BAR + 64;     // [4] leader only: the PEER's half of entry e has landed
+  const uint32_t bar_full = sbase + SMEM_BAR;           // [2] ring entry e has landed (leader: in both CTAs; peer: its own half)
+  const uint32_t bar_empty = sbase + SMEM_BAR + 32;     // [2] ring entry e consumed by the pair's MMAs
   const uint32_t bar_acc = sbase + SMEM_BAR + 96;       // [2] accumulator of slot s complete
   const uint32_t bar_aready = sbase + SMEM_BAR + 112;   // [2] leader only: both CTAs' activations of slot s written
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + SMEM_BAR + 128);
@@ -97,10 +97,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((4 + 2 * EW) * 32, 1
   const bool leader = crank == 0;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < N_STAGES; ++i) {
-      mbar_init(bar_full + 8 * i, 1);
+    for (int i = 0; i < N_ENT; ++i) {
+      mbar_init(bar_full + 8 * i, leader ? 2 : 1);
       mbar_init(bar_empty + 8 * i, 1);
-      mbar_init(bar_pfull + 8 * i, 1);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(bar_acc + 8 * s, 1);
@@ -127,52 +126,57 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((4 + 2 * EW) * 32, 1
   const int n_iter = n_local / NSLOT;
   auto group_of = [&](int j, int s) { return (j * C + c) * NSLOT + s; };
 
+  // Ring: two entries of two weight K-blocks each (2 x 32 KB) on one `full` / `empty` barrier pair per entry -- the MMA issuer is one
+  // thread, an mbarrier poll costs it 130-220 cycles even when the phase is complete and issuing an MMA ~95, so with a poll per K-block
+  // (plus one for the peer's half) it could not keep up with the tensor pipe (128 cycles per MMA); per entry of eight MMAs it can.
+  // The leader's `full` barrier counts two arrivals: its own producer's expect_tx and the peer relay's forward of the peer's completion.
+  // Layers of at most four K-blocks (all but the skip layer) are loaded ONCE per iteration and read by both slots' MMAs (flag bit 0).
+  auto n_uses = [&](int live, int nkb) { return ((P.flags & 1) && live == 2 && nkb <= 2 * N_ENT) ? 1 : live; };
   if (warp == 0) {
     // ============================== weight producer: this CTA's half of every K-block ===================
     uint32_t cnt = 0;
     for (int j = 0; j < n_iter; ++j) {
+      const int live = (group_of(j, 0) < n_groups ? 1 : 0) + (group_of(j, 1) < n_groups ? 1 : 0);
       for (int l = 0; l < P.n_layers; ++l) {
         const TcLayer& L = P.layers[l];
-        const uint32_t bytes = (uint32_t)L.n * 64u;   // n/2 rows x 128 bytes
-        for (int s = 0; s < NSLOT; ++s) {
-          if (group_of(j, s) >= n_groups) continue;
-          const uint8_t* src = P.w + L.woff + crank * bytes;
-          for (int kbi = 0; kbi < L.nkb; ++kbi) {
-            const uint32_t e = cnt % N_STAGES, par = (cnt / N_STAGES) & 1u;
+        const uint32_t bytes = (uint32_t)L.n * 64u;   // one K-block of this CTA: n/2 rows x 128 bytes
+        const int uses = n_uses(live, L.nkb);
+        for (int u = 0; u < uses; ++u) {
+          const uint8_t* src = P.w + L.woff + crank * (uint32_t)L.nkb * bytes;
+          for (int kb0 = 0; kb0 < L.nkb; kb0 += 2) {
+            const uint32_t nb = L.nkb - kb0 >= 2 ? 2u : 1u;
+            const uint32_t e = cnt % N_ENT, par = (cnt / N_ENT) & 1u;
             mbar_wait(bar_empty + 8 * e, par ^ 1u);
-            if (P.trace != nullptr && blockIdx.x == 0 && j < P.trace_tiles && lane == 0 && kbi < 4)
-              P.trace[(size_t)P.trace_tiles * P.n_layers * 16 + ((size_t)(j * P.n_layers + l) * 2 + s) * 16 + kbi] = (unsigned long long)clock64();
             if (elect_one_sync()) {
-              mbar_expect_tx(bar_full + 8 * e, bytes);
-              tma_bulk_load(sbase + SMEM_RING + e * STAGE_BYTES, src, bytes, bar_full + 8 * e);
+              mbar_expect_tx(bar_full + 8 * e, nb * bytes);
+              tma_bulk_load(sbase + SMEM_RING + e * ENT_BYTES, src, nb * bytes, bar_full + 8 * e);
             }
             __syncwarp();
-            src += 2u * bytes;
+            src += nb * bytes;
             ++cnt;
           }
         }
       }
     }
     // the leader's last commits still target this CTA's `empty` barriers: wait for the final release of every entry
-    for (uint32_t k = 0; k < (uint32_t)N_STAGES && k < cnt; ++k) {
+    for (uint32_t k = 0; k < (uint32_t)N_ENT && k < cnt; ++k) {
       const uint32_t u = cnt - 1u - k;
-      mbar_wait(bar_empty + 8 * (u % N_STAGES), (u / N_STAGES) & 1u);
+      mbar_wait(bar_empty + 8 * (u % N_ENT), (u / N_ENT) & 1u);
     }
   } else if (warp == 1 && !leader) {
-    // ============================== relay (peer CTA): local `full` -> leader's `pfull` ==================
+    // ============================== relay (peer CTA): local `full` -> the leader's `full` ==================
     uint32_t cnt = 0;
     for (int j = 0; j < n_iter; ++j) {
+      const int live = (group_of(j, 0) < n_groups ? 1 : 0) + (group_of(j, 1) < n_groups ? 1 : 0);
       for (int l = 0; l < P.n_layers; ++l) {
         const int nkb = P.layers[l].nkb;
-        for (int s = 0; s < NSLOT; ++s) {
-          if (group_of(j, s) >= n_groups) continue;
-          for (int kbi = 0; kbi < nkb; ++kbi) {
-            const uint32_t e = cnt % N_STAGES, par = (cnt / N_STAGES) & 1u;
-            mbar_wait(bar_full + 8 * e, par);
-            if (elect_one_sync()) mbar_arrive_remote_light(bar_pfull + 8 * e, 0u);
-            __syncwarp();
-            ++cnt;
-          }
+        const int n_ent = n_uses(live, nkb) * ((nkb + 1) >> 1);
+        for (int u = 0; u < n_ent; ++u) {
+          const uint32_t e = cnt % N_ENT, par = (cnt / N_ENT) & 1u;
+          mbar_wait(bar_full + 8 * e, par);
+          if (elect_one_sync()) mbar_arrive_remote_light(bar_full + 8 * e, 0u);   // forwards a completion it observed: CTA-scope release
+          __syncwarp();
+          ++cnt;
         }
       }
     }
@@ -181,44 +185,45 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((4 + 2 * EW) * 32, 1
     uint32_t cnt = 0;
     uint32_t apar[2] = {0u, 0u};
     for (int j = 0; j < n_iter; ++j) {
+      const int live = (group_of(j, 0) < n_groups ? 1 : 0) + (group_of(j, 1) < n_groups ? 1 : 0);
       for (int l = 0; l < P.n_layers; ++l) {
         const TcLayer& L = P.layers[l];
         const uint32_t idesc = make_idesc_pair<F16>(L.n);
+        const uint32_t bytes = (uint32_t)L.n * 64u;
+        const bool reuse = n_uses(live, L.nkb) == 1 && live == 2;
+        const uint32_t base = cnt;
         for (int s = 0; s < NSLOT; ++s) {
           if (group_of(j, s) >= n_groups) continue;
           const bool tr = P.trace != nullptr && blockIdx.x == 0 && j < P.trace_tiles;
-          long long t_w0 = 0, t_w1 = 0, t_full = 0, t_pfull = 0;
+          long long t_w0 = 0, t_w1 = 0, t_full = 0;
           if (tr) t_w0 = clock64();
           mbar_wait_cluster(bar_aready + 8 * s, apar[s]);
           apar[s] ^= 1u;
           tcgen05_fence_after();
           if (tr) t_w1 = clock64();
           const uint32_t acc = tmem_base + (uint32_t)s * 256u;
-          for (int kbi = 0; kbi < L.nkb; ++kbi) {
-            const uint64_t adesc = make_smem_desc(sbase + (uint32_t)(s * TC_KB_PER_TILE + L.kb[kbi]) * KB_BYTES);
-            const uint32_t e = cnt % N_STAGES, par = (cnt / N_STAGES) & 1u;
-            long long t_f0 = 0;
-            if (tr) t_f0 = clock64();
-            mbar_wait(bar_full + 8 * e, par);
-            long long t_f1 = 0;
-            if (tr) t_f1 = clock64();
-            mbar_wait_cluster(bar_pfull + 8 * e, par);
-            tcgen05_fence_after();
-            if (tr) {
-              t_full += t_f1 - t_f0;
-              t_pfull += clock64() - t_f1;
-              if (lane == 0 && kbi < 4) {
-                unsigned long long* d = P.trace + (size_t)P.trace_tiles * P.n_layers * 16 + ((size_t)(j * P.n_layers + l) * 2 + s) * 16;
-                d[4 + kbi] = (unsigned long long)t_f0;
-                d[8 + kbi] = (unsigned long long)t_f1;
-                d[12 + kbi] = (unsigned long long)clock64();
+          const bool first_use = !reuse || s == 0, last_use = !reuse || s == 1;
+          if (reuse) cnt = base;
+          for (int kb0 = 0; kb0 < L.nkb; kb0 += 2) {
+            const uint32_t e = cnt % N_ENT, par = (cnt / N_ENT) & 1u;
+            if (first_use) {
+              long long t_f0 = 0;
+              if (tr) t_f0 = clock64();
+              mbar_wait_cluster(bar_full + 8 * e, par);
+              tcgen05_fence_after();
+              if (tr) t_full += clock64() - t_f0;
+            }
+#pragma unroll
+            for (int b = 0; b < 2; ++b) {
+              if (kb0 + b < L.nkb) {
+                const uint64_t adesc = make_smem_desc(sbase + (uint32_t)(s * TC_KB_PER_TILE + L.kb[kb0 + b]) * KB_BYTES);
+                const uint64_t bdesc = make_smem_desc(sbase + SMEM_RING + e * ENT_BYTES + (uint32_t)b * bytes);
+#pragma unroll
+                for (int q = 0; q < 4; ++q)   // K = 16 per instruction: both operands advance 32 bytes inside the swizzle atom
+                  umma_bf16_2cta(acc, adesc + 2 * q, bdesc + 2 * q, idesc, (kb0 | b | q) != 0 ? 1u : 0u);
               }
             }
-            const uint64_t bdesc = make_smem_desc(sbase + SMEM_RING + e * STAGE_BYTES);
-#pragma unroll
-            for (int q = 0; q < 4; ++q)   // K = 16 per instruction: both operands advance 32 bytes inside the swizzle atom
-              umma_bf16_2cta(acc, adesc + 2 * q, bdesc + 2 * q, idesc, (kbi | q) != 0 ? 1u : 0u);
-            umma_commit2_mc(bar_empty + 8 * e, (uint16_t)3);
+            if (last_use) umma_commit2_mc(bar_empty + 8 * e, (uint16_t)3);
             ++cnt;
           }
           umma_commit2_mc(bar_acc + 8 * s, (uint16_t)3);
@@ -227,7 +232,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((4 + 2 * EW) * 32, 1
             r[0] = (unsigned long long)t_w0;
             r[1] = (unsigned long long)t_w1;
             r[2] = (unsigned long long)clock64();
-            r[3] = (unsigned long long)t_full | ((unsigned long long)t_pfull << 32);
+            r[3] = (unsigned long long)t_full;
           }
         }
       }
@@ -254,6 +259,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((4 + 2 * EW) * 32, 1
       __syncwarp();
       if (lane == 0) {
         if (leader) mbar_arrive(bar_aready + 8 * s);
+        else if (P.flags & 2) mbar_arrive_remote_light(bar_aready + 8 * s, 0u);
         else mbar_arrive_remote(bar_aready + 8 * s, 0u);
       }
     };
@@ -385,8 +391,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((4 + 2 * EW) * 32, 1
 
 }  // namespace tcp
 
-static int g_pair_ew = 8;   // epilogue warps per slot (debug: dfn_debug_set_impl(3) -> 8, (8) -> 4)
+static int g_pair_ew = 8, g_pair_flags = 0;   // epilogue warps per slot (debug: dfn_debug_set_impl(3) -> 8, (8) -> 4)
 void pair_set_epilogue_warps(int ew) { g_pair_ew = ew == 4 ? 4 : 8; }
+void pair_set_flags(int flags) { g_pair_flags = flags; }
 
 int pair_launch(const dfn_model* m, const float* bias_ws, const float* vbias_ws, int64_t R, int S, const float* rays_o,
                 const float* rays_d, const float* z_vals, float* raw, int precision, cudaStream_t st) {
@@ -412,6 +419,7 @@ int pair_launch(const dfn_model* m, const float* bias_ws, const float* vbias_ws,
   P.multires = d.multires;
   P.view_w = d.W / 2;
   tc_get_trace(reinterpret_cast<void**>(&P.trace), &P.trace_tiles);
+  P.flags = g_pair_flags;
   for (int i = 0; i < m->prog.n_layers; ++i) {
     P.layers[i] = m->prog.layers[i];
     P.layers[i].woff = m->tc2_woff[i];

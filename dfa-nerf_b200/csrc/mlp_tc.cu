@@ -67,10 +67,8 @@ struct Params {
 // ------------------------------------------------------------------------------------ kernel
 // X3 = false: bf16, two tile slots (384 threads).  X3 = true: split-bf16, one slot (256 threads).
 // F16 (bf16-mode schedule only): fp16 operands -- P.w_hi then points at the fp16 weight stages.
-// MC: clusters of two CTAs share every weight stage by multicast (launch with a cluster dimension of 2); !MC: every CTA streams its own.
-// CD: column-distributed epilogue (tc_epi.cuh, epilogue_relu_cd) for the ReLU layers of the single-pass precisions.
-template <bool X3, bool F16 = false, bool MC = true, bool CD = false>
-__global__ void __launch_bounds__(X3 ? 256 : 384, 1)
+template <bool X3, bool F16 = false>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(X3 ? 256 : 384, 1)
     mlp_tc_kernel(const __grid_constant__ Params P) {
   static_assert(!(X3 && F16), "fp16 operands run in the single-pass schedule");
   constexpr int NSLOT = X3 ? 1 : 2;
@@ -92,7 +90,7 @@ __global__ void __launch_bounds__(X3 ? 256 : 384, 1)
   if (threadIdx.x == 0) {
     for (int i = 0; i < N_STAGES; ++i) {
       mbar_init(bar_full + 8 * i, 1);
-      mbar_init(bar_empty + 8 * i, MC ? 2 : 1);  // released by the MMA commits of both CTAs of the cluster
+      mbar_init(bar_empty + 8 * i, 2);  // released by the MMA commits of both CTAs of the cluster
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(bar_acc + 8 * s, 1);
@@ -105,7 +103,7 @@ __global__ void __launch_bounds__(X3 ? 256 : 384, 1)
   if (warp == 2) tmem_alloc(smem_u32(tmem_ptr_smem), 512);
   tcgen05_fence_before();
   __syncthreads();
-  if (MC) cluster_sync_all();  // both CTAs' barriers exist before any multicast copy or remote commit targets them
+  cluster_sync_all();  // both CTAs' barriers exist before any multicast copy or remote commit targets them
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
 
@@ -114,10 +112,9 @@ __global__ void __launch_bounds__(X3 ? 256 : 384, 1)
   // The two CTAs therefore walk the same (iteration, layer, slot) sequence; tile group g = (j*C + c)*NSLOT + s
   // holds tiles 2g (rank 0) and 2g+1 (rank 1); a tile index past the end is computed on a clamped point
   // and not stored.
-  constexpr int CS = MC ? 2 : 1;   // tiles per group = CTAs per cluster
-  const uint32_t crank = MC ? cluster_ctarank() : 0u;
-  const int C = gridDim.x / CS, c = (int)blockIdx.x / CS;
-  const int n_groups = (P.n_tiles + CS - 1) / CS;
+  const uint32_t crank = cluster_ctarank();
+  const int C = gridDim.x >> 1, c = (int)blockIdx.x >> 1;
+  const int n_groups = (P.n_tiles + 1) >> 1;
   const int n_local = c * NSLOT < n_groups ? (n_groups - c * NSLOT + C * NSLOT - 1) / (C * NSLOT) * NSLOT : 0;  // slots incl. tail
   const int n_iter = n_local / NSLOT;
   auto group_of = [&](int j, int s) { return (j * C + c) * NSLOT + s; };
@@ -145,9 +142,7 @@ __global__ void __launch_bounds__(X3 ? 256 : 384, 1)
                   mbar_wait(bar_empty + 8 * e, par ^ 1u);
                   if (elect_one_sync()) {
                     mbar_expect_tx(bar_full + 8 * e, bytes);
-                    if (!MC)
-                      tma_bulk_load(sbase + SMEM_RING + e * STAGE_BYTES, P.w_hi + off + kh * bytes, bytes, bar_full + 8 * e);
-                    else if ((cnt & 1u) == crank)
+                    if ((cnt & 1u) == crank)
                       tma_bulk_load_mc(sbase + SMEM_RING + e * STAGE_BYTES, P.w_hi + off + kh * bytes, bytes, bar_full + 8 * e, (uint16_t)3);
                   }
                   __syncwarp();
@@ -161,10 +156,7 @@ __global__ void __launch_bounds__(X3 ? 256 : 384, 1)
                   mbar_expect_tx(bar_full + 8 * pair, 2u * bytes);  // both CTAs arm their own barrier ...
                   const uint8_t* src = (part == 0 ? P.w_hi : P.w_lo) + off;
                   const uint32_t dst = sbase + SMEM_RING + pair * 2u * STAGE_BYTES;
-                  if (!MC) {
-                    tma_bulk_load(dst, src, bytes, bar_full + 8 * pair);
-                    tma_bulk_load(dst + STAGE_BYTES, src + bytes, bytes, bar_full + 8 * pair);
-                  } else if ((cnt & 1u) == crank) {                 // ... and take turns issuing the multicast copies
+                  if ((cnt & 1u) == crank) {                        // ... and take turns issuing the multicast copies
                     tma_bulk_load_mc(dst, src, bytes, bar_full + 8 * pair, (uint16_t)3);
                     tma_bulk_load_mc(dst + STAGE_BYTES, src + bytes, bytes, bar_full + 8 * pair, (uint16_t)3);
                   }
@@ -220,8 +212,7 @@ __global__ void __launch_bounds__(X3 ? 256 : 384, 1)
 #pragma unroll
                   for (int ks = 0; ks < 2; ++ks)
                     umma_bf16(acc, adesc_hi + 2 * (2 * kh + ks), bdesc + (uint64_t)(ks * 2), idesc, (kbi | kh | ks) != 0 ? 1u : 0u);
-                  if (MC) umma_commit_mc(bar_empty + 8 * e, (uint16_t)3);
-                  else umma_commit(bar_empty + 8 * e);
+                  umma_commit_mc(bar_empty + 8 * e, (uint16_t)3);
                   ++cnt;
                 }
               } else
@@ -245,8 +236,7 @@ __global__ void __launch_bounds__(X3 ? 256 : 384, 1)
                     umma_bf16(acc, adesc_lo + 2 * q, bd, idesc, 1u);
                   }
                 }
-                if (MC) umma_commit_mc(bar_empty + 8 * pair, (uint16_t)3);
-                else umma_commit(bar_empty + 8 * pair);
+                umma_commit_mc(bar_empty + 8 * pair, (uint16_t)3);
                 ++cnt;
               }
             }
@@ -280,7 +270,7 @@ __global__ void __launch_bounds__(X3 ? 256 : 384, 1)
     for (int j = 0; j < n_iter; ++j) {
       if (group_of(j, s) >= n_groups) break;
       const int i = j * NSLOT + s;
-      const int tile = CS * group_of(j, s) + (int)crank;
+      const int tile = 2 * group_of(j, s) + (int)crank;
       const long long t_tile0 = clock64();
       int64_t pt = (int64_t)tile * TILE_M + row;
       const bool valid = pt < P.n_points;
@@ -331,8 +321,6 @@ __global__ void __launch_bounds__(X3 ? 256 : 384, 1)
         } else {
           if (L.epi == TC_EPI_VIEW0)
             epilogue_relu<X3, true, F16>(acc, P.view_w, P.view_bias + ray * P.view_w, 0u, arena_hi, arena_lo, row);
-          else if (CD && !X3 && (L.n & 63) == 0)
-            epilogue_relu_cd<F16>(acc, 0, (int)L.n >> 6, smem_u32(bias_s), arena_hi, (uint32_t)((warp & 3) * 32), (uint32_t)lane);
           else
             epilogue_relu<X3, false, F16>(acc, (int)L.n, nullptr, smem_u32(bias_s), arena_hi, arena_lo, row);
           if (L.epi == TC_EPI_VIEW0) {
@@ -376,7 +364,7 @@ __global__ void __launch_bounds__(X3 ? 256 : 384, 1)
         if (j > 0) mbar_wait(bar_pefree + 8 * s, (uint32_t)(j - 1) & 1u);
         uint8_t* pe_hi = smem + (size_t)(s * TC_KB_PER_TILE + TC_KB_PE) * KB_BYTES;
         uint8_t* pe_lo = pe_hi + (size_t)TC_KB_PER_TILE * KB_BYTES;
-        const int tile = CS * group_of(j, s) + (int)crank;
+        const int tile = 2 * group_of(j, s) + (int)crank;
 #pragma unroll 1
         for (int h = 0; h < 2; ++h) {
           const uint32_t row = (uint32_t)(t + 64 * h);
@@ -402,7 +390,7 @@ __global__ void __launch_bounds__(X3 ? 256 : 384, 1)
 
   tcgen05_fence_before();
   __syncthreads();
-  if (MC) cluster_sync_all();  // the peer may still multicast into this CTA's ring / arrive on its barriers until it is done
+  cluster_sync_all();  // the peer may still multicast into this CTA's ring / arrive on its barriers until it is done
   tcgen05_fence_after();
   if (warp == 2) tmem_dealloc(tmem_base, 512);
 }
@@ -574,18 +562,10 @@ __global__ void render_prep_kernel(PrepNet A, PrepNet B, int W, int dim_aud, con
 
 }  // namespace tc
 
-#ifdef DFN_EXPERIMENTS
-int ts_pack_from_tc(dfn_model* m, const std::vector<uint8_t>& hi, const std::vector<uint8_t>& lo, cudaStream_t st);
-#endif
-
 void tc_free_model(dfn_model* m) {
-  cudaFree(m->ts_hi);
-  cudaFree(m->ts_lo);
-  m->ts_hi = m->ts_lo = nullptr;
   cudaFree(m->tc2_hi);
-  cudaFree(m->tc2_lo);
   cudaFree(m->tc2_h16);
-  m->tc2_hi = m->tc2_lo = m->tc2_h16 = nullptr;
+  m->tc2_hi = m->tc2_h16 = nullptr;
   cudaFree(m->tc_hi);
   cudaFree(m->tc_lo);
   cudaFree(m->tc_h16);
@@ -614,9 +594,6 @@ int tc_pack_model(dfn_model* m, const float* const* t, cudaStream_t st, TcHostDu
   const int i_views0 = d.D, i_feature = d.D + m->n_views, i_alpha = i_feature + 1, i_rgb = i_feature + 2;
 
   tc::Packer pk;
-#ifndef DFN_EXPERIMENTS
-  pk.want64 = false;   // stage images of the experimental kernel mlp_ts.cu (make EXPERIMENTS=1)
-#endif
   if (dump) pk.dense = &dump->dense;
   TcProgram& pg = m->prog;
   pg = TcProgram();
@@ -759,10 +736,6 @@ int tc_pack_model(dfn_model* m, const float* const* t, cudaStream_t st, TcHostDu
   DFN_CUDA(cudaMalloc(&m->tc2_h16, pk.h16_2.size()));
   DFN_CUDA(cudaMemcpyAsync(m->tc2_hi, pk.hi2.data(), pk.hi2.size(), cudaMemcpyHostToDevice, st));
   DFN_CUDA(cudaMemcpyAsync(m->tc2_h16, pk.h16_2.data(), pk.h16_2.size(), cudaMemcpyHostToDevice, st));
-#ifdef DFN_EXPERIMENTS
-  DFN_CUDA(cudaMalloc(&m->tc2_lo, pk.lo2.size()));
-  DFN_CUDA(cudaMemcpyAsync(m->tc2_lo, pk.lo2.data(), pk.lo2.size(), cudaMemcpyHostToDevice, st));
-#endif
   DFN_CUDA(cudaMalloc(&m->tc_hi, pk.hi32.size()));
   DFN_CUDA(cudaMalloc(&m->tc_lo, pk.lo32.size()));
   DFN_CUDA(cudaMalloc(&m->tc_h16, pk.h16.size()));
@@ -774,17 +747,13 @@ int tc_pack_model(dfn_model* m, const float* const* t, cudaStream_t st, TcHostDu
   DFN_CUDA(cudaMemcpyAsync(m->tc_bias, bias.data(), bias.size() * 4, cudaMemcpyHostToDevice, st));
   DFN_CUDA(cudaMemcpyAsync(m->tc_fold_w, fold_w.data(), fold_w.size() * 4, cudaMemcpyHostToDevice, st));
   DFN_CUDA(cudaStreamSynchronize(st));
-#ifdef DFN_EXPERIMENTS
-  return ts_pack_from_tc(m, pk.hi, pk.lo, st);
-#else
   return 0;
-#endif
 }
 
 static inline int64_t align256(int64_t x) { return (x + 255) / 256 * 256; }
 
 // debug timeline hook (dfn_debug_trace): device buffer of 2 * trace_tiles * n_layers * 8 uint64
-static int g_impl = -1;  // -1 auto: bf16 -> mlp_tc.cu (1), bf16x3 -> mlp_pp.cu (2); with EXPERIMENTS=1 also 0: mlp_ts.cu, 3: mlp_tc2.cu
+static int g_impl = -1;  // -1 auto; debug (dfn_debug_set_impl): low 4 bits 1 mlp_tc.cu, 2 mlp_pp.cu, 3 mlp_pair.cu (8: four epilogue warps per slot); high bits: pair flags + 1
 void tc_set_impl(int impl) { g_impl = impl; }
 static void* g_trace_ptr = nullptr;
 static int g_trace_tiles = 0;
@@ -841,23 +810,10 @@ int tc_prep_launch(const dfn_model* a, const dfn_model* b, int64_t R, int Nc, co
   return 0;
 }
 
-// One launch of an mlp_tc_kernel instantiation; `pair`: clusters of two CTAs (the multicast variants).
 template <class K>
-static int launch_tc(K kernel, int grid, int threads, bool pair, const tc::Params& P, cudaStream_t st) {
+static int launch_tc(K kernel, int grid, int threads, const tc::Params& P, cudaStream_t st) {
   DFN_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_TOTAL));
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3((unsigned)grid);
-  cfg.blockDim = dim3((unsigned)threads);
-  cfg.dynamicSmemBytes = tc::SMEM_TOTAL;
-  cfg.stream = st;
-  cudaLaunchAttribute at[1];
-  at[0].id = cudaLaunchAttributeClusterDimension;
-  at[0].val.clusterDim.x = pair ? 2 : 1;
-  at[0].val.clusterDim.y = 1;
-  at[0].val.clusterDim.z = 1;
-  cfg.attrs = at;
-  cfg.numAttrs = 1;
-  DFN_CUDA(cudaLaunchKernelEx(&cfg, kernel, P));
+  kernel<<<grid, threads, tc::SMEM_TOTAL, st>>>(P);
   return 0;
 }
 
@@ -934,7 +890,9 @@ int tc_query_points(const dfn_model* m, int64_t R, int S, const float* rays_o, c
   macs_pt += (double)d.W * Wh + d.W;                       // views_linears.0 (+ composed feature) and alpha
   macs_pt += (double)(m->n_views - 1) * Wh * Wh + 3.0 * Wh;  // remaining view layers and rgb
   const bool prof = profile_begin(st, macs_pt * (double)P.n_points);
-  const int impl = g_impl >= 0 ? g_impl : (precision == DFN_PREC_BF16X3 ? 2 : 1);
+  // default: bf16x3 -> mlp_pp.cu (2), bf16 / fp16 -> the CTA-pair kernel mlp_pair.cu (3)
+  const int impl = g_impl >= 0 ? (g_impl & 15) : (precision == DFN_PREC_BF16X3 ? 2 : 3);
+  pair_set_flags(g_impl >= 16 ? (g_impl >> 4) - 1 : 3);   // debug: flags + 1 in the high bits
   if (impl == 2 && (precision == DFN_PREC_BF16 || precision == DFN_PREC_BF16X3)) {
     int rc = pp_launch(m, bias_ws, vbias_ws, scratch_ws, R, S, rays_o, rays_d, z_vals, raw, precision, st);
     if (rc) return rc;
@@ -942,37 +900,14 @@ int tc_query_points(const dfn_model* m, int64_t R, int S, const float* rays_o, c
     pair_set_epilogue_warps(impl == 8 ? 4 : 8);
     int rc = pair_launch(m, bias_ws, vbias_ws, R, S, rays_o, rays_d, z_vals, raw, precision, st);
     if (rc) return rc;
-#ifdef DFN_EXPERIMENTS
-  } else if (impl == 7 && precision == DFN_PREC_BF16) {
-    int rc = tc2_launch(m, bias_ws, vbias_ws, R, S, rays_o, rays_d, z_vals, raw, precision, st);
-    if (rc) return rc;
-  } else if (impl == 0 && (precision == DFN_PREC_BF16 || precision == DFN_PREC_BF16X3)) {
-    int rc = ts_launch(m, bias_ws, vbias_ws, R, S, rays_o, rays_d, z_vals, raw, precision, st);
-    if (rc) return rc;
-#else
-  } else if (impl == 0 || impl == 7) {
-    set_error("dfn_debug_set_impl(%d): the experimental kernels (mlp_ts.cu, mlp_tc2.cu) are not in this build (make EXPERIMENTS=1)", impl);
-    return DFN_E_UNSUPPORTED;
-#endif
   } else if (precision == DFN_PREC_BF16 || precision == DFN_PREC_FP16 || precision == DFN_PREC_BF16X3) {
-    // impl 1 (default): multicast pairs, row-per-thread epilogue.  Debug variants (dfn_debug_set_impl): 4 = own weight stream per CTA,
-    // 5 = 4 + column-distributed epilogue, 6 = multicast + column-distributed epilogue.
-    const bool mc = !(impl == 4 || impl == 5), cd = (impl == 5 || impl == 6);
-    if (!mc) grid = P.n_tiles < num_sms() ? P.n_tiles : num_sms();
-    int rc = 0;
-    if (precision == DFN_PREC_BF16X3) rc = launch_tc(tc::mlp_tc_kernel<true, false, true, false>, grid, 256, true, P, st);
+    // the 1-CTA generation (impl 1): clusters of two CTAs that only share the weight stream by multicast
+    int rc;
+    if (precision == DFN_PREC_BF16X3) rc = launch_tc(tc::mlp_tc_kernel<true>, grid, 256, P, st);
     else if (precision == DFN_PREC_FP16) {
       P.w_hi = m->tc_h16;
-      rc = !mc ? (cd ? launch_tc(tc::mlp_tc_kernel<false, true, false, true>, grid, 384, false, P, st)
-                     : launch_tc(tc::mlp_tc_kernel<false, true, false, false>, grid, 384, false, P, st))
-               : (cd ? launch_tc(tc::mlp_tc_kernel<false, true, true, true>, grid, 384, true, P, st)
-                     : launch_tc(tc::mlp_tc_kernel<false, true, true, false>, grid, 384, true, P, st));
-    } else {
-      rc = !mc ? (cd ? launch_tc(tc::mlp_tc_kernel<false, false, false, true>, grid, 384, false, P, st)
-                     : launch_tc(tc::mlp_tc_kernel<false, false, false, false>, grid, 384, false, P, st))
-               : (cd ? launch_tc(tc::mlp_tc_kernel<false, false, true, true>, grid, 384, true, P, st)
-                     : launch_tc(tc::mlp_tc_kernel<false, false, true, false>, grid, 384, true, P, st));
-    }
+      rc = launch_tc(tc::mlp_tc_kernel<false, true>, grid, 384, P, st);
+    } else rc = launch_tc(tc::mlp_tc_kernel<false>, grid, 384, P, st);
     if (rc) return rc;
   } else {
     set_error("tc_query_points: precision %d is not a tensor-core mode", precision);

@@ -82,15 +82,10 @@ struct dfn_model {
   float* tc_fold_w = nullptr;   // [2][W][dim_aud] latent columns of the two folding layers
   float* tc_view_w = nullptr;   // [W/2][input_ch_views] view-direction columns of views_linears.0
   float* tc_view_b = nullptr;   // [W/2] its (composed) bias
-  // cta_group::2 kernel (mlp_tc2.cu): per K-block, per CTA of the pair, [n/2 rows x 64 K] stages
+  // cta_group::2 kernel (mlp_pair.cu): per CTA of the pair, per K-block, [n/2 rows x 64 K] stages
   uint8_t* tc2_hi = nullptr;
-  uint8_t* tc2_lo = nullptr;
   uint8_t* tc2_h16 = nullptr;   // fp16 images, same offsets
   uint32_t tc2_woff[dfn::TC_MAX_LAYERS] = {};
-  // TMEM-activation kernel (mlp_ts.cu): the same stage images in half-major order
-  uint8_t* ts_hi = nullptr;
-  uint8_t* ts_lo = nullptr;
-  uint32_t ts_woff[dfn::TC_MAX_LAYERS] = {};
 };
 
 namespace dfn {
@@ -100,7 +95,7 @@ int mlp_fp32_forward(const dfn_model* m, int64_t P, const float* x, float* out, 
 
 void tc_set_trace(void* dev_ptr, int tiles);
 void tc_get_trace(void** dev_ptr, int* tiles);
-void tc_set_impl(int impl);  // 2: ping-pong + cooperative epilogue (mlp_pp.cu, default); 1: mlp_tc.cu; 0: mlp_ts.cu
+void tc_set_impl(int impl);  // debug: 1 mlp_tc.cu, 2 mlp_pp.cu, 3 mlp_pair.cu (see tc_query_points)
 int64_t pp_scratch_bytes();
 int64_t pp_dec_scratch_bytes();
 int pp_launch_prog(const TcProgram& prog, const uint32_t* woff32, const uint8_t* w_hi, const uint8_t* w_lo, const float* dot_w, bool decoder,
@@ -113,10 +108,7 @@ int pp_launch(const dfn_model* m, const float* bias_ws, const float* vbias_ws, v
 int pair_launch(const dfn_model* m, const float* bias_ws, const float* vbias_ws, int64_t R, int S, const float* rays_o,
                 const float* rays_d, const float* z_vals, float* raw, int precision, cudaStream_t st);
 void pair_set_epilogue_warps(int ew);
-int tc2_launch(const dfn_model* m, const float* bias_ws, const float* vbias_ws, int64_t R, int S, const float* rays_o,
-               const float* rays_d, const float* z_vals, float* raw, int precision, cudaStream_t st);
-int ts_launch(const dfn_model* m, const float* bias_ws, const float* vbias_ws, int64_t R, int S, const float* rays_o,
-              const float* rays_d, const float* z_vals, float* raw, int precision, cudaStream_t st);
+void pair_set_flags(int flags);
 struct TcHostDump {   // host-only view of a packed model (dfn_model_program_host)
   std::vector<float> dense;    // [layer][256][6][64]
   std::vector<float> bias;     // [TC_MAX_LAYERS][256]

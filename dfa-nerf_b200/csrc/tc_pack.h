@@ -26,10 +26,9 @@ static inline float bf2f(uint16_t h) {
 }
 
 struct Packer {
-  std::vector<uint8_t> hi, lo;       // [<=128 rows x 64 K] stages, 128-byte swizzle (mlp_ts.cu)
   std::vector<uint8_t> hi32, lo32;   // [n rows x 32 K] stages, 64-byte swizzle (mlp_tc.cu)
   std::vector<uint8_t> h16;          // the hi32 images with fp16 instead of bf16 values (DFN_PREC_FP16), same offsets
-  std::vector<uint8_t> hi2, lo2;     // [n/2 rows x 64 K] per CTA of a pair, 128-byte swizzle (mlp_pair.cu; lo2: experiments only)
+  std::vector<uint8_t> hi2;          // [n/2 rows x 64 K] per CTA of a pair, 128-byte swizzle (mlp_pair.cu)
   std::vector<uint8_t> h16_2;        // the hi2 images with fp16 values (DFN_PREC_FP16), same offsets
   uint32_t last32 = 0;               // offset of the last layer added to hi32
   uint32_t last2 = 0;                // offset of the last layer added to hi2
@@ -38,13 +37,12 @@ struct Packer {
   static constexpr size_t kDenseLayer = (size_t)256 * 6 * 64;
   std::vector<float>* dense = nullptr;
   int n_dense = 0;
-  bool want64 = true;                // also build the 128-byte-swizzle images (only mlp_ts.cu reads them)
   // Appends the stages of one layer: for each K-block, for each chunk of <=128 output rows, a
   // [rows x 64] bf16 image in the swizzled K-major layout.  wfun(n, kbi, k) returns W[n][column
   // of K-block kbi, position k] or 0.
   template <class F>
   uint32_t add_layer(int n_out, int nkb, F wfun) {
-    const uint32_t start = (uint32_t)hi.size();
+    const uint32_t start = (uint32_t)hi32.size();
     if (dense) {
       dense->resize((size_t)(n_dense + 1) * kDenseLayer, 0.f);
       float* d = dense->data() + (size_t)n_dense * kDenseLayer;
@@ -52,24 +50,6 @@ struct Packer {
         for (int kbi = 0; kbi < nkb; ++kbi)
           for (int k = 0; k < 64; ++k) d[((size_t)r * 6 + kbi) * 64 + k] = wfun(r, kbi, k);
       ++n_dense;
-    }
-    for (int kbi = 0; want64 && kbi < nkb; ++kbi) {
-      for (int c0 = 0; c0 < n_out; c0 += 128) {
-        const int rows = n_out - c0 < 128 ? n_out - c0 : 128;
-        const size_t base = hi.size();
-        hi.resize(base + (size_t)rows * 128, 0);
-        lo.resize(base + (size_t)rows * 128, 0);
-        for (int r = 0; r < rows; ++r) {
-          for (int k = 0; k < 64; ++k) {
-            const float w = wfun(c0 + r, kbi, k);
-            const uint16_t h = f2bf(w);
-            const uint16_t l = f2bf(w - bf2f(h));
-            const size_t o = base + (size_t)r * 128 + ((((size_t)k >> 3) ^ ((size_t)r & 7)) << 4) + ((size_t)k & 7) * 2;
-            memcpy(&hi[o], &h, 2);
-            memcpy(&lo[o], &l, 2);
-          }
-        }
-      }
     }
     // K = 32 stages: for each K-block, for each half of it, all n_out rows x 32 K; 64-byte rows, 16-byte
     // chunk index XORed with (row >> 1) & 3 (cute Swizzle<2,4,3>), 8-row groups 512 bytes apart.
@@ -94,25 +74,23 @@ struct Packer {
         }
       }
     }
-    // cta_group::2 stages: for each K-block, for each CTA rank of the pair, rows [rank*n/2, (rank+1)*n/2) x 64 K in the
-    // 128-byte-swizzled K-major layout (the pair's MMA takes half of B's N rows from each CTA's shared memory).
+    // cta_group::2 stages (mlp_pair.cu): for each CTA rank of the pair, for each K-block, rows [rank*n/2, (rank+1)*n/2) x 64 K in the
+    // 128-byte-swizzled K-major layout (the pair's MMA takes half of B's N rows from each CTA's shared memory).  Rank-major, so that a
+    // CTA's halves of consecutive K-blocks are contiguous: one bulk copy fills a ring entry of two K-blocks.
     last2 = (uint32_t)hi2.size();
     if (want2 && n_out % 16 == 0) {
       const int half = n_out / 2;
-      for (int kbi = 0; kbi < nkb; ++kbi) {
-        for (int rank = 0; rank < 2; ++rank) {
+      for (int rank = 0; rank < 2; ++rank) {
+        for (int kbi = 0; kbi < nkb; ++kbi) {
           const size_t base = hi2.size();
           hi2.resize(base + (size_t)half * 128, 0);
-          lo2.resize(base + (size_t)half * 128, 0);
           h16_2.resize(base + (size_t)half * 128, 0);
           for (int r = 0; r < half; ++r) {
             for (int k = 0; k < 64; ++k) {
               const float w = wfun(rank * half + r, kbi, k);
               const uint16_t h = f2bf(w);
-              const uint16_t l = f2bf(w - bf2f(h));
               const size_t o = base + (size_t)r * 128 + ((((size_t)k >> 3) ^ ((size_t)r & 7)) << 4) + ((size_t)k & 7) * 2;
               memcpy(&hi2[o], &h, 2);
-              memcpy(&lo2[o], &l, 2);
               const __half hh = __float2half_rn(w);
               memcpy(&h16_2[o], &hh, 2);
             }

@@ -26,7 +26,7 @@ for mode, prec in (('bf16', dfn.PREC_BF16), ('bf16x3', dfn.PREC_BF16X3)):
     eng = dfn.RenderEngine(net, None, S, 0, precision=prec)
     outs = {}
     for impl in impls:
-        if impl >= 3 and mode != 'bf16':
+        if (impl & 15) >= 3 and mode != 'bf16':
             continue
         dfn.lib.dfn_debug_set_impl(impl)
         for _ in range(2):
@@ -42,7 +42,7 @@ for mode, prec in (('bf16', dfn.PREC_BF16), ('bf16x3', dfn.PREC_BF16X3)):
         msg = ''
         if impls[0] in outs and impl != impls[0]:
             d = (outs[impl] - outs[impls[0]]).abs()
-            msg = '  max|diff vs %s| rgb %.3e sigma %.3e finite=%s' % (NAMES[impls[0]], d[..., :3].max().item(), d[..., 3].max().item(),
+            msg = '  max|diff vs %s| rgb %.3e sigma %.3e finite=%s' % (NAMES.get(impls[0], str(impls[0])), d[..., :3].max().item(), d[..., 3].max().item(),
                                                                       bool(torch.isfinite(outs[impl]).all()))
-        print('%s impl=%s: %.3f ms -> %.1f TFLOP/s%s' % (mode, NAMES[impl], ms, 2 * 557184 * R * S / ms / 1e9, msg), flush=True)
+        print('%s impl=%s: %.3f ms -> %.1f TFLOP/s%s' % (mode, NAMES.get(impl, 'impl%d+flags%d' % (impl & 15, impl >> 4)), ms, 2 * 557184 * R * S / ms / 1e9, msg), flush=True)
 dfn.lib.dfn_debug_set_impl(-1)

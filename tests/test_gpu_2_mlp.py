@@ -242,37 +242,58 @@ def test_tc_matches_fp32_kernel_at_scale(dfn):
 
 
 def test_kernel_variants_agree(dfn):
-    """The two tcgen05 kernel generations of the product build (dfn_debug_set_impl: 1 = mlp_tc.cu, 2 = mlp_pp.cu) compute
-    the same function: bit-identical in bf16 (same operands, same K order); in bf16x3 the hi/lo products are accumulated
-    in a different order, so they agree to the operand precision.  The experimental generations (0 = TMEM activations,
-    3 = CTA pairs) are only in `make EXPERIMENTS=1` builds and are compared when present."""
-    R, S = 700, 192
-    ro, rd, vd, z, aud = _query_case(R, S, seed=9)
+    """The tcgen05 kernel generations (dfn_debug_set_impl: 1 = mlp_tc.cu, one CTA per tile pair of slots; 2 = mlp_pp.cu, the layer-program
+    interpreter; 3 = mlp_pair.cu, cta_group::2 CTA pairs -- the default of the single-pass precisions; 8 = the same with four epilogue warps
+    per slot; 3 + 16 (f + 1): pair kernel with flag set f, 0 = every slot streams its own weights and cluster-scope releases) compute the
+    same function: bit-identical in bf16 and fp16 (same operands, same fp32 bias add and rounding); in bf16x3 the hi/lo products are
+    accumulated in a different order, so the two generations agree to the operand precision.  Sizes: a ragged tail, fewer tiles than
+    SMs, an odd tile count, and several tiles per CTA."""
     net = face(dfn, 1)
-    args = [t.to(DEV) for t in (ro, rd, vd, z, aud)]
     try:
-        for prec in (dfn.PREC_BF16, dfn.PREC_BF16X3):
-            eng = dfn.RenderEngine(net, None, S, 0, precision=prec)
-            outs = {}
-            for impl in (1, 2, 0, 3):
-                if impl == 3 and prec != dfn.PREC_BF16:
-                    continue
-                dfn.lib.dfn_debug_set_impl(impl)
-                try:
+        for R, S in ((700, 192), (1, 64), (37, 64), (5000, 64)):
+            ro, rd, vd, z, aud = _query_case(R, S, seed=9)
+            args = [t.to(DEV) for t in (ro, rd, vd, z, aud)]
+            for prec in (dfn.PREC_BF16, dfn.PREC_FP16, dfn.PREC_BF16X3):
+                eng = dfn.RenderEngine(net, None, S, 0, precision=prec)
+                outs = {}
+                impls = (1, 2) if prec == dfn.PREC_BF16X3 else ((1, 2, 3, 8, 3 + 16, 3 + 32, 3 + 48) if prec == dfn.PREC_BF16 else (1, 3, 8))
+                for impl in impls:
+                    dfn.lib.dfn_debug_set_impl(impl)
                     outs[impl] = eng.query_points(net, *args).clone()
-                except dfn.DfnError as ex:
-                    assert impl in (0, 3) and 'EXPERIMENTS' in str(ex)
-                    continue
-                assert torch.isfinite(outs[impl]).all()
-            if prec == dfn.PREC_BF16:
-                for impl in outs:
-                    assert torch.equal(outs[impl], outs[1]), impl
-            else:
-                for impl in outs:
-                    assert maxerr(outs[impl], outs[1]) < 2e-3, impl      # x3: K-half order differs
-            wa = dfn.calc_volume_weights(args[3], args[1], outs[1][..., 3].contiguous())
-            wb = dfn.calc_volume_weights(args[3], args[1], outs[2][..., 3].contiguous())
-            tol = 1e-4 if prec == dfn.PREC_BF16X3 else 5e-2
-            assert maxerr(wa, wb) < tol
+                    assert torch.isfinite(outs[impl]).all()
+                dfn.lib.dfn_debug_set_impl(-1)
+                outs[-1] = eng.query_points(net, *args).clone()
+                if prec != dfn.PREC_BF16X3:
+                    for impl in outs:
+                        assert torch.equal(outs[impl], outs[1]), (R, S, prec, impl)
+                else:
+                    for impl in outs:
+                        assert maxerr(outs[impl], outs[1]) < 2e-3, impl      # x3: K-half order differs
+                    wa = dfn.calc_volume_weights(args[3], args[1], outs[1][..., 3].contiguous())
+                    wb = dfn.calc_volume_weights(args[3], args[1], outs[2][..., 3].contiguous())
+                    assert maxerr(wa, wb) < 1e-4
+    finally:
+        dfn.lib.dfn_debug_set_impl(-1)
+
+
+def test_pair_kernel_stress_bit_identical(dfn):
+    """The CTA-pair kernel against the 1-CTA generation on a full 450 x 450 x 192 query (405,000 tiles, 4.9 M tile-layers), bit for bit:
+    the peer CTA's `aready` arrivals carry a CTA-scope release (mlp_pair.cu), so a mis-ordered handshake would show up here as a stale
+    activation block."""
+    R, S = 202500, 192
+    net = face(dfn, 2)
+    fr = synth.frame_inputs(H=450, W=450, seed=3)
+    ro, rd, vd = dfn.get_rays(450, 450, fr['focal'], fr['c2w'], fr['cx'], fr['cy'], device=DEV, return_viewdirs=True)
+    ro, rd, vd = [t.reshape(-1, 3).contiguous() for t in (ro, rd, vd)]
+    z, _ = torch.sort(torch.rand(R, S, device=DEV) * 0.6 + 0.4, -1)
+    aud = fr['aud'].to(DEV)
+    eng = dfn.RenderEngine(net, None, S, 0, precision=dfn.PREC_BF16)
+    try:
+        dfn.lib.dfn_debug_set_impl(1)
+        ref = eng.query_points(net, ro, rd, vd, z, aud).clone()
+        dfn.lib.dfn_debug_set_impl(-1)
+        for rep in range(3):
+            out = eng.query_points(net, ro, rd, vd, z, aud)
+            assert torch.equal(out, ref), rep
     finally:
         dfn.lib.dfn_debug_set_impl(-1)
