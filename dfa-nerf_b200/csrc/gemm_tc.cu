@@ -229,6 +229,97 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const __grid_consta
   if (warp == 12) tmem_dealloc(tmem_base, 256);
 }
 
+
+// ---- DFN_PREC_FP32: the same contract on the CUDA cores (FFMA, round-to-nearest fp32 accumulation) ----
+// The tensor core's fp32 accumulator truncates (measured: ~3e-8 of the running sum per accumulating MMA, biased -- splitting the
+// operands into three bf16 pieces and issuing six products instead of three only moved the GEMM error from 4.7e-6 to 2.2e-6), and the
+// backward pass of the deformation path is ill-conditioned: its gradient sums over the batch cancel to ~1e-3 of their terms, so a GEMM
+// error of 4e-6 becomes 5e-3 on a dozen of the 74 gradient tensors (profiles/diag_train_precision.py; with exact GEMMs the same tape
+// agrees with autograd to 3e-6 on all of them).  This kernel is the reference-exact mode of the training step, as the FFMA kernels of
+// mlp_fp32.cu are for rendering: 64 x 64 output tile per CTA, 16-wide K steps through shared memory, 4 x 4 outputs per thread.
+static constexpr int FM = 64, FN = 64, FK = 16;
+
+// Acc = double: the per-frame vector products (M = 1 matrix-vector products, K = 1 outer products: at most 2^20 MACs) in EVERY precision.
+// Their results (fc_z(z_shape), the signal encoders' outputs, ...) enter all points of the batch as biases, so their rounding error is
+// coherent over the batch: 5e-7 there moved the first torso layer's bias-like gradients, sums that cancel to ~1e-4 of their terms, by 5e-3.
+template <typename Acc>
+__global__ void __launch_bounds__(256) gemm_fp32_kernel(const __grid_constant__ Params P) {
+  __shared__ float As[FK][FM + 1];
+  __shared__ float Bs[FK][FN + 1];
+  const dfn_gemm_desc& d = P.d;
+  const int n_tiles = (d.N + FN - 1) / FN;
+  const int tile = (int)blockIdx.x % (P.m_tiles * n_tiles), ks = (int)blockIdx.x / (P.m_tiles * n_tiles);
+  const int64_t m0 = (int64_t)(tile / n_tiles) * FM;
+  const int n0 = (tile % n_tiles) * FN;
+  const int k_begin = ks * P.per_split * FK, k_end = min(d.K, (ks + 1) * P.per_split * FK);
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  Acc acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = (Acc)0;
+  for (int k0 = k_begin; k0 < k_end; k0 += FK) {
+    // A tile [64 x 16] and B tile [64 x 16]: 1,024 elements each, four per thread; the index split follows the unit stride
+    for (int e = threadIdx.x; e < FM * FK; e += 256) {
+      int r, k;
+      if (d.a_ld_k == 1) { r = e / FK; k = e % FK; } else { r = e % FM; k = e / FM; }
+      const int64_t m = m0 + r;
+      float v = 0.f;
+      if (m < d.M && k0 + k < k_end) {
+        const int64_t off = m * d.a_ld_r + (int64_t)(k0 + k) * d.a_ld_k;
+        v = d.A[off];
+        if (d.A_mask != nullptr) v *= mask_factor(d.a_mask_mode, d.A_mask[off]);
+      }
+      As[k][r] = v;
+    }
+    for (int e = threadIdx.x; e < FN * FK; e += 256) {
+      int r, k;
+      if (d.b_ld_k == 1) { r = e / FK; k = e % FK; } else { r = e % FN; k = e / FN; }
+      const int n = n0 + r;
+      Bs[k][r] = (n < d.N && k0 + k < k_end) ? d.B[(int64_t)n * d.b_ld_r + (int64_t)(k0 + k) * d.b_ld_k] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < FK; ++k) {
+      float a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = As[k][ty * 4 + i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b[j] = Bs[k][tx * 4 + j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fma((Acc)a[i], (Acc)b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+  const bool atomic = d.k_splits > 1;
+  const int act = d.act & 3;
+  const bool pre_add = (d.act & 4) != 0;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int64_t m = m0 + ty * 4 + i;
+    if (m >= d.M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tx * 4 + j;
+      if (n >= d.N) continue;
+      Acc xa = acc[i][j];
+      if (d.bias != nullptr && ks == 0) xa += (Acc)d.bias[n];
+      const float add = d.addend != nullptr && ks == 0 ? d.addend[m * d.add_ld_r + (int64_t)n * d.add_ld_c] : 0.f;
+      if (pre_add) xa += (Acc)add;
+      float x = (float)xa;
+      if (act == 1) x = fmaxf(x, 0.f);
+      else if (act == 2) x = __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-x)));
+      else if (act == 3) x = x > 0.f ? x : __fmul_rn(0.02f, x);
+      if (!pre_add) x += add;
+      float* dst = d.C + m * d.c_ld_r + (int64_t)n * d.c_ld_c;
+      if (atomic) atomicAdd(dst, x);
+      else *dst = d.beta ? *dst + x : x;
+    }
+  }
+}
+
 }  // namespace gemm
 }  // namespace dfn
 
@@ -237,7 +328,8 @@ using namespace dfn;
 extern "C" int dfn_gemm(const dfn_gemm_desc* d, void* stream) {
   DFN_CHECK_ARG(d && d->A && d->B && d->C && d->M > 0 && d->N > 0 && d->K > 0, "dfn_gemm: null operand or empty shape");
   DFN_CHECK_ARG(d->N <= gemm::BN_MAX, "dfn_gemm: N = %d > %d output columns per call", d->N, gemm::BN_MAX);
-  DFN_CHECK_ARG(d->precision == DFN_PREC_BF16X3 || d->precision == DFN_PREC_BF16, "dfn_gemm: precision must be BF16X3 or BF16");
+  DFN_CHECK_ARG(d->precision == DFN_PREC_BF16X3 || d->precision == DFN_PREC_BF16 || d->precision == DFN_PREC_FP32,
+                "dfn_gemm: precision must be FP32, BF16X3 or BF16");
   DFN_CHECK_ARG(d->act >= 0 && d->act <= 7 && d->a_mask_mode >= 0 && d->a_mask_mode <= 3, "dfn_gemm: bad act / mask mode");
   DFN_CHECK_ARG(d->A_mask == nullptr || d->a_mask_mode != 0, "dfn_gemm: A_mask given without a mask mode");
   gemm::Params P;
@@ -245,8 +337,10 @@ extern "C" int dfn_gemm(const dfn_gemm_desc* d, void* stream) {
   P.d = *d;
   if (P.d.A_mask == nullptr) P.d.a_mask_mode = 0;
   P.n_pad = (d->N + 15) / 16 * 16;
-  P.m_tiles = (d->M + gemm::BM - 1) / gemm::BM;
-  P.chunks = (d->K + gemm::BK - 1) / gemm::BK;
+  const bool vec = (double)d->M * (double)d->N * (double)d->K <= 1048576.0;    // per-frame vector products: CUDA cores, fp64 accumulation
+  const bool fp32 = d->precision == DFN_PREC_FP32 || vec;
+  P.m_tiles = fp32 ? (d->M + gemm::FM - 1) / gemm::FM : (d->M + gemm::BM - 1) / gemm::BM;
+  P.chunks = fp32 ? (d->K + gemm::FK - 1) / gemm::FK : (d->K + gemm::BK - 1) / gemm::BK;
   int splits = d->k_splits < 1 ? 1 : d->k_splits;
   if (splits > P.chunks) splits = P.chunks;
   P.per_split = (P.chunks + splits - 1) / splits;
@@ -255,11 +349,15 @@ extern "C" int dfn_gemm(const dfn_gemm_desc* d, void* stream) {
   DFN_CHECK_ARG(splits == 1 || ((d->act & 3) == 0 && d->beta == 1),
                 "dfn_gemm: a split-K call accumulates into C with atomics: it needs act = 0 and beta = 1 (C zeroed or running)");
   cudaStream_t st = (cudaStream_t)stream;
-  const int64_t grid = (int64_t)P.m_tiles * splits;
+  const int64_t grid = (int64_t)P.m_tiles * splits * (fp32 ? (d->N + gemm::FN - 1) / gemm::FN : 1);
   DFN_CHECK_ARG(grid < (1ll << 31), "dfn_gemm: grid too large");
   static bool attr_done[2] = {false, false};
   const bool prof = profile_begin(st, (double)d->M * (double)d->N * (double)d->K);
-  if (d->precision == DFN_PREC_BF16X3) {
+  if (vec) {
+    gemm::gemm_fp32_kernel<double><<<(int)grid, 256, 0, st>>>(P);
+  } else if (fp32) {
+    gemm::gemm_fp32_kernel<float><<<(int)grid, 256, 0, st>>>(P);
+  } else if (d->precision == DFN_PREC_BF16X3) {
     if (!attr_done[0]) {
       DFN_CUDA(cudaFuncSetAttribute(gemm::gemm_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm::SMEM_TOTAL));
       attr_done[0] = true;

