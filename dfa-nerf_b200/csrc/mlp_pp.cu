@@ -518,6 +518,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1) mlp_pp_kerne
             epilogue_chunk_dot1<F16>(v1, cc + 1, sbias, sdot, arena_hi, row, d4);
           }
           alpha = (d4[0] + d4[1]) + (d4[2] + d4[3]) + P.dot_w[TC_BIAS_STRIDE];
+        } else if (!X3 && L.epi == TC_EPI_RELU && (L.n & 63) == 0) {
+          // column-distributed readout (tc_epi.cuh): the bias in registers instead of warp-broadcast loads
+          epilogue_relu_cd<F16>(acc, 0, (int)L.n >> 6, sbias, arena_hi, (uint32_t)(q * 32), (uint32_t)(threadIdx.x & 31));
         } else {
           const bool per_ray = L.epi == TC_EPI_VIEW0;
           const int nch = (per_ray ? P.view_w : (int)L.n) >> 5;   // 32-column chunks: 8 or 4
