@@ -251,7 +251,7 @@ class Job:
         self.b, self.e, _ = shard_range(self.n_rays, rank, world)
         self.launches = 0
         self.frames = args.frames
-        tc_name = 'mlp_pp_kernel<bf16x3>' if prec == dfn.PREC_BF16X3 else 'mlp_tc_kernel<%s>' % precision
+        tc_name = 'mlp_pp_kernel<bf16x3>' if prec == dfn.PREC_BF16X3 else 'mlp_pair_kernel<%s>' % precision
         self.flops_note = 'algorithmic, latent/viewdir columns folded: 2*557,184 per MLP evaluation (BASELINE.md section 2)'
 
         def mk(seed):

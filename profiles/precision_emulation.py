@@ -157,6 +157,22 @@ def main():
         'bf16x3 on trunk, fp16 single on view layers': lambda name: s_x3(BF) if trunk(name) else s_single(H16),
         'bf16 + fp8 corrections (bf16 hi)': lambda name: s_f16_f8(hi=BF, a8_scale=1., wl_scale=2. ** 6),
     }
+    if sys.argv[1:2] == ['--sweep']:
+        # per-layer sensitivity: ONE layer in a cheaper scheme, all others split in three; then cumulative prefixes
+        names = ['pts_linears.%d' % i for i in range(8)] + ['alpha_linear', 'views_linears.0', 'views_linears.1', 'views_linears.2', 'rgb_linear']
+        base, cheap = s_x3(H16), {'fp16': s_single(H16), 'fp16 w-split': s_x2w(H16), 'fp16 a-split': s_x2a(H16)}
+        schemes = {'fp16x3 everywhere': lambda name: base}
+        for cn, cs in cheap.items():
+            for nm in names:
+                schemes['%s on %s only' % (cn, nm)] = (lambda name, nm=nm, cs=cs: cs if name == nm else base)
+        view = ('views_linears.0', 'views_linears.1', 'views_linears.2', 'rgb_linear')
+        for k in range(0, 9):
+            single = set(names[:k]) | set(view)
+            schemes['fp16 single on the view layers + pts_linears.0..%d, x3 on the rest' % (k - 1)] = (lambda name, single=single: s_single(H16) if name in single else base)
+        for k in range(0, 9):
+            single = set(names[:k]) | set(view)
+            schemes['fp16 w-split on the view layers + pts_linears.0..%d, x3 on the rest' % (k - 1)] = (lambda name, single=single: s_x2w(H16) if name in single else base)
+        sys.argv = sys.argv[:1]
     only = sys.argv[1:]
     for label, pick in schemes.items():
         if only and not any(o in label for o in only):
