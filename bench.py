@@ -42,7 +42,7 @@ sys.path.insert(0, ROOT)
 METRIC = 'rendered rays/sec at 450x450x(64+128) samples; 1/2/4/8 B200 vs CPU ref'
 H = W = 450
 N_SAMPLES, N_IMPORTANCE = 64, 128
-PRECISIONS = ('bf16', 'fp16', 'bf16x3', 'fp32')
+PRECISIONS = ('bf16', 'fp16', 'bf16x3', 'fp16x3m', 'fp32')
 
 
 def peaks():
@@ -242,7 +242,7 @@ class Job:
         import synth                       # seeded synthetic data (repo root; nothing under oracle/ is touched on this path)
         self.workload, self.precision, self.ctx, self.dfn, self.torch = workload, precision, ctx, dfn, torch
         dev, rank, world = ctx['dev'], ctx['rank'], ctx['world']
-        self.prec = {'bf16': dfn.PREC_BF16, 'fp16': dfn.PREC_FP16, 'bf16x3': dfn.PREC_BF16X3, 'fp32': dfn.PREC_FP32}[precision]
+        self.prec = {'bf16': dfn.PREC_BF16, 'fp16': dfn.PREC_FP16, 'bf16x3': dfn.PREC_BF16X3, 'fp16x3m': dfn.PREC_FP16X3M, 'fp32': dfn.PREC_FP32}[precision]
         prec = self.prec
         hw = 64 if workload == 'coarse64' else H
         self.hw = hw
@@ -251,7 +251,7 @@ class Job:
         self.b, self.e, _ = shard_range(self.n_rays, rank, world)
         self.launches = 0
         self.frames = args.frames
-        tc_name = 'mlp_pp_kernel<bf16x3>' if prec == dfn.PREC_BF16X3 else 'mlp_pair_kernel<%s>' % precision
+        tc_name = ('mlp_pp_kernel<%s>' % precision) if prec in (dfn.PREC_BF16X3, dfn.PREC_FP16X3M) else 'mlp_pair_kernel<%s>' % precision
         self.flops_note = 'algorithmic, latent/viewdir columns folded: 2*557,184 per MLP evaluation (BASELINE.md section 2)'
 
         def mk(seed):
@@ -527,7 +527,7 @@ def parity_leg(ctx, cpu, workload, precisions):
     near, far = torch.full((e - b,), fr['near'], device=dev), torch.full((e - b,), fr['far'], device=dev)
     bc, aud = fr['bc_rgb'][b:e].to(dev), fr['aud'].to(dev)
     for name in precisions:
-        prec = {'bf16': dfn.PREC_BF16, 'fp16': dfn.PREC_FP16, 'bf16x3': dfn.PREC_BF16X3, 'fp32': dfn.PREC_FP32}[name]
+        prec = {'bf16': dfn.PREC_BF16, 'fp16': dfn.PREC_FP16, 'bf16x3': dfn.PREC_BF16X3, 'fp16x3m': dfn.PREC_FP16X3M, 'fp32': dfn.PREC_FP32}[name]
         eng = dfn.RenderEngine(nc, nf, N_SAMPLES, N_IMPORTANCE, precision=prec)
         tf = eng.render_rays(ro, rd, vd, near, far, bc, aud, z_samples=ref['z_samples'].to(dev), want=('rgb_map', 'rgb0'))
         free = eng.render_rays(ro, rd, vd, near, far, bc, aud, want=('rgb_map',))
@@ -582,7 +582,7 @@ def main():
     extras = not args.no_extras
     modes, extra = {}, {}
     if extras and args.workload in ('facenerf', 'head_torso'):
-        for name in ('bf16', 'fp16', 'bf16x3'):
+        for name in ('bf16', 'fp16', 'bf16x3') + (('fp16x3m',) if args.workload == 'facenerf' else ()):
             if name == args.precision:
                 continue
             r = measure(ctx, Job(args.workload, name, args, ctx), max(3, min(args.steps, 5)), 3)
@@ -617,7 +617,7 @@ def main():
                'sample': '%d rays (chunks of 2048, image centre) x %s network evaluations per ray, median of 3 (%.1f s each)'
                          % (c['rays'], EVALS[args.workload], c['sec'])}
         if extras and args.workload in ('facenerf', 'head_torso'):
-            parity = parity_leg(ctx, c, args.workload, [p for p in ('bf16', 'fp16', 'bf16x3')])
+            parity = parity_leg(ctx, c, args.workload, [p for p in ('bf16', 'fp16', 'bf16x3') + (('fp16x3m',) if args.workload == 'facenerf' else ())])
             parity['precision'] = args.precision
             if args.workload == 'facenerf':
                 parity['teacher_forced_max_abs_rgb'] = parity[args.precision]['teacher_forced_max_abs_rgb'] \
@@ -631,7 +631,8 @@ def main():
         print(json.dumps({
             'metric': METRIC, 'value': main_res['value'], 'unit': 'rays/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
             'ms_per_step': main_res['ms_per_step'], 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None,
-            'dtype': {'bf16': 'bf16', 'fp16': 'fp16', 'bf16x3': 'bf16x3 (split bf16, fp32-parity)', 'fp32': 'f32'}[args.precision],
+            'dtype': {'bf16': 'bf16', 'fp16': 'fp16', 'bf16x3': 'bf16x3 (split bf16, fp32-parity)',
+                      'fp16x3m': 'fp16x3m (fp16, split on the density layers: fp32-parity)', 'fp32': 'f32'}[args.precision],
             'data': 'synthetic',
             'config': {'workload': WORKLOADS[args.workload],
                        'rays_per_step': job.n_rays, 'mlp_evals_per_ray': job.evals_per_ray, 'precision': args.precision,

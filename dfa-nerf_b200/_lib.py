@@ -8,7 +8,7 @@ import os
 
 import torch
 
-PREC_FP32, PREC_BF16, PREC_FP16, PREC_BF16X3 = 0, 1, 2, 3
+PREC_FP32, PREC_BF16, PREC_FP16, PREC_BF16X3, PREC_FP16X3M = 0, 1, 2, 3, 4
 MODEL_FACENERF, MODEL_NERF = 0, 1
 
 _HERE = os.path.dirname(os.path.abspath(__file__))

@@ -333,7 +333,7 @@ static int query_points_impl(const dfn_model* m, int64_t R, int S, const float* 
                 m->desc.dim_aud);
   if (precision == DFN_PREC_FP32)
     return fp32_query_points(m, R, S, rays_o, rays_d, viewdirs, z_vals, latent, raw, workspace, workspace_bytes, st);
-  if (precision != DFN_PREC_BF16 && precision != DFN_PREC_BF16X3 && precision != DFN_PREC_FP16) {
+  if (precision != DFN_PREC_BF16 && precision != DFN_PREC_BF16X3 && precision != DFN_PREC_FP16 && precision != DFN_PREC_FP16X3M) {
     set_error("dfn_query_points: unknown precision %d", precision);
     return DFN_E_ARG;
   }

@@ -92,9 +92,14 @@ __device__ __forceinline__ int layer_phases(const TcLayer& L, int view_w) {
   if (L.epi == TC_EPI_VIEW0) return view_w >> 6;
   return 1;
 }
+// operand passes of a layer's weights through the ring: hi and lo stages in the split modes, unless the layer is single-pass
+template <int NPART>
+__device__ __forceinline__ int layer_parts(const TcLayer& L) {
+  return (NPART == 2 && (L.flags & TC_F_SINGLE)) ? 1 : NPART;
+}
 template <int NPART>
 __device__ __forceinline__ uint32_t layer_entries(const TcLayer& L) {
-  return (uint32_t)L.nkb * NPART + (layer_has_pe(L) ? 1u : 0u);
+  return (uint32_t)L.nkb * (uint32_t)layer_parts<NPART>(L) + (layer_has_pe(L) ? 1u : 0u);
 }
 
 // One 64-column row of a staged block -> scratch, bf16 / fp16 (hi [, lo = bf16(v - hi)]) in the [16-byte chunk][row]
@@ -119,10 +124,10 @@ __device__ __forceinline__ void scratch_row(uint8_t* blk_base, uint32_t row, con
     dst[ch * TILE_M] = h;
     if (X3) {
       uint4 l;
-      l.x = pack_bf16(v[ch * 8 + 0] - bf16_lo_f(h.x), v[ch * 8 + 1] - bf16_hi_f(h.x));
-      l.y = pack_bf16(v[ch * 8 + 2] - bf16_lo_f(h.y), v[ch * 8 + 3] - bf16_hi_f(h.y));
-      l.z = pack_bf16(v[ch * 8 + 4] - bf16_lo_f(h.z), v[ch * 8 + 5] - bf16_hi_f(h.z));
-      l.w = pack_bf16(v[ch * 8 + 6] - bf16_lo_f(h.w), v[ch * 8 + 7] - bf16_hi_f(h.w));
+      l.x = pack_lo<F16>(v[ch * 8 + 0], v[ch * 8 + 1], h.x);
+      l.y = pack_lo<F16>(v[ch * 8 + 2], v[ch * 8 + 3], h.y);
+      l.z = pack_lo<F16>(v[ch * 8 + 4], v[ch * 8 + 5], h.z);
+      l.w = pack_lo<F16>(v[ch * 8 + 6], v[ch * 8 + 7], h.w);
       dst[(8 + ch) * TILE_M] = l;
     }
   }
@@ -156,10 +161,10 @@ __device__ __forceinline__ void stage_chunk(const uint32_t (&v)[32], int chunk32
     dst[c16 * TILE_M] = h;
     if (X3) {
       uint4 l;
-      l.x = pack_bf16(o[0] - bf16_lo_f(h.x), o[1] - bf16_hi_f(h.x));
-      l.y = pack_bf16(o[2] - bf16_lo_f(h.y), o[3] - bf16_hi_f(h.y));
-      l.z = pack_bf16(o[4] - bf16_lo_f(h.z), o[5] - bf16_hi_f(h.z));
-      l.w = pack_bf16(o[6] - bf16_lo_f(h.w), o[7] - bf16_hi_f(h.w));
+      l.x = pack_lo<F16>(o[0], o[1], h.x);
+      l.y = pack_lo<F16>(o[2], o[3], h.y);
+      l.z = pack_lo<F16>(o[4], o[5], h.z);
+      l.w = pack_lo<F16>(o[6], o[7], h.w);
       dst[(8 + c16) * TILE_M] = l;
     }
   }
@@ -171,7 +176,6 @@ __device__ __forceinline__ float sigmoid_f(float x) { return __fdividef(1.f, 1.f
 // F16 (single-pass schedule only): fp16 operands -- P.w_hi then points at the fp16 weight stages (DFN_PREC_FP16).
 template <bool X3, bool DEC, bool F16 = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1) mlp_pp_kernel(const __grid_constant__ Params P) {
-  static_assert(!(X3 && F16), "fp16 operands run in the single-pass schedule");
   constexpr int NSLOT = X3 ? 1 : 2;
   constexpr int NPART = X3 ? 2 : 1;
   constexpr int ROWB = X3 ? 256 : 128;  // scratch bytes per row of a staged block
@@ -243,7 +247,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1) mlp_pp_kerne
           const uint32_t bytes = (uint32_t)L.n * 64u;
           for (int kbi = 0; kbi < L.nkb; ++kbi) {
             if (L.kb[kbi] >= TC_KB_PE) ++cnt;  // the entry before this K-block's weights is filled by the epilogue warps
-            for (int part = 0; part < NPART; ++part) {
+            for (int part = 0; part < layer_parts<NPART>(L); ++part) {
               const uint32_t e = cnt % N_ENTRIES, par = (cnt / N_ENTRIES) & 1u;
               mbar_wait(bar_empty + 8 * e, par ^ 1u);
               if (elect_one_sync()) {
@@ -334,7 +338,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1) mlp_pp_kerne
             }
             const uint64_t adesc_hi = make_smem_desc(a_hi);
             const uint64_t adesc_lo = make_smem_desc(a_lo);
-            for (int part = 0; part < NPART; ++part) {
+            const int nparts = layer_parts<NPART>(L);
+            for (int part = 0; part < nparts; ++part) {
               const uint32_t e = cnt % N_ENTRIES, par = (cnt / N_ENTRIES) & 1u;
               long long t_f0 = 0;
               if (tr) t_f0 = clock64();
@@ -347,7 +352,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1) mlp_pp_kerne
                 const uint64_t bd = bdesc + (uint64_t)((q >> 1) * (SLOT_BYTES >> 4) + (q & 1) * 2);
                 umma_bf16(acc, adesc_hi + 2 * q, bd, idesc, (kbi | part | q) != 0 ? 1u : acc0);
               }
-              if (X3 && part == 0) {
+              if (X3 && part == 0 && nparts == 2) {
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                   const uint64_t bd = bdesc + (uint64_t)((q >> 1) * (SLOT_BYTES >> 4) + (q & 1) * 2);
@@ -739,6 +744,45 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1) mlp_pp_kerne
               if (cc + 2 < nch) tmem_ld32(acc + (ch0 + cc + 2) * 32, v0);
               stage_chunk<X3, F16>(v1, ch0 + cc + 1, sbias, scr(j & 1, s, (ch0 + cc + 1) >> 1), row);
             }
+          } else if (L.epi == TC_EPI_RELU && (L.n & 63) == 0) {
+            // column-distributed readout (tc_epi.cuh): the two warps of a lane quarter take its two 16-lane halves of every
+            // 64-column block, so block k is complete after everybody's k-th piece and is signalled as below; the lo plane is
+            // skipped when the consuming layer is single-pass
+            const int nkb_out = (int)L.n >> 6;
+            const bool need_lo = !(P.layers[ln].flags & TC_F_SINGLE);
+            const uint32_t accp = acc + ((uint32_t)(16 * hf) << 16);
+            const uint32_t r0 = (uint32_t)(q * 32 + 16 * hf) + ((uint32_t)lane >> 2);
+            uint32_t v0[32], v1[32];
+            auto bias16 = [&](int kb, float (&b)[16]) {
+              const uint32_t ba = sbias + (uint32_t)(kb * 64 + 2 * (lane & 3)) * 4u;
+#pragma unroll
+              for (int g = 0; g < 8; ++g)
+                asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(b[2 * g]), "=f"(b[2 * g + 1]) : "r"(ba + (uint32_t)g * 32u));
+            };
+            auto done = [&](int k) {
+              if (k + 1 < nkb_out) {
+                tcgen05_fence_before();
+                fence_proxy_async();
+                mbar_arrive(bar_kready + 8 * k);
+              }
+            };
+            tmem_ld_16x256b_x8(accp, v0);
+            for (int kb = 0; kb < nkb_out; kb += 2) {
+              float b[16];
+              bias16(kb, b);
+              tmem_ld_wait();
+              if (kb + 1 < nkb_out) tmem_ld_16x256b_x8(accp + (uint32_t)(kb + 1) * 64u, v1);
+              epilogue_piece_cd_split<F16>(v0, b, arena_hi + (size_t)kb * KB_BYTES, arena_lo + (size_t)kb * KB_BYTES, need_lo, r0, (uint32_t)lane);
+              done(kb);
+              if (kb + 1 < nkb_out) {
+                bias16(kb + 1, b);
+                tmem_ld_wait();
+                if (kb + 2 < nkb_out) tmem_ld_16x256b_x8(accp + (uint32_t)(kb + 2) * 64u, v0);
+                epilogue_piece_cd_split<F16>(v1, b, arena_hi + (size_t)(kb + 1) * KB_BYTES, arena_lo + (size_t)(kb + 1) * KB_BYTES, need_lo, r0,
+                                             (uint32_t)lane);
+                done(kb + 1);
+              }
+            }
           } else {
             const bool per_ray = L.epi == TC_EPI_VIEW0;
             const int n_relu = per_ray ? P.view_w : (int)L.n;
@@ -906,13 +950,20 @@ int pp_launch_prog(const TcProgram& prog, const uint32_t* woff32, const uint8_t*
   int grid = P.n_tiles < num_sms() ? P.n_tiles : num_sms();
   grid = (grid + 1) & ~1;
   if (grid > num_sms()) grid = num_sms() & ~1;
-  const bool x3 = precision == DFN_PREC_BF16X3;
+  const bool x3 = precision == DFN_PREC_BF16X3 || precision == DFN_PREC_FP16X3M;
   for (int i = 0; i < prog.n_layers; ++i)
     if ((prog.layers[i].flags & TC_F_DOT_SIGMA) && (x3 || !decoder || dot_w == nullptr)) {
       set_error("pp_launch_prog: a program with a folded density head runs on the single-pass Decoder kernels only");
       return DFN_E_STATE;
     }
-  if (precision == DFN_PREC_FP16) {   // w_hi: the fp16 stages (Decoder programs; FaceNeRF / NeRF use mlp_tc.cu)
+  if (precision == DFN_PREC_FP16X3M) {   // w_hi / w_lo: the fp16 stages and their fp16 residuals; TC_F_SINGLE set by the caller
+    if (decoder) {
+      set_error("pp_launch_prog: DFN_PREC_FP16X3M is wired for FaceNeRF / NeRF only");
+      return DFN_E_UNSUPPORTED;
+    }
+    return pp_launch_t<true, false, true>(P, grid, st);
+  }
+  if (precision == DFN_PREC_FP16) {   // w_hi: the fp16 stages (Decoder programs; FaceNeRF / NeRF use mlp_pair.cu)
     if (!decoder) {
       set_error("pp_launch_prog: DFN_PREC_FP16 is wired for the Decoder programs only");
       return DFN_E_UNSUPPORTED;
@@ -926,6 +977,17 @@ int pp_launch_prog(const TcProgram& prog, const uint32_t* woff32, const uint8_t*
 int pp_launch(const dfn_model* m, const float* bias_ws, const float* vbias_ws, void* scratch, int64_t R, int S,
               const float* rays_o, const float* rays_d, const float* z_vals, float* raw, int precision,
               cudaStream_t st) {
+  if (precision == DFN_PREC_FP16X3M) {
+    // fp16 operands; three products (hi hi + lo hi + hi lo) only where the density is formed after the skip connection -- the trunk
+    // layers from the one that consumes the skip on, and views_linears.0 whose MMA carries alpha_linear as an output row -- one
+    // product everywhere else (profiles/precision_emulation.py --sweep: those four layers carry the whole sensitivity).
+    TcProgram prog = m->prog;
+    const int D = m->desc.D, skip = m->desc.skip;
+    for (int i = 0; i < prog.n_layers; ++i)
+      if (!(i > skip && i <= D)) prog.layers[i].flags |= TC_F_SINGLE;
+    return pp_launch_prog(prog, m->tc32_woff, m->tc_h16, m->tc_l16, nullptr, false, m->desc.multires, m->desc.multires_views, m->desc.W / 2,
+                          bias_ws, vbias_ws, scratch, R, S, rays_o, rays_d, z_vals, raw, precision, st);
+  }
   return pp_launch_prog(m->prog, m->tc32_woff, m->tc_hi, m->tc_lo, nullptr, false, m->desc.multires, m->desc.multires_views, m->desc.W / 2,
                         bias_ws, vbias_ws,
                         scratch, R, S, rays_o, rays_d, z_vals, raw, precision, st);

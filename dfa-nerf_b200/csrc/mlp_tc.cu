@@ -569,7 +569,8 @@ void tc_free_model(dfn_model* m) {
   cudaFree(m->tc_hi);
   cudaFree(m->tc_lo);
   cudaFree(m->tc_h16);
-  m->tc_h16 = nullptr;
+  cudaFree(m->tc_l16);
+  m->tc_h16 = m->tc_l16 = nullptr;
   cudaFree(m->tc_bias);
   cudaFree(m->tc_fold_w);
   cudaFree(m->tc_view_w);
@@ -740,6 +741,8 @@ int tc_pack_model(dfn_model* m, const float* const* t, cudaStream_t st, TcHostDu
   DFN_CUDA(cudaMalloc(&m->tc_lo, pk.lo32.size()));
   DFN_CUDA(cudaMalloc(&m->tc_h16, pk.h16.size()));
   DFN_CUDA(cudaMemcpyAsync(m->tc_h16, pk.h16.data(), pk.h16.size(), cudaMemcpyHostToDevice, st));
+  DFN_CUDA(cudaMalloc(&m->tc_l16, pk.l16.size()));
+  DFN_CUDA(cudaMemcpyAsync(m->tc_l16, pk.l16.data(), pk.l16.size(), cudaMemcpyHostToDevice, st));
   DFN_CUDA(cudaMalloc(&m->tc_bias, bias.size() * 4));
   DFN_CUDA(cudaMalloc(&m->tc_fold_w, fold_w.size() * 4));
   DFN_CUDA(cudaMemcpyAsync(m->tc_hi, pk.hi32.data(), pk.hi32.size(), cudaMemcpyHostToDevice, st));
@@ -891,9 +894,9 @@ int tc_query_points(const dfn_model* m, int64_t R, int S, const float* rays_o, c
   macs_pt += (double)(m->n_views - 1) * Wh * Wh + 3.0 * Wh;  // remaining view layers and rgb
   const bool prof = profile_begin(st, macs_pt * (double)P.n_points);
   // default: bf16x3 -> mlp_pp.cu (2), bf16 / fp16 -> the CTA-pair kernel mlp_pair.cu (3)
-  const int impl = g_impl >= 0 ? (g_impl & 15) : (precision == DFN_PREC_BF16X3 ? 2 : 3);
+  const int impl = g_impl >= 0 ? (g_impl & 15) : ((precision == DFN_PREC_BF16X3 || precision == DFN_PREC_FP16X3M) ? 2 : 3);
   pair_set_flags(g_impl >= 16 ? (g_impl >> 4) - 1 : 3);   // debug: flags + 1 in the high bits
-  if (impl == 2 && (precision == DFN_PREC_BF16 || precision == DFN_PREC_BF16X3)) {
+  if (precision == DFN_PREC_FP16X3M || (impl == 2 && (precision == DFN_PREC_BF16 || precision == DFN_PREC_BF16X3))) {
     int rc = pp_launch(m, bias_ws, vbias_ws, scratch_ws, R, S, rays_o, rays_d, z_vals, raw, precision, st);
     if (rc) return rc;
   } else if ((impl == 3 || impl == 8) && (precision == DFN_PREC_BF16 || precision == DFN_PREC_FP16)) {

@@ -37,7 +37,10 @@ enum {
   // Decoder, single-pass precisions: sigma_out (DEC:329) is evaluated on the CUDA cores inside the epilogue of the block
   // that produces its input -- an M=128 x K=16 MMA costs the same for N=16 as for N=256, and every layer is one more
   // MMA -> epilogue -> barrier step on the tile's dependency chain.  dot_w = the head row [256] + its bias.
-  TC_F_DOT_SIGMA = 2   // TC_EPI_RELU layer: density register = dot_w[0..255] . relu(out) + dot_w[256]
+  TC_F_DOT_SIGMA = 2,  // TC_EPI_RELU layer: density register = dot_w[0..255] . relu(out) + dot_w[256]
+  // split modes (mlp_pp.cu, X3): this layer issues the hi x hi product only (DFN_PREC_FP16X3M: everything but the layers that form the
+  // density after the skip connection)
+  TC_F_SINGLE = 4
 };
 static constexpr int TC_DOT_FLOATS = 256 + 4;
 static constexpr int TC_MAX_LAYERS = 20;
@@ -77,6 +80,7 @@ struct dfn_model {
   uint8_t* tc_hi = nullptr;     // packed bf16 (hi) weight stages
   uint8_t* tc_lo = nullptr;     // packed bf16 (lo = bf16(w - hi)) weight stages, same offsets
   uint8_t* tc_h16 = nullptr;    // packed fp16 weight stages (DFN_PREC_FP16), same offsets
+  uint8_t* tc_l16 = nullptr;    // fp16 residuals fp16(w - fp16(w)) (DFN_PREC_FP16X3M), same offsets
   int64_t tc_blob_bytes = 0;
   float* tc_bias = nullptr;     // [n_layers][256] static biases
   float* tc_fold_w = nullptr;   // [2][W][dim_aud] latent columns of the two folding layers

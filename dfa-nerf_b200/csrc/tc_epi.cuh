@@ -27,10 +27,10 @@ __device__ __forceinline__ void store_chunk(uint8_t* blk_hi, uint8_t* blk_lo, ui
   *reinterpret_cast<uint4*>(blk_hi + swz(row, chunk)) = h;
   if (X3) {
     uint4 l;
-    l.x = pack_bf16(v[0] - bf16_lo_f(h.x), v[1] - bf16_hi_f(h.x));
-    l.y = pack_bf16(v[2] - bf16_lo_f(h.y), v[3] - bf16_hi_f(h.y));
-    l.z = pack_bf16(v[4] - bf16_lo_f(h.z), v[5] - bf16_hi_f(h.z));
-    l.w = pack_bf16(v[6] - bf16_lo_f(h.w), v[7] - bf16_hi_f(h.w));
+    l.x = pack_lo<F16>(v[0], v[1], h.x);
+    l.y = pack_lo<F16>(v[2], v[3], h.y);
+    l.z = pack_lo<F16>(v[4], v[5], h.z);
+    l.w = pack_lo<F16>(v[6], v[7], h.w);
     *reinterpret_cast<uint4*>(blk_lo + swz(row, chunk)) = l;
   }
 }
@@ -66,7 +66,7 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[32], int chun
       float o[8];
 #pragma unroll
       for (int e = 0; e < 8; ++e) o[e] = fmaxf(__uint_as_float(v[g * 8 + e]) + b[e], 0.f);
-      store_chunk<true>(dst_hi, dst_lo, row, c16, o);
+      store_chunk<true, F16>(dst_hi, dst_lo, row, c16, o);
     }
   }
 }
@@ -151,6 +151,26 @@ __device__ __forceinline__ void epilogue_piece_cd(const uint32_t (&v)[32], const
     }
     *reinterpret_cast<uint32_t*>(blk + swz(row_lo, (uint32_t)g) + sub) = p0;
     *reinterpret_cast<uint32_t*>(blk + swz(row_lo + 8u, (uint32_t)g) + sub) = p1;
+  }
+}
+
+// The same piece for the split modes: relu(v + b) in fp32 -> hi = rn16(x) [, lo = rn16(x - hi)] as 4-byte stores into the hi / lo planes.
+// need_lo = false when every consumer of the block is a single-pass layer (DFN_PREC_FP16X3M).
+template <bool F16>
+__device__ __forceinline__ void epilogue_piece_cd_split(const uint32_t (&v)[32], const float (&b)[16], uint8_t* blk_hi, uint8_t* blk_lo,
+                                                        bool need_lo, uint32_t row_lo, uint32_t lane) {
+  const uint32_t sub = (lane & 3u) * 4u;
+#pragma unroll
+  for (int g = 0; g < 8; ++g) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const float x0 = fmaxf(__uint_as_float(v[4 * g + 2 * h]) + b[2 * g], 0.f);
+      const float x1 = fmaxf(__uint_as_float(v[4 * g + 2 * h + 1]) + b[2 * g + 1], 0.f);
+      const uint32_t hi = F16 ? pack_f16(x0, x1) : pack_bf16(x0, x1);
+      const uint32_t off = swz(row_lo + 8u * (uint32_t)h, (uint32_t)g) + sub;
+      *reinterpret_cast<uint32_t*>(blk_hi + off) = hi;
+      if (need_lo) *reinterpret_cast<uint32_t*>(blk_lo + off) = pack_lo<F16>(x0, x1, hi);
+    }
   }
 }
 

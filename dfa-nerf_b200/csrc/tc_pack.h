@@ -28,6 +28,7 @@ static inline float bf2f(uint16_t h) {
 struct Packer {
   std::vector<uint8_t> hi32, lo32;   // [n rows x 32 K] stages, 64-byte swizzle (mlp_tc.cu)
   std::vector<uint8_t> h16;          // the hi32 images with fp16 instead of bf16 values (DFN_PREC_FP16), same offsets
+  std::vector<uint8_t> l16;          // fp16 residuals fp16(w - fp16(w)), same offsets (DFN_PREC_FP16X3M)
   std::vector<uint8_t> hi2;          // [n/2 rows x 64 K] per CTA of a pair, 128-byte swizzle (mlp_pair.cu)
   std::vector<uint8_t> h16_2;        // the hi2 images with fp16 values (DFN_PREC_FP16), same offsets
   uint32_t last32 = 0;               // offset of the last layer added to hi32
@@ -60,6 +61,7 @@ struct Packer {
         hi32.resize(base + (size_t)n_out * 64, 0);
         lo32.resize(base + (size_t)n_out * 64, 0);
         h16.resize(base + (size_t)n_out * 64, 0);
+        l16.resize(base + (size_t)n_out * 64, 0);
         for (int r = 0; r < n_out; ++r) {
           for (int k = 0; k < 32; ++k) {
             const float w = wfun(r, kbi, kh * 32 + k);
@@ -70,6 +72,8 @@ struct Packer {
             memcpy(&lo32[o], &l, 2);
             const __half hh = __float2half_rn(w);
             memcpy(&h16[o], &hh, 2);
+            const __half hl = __float2half_rn(w - __half2float(hh));
+            memcpy(&l16[o], &hl, 2);
           }
         }
       }

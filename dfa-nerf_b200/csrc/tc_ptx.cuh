@@ -222,6 +222,19 @@ __device__ __forceinline__ void unpack_h2(uint32_t u, float& lo, float& hi) {
     hi = __uint_as_float(u & 0xffff0000u);
   }
 }
+// the residual pair lo = rn(v - hi) of a packed 16-bit pair `h` (bf16 or fp16): the second operand piece of the split modes
+template <bool F16>
+__device__ __forceinline__ uint32_t pack_lo(float v0, float v1, uint32_t h) {
+  float h0, h1;
+  unpack_h2<F16>(h, h0, h1);
+  if (F16) {
+    uint32_t r;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(v1 - h1), "f"(v0 - h0));
+    return r;
+  }
+  __nv_bfloat162 t = __floats2bfloat162_rn(v0 - h0, v1 - h1);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
 // relu(a + b) for two adjacent columns -> packed bf16x2 (FADD2 + F2FP.RELU.BF16.PACK_AB: one instruction per element)
 __device__ __forceinline__ uint32_t add_relu_pack(uint32_t a0, uint32_t a1, float b0, float b1) {
   uint64_t a, b, c;

@@ -41,7 +41,10 @@ enum {
   DFN_PREC_BF16 = 1,   /* tcgen05 kind::f16 bf16 operands, fp32 accumulate in TMEM (throughput mode) */
   DFN_PREC_FP16 = 2,   /* same kernel and speed with fp16 operands (11-bit significands, saturating): ~10x closer to
                           fp32 than bf16 */
-  DFN_PREC_BF16X3 = 3  /* tcgen05 split-bf16: A_hi*W_hi + A_lo*W_hi + A_hi*W_lo (fp32-parity mode) */
+  DFN_PREC_BF16X3 = 3, /* tcgen05 split-bf16: A_hi*W_hi + A_lo*W_hi + A_hi*W_lo (fp32-parity mode) */
+  DFN_PREC_FP16X3M = 4 /* FaceNeRF / NeRF: fp16 operands, the three split products only on the layers that form the density after the
+                          skip connection (trunk layers skip+1 .. D-1 and views_linears.0 + alpha_linear), one product elsewhere: the
+                          fast fp32-parity mode (teacher-forced RGB <= 1e-4; ~1.8x the single-pass MMA work instead of 3x) */
 };
 
 enum {

@@ -21,7 +21,7 @@ ro, rd, vd = dfn.get_rays(450, 450, fr['focal'], fr['c2w'], fr['cx'], fr['cy'], 
 ro, rd, vd = [t.reshape(-1, 3)[:R].contiguous() for t in (ro, rd, vd)]
 z, _ = torch.sort(torch.rand(R, S, device=dev) * 0.6 + 0.4, -1)
 aud = fr['aud'].to(dev)
-eng = dfn.RenderEngine(net, None, S, 0, precision={'bf16': dfn.PREC_BF16, 'bf16x3': dfn.PREC_BF16X3}[mode])
+eng = dfn.RenderEngine(net, None, S, 0, precision={'bf16': dfn.PREC_BF16, 'bf16x3': dfn.PREC_BF16X3, 'fp16x3m': dfn.PREC_FP16X3M}[mode])
 eng.query_points(net, ro, rd, vd, z, aud)
 T, NL = 6, 12
 buf = torch.zeros(2 * T * NL * 8 + T * NL * 2 * 16, dtype=torch.int64, device=dev)
@@ -33,6 +33,8 @@ detail = buf.cpu()[2 * T * NL * 8:].reshape(T, NL, 2, 4, 4)
 b = buf.cpu()[:2 * T * NL * 8].reshape(2, T, NL, 2, 4)
 t0 = int(b[0, 0, 0, 0, 0])
 nslot = 2 if mode == 'bf16' else 1
+if len(sys.argv) > 2:
+    nslot = int(sys.argv[2])
 print('MMA issuer (cycles rel. to start): tile layer slot | wait_aready  issue(incl. full waits)  full_wait')
 for j in range(2, 4):
     for l in range(NL):

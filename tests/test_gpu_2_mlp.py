@@ -87,18 +87,46 @@ def test_query_points_fp32(dfn, R, S):
     assert ew < 1e-5 and ec < 1e-5, (ew, ec)
 
 
+@pytest.mark.parametrize('prec_name', ['PREC_BF16X3', 'PREC_FP16X3M'])
 @pytest.mark.parametrize('R,S', [(2, 64), (37, 64), (21, 192), (600, 64)])
-def test_query_points_bf16x3_vs_fp32_oracle(dfn, R, S):
+def test_query_points_parity_modes_vs_fp32_oracle(dfn, R, S, prec_name):
+    """The two fp32-parity modes against the fp32 oracle at the north star's 1e-4: split bf16 on every layer, and fp16 operands with the
+    three split products only on the layers that form the density after the skip connection (DFN_PREC_FP16X3M)."""
     ro, rd, vd, z, aud = _query_case(R, S)
     sd = synth.facenerf_state_dict(0)
-    eng = dfn.RenderEngine(face(dfn, 0), None, S, 0, precision=dfn.PREC_BF16X3)
+    eng = dfn.RenderEngine(face(dfn, 0), None, S, 0, precision=getattr(dfn, prec_name))
     raw = eng.query_points(eng.network_fn, ro.to(DEV), rd.to(DEV), vd.to(DEV), z.to(DEV), aud.to(DEV))
     with torch.no_grad():
         ref = O.run_network(sd, 'facenerf', ro[:, None] + rd[:, None] * z[:, :, None], vd, aud)
     assert torch.isfinite(raw).all()
     ew, ec = _alpha_err(raw, ref, z, rd)
-    print('bf16x3 R=%d S=%d: weights err %.2e, colour err %.2e, raw sigma err %.2e' % (R, S, ew, ec, maxerr(raw[..., 3], ref[..., 3])))
+    print('%s R=%d S=%d: weights err %.2e, colour err %.2e, raw sigma err %.2e' % (prec_name, R, S, ew, ec, maxerr(raw[..., 3], ref[..., 3])))
     assert ew < 1e-4 and ec < 1e-4, (ew, ec)      # north-star tolerance: 1e-4 max-abs
+
+
+def test_query_points_mixed_mode_at_scale_and_nerf(dfn):
+    """DFN_PREC_FP16X3M on 20,000 rays x 192 samples against the FFMA kernels (compositing weights and colours <= 1e-4), and on the NeRF
+    class (no latent, feature_linear composed into the view layer)."""
+    R, S = 20000, 192
+    ro, rd, vd, z, aud = _query_case(R, S, seed=11)
+    net = face(dfn, 1)
+    args = [t.to(DEV) for t in (ro, rd, vd, z, aud)]
+    a = dfn.RenderEngine(net, None, S, 0, precision=dfn.PREC_FP32).query_points(net, *args)
+    b = dfn.RenderEngine(net, None, S, 0, precision=dfn.PREC_FP16X3M).query_points(net, *args)
+    wa = dfn.calc_volume_weights(args[3], args[1], a[..., 3].contiguous())
+    wb = dfn.calc_volume_weights(args[3], args[1], b[..., 3].contiguous())
+    print('mixed mode, 20,000 x 192: weights %.2e colours %.2e' % (maxerr(wa, wb), maxerr(torch.sigmoid(a[..., :3]), torch.sigmoid(b[..., :3]))))
+    assert maxerr(wa, wb) < 1e-4 and maxerr(torch.sigmoid(a[..., :3]), torch.sigmoid(b[..., :3])) < 1e-4
+    nn_ = dfn.NeRF(D=8, W=256, input_ch=63, input_ch_views=27, output_ch=4, skips=[4], use_viewdirs=True)
+    nn_.load_state_dict(synth.nerf_state_dict(0))
+    nn_ = nn_.to(DEV)
+    ro, rd, vd, z, _ = _query_case(300, 64, seed=5)
+    args = [t.to(DEV) for t in (ro, rd, vd, z)]
+    a = dfn.RenderEngine(nn_, None, 64, 0, precision=dfn.PREC_FP32).query_points(nn_, *args)
+    b = dfn.RenderEngine(nn_, None, 64, 0, precision=dfn.PREC_FP16X3M).query_points(nn_, *args)
+    wa = dfn.calc_volume_weights(args[3], args[1], a[..., 3].contiguous())
+    wb = dfn.calc_volume_weights(args[3], args[1], b[..., 3].contiguous())
+    assert maxerr(wa, wb) < 1e-4 and maxerr(torch.sigmoid(a[..., :3]), torch.sigmoid(b[..., :3])) < 1e-4
 
 
 # Gates of the single-pass kernels against the reduced-precision restatement (oracle/quantized.py: same operands rounded

@@ -38,7 +38,7 @@ def golden_rays(g):
     return ro, rd, vd, torch.full((n,), g['near']), torch.full((n,), g['far'])
 
 
-@pytest.mark.parametrize('prec_name,tol', [('PREC_FP32', 2e-5), ('PREC_BF16X3', 1e-4)])
+@pytest.mark.parametrize('prec_name,tol', [('PREC_FP32', 2e-5), ('PREC_BF16X3', 1e-4), ('PREC_FP16X3M', 1e-4)])
 def test_render_rays_golden_teacher_forced(dfn, golden, prec_name, tol):
     g = golden('render_rays')
     nc, nf = nets(dfn, g['coarse_seed'], g['fine_seed'])
@@ -59,7 +59,7 @@ def test_render_rays_free_running_report(dfn, golden):
     g = golden('render_rays')
     nc, nf = nets(dfn, g['coarse_seed'], g['fine_seed'])
     ro, rd, vd, near, far = golden_rays(g)
-    for prec_name in ('PREC_FP32', 'PREC_BF16X3', 'PREC_FP16', 'PREC_BF16'):
+    for prec_name in ('PREC_FP32', 'PREC_BF16X3', 'PREC_FP16X3M', 'PREC_FP16', 'PREC_BF16'):
         eng = dfn.RenderEngine(nc, nf, 64, 128, precision=getattr(dfn, prec_name))
         out = eng.render_rays(ro.to(DEV), rd.to(DEV), vd.to(DEV), near.to(DEV), far.to(DEV), g['bc_rgb'].to(DEV),
                               g['aud'].to(DEV), want=('rgb_map', 'z_samples'))
@@ -68,7 +68,7 @@ def test_render_rays_free_running_report(dfn, golden):
         print('%s free-running: rgb max %.2e p99 %.2e median %.2e | z_samples max %.2e'
               % (prec_name, e.max(), e.kthvalue(int(0.99 * e.numel())).values, e.median(), zs))
         assert torch.isfinite(out['rgb_map']).all()
-        if prec_name in ('PREC_FP32', 'PREC_BF16X3'):
+        if prec_name in ('PREC_FP32', 'PREC_BF16X3', 'PREC_FP16X3M'):
             assert e.median() < 1e-5 and e.max() < 5e-2
         elif prec_name == 'PREC_FP16':
             assert e.median() < 2e-4
