@@ -39,6 +39,9 @@ struct DecField {
   uint8_t* w_hi = nullptr;
   uint8_t* w_lo = nullptr;
   uint8_t* w_h16 = nullptr;  // fp16 stages (DFN_PREC_FP16), same offsets
+  uint32_t woff2[TC_MAX_LAYERS] = {};   // CTA-pair stage images (mlp_pair.cu: the head field's single-pass path), or w2_hi == nullptr
+  uint8_t* w2_hi = nullptr;
+  uint8_t* w2_h16 = nullptr;
   float* bias = nullptr;     // [n_layers][256] static part
   int n_fold = 0;
   int fold_layer[8] = {};
@@ -131,7 +134,7 @@ struct Builder {
   std::vector<float> dot;                  // folded heads (TC_DOT_FLOATS) or empty
   int nl = 0;
   explicit Builder(DecField* f, int dimL) : F(f), bias((size_t)TC_MAX_LAYERS * TC_BIAS_STRIDE, 0.f) {
-    pk.want2 = false;   // the Decoder programs run on mlp_pp.cu
+    pk.want2 = false;   // set by the caller for the program that also runs on mlp_pair.cu
     F->prog = TcProgram();
     F->dimL = dimL;
     F->n_fold = 0;
@@ -147,6 +150,7 @@ struct Builder {
     for (int kb : kbs) L.kb[L.nkb++] = (uint8_t)kb;
     pk.add_layer(n, L.nkb, wfun);
     F->woff32[nl] = pk.last32;
+    F->woff2[nl] = pk.last2;
     F->prog.layers[nl] = L;
     return nl++;
   }
@@ -165,6 +169,12 @@ struct Builder {
     DFN_CUDA(cudaMalloc(&F->w_lo, pk.lo32.size()));
     DFN_CUDA(cudaMalloc(&F->w_h16, pk.h16.size()));
     DFN_CUDA(cudaMemcpyAsync(F->w_h16, pk.h16.data(), pk.h16.size(), cudaMemcpyHostToDevice, st));
+    if (pk.want2 && !pk.hi2.empty()) {
+      DFN_CUDA(cudaMalloc(&F->w2_hi, pk.hi2.size()));
+      DFN_CUDA(cudaMalloc(&F->w2_h16, pk.h16_2.size()));
+      DFN_CUDA(cudaMemcpyAsync(F->w2_hi, pk.hi2.data(), pk.hi2.size(), cudaMemcpyHostToDevice, st));
+      DFN_CUDA(cudaMemcpyAsync(F->w2_h16, pk.h16_2.data(), pk.h16_2.size(), cudaMemcpyHostToDevice, st));
+    }
     DFN_CUDA(cudaMalloc(&F->bias, bias.size() * 4));
     std::vector<float> fw;
     for (auto& f : folds) fw.insert(fw.end(), f.begin(), f.end());
@@ -195,7 +205,9 @@ static void free_field(DecField& F) {
   cudaFree(F.w_hi);
   cudaFree(F.w_lo);
   cudaFree(F.w_h16);
-  F.w_h16 = nullptr;
+  cudaFree(F.w2_hi);
+  cudaFree(F.w2_h16);
+  F.w_h16 = F.w2_hi = F.w2_h16 = nullptr;
   cudaFree(F.bias);
   cudaFree(F.fold_w);
   cudaFree(F.dot_w);
@@ -439,7 +451,10 @@ static int dec_query(const dfn_decoder* m, int field, int64_t R, int S, const fl
     set_error("dfn_decoder_query: workspace %lld < %lld bytes", (long long)workspace_bytes, (long long)dec_workspace_bytes(m, R));
     return DFN_E_WORKSPACE;
   }
-  const DecField& F = precision == DFN_PREC_BF16X3 ? m->f[field] : m->g[field];   // single-pass kernels: folded heads
+  // split precision: the plain programs on mlp_pp.cu; single-pass: the head field's plain program on the CTA-pair kernel (mlp_pair.cu),
+  // the torso field (deformation net, staged blocks through the ring) on mlp_pp.cu with the density head folded into an epilogue
+  const bool on_pair = precision != DFN_PREC_BF16X3 && field == 0 && m->f[0].w2_hi != nullptr && !(pair_get_flags() & 8);
+  const DecField& F = (precision == DFN_PREC_BF16X3 || on_pair) ? m->f[field] : m->g[field];
   const dfn_decoder_desc& d = m->desc;
   float* bias_ws = reinterpret_cast<float*>(workspace);
   void* scratch = reinterpret_cast<char*>(workspace) + align256((int64_t)TC_MAX_LAYERS * TC_BIAS_STRIDE * 4);
@@ -456,8 +471,10 @@ static int dec_query(const dfn_decoder* m, int field, int64_t R, int S, const fl
   dec_fold_kernel<<<F.prog.n_layers, TC_BIAS_STRIDE, 0, st>>>(F.prog.n_layers, F.dimL, F.bias, F.fold_w, fa, bias_ws);
   DFN_LAUNCH_CHECK();
   const bool prof = profile_begin(st, F.macs_pt * (double)R * S);
-  int rc = pp_launch_prog(F.prog, F.woff32, precision == DFN_PREC_FP16 ? F.w_h16 : F.w_hi, F.w_lo, F.dot_w, true, d.n_freq, d.n_freq_views, d.hidden, bias_ws, nullptr, scratch, R, S, rays_o,
-                          rays_d, z_vals, raw, precision, st);
+  int rc = on_pair ? pair_launch_prog(F.prog, F.woff2, precision == DFN_PREC_FP16 ? F.w2_h16 : F.w2_hi, precision == DFN_PREC_FP16, true, d.n_freq,
+                                      d.n_freq_views, d.hidden, bias_ws, nullptr, R, S, rays_o, rays_d, z_vals, raw, st)
+                   : pp_launch_prog(F.prog, F.woff32, precision == DFN_PREC_FP16 ? F.w_h16 : F.w_hi, F.w_lo, F.dot_w, true, d.n_freq, d.n_freq_views,
+                                    d.hidden, bias_ws, nullptr, scratch, R, S, rays_o, rays_d, z_vals, raw, precision, st);
   if (prof) profile_end(st);
   if (rc) return rc;
   DFN_LAUNCH_CHECK();
@@ -516,6 +533,7 @@ extern "C" int dfn_decoder_load(dfn_decoder* m, const float* const* t, int n_ten
     DecField* F = folded ? m->g : m->f;
     {
       Builder B(&F[0], d.dim_signal + 2 * d.z_dim);
+      B.pk.want2 = folded == 0 && d.hidden == 256;   // the head's plain program also runs on the CTA-pair kernel (single-pass precisions)
       build_trunk(B, T, d, false, d.dim_signal, d.dim_signal + d.z_dim, folded != 0);
       int rc = B.upload(st);
       if (rc) return rc;

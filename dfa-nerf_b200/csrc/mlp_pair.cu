@@ -21,6 +21,10 @@
 // barrier (the peer's with a cluster-scope release); the leader's tcgen05.commit multicasts to both CTAs' `empty` and
 // `acc` barriers.
 //
+// The Decoder HEAD field of the live model (DEC:277-349; program built in mlp_dec.cu) runs here too: its two staged inputs -- the
+// positional encoding and, for the view layer, the view-direction encoding (TC_KB_DIR) -- take turns in the slot's fifth block (the helper
+// warps write the second once the skip layer has released the first), the density is a 16-column layer (TC_EPI_SIGMA).
+//
 // Reference arithmetic: HELP:21-52 (Embedder), HELP:275-299 (FaceNeRF.forward), HELP:372-396 (NeRF.forward); output
 // bit-identical to mlp_tc.cu (same operands, same fp32 bias add and rounding; the accumulation order inside an MMA is
 // the hardware's in both).
@@ -64,6 +68,9 @@ struct Params {
   unsigned long long* trace;  // debug: per-role clock64 records of CTA 0 (null in production), format of mlp_tc.cu
   int trace_tiles;
   int flags;                  // bit 0: a layer's weights stay in the ring for both slots; bit 1: CTA-scope release on the peer's `aready` arrivals
+  int dec;                    // Decoder head program (DEC:277-349): the encoding of DEC:257-275, sigma_out as a 16-column layer, sigmoid colours
+  int multires_views;         // Decoder: frequencies of the view-direction encoding
+  int dir_layer;              // Decoder: the layer that reads the view-direction encoding (TC_KB_DIR), or -1
   TcLayer layers[TC_MAX_LAYERS];
 };
 
@@ -216,7 +223,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((4 + 2 * EW) * 32, 1
 #pragma unroll
             for (int b = 0; b < 2; ++b) {
               if (kb0 + b < L.nkb) {
-                const uint64_t adesc = make_smem_desc(sbase + (uint32_t)(s * TC_KB_PER_TILE + L.kb[kb0 + b]) * KB_BYTES);
+                const uint32_t blk = L.kb[kb0 + b] >= TC_KB_PE ? (uint32_t)TC_KB_PE : (uint32_t)L.kb[kb0 + b];   // staged inputs share block 4
+                const uint64_t adesc = make_smem_desc(sbase + ((uint32_t)s * TC_KB_PER_TILE + blk) * KB_BYTES);
                 const uint64_t bdesc = make_smem_desc(sbase + SMEM_RING + e * ENT_BYTES + (uint32_t)b * bytes);
 #pragma unroll
                 for (int q = 0; q < 4; ++q)   // K = 16 per instruction: both operands advance 32 bytes inside the swizzle atom
@@ -252,6 +260,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((4 + 2 * EW) * 32, 1
     for (int l2 = 0; l2 < P.n_layers; ++l2)
       for (int k = 0; k < P.layers[l2].nkb; ++k)
         if (P.layers[l2].kb[k] == TC_KB_PE) last_pe_layer = l2;
+    const int ppt = P.dir_layer >= 0 ? 2 : 1;   // fills of the slot's staged block per tile: encoding [, view-direction encoding]
     // this warp's writes to the slot are done and its accumulator reads have completed: tell the leader's MMA issuer
     auto signal_ready = [&]() {
       tcgen05_fence_before();
@@ -279,7 +288,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((4 + 2 * EW) * 32, 1
 
       stage_bias(P.bias);   // the first layer's bias
       // the tile's positional encoding was written into the PE K-block by the helper warps (below), one tile ahead
-      mbar_wait(bar_peready + 8 * s, (uint32_t)j & 1u);
+      mbar_wait(bar_peready + 8 * s, (uint32_t)(j * ppt) & 1u);
       signal_ready();
       named_bar_sync(1 + s, ETH);  // bias_s visible to the slot's warps
 
@@ -294,7 +303,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((4 + 2 * EW) * 32, 1
         acc_par ^= 1u;
         tcgen05_fence_after();
         if (tr) t_e1 = clock64();
-        if (l == last_pe_layer) mbar_arrive(bar_pefree + 8 * s);   // its MMAs were the last readers of the PE block
+        if (l == last_pe_layer || l == P.dir_layer) mbar_arrive(bar_pefree + 8 * s);   // its MMAs were the last readers of the staged block
 
         if (L.epi == TC_EPI_RGB) {
           if (hf == 0) {
@@ -306,11 +315,26 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((4 + 2 * EW) * 32, 1
               o.x = __uint_as_float(v[0]) + bias_s[0];
               o.y = __uint_as_float(v[1]) + bias_s[1];
               o.z = __uint_as_float(v[2]) + bias_s[2];
+              if (P.dec) {   // DEC:346-347
+                o.x = __fdividef(1.f, 1.f + __expf(-o.x));
+                o.y = __fdividef(1.f, 1.f + __expf(-o.y));
+                o.z = __fdividef(1.f, 1.f + __expf(-o.z));
+              }
               o.w = alpha;
               reinterpret_cast<float4*>(P.raw)[pt] = o;
             }
           }
           tcgen05_fence_before();
+        } else if (L.epi == TC_EPI_SIGMA) {
+          // Decoder density head (DEC:329): column 0 + bias stays in a register until the last layer writes raw
+          if (hf == 0) {
+            uint32_t v[16];
+            tmem_ld16(acc, v);
+            tmem_ld_wait();
+            alpha = __uint_as_float(v[0]) + bias_s[0];
+          }
+          if (l + 1 == P.dir_layer) mbar_wait(bar_peready + 8 * s, (uint32_t)(j * ppt + 1) & 1u);   // the view-direction encoding is in place
+          signal_ready();
         } else {
           if (L.epi == TC_EPI_VIEW0) {
             const int per = P.view_w / NH;
@@ -328,6 +352,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((4 + 2 * EW) * 32, 1
             const int per = (int)L.n / NH;
             epilogue_relu_rows16<false, F16>(acc, hf * per, (hf + 1) * per, nullptr, smem_u32(bias_s), arena, row);
           }
+          if (l + 1 == P.dir_layer) mbar_wait(bar_peready + 8 * s, (uint32_t)(j * ppt + 1) & 1u);   // the view-direction encoding is in place
           signal_ready();
         }
         if (tr) {
@@ -353,31 +378,40 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((4 + 2 * EW) * 32, 1
     // x = o + d*z -> [x | sin(2^k x) | cos(2^k x)] (HELP:42-52, pe.cuh) for the NEXT tile of each slot, written straight
     // into the slot's PE K-block as soon as the last layer that reads it (the skip layer) has finished its MMAs.
     const int t = (warp - 2) * 32 + lane;
+    const int ppt = P.dir_layer >= 0 ? 2 : 1;
     for (int j = 0; j < n_iter; ++j) {
-      for (int s = 0; s < NSLOT; ++s) {
-        if (group_of(j, s) >= n_groups) continue;
-        if (j > 0) mbar_wait(bar_pefree + 8 * s, (uint32_t)(j - 1) & 1u);
-        uint8_t* pe_blk = smem + (size_t)(s * TC_KB_PER_TILE + TC_KB_PE) * KB_BYTES;
-        const int tile = 2 * group_of(j, s) + (int)crank;
+      for (int ph = 0; ph < ppt; ++ph) {        // 0: the tile's positional encoding; 1 (Decoder): its view-direction encoding
+        for (int s = 0; s < NSLOT; ++s) {
+          if (group_of(j, s) >= n_groups) continue;
+          const int fill = j * ppt + ph;         // fills of this slot's staged block so far
+          if (fill > 0) mbar_wait(bar_pefree + 8 * s, (uint32_t)(fill - 1) & 1u);
+          uint8_t* pe_blk = smem + (size_t)(s * TC_KB_PER_TILE + TC_KB_PE) * KB_BYTES;
+          const int tile = 2 * group_of(j, s) + (int)crank;
 #pragma unroll 1
-        for (int h = 0; h < 2; ++h) {
-          const uint32_t row = (uint32_t)(t + 64 * h);
-          int64_t pt = (int64_t)tile * TILE_M + row;
-          if (pt >= P.n_points) pt = P.n_points - 1;
-          const int64_t ray = pt / P.S;
-          float pe[64], x[3];
-          sample_point(P.rays_o, P.rays_d, ray, P.z_vals[pt], x);
-          pe_embedder(x, P.multires, pe);
+          for (int h = 0; h < 2; ++h) {
+            const uint32_t row = (uint32_t)(t + 64 * h);
+            int64_t pt = (int64_t)tile * TILE_M + row;
+            if (pt >= P.n_points) pt = P.n_points - 1;
+            const int64_t ray = pt / P.S;
+            float pe[64], x[3];
+            if (ph == 1) {
+              pe_decoder_viewdir(P.rays_d, ray, P.multires_views, pe);
+            } else {
+              sample_point(P.rays_o, P.rays_d, ray, P.z_vals[pt], x);
+              if (P.dec) pe_decoder(x, P.multires, pe);
+              else pe_embedder(x, P.multires, pe);
+            }
 #pragma unroll
-          for (int ch = 0; ch < 8; ++ch) {
-            float o[8];
+            for (int ch = 0; ch < 8; ++ch) {
+              float o[8];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) o[e] = pe[ch * 8 + e];
-            store_chunk<false, F16>(pe_blk, pe_blk, row, (uint32_t)ch, o);
+              for (int e = 0; e < 8; ++e) o[e] = pe[ch * 8 + e];
+              store_chunk<false, F16>(pe_blk, pe_blk, row, (uint32_t)ch, o);
+            }
           }
+          fence_proxy_async();
+          mbar_arrive(bar_peready + 8 * s);
         }
-        fence_proxy_async();
-        mbar_arrive(bar_peready + 8 * s);
       }
     }
   }
@@ -391,21 +425,19 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((4 + 2 * EW) * 32, 1
 
 }  // namespace tcp
 
-static int g_pair_ew = 8, g_pair_flags = 0;   // epilogue warps per slot (debug: dfn_debug_set_impl(3) -> 8, (8) -> 4)
+static int g_pair_ew = 8, g_pair_flags = 3;   // epilogue warps per slot (debug: dfn_debug_set_impl(3) -> 8, (8) -> 4)
 void pair_set_epilogue_warps(int ew) { g_pair_ew = ew == 4 ? 4 : 8; }
 void pair_set_flags(int flags) { g_pair_flags = flags; }
+int pair_get_flags() { return g_pair_flags; }
 
-int pair_launch(const dfn_model* m, const float* bias_ws, const float* vbias_ws, int64_t R, int S, const float* rays_o,
-                const float* rays_d, const float* z_vals, float* raw, int precision, cudaStream_t st) {
-  const bool f16 = precision == DFN_PREC_FP16;
-  if ((precision != DFN_PREC_BF16 && !f16) || m->tc2_hi == nullptr || m->tc2_h16 == nullptr) {
-    set_error("pair_launch: the cta_group::2 kernel covers DFN_PREC_BF16 / DFN_PREC_FP16");
-    return DFN_E_UNSUPPORTED;
-  }
-  const dfn_model_desc& d = m->desc;
+// prog: layer program; woff2 / w: per-layer offsets into, and the blob of, the CTA-pair stage images (tc_pack.h); decoder: the head
+// program of the live model (mlp_dec.cu).
+int pair_launch_prog(const TcProgram& prog, const uint32_t* woff2, const uint8_t* w, bool f16, bool decoder, int multires, int multires_views,
+                     int view_w, const float* bias_ws, const float* vbias_ws, int64_t R, int S, const float* rays_o, const float* rays_d,
+                     const float* z_vals, float* raw, cudaStream_t st) {
   tcp::Params P;
   memset(&P, 0, sizeof(P));
-  P.w = f16 ? m->tc2_h16 : m->tc2_hi;
+  P.w = w;
   P.bias = bias_ws;
   P.view_bias = vbias_ws;
   P.rays_o = rays_o;
@@ -415,14 +447,32 @@ int pair_launch(const dfn_model* m, const float* bias_ws, const float* vbias_ws,
   P.n_points = R * S;
   P.S = S;
   P.n_tiles = (int)((P.n_points + tc::TILE_M - 1) / tc::TILE_M);
-  P.n_layers = m->prog.n_layers;
-  P.multires = d.multires;
-  P.view_w = d.W / 2;
+  P.n_layers = prog.n_layers;
+  P.multires = multires;
+  P.multires_views = multires_views;
+  P.view_w = view_w;
+  P.dec = decoder ? 1 : 0;
+  P.dir_layer = -1;
   tc_get_trace(reinterpret_cast<void**>(&P.trace), &P.trace_tiles);
   P.flags = g_pair_flags;
-  for (int i = 0; i < m->prog.n_layers; ++i) {
-    P.layers[i] = m->prog.layers[i];
-    P.layers[i].woff = m->tc2_woff[i];
+  for (int i = 0; i < prog.n_layers; ++i) {
+    P.layers[i] = prog.layers[i];
+    P.layers[i].woff = woff2[i];
+    const TcLayer& L = prog.layers[i];
+    bool ok = L.epi == TC_EPI_RELU || L.epi == TC_EPI_RGB || (!decoder && L.epi == TC_EPI_VIEW0) || (decoder && L.epi == TC_EPI_SIGMA);
+    if (L.flags != 0 || L.nkb > 5) ok = false;
+    for (int k = 0; k < L.nkb; ++k) {
+      if (L.kb[k] == TC_KB_DIR) {
+        if (!decoder || P.dir_layer >= 0 || i == 0) ok = false;
+        P.dir_layer = i;
+      } else if (L.kb[k] > TC_KB_PE) {
+        ok = false;
+      }
+    }
+    if (!ok) {
+      set_error("pair_launch_prog: layer %d of the program is outside what the CTA-pair kernel runs", i);
+      return DFN_E_UNSUPPORTED;
+    }
   }
   int grid = P.n_tiles < num_sms() ? P.n_tiles : num_sms();
   grid = (grid + 1) & ~1;
@@ -433,11 +483,19 @@ int pair_launch(const dfn_model* m, const float* bias_ws, const float* vbias_ws,
     kernel<<<grid, threads, tcp::SMEM_TOTAL, st>>>(P);
     return 0;
   };
-  int rc;
-  if (ew == 8) rc = f16 ? launch(tcp::mlp_pair_kernel<true, 8>, 640) : launch(tcp::mlp_pair_kernel<false, 8>, 640);
-  else rc = f16 ? launch(tcp::mlp_pair_kernel<true, 4>, 384) : launch(tcp::mlp_pair_kernel<false, 4>, 384);
-  if (rc) return rc;
-  return 0;
+  if (ew == 8) return f16 ? launch(tcp::mlp_pair_kernel<true, 8>, 640) : launch(tcp::mlp_pair_kernel<false, 8>, 640);
+  return f16 ? launch(tcp::mlp_pair_kernel<true, 4>, 384) : launch(tcp::mlp_pair_kernel<false, 4>, 384);
+}
+
+int pair_launch(const dfn_model* m, const float* bias_ws, const float* vbias_ws, int64_t R, int S, const float* rays_o,
+                const float* rays_d, const float* z_vals, float* raw, int precision, cudaStream_t st) {
+  const bool f16 = precision == DFN_PREC_FP16;
+  if ((precision != DFN_PREC_BF16 && !f16) || m->tc2_hi == nullptr || m->tc2_h16 == nullptr) {
+    set_error("pair_launch: the cta_group::2 kernel covers DFN_PREC_BF16 / DFN_PREC_FP16");
+    return DFN_E_UNSUPPORTED;
+  }
+  return pair_launch_prog(m->prog, m->tc2_woff, f16 ? m->tc2_h16 : m->tc2_hi, f16, false, m->desc.multires, m->desc.multires_views,
+                          m->desc.W / 2, bias_ws, vbias_ws, R, S, rays_o, rays_d, z_vals, raw, st);
 }
 
 }  // namespace dfn
