@@ -338,7 +338,7 @@ class Job:
             self.aud_dev, self.lat_host = lat.to(dev), lat.pin_memory()
             self.bc_dev, self.bc_host = fr['bc_rgb'].to(dev), fr['bc_rgb'].pin_memory()
             self.evals_per_ray = 2 * N_SAMPLES
-            self.kernel_name = 'mlp_pp_kernel<%s, Decoder>' % precision
+            self.kernel_name = ('mlp_pp_kernel<%s, Decoder>' if precision == 'bf16x3' else 'mlp_pair_kernel<%s, Decoder>') % precision
             self.flops_note = 'algorithmic, per-frame latents and per-ray view term folded: 2*556,032 (head) + 2*628,352 (torso ' \
                               'incl. deformation field) per sample (SURVEY.md section 8d, appendix A)'
         if workload not in ('sequence', 'train_step'):

@@ -59,6 +59,7 @@ struct dfn_decoder {
   bool loaded = false;
   dfn::DecField f[2];        // 0 head, 1 torso: plain programs (bf16x3)
   dfn::DecField g[2];        // the same fields with sigma_out folded into an epilogue (bf16 / fp16)
+  dfn::DecField tp;          // the torso field's plain program in the layout of the CTA-pair kernel (fc_in_torso as one layer)
 };
 
 namespace dfn {
@@ -133,6 +134,7 @@ struct Builder {
   std::vector<std::vector<float>> folds;   // each [dimL][256]
   std::vector<float> dot;                  // folded heads (TC_DOT_FLOATS) or empty
   int nl = 0;
+  bool pair_layout = false;   // program for mlp_pair.cu: the torso's fc_in as ONE layer over [PE' | signal' in hidden block 3]
   explicit Builder(DecField* f, int dimL) : F(f), bias((size_t)TC_MAX_LAYERS * TC_BIAS_STRIDE, 0.f) {
     pk.want2 = false;   // set by the caller for the program that also runs on mlp_pair.cu
     F->prog = TcProgram();
@@ -231,6 +233,12 @@ static void build_trunk(Builder& B, const std::vector<Lin>& T, const dfn_decoder
     float* fw = B.fold(l);
     for (int n = 0; n < H; ++n)
       for (int j = 0; j < dsig; ++j) fw[(size_t)j * TC_BIAS_STRIDE + n] = fcin.W(n, de + j);   // per-frame signal columns
+  } else if (B.pair_layout) {
+    // mlp_pair.cu: the deformation output's epilogue leaves PE' in the staged block and signal' in hidden block 3 (free under the 128-wide
+    // deformation layers), so fc_in_torso reads both at once
+    l = B.layer(H, TC_EPI_RELU, 0, {TC_KB_PE, 3}, [&](int n, int kbi, int k) {
+      return kbi == 0 ? (k < de ? fcin.W(n, k) : 0.f) : (k < dsig ? fcin.W(n, de + k) : 0.f);
+    });
   } else {
     B.layer(H, TC_EPI_CONT, 0, {TC_KB_PE}, [&](int n, int, int k) { return k < de ? fcin.W(n, k) : 0.f; });
     l = B.layer(H, TC_EPI_RELU, TC_F_ACCUM, {TC_KB_IN1}, [&](int n, int, int k) { return k < dsig ? fcin.W(n, de + k) : 0.f; });
@@ -451,10 +459,11 @@ static int dec_query(const dfn_decoder* m, int field, int64_t R, int S, const fl
     set_error("dfn_decoder_query: workspace %lld < %lld bytes", (long long)workspace_bytes, (long long)dec_workspace_bytes(m, R));
     return DFN_E_WORKSPACE;
   }
-  // split precision: the plain programs on mlp_pp.cu; single-pass: the head field's plain program on the CTA-pair kernel (mlp_pair.cu),
-  // the torso field (deformation net, staged blocks through the ring) on mlp_pp.cu with the density head folded into an epilogue
-  const bool on_pair = precision != DFN_PREC_BF16X3 && field == 0 && m->f[0].w2_hi != nullptr && !(pair_get_flags() & 8);
-  const DecField& F = (precision == DFN_PREC_BF16X3 || on_pair) ? m->f[field] : m->g[field];
+  // split precision: the plain programs on mlp_pp.cu; single-pass: the plain programs on the CTA-pair kernel (mlp_pair.cu; the torso's in
+  // its own layout), or -- debug flags 8 / 16, hidden != 256 -- the folded-head programs on mlp_pp.cu
+  const DecField& P2 = field == 0 ? m->f[0] : m->tp;
+  const bool on_pair = precision != DFN_PREC_BF16X3 && P2.w2_hi != nullptr && !(pair_get_flags() & (field == 0 ? 8 : 16));
+  const DecField& F = on_pair ? P2 : (precision == DFN_PREC_BF16X3 ? m->f[field] : m->g[field]);
   const dfn_decoder_desc& d = m->desc;
   float* bias_ws = reinterpret_cast<float*>(workspace);
   void* scratch = reinterpret_cast<char*>(workspace) + align256((int64_t)TC_MAX_LAYERS * TC_BIAS_STRIDE * 4);
@@ -472,7 +481,7 @@ static int dec_query(const dfn_decoder* m, int field, int64_t R, int S, const fl
   DFN_LAUNCH_CHECK();
   const bool prof = profile_begin(st, F.macs_pt * (double)R * S);
   int rc = on_pair ? pair_launch_prog(F.prog, F.woff2, precision == DFN_PREC_FP16 ? F.w2_h16 : F.w2_hi, precision == DFN_PREC_FP16, true, d.n_freq,
-                                      d.n_freq_views, d.hidden, bias_ws, nullptr, R, S, rays_o, rays_d, z_vals, raw, st)
+                                      d.n_freq_views, d.hidden, bias_ws, nullptr, scratch, R, S, rays_o, rays_d, z_vals, raw, st)
                    : pp_launch_prog(F.prog, F.woff32, precision == DFN_PREC_FP16 ? F.w_h16 : F.w_hi, F.w_lo, F.dot_w, true, d.n_freq, d.n_freq_views,
                                     d.hidden, bias_ws, nullptr, scratch, R, S, rays_o, rays_d, z_vals, raw, precision, st);
   if (prof) profile_end(st);
@@ -510,6 +519,7 @@ extern "C" void dfn_decoder_destroy(dfn_decoder* m) {
     free_field(m->f[i]);
     free_field(m->g[i]);
   }
+  free_field(m->tp);
   delete m;
 }
 
@@ -528,7 +538,17 @@ extern "C" int dfn_decoder_load(dfn_decoder* m, const float* const* t, int n_ten
     free_field(m->f[i]);
     free_field(m->g[i]);
   }
+  free_field(m->tp);
   m->loaded = false;
+  if (d.hidden == 256) {
+    Builder B(&m->tp, dt + 2 * d.z_dim);
+    B.pk.want2 = true;
+    B.pair_layout = true;
+    build_deform(B, T, d);
+    build_trunk(B, T, d, true, dt, dt + d.z_dim, false);
+    int rc = B.upload(st);
+    if (rc) return rc;
+  }
   for (int folded = 0; folded < 2; ++folded) {
     DecField* F = folded ? m->g : m->f;
     {
@@ -559,7 +579,7 @@ extern "C" int dfn_decoder_program_host(const dfn_decoder_desc* desc, const floa
                 "dfn_decoder_program_host: null argument");
   DFN_CHECK_ARG(n_tensors == 2 * T_COUNT && (field == 0 || field == 1) && max_layers >= TC_MAX_LAYERS,
                 "dfn_decoder_program_host: expected %d tensors, field 0|1, max_layers >= %d", 2 * T_COUNT, TC_MAX_LAYERS);
-  DFN_CHECK_ARG(!folded_heads || dot_w, "dfn_decoder_program_host: dot_w is required for the folded-head program");
+  DFN_CHECK_ARG(folded_heads != 1 || dot_w, "dfn_decoder_program_host: dot_w is required for the folded-head program");
   DFN_CHECK_ARG(desc->hidden == 256 && desc->n_blocks == 8 && desc->skip == 4 && desc->n_freq >= 1 && desc->n_freq <= 10 &&
                     desc->dim_et_embed >= 1 && desc->dim_et_embed <= 64,
                 "dfn_decoder_program_host: unsupported decoder shape");
@@ -569,9 +589,10 @@ extern "C" int dfn_decoder_program_host(const dfn_decoder_desc* desc, const floa
   Builder B(&F, dsig + 2 * desc->z_dim);
   std::vector<float> dense;
   B.pk.dense = &dense;
+  B.pair_layout = folded_heads == 2;   // the plain program in the layout mlp_pair.cu runs (torso: fc_in_torso as one layer)
   if (field == 1) build_deform(B, T, *desc);
-  build_trunk(B, T, *desc, field == 1, dsig, dsig + desc->z_dim, folded_heads != 0);
-  if (folded_heads) memcpy(dot_w, B.dot.data(), B.dot.size() * 4);
+  build_trunk(B, T, *desc, field == 1, dsig, dsig + desc->z_dim, folded_heads == 1);
+  if (folded_heads == 1) memcpy(dot_w, B.dot.data(), B.dot.size() * 4);
   *n_layers = B.nl;
   for (int l = 0; l < B.nl; ++l) {
     const TcLayer& L = F.prog.layers[l];

@@ -70,7 +70,12 @@ struct Params {
   int flags;                  // bit 0: a layer's weights stay in the ring for both slots; bit 1: CTA-scope release on the peer's `aready` arrivals
   int dec;                    // Decoder head program (DEC:277-349): the encoding of DEC:257-275, sigma_out as a 16-column layer, sigmoid colours
   int multires_views;         // Decoder: frequencies of the view-direction encoding
-  int dir_layer;              // Decoder: the layer that reads the view-direction encoding (TC_KB_DIR), or -1
+  // Staged inputs: the slot's fifth block is (re)filled n_fills times per tile by the helper warps -- fill k holds staged block
+  // fill_kb[k] (TC_KB_PE: positional encoding, computed; TC_KB_IN1: the torso's deformed signal, copied from `scratch`; TC_KB_DIR:
+  // view-direction encoding, computed), is first read by layer fill_use[k] and dead once the MMAs of layer fill_rel[k] have completed.
+  int n_fills;
+  int fill_kb[3], fill_use[3], fill_rel[3];
+  uint8_t* scratch;           // torso field: [grid][2 slots] byte images of the deformed-signal block (TC_EPI_STAGE writes, fill IN1 reads)
   TcLayer layers[TC_MAX_LAYERS];
 };
 
@@ -228,7 +233,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((4 + 2 * EW) * 32, 1
                 const uint64_t bdesc = make_smem_desc(sbase + SMEM_RING + e * ENT_BYTES + (uint32_t)b * bytes);
 #pragma unroll
                 for (int q = 0; q < 4; ++q)   // K = 16 per instruction: both operands advance 32 bytes inside the swizzle atom
-                  umma_bf16_2cta(acc, adesc + 2 * q, bdesc + 2 * q, idesc, (kb0 | b | q) != 0 ? 1u : 0u);
+                  umma_bf16_2cta(acc, adesc + 2 * q, bdesc + 2 * q, idesc, ((kb0 | b | q) != 0 || (L.flags & TC_F_ACCUM)) ? 1u : 0u);
               }
             }
             if (last_use) umma_commit2_mc(bar_empty + 8 * e, (uint16_t)3);
@@ -256,11 +261,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((4 + 2 * EW) * 32, 1
     float* bias_s = reinterpret_cast<float*>(smem + SMEM_BIAS) + s * TC_BIAS_STRIDE;
     const uint32_t acc = tmem_base + (uint32_t)s * 256u + ((uint32_t)((warp & 3) * 32) << 16);
     uint32_t acc_par = 0u;
-    int last_pe_layer = 0;
-    for (int l2 = 0; l2 < P.n_layers; ++l2)
-      for (int k = 0; k < P.layers[l2].nkb; ++k)
-        if (P.layers[l2].kb[k] == TC_KB_PE) last_pe_layer = l2;
-    const int ppt = P.dir_layer >= 0 ? 2 : 1;   // fills of the slot's staged block per tile: encoding [, view-direction encoding]
+    const int nf = P.n_fills;   // fills of the slot's staged block per tile
+    // fill k >= 1 must be in place before the layer that first reads it is handed to the MMA issuer
+    auto wait_fill_for = [&](int next_layer, int j) {
+      for (int k = 1; k < nf; ++k)
+        if (P.fill_use[k] == next_layer) mbar_wait(bar_peready + 8 * s, (uint32_t)(j * nf + k) & 1u);
+    };
     // this warp's writes to the slot are done and its accumulator reads have completed: tell the leader's MMA issuer
     auto signal_ready = [&]() {
       tcgen05_fence_before();
@@ -288,7 +294,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((4 + 2 * EW) * 32, 1
 
       stage_bias(P.bias);   // the first layer's bias
       // the tile's positional encoding was written into the PE K-block by the helper warps (below), one tile ahead
-      mbar_wait(bar_peready + 8 * s, (uint32_t)(j * ppt) & 1u);
+      mbar_wait(bar_peready + 8 * s, (uint32_t)(j * nf) & 1u);
       signal_ready();
       named_bar_sync(1 + s, ETH);  // bias_s visible to the slot's warps
 
@@ -303,7 +309,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((4 + 2 * EW) * 32, 1
         acc_par ^= 1u;
         tcgen05_fence_after();
         if (tr) t_e1 = clock64();
-        if (l == last_pe_layer || l == P.dir_layer) mbar_arrive(bar_pefree + 8 * s);   // its MMAs were the last readers of the staged block
+        for (int k = 0; k < nf; ++k)
+          if (P.fill_rel[k] == l) mbar_arrive(bar_pefree + 8 * s);   // its MMAs were the last readers of this fill of the staged block
 
         if (L.epi == TC_EPI_RGB) {
           if (hf == 0) {
@@ -333,7 +340,22 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((4 + 2 * EW) * 32, 1
             tmem_ld_wait();
             alpha = __uint_as_float(v[0]) + bias_s[0];
           }
-          if (l + 1 == P.dir_layer) mbar_wait(bar_peready + 8 * s, (uint32_t)(j * ppt + 1) & 1u);   // the view-direction encoding is in place
+          wait_fill_for(l + 1, j);
+          signal_ready();
+        } else if (L.epi == TC_EPI_CONT) {
+          // partial sums stay in the accumulator (the next layer continues them, TC_F_ACCUM); only the hand-over
+          tcgen05_fence_before();
+          wait_fill_for(l + 1, j);
+          signal_ready();
+        } else if (L.epi == TC_EPI_STAGE) {
+          // deformation output (DEC:299), + bias, no activation: columns 0..63 = PE' replace the encoding in the staged block, columns 64..127
+          // = signal' go to hidden block 3 (read by fc_in_torso) and, as a byte image of the block, to the scratch the IN1 fill copies back
+          for (int b = hf * (2 / NH); b < (hf + 1) * (2 / NH); ++b) {
+            uint8_t* dst = b == 0 ? arena + (size_t)TC_KB_PE * KB_BYTES : arena + (size_t)3 * KB_BYTES;
+            uint8_t* gdst = b == 0 ? nullptr : P.scratch + ((size_t)blockIdx.x * 2 + s) * KB_BYTES;
+            epilogue_stage_cd<F16>(acc + (uint32_t)b * 64u, smem_u32(bias_s) + (uint32_t)b * 256u, dst, gdst, (uint32_t)((warp & 3) * 32), (uint32_t)lane);
+          }
+          wait_fill_for(l + 1, j);
           signal_ready();
         } else {
           if (L.epi == TC_EPI_VIEW0) {
@@ -352,7 +374,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((4 + 2 * EW) * 32, 1
             const int per = (int)L.n / NH;
             epilogue_relu_rows16<false, F16>(acc, hf * per, (hf + 1) * per, nullptr, smem_u32(bias_s), arena, row);
           }
-          if (l + 1 == P.dir_layer) mbar_wait(bar_peready + 8 * s, (uint32_t)(j * ppt + 1) & 1u);   // the view-direction encoding is in place
+          wait_fill_for(l + 1, j);
           signal_ready();
         }
         if (tr) {
@@ -378,35 +400,43 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((4 + 2 * EW) * 32, 1
     // x = o + d*z -> [x | sin(2^k x) | cos(2^k x)] (HELP:42-52, pe.cuh) for the NEXT tile of each slot, written straight
     // into the slot's PE K-block as soon as the last layer that reads it (the skip layer) has finished its MMAs.
     const int t = (warp - 2) * 32 + lane;
-    const int ppt = P.dir_layer >= 0 ? 2 : 1;
+    const int nf = P.n_fills;
     for (int j = 0; j < n_iter; ++j) {
-      for (int ph = 0; ph < ppt; ++ph) {        // 0: the tile's positional encoding; 1 (Decoder): its view-direction encoding
+      for (int k = 0; k < nf; ++k) {
         for (int s = 0; s < NSLOT; ++s) {
           if (group_of(j, s) >= n_groups) continue;
-          const int fill = j * ppt + ph;         // fills of this slot's staged block so far
+          const int fill = j * nf + k;         // fills of this slot's staged block so far
           if (fill > 0) mbar_wait(bar_pefree + 8 * s, (uint32_t)(fill - 1) & 1u);
           uint8_t* pe_blk = smem + (size_t)(s * TC_KB_PER_TILE + TC_KB_PE) * KB_BYTES;
           const int tile = 2 * group_of(j, s) + (int)crank;
+          if (P.fill_kb[k] == TC_KB_IN1) {
+            // the deformed signal written by this tile's TC_EPI_STAGE epilogue: a byte image of the block
+            const uint4* src = reinterpret_cast<const uint4*>(P.scratch + ((size_t)blockIdx.x * 2 + s) * KB_BYTES);
+            uint4* dst = reinterpret_cast<uint4*>(pe_blk);
+#pragma unroll 4
+            for (int i = t; i < KB_BYTES / 16; i += PE_HELPERS) dst[i] = src[i];
+          } else {
 #pragma unroll 1
-          for (int h = 0; h < 2; ++h) {
-            const uint32_t row = (uint32_t)(t + 64 * h);
-            int64_t pt = (int64_t)tile * TILE_M + row;
-            if (pt >= P.n_points) pt = P.n_points - 1;
-            const int64_t ray = pt / P.S;
-            float pe[64], x[3];
-            if (ph == 1) {
-              pe_decoder_viewdir(P.rays_d, ray, P.multires_views, pe);
-            } else {
-              sample_point(P.rays_o, P.rays_d, ray, P.z_vals[pt], x);
-              if (P.dec) pe_decoder(x, P.multires, pe);
-              else pe_embedder(x, P.multires, pe);
-            }
+            for (int h = 0; h < 2; ++h) {
+              const uint32_t row = (uint32_t)(t + 64 * h);
+              int64_t pt = (int64_t)tile * TILE_M + row;
+              if (pt >= P.n_points) pt = P.n_points - 1;
+              const int64_t ray = pt / P.S;
+              float pe[64], x[3];
+              if (P.fill_kb[k] == TC_KB_DIR) {
+                pe_decoder_viewdir(P.rays_d, ray, P.multires_views, pe);
+              } else {
+                sample_point(P.rays_o, P.rays_d, ray, P.z_vals[pt], x);
+                if (P.dec) pe_decoder(x, P.multires, pe);
+                else pe_embedder(x, P.multires, pe);
+              }
 #pragma unroll
-            for (int ch = 0; ch < 8; ++ch) {
-              float o[8];
+              for (int ch = 0; ch < 8; ++ch) {
+                float o[8];
 #pragma unroll
-              for (int e = 0; e < 8; ++e) o[e] = pe[ch * 8 + e];
-              store_chunk<false, F16>(pe_blk, pe_blk, row, (uint32_t)ch, o);
+                for (int e = 0; e < 8; ++e) o[e] = pe[ch * 8 + e];
+                store_chunk<false, F16>(pe_blk, pe_blk, row, (uint32_t)ch, o);
+              }
             }
           }
           fence_proxy_async();
@@ -433,8 +463,8 @@ int pair_get_flags() { return g_pair_flags; }
 // prog: layer program; woff2 / w: per-layer offsets into, and the blob of, the CTA-pair stage images (tc_pack.h); decoder: the head
 // program of the live model (mlp_dec.cu).
 int pair_launch_prog(const TcProgram& prog, const uint32_t* woff2, const uint8_t* w, bool f16, bool decoder, int multires, int multires_views,
-                     int view_w, const float* bias_ws, const float* vbias_ws, int64_t R, int S, const float* rays_o, const float* rays_d,
-                     const float* z_vals, float* raw, cudaStream_t st) {
+                     int view_w, const float* bias_ws, const float* vbias_ws, void* scratch, int64_t R, int S, const float* rays_o,
+                     const float* rays_d, const float* z_vals, float* raw, cudaStream_t st) {
   tcp::Params P;
   memset(&P, 0, sizeof(P));
   P.w = w;
@@ -452,27 +482,52 @@ int pair_launch_prog(const TcProgram& prog, const uint32_t* woff2, const uint8_t
   P.multires_views = multires_views;
   P.view_w = view_w;
   P.dec = decoder ? 1 : 0;
-  P.dir_layer = -1;
+  P.scratch = reinterpret_cast<uint8_t*>(scratch);
   tc_get_trace(reinterpret_cast<void**>(&P.trace), &P.trace_tiles);
   P.flags = g_pair_flags;
+  int use[7], rel[7];
+  for (int k = 0; k < 7; ++k) use[k] = rel[k] = -1;
   for (int i = 0; i < prog.n_layers; ++i) {
     P.layers[i] = prog.layers[i];
     P.layers[i].woff = woff2[i];
     const TcLayer& L = prog.layers[i];
-    bool ok = L.epi == TC_EPI_RELU || L.epi == TC_EPI_RGB || (!decoder && L.epi == TC_EPI_VIEW0) || (decoder && L.epi == TC_EPI_SIGMA);
-    if (L.flags != 0 || L.nkb > 5) ok = false;
-    for (int k = 0; k < L.nkb; ++k) {
-      if (L.kb[k] == TC_KB_DIR) {
-        if (!decoder || P.dir_layer >= 0 || i == 0) ok = false;
-        P.dir_layer = i;
-      } else if (L.kb[k] > TC_KB_PE) {
-        ok = false;
+    bool ok = L.epi == TC_EPI_RELU || L.epi == TC_EPI_RGB || (!decoder && L.epi == TC_EPI_VIEW0) ||
+              (decoder && (L.epi == TC_EPI_SIGMA || L.epi == TC_EPI_CONT || (L.epi == TC_EPI_STAGE && L.n == 128 && scratch != nullptr)));
+    if ((L.flags & ~TC_F_ACCUM) != 0 || L.nkb > 5) ok = false;
+    if ((L.flags & TC_F_ACCUM) && (i == 0 || prog.layers[i - 1].epi != TC_EPI_CONT)) ok = false;
+    if (L.epi == TC_EPI_CONT && (i + 1 >= prog.n_layers || !(prog.layers[i + 1].flags & TC_F_ACCUM) || prog.layers[i + 1].n != L.n)) ok = false;
+    for (int k = 0; k < L.nkb; ++k)
+      if (L.kb[k] >= TC_KB_PE) {
+        if (L.kb[k] > TC_KB_DIR || (!decoder && L.kb[k] != TC_KB_PE)) ok = false;
+        else {
+          if (use[L.kb[k]] < 0) use[L.kb[k]] = i;
+          rel[L.kb[k]] = i;
+        }
       }
-    }
     if (!ok) {
       set_error("pair_launch_prog: layer %d of the program is outside what the CTA-pair kernel runs", i);
       return DFN_E_UNSUPPORTED;
     }
+  }
+  // fills of the staged block in the order of their first use; each must be dead before the next one is first read
+  P.n_fills = 0;
+  for (int round = 0; round < 3; ++round) {
+    int best = -1;
+    for (int kb = TC_KB_PE; kb <= TC_KB_DIR; ++kb)
+      if (use[kb] >= 0 && (best < 0 || use[kb] < use[best])) best = kb;
+    if (best < 0) break;
+    P.fill_kb[P.n_fills] = best;
+    P.fill_use[P.n_fills] = use[best];
+    P.fill_rel[P.n_fills] = rel[best];
+    ++P.n_fills;
+    use[best] = -1;
+  }
+  bool fills_ok = P.n_fills >= 1 && P.fill_kb[0] == TC_KB_PE && P.fill_use[0] == 0;
+  for (int k = 1; k < P.n_fills; ++k)
+    if (P.fill_rel[k - 1] >= P.fill_use[k] || P.fill_use[k] < 1) fills_ok = false;
+  if (!fills_ok) {
+    set_error("pair_launch_prog: the program's staged inputs do not take turns in one block");
+    return DFN_E_UNSUPPORTED;
   }
   int grid = P.n_tiles < num_sms() ? P.n_tiles : num_sms();
   grid = (grid + 1) & ~1;
@@ -495,7 +550,7 @@ int pair_launch(const dfn_model* m, const float* bias_ws, const float* vbias_ws,
     return DFN_E_UNSUPPORTED;
   }
   return pair_launch_prog(m->prog, m->tc2_woff, f16 ? m->tc2_h16 : m->tc2_hi, f16, false, m->desc.multires, m->desc.multires_views,
-                          m->desc.W / 2, bias_ws, vbias_ws, R, S, rays_o, rays_d, z_vals, raw, st);
+                          m->desc.W / 2, bias_ws, vbias_ws, nullptr, R, S, rays_o, rays_d, z_vals, raw, st);
 }
 
 }  // namespace dfn

@@ -218,6 +218,36 @@ __device__ __forceinline__ void epilogue_relu_cd(uint32_t acc, int kb_begin, int
   }
 }
 
+// TC_EPI_STAGE on the column-distributed layout: one 64-column block of the accumulator (acc: lane quarter + first column of the block)
+// + bias, NO activation -> 16-bit pairs into the block `dst` (shared memory) and, when gdst != nullptr, into a byte image of the block
+// in global memory.
+template <bool F16>
+__device__ __forceinline__ void epilogue_stage_cd(uint32_t acc, uint32_t sbias, uint8_t* dst, uint8_t* gdst, uint32_t row0, uint32_t lane) {
+  const uint32_t r = row0 + (lane >> 2);
+  const uint32_t sub = (lane & 3u) * 4u;
+  float b[16];
+#pragma unroll
+  for (int g = 0; g < 8; ++g)
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(b[2 * g]), "=f"(b[2 * g + 1]) : "r"(sbias + (uint32_t)(g * 8 + 2 * (int)(lane & 3u)) * 4u));
+  uint32_t v[32];
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    tmem_ld_16x256b_x8(acc + ((uint32_t)(16 * half) << 16), v);
+    tmem_ld_wait();
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const float x0 = __uint_as_float(v[4 * g + 2 * h]) + b[2 * g], x1 = __uint_as_float(v[4 * g + 2 * h + 1]) + b[2 * g + 1];
+        const uint32_t p = F16 ? pack_f16(x0, x1) : pack_bf16(x0, x1);
+        const uint32_t off = swz(r + (uint32_t)(16 * half + 8 * h), (uint32_t)g) + sub;
+        *reinterpret_cast<uint32_t*>(dst + off) = p;
+        if (gdst != nullptr) *reinterpret_cast<uint32_t*>(gdst + off) = p;
+      }
+    }
+  }
+}
+
 // Row-per-thread epilogue over columns [c_begin, c_end) (multiples of 32) with 16-column TMEM loads, the next one in flight (32 data
 // registers): the per-ray-bias layer (GLOBAL_BIAS: every row has its own bias row in global memory) in the 96-register kernels.
 template <bool GLOBAL_BIAS, bool F16>

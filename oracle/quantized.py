@@ -139,6 +139,7 @@ def run_program_q(layers, weights, bias, blocks_in, dtype, fold_bias=None, dot_w
         if L.epi == EPI_STAGE:
             o = rnd(acc + b, dtype)
             blocks[KB_PE], blocks[KB_IN1] = o[:, :64].clone(), o[:, 64:128].clone()
+            blocks[3] = o[:, 64:128].clone()      # mlp_pair.cu also leaves signal' in hidden block 3 (read by the one-layer fc_in_torso)
             continue
         if L.epi == EPI_RGB:
             col = acc[:, :3] + b[:3]

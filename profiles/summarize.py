@@ -119,15 +119,16 @@ else:
     report('bench_pair', 'mlp_pair_kernel<bf16> (CTA pairs, cta_group::2; the default since this round): the bench frame\'s coarse (202,500 x 64) and fine (202,500 x 192) launches')
     report('bench_bf16', 'mlp_tc_kernel<bf16> (1-CTA generation, the default until this round): the bench frame\'s coarse (202,500 x 64) and fine (202,500 x 192) launches')
     report('bench_x3', 'mlp_pp_kernel<bf16x3>: the bench frame\'s coarse and fine launches')
-    report('bench_dec', 'mlp_pp_kernel<bf16, Decoder>: the head_torso frame\'s head and torso launches (202,500 x 64 each)')
+    report('bench_dec', 'mlp_pair_kernel<bf16> running the Decoder programs: the head_torso frame\'s head and torso launches (202,500 x 64 each)')
+    report('bench_dec_x3', 'mlp_pp_kernel<bf16x3, Decoder>: the head_torso frame\'s head and torso launches in the split precision')
     report('embed', 'embed_kernel (dfn_embed, HELP:21-52): 12.96 M points -> [P,63] (12 B in + 252 B out per point)')
     report('stages', 'HBM-bound stage kernels of the bench frame')
     report('gemm', 'gemm_tc_kernel (training step GEMMs)')
     traffic('bench_pair', 'mlp_pair_kernel<bf16>', [frame * 64, frame * 192], also=('mlp_pair_kernel<fp16>',))
     traffic('bench_bf16', 'mlp_tc_kernel<bf16>', [frame * 64, frame * 192], also=('mlp_tc_kernel<fp16>',))
     traffic('bench_x3', 'mlp_pp_kernel<bf16x3>', [frame * 64, frame * 192])
-    traffic('bench_dec', 'mlp_pp_kernel<bf16, Decoder>', [frame * 64, frame * 64],
-            also=('mlp_pp_kernel<fp16, Decoder>', 'mlp_pp_kernel<bf16x3, Decoder>'))
+    traffic('bench_dec', 'mlp_pair_kernel<bf16, Decoder>', [frame * 64, frame * 64], also=('mlp_pair_kernel<fp16, Decoder>',))
+    traffic('bench_dec_x3', 'mlp_pp_kernel<bf16x3, Decoder>', [frame * 64, frame * 64])
     if TRAFFIC:
         import json
         old = {}
