@@ -59,7 +59,7 @@ struct dfn_decoder {
   bool loaded = false;
   dfn::DecField f[2];        // 0 head, 1 torso: plain programs (bf16x3)
   dfn::DecField g[2];        // the same fields with sigma_out folded into an epilogue (bf16 / fp16)
-  dfn::DecField tp;          // the torso field's plain program in the layout of the CTA-pair kernel (fc_in_torso as one layer)
+  dfn::DecField tp;          // the torso field's folded-head program in the layout of the CTA-pair kernel (fc_in_torso as one layer)
 };
 
 namespace dfn {
@@ -459,9 +459,9 @@ static int dec_query(const dfn_decoder* m, int field, int64_t R, int S, const fl
     set_error("dfn_decoder_query: workspace %lld < %lld bytes", (long long)workspace_bytes, (long long)dec_workspace_bytes(m, R));
     return DFN_E_WORKSPACE;
   }
-  // split precision: the plain programs on mlp_pp.cu; single-pass: the plain programs on the CTA-pair kernel (mlp_pair.cu; the torso's in
-  // its own layout), or -- debug flags 8 / 16, hidden != 256 -- the folded-head programs on mlp_pp.cu
-  const DecField& P2 = field == 0 ? m->f[0] : m->tp;
+  // split precision: the plain programs on mlp_pp.cu; single-pass: the folded-head programs on the CTA-pair kernel (mlp_pair.cu; the
+  // torso's in its own layout), or -- debug flags 8 / 16, hidden != 256 -- on mlp_pp.cu
+  const DecField& P2 = field == 0 ? m->g[0] : m->tp;
   const bool on_pair = precision != DFN_PREC_BF16X3 && P2.w2_hi != nullptr && !(pair_get_flags() & (field == 0 ? 8 : 16));
   const DecField& F = on_pair ? P2 : (precision == DFN_PREC_BF16X3 ? m->f[field] : m->g[field]);
   const dfn_decoder_desc& d = m->desc;
@@ -481,7 +481,7 @@ static int dec_query(const dfn_decoder* m, int field, int64_t R, int S, const fl
   DFN_LAUNCH_CHECK();
   const bool prof = profile_begin(st, F.macs_pt * (double)R * S);
   int rc = on_pair ? pair_launch_prog(F.prog, F.woff2, precision == DFN_PREC_FP16 ? F.w2_h16 : F.w2_hi, precision == DFN_PREC_FP16, true, d.n_freq,
-                                      d.n_freq_views, d.hidden, bias_ws, nullptr, scratch, R, S, rays_o, rays_d, z_vals, raw, st)
+                                      d.n_freq_views, d.hidden, bias_ws, nullptr, F.dot_w, scratch, R, S, rays_o, rays_d, z_vals, raw, st)
                    : pp_launch_prog(F.prog, F.woff32, precision == DFN_PREC_FP16 ? F.w_h16 : F.w_hi, F.w_lo, F.dot_w, true, d.n_freq, d.n_freq_views,
                                     d.hidden, bias_ws, nullptr, scratch, R, S, rays_o, rays_d, z_vals, raw, precision, st);
   if (prof) profile_end(st);
@@ -545,7 +545,7 @@ extern "C" int dfn_decoder_load(dfn_decoder* m, const float* const* t, int n_ten
     B.pk.want2 = true;
     B.pair_layout = true;
     build_deform(B, T, d);
-    build_trunk(B, T, d, true, dt, dt + d.z_dim, false);
+    build_trunk(B, T, d, true, dt, dt + d.z_dim, true);
     int rc = B.upload(st);
     if (rc) return rc;
   }
@@ -553,7 +553,7 @@ extern "C" int dfn_decoder_load(dfn_decoder* m, const float* const* t, int n_ten
     DecField* F = folded ? m->g : m->f;
     {
       Builder B(&F[0], d.dim_signal + 2 * d.z_dim);
-      B.pk.want2 = folded == 0 && d.hidden == 256;   // the head's plain program also runs on the CTA-pair kernel (single-pass precisions)
+      B.pk.want2 = folded == 1 && d.hidden == 256;   // the head's folded-head program runs on the CTA-pair kernel (single-pass precisions)
       build_trunk(B, T, d, false, d.dim_signal, d.dim_signal + d.z_dim, folded != 0);
       int rc = B.upload(st);
       if (rc) return rc;
@@ -579,7 +579,7 @@ extern "C" int dfn_decoder_program_host(const dfn_decoder_desc* desc, const floa
                 "dfn_decoder_program_host: null argument");
   DFN_CHECK_ARG(n_tensors == 2 * T_COUNT && (field == 0 || field == 1) && max_layers >= TC_MAX_LAYERS,
                 "dfn_decoder_program_host: expected %d tensors, field 0|1, max_layers >= %d", 2 * T_COUNT, TC_MAX_LAYERS);
-  DFN_CHECK_ARG(folded_heads != 1 || dot_w, "dfn_decoder_program_host: dot_w is required for the folded-head program");
+  DFN_CHECK_ARG((folded_heads != 1 && folded_heads != 3) || dot_w, "dfn_decoder_program_host: dot_w is required for the folded-head program");
   DFN_CHECK_ARG(desc->hidden == 256 && desc->n_blocks == 8 && desc->skip == 4 && desc->n_freq >= 1 && desc->n_freq <= 10 &&
                     desc->dim_et_embed >= 1 && desc->dim_et_embed <= 64,
                 "dfn_decoder_program_host: unsupported decoder shape");
@@ -589,10 +589,11 @@ extern "C" int dfn_decoder_program_host(const dfn_decoder_desc* desc, const floa
   Builder B(&F, dsig + 2 * desc->z_dim);
   std::vector<float> dense;
   B.pk.dense = &dense;
-  B.pair_layout = folded_heads == 2;   // the plain program in the layout mlp_pair.cu runs (torso: fc_in_torso as one layer)
+  B.pair_layout = folded_heads >= 2;   // 2 / 3: the plain / folded-head program in the layout mlp_pair.cu runs (torso: fc_in_torso as one layer)
+  const bool fold = folded_heads == 1 || folded_heads == 3;
   if (field == 1) build_deform(B, T, *desc);
-  build_trunk(B, T, *desc, field == 1, dsig, dsig + desc->z_dim, folded_heads == 1);
-  if (folded_heads == 1) memcpy(dot_w, B.dot.data(), B.dot.size() * 4);
+  build_trunk(B, T, *desc, field == 1, dsig, dsig + desc->z_dim, fold);
+  if (fold) memcpy(dot_w, B.dot.data(), B.dot.size() * 4);
   *n_layers = B.nl;
   for (int l = 0; l < B.nl; ++l) {
     const TcLayer& L = F.prog.layers[l];

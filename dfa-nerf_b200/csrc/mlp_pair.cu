@@ -48,7 +48,8 @@ static constexpr int ARENA_BLOCKS = 2 * TC_KB_PER_TILE;
 static constexpr int SMEM_RING = ARENA_BLOCKS * KB_BYTES;
 static constexpr int SMEM_BIAS = SMEM_RING + N_ENT * ENT_BYTES;
 static constexpr int SMEM_BAR = SMEM_BIAS + 2 * TC_BIAS_STRIDE * 4;
-static constexpr int SMEM_TOTAL = SMEM_BAR + 256;
+static constexpr int SMEM_DOT = SMEM_BAR + 256;    // Decoder: the folded density head's row as packed 16-bit pairs (512 bytes)
+static constexpr int SMEM_TOTAL = SMEM_DOT + 512;
 static_assert(SMEM_TOTAL <= 227 * 1024, "shared memory budget");
 
 struct Params {
@@ -75,6 +76,7 @@ struct Params {
   // view-direction encoding, computed), is first read by layer fill_use[k] and dead once the MMAs of layer fill_rel[k] have completed.
   int n_fills;
   int fill_kb[3], fill_use[3], fill_rel[3];
+  const float* dot_w;         // Decoder: density head folded into the last block's epilogue (TC_F_DOT_SIGMA): row [256] + bias, or null
   uint8_t* scratch;           // torso field: [grid][2 slots] byte images of the deformed-signal block (TC_EPI_STAGE writes, fill IN1 reads)
   TcLayer layers[TC_MAX_LAYERS];
 };
@@ -132,6 +134,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((4 + 2 * EW) * 32, 1
 
   // tile group g = (j*C + c)*NSLOT + s holds tiles 2g (leader) and 2g+1 (peer); a tile index past the end is computed
   // on a clamped point and not stored.
+  if (P.dot_w != nullptr) {   // (ordered before its first use by the barriers every tile passes)
+    for (int i = threadIdx.x; i < 128; i += blockDim.x) {
+      const float2 w2 = reinterpret_cast<const float2*>(P.dot_w)[i];
+      reinterpret_cast<uint32_t*>(smem + SMEM_DOT)[i] = F16 ? pack_f16(w2.x, w2.y) : pack_bf16(w2.x, w2.y);
+    }
+    __syncthreads();
+  }
   const int C = gridDim.x >> 1, c = (int)blockIdx.x >> 1;
   const int n_groups = (P.n_tiles + 1) >> 1;
   const int n_local = c * NSLOT < n_groups ? (n_groups - c * NSLOT + C * NSLOT - 1) / (C * NSLOT) * NSLOT : 0;
@@ -300,6 +309,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((4 + 2 * EW) * 32, 1
 
       float alpha = 0.f;
       for (int l = 0; l < P.n_layers; ++l) {
+        const bool dot_next_rgb = P.dot_w != nullptr && NH == 2 && l + 1 < P.n_layers && P.layers[l + 1].epi == TC_EPI_RGB;
         const TcLayer& L = P.layers[l];
         const bool tr = P.trace != nullptr && blockIdx.x == 0 && tid_s == 0 && j < P.trace_tiles;
         long long t_e0 = 0, t_e1 = 0;
@@ -327,7 +337,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((4 + 2 * EW) * 32, 1
                 o.y = __fdividef(1.f, 1.f + __expf(-o.y));
                 o.z = __fdividef(1.f, 1.f + __expf(-o.z));
               }
-              o.w = alpha;
+              // folded density head: this thread's column part + the other part (left in the bias staging area by its thread) + bias
+              o.w = P.dot_w != nullptr ? alpha + (NH == 2 ? bias_s[128 + row] : 0.f) + __ldg(P.dot_w + TC_BIAS_STRIDE) : alpha;
               reinterpret_cast<float4*>(P.raw)[pt] = o;
             }
           }
@@ -367,6 +378,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((4 + 2 * EW) * 32, 1
               tmem_ld_wait();
               alpha = __uint_as_float(v[0]) + bias_s[P.view_w];
             }
+          } else if (L.flags & TC_F_DOT_SIGMA) {
+            // last trunk block + sigma_out (DEC:329): the density from the layer's fp32 activations, this warp's columns' part
+            const int per = ((int)L.n >> 6) / NH;
+            alpha = epilogue_relu_cd_dotpart<F16>(acc, hf * per, (hf + 1) * per, smem_u32(bias_s), sbase + SMEM_DOT, arena,
+                                                  (uint32_t)((warp & 3) * 32), (uint32_t)lane);
           } else if ((L.n % (64 * NH)) == 0) {
             const int per = ((int)L.n >> 6) / NH;
             epilogue_relu_cd<F16, EW == 4>(acc, hf * per, (hf + 1) * per, smem_u32(bias_s), arena, (uint32_t)((warp & 3) * 32), (uint32_t)lane);
@@ -387,7 +403,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((4 + 2 * EW) * 32, 1
         // swap in the next layer's bias
         if (l + 1 < P.n_layers) {
           named_bar_sync(1 + s, ETH);
-          stage_bias(P.bias + (l + 1) * TC_BIAS_STRIDE);
+          if (dot_next_rgb && hf == 1) bias_s[tid_s] = alpha;     // tid_s = 128 + row: the second column part of the row's density
+          else stage_bias(P.bias + (l + 1) * TC_BIAS_STRIDE);
           named_bar_sync(1 + s, ETH);
         }
       }
@@ -463,8 +480,8 @@ int pair_get_flags() { return g_pair_flags; }
 // prog: layer program; woff2 / w: per-layer offsets into, and the blob of, the CTA-pair stage images (tc_pack.h); decoder: the head
 // program of the live model (mlp_dec.cu).
 int pair_launch_prog(const TcProgram& prog, const uint32_t* woff2, const uint8_t* w, bool f16, bool decoder, int multires, int multires_views,
-                     int view_w, const float* bias_ws, const float* vbias_ws, void* scratch, int64_t R, int S, const float* rays_o,
-                     const float* rays_d, const float* z_vals, float* raw, cudaStream_t st) {
+                     int view_w, const float* bias_ws, const float* vbias_ws, const float* dot_w, void* scratch, int64_t R, int S,
+                     const float* rays_o, const float* rays_d, const float* z_vals, float* raw, cudaStream_t st) {
   tcp::Params P;
   memset(&P, 0, sizeof(P));
   P.w = w;
@@ -483,6 +500,7 @@ int pair_launch_prog(const TcProgram& prog, const uint32_t* woff2, const uint8_t
   P.view_w = view_w;
   P.dec = decoder ? 1 : 0;
   P.scratch = reinterpret_cast<uint8_t*>(scratch);
+  P.dot_w = nullptr;
   tc_get_trace(reinterpret_cast<void**>(&P.trace), &P.trace_tiles);
   P.flags = g_pair_flags;
   int use[7], rel[7];
@@ -493,7 +511,11 @@ int pair_launch_prog(const TcProgram& prog, const uint32_t* woff2, const uint8_t
     const TcLayer& L = prog.layers[i];
     bool ok = L.epi == TC_EPI_RELU || L.epi == TC_EPI_RGB || (!decoder && L.epi == TC_EPI_VIEW0) ||
               (decoder && (L.epi == TC_EPI_SIGMA || L.epi == TC_EPI_CONT || (L.epi == TC_EPI_STAGE && L.n == 128 && scratch != nullptr)));
-    if ((L.flags & ~TC_F_ACCUM) != 0 || L.nkb > 5) ok = false;
+    if (L.flags & TC_F_DOT_SIGMA) {
+      if (!decoder || dot_w == nullptr || L.epi != TC_EPI_RELU || L.n != 256 || P.dot_w != nullptr) ok = false;
+      P.dot_w = dot_w;
+    }
+    if ((L.flags & ~(TC_F_ACCUM | TC_F_DOT_SIGMA)) != 0 || L.nkb > 5) ok = false;
     if ((L.flags & TC_F_ACCUM) && (i == 0 || prog.layers[i - 1].epi != TC_EPI_CONT)) ok = false;
     if (L.epi == TC_EPI_CONT && (i + 1 >= prog.n_layers || !(prog.layers[i + 1].flags & TC_F_ACCUM) || prog.layers[i + 1].n != L.n)) ok = false;
     for (int k = 0; k < L.nkb; ++k)
@@ -550,7 +572,7 @@ int pair_launch(const dfn_model* m, const float* bias_ws, const float* vbias_ws,
     return DFN_E_UNSUPPORTED;
   }
   return pair_launch_prog(m->prog, m->tc2_woff, f16 ? m->tc2_h16 : m->tc2_hi, f16, false, m->desc.multires, m->desc.multires_views,
-                          m->desc.W / 2, bias_ws, vbias_ws, nullptr, R, S, rays_o, rays_d, z_vals, raw, st);
+                          m->desc.W / 2, bias_ws, vbias_ws, nullptr, nullptr, R, S, rays_o, rays_d, z_vals, raw, st);
 }
 
 }  // namespace dfn

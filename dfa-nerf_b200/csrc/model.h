@@ -112,8 +112,8 @@ int pp_launch(const dfn_model* m, const float* bias_ws, const float* vbias_ws, v
 int pair_launch(const dfn_model* m, const float* bias_ws, const float* vbias_ws, int64_t R, int S, const float* rays_o,
                 const float* rays_d, const float* z_vals, float* raw, int precision, cudaStream_t st);
 int pair_launch_prog(const TcProgram& prog, const uint32_t* woff2, const uint8_t* w, bool f16, bool decoder, int multires, int multires_views,
-                     int view_w, const float* bias_ws, const float* vbias_ws, void* scratch, int64_t R, int S, const float* rays_o,
-                     const float* rays_d, const float* z_vals, float* raw, cudaStream_t st);
+                     int view_w, const float* bias_ws, const float* vbias_ws, const float* dot_w, void* scratch, int64_t R, int S,
+                     const float* rays_o, const float* rays_d, const float* z_vals, float* raw, cudaStream_t st);
 void pair_set_epilogue_warps(int ew);
 int pair_get_flags();
 void pair_set_flags(int flags);

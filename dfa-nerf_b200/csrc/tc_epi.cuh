@@ -218,6 +218,53 @@ __device__ __forceinline__ void epilogue_relu_cd(uint32_t acc, int kb_begin, int
   }
 }
 
+// Column-distributed epilogue of a ReLU layer that also evaluates a folded density head (TC_F_DOT_SIGMA, Decoder single-pass programs):
+// K-blocks [kb_begin, kb_end) as epilogue_relu_cd, plus dot = sum_c relu(v + b)[c] * w[c] over THESE columns on the fp32 activations,
+// w = the head row as packed 16-bit pairs in shared memory (sdot).  Returns the partial dot product of row row0 + lane (the row this
+// thread owns in the row-per-thread epilogues); the caller adds the other column parts and the head's bias.
+template <bool F16>
+__device__ __forceinline__ float epilogue_relu_cd_dotpart(uint32_t acc, int kb_begin, int kb_end, uint32_t sbias, uint32_t sdot, uint8_t* arena_hi,
+                                                          uint32_t row0, uint32_t lane) {
+  const uint32_t r = row0 + (lane >> 2);
+  const uint32_t sub = (lane & 3u) * 4u;
+  float d[4] = {0.f, 0.f, 0.f, 0.f};   // rows r, r + 8, r + 16, r + 24
+  uint32_t v[32];
+  for (int kb = kb_begin; kb < kb_end; ++kb) {
+    uint8_t* blk = arena_hi + (size_t)kb * KB_BYTES;
+    const uint32_t c0 = (uint32_t)(kb * 64) + 2u * (lane & 3u);
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      tmem_ld_16x256b_x8(acc + ((uint32_t)(16 * half) << 16) + (uint32_t)kb * 64u, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int g = 0; g < 8; ++g) {
+        float b0, b1, w0, w1;
+        uint32_t wp;
+        asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(b0), "=f"(b1) : "r"(sbias + (c0 + (uint32_t)g * 8u) * 4u));
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(wp) : "r"(sdot + (c0 + (uint32_t)g * 8u) * 2u));
+        unpack_h2<F16>(wp, w0, w1);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const float x0 = fmaxf(__uint_as_float(v[4 * g + 2 * h]) + b0, 0.f);
+          const float x1 = fmaxf(__uint_as_float(v[4 * g + 2 * h + 1]) + b1, 0.f);
+          d[2 * half + h] = fmaf(x1, w1, fmaf(x0, w0, d[2 * half + h]));
+          *reinterpret_cast<uint32_t*>(blk + swz(r + (uint32_t)(16 * half + 8 * h), (uint32_t)g) + sub) = F16 ? pack_f16(x0, x1) : pack_bf16(x0, x1);
+        }
+      }
+    }
+  }
+  float out = 0.f;
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+    float t = d[a];
+    t += __shfl_xor_sync(0xffffffffu, t, 1);
+    t += __shfl_xor_sync(0xffffffffu, t, 2);
+    t = __shfl_sync(0xffffffffu, t, (int)((lane & 7u) << 2));   // row (lane % 8) + 8 a lives in quad lane % 8
+    if ((lane >> 3) == (uint32_t)a) out = t;
+  }
+  return out;
+}
+
 // TC_EPI_STAGE on the column-distributed layout: one 64-column block of the accumulator (acc: lane quarter + first column of the block)
 // + bias, NO activation -> 16-bit pairs into the block `dst` (shared memory) and, when gdst != nullptr, into a byte image of the block
 // in global memory.

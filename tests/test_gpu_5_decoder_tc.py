@@ -97,9 +97,9 @@ def test_decoder_query_single_pass_vs_quantized_program(dfn, prec_name, which, R
     f, s = dec.query_rays(ro.to(DEV), rd.to(DEV), z.to(DEV), zs.to(DEV), za.to(DEV), sig.to(DEV), which, precision=prec)
     assert torch.isfinite(f).all() and torch.isfinite(s).all()
     rf, rs = _oracle(sd, ro, rd, z, zs, za, sig, which)
-    # the single-pass path runs the PLAIN programs (sigma_out as a 16-column layer) on the CTA-pair kernel; the torso's there has fc_in_torso as
-    # one layer instead of two accumulate-chained halves -- the same sums of the same rounded operands
-    layers, weights, bias, folds, dimL, view_layer, dot_w = dump_program(sd, 0 if which == 'head' else 1, 0)
+    # the single-pass path runs the folded-head programs on the CTA-pair kernel; the torso's there (mode 3) has fc_in_torso as one layer
+    # instead of two accumulate-chained halves -- the same sums of the same rounded operands
+    layers, weights, bias, folds, dimL, view_layer, dot_w = dump_program(sd, 0 if which == 'head' else 1, 1 if which == 'head' else 3)
     latent = torch.cat([sig.reshape(-1), zs.reshape(-1), za.reshape(-1)])
     fold = {l: (torch.as_tensor(fw).double().t() @ latent.double()).float() for l, fw in folds.items()}
     p = (ro[:, None, :] + rd[:, None, :] * z[:, :, None]).reshape(1, -1, 3)
