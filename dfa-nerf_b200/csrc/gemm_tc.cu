@@ -50,6 +50,13 @@ __device__ __forceinline__ float mask_factor(int mode, float y) {
   if (mode == DFN_MASK_LEAKY) return y > 0.f ? 1.f : 0.02f;
   return y * (1.f - y);   // DFN_MASK_SIGMOID: y is the sigmoid's output
 }
+// the same without control flow (selects on the uniform mode): the loaders issue all of a half-chunk's loads before the first use --
+// with mask_factor's branches every mask load sat in its own basic block and paid its own memory latency (a 64-wide K chunk of the
+// weight-gradient GEMM took 63,000 cycles)
+__device__ __forceinline__ float mask_factor_sel(bool sig, float lo, float y) {
+  const float step = y > 0.f ? 1.f : lo;
+  return sig ? y * (1.f - y) : step;
+}
 
 // 32 consecutive k of one operand row -> registers (zero outside the matrix), optionally times act'(mask)
 __device__ __forceinline__ void fetch32(const float* __restrict__ src, const float* __restrict__ msk, int mmode, int64_t row_off,
@@ -60,6 +67,8 @@ __device__ __forceinline__ void fetch32(const float* __restrict__ src, const flo
     return;
   }
   const float* p = src + row_off;
+  const bool sig = mmode == DFN_MASK_SIGMOID;
+  const float lo = mmode == DFN_MASK_LEAKY ? 0.02f : 0.f;
   if (ld_k == 1 && k0 + 32 <= K && ((reinterpret_cast<uintptr_t>(p + k0) & 15) == 0)) {
     const float4* q = reinterpret_cast<const float4*>(p + k0);
 #pragma unroll
@@ -70,10 +79,16 @@ __device__ __forceinline__ void fetch32(const float* __restrict__ src, const flo
     if (msk) {
       const float4* qm = reinterpret_cast<const float4*>(msk + row_off + k0);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float4 t = __ldg(qm + j);
-        v[4 * j] *= mask_factor(mmode, t.x); v[4 * j + 1] *= mask_factor(mmode, t.y);
-        v[4 * j + 2] *= mask_factor(mmode, t.z); v[4 * j + 3] *= mask_factor(mmode, t.w);
+      for (int b = 0; b < 2; ++b) {       // sixteen mask values in flight at a time (register budget)
+        float4 t[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) t[j] = __ldg(qm + 4 * b + j);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int e = 16 * b + 4 * j;
+          v[e] *= mask_factor_sel(sig, lo, t[j].x); v[e + 1] *= mask_factor_sel(sig, lo, t[j].y);
+          v[e + 2] *= mask_factor_sel(sig, lo, t[j].z); v[e + 3] *= mask_factor_sel(sig, lo, t[j].w);
+        }
       }
     }
     return;
@@ -86,9 +101,15 @@ __device__ __forceinline__ void fetch32(const float* __restrict__ src, const flo
   if (msk) {
     const float* pm = msk + row_off;
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      const int k = k0 + j;
-      if (k < K) v[j] *= mask_factor(mmode, __ldg(pm + (int64_t)k * ld_k));
+    for (int b = 0; b < 2; ++b) {
+      float y[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const int k = k0 + 16 * b + j;
+        y[j] = k < K ? __ldg(pm + (int64_t)k * ld_k) : 1.f;
+      }
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[16 * b + j] *= mask_factor_sel(sig, lo, y[j]);
     }
   }
 }
@@ -193,32 +214,70 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const __grid_consta
     // ================================================ epilogue ================================================
     mbar_wait(bar_acc, 0u);
     tcgen05_fence_after();
-    const uint32_t row = (uint32_t)threadIdx.x;
-    const int64_t m = m0 + row;
     const uint32_t acc = tmem_base + ((uint32_t)(warp * 32) << 16);
     const bool atomic = d.k_splits > 1;
     const int act = d.act & 3;
     const bool pre_add = (d.act & 4) != 0;
-    for (int c0 = 0; c0 < P.n_pad; c0 += 16) {
-      uint32_t v[16];
-      tmem_ld16(acc + (uint32_t)c0, v);
-      tmem_ld_wait();
-      if (m < d.M) {
+    auto finish = [&](float x, int64_t m, int n) -> float {     // bias, addend, activation of one element (first K split only)
+      if (d.bias != nullptr && ks == 0) x += d.bias[n];
+      const float add = d.addend != nullptr && ks == 0 ? d.addend[m * d.add_ld_r + (int64_t)n * d.add_ld_c] : 0.f;
+      if (pre_add) x += add;
+      if (act == 1) x = fmaxf(x, 0.f);
+      else if (act == 2) x = __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-x)));
+      else if (act == 3) x = x > 0.f ? x : __fmul_rn(0.02f, x);
+      if (!pre_add) x += add;
+      return x;
+    };
+    if (!atomic) {
+      // row per thread: 16 consecutive columns per TMEM load, written as 64 contiguous bytes of the row
+      const int64_t m = m0 + (int64_t)threadIdx.x;
+      for (int c0 = 0; c0 < P.n_pad; c0 += 16) {
+        uint32_t v[16];
+        tmem_ld16(acc + (uint32_t)c0, v);
+        tmem_ld_wait();
+        if (m < d.M) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const int n = c0 + j;
-          if (n >= d.N) continue;
-          float x = __uint_as_float(v[j]);
-          if (d.bias != nullptr && ks == 0) x += d.bias[n];
-          const float add = d.addend != nullptr && ks == 0 ? d.addend[m * d.add_ld_r + (int64_t)n * d.add_ld_c] : 0.f;
-          if (pre_add) x += add;
-          if (act == 1) x = fmaxf(x, 0.f);
-          else if (act == 2) x = __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-x)));
-          else if (act == 3) x = x > 0.f ? x : __fmul_rn(0.02f, x);
-          if (!pre_add) x += add;
-          float* dst = d.C + m * d.c_ld_r + (int64_t)n * d.c_ld_c;
-          if (atomic) atomicAdd(dst, x);
-          else *dst = d.beta ? *dst + x : x;
+          for (int j = 0; j < 16; ++j) {
+            const int n = c0 + j;
+            if (n >= d.N) continue;
+            const float x = finish(__uint_as_float(v[j]), m, n);
+            float* dst = d.C + m * d.c_ld_r + (int64_t)n * d.c_ld_c;
+            *dst = d.beta ? *dst + x : x;
+          }
+        }
+      }
+    } else {
+      // split-K partial tile -> fp32 reductions into C.  Column-distributed readout (tcgen05.ld.16x256b): a thread holds two adjacent
+      // columns of rows r and r + 8, so a row-major C takes ONE 8-byte reduction per pair instead of two 4-byte ones.
+      const bool pairs = d.c_ld_c == 1 && (d.c_ld_r & 1) == 0 && (reinterpret_cast<uintptr_t>(d.C) & 7) == 0;
+      for (int c0 = 0; c0 < P.n_pad; c0 += 16) {
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          uint32_t v[8];
+          asm volatile("tcgen05.ld.sync.aligned.16x256b.x2.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                       : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                       : "r"(acc + ((uint32_t)(16 * half) << 16) + (uint32_t)c0)
+                       : "memory");
+          tmem_ld_wait();
+#pragma unroll
+          for (int g = 0; g < 2; ++g) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const int64_t m = m0 + warp * 32 + 16 * half + 8 * h + (lane >> 2);
+              const int n = c0 + 8 * g + 2 * (lane & 3);
+              if (m >= d.M || n >= d.N) continue;
+              const bool two = n + 1 < d.N;
+              const float x0 = finish(__uint_as_float(v[4 * g + 2 * h]), m, n);
+              const float x1 = two ? finish(__uint_as_float(v[4 * g + 2 * h + 1]), m, n + 1) : 0.f;
+              float* dst = d.C + m * d.c_ld_r + (int64_t)n * d.c_ld_c;
+              if (pairs && two) {
+                atomicAdd(reinterpret_cast<float2*>(dst), make_float2(x0, x1));
+              } else {
+                atomicAdd(dst, x0);
+                if (two) atomicAdd(dst + d.c_ld_c, x1);
+              }
+            }
+          }
         }
       }
     }

@@ -247,7 +247,9 @@ class PNode(_PT):
         P = x.shape[0]
         if self.gW is not None:
             m_tiles = (self.W.shape[0] + 127) // 128
-            splits = max(1, min((P + 63) // 64, (2 * N_SM) // m_tiles))
+            # split-K partial tiles are reduced with fp32 atomics (M x N per split): one wave of CTAs, not two -- the atomics, not the
+            # K loop, were most of this GEMM's time
+            splits = max(1, min((P + 63) // 64, N_SM // m_tiles))
             tape.count(mm(A.t(), x.t(), self.gW, mask=M.t() if M is not None else None, mask_mode=mode, beta=1, k_splits=splits,
                           precision=tape.precision))
         if isinstance(self.bias, VNode):
