@@ -112,8 +112,12 @@ def test_decoder_programs_without_rounding_are_the_reference():
         ped[:, :24] = O.decoder_transform_points(rd / torch.norm(rd, dim=-1, keepdim=True), 4)[0]
         for field, which in ((0, 'head'), (1, 'torso')):
             rf, rs = O.decoder_forward(sd, p, rd, zs, za, sig[field], which)
-            for folded in (0, 1):
+            # 0 / 1: the plain / folded-head program (mlp_pp.cu); 2 / 3: the same in the layout the CTA-pair kernel runs (mlp_pair.cu: the
+            # torso's fc_in_torso as one layer over [PE' | signal' in hidden block 3])
+            for folded in (0, 1, 2, 3):
                 layers, weights, bias, folds, dimL, view_layer, dot_w = dump_program(sd, field, folded)
+                if folded >= 2 and field == 1:
+                    assert len(layers) == len(dump_program(sd, field, folded - 2)[0]) - 1
                 latent = torch.cat([sig[field].reshape(-1), zs.reshape(-1), za.reshape(-1)])
                 fold = {l: (torch.as_tensor(fw).double().t() @ latent.double()).float() for l, fw in folds.items()}
                 feat, sigma = Q.run_program_q(layers, weights, bias, {KB_PE: pe, KB_DIR: ped}, None, fold_bias=fold, dot_w=dot_w)
