@@ -60,8 +60,9 @@ def test_embed(dfn, golden):
         assert torch.equal(y[:, :3].cpu(), g['x'])
     assert maxerr(dfn.decoder_transform_points(x[None], 10), g['tp10'][None]) < 1e-6
     assert maxerr(dfn.decoder_transform_points(x[None], 4, views=True), g['tp4'][None]) < 1e-6
-    big = (torch.rand(200000, 3) * 2 - 1) * 1.2
-    assert maxerr(dfn.get_embedder(10)[0](big.to(DEV)), O.embed(big, 10)) < 1e-6
+    # seeded, and checked against the float64 restatement so a miss can only be the kernel's
+    big = (torch.rand(200000, 3, generator=torch.Generator().manual_seed(11)) * 2 - 1) * 1.2
+    assert maxerr(dfn.get_embedder(10)[0](big.to(DEV)), O.embed(big.double(), 10).float()) < 1e-6
 
 
 def test_calc_volume_weights(dfn, golden):
