@@ -47,7 +47,7 @@ class LayerInfo(C.Structure):
 class HeadTorsoIO(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ('rays_o_head', 'rays_d_head', 'rays_o_torso', 'rays_d_torso', 'near', 'far',
                                           't_vals', 'bc_rgb', 'z_shape', 'z_app', 'signal', 'signal_torso', 'rgb_head',
-                                          'rgb_person')] + [('last_dist', C.c_float)]
+                                          'rgb_person')] + [('last_dist', C.c_float), ('expression_term', C.c_void_p)]
 
 
 class GemmDesc(C.Structure):
@@ -106,6 +106,7 @@ def _load():
         'dfn_decoder_load': (i32, [vp, C.POINTER(vp), i32, vp]),
         'dfn_decoder_query_workspace_bytes': (i64, [vp, i64, i32]),
         'dfn_decoder_query': (i32, [vp, i32, i64, i32, vp, vp, vp, vp, vp, vp, vp, i32, vp, i64, vp]),
+        'dfn_decoder_query_ex': (i32, [vp, i32, i64, i32, vp, vp, vp, vp, vp, vp, vp, vp, i32, vp, i64, vp]),
         'dfn_decoder_macs_per_sample': (C.c_double, [vp, i32]),
         'dfn_model_program_host': (i32, [vp, C.POINTER(vp), i32, i32, C.POINTER(LayerInfo), C.POINTER(i32), vp, vp,
                                          C.POINTER(i32), vp, vp, vp]),
@@ -134,7 +135,7 @@ EXPORTS = ['dfn_abi_version', 'dfn_last_error', 'dfn_last_launch_count', 'dfn_pr
            'dfn_sort_merge', 'dfn_to8b', 'dfn_audionet_forward', 'dfn_att_smooth', 'dfn_pose_signal', 'dfn_model_create', 'dfn_model_destroy', 'dfn_model_num_tensors', 'dfn_model_load',
            'dfn_mlp_workspace_bytes', 'dfn_mlp_forward', 'dfn_query_workspace_bytes', 'dfn_query_points',
            'dfn_render_workspace_bytes', 'dfn_render_rays', 'dfn_decoder_create', 'dfn_decoder_destroy',
-           'dfn_decoder_num_tensors', 'dfn_decoder_load', 'dfn_decoder_query_workspace_bytes', 'dfn_decoder_query',
+           'dfn_decoder_num_tensors', 'dfn_decoder_load', 'dfn_decoder_query_workspace_bytes', 'dfn_decoder_query', 'dfn_decoder_query_ex',
            'dfn_decoder_macs_per_sample', 'dfn_decoder_program_host', 'dfn_model_program_host', 'dfn_render_head_torso_workspace_bytes', 'dfn_render_head_torso',
            'dfn_coarse_to_fine', 'dfn_gemm', 'dfn_colsum', 'dfn_head_torso_loss_bwd', 'dfn_adam_step']
 

@@ -70,6 +70,8 @@ struct FoldArgs {
   int layer[8];
   int seg[3];
   const float* lat[3];
+  const float* extra;   // [hidden] added to the biases of layer extra_layer (expnet(expression), DEC:279-281,333-334), or null
+  int extra_layer;
 };
 
 // bias_out[l][n] = bias[l][n] + sum_j fold_w[f(l)][j][n] * latent[j]; one block per layer, fp32, sequential in j.
@@ -95,6 +97,7 @@ __global__ void dec_fold_kernel(int n_layers, int dimL, const float* __restrict_
     for (int j = 0; j < dimL; ++j) acc = fmaf(w[(size_t)j * TC_BIAS_STRIDE], lat[j], acc);
     v += acc;
   }
+  if (a.extra != nullptr && l == a.extra_layer) v += a.extra[n];
   bias_out[l * TC_BIAS_STRIDE + n] = v;
 }
 
@@ -444,7 +447,7 @@ static int64_t dec_workspace_bytes(const dfn_decoder* m, int64_t R) {
 
 static int dec_query(const dfn_decoder* m, int field, int64_t R, int S, const float* rays_o, const float* rays_d,
                      const float* z_vals, const float* z_shape, const float* z_app, const float* signal, float* raw,
-                     int precision, void* workspace, int64_t workspace_bytes, cudaStream_t st) {
+                     int precision, void* workspace, int64_t workspace_bytes, cudaStream_t st, const float* view_term = nullptr) {
   DFN_CHECK_ARG(m && (field == 0 || field == 1) && R > 0 && S > 0 && rays_o && rays_d && z_vals && z_shape && z_app && signal &&
                     raw && workspace,
                 "dfn_decoder_query: bad argument");
@@ -477,6 +480,8 @@ static int dec_query(const dfn_decoder* m, int field, int64_t R, int S, const fl
   fa.lat[0] = signal;
   fa.lat[1] = z_shape;
   fa.lat[2] = z_app;
+  fa.extra = view_term;
+  fa.extra_layer = F.view_layer;
   dec_fold_kernel<<<F.prog.n_layers, TC_BIAS_STRIDE, 0, st>>>(F.prog.n_layers, F.dimL, F.bias, F.fold_w, fa, bias_ws);
   DFN_LAUNCH_CHECK();
   const bool prof = profile_begin(st, F.macs_pt * (double)R * S);
@@ -629,6 +634,15 @@ extern "C" int dfn_decoder_query(const dfn_decoder* m, int field, int64_t R, int
                    (cudaStream_t)stream);
 }
 
+extern "C" int dfn_decoder_query_ex(const dfn_decoder* m, int field, int64_t R, int S, const float* rays_o, const float* rays_d,
+                                    const float* z_vals, const float* z_shape, const float* z_app, const float* signal,
+                                    const float* view_term, float* raw, int precision, void* workspace, int64_t workspace_bytes,
+                                    void* stream) {
+  reset_launch_count();
+  return dec_query(m, field, R, S, rays_o, rays_d, z_vals, z_shape, z_app, signal, raw, precision, workspace, workspace_bytes,
+                   (cudaStream_t)stream, view_term);
+}
+
 extern "C" double dfn_decoder_macs_per_sample(const dfn_decoder* m, int field) {
   return m && m->loaded && (field == 0 || field == 1) ? m->f[field].macs_pt : 0.0;
 }
@@ -662,7 +676,7 @@ extern "C" int dfn_render_head_torso(const dfn_decoder* m, int64_t R, int S, con
   int rc = dfn_z_vals((int)R, S, io->t_vals, io->near, io->far, nullptr, z, st);   // MAIN:617-619
   if (rc) return rc;
   rc = dec_query(m, 0, R, S, io->rays_o_head, io->rays_d_head, z, io->z_shape, io->z_app, io->signal, raw_h, precision, qws,
-                 qbytes, st);
+                 qbytes, st, io->expression_term);
   if (rc) return rc;
   rc = dec_query(m, 1, R, S, io->rays_o_torso, io->rays_d_torso, z, io->z_shape + zd, io->z_app + zd, io->signal_torso, raw_t,
                  precision, qws, qbytes, st);

@@ -89,8 +89,12 @@ __device__ __forceinline__ uint32_t make_idesc_pair(uint32_t n) {
 
 // EW: epilogue warps per tile slot -- 4 (one per TMEM lane quarter, 384 threads) or 8 (two per quarter, each half of the columns; 640
 // threads, 96 registers).
-template <bool F16, int EW>
+// DEC: the Decoder programs (staged fills beyond the encoding, TC_EPI_SIGMA / CONT / STAGE, the folded density head).  The FaceNeRF / NeRF
+// instantiation compiles none of that: 3.4 k instead of 5.6 k instructions, which is worth 9 % of the frame (measured on one box: 52.0 ms
+// with the Decoder paths merged into the one instantiation, 47.3 ms apart -- the five roles' code then stays in the instruction cache).
+template <bool F16, int EW, int MODE>   // MODE 0: FaceNeRF / NeRF; 1: Decoder head; 2: Decoder torso (deformation field in front)
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((4 + 2 * EW) * 32, 1) mlp_pair_kernel(const __grid_constant__ Params P) {
+  constexpr bool DEC = MODE != 0, TORSO = MODE == 2;
   constexpr int NSLOT = 2;
   constexpr int NH = EW / 4;          // column halves per row
   constexpr int ETH = EW * 32;        // epilogue threads per slot
@@ -134,7 +138,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((4 + 2 * EW) * 32, 1
 
   // tile group g = (j*C + c)*NSLOT + s holds tiles 2g (leader) and 2g+1 (peer); a tile index past the end is computed
   // on a clamped point and not stored.
-  if (P.dot_w != nullptr) {   // (ordered before its first use by the barriers every tile passes)
+  if (DEC && P.dot_w != nullptr) {   // (ordered before its first use by the barriers every tile passes)
     for (int i = threadIdx.x; i < 128; i += blockDim.x) {
       const float2 w2 = reinterpret_cast<const float2*>(P.dot_w)[i];
       reinterpret_cast<uint32_t*>(smem + SMEM_DOT)[i] = F16 ? pack_f16(w2.x, w2.y) : pack_bf16(w2.x, w2.y);
@@ -242,7 +246,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((4 + 2 * EW) * 32, 1
                 const uint64_t bdesc = make_smem_desc(sbase + SMEM_RING + e * ENT_BYTES + (uint32_t)b * bytes);
 #pragma unroll
                 for (int q = 0; q < 4; ++q)   // K = 16 per instruction: both operands advance 32 bytes inside the swizzle atom
-                  umma_bf16_2cta(acc, adesc + 2 * q, bdesc + 2 * q, idesc, ((kb0 | b | q) != 0 || (L.flags & TC_F_ACCUM)) ? 1u : 0u);
+                  umma_bf16_2cta(acc, adesc + 2 * q, bdesc + 2 * q, idesc, ((kb0 | b | q) != 0 || (TORSO && (L.flags & TC_F_ACCUM))) ? 1u : 0u);
               }
             }
             if (last_use) umma_commit2_mc(bar_empty + 8 * e, (uint16_t)3);
@@ -270,7 +274,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((4 + 2 * EW) * 32, 1
     float* bias_s = reinterpret_cast<float*>(smem + SMEM_BIAS) + s * TC_BIAS_STRIDE;
     const uint32_t acc = tmem_base + (uint32_t)s * 256u + ((uint32_t)((warp & 3) * 32) << 16);
     uint32_t acc_par = 0u;
-    const int nf = P.n_fills;   // fills of the slot's staged block per tile
+    const int nf = DEC ? P.n_fills : 1;   // fills of the slot's staged block per tile
     // fill k >= 1 must be in place before the layer that first reads it is handed to the MMA issuer
     auto wait_fill_for = [&](int next_layer, int j) {
       for (int k = 1; k < nf; ++k)
@@ -309,12 +313,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((4 + 2 * EW) * 32, 1
 
       float alpha = 0.f;
       for (int l = 0; l < P.n_layers; ++l) {
-        const bool dot_next_rgb = P.dot_w != nullptr && NH == 2 && l + 1 < P.n_layers && P.layers[l + 1].epi == TC_EPI_RGB;
+        const bool dot_next_rgb = DEC && P.dot_w != nullptr && NH == 2 && l + 1 < P.n_layers && P.layers[l + 1].epi == TC_EPI_RGB;
         const TcLayer& L = P.layers[l];
         const bool tr = P.trace != nullptr && blockIdx.x == 0 && tid_s == 0 && j < P.trace_tiles;
         long long t_e0 = 0, t_e1 = 0;
         if (tr) t_e0 = clock64();
-        if (L.epi == TC_EPI_VIEW0) prefetch_row_l1(P.view_bias + ray * P.view_w + hf * (P.view_w / NH), P.view_w / NH);   // hidden behind the wait
+        if (!DEC && L.epi == TC_EPI_VIEW0) prefetch_row_l1(P.view_bias + ray * P.view_w + hf * (P.view_w / NH), P.view_w / NH);   // hidden behind the wait
         mbar_wait(bar_acc + 8 * s, acc_par);
         acc_par ^= 1u;
         tcgen05_fence_after();
@@ -332,18 +336,18 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((4 + 2 * EW) * 32, 1
               o.x = __uint_as_float(v[0]) + bias_s[0];
               o.y = __uint_as_float(v[1]) + bias_s[1];
               o.z = __uint_as_float(v[2]) + bias_s[2];
-              if (P.dec) {   // DEC:346-347
+              if (DEC) {   // DEC:346-347
                 o.x = __fdividef(1.f, 1.f + __expf(-o.x));
                 o.y = __fdividef(1.f, 1.f + __expf(-o.y));
                 o.z = __fdividef(1.f, 1.f + __expf(-o.z));
               }
               // folded density head: this thread's column part + the other part (left in the bias staging area by its thread) + bias
-              o.w = P.dot_w != nullptr ? alpha + (NH == 2 ? bias_s[128 + row] : 0.f) + __ldg(P.dot_w + TC_BIAS_STRIDE) : alpha;
+              o.w = DEC && P.dot_w != nullptr ? alpha + (NH == 2 ? bias_s[128 + row] : 0.f) + __ldg(P.dot_w + TC_BIAS_STRIDE) : alpha;
               reinterpret_cast<float4*>(P.raw)[pt] = o;
             }
           }
           tcgen05_fence_before();
-        } else if (L.epi == TC_EPI_SIGMA) {
+        } else if (DEC && L.epi == TC_EPI_SIGMA) {
           // Decoder density head (DEC:329): column 0 + bias stays in a register until the last layer writes raw
           if (hf == 0) {
             uint32_t v[16];
@@ -353,12 +357,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((4 + 2 * EW) * 32, 1
           }
           wait_fill_for(l + 1, j);
           signal_ready();
-        } else if (L.epi == TC_EPI_CONT) {
+        } else if (TORSO && L.epi == TC_EPI_CONT) {
           // partial sums stay in the accumulator (the next layer continues them, TC_F_ACCUM); only the hand-over
           tcgen05_fence_before();
           wait_fill_for(l + 1, j);
           signal_ready();
-        } else if (L.epi == TC_EPI_STAGE) {
+        } else if (TORSO && L.epi == TC_EPI_STAGE) {
           // deformation output (DEC:299), + bias, no activation: columns 0..63 = PE' replace the encoding in the staged block, columns 64..127
           // = signal' go to hidden block 3 (read by fc_in_torso) and, as a byte image of the block, to the scratch the IN1 fill copies back
           for (int b = hf * (2 / NH); b < (hf + 1) * (2 / NH); ++b) {
@@ -369,7 +373,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((4 + 2 * EW) * 32, 1
           wait_fill_for(l + 1, j);
           signal_ready();
         } else {
-          if (L.epi == TC_EPI_VIEW0) {
+          if (!DEC && L.epi == TC_EPI_VIEW0) {
             const int per = P.view_w / NH;
             epilogue_relu_rows16<true, F16>(acc, hf * per, (hf + 1) * per, P.view_bias + ray * P.view_w, 0u, arena, row);
             if (hf == 0) {
@@ -378,7 +382,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((4 + 2 * EW) * 32, 1
               tmem_ld_wait();
               alpha = __uint_as_float(v[0]) + bias_s[P.view_w];
             }
-          } else if (L.flags & TC_F_DOT_SIGMA) {
+          } else if (DEC && (L.flags & TC_F_DOT_SIGMA)) {
             // last trunk block + sigma_out (DEC:329): the density from the layer's fp32 activations, this warp's columns' part
             const int per = ((int)L.n >> 6) / NH;
             alpha = epilogue_relu_cd_dotpart<F16>(acc, hf * per, (hf + 1) * per, smem_u32(bias_s), sbase + SMEM_DOT, arena,
@@ -417,7 +421,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((4 + 2 * EW) * 32, 1
     // x = o + d*z -> [x | sin(2^k x) | cos(2^k x)] (HELP:42-52, pe.cuh) for the NEXT tile of each slot, written straight
     // into the slot's PE K-block as soon as the last layer that reads it (the skip layer) has finished its MMAs.
     const int t = (warp - 2) * 32 + lane;
-    const int nf = P.n_fills;
+    const int nf = DEC ? P.n_fills : 1;
     for (int j = 0; j < n_iter; ++j) {
       for (int k = 0; k < nf; ++k) {
         for (int s = 0; s < NSLOT; ++s) {
@@ -426,7 +430,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((4 + 2 * EW) * 32, 1
           if (fill > 0) mbar_wait(bar_pefree + 8 * s, (uint32_t)(fill - 1) & 1u);
           uint8_t* pe_blk = smem + (size_t)(s * TC_KB_PER_TILE + TC_KB_PE) * KB_BYTES;
           const int tile = 2 * group_of(j, s) + (int)crank;
-          if (P.fill_kb[k] == TC_KB_IN1) {
+          if (TORSO && P.fill_kb[k] == TC_KB_IN1) {
             // the deformed signal written by this tile's TC_EPI_STAGE epilogue: a byte image of the block
             const uint4* src = reinterpret_cast<const uint4*>(P.scratch + ((size_t)blockIdx.x * 2 + s) * KB_BYTES);
             uint4* dst = reinterpret_cast<uint4*>(pe_blk);
@@ -440,11 +444,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((4 + 2 * EW) * 32, 1
               if (pt >= P.n_points) pt = P.n_points - 1;
               const int64_t ray = pt / P.S;
               float pe[64], x[3];
-              if (P.fill_kb[k] == TC_KB_DIR) {
+              if (DEC && P.fill_kb[k] == TC_KB_DIR) {
                 pe_decoder_viewdir(P.rays_d, ray, P.multires_views, pe);
               } else {
                 sample_point(P.rays_o, P.rays_d, ray, P.z_vals[pt], x);
-                if (P.dec) pe_decoder(x, P.multires, pe);
+                if (DEC) pe_decoder(x, P.multires, pe);
                 else pe_embedder(x, P.multires, pe);
               }
 #pragma unroll
@@ -503,6 +507,7 @@ int pair_launch_prog(const TcProgram& prog, const uint32_t* woff2, const uint8_t
   P.dot_w = nullptr;
   tc_get_trace(reinterpret_cast<void**>(&P.trace), &P.trace_tiles);
   P.flags = g_pair_flags;
+  bool torso = false;   // the program uses what only the torso instantiation compiles: TC_EPI_CONT / TC_EPI_STAGE / TC_F_ACCUM / TC_KB_IN1
   int use[7], rel[7];
   for (int k = 0; k < 7; ++k) use[k] = rel[k] = -1;
   for (int i = 0; i < prog.n_layers; ++i) {
@@ -516,12 +521,14 @@ int pair_launch_prog(const TcProgram& prog, const uint32_t* woff2, const uint8_t
       P.dot_w = dot_w;
     }
     if ((L.flags & ~(TC_F_ACCUM | TC_F_DOT_SIGMA)) != 0 || L.nkb > 5) ok = false;
+    if (L.epi == TC_EPI_CONT || L.epi == TC_EPI_STAGE || (L.flags & TC_F_ACCUM)) torso = true;
     if ((L.flags & TC_F_ACCUM) && (i == 0 || prog.layers[i - 1].epi != TC_EPI_CONT)) ok = false;
     if (L.epi == TC_EPI_CONT && (i + 1 >= prog.n_layers || !(prog.layers[i + 1].flags & TC_F_ACCUM) || prog.layers[i + 1].n != L.n)) ok = false;
     for (int k = 0; k < L.nkb; ++k)
       if (L.kb[k] >= TC_KB_PE) {
         if (L.kb[k] > TC_KB_DIR || (!decoder && L.kb[k] != TC_KB_PE)) ok = false;
         else {
+          if (L.kb[k] == TC_KB_IN1) torso = true;
           if (use[L.kb[k]] < 0) use[L.kb[k]] = i;
           rel[L.kb[k]] = i;
         }
@@ -560,8 +567,16 @@ int pair_launch_prog(const TcProgram& prog, const uint32_t* woff2, const uint8_t
     kernel<<<grid, threads, tcp::SMEM_TOTAL, st>>>(P);
     return 0;
   };
-  if (ew == 8) return f16 ? launch(tcp::mlp_pair_kernel<true, 8>, 640) : launch(tcp::mlp_pair_kernel<false, 8>, 640);
-  return f16 ? launch(tcp::mlp_pair_kernel<true, 4>, 384) : launch(tcp::mlp_pair_kernel<false, 4>, 384);
+  if (decoder && torso) {
+    if (ew == 8) return f16 ? launch(tcp::mlp_pair_kernel<true, 8, 2>, 640) : launch(tcp::mlp_pair_kernel<false, 8, 2>, 640);
+    return f16 ? launch(tcp::mlp_pair_kernel<true, 4, 2>, 384) : launch(tcp::mlp_pair_kernel<false, 4, 2>, 384);
+  }
+  if (decoder) {
+    if (ew == 8) return f16 ? launch(tcp::mlp_pair_kernel<true, 8, 1>, 640) : launch(tcp::mlp_pair_kernel<false, 8, 1>, 640);
+    return f16 ? launch(tcp::mlp_pair_kernel<true, 4, 1>, 384) : launch(tcp::mlp_pair_kernel<false, 4, 1>, 384);
+  }
+  if (ew == 8) return f16 ? launch(tcp::mlp_pair_kernel<true, 8, 0>, 640) : launch(tcp::mlp_pair_kernel<false, 8, 0>, 640);
+  return f16 ? launch(tcp::mlp_pair_kernel<true, 4, 0>, 384) : launch(tcp::mlp_pair_kernel<false, 4, 0>, 384);
 }
 
 int pair_launch(const dfn_model* m, const float* bias_ws, const float* vbias_ws, int64_t R, int S, const float* rays_o,

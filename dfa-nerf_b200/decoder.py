@@ -77,8 +77,13 @@ class DeformationField_ori(nn.Module):
 
 
 class Decoder(nn.Module):
-    """DEC:137-349 in the configuration MAIN:518 builds (z_dim=256, hidden_size=256, dim_signal=96,
-    use_deformation_field=True, 'normal' positional encoding, use_viewdirs, final sigmoid)."""
+    """DEC:137-349.  The fp32 ``forward`` covers the constructor's options ('normal' positional encoding, downscale_p_by=2): any
+    n_blocks / skips / hidden_size / rgb_out_dim, the listener branch (head, signal None: fc_in_listener, fc_p_skips_listener,
+    DEC:305-308,322-325), use_expression (DEC:279-281,333-334), use_viewdirs off or ray_d None (DEC:336), final sigmoid off, no
+    deformation field.  The fused tcgen05 path (``query_rays`` / ``render_head_torso``) is built for what MAIN:518 constructs
+    (z_dim=256, hidden_size=256, dim_signal=96, use_deformation_field=True, n_blocks=8, skips=[4], viewdirs, final sigmoid).
+    Not built: 'gauss' encoding (DEC:188-199, needs CUDA at construction in the reference), z_dim <= 0 and n_blocks_view > 1 (both
+    fail inside the reference's own forward: DEC:319 / DEC:341-343 feed hidden_size features to a dim_embed_view+hidden_size layer)."""
 
     def __init__(self, hidden_size=128, n_blocks=8, n_blocks_view=1, dim_signal=64, skips=[4], use_viewdirs=True,
                  n_freq_posenc=10, dim_exp=256, dim_et_embed=42, n_freq_posenc_views=4, use_aud_net=False, dim_aud=64,
@@ -86,32 +91,49 @@ class Decoder(nn.Module):
                  use_wav2lip=False, dim_w2lfeature=512, gauss_dim_pos=10, gauss_dim_view=4, gauss_std=4.,
                  use_deformation_field=False, use_expression=False, **kwargs):
         super().__init__()
-        if positional_encoding != 'normal' or not use_viewdirs or n_blocks_view != 1 or downscale_p_by != 2. or \
-                use_expression or use_wav2lip or not final_sigmoid_activation or z_dim <= 0 or rgb_out_dim != 3 or \
-                list(skips) != [4] or n_blocks != 8:
-            raise DfnError('Decoder: only the configuration of MAIN:518 is built (n_blocks=8, skips=[4], one view block, '
-                           "'normal' encoding, final sigmoid)")
+        if positional_encoding != 'normal' or downscale_p_by != 2. or z_dim <= 0:
+            raise DfnError("Decoder: only the 'normal' positional encoding with downscale_p_by=2 and z_dim > 0 is built")
+        self.use_viewdirs, self.n_blocks_view, self.final_sigmoid_activation = use_viewdirs, n_blocks_view, final_sigmoid_activation
+        self.use_expression, self.use_wav2lip, self.rgb_out_dim = use_expression, use_wav2lip, rgb_out_dim
         self.n_freq_posenc, self.n_freq_posenc_views, self.skips = n_freq_posenc, n_freq_posenc_views, skips
         self.z_dim, self.hidden_size, self.n_blocks, self.dim_signal = z_dim, hidden_size, n_blocks, dim_signal
-        self.dim_et_embed, self.use_deformation_field = dim_et_embed, use_deformation_field
+        self.dim_et_embed, self.use_deformation_field, self.dim_exp = dim_et_embed, use_deformation_field, dim_exp
         de, dv = 6 * n_freq_posenc, 6 * n_freq_posenc_views
+        # registration order = the reference's (DEC:206-255), so state_dict() lists the same keys in the same order
         if use_deformation_field:
             self.deform_net = DeformationField_ori(de, dim_et_embed)
+        if use_expression:
+            self.expnet = nn.Linear(dim_exp, hidden_size)
+        if use_wav2lip:
+            self.w2lnet = nn.Linear(dim_w2lfeature, hidden_size)      # constructed, never used by forward (DEC:221-222)
         self.fc_in = nn.Linear(de + dim_signal, hidden_size)
         self.fc_in_listener = nn.Linear(de, hidden_size)
         self.fc_in_torso = nn.Linear(de + dim_et_embed, hidden_size)
         self.fc_z = nn.Linear(z_dim, hidden_size)
         self.blocks = nn.ModuleList([nn.Linear(hidden_size, hidden_size) for _ in range(n_blocks - 1)])
         n_skips = sum([i in skips for i in range(n_blocks - 1)])
-        self.fc_z_skips = nn.ModuleList([nn.Linear(z_dim, hidden_size) for _ in range(n_skips)])
-        self.fc_p_skips = nn.ModuleList([nn.Linear(de + dim_signal, hidden_size) for _ in range(n_skips)])
-        self.fc_p_skips_listener = nn.ModuleList([nn.Linear(de, hidden_size) for _ in range(n_skips)])
-        self.fc_p_skips_torso = nn.ModuleList([nn.Linear(de + dim_et_embed, hidden_size) for _ in range(n_skips)])
+        if n_skips > 0:
+            self.fc_z_skips = nn.ModuleList([nn.Linear(z_dim, hidden_size) for _ in range(n_skips)])
+            self.fc_p_skips = nn.ModuleList([nn.Linear(de + dim_signal, hidden_size) for _ in range(n_skips)])
+            self.fc_p_skips_listener = nn.ModuleList([nn.Linear(de, hidden_size) for _ in range(n_skips)])
+            self.fc_p_skips_torso = nn.ModuleList([nn.Linear(de + dim_et_embed, hidden_size) for _ in range(n_skips)])
         self.sigma_out = nn.Linear(hidden_size, 1)
         self.fc_z_view = nn.Linear(z_dim, hidden_size)
         self.feat_view = nn.Linear(hidden_size, hidden_size)
         self.fc_view = nn.Linear(dv, hidden_size)
         self.feat_out = nn.Linear(hidden_size, rgb_out_dim)
+        if use_viewdirs and n_blocks_view > 1:
+            self.blocks_view = nn.ModuleList([nn.Linear(dv + hidden_size, hidden_size) for _ in range(n_blocks_view - 1)])
+
+    def _fused_config_error(self):
+        """None when the module is what the fused tcgen05 programs are compiled for (MAIN:518), else the reason."""
+        if not self.use_deformation_field:
+            return 'use_deformation_field=True'
+        if self.n_blocks != 8 or list(self.skips) != [4]:
+            return 'n_blocks=8, skips=[4]'
+        if not self.use_viewdirs or self.n_blocks_view != 1 or not self.final_sigmoid_activation or self.rgb_out_dim != 3:
+            return 'use_viewdirs, one view block, final sigmoid, rgb_out_dim=3'
+        return None
 
     def transform_points(self, p, views=False):
         return decoder_transform_points(p, self.n_freq_posenc_views if views else self.n_freq_posenc)
@@ -119,8 +141,9 @@ class Decoder(nn.Module):
     # -- libdfn handle of the fused tcgen05 path ------------------------------------------------------------
     def _tensor_list(self):
         """{weight, bias} in the load order of dfn_decoder_load (include/dfn.h)."""
-        if not self.use_deformation_field:
-            raise DfnError('Decoder: the fused path needs use_deformation_field=True (MAIN:518)')
+        why = self._fused_config_error()
+        if why is not None:
+            raise DfnError('Decoder: the fused path is built for the configuration of MAIN:518 (%s); use forward() in fp32' % why)
         dn = self.deform_net
         mods = list(dn.blocks_embed) + [dn.out_embed] + list(dn.blocks_signal) + [dn.out_signal, dn.fc_embed_skips[0],
                                                                                   dn.fc_signal_skips[0]]
@@ -142,8 +165,6 @@ class Decoder(nn.Module):
         if getattr(self, '_handle', None) is not None and sig == self._loaded_sig:
             return self._handle
         if getattr(self, '_handle', None) is None:
-            if list(self.skips) != [4]:
-                raise DfnError('Decoder: the fused path covers skips=[4]')
             desc = DecoderDesc(self.hidden_size, self.z_dim, self.dim_signal, self.dim_et_embed, self.n_freq_posenc,
                                self.n_freq_posenc_views, self.n_blocks, 4)
             h = C.c_void_p()
@@ -170,8 +191,13 @@ class Decoder(nn.Module):
         un-normalised), z_vals [R,S] -> (feat [R,S,3] after the sigmoid, sigma [R,S] before MAIN:688's relu)."""
         if head_or_torso not in ('head', 'torso'):
             raise Exception('Do not give head or torso!!')
+        expression = None
         if isinstance(signal, (list, tuple)):
+            if self.use_expression and head_or_torso == 'head' and len(signal) > 1 and signal[1] is not None:
+                expression = signal[1]
             signal = signal[0]
+        if signal is None:
+            raise DfnError('Decoder.query_rays: the listener branch (signal None, DEC:307) runs through forward() in fp32')
         rays_o, p_o = dev(rays_o, 'rays_o')
         rays_d, p_d = dev(rays_d, 'rays_d')
         z_vals, p_z = dev(z_vals, 'z_vals')
@@ -188,67 +214,105 @@ class Decoder(nn.Module):
         raw = torch.empty((R, S, 4), dtype=torch.float32, device=d)
         nbytes = lib.dfn_decoder_query_workspace_bytes(h, R, S)
         ws = Workspace.get(nbytes, d, 'decoder')
+        term = self._expression_term(expression, d)
         with torch.cuda.device(d):
-            check(lib.dfn_decoder_query(h, field, R, S, p_o, p_d, p_z, p_zs, p_za, p_s, ptr(raw), int(precision), ptr(ws),
-                                        nbytes, stream_ptr()), 'dfn_decoder_query')
+            check(lib.dfn_decoder_query_ex(h, field, R, S, p_o, p_d, p_z, p_zs, p_za, p_s, ptr(term), ptr(raw), int(precision),
+                                           ptr(ws), nbytes, stream_ptr()), 'dfn_decoder_query')
         return raw[..., :3], raw[..., 3]
+
+    def _expression_term(self, expression, device):
+        """expnet(expression) [1, hidden] (DEC:279-281), the per-frame row the fused programs add at the view layer; None without."""
+        if expression is None:
+            return None
+        ex, _ = dev(expression.reshape(1, -1).to(device), 'expression')
+        return _linear(1, self.hidden_size, ex, ex.shape[1], ex.shape[1], self.expnet.weight, self.expnet.bias, 0)
 
     @torch.no_grad()
     def forward(self, p_in, ray_d, z_shape=None, z_app=None, signal=None, head_or_torso=None, precision=_lib.PREC_FP32):
-        """p_in, ray_d [1,P,3]; z_shape, z_app [1,z_dim]; signal [1,dim_signal] (head; a [signal, None] list as the
-        reference passes is accepted) or [1,dim_et_embed] (torso) -> (feat [1,P,3], sigma [1,P]).
-        precision PREC_FP32 (default): the fp32 FFMA building blocks; PREC_BF16 / PREC_FP16 / PREC_BF16X3: the fused tcgen05
-        kernel on the explicit points (every point is a one-sample ray: origin p, depth 0, its own view direction)."""
+        """DEC:277-349.  p_in, ray_d [1,P,3]; z_shape, z_app [1,z_dim] (None: drawn from N(0,1) as DEC:287-290); signal: head --
+        [1,dim_signal], or the reference's [signal, expression] pair (signal None selects the listener layers, expression
+        [1,dim_exp] feeds expnet when use_expression); torso -- [1,dim_et_embed].  -> (feat [1,P,rgb_out_dim], sigma [1,P]).
+        precision PREC_FP32 (default): the fp32 FFMA building blocks, every constructor option above; PREC_BF16 / PREC_FP16 /
+        PREC_BF16X3: the fused tcgen05 kernel on the explicit points (every point is a one-sample ray: origin p, depth 0, its own
+        view direction), MAIN:518's configuration only."""
         if head_or_torso not in ('head', 'torso'):
             raise Exception('Do not give head or torso!!')
+        head = head_or_torso == 'head'
+        expression = None
         if isinstance(signal, (list, tuple)):
+            if head and self.use_expression and len(signal) > 1 and signal[1] is not None:
+                expression = signal[1]
             signal = signal[0]
-        if z_shape is None or z_app is None or signal is None:
-            raise DfnError('Decoder.forward: z_shape, z_app and signal are required (as in MAIN:666,675)')
+        if signal is None and not head:
+            raise DfnError('Decoder.forward: the torso field needs its signal (fc_in_torso takes dim_embed + dim_et_embed, DEC:309)')
+        if self.use_viewdirs and ray_d is not None and self.n_blocks_view > 1:
+            raise DfnError('Decoder.forward: n_blocks_view > 1 feeds hidden_size features to layers of dim_embed_view + hidden_size '
+                           'inputs (DEC:253,341-343); the reference fails there too')
+        device = p_in.device
+        if z_shape is None:
+            z_shape = torch.randn(1, self.z_dim, device=device)
+        if z_app is None:
+            z_app = torch.randn(1, self.z_dim, device=device)
         if precision != _lib.PREC_FP32:
+            if ray_d is None:
+                raise DfnError('Decoder.forward: the fused path needs view directions; use PREC_FP32')
             pts = p_in.reshape(-1, 3)
             n = pts.shape[0]
             feat, sigma = self.query_rays(pts, ray_d.reshape(-1, 3), torch.zeros((n, 1), dtype=torch.float32, device=pts.device),
-                                          z_shape, z_app, signal, head_or_torso, precision=precision)
+                                          z_shape, z_app, [signal, expression], head_or_torso, precision=precision)
             return feat.reshape(1, n, 3), sigma.reshape(1, n)
         p_in, _ = dev(p_in.reshape(-1, 3), 'p_in')
-        ray_d, _ = dev(ray_d.reshape(-1, 3), 'ray_d')
         z_shape, _ = dev(z_shape.reshape(1, -1), 'z_shape')
         z_app, _ = dev(z_app.reshape(1, -1), 'z_app')
-        sig, _ = dev(signal.reshape(1, -1), 'signal')
         P, H, zd = p_in.shape[0], self.hidden_size, self.z_dim
         de = 6 * self.n_freq_posenc
-        pe = self.transform_points(p_in)                                   # [P, 60]
-        if head_or_torso == 'torso':
+        pe = self.transform_points(p_in)                                   # [P, de]
+        sig_pts, ld_sig, ds = None, 0, 0
+        if signal is not None:
+            sig, _ = dev(signal.reshape(1, -1), 'signal')
+            sig_pts, ds = sig, sig.shape[1]                                # per-frame signal: one broadcast row (DEC:293-295)
+        n_skips = sum([i in self.skips for i in range(self.n_blocks - 1)])
+        if not head:
             if self.use_deformation_field:
                 pe, sig_pts = self.deform_net.deform(pe, sig)              # DEC:297-299: p = deform_net(p) + p
                 ld_sig = sig_pts.shape[1]
-            else:
-                sig_pts, ld_sig = sig, 0
-            fc_in, fc_skip = self.fc_in_torso, self.fc_p_skips_torso[0]
+            fc_in, fc_skips = self.fc_in_torso, (self.fc_p_skips_torso if n_skips else [])
+        elif signal is None:
+            fc_in, fc_skips = self.fc_in_listener, (self.fc_p_skips_listener if n_skips else [])
         else:
-            sig_pts, ld_sig = sig, 0                                       # per-frame signal: one broadcast row
-            fc_in, fc_skip = self.fc_in, self.fc_p_skips[0]
-        ds = sig.shape[1]
-        # per-frame latent terms become biases (DEC:311, DEC:319, DEC:332)
-        b_in = _linear(1, H, z_shape, zd, zd, self.fc_z.weight, self.fc_z.bias, 0, addend=fc_in.bias.reshape(1, -1), ld_add=H)
-        b_skip = _linear(1, H, z_shape, zd, zd, self.fc_z_skips[0].weight, self.fc_z_skips[0].bias, 0,
-                         addend=fc_skip.bias.reshape(1, -1), ld_add=H)
-        b_view = _linear(1, H, z_app, zd, zd, self.fc_z_view.weight, self.fc_z_view.bias, 0,
-                         addend=self.feat_view.bias.reshape(1, -1), ld_add=H)
+            fc_in, fc_skips = self.fc_in, (self.fc_p_skips if n_skips else [])
+        if fc_in.in_features != de + ds:
+            raise DfnError('Decoder.forward: signal has %d values, the %s layers take %d' % (ds, head_or_torso, fc_in.in_features - de))
+        row = lambda b: b.reshape(1, -1)
+        # per-frame latent terms become biases (DEC:311, DEC:319, DEC:332-334)
+        b_in = _linear(1, H, z_shape, zd, zd, self.fc_z.weight, self.fc_z.bias, 0, addend=row(fc_in.bias), ld_add=H)
         net = _linear(P, H, pe, de, de, fc_in.weight, b_in, RELU, X2=sig_pts, ld2=ld_sig, K2=ds)
-        s_term = _linear(P, H, pe, de, de, fc_skip.weight, b_skip, 0, X2=sig_pts, ld2=ld_sig, K2=ds)
         n = len(self.blocks)
+        skip_idx = 0
         for idx, layer in enumerate(self.blocks):
-            add = (idx + 1) in self.skips and idx < n - 1
-            net = _linear(P, H, net, H, H, layer.weight, layer.bias, RELU, addend=s_term if add else None, ld_add=H)
+            s_term = None
+            if (idx + 1) in self.skips and idx < n - 1:                    # DEC:316-325: added after the relu
+                fc_skip = fc_skips[skip_idx]
+                b_skip = _linear(1, H, z_shape, zd, zd, self.fc_z_skips[skip_idx].weight, self.fc_z_skips[skip_idx].bias, 0,
+                                 addend=row(fc_skip.bias), ld_add=H)
+                s_term = _linear(P, H, pe, de, de, fc_skip.weight, b_skip, 0, X2=sig_pts, ld2=ld_sig, K2=ds)
+                skip_idx += 1
+            net = _linear(P, H, net, H, H, layer.weight, layer.bias, RELU, addend=s_term, ld_add=H)
         sigma = _linear(P, 1, net, H, H, self.sigma_out.weight, self.sigma_out.bias, 0)
-        t = _linear(P, H, net, H, H, self.feat_view.weight, b_view, 0)
-        pev = decoder_transform_points(ray_d, self.n_freq_posenc_views, normalize=True)   # [P, 24], DEC:337-338
-        dv = pev.shape[1]
-        net = _linear(P, H, pev, dv, dv, self.fc_view.weight, self.fc_view.bias, RELU | PRE_ADD, addend=t, ld_add=H)
-        feat = _linear(P, 3, net, H, H, self.feat_out.weight, self.feat_out.bias, SIGMOID)
-        return feat.reshape(1, P, 3), sigma.reshape(1, P)
+        b_view = _linear(1, H, z_app, zd, zd, self.fc_z_view.weight, self.fc_z_view.bias, 0,
+                         addend=row(self.feat_view.bias), ld_add=H)
+        if expression is not None:                                         # DEC:279-281, 333-334
+            ex, _ = dev(expression.reshape(1, -1), 'expression')
+            b_view = _linear(1, H, ex, ex.shape[1], ex.shape[1], self.expnet.weight, self.expnet.bias, 0, addend=b_view, ld_add=H)
+        net = _linear(P, H, net, H, H, self.feat_view.weight, b_view, 0)
+        if self.use_viewdirs and ray_d is not None:                        # DEC:336-340; without it there is no relu either
+            ray_d, _ = dev(ray_d.reshape(-1, 3), 'ray_d')
+            pev = decoder_transform_points(ray_d, self.n_freq_posenc_views, normalize=True)   # [P, dv], DEC:337-338
+            dv = pev.shape[1]
+            net = _linear(P, H, pev, dv, dv, self.fc_view.weight, self.fc_view.bias, RELU | PRE_ADD, addend=net, ld_add=H)
+        feat = _linear(P, self.rgb_out_dim, net, H, H, self.feat_out.weight, self.feat_out.bias,
+                       SIGMOID if self.final_sigmoid_activation else 0)
+        return feat.reshape(1, P, self.rgb_out_dim), sigma.reshape(1, P)
 
 
 @torch.no_grad()
@@ -268,7 +332,10 @@ def render_head_torso(decoder, H, W, focal, c2w_head, c2w_torso, bc_rgb, z_shape
     ro, rd, rot, rdt = [t.reshape(-1, 3)[b:e].contiguous() for t in (ro, rd, rot, rdt)]
     R = e - b
     if precision != _lib.PREC_FP32:
+        expression = None
         if isinstance(signal, (list, tuple)):
+            if decoder.use_expression and len(signal) > 1 and signal[1] is not None:
+                expression = signal[1]
             signal = signal[0]
         io = HeadTorsoIO()
         nr = torch.full((R,), float(near), device=device)
@@ -284,6 +351,8 @@ def render_head_torso(decoder, H, W, focal, c2w_head, c2w_torso, bc_rgb, z_shape
         rgb_head = torch.empty((R, 3), dtype=torch.float32, device=device)
         rgb_person = torch.empty((R, 3), dtype=torch.float32, device=device)
         io.rgb_head, io.rgb_person, io.last_dist = ptr(rgb_head), ptr(rgb_person), float(last_dist)
+        term = decoder._expression_term(expression, device)
+        io.expression_term = ptr(term)
         h = decoder.dfn_handle(device)
         nbytes = lib.dfn_render_head_torso_workspace_bytes(h, R, N_samples)
         ws = Workspace.get(nbytes, device, 'head_torso')

@@ -224,6 +224,12 @@ int64_t dfn_decoder_query_workspace_bytes(const dfn_decoder* m, int64_t R, int S
 int dfn_decoder_query(const dfn_decoder* m, int field, int64_t R, int S, const float* rays_o, const float* rays_d,
                       const float* z_vals, const float* z_shape, const float* z_app, const float* signal, float* raw,
                       int precision, void* workspace, int64_t workspace_bytes, void* stream);
+/* The same with the head's expression term (use_expression, DEC:279-281, 333-334): view_term [hidden] = expnet(expression),
+ * a per-frame row the caller forms with dfn_linear, added to the input of the view layer's relu; null = dfn_decoder_query. */
+int dfn_decoder_query_ex(const dfn_decoder* m, int field, int64_t R, int S, const float* rays_o, const float* rays_d,
+                         const float* z_vals, const float* z_shape, const float* z_app, const float* signal,
+                         const float* view_term, float* raw, int precision, void* workspace, int64_t workspace_bytes,
+                         void* stream);
 /* algorithmic MACs per sample of a field with the per-frame and per-ray terms folded (roofline accounting) */
 double dfn_decoder_macs_per_sample(const dfn_decoder* m, int field);
 
@@ -273,6 +279,7 @@ typedef struct {
   float* rgb_head;
   float* rgb_person;
   float last_dist; /* <= 0: 1e10 (MAIN:169) */
+  const float* expression_term; /* head field: expnet(expression) [hidden] (DEC:279-281), or null */
 } dfn_head_torso_io;
 
 int64_t dfn_render_head_torso_workspace_bytes(const dfn_decoder* m, int64_t R, int S);

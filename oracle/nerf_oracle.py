@@ -160,32 +160,46 @@ def deformation_forward(sd, x, dim_embed=60, dim_signal=42, skips=(4,), prefix='
 
 
 def decoder_forward(sd, p_in, ray_d, z_shape, z_app, signal, head_or_torso,
-                    n_freq=10, n_freq_views=4, skips=(4,), n_blocks=8):
-    """DEC:277-349 (live reference model).  p_in, ray_d: [1,P,3]; z_*: [1,256];
-    signal: [1,96] (head) or [1,42] (torso).  Returns feat [1,P,3] (sigmoid inside),
-    sigma [1,P] (no relu inside)."""
+                    n_freq=10, n_freq_views=4, skips=(4,), n_blocks=8, expression=None, use_deformation_field=True,
+                    final_sigmoid=True):
+    """DEC:277-349 (live reference model).  p_in, ray_d: [1,P,3]; z_*: [1,z_dim];
+    signal: [1,dim_signal] (head) or [1,dim_et_embed] (torso).  Returns feat [1,P,3] (sigmoid inside),
+    sigma [1,P] (no relu inside).
+    The options the live script leaves at their defaults: signal None on the head selects the listener layers (DEC:305-308,
+    322-325); expression [1,dim_exp] adds expnet(expression) to the view layer's input (DEC:279-281, 333-334; the caller
+    passes it only when the module was built with use_expression); ray_d None skips the view term AND the relu (DEC:336-340);
+    several skips use fc_*_skips.{0,1,..} in turn (DEC:314-327)."""
     p = decoder_transform_points(p_in, n_freq)
-    p = torch.cat((p, signal.expand(p.shape[1], -1).unsqueeze(0)), -1)
+    if signal is not None:
+        p = torch.cat((p, signal.expand(p.shape[1], -1).unsqueeze(0)), -1)
     if head_or_torso == 'torso':
-        p = deformation_forward(sd, p, dim_embed=6 * n_freq, dim_signal=signal.shape[-1]) + p
+        if use_deformation_field:
+            p = deformation_forward(sd, p, dim_embed=6 * n_freq, dim_signal=signal.shape[-1]) + p
         net = _lin(sd, 'fc_in_torso', p)
-        pskip = 'fc_p_skips_torso.0'
+        pskip = 'fc_p_skips_torso.%d'
     elif head_or_torso == 'head':
-        net = _lin(sd, 'fc_in', p)
-        pskip = 'fc_p_skips.0'
+        net = _lin(sd, 'fc_in' if signal is not None else 'fc_in_listener', p)
+        pskip = 'fc_p_skips.%d' if signal is not None else 'fc_p_skips_listener.%d'
     else:
         raise ValueError('head_or_torso')
     net = F.relu(net + _lin(sd, 'fc_z', z_shape).unsqueeze(1))
+    skip_idx = 0
     for idx in range(n_blocks - 1):
         net = F.relu(_lin(sd, 'blocks.%d' % idx, net))
         if (idx + 1) in skips and idx < n_blocks - 2:
-            net = net + _lin(sd, 'fc_z_skips.0', z_shape).unsqueeze(1)
-            net = net + _lin(sd, pskip, p)
+            net = net + _lin(sd, 'fc_z_skips.%d' % skip_idx, z_shape).unsqueeze(1)
+            net = net + _lin(sd, pskip % skip_idx, p)
+            skip_idx += 1
     sigma = _lin(sd, 'sigma_out', net).squeeze(-1)
     net = _lin(sd, 'feat_view', net) + _lin(sd, 'fc_z_view', z_app).unsqueeze(1)
-    d = ray_d / torch.norm(ray_d, dim=-1, keepdim=True)
-    net = F.relu(net + _lin(sd, 'fc_view', decoder_transform_points(d, n_freq_views)))
-    feat = torch.sigmoid(_lin(sd, 'feat_out', net))
+    if expression is not None:
+        net = net + _lin(sd, 'expnet', expression)
+    if ray_d is not None:
+        d = ray_d / torch.norm(ray_d, dim=-1, keepdim=True)
+        net = F.relu(net + _lin(sd, 'fc_view', decoder_transform_points(d, n_freq_views)))
+    feat = _lin(sd, 'feat_out', net)
+    if final_sigmoid:
+        feat = torch.sigmoid(feat)
     return feat, sigma
 
 

@@ -119,3 +119,33 @@ def test_composite_head_torso_edge_cases(dfn):
     oh, op = torch.empty(R, 3, device=DEV), torch.empty(R, 3, device=DEV)
     assert lib.dfn_composite_head_torso(R, S, *[ptr(x) for x in t], 1e10, ptr(oh), ptr(op), stream_ptr()) == 0
     assert maxerr(oh, ref_h) < 2e-6 and maxerr(op, ref_p) < 2e-6
+
+
+def test_decoder_options_golden(dfn, golden):
+    """Decoder options outside MAIN:518's configuration (listener layers DEC:305-308,322-325; use_expression DEC:279-281,
+    333-334; several skips; ray_d None; no final sigmoid; no deformation field; other widths) through the fp32 building blocks,
+    against the reference's own outputs; the state_dict loads strictly (same parameter names, incl. expnet / w2lnet)."""
+    from oracle.decoder_option_cases import CASES
+    g = golden('decoder_options')
+    for name, (kw, calls) in CASES.items():
+        sd = {k[len(name) + 4:]: v for k, v in g.items() if k.startswith(name + '/sd/')}
+        inp = {k[len(name) + 4:]: v.to(DEV) for k, v in g.items() if k.startswith(name + '/in/')}
+        dec = dfn.Decoder(**kw)
+        assert list(dec.state_dict().keys()) == list(sd.keys())
+        dec.load_state_dict(sd, strict=True)
+        dec = dec.to(DEV)
+        for call, which, has_sig, has_ex, has_rd in calls:
+            sig = (inp['signal'] if which == 'head' else inp['signal_torso']) if has_sig else None
+            arg = [sig, inp['expression'] if has_ex else None] if which == 'head' else sig
+            f, s = dec(inp['p'], inp['ray_d'] if has_rd else None, inp['z_shape'], inp['z_app'], arg, which)
+            rf, rs = g['%s/out/%s/feat' % (name, call)], g['%s/out/%s/sigma' % (name, call)]
+            assert f.shape == rf.shape and s.shape == rs.shape
+            assert maxerr(f, rf) < 2e-5 and maxerr(s, rs) < 2e-5, (name, call, maxerr(f, rf), maxerr(s, rs))
+    # what the reference cannot run either is refused with a reason, and the fused path says what it is built for
+    with pytest.raises(dfn.DfnError):
+        dfn.Decoder(positional_encoding='gauss')
+    d2 = dfn.Decoder(n_blocks_view=2).to(DEV)
+    with pytest.raises(dfn.DfnError):
+        d2(inp['p'], inp['ray_d'], torch.zeros(1, 64, device=DEV), torch.zeros(1, 64, device=DEV), torch.zeros(1, 64, device=DEV), 'head')
+    with pytest.raises(dfn.DfnError):
+        dec.query_rays(inp['p'][0], inp['ray_d'][0], torch.zeros(53, 1, device=DEV), inp['z_shape'], inp['z_app'], inp['signal'], 'head')

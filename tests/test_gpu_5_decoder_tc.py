@@ -198,3 +198,33 @@ def test_head_torso_full_frame_properties(dfn):
     n = H * W
     tail = run((n - 1796, n))[1]            # the reference's short last chunk (202,500 = 98 x 2048 + 1796)
     assert torch.equal(tail, person[n - 1796:])
+
+
+def test_expression_term_on_the_fused_path(dfn, golden):
+    """use_expression (DEC:279-281, 333-334): expnet(expression) rides the fused programs as a per-frame row at the view layer
+    (dfn_decoder_query_ex, dfn_head_torso_io.expression_term).  Checked against the fp32 forward, which
+    test_gpu_4_decoder::test_decoder_options_golden pins to the reference's outputs."""
+    m = dfn.Decoder(z_dim=256, hidden_size=256, dim_signal=96, use_deformation_field=True, use_expression=True, dim_exp=79)
+    missing = m.load_state_dict(synth.decoder_state_dict(2), strict=False)
+    assert sorted(missing.missing_keys) == ['expnet.bias', 'expnet.weight'] and not missing.unexpected_keys
+    gen = torch.Generator().manual_seed(5)
+    with torch.no_grad():
+        m.expnet.weight.copy_(torch.randn(256, 79, generator=gen) * 0.15)
+        m.expnet.bias.copy_(torch.randn(256, generator=gen) * 0.2)
+    m = m.to(DEV)
+    ro, rd, z, zs, za, sig_h, _ = _case(600, 8, 9)
+    ex = torch.randn(1, 79, generator=gen)
+    p, r = [t.reshape(1, -1, 3) for t in dfn.make_points(ro.to(DEV), rd.to(DEV), z.to(DEV))]
+    rf, rs = m(p, r, zs.to(DEV), za.to(DEV), [sig_h.to(DEV), ex.to(DEV)], 'head')
+    nf, _ = m(p, r, zs.to(DEV), za.to(DEV), [sig_h.to(DEV), None], 'head')
+    assert maxerr(rf, nf) > 1e-2                     # the term matters on this input
+    f, s = m.query_rays(ro.to(DEV), rd.to(DEV), z.to(DEV), zs.to(DEV), za.to(DEV), [sig_h.to(DEV), ex.to(DEV)], 'head',
+                        precision=dfn.PREC_BF16X3)
+    assert maxerr(f.reshape(1, -1, 3), rf) < 1e-4 and maxerr(s.reshape(1, -1), rs) < 1e-4 * rs.abs().max().item() + 1e-4
+    f16, _ = m.query_rays(ro.to(DEV), rd.to(DEV), z.to(DEV), zs.to(DEV), za.to(DEV), [sig_h.to(DEV), ex.to(DEV)], 'head',
+                          precision=dfn.PREC_FP16)
+    assert maxerr(f16.reshape(1, -1, 3), rf) < 5e-3
+    # the torso never takes it (DEC:279: head only), and a missing expression is the plain program
+    f0, _ = m.query_rays(ro.to(DEV), rd.to(DEV), z.to(DEV), zs.to(DEV), za.to(DEV), [sig_h.to(DEV), None], 'head',
+                         precision=dfn.PREC_BF16X3)
+    assert maxerr(f0.reshape(1, -1, 3), nf) < 1e-4

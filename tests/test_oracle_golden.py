@@ -154,3 +154,19 @@ def test_encoders(golden):
 
 def test_to8b():
     assert np.array_equal(O.to8b(np.array([-1., 0., 0.5, 1., 2.])), np.array([0, 0, 127, 255, 255], np.uint8))
+
+
+def test_decoder_options(golden):
+    """Listener layers, expression term, several skips, no view directions / sigmoid / deformation field: the restatement against
+    the reference's own outputs (oracle/make_golden_decoder_options.py)."""
+    from oracle.decoder_option_cases import CASES, oracle_kwargs
+    g = golden('decoder_options')
+    for name, (kw, calls) in CASES.items():
+        sd = {k[len(name) + 4:]: v for k, v in g.items() if k.startswith(name + '/sd/')}
+        inp = {k[len(name) + 4:]: v for k, v in g.items() if k.startswith(name + '/in/')}
+        for call, which, has_sig, has_ex, has_rd in calls:
+            sig = (inp['signal'] if which == 'head' else inp['signal_torso']) if has_sig else None
+            f, s = O.decoder_forward(sd, inp['p'], inp['ray_d'] if has_rd else None, inp['z_shape'], inp['z_app'], sig, which,
+                                     expression=inp['expression'] if has_ex else None, **oracle_kwargs(kw, has_ex))
+            close(f, g['%s/out/%s/feat' % (name, call)], 1e-6)
+            close(s, g['%s/out/%s/sigma' % (name, call)], 1e-5)
