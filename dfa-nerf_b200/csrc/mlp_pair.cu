@@ -238,7 +238,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((4 + 2 * EW) * 32, 1
               tcgen05_fence_after();
               if (tr) t_full += clock64() - t_f0;
             }
-#pragma unroll
+#pragma unroll 1   // (rolled: the issue loop is a fifth of the kernel's instructions when ptxas clones it per K-block, and one thread issues it)
             for (int b = 0; b < 2; ++b) {
               if (kb0 + b < L.nkb) {
                 const uint32_t blk = L.kb[kb0 + b] >= TC_KB_PE ? (uint32_t)TC_KB_PE : (uint32_t)L.kb[kb0 + b];   // staged inputs share block 4
@@ -444,12 +444,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((4 + 2 * EW) * 32, 1
               if (pt >= P.n_points) pt = P.n_points - 1;
               const int64_t ray = pt / P.S;
               float pe[64], x[3];
-              if (DEC && P.fill_kb[k] == TC_KB_DIR) {
-                pe_decoder_viewdir(P.rays_d, ray, P.multires_views, pe);
+              if (DEC) {   // one copy of the encoding loop for both staged encodings of the Decoder programs
+                const bool dir = P.fill_kb[k] == TC_KB_DIR;
+                if (dir) view_direction(P.rays_d, ray, x);
+                else sample_point(P.rays_o, P.rays_d, ray, P.z_vals[pt], x);
+                pe_decoder(x, dir ? P.multires_views : P.multires, pe);
               } else {
                 sample_point(P.rays_o, P.rays_d, ray, P.z_vals[pt], x);
-                if (DEC) pe_decoder(x, P.multires, pe);
-                else pe_embedder(x, P.multires, pe);
+                pe_embedder(x, P.multires, pe);
               }
 #pragma unroll
               for (int ch = 0; ch < 8; ++ch) {

@@ -61,11 +61,17 @@ __device__ __forceinline__ void pe_decoder(const float (&p)[3], int L, float (&p
   pe[60] = pe[61] = pe[62] = pe[63] = 0.f;
 }
 
-// DEC:337-338: the view direction d / |d| through transform_points(views=True)
-__device__ __forceinline__ void pe_decoder_viewdir(const float* __restrict__ rays_d, int64_t ray, int L, float (&pe)[64]) {
+// DEC:337-338: the view direction d / |d| (then through transform_points(views=True) = pe_decoder)
+__device__ __forceinline__ void view_direction(const float* __restrict__ rays_d, int64_t ray, float (&dn)[3]) {
   const float dx = rays_d[ray * 3], dy = rays_d[ray * 3 + 1], dz = rays_d[ray * 3 + 2];
   const float nrm = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)));
-  const float dn[3] = {__fdiv_rn(dx, nrm), __fdiv_rn(dy, nrm), __fdiv_rn(dz, nrm)};
+  dn[0] = __fdiv_rn(dx, nrm);
+  dn[1] = __fdiv_rn(dy, nrm);
+  dn[2] = __fdiv_rn(dz, nrm);
+}
+__device__ __forceinline__ void pe_decoder_viewdir(const float* __restrict__ rays_d, int64_t ray, int L, float (&pe)[64]) {
+  float dn[3];
+  view_direction(rays_d, ray, dn);
   pe_decoder(dn, L, pe);
 }
 

@@ -57,16 +57,14 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   }
 }
 #else
+// A spin COUNT, not a clock: three instructions per wait site instead of fifteen (the kernels inline ~25 waits, and their instruction
+// footprint is worth real time: see mlp_pair.cu).  A failed try_wait takes >= 0.1 us (it suspends inside the hardware up to its time limit),
+// so 2^22 of them are >= 0.4 s and at most some tens of seconds; legitimate waits are a tile's time (tens of us).
+static constexpr uint32_t MBAR_SPIN_LIMIT = 1u << 22;
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t spins = 0;
-  uint64_t t0 = 0;
-  while (!mbar_try_wait(bar, parity)) {
-    if ((++spins & 0x3FFu) == 0) {
-      const uint64_t t = globaltimer_ns();
-      if (t0 == 0) t0 = t;
-      else if (t - t0 > 2000000000ull) __trap();
-    }
-  }
+  while (!mbar_try_wait(bar, parity))
+    if (++spins == MBAR_SPIN_LIMIT) __trap();
 }
 #endif
 // One lane of a converged warp.  The MMA / TMA warps run their loops warp-uniformly (so descriptors and
@@ -347,7 +345,6 @@ __device__ __forceinline__ void mbar_arrive_remote_light(uint32_t bar, uint32_t 
 // wait with cluster-scope acquire: pairs with remote arrivals / another CTA's writes
 __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
   uint32_t spins = 0;
-  uint64_t t0 = 0;
   for (;;) {
     uint32_t ok;
     asm volatile(
@@ -358,11 +355,15 @@ __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity)
         : "r"(bar), "r"(parity)
         : "memory");
     if (ok) return;
-    if ((++spins & 0x3FFu) == 0) {
-      const uint64_t t = globaltimer_ns();
-      if (t0 == 0) t0 = t;
-      else if (t - t0 > 2000000000ull) __trap();
+#ifdef DFN_DEBUG_TIMEOUT
+    if (++spins == (1u << 18)) {
+      if ((threadIdx.x & 31) == 0)
+        printf("TIMEOUT (cluster wait) blk %d warp %d bar+0x%x parity %u\n", (int)blockIdx.x, (int)(threadIdx.x >> 5), bar & 0x3ffu, parity);
+      return;
     }
+#else
+    if (++spins == (1u << 22)) __trap();
+#endif
   }
 }
 __device__ __forceinline__ void fence_proxy_async_all() {
