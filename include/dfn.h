@@ -367,10 +367,12 @@ int dfn_profile_enable(int on);
  * done, aux} (uint64 each; 2*tiles*20*2*4 entries at most).  Pass null to switch it off. */
 int dfn_debug_trace(void* dev_buffer, int tiles);
 
-/* Selects the tcgen05 kernel variant (A/B measurements): -1 (default) the fastest measured per precision
- * (bf16 -> 1, bf16x3 -> 2); 1 two tiles in flight, per-tile epilogue warps (mlp_tc.cu); 2 cooperative
- * epilogue + PE through the weight ring (mlp_pp.cu); 0 activations in tensor memory (mlp_ts.cu); 3 (bf16 only) CTA-pair
- * cta_group::2 MMAs (mlp_tc2.cu; measured slower, kept as an experiment). */
+/* Selects the tcgen05 kernel variant (A/B measurements): -1 (default) the fastest measured per precision (bf16 / fp16 -> 3,
+ * bf16x3 / fp16x3m -> 2).  Low 4 bits: 1 the 1-CTA generation, two tiles in flight with per-tile epilogue warps (mlp_tc.cu);
+ * 2 cooperative epilogue + PE through the weight ring, the split-precision schedule (mlp_pp.cu); 3 CTA pairs, cta_group::2
+ * MMAs (mlp_pair.cu); 8 the same with four epilogue warps per slot.  Higher bits: (flags + 1) << 4 for the pair kernel --
+ * flag 1 a layer's weights are loaded once for both slots, 2 CTA-scope release on the peer's arrivals (default 3), 8 / 16
+ * keep the Decoder head / torso programs on mlp_pp.cu. */
 int dfn_debug_set_impl(int impl);
 int dfn_profile_collect(double* kernel_ms, int64_t* launches, double* algorithmic_macs);
 
