@@ -590,7 +590,7 @@ def main():
                            'frac': r['roofline']['frac'] if r['roofline'] else None,
                            'kernel': r['roofline']['kernel'] if r['roofline'] else None}
     if extras and args.workload == 'facenerf':
-        plan = [('head_torso', 'head_torso', max(3, min(args.steps, 5))), ('coarse64', 'coarse64', 10),
+        plan = [('head_torso', 'head_torso', max(3, min(args.steps, 5))), ('coarse64', 'coarse64', 10), ('mlp_1m', 'mlp_1m', 3),
                 ('sequence', 'sequence_%d' % args.frames, 1)]
         if world == 1:
             plan.append(('train_step', 'train_step', 10))

@@ -203,7 +203,7 @@ static constexpr int kMaxSeg = 8;  // samples per lane: S <= 256
 // SEG = samples per lane (compile-time, >= ceil(S/32)): the per-lane arrays live in registers, so a 64-sample ray (SEG 2)
 // does not pay the register footprint -- and the occupancy -- of a 256-sample one.
 template <int MODE, int SEG>
-__global__ void volume_weights_kernel(int R, int S, const float* __restrict__ src,
+__global__ void __launch_bounds__(256, 4) volume_weights_kernel(int R, int S, const float* __restrict__ src,
                                       const float* __restrict__ z_vals,
                                       const float* __restrict__ rays_d,
                                       const float* __restrict__ bc_rgb, int raw_is_feat,
@@ -314,7 +314,7 @@ __global__ void volume_weights_kernel(int R, int S, const float* __restrict__ sr
 // feat_* / sig_* are addressed with element strides (3 and 1 for separate tensors; 4 and 4 for the fused kernels'
 // interleaved raw [R,S,4] = (feat, sigma)).
 template <int SEG>
-__global__ void head_torso_kernel(int R, int S, const float* __restrict__ feat_h, int fs_h, const float* __restrict__ sig_h,
+__global__ void __launch_bounds__(256, 4) head_torso_kernel(int R, int S, const float* __restrict__ feat_h, int fs_h, const float* __restrict__ sig_h,
                                   int ss_h, const float* __restrict__ feat_t, int fs_t, const float* __restrict__ sig_t,
                                   int ss_t, const float* __restrict__ bc_rgb, const float* __restrict__ z_vals,
                                   const float* __restrict__ rays_d_h, const float* __restrict__ rays_d_t,
@@ -578,7 +578,7 @@ struct C2FSmem {   // floats per warp
 };
 
 template <int SEG>
-__global__ void coarse_to_fine_kernel(int R, int Nc, int Nf, const float* __restrict__ raw0, const float* __restrict__ z0,
+__global__ void __launch_bounds__(256, 4) coarse_to_fine_kernel(int R, int Nc, int Nf, const float* __restrict__ raw0, const float* __restrict__ z0,
                                       const float* __restrict__ rays_d, const float* __restrict__ bc_rgb, int white_bkgd,
                                       float last_dist, const float* __restrict__ u, int u_per_ray,
                                       const float* __restrict__ zs_in, float* __restrict__ rgb0, float* __restrict__ zs_out,
