@@ -14,11 +14,13 @@
 One step = one 450x450 frame (202,500 rays) x (64 coarse + 128 fine samples) of the synthetic
 FaceNeRF field (configs[1] of BASELINE.json): get_rays -> z sampling -> PE + 8x256 skip-MLP ->
 compositing -> sample_pdf -> sort-merge -> fine MLP -> RGB.  With N > 1 the frame's rays are sharded
-contiguously over the ranks and the RGB tile is all-gathered (NCCL) inside the timed step.
+contiguously over the ranks and every frame's RGB tiles are all-gathered (NCCL) inside the timed region -- on a side
+stream, frame i's gather under frame i+1's kernels (dfa_nerf_b200.RayShardSink).
 
 Printed JSON (rank 0), one line:
   value         rays/s with inputs resident in HBM             e2e      the same through the public API, pinned-host
-  roofline      tcgen05 MLP kernel vs the measured bf16 peak            inputs / outputs copied every step
+  roofline      tcgen05 MLP kernel vs the measured bf16 peak            inputs / outputs copied every step (the frame's
+                                                                        D2H double-buffered; the host takes frame i-1)
   modes         the same frame in the other tensor-core precisions (value, e2e, roofline fraction) -- bf16x3 is the
                 mode that meets the 1e-4 float tolerance, bf16 the one BASELINE.json's config names
   parity        max-abs RGB error of every precision against the CPU arm's render of the same rays: teacher-forced (the
@@ -250,6 +252,7 @@ class Job:
         self.n_rays = hw * hw
         self.b, self.e, _ = shard_range(self.n_rays, rank, world)
         self.launches = 0
+        self.sinks = {}
         self.frames = args.frames
         tc_name = ('mlp_pp_kernel<%s>' % precision) if prec in (dfn.PREC_BF16X3, dfn.PREC_FP16X3M) else 'mlp_pair_kernel<%s>' % precision
         self.flops_note = 'algorithmic, latent/viewdir columns folded: 2*557,184 per MLP evaluation (BASELINE.md section 2)'
@@ -341,8 +344,6 @@ class Job:
             self.kernel_name = ('mlp_pp_kernel<%s, Decoder>' if precision == 'bf16x3' else 'mlp_pair_kernel<%s, Decoder>') % precision
             self.flops_note = 'algorithmic, per-frame latents and per-ray view term folded: 2*556,032 (head) + 2*628,352 (torso ' \
                               'incl. deformation field) per sample (SURVEY.md section 8d, appendix A)'
-        if workload not in ('sequence', 'train_step'):
-            self.rgb_host = torch.empty((self.n_rays, 3), dtype=torch.float32).pin_memory()
 
     # -- one frame on this rank's ray range
     def render(self, bc_full, lat):
@@ -382,17 +383,22 @@ class Job:
         self.launches += self.trainer.last_launches
         return float(loss) if e2e else loss
 
+    def sink(self, to_host):
+        if to_host not in self.sinks:
+            self.sinks[to_host] = self.dfn.RayShardSink(self.n_rays, self.ctx['dev'], to_host=to_host)
+        return self.sinks[to_host]
+
     def step_resident(self):
-        from dfa_nerf_b200.distributed import gather_rgb
         if self.workload == 'train_step':
             return self.step_train()
         if self.workload == 'sequence':
             return self.step_sequence()
         rgb = self.render(self.bc_dev, self.aud_dev)
-        return gather_rgb(rgb, self.n_rays) if self.ctx['world'] > 1 else rgb
+        if self.ctx['world'] == 1:
+            return rgb
+        return self.sink(False).push(rgb)       # the all-gather of frame i runs on the sink's stream under frame i+1's kernels
 
     def step_e2e(self):
-        from dfa_nerf_b200.distributed import gather_rgb
         torch, dev = self.torch, self.ctx['dev']
         if self.workload == 'train_step':
             return self.step_train(e2e=True)
@@ -403,10 +409,12 @@ class Job:
         bc_full = torch.empty((self.n_rays, 3), dtype=torch.float32, device=dev)
         bc_full[self.b:self.e] = bc
         rgb = self.render(bc_full, lat)
-        full = gather_rgb(rgb, self.n_rays) if self.ctx['world'] > 1 else rgb
-        if self.ctx['rank'] == 0:
-            self.rgb_host.copy_(full, non_blocking=True)
-        torch.cuda.current_stream().synchronize()       # the caller consumes the frame
+        # frame loop as a user of the package writes it (dfa_nerf_b200.RayShardSink): frame i's all-gather and rank 0's copy into
+        # pinned host memory run on a side stream while frame i+1 renders; the host takes frame i-1 (blocking on ITS copy) each step
+        sink = self.sink(True)
+        i = sink.push(rgb)
+        if i > 0:
+            sink.wait(i - 1)
 
     def points_per_step(self):
         """Network evaluations this rank performs per step."""
@@ -637,7 +645,7 @@ def main():
             'config': {'workload': WORKLOADS[args.workload],
                        'rays_per_step': job.n_rays, 'mlp_evals_per_ray': job.evals_per_ray, 'precision': args.precision,
                        'parallelism': ('frames sharded over %d GPU(s), uint8 frames gathered to rank 0 per frame' % world)
-                       if args.workload == 'sequence' else 'single GPU' if args.workload == 'train_step' else 'rays sharded over %d GPU(s), one all-gather of the RGB tile' % world,
+                       if args.workload == 'sequence' else 'single GPU' if args.workload == 'train_step' else 'rays sharded over %d GPU(s), one all-gather of the RGB tile per frame on a side stream (frame i gathers / copies out while frame i+1 renders)' % world,
                        'l2': 'per-step intermediates (~1.4 GB of raw/z buffers) exceed the 126 MB L2; no explicit flush'},
             'e2e': main_res['e2e'], 'gpu_launches': main_res['gpu_launches'], 'clocks': clocks, 'roofline': main_res['roofline'],
             'cpu_baseline': cpu, 'modes': modes or None, 'parity': parity, 'extra': extra or None,

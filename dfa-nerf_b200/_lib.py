@@ -99,6 +99,7 @@ def _load():
         'dfn_query_workspace_bytes': (i64, [vp, i64, i32, i32]),
         'dfn_query_points': (i32, [vp, i64, i32, vp, vp, vp, vp, vp, vp, i32, vp, i64, vp]),
         'dfn_render_workspace_bytes': (i64, [vp, i64, i32, i32, i32]),
+        'dfn_render_workspace_bytes2': (i64, [vp, vp, i64, i32, i32, i32]),
         'dfn_render_rays': (i32, [vp, vp, i64, i32, i32, C.POINTER(RenderIO), i32, i32, vp, i64, vp]),
         'dfn_decoder_create': (i32, [C.POINTER(DecoderDesc), C.POINTER(vp)]),
         'dfn_decoder_destroy': (None, [vp]),
@@ -134,7 +135,7 @@ EXPORTS = ['dfn_abi_version', 'dfn_last_error', 'dfn_last_launch_count', 'dfn_pr
            'dfn_composite_fields', 'dfn_composite_head_torso', 'dfn_linear', 'dfn_calc_volume_weights', 'dfn_raw2outputs', 'dfn_sample_pdf', 'dfn_invert_cdf',
            'dfn_sort_merge', 'dfn_to8b', 'dfn_audionet_forward', 'dfn_att_smooth', 'dfn_pose_signal', 'dfn_model_create', 'dfn_model_destroy', 'dfn_model_num_tensors', 'dfn_model_load',
            'dfn_mlp_workspace_bytes', 'dfn_mlp_forward', 'dfn_query_workspace_bytes', 'dfn_query_points',
-           'dfn_render_workspace_bytes', 'dfn_render_rays', 'dfn_decoder_create', 'dfn_decoder_destroy',
+           'dfn_render_workspace_bytes', 'dfn_render_workspace_bytes2', 'dfn_render_rays', 'dfn_decoder_create', 'dfn_decoder_destroy',
            'dfn_decoder_num_tensors', 'dfn_decoder_load', 'dfn_decoder_query_workspace_bytes', 'dfn_decoder_query', 'dfn_decoder_query_ex',
            'dfn_decoder_macs_per_sample', 'dfn_decoder_program_host', 'dfn_model_program_host', 'dfn_render_head_torso_workspace_bytes', 'dfn_render_head_torso',
            'dfn_coarse_to_fine', 'dfn_gemm', 'dfn_colsum', 'dfn_head_torso_loss_bwd', 'dfn_adam_step']

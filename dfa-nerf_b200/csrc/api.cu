@@ -357,7 +357,9 @@ struct RenderWs {
   int64_t z0, raw0, w0, zmid, zs, zall, raw1, query, pre_a, pre_b, total;
 };
 
-static RenderWs render_layout(const dfn_model* m, int64_t R, int Nc, int Nf, int precision) {
+// query scratch and prepared-bias regions are sized for the LARGER of the two networks (a fine network of another width or latent size
+// runs in the same regions)
+static RenderWs render_layout(const dfn_model* m, const dfn_model* m2, int64_t R, int Nc, int Nf, int precision) {
   RenderWs w;
   int64_t o = 0;
   auto take = [&](int64_t bytes) {
@@ -373,10 +375,15 @@ static RenderWs render_layout(const dfn_model* m, int64_t R, int Nc, int Nf, int
   w.zs = take(R * (Nf > 0 ? Nf : 1) * 4);
   w.zall = take(R * Nt * 4);
   w.raw1 = take(Nf > 0 ? R * Nt * 16 : 16);
-  int64_t q = dfn_query_workspace_bytes(m, R, Nf > 0 ? Nt : Nc, precision);
-  int64_t q0 = dfn_query_workspace_bytes(m, R, Nc, precision);
-  w.query = take(q > q0 ? q : q0);
-  const int64_t pb = precision == DFN_PREC_FP32 ? 16 : tc_prep_bytes(m, R);   // both networks' prepared biases (tc_prep_launch)
+  int64_t q = dfn_query_workspace_bytes(m, R, Nc, precision);
+  int64_t pb = precision == DFN_PREC_FP32 ? 16 : tc_prep_bytes(m, R);   // both networks' prepared biases (tc_prep_launch)
+  const dfn_model* mf = m2 ? m2 : m;
+  if (Nf > 0) {
+    const int64_t qf = dfn_query_workspace_bytes(mf, R, Nt, precision);
+    if (qf > q) q = qf;
+    if (precision != DFN_PREC_FP32 && tc_prep_bytes(mf, R) > pb) pb = tc_prep_bytes(mf, R);
+  }
+  w.query = take(q);
   w.pre_a = take(pb);
   w.pre_b = take(pb);
   w.total = o;
@@ -386,7 +393,13 @@ static RenderWs render_layout(const dfn_model* m, int64_t R, int Nc, int Nf, int
 extern "C" int64_t dfn_render_workspace_bytes(const dfn_model* coarse, int64_t R, int N_samples, int N_importance,
                                               int precision) {
   if (!coarse || R <= 0 || N_samples <= 0 || N_importance < 0) return 0;
-  return render_layout(coarse, R, N_samples, N_importance, precision).total;
+  return render_layout(coarse, nullptr, R, N_samples, N_importance, precision).total;
+}
+
+extern "C" int64_t dfn_render_workspace_bytes2(const dfn_model* coarse, const dfn_model* fine, int64_t R, int N_samples,
+                                               int N_importance, int precision) {
+  if (!coarse || R <= 0 || N_samples <= 0 || N_importance < 0) return 0;
+  return render_layout(coarse, fine, R, N_samples, N_importance, precision).total;
 }
 
 extern "C" int dfn_render_rays(const dfn_model* coarse, const dfn_model* fine, int64_t R, int N_samples,
@@ -402,7 +415,7 @@ extern "C" int dfn_render_rays(const dfn_model* coarse, const dfn_model* fine, i
   if (fine == nullptr) fine = coarse;
   cudaStream_t st = (cudaStream_t)stream;
   const int Nc = N_samples, Nf = N_importance, Nt = Nc + Nf;
-  const RenderWs L = render_layout(coarse, R, Nc, Nf, precision);
+  const RenderWs L = render_layout(coarse, fine, R, Nc, Nf, precision);
   if (workspace_bytes < L.total) {
     set_error("dfn_render_rays: workspace %lld < %lld bytes", (long long)workspace_bytes, (long long)L.total);
     return DFN_E_WORKSPACE;

@@ -477,8 +477,14 @@ struct PrepNet {
   int n_layers, fold0, fold1;
 };
 
-__global__ void render_prep_kernel(PrepNet A, PrepNet B, int W, int dim_aud, const float* __restrict__ latent, int64_t R, int Wh,
-                                   int ncol, const float* __restrict__ viewdirs, int Nc, const float* __restrict__ t_vals,
+// NCOL = input_ch_views at compile time (27 for multires_views = 4: a thread keeps its output's view-direction weights in registers and
+// reads the encodings of PREP_RAYS rays as two broadcast 16-byte loads per column -- the first version re-read the weight row and four
+// scalar encodings from shared memory per column and was bound by those loads, 305 us per 202,500-ray frame) or 0 (any width: weights in
+// shared memory).  Same fmaf chain over the columns in both, so the rows are bit-identical.
+static constexpr int PREP_RAYS = 8;
+template <int NCOL>
+__global__ void __launch_bounds__(256) render_prep_kernel(PrepNet A, PrepNet B, int W, int dim_aud, const float* __restrict__ latent, int64_t R, int Wh,
+                                   int ncol_rt, const float* __restrict__ viewdirs, int Nc, const float* __restrict__ t_vals,
                                    const float* __restrict__ near, const float* __restrict__ far,
                                    const float* __restrict__ rnd, float* __restrict__ z_out) {
   const int n_fold_blocks = A.n_layers + B.n_layers;
@@ -498,20 +504,27 @@ __global__ void render_prep_kernel(PrepNet A, PrepNet B, int W, int dim_aud, con
     N.bias_out[l * TC_BIAS_STRIDE + n] = v;
     return;
   }
-  extern __shared__ float sm[];
-  float* w_s = sm;                       // [2][Wh][ncol]
-  float* pe = sm + 2 * Wh * ncol;        // [VB_RAYS][ncol]
-  for (int i = threadIdx.x; i < Wh * ncol; i += blockDim.x) {
-    w_s[i] = A.view_w[i];
-    w_s[Wh * ncol + i] = B.view_w[i];
-  }
+  const int ncol = NCOL ? NCOL : ncol_rt;
+  extern __shared__ __align__(16) float sm[];
+  float* pe = sm;                          // [ncol][PREP_RAYS]
+  float* w_s = sm + ncol * PREP_RAYS;      // NCOL == 0: [2][Wh][ncol]
   const int net = (int)threadIdx.x / Wh, nn = (int)threadIdx.x % Wh;      // blockDim = 2 * Wh
   const PrepNet& N = net == 0 ? A : B;
+  float wreg[NCOL ? NCOL : 1];
+  if (NCOL) {
+#pragma unroll
+    for (int j = 0; j < (NCOL ? NCOL : 1); ++j) wreg[j] = N.view_w[nn * ncol + j];
+  } else {
+    for (int i = threadIdx.x; i < Wh * ncol; i += blockDim.x) {
+      w_s[i] = A.view_w[i];
+      w_s[Wh * ncol + i] = B.view_w[i];
+    }
+  }
   const float bn = N.view_b[nn];
   const int ray_blocks = (int)gridDim.x - n_fold_blocks;
-  for (int64_t r0 = (int64_t)((int)blockIdx.x - n_fold_blocks) * VB_RAYS; r0 < R; r0 += (int64_t)ray_blocks * VB_RAYS) {
+  for (int64_t r0 = (int64_t)((int)blockIdx.x - n_fold_blocks) * PREP_RAYS; r0 < R; r0 += (int64_t)ray_blocks * PREP_RAYS) {
     __syncthreads();
-    for (int i = threadIdx.x; i < VB_RAYS * ncol; i += blockDim.x) {
+    for (int i = threadIdx.x; i < PREP_RAYS * ncol; i += blockDim.x) {
       const int q = i / ncol, j = i % ncol;
       const int64_t r = r0 + q < R ? r0 + q : R - 1;
       float v;
@@ -522,25 +535,32 @@ __global__ void render_prep_kernel(PrepNet A, PrepNet B, int W, int dim_aud, con
         const float a = __fmul_rn(viewdirs[r * 3 + (c % 3)], pow2i(k));
         v = c < 3 ? sinf(a) : cosf(a);
       }
-      pe[i] = v;
+      pe[j * PREP_RAYS + q] = v;
     }
     __syncthreads();
     {
-      float acc[VB_RAYS];
+      float acc[PREP_RAYS];
 #pragma unroll
-      for (int q = 0; q < VB_RAYS; ++q) acc[q] = 0.f;
-      const float* w = w_s + (size_t)net * Wh * ncol + nn * ncol;
-      for (int j = 0; j < ncol; ++j) {
-        const float wj = w[j];
+      for (int q = 0; q < PREP_RAYS; ++q) acc[q] = 0.f;
+      auto column = [&](float wj, int j) {
+        const float4 p0 = *reinterpret_cast<const float4*>(pe + j * PREP_RAYS);
+        const float4 p1 = *reinterpret_cast<const float4*>(pe + j * PREP_RAYS + 4);
+        acc[0] = fmaf(wj, p0.x, acc[0]); acc[1] = fmaf(wj, p0.y, acc[1]); acc[2] = fmaf(wj, p0.z, acc[2]); acc[3] = fmaf(wj, p0.w, acc[3]);
+        acc[4] = fmaf(wj, p1.x, acc[4]); acc[5] = fmaf(wj, p1.y, acc[5]); acc[6] = fmaf(wj, p1.z, acc[6]); acc[7] = fmaf(wj, p1.w, acc[7]);
+      };
+      if (NCOL) {
 #pragma unroll
-        for (int q = 0; q < VB_RAYS; ++q) acc[q] = fmaf(wj, pe[q * ncol + j], acc[q]);
+        for (int j = 0; j < (NCOL ? NCOL : 1); ++j) column(wreg[j], j);
+      } else {
+        const float* w = w_s + (size_t)net * Wh * ncol + nn * ncol;
+        for (int j = 0; j < ncol; ++j) column(w[j], j);
       }
 #pragma unroll
-      for (int q = 0; q < VB_RAYS; ++q)
+      for (int q = 0; q < PREP_RAYS; ++q)
         if (r0 + q < R) N.vbias_out[(r0 + q) * Wh + nn] = bn + acc[q];
     }
     // coarse depths of these rays (z_vals_kernel)
-    for (int i = threadIdx.x; i < VB_RAYS * Nc; i += blockDim.x) {
+    for (int i = threadIdx.x; i < PREP_RAYS * Nc; i += blockDim.x) {
       const int q = i / Nc, sidx = i % Nc;
       const int64_t r = r0 + q;
       if (r >= R) break;
@@ -803,12 +823,18 @@ int tc_prep_launch(const dfn_model* a, const dfn_model* b, int64_t R, int Nc, co
     n.fold1 = m->prog.fold_layer[1];
     return n;
   };
-  int64_t ray_blocks = (R + tc::VB_RAYS - 1) / tc::VB_RAYS;
+  int64_t ray_blocks = (R + tc::PREP_RAYS - 1) / tc::PREP_RAYS;
   if (ray_blocks > (int64_t)num_sms() * 8) ray_blocks = (int64_t)num_sms() * 8;
   const int grid = a->prog.n_layers + b->prog.n_layers + (int)ray_blocks;
-  const size_t sm = ((size_t)2 * Wh * da.input_ch_views + tc::VB_RAYS * da.input_ch_views) * sizeof(float);
-  tc::render_prep_kernel<<<grid, 2 * Wh, sm, st>>>(net(a, pre_a), net(b, pre_b), da.W, da.dim_aud, latent, R, Wh, da.input_ch_views,
-                                                  viewdirs, Nc, t_vals, near, far, rnd, z0);
+  const int ncol = da.input_ch_views;
+  if (ncol == 27) {
+    tc::render_prep_kernel<27><<<grid, 2 * Wh, (size_t)tc::PREP_RAYS * ncol * sizeof(float), st>>>(
+        net(a, pre_a), net(b, pre_b), da.W, da.dim_aud, latent, R, Wh, ncol, viewdirs, Nc, t_vals, near, far, rnd, z0);
+  } else {
+    const size_t sm = ((size_t)2 * Wh * ncol + tc::PREP_RAYS * ncol) * sizeof(float);
+    tc::render_prep_kernel<0><<<grid, 2 * Wh, sm, st>>>(net(a, pre_a), net(b, pre_b), da.W, da.dim_aud, latent, R, Wh, ncol, viewdirs, Nc,
+                                                        t_vals, near, far, rnd, z0);
+  }
   DFN_LAUNCH_CHECK();
   return 0;
 }

@@ -679,10 +679,10 @@ __global__ void __launch_bounds__(256, 4) coarse_to_fine_kernel(int R, int Nc, i
       for (int i = lane; i < nb; i += 32) zmid[i] = __fmul_rn(0.5f, __fadd_rn(v[i + 1], v[i]));
       {
         const int sg = (nw + 31) / 32;
-        float wv[kMaxBins / 32];
+        float wv[SEG];   // (Nc - 2 + 31) / 32 <= SEG
         double part = 0.0;
 #pragma unroll
-        for (int k = 0; k < kMaxBins / 32; ++k) {
+        for (int k = 0; k < SEG; ++k) {
           const int i = lane * sg + k;
           wv[k] = 0.f;
           if (k < sg && i < nw) {
@@ -696,7 +696,7 @@ __global__ void __launch_bounds__(256, 4) coarse_to_fine_kernel(int R, int Nc, i
         const float total = (float)tot;
         double lsum = 0.0;
 #pragma unroll
-        for (int k = 0; k < kMaxBins / 32; ++k) {
+        for (int k = 0; k < SEG; ++k) {
           const int i = lane * sg + k;
           if (k < sg && i < nw) {
             wv[k] = __fdiv_rn(wv[k], total);
@@ -715,7 +715,7 @@ __global__ void __launch_bounds__(256, 4) coarse_to_fine_kernel(int R, int Nc, i
           cdf[0] = 0.f;
         }
 #pragma unroll
-        for (int k = 0; k < kMaxBins / 32; ++k) {
+        for (int k = 0; k < SEG; ++k) {
           const int i = lane * sg + k;
           if (k < sg && i < nw) {
             r2 += (double)wv[k];

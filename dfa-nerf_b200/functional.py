@@ -38,7 +38,9 @@ def _device_of(*ts):
 
 def get_rays(H, W, focal, c2w, cx=None, cy=None, stride=1, device=None, return_viewdirs=False):
     """HELP:449-465.  c2w: [3,4] or [4,4] tensor / array (host or device).  Returns rays_o, rays_d
-    of shape [H//stride, W//stride, 3]; rays_d is R @ dir, not normalised."""
+    of shape [H//stride, W//stride, 3]; rays_d is R @ dir, not normalised.
+    The pose reaches the kernel as launch arguments, so a DEVICE c2w costs one blocking device->host copy per call: frame loops
+    keep their pose table on the host (render_sequence / render_sequence_head_torso copy it once per sequence)."""
     device = device or _device_of(c2w)
     n_cols, n_rows = int(W) // stride, int(H) // stride
     xs = linspace_table(n_cols, device, 0., float(W - 1))

@@ -102,8 +102,7 @@ class RenderEngine:
                 raise DfnError('output %r must be contiguous fp32 of shape %s' % (name, shapes[key]))
             setattr(io, key, ptr(t))
             res[name] = t
-        nbytes = max(lib.dfn_render_workspace_bytes(hc, R, Nc, Nf, self.precision),
-                     lib.dfn_render_workspace_bytes(hf, R, Nc, Nf, self.precision) if hf is not None else 0)
+        nbytes = lib.dfn_render_workspace_bytes2(hc, hf, R, Nc, Nf, self.precision)    # sized for the larger of the two networks
         ws = Workspace.get(nbytes, d, 'render')
         with torch.cuda.device(d):
             check(lib.dfn_render_rays(hc, hf, R, Nc, Nf, C.byref(io), int(self.white_bkgd), self.precision, ptr(ws),

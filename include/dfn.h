@@ -349,6 +349,11 @@ typedef struct {
 
 int64_t dfn_render_workspace_bytes(const dfn_model* coarse, int64_t R, int N_samples,
                                    int N_importance, int precision);
+/* The same for a coarse / fine pair whose networks differ in shape (width, latent size): the query scratch and the
+ * prepared-bias regions are sized for the larger of the two.  fine == NULL: the coarse network runs both passes.  This is
+ * the size dfn_render_rays checks its workspace against. */
+int64_t dfn_render_workspace_bytes2(const dfn_model* coarse, const dfn_model* fine, int64_t R, int N_samples,
+                                    int N_importance, int precision);
 int dfn_render_rays(const dfn_model* coarse, const dfn_model* fine, int64_t R, int N_samples,
                     int N_importance, const dfn_render_io* io, int white_bkgd, int precision,
                     void* workspace, int64_t workspace_bytes, void* stream);

@@ -161,3 +161,61 @@ def test_frame_gather_to_rank0_two_ranks_gloo():
     want = [int(_frame(i).sum()) for i in range(n)]
     assert shape == (n, 1, 12, 10, 3) and sums == want
     assert seen == [(i, want[i]) for i in range(n)]          # on_frame saw every global frame exactly once, on rank 0
+
+
+def _sink_worker(rank, world, port, n, q):
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        from dfa_nerf_b200.distributed import RayShardSink, shard_range
+        b, e, per = shard_range(n, rank, world)
+        sink = RayShardSink(n, 'cpu', depth=2)
+        frames = [torch.arange(n * 3, dtype=torch.float32).reshape(n, 3) * (k + 1) for k in range(5)]
+        ok = True
+        for k, f in enumerate(frames):
+            i = sink.push(f[b:e])
+            ok &= i == k
+            if i > 0:                                   # lag-one consumption, as the frame loop does
+                h = sink.wait(i - 1)
+                ok &= (h is not None) == (rank == 0)
+                if h is not None:
+                    ok &= torch.equal(h, frames[i - 1])
+            ok &= torch.equal(sink.device(i), f)        # every rank holds the gathered frame
+        sink.finish()
+        try:
+            sink.wait(1)                                # long recycled
+            ok = False
+        except IndexError:
+            pass
+        q.put((rank, bool(ok), per))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_ray_shard_sink_two_ranks_gloo():
+    """RayShardSink (the pipelined gather + copy-out of a ray-sharded frame loop): frame order, ragged tiles, double-buffer
+    reuse, rank 0 alone receives host frames."""
+    n = 63                                             # 32 + 31
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_sink_worker, args=(r, 2, port, n, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=180)
+        assert p.exitcode == 0
+    got = sorted(q.get(timeout=10) for _ in range(2))
+    assert got == [(0, True, 32), (1, True, 32)]
+
+
+def test_ray_shard_sink_single_process():
+    from dfa_nerf_b200.distributed import RayShardSink
+    sink = RayShardSink(10, 'cpu')
+    x = torch.rand(10, 3)
+    i = sink.push(x)
+    assert torch.equal(sink.wait(i), x) and torch.equal(sink.device(i), x)
+    import pytest
+    with pytest.raises(ValueError):
+        sink.push(torch.rand(11, 3))

@@ -193,3 +193,25 @@ def test_render_rays_maximum_samples_and_limits(dfn):
     with pytest.raises(dfn.DfnError):
         dfn.RenderEngine(nc, nf, 129, 128, precision=dfn.PREC_BF16X3).render_rays(
             ro.to(DEV), rd.to(DEV), vd.to(DEV), near.to(DEV), far.to(DEV), fr['bc_rgb'].to(DEV), fr['aud'].to(DEV))
+
+
+def test_render_rays_ragged_ray_count(dfn):
+    """A ray count that is no multiple of the preparation kernel's 8-ray blocks (render_prep_kernel: per-ray view-bias rows and
+    coarse depths of both networks), teacher-forced against the oracle; the last rays are the ones a block-tail bug would miss."""
+    R = 37
+    fr = synth.frame_inputs(H=R, W=1, seed=11)
+    sd_c, sd_f = synth.facenerf_state_dict(0), synth.facenerf_state_dict(1)
+    nc, nf = nets(dfn, 0, 1)
+    ro, rd = O.get_rays(R, 1, fr['focal'], fr['c2w'], fr['cx'], fr['cy'])
+    ro, rd = ro.reshape(-1, 3).contiguous(), rd.reshape(-1, 3)
+    vd = rd / torch.norm(rd, dim=-1, keepdim=True)
+    near, far = torch.full((R,), fr['near']), torch.full((R,), fr['far'])
+    rays = torch.cat([ro, rd, near[:, None], far[:, None], vd], -1)
+    with torch.no_grad():
+        ref = O.render_rays(rays, fr['bc_rgb'], fr['aud'], sd_c, sd_f, 64, 128)
+    eng = dfn.RenderEngine(nc, nf, 64, 128, precision=dfn.PREC_BF16X3)
+    out = eng.render_rays(ro.to(DEV), rd.to(DEV), vd.to(DEV), near.to(DEV), far.to(DEV), fr['bc_rgb'].to(DEV), fr['aud'].to(DEV),
+                          z_samples=ref['z_samples'].to(DEV), want=('rgb_map', 'rgb0', 'z_vals'))
+    assert torch.equal(out['z_vals'].cpu(), ref['z_vals'])
+    assert maxerr(out['rgb0'], ref['rgb0']) < 1e-4 and maxerr(out['rgb_map'], ref['rgb_map']) < 1e-4
+    assert maxerr(out['rgb_map'][-5:], ref['rgb_map'][-5:]) < 1e-4
