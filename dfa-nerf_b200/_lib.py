@@ -72,6 +72,7 @@ def _load():
         'dfn_profile_enable': (i32, [i32]),
         'dfn_debug_trace': (i32, [vp, i32]),
         'dfn_debug_set_impl': (i32, [i32]),
+        'dfn_debug_set_pp_flags': (i32, [i32]),
         'dfn_profile_collect': (i32, [C.POINTER(C.c_double), C.POINTER(i64), C.POINTER(C.c_double)]),
         'dfn_get_rays': (i32, [i32, i32, vp, vp, f32, f32, f32, C.POINTER(f32), vp, vp, vp, vp]),
         'dfn_z_vals': (i32, [i32, i32, vp, vp, vp, vp, vp, vp]),
@@ -131,7 +132,7 @@ def _load():
 
 
 lib = _load()
-EXPORTS = ['dfn_abi_version', 'dfn_last_error', 'dfn_last_launch_count', 'dfn_profile_enable', 'dfn_profile_collect', 'dfn_debug_trace', 'dfn_debug_set_impl', 'dfn_get_rays', 'dfn_z_vals', 'dfn_make_points', 'dfn_embed',
+EXPORTS = ['dfn_abi_version', 'dfn_last_error', 'dfn_last_launch_count', 'dfn_profile_enable', 'dfn_profile_collect', 'dfn_debug_trace', 'dfn_debug_set_impl', 'dfn_debug_set_pp_flags', 'dfn_get_rays', 'dfn_z_vals', 'dfn_make_points', 'dfn_embed',
            'dfn_composite_fields', 'dfn_composite_head_torso', 'dfn_linear', 'dfn_calc_volume_weights', 'dfn_raw2outputs', 'dfn_sample_pdf', 'dfn_invert_cdf',
            'dfn_sort_merge', 'dfn_to8b', 'dfn_audionet_forward', 'dfn_att_smooth', 'dfn_pose_signal', 'dfn_model_create', 'dfn_model_destroy', 'dfn_model_num_tensors', 'dfn_model_load',
            'dfn_mlp_workspace_bytes', 'dfn_mlp_forward', 'dfn_query_workspace_bytes', 'dfn_query_points',

@@ -155,6 +155,11 @@ extern "C" int dfn_debug_set_impl(int impl) {
   return 0;
 }
 
+extern "C" int dfn_debug_set_pp_flags(int flags) {
+  pp_set_flags(flags);
+  return 0;
+}
+
 extern "C" int dfn_debug_trace(void* dev_buffer, int tiles) {
   tc_set_trace(dev_buffer, tiles);
   return 0;

@@ -72,6 +72,7 @@ struct Params {
   int multires;
   int multires_views;      // Decoder: frequencies of the view-direction encoding (staged block TC_KB_DIR)
   int view_w;
+  int flags;               // bit 0: split schedule stages a layer's input block at the START of the previous layer's epilogue (early_staged); bit 1: weight-stage barrier polled first
   TcLayer layers[TC_MAX_LAYERS];  // woff: offsets into the K=32 / 64-byte-swizzle blobs
 };
 
@@ -234,6 +235,18 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1) mlp_pp_kerne
   uint8_t* scratch = P.pe_scratch + (size_t)blockIdx.x * 2 * 2 * NBLK * TILE_M * ROWB;
   // staged block `blk` of the tile in slot s of scratch buffer buf
   auto scr = [&](int buf, int s, int blk) { return scratch + (size_t)((buf * 2 + s) * NBLK + blk) * TILE_M * ROWB; };
+  // Split schedule (one tile per CTA): the staged input block of layer (j, l) -- the positional encoding of layer 0 and of the skip
+  // layer -- does not depend on the previous layer, and its ring entry is free as soon as the previous layer's accumulator is
+  // complete, so the epilogue warps copy it in BEFORE they drain that accumulator and the issuer starts layer l on it while the
+  // hidden blocks are still being written (the skip layer was 15,000 cycles with the copy at the end of the epilogue and no
+  // overlap).  Not for the very first layer (the prologue's copy is ordered by `aready` alone) and not after a TC_EPI_STAGE
+  // layer (whose epilogue WRITES the block its successor stages).  Evaluated identically by the issuer and the epilogue warps.
+  uint32_t early_mask = 0u;    // bit l: layer l's staged block is copied early (every tile but the very first layer of the kernel)
+  if (X3 && (P.flags & 1)) {
+    for (int l = 0; l < NL; ++l)
+      if (layer_has_pe(P.layers[l]) && !(DEC && P.layers[(l + NL - 1) % NL].epi == TC_EPI_STAGE)) early_mask |= 1u << l;
+  }
+  auto early_staged = [&](int j, int l) -> bool { return X3 && ((early_mask >> l) & 1u) != 0u && (j | l) != 0; };
 
   if (warp == 0) {
     // ============================== weight producer (TMA multicast) ==========================
@@ -305,9 +318,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1) mlp_pp_kerne
             fin = true;
           };
           const bool staged_layer = layer_has_pe(L);
+          const bool early = early_staged(j, l);
           if (X3 && !(L.flags & TC_F_ACCUM)) abuf ^= 1u;
-          if (!X3 || staged_layer) {
-            // (bf16x3: a staged input is copied at the very end of the previous epilogue -- no overlap for those layers)
+          if (!X3 || (staged_layer && !early)) {
+            // (split schedule without early staging: the input is copied at the very end of the previous epilogue -- no overlap)
             for (; kw < nk; ++kw) wait_block(kw);
             wait_final();
           }
@@ -316,14 +330,31 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1) mlp_pp_kerne
           for (int kbi = 0; kbi < L.nkb; ++kbi) {
             uint32_t a_hi, a_lo, pe_entry = 0;
             const bool is_pe = L.kb[kbi] >= TC_KB_PE;
+            // split schedule: the K-block's first weight stage does not depend on the activations -- poll its barrier BEFORE the
+            // block's (a completed mbarrier wait still costs ~150 cycles, and with one tile per CTA the last block's sits on the
+            // layer's critical chain: epilogue -> final signal -> last K-block's MMAs -> accumulator barrier -> epilogue)
+            bool prewaited = false;
+            if (X3 && (P.flags & 2)) {
+              const uint32_t cw = cnt + (is_pe ? 1u : 0u);
+              mbar_wait(bar_full + 8 * (cw % N_ENTRIES), (cw / N_ENTRIES) & 1u);
+              prewaited = true;
+            }
             // bf16x3: hidden block kbi is complete once phase kbi+1 of the previous epilogue has been signalled
-            if (X3 && !fin) {
+            if (X3 && !fin && !early) {
               if (kbi < nk) {
                 wait_block(kbi);
                 kw = kbi + 1;
               } else {
                 wait_final();
               }
+            } else if (X3 && !fin && !is_pe) {
+              // early-staged layer: the staged block (waited for on its ring entry below) precedes the hidden blocks in K order
+              const int hb = (int)L.kb[kbi];
+              while (kw < nk && kw <= hb) {
+                wait_block(kw);
+                ++kw;
+              }
+              if (hb >= nk) wait_final();
             }
             if (is_pe) {
               pe_entry = cnt % N_ENTRIES;
@@ -343,7 +374,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1) mlp_pp_kerne
               const uint32_t e = cnt % N_ENTRIES, par = (cnt / N_ENTRIES) & 1u;
               long long t_f0 = 0;
               if (tr) t_f0 = clock64();
-              mbar_wait(bar_full + 8 * e, par);
+              if (!(prewaited && part == 0)) mbar_wait(bar_full + 8 * e, par);
               tcgen05_fence_after();
               if (tr) t_full += clock64() - t_f0;
               const uint64_t bdesc = make_smem_desc_sw64(sbase + SMEM_RING + e * 2u * SLOT_BYTES);
@@ -653,7 +684,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1) mlp_pp_kerne
       mbar_arrive(bar_aready + 8 * pend.s);
       pend.on = false;
     };
-
     // first layer's bias + the PE blocks of iteration 0
     bias_s[et] = P.bias[et];
     {
@@ -696,11 +726,49 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1) mlp_pp_kerne
           if (tr) t_e0 = clock64();
 
           if (L.epi == TC_EPI_VIEW0) prefetch_row_l1(P.view_bias + ray * P.view_w, P.view_w);   // hidden behind the wait
+          const bool next_valid = jn < n_iter && valid_slot(jn, s);
+          const bool early_next = next_valid && early_staged(jn, ln);
+          // early staging (see early_staged): the next layer's staged block is pulled from the L2-resident scratch into L1 before the
+          // accumulator wait (no registers held across it) ...
+          const uint4* esrc = nullptr;
+          if (early_next) {
+            if (jn != pe_waited_j) {
+              mbar_wait(bar_pe_ready + 8 * (jn & 1), (uint32_t)(jn >> 1) & 1u);
+              pe_waited_j = jn;
+            }
+            esrc = reinterpret_cast<const uint4*>(scr(jn & 1, s, layer_staged(P.layers[ln]))) + row;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              asm volatile("prefetch.global.L1 [%0];" ::"l"(esrc + (4 * hf + k) * TILE_M));
+              asm volatile("prefetch.global.L1 [%0];" ::"l"(esrc + (8 + 4 * hf + k) * TILE_M));
+            }
+          }
           mbar_wait(bar_acc + 8 * s, acc_par[s]);
           acc_par[s] ^= 1u;
           tcgen05_fence_after();
           if (tr) t_e1 = clock64();
-          if (pend.on) pe_store();  // every ring entry before the pending PE block has now been consumed
+          if (early_next) {
+            // ... and copied into its ring entry (one slot: the consumer's entries follow this layer's, all earlier ones are consumed now), published
+            // through the entry's `full` barrier alone: the issuer waits for it before the staged K-block and consumes `aready` after the
+            // layer's last hidden block as for any other layer
+            const uint32_t e = (cnt + ents) % N_ENTRIES;
+            uint8_t* dst = smem + SMEM_RING + (size_t)e * 2 * SLOT_BYTES;
+            uint4 eh[4], el[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) eh[k] = esrc[(4 * hf + k) * TILE_M];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) el[k] = esrc[(8 + 4 * hf + k) * TILE_M];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) *reinterpret_cast<uint4*>(dst + swz(row, (uint32_t)(4 * hf + k))) = eh[k];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) *reinterpret_cast<uint4*>(dst + SLOT_BYTES + swz(row, (uint32_t)(4 * hf + k))) = el[k];
+            fence_proxy_async();
+            named_bar_sync(2, EPI_THREADS);
+            if (et == 0) mbar_arrive(bar_full + 8 * e);
+            maybe_free(jn, ln, s);
+          } else if (pend.on) {
+            pe_store();  // every ring entry before the pending PE block has now been consumed
+          }
 
           if (L.epi == TC_EPI_RGB) {
             if (hf == 0) {
@@ -824,9 +892,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1) mlp_pp_kerne
           fence_proxy_async();
 
           // hand the slot back to the MMA issuer; if its next layer consumes the PE block, stage that first
-          const bool next_valid = jn < n_iter && valid_slot(jn, s);
           if (next_valid) {
-            if (next_has_pe) {
+            if (next_has_pe && !early_next) {
               // ring position of the next layer of this slot: the rest of this layer, then the earlier slots of the next
               uint32_t cn = cnt + ents;
               bool between = false;  // another layer-slot is issued between this one and the consumer
@@ -903,6 +970,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1) mlp_pp_kerne
 
 }  // namespace pp
 
+static int g_pp_flags = 3;   // bit 0: early staging in the split schedule, bit 1: weight barrier polled before the activation block's (debug: dfn_debug_set_pp_flags)
+void pp_set_flags(int flags) { g_pp_flags = flags; }
+
 int64_t pp_scratch_bytes() { return (int64_t)(num_sms() + 1) * 2 * 2 * tc::TILE_M * 256; }
 int64_t pp_dec_scratch_bytes() { return 3 * pp_scratch_bytes(); }  // three staged blocks per tile
 
@@ -943,6 +1013,7 @@ int pp_launch_prog(const TcProgram& prog, const uint32_t* woff32, const uint8_t*
   P.multires = multires;
   P.multires_views = multires_views;
   P.view_w = view_w;
+  P.flags = g_pp_flags;
   for (int i = 0; i < prog.n_layers; ++i) {
     P.layers[i] = prog.layers[i];
     P.layers[i].woff = woff32[i];

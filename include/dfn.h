@@ -379,6 +379,11 @@ int dfn_debug_trace(void* dev_buffer, int tiles);
  * flag 1 a layer's weights are loaded once for both slots, 2 CTA-scope release on the peer's arrivals (default 3), 8 / 16
  * keep the Decoder head / torso programs on mlp_pp.cu. */
 int dfn_debug_set_impl(int impl);
+/* Schedule switches of the split-precision kernel (mlp_pp.cu; A/B measurements).  Bit 0 (default on): a layer's staged input
+ * block (the positional encoding of layer 0 and of the skip layer) is copied into its ring entry at the START of the previous
+ * layer's epilogue, so that layer's MMAs overlap the epilogue; 0: copied at its end (the round-1 schedule; bit-identical output).
+ * Bit 1 (default on): the issuer polls a K-block's weight-stage barrier before the activation block's. */
+int dfn_debug_set_pp_flags(int flags);
 int dfn_profile_collect(double* kernel_ms, int64_t* launches, double* algorithmic_macs);
 
 /* ---- f-3  training step  (MAIN:855-931: two-field forward on N_rand rays, img2mse x2, loss.backward(), Adam) ---------

@@ -22,6 +22,8 @@ ro, rd, vd = [t.reshape(-1, 3)[:R].contiguous() for t in (ro, rd, vd)]
 z, _ = torch.sort(torch.rand(R, S, device=dev) * 0.6 + 0.4, -1)
 aud = fr['aud'].to(dev)
 eng = dfn.RenderEngine(net, None, S, 0, precision={'bf16': dfn.PREC_BF16, 'bf16x3': dfn.PREC_BF16X3, 'fp16x3m': dfn.PREC_FP16X3M}[mode])
+if os.environ.get('DFN_PP_FLAGS'):
+    dfn.lib.dfn_debug_set_pp_flags(int(os.environ['DFN_PP_FLAGS']))      # schedule switches of mlp_pp.cu
 eng.query_points(net, ro, rd, vd, z, aud)
 T, NL = 6, 12
 buf = torch.zeros(2 * T * NL * 8 + T * NL * 2 * 16, dtype=torch.int64, device=dev)
