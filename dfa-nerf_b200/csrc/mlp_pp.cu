@@ -58,6 +58,7 @@ struct Params {
   const float* bias;       // [n_layers][256], latent already folded
   const float* view_bias;  // [R][W/2]
   const float* dot_w;      // Decoder density head folded into an epilogue (TC_F_DOT_SIGMA): row [256] + bias, or null
+  const float* dot_b;      // TC_F_DOT_ALPHA: alpha_linear's bias (dot_w = its weight row, fp32)
   const float* rays_o;
   const float* rays_d;
   const float* z_vals;
@@ -626,10 +627,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1) mlp_pp_kerne
     uint32_t abuf = 0u;                   // accumulator buffer of the current layer (mirrors the MMA issuer)
     uint32_t cnt = 0;                     // ring entries before the current (j, l, s) in MMA order
     float alpha[2] = {0.f, 0.f};
+    float* alpha_s = reinterpret_cast<float*>(smem + SMEM_DOT);   // TC_F_DOT_ALPHA: the tile's densities [128] (the region is otherwise
+    bool dot_alpha_prog = false;                                  // used by the single-pass Decoder kernels only)
     int pe_waited_j = -1;
     int last_pe_layer = 0;
-    for (int l2 = 0; l2 < NL; ++l2)
+    for (int l2 = 0; l2 < NL; ++l2) {
       if (layer_has_pe(P.layers[l2])) last_pe_layer = l2;
+      if (!DEC && (P.layers[l2].flags & TC_F_DOT_ALPHA)) dot_alpha_prog = true;
+    }
     // the scratch buffer of iteration jj is dead once its last slot's copy for the last PE-consuming layer is made
     auto maybe_free = [&](int jj, int layer, int s) {
       if (layer != last_pe_layer) return;
@@ -785,7 +790,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1) mlp_pp_kerne
                   o.y = sigmoid_f(o.y);
                   o.z = sigmoid_f(o.z);
                 }
-                o.w = alpha[s];
+                o.w = dot_alpha_prog ? alpha_s[row] : alpha[s];
                 reinterpret_cast<float4*>(P.raw)[pt] = o;
               }
             }
@@ -834,6 +839,23 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1) mlp_pp_kerne
                 mbar_arrive(bar_kready + 8 * k);
               }
             };
+            // TC_F_DOT_ALPHA: density = alpha_linear.weight . relu(out) + bias from the fp32 activations (rows r0 and r0 + 8 of this thread,
+            // its 16 columns of every block; the four lanes of a quad hold a row's other columns)
+            const bool dot_alpha = !DEC && (L.flags & TC_F_DOT_ALPHA) != 0;
+            float dsum[2] = {0.f, 0.f};
+            auto dot16 = [&](const uint32_t (&v)[32], const float (&b)[16], int kb) {
+              const float2* wp = reinterpret_cast<const float2*>(P.dot_w + kb * 64 + 2 * (lane & 3));
+#pragma unroll
+              for (int g = 0; g < 8; ++g) {
+                const float2 w = __ldg(wp + 4 * g);
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                  const float x0 = fmaxf(__uint_as_float(v[4 * g + 2 * h]) + b[2 * g], 0.f);
+                  const float x1 = fmaxf(__uint_as_float(v[4 * g + 2 * h + 1]) + b[2 * g + 1], 0.f);
+                  dsum[h] = fmaf(x1, w.y, fmaf(x0, w.x, dsum[h]));
+                }
+              }
+            };
             tmem_ld_16x256b_x8(accp, v0);
             for (int kb = 0; kb < nkb_out; kb += 2) {
               float b[16];
@@ -842,6 +864,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1) mlp_pp_kerne
               if (kb + 1 < nkb_out) tmem_ld_16x256b_x8(accp + (uint32_t)(kb + 1) * 64u, v1);
               epilogue_piece_cd_split<F16>(v0, b, arena_hi + (size_t)kb * KB_BYTES, arena_lo + (size_t)kb * KB_BYTES, need_lo, r0, (uint32_t)lane);
               done(kb);
+              if (dot_alpha) dot16(v0, b, kb);
               if (kb + 1 < nkb_out) {
                 bias16(kb + 1, b);
                 tmem_ld_wait();
@@ -849,6 +872,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1) mlp_pp_kerne
                 epilogue_piece_cd_split<F16>(v1, b, arena_hi + (size_t)(kb + 1) * KB_BYTES, arena_lo + (size_t)(kb + 1) * KB_BYTES, need_lo, r0,
                                              (uint32_t)lane);
                 done(kb + 1);
+                if (dot_alpha) dot16(v1, b, kb + 1);
+              }
+            }
+            if (dot_alpha) {
+              const float ab = __ldg(P.dot_b);
+#pragma unroll
+              for (int h = 0; h < 2; ++h) {
+                float t = dsum[h];
+                t += __shfl_xor_sync(0xffffffffu, t, 1);
+                t += __shfl_xor_sync(0xffffffffu, t, 2);
+                if ((lane & 3) == 0) alpha_s[r0 + 8u * (uint32_t)h] = t + ab;     // read by the row's owner in the TC_EPI_RGB epilogue
               }
             }
           } else {
@@ -970,7 +1004,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1) mlp_pp_kerne
 
 }  // namespace pp
 
-static int g_pp_flags = 3;   // bit 0: early staging in the split schedule, bit 1: weight barrier polled before the activation block's (debug: dfn_debug_set_pp_flags)
+static int g_pp_flags = 7;   // bit 0: early staging in the split schedule, bit 1: weight barrier polled before the activation block's,
+                             // bit 2: fp16x3m evaluates alpha_linear in the last trunk layer's epilogue (debug: dfn_debug_set_pp_flags)
 void pp_set_flags(int flags) { g_pp_flags = flags; }
 
 int64_t pp_scratch_bytes() { return (int64_t)(num_sms() + 1) * 2 * 2 * tc::TILE_M * 256; }
@@ -992,7 +1027,7 @@ static int pp_launch_t(const pp::Params& P, int grid, cudaStream_t st) {
 int pp_launch_prog(const TcProgram& prog, const uint32_t* woff32, const uint8_t* w_hi, const uint8_t* w_lo, const float* dot_w,
                    bool decoder, int multires, int multires_views, int view_w, const float* bias_ws, const float* vbias_ws, void* scratch, int64_t R, int S,
                    const float* rays_o, const float* rays_d, const float* z_vals, float* raw, int precision,
-                   cudaStream_t st) {
+                   cudaStream_t st, const float* dot_b) {
   pp::Params P;
   memset(&P, 0, sizeof(P));
   P.w_hi = w_hi;
@@ -1000,6 +1035,7 @@ int pp_launch_prog(const TcProgram& prog, const uint32_t* woff32, const uint8_t*
   P.bias = bias_ws;
   P.view_bias = vbias_ws;
   P.dot_w = dot_w;
+  P.dot_b = dot_b;
   P.rays_o = rays_o;
   P.rays_d = rays_d;
   P.z_vals = z_vals;
@@ -1054,10 +1090,16 @@ int pp_launch(const dfn_model* m, const float* bias_ws, const float* vbias_ws, v
     // product everywhere else (profiles/precision_emulation.py --sweep: those four layers carry the whole sensitivity).
     TcProgram prog = m->prog;
     const int D = m->desc.D, skip = m->desc.skip;
+    // bit 2 of the schedule switches: alpha_linear in fp32 inside the epilogue of the last trunk layer (TC_F_DOT_ALPHA), which leaves
+    // views_linears.0 single-pass as well (its density row is computed and ignored)
+    const bool dot_alpha = (g_pp_flags & 4) != 0 && m->alpha.w != nullptr && m->alpha.b != nullptr && m->desc.W == 256 && D >= 2 &&
+                           prog.layers[D - 1].epi == TC_EPI_RELU && prog.layers[D].epi == TC_EPI_VIEW0;
     for (int i = 0; i < prog.n_layers; ++i)
-      if (!(i > skip && i <= D)) prog.layers[i].flags |= TC_F_SINGLE;
-    return pp_launch_prog(prog, m->tc32_woff, m->tc_h16, m->tc_l16, nullptr, false, m->desc.multires, m->desc.multires_views, m->desc.W / 2,
-                          bias_ws, vbias_ws, scratch, R, S, rays_o, rays_d, z_vals, raw, precision, st);
+      if (!(i > skip && i <= (dot_alpha ? D - 1 : D))) prog.layers[i].flags |= TC_F_SINGLE;
+    if (dot_alpha) prog.layers[D - 1].flags |= TC_F_DOT_ALPHA;
+    return pp_launch_prog(prog, m->tc32_woff, m->tc_h16, m->tc_l16, dot_alpha ? m->alpha.w : nullptr, false, m->desc.multires,
+                          m->desc.multires_views, m->desc.W / 2, bias_ws, vbias_ws, scratch, R, S, rays_o, rays_d, z_vals, raw, precision, st,
+                          dot_alpha ? m->alpha.b : nullptr);
   }
   return pp_launch_prog(m->prog, m->tc32_woff, m->tc_hi, m->tc_lo, nullptr, false, m->desc.multires, m->desc.multires_views, m->desc.W / 2,
                         bias_ws, vbias_ws,

@@ -40,7 +40,11 @@ enum {
   TC_F_DOT_SIGMA = 2,  // TC_EPI_RELU layer: density register = dot_w[0..255] . relu(out) + dot_w[256]
   // split modes (mlp_pp.cu, X3): this layer issues the hi x hi product only (DFN_PREC_FP16X3M: everything but the layers that form the
   // density after the skip connection)
-  TC_F_SINGLE = 4
+  TC_F_SINGLE = 4,
+  // split modes, FaceNeRF / NeRF (DFN_PREC_FP16X3M): alpha_linear (HELP:286 / 383) is evaluated in fp32 on the CUDA cores inside the
+  // epilogue of the last trunk layer, from its fp32 activations -- so views_linears.0, whose MMA otherwise carries the density as an
+  // output row and needs the three split products for it, runs single-pass.  dot_w = alpha_linear.weight [W], dot_b = its bias.
+  TC_F_DOT_ALPHA = 8
 };
 static constexpr int TC_DOT_FLOATS = 256 + 4;
 static constexpr int TC_MAX_LAYERS = 20;
@@ -105,7 +109,7 @@ int64_t pp_dec_scratch_bytes();
 int pp_launch_prog(const TcProgram& prog, const uint32_t* woff32, const uint8_t* w_hi, const uint8_t* w_lo, const float* dot_w, bool decoder,
                    int multires, int multires_views, int view_w, const float* bias_ws, const float* vbias_ws, void* scratch, int64_t R, int S,
                    const float* rays_o, const float* rays_d, const float* z_vals, float* raw, int precision,
-                   cudaStream_t st);
+                   cudaStream_t st, const float* dot_b = nullptr);
 int pp_launch(const dfn_model* m, const float* bias_ws, const float* vbias_ws, void* scratch, int64_t R, int S,
               const float* rays_o, const float* rays_d, const float* z_vals, float* raw, int precision,
               cudaStream_t st);

@@ -11,7 +11,7 @@ import dfa_nerf_b200 as dfn  # noqa: E402
 import synth  # noqa: E402
 
 R = int(sys.argv[1]) if len(sys.argv) > 1 else 20000
-flag_sets = [int(x) for x in sys.argv[2].split(',')] if len(sys.argv) > 2 else [0, 1, 2, 3]
+flag_sets = [int(x) for x in sys.argv[2].split(',')] if len(sys.argv) > 2 else [0, 3, 7]
 S = 192
 dev = torch.device('cuda', 0)
 net = dfn.FaceNeRF(D=8, W=256, input_ch=63, input_ch_views=27, dim_aud=64, output_ch=4, skips=[4], use_viewdirs=True)
@@ -47,8 +47,10 @@ try:
             outs[f] = raw.clone()
             msg = ''
             if f != flag_sets[0]:
-                msg = '  bit-identical to flags %d: %s  finite=%s' % (flag_sets[0], bool(torch.equal(outs[f], outs[flag_sets[0]])),
-                                                                     bool(torch.isfinite(outs[f]).all()))
+                d = (outs[f] - outs[flag_sets[0]]).abs()
+                msg = '  bit-identical to flags %d: %s  (max |d rgb_raw| %.2e, |d sigma| %.2e)  finite=%s' % (
+                    flag_sets[0], bool(torch.equal(outs[f], outs[flag_sets[0]])), d[..., :3].max().item(), d[..., 3].max().item(),
+                    bool(torch.isfinite(outs[f]).all()))
             print('FaceNeRF %s flags=%d: %.3f ms -> %.1f TFLOP/s%s' % (mode, f, ms, 2 * 557184 * R * S / ms / 1e9, msg), flush=True)
     # Decoder fields (bf16x3 on mlp_pp.cu)
     dec = dfn.Decoder(z_dim=256, hidden_size=256, dim_signal=96, use_deformation_field=True)
@@ -71,4 +73,4 @@ try:
                                                                       torch.equal(outs[f][1], outs[flag_sets[0]][1])))
         print('Decoder head+torso bf16x3 (%d rays x 64) flags=%d: %.3f ms%s' % (R * 3, f, ms, msg), flush=True)
 finally:
-    dfn.lib.dfn_debug_set_pp_flags(3)
+    dfn.lib.dfn_debug_set_pp_flags(7)

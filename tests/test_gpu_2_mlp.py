@@ -325,3 +325,35 @@ def test_pair_kernel_stress_bit_identical(dfn):
             assert torch.equal(out, ref), rep
     finally:
         dfn.lib.dfn_debug_set_impl(-1)
+
+
+def test_split_schedule_switches(dfn):
+    """dfn_debug_set_pp_flags: early staging of the skip layer's input and the weight-barrier order (bits 0, 1) change WHEN things
+    happen, never what is computed -- bit-identical to the round-1 schedule (flags 0) in both parity modes, ragged and multi-tile sizes;
+    bit 2 (fp16x3m: alpha_linear in fp32 inside the last trunk layer's epilogue, views_linears.0 single-pass) changes the arithmetic and is
+    gated against the fp32 oracle like the mode itself."""
+    net = face(dfn, 1)
+    sd = synth.facenerf_state_dict(1)
+    try:
+        for R, S in ((37, 64), (700, 192), (5000, 64)):
+            ro, rd, vd, z, aud = _query_case(R, S, seed=13)
+            args = [t.to(DEV) for t in (ro, rd, vd, z, aud)]
+            for prec in (dfn.PREC_BF16X3, dfn.PREC_FP16X3M):
+                eng = dfn.RenderEngine(net, None, S, 0, precision=prec)
+                outs = {}
+                for f in (0, 1, 2, 3, 7):
+                    dfn.lib.dfn_debug_set_pp_flags(f)
+                    outs[f] = eng.query_points(net, *args).clone()
+                for f in (1, 2, 3):
+                    assert torch.equal(outs[f], outs[0]), (R, S, prec, f)
+                if prec == dfn.PREC_BF16X3:
+                    assert torch.equal(outs[7], outs[0])          # bit 2 is an fp16x3m switch
+                elif R <= 700:
+                    with torch.no_grad():
+                        ref = O.run_network(sd, 'facenerf', ro[:, None] + rd[:, None] * z[:, :, None], vd, aud)
+                    for f in (3, 7):
+                        ew, ec = _alpha_err(outs[f], ref, z, rd)
+                        print('fp16x3m flags %d R=%d: weights %.2e colours %.2e sigma %.2e' % (f, R, ew, ec, maxerr(outs[f][..., 3], ref[..., 3])))
+                        assert ew < 1e-4 and ec < 1e-4, (f, ew, ec)
+    finally:
+        dfn.lib.dfn_debug_set_pp_flags(7)
