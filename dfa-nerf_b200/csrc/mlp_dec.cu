@@ -464,9 +464,12 @@ static int dec_query(const dfn_decoder* m, int field, int64_t R, int S, const fl
   }
   // split precision: the plain programs on mlp_pp.cu; single-pass: the folded-head programs on the CTA-pair kernel (mlp_pair.cu; the
   // torso's in its own layout), or -- debug flags 8 / 16, hidden != 256 -- on mlp_pp.cu
+  const dfn_decoder_desc& d0 = m->desc;
   const DecField& P2 = field == 0 ? m->g[0] : m->tp;
   const bool on_pair = precision != DFN_PREC_BF16X3 && P2.w2_hi != nullptr && !(pair_get_flags() & (field == 0 ? 8 : 16));
-  const DecField& F = on_pair ? P2 : (precision == DFN_PREC_BF16X3 ? m->f[field] : m->g[field]);
+  // (split precision with schedule switch 4: the folded-head program as well, sigma_out in fp32 from the fp32 activations of blocks[6])
+  const bool x3_folded = precision == DFN_PREC_BF16X3 && (pp_get_flags() & 4) != 0 && m->g[field].dot_w != nullptr && d0.hidden == 256;
+  const DecField& F = on_pair ? P2 : (precision == DFN_PREC_BF16X3 && !x3_folded ? m->f[field] : m->g[field]);
   const dfn_decoder_desc& d = m->desc;
   float* bias_ws = reinterpret_cast<float*>(workspace);
   void* scratch = reinterpret_cast<char*>(workspace) + align256((int64_t)TC_MAX_LAYERS * TC_BIAS_STRIDE * 4);
@@ -488,7 +491,8 @@ static int dec_query(const dfn_decoder* m, int field, int64_t R, int S, const fl
   int rc = on_pair ? pair_launch_prog(F.prog, F.woff2, precision == DFN_PREC_FP16 ? F.w2_h16 : F.w2_hi, precision == DFN_PREC_FP16, true, d.n_freq,
                                       d.n_freq_views, d.hidden, bias_ws, nullptr, F.dot_w, scratch, R, S, rays_o, rays_d, z_vals, raw, st)
                    : pp_launch_prog(F.prog, F.woff32, precision == DFN_PREC_FP16 ? F.w_h16 : F.w_hi, F.w_lo, F.dot_w, true, d.n_freq, d.n_freq_views,
-                                    d.hidden, bias_ws, nullptr, scratch, R, S, rays_o, rays_d, z_vals, raw, precision, st);
+                                    d.hidden, bias_ws, nullptr, scratch, R, S, rays_o, rays_d, z_vals, raw, precision, st,
+                                    F.dot_w != nullptr ? F.dot_w + TC_BIAS_STRIDE : nullptr);
   if (prof) profile_end(st);
   if (rc) return rc;
   DFN_LAUNCH_CHECK();

@@ -633,7 +633,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1) mlp_pp_kerne
     int last_pe_layer = 0;
     for (int l2 = 0; l2 < NL; ++l2) {
       if (layer_has_pe(P.layers[l2])) last_pe_layer = l2;
-      if (!DEC && (P.layers[l2].flags & TC_F_DOT_ALPHA)) dot_alpha_prog = true;
+      if (P.layers[l2].flags & (DEC ? TC_F_DOT_SIGMA : TC_F_DOT_ALPHA)) dot_alpha_prog = true;
     }
     // the scratch buffer of iteration jj is dead once its last slot's copy for the last PE-consuming layer is made
     auto maybe_free = [&](int jj, int layer, int s) {
@@ -841,7 +841,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1) mlp_pp_kerne
             };
             // TC_F_DOT_ALPHA: density = alpha_linear.weight . relu(out) + bias from the fp32 activations (rows r0 and r0 + 8 of this thread,
             // its 16 columns of every block; the four lanes of a quad hold a row's other columns)
-            const bool dot_alpha = !DEC && (L.flags & TC_F_DOT_ALPHA) != 0;
+            const bool dot_alpha = DEC ? (L.flags & TC_F_DOT_SIGMA) != 0 : (L.flags & TC_F_DOT_ALPHA) != 0;   // (Decoder: sigma_out, DEC:329)
             float dsum[2] = {0.f, 0.f};
             auto dot16 = [&](const uint32_t (&v)[32], const float (&b)[16], int kb) {
               const float2* wp = reinterpret_cast<const float2*>(P.dot_w + kb * 64 + 2 * (lane & 3));
@@ -1005,8 +1005,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1) mlp_pp_kerne
 }  // namespace pp
 
 static int g_pp_flags = 7;   // bit 0: early staging in the split schedule, bit 1: weight barrier polled before the activation block's,
-                             // bit 2: fp16x3m evaluates alpha_linear in the last trunk layer's epilogue (debug: dfn_debug_set_pp_flags)
+                             // bit 2: the density head (alpha_linear in fp16x3m, the Decoder's sigma_out in bf16x3) is evaluated in fp32 inside the last
+                             // trunk layer's epilogue (debug: dfn_debug_set_pp_flags)
 void pp_set_flags(int flags) { g_pp_flags = flags; }
+int pp_get_flags() { return g_pp_flags; }
 
 int64_t pp_scratch_bytes() { return (int64_t)(num_sms() + 1) * 2 * 2 * tc::TILE_M * 256; }
 int64_t pp_dec_scratch_bytes() { return 3 * pp_scratch_bytes(); }  // three staged blocks per tile
@@ -1058,9 +1060,11 @@ int pp_launch_prog(const TcProgram& prog, const uint32_t* woff32, const uint8_t*
   grid = (grid + 1) & ~1;
   if (grid > num_sms()) grid = num_sms() & ~1;
   const bool x3 = precision == DFN_PREC_BF16X3 || precision == DFN_PREC_FP16X3M;
+  // folded density head: packed 16-bit row in shared memory on the single-pass Decoder kernels; fp32 row + bias (dot_w, dot_b) read
+  // through L1 by the split kernels' column-distributed epilogue
   for (int i = 0; i < prog.n_layers; ++i)
-    if ((prog.layers[i].flags & TC_F_DOT_SIGMA) && (x3 || !decoder || dot_w == nullptr)) {
-      set_error("pp_launch_prog: a program with a folded density head runs on the single-pass Decoder kernels only");
+    if ((prog.layers[i].flags & TC_F_DOT_SIGMA) && (!decoder || dot_w == nullptr || (x3 && dot_b == nullptr))) {
+      set_error("pp_launch_prog: a program with a folded density head needs the Decoder kernels and its head row");
       return DFN_E_STATE;
     }
   if (precision == DFN_PREC_FP16X3M) {   // w_hi / w_lo: the fp16 stages and their fp16 residuals; TC_F_SINGLE set by the caller

@@ -121,7 +121,8 @@ int pair_launch_prog(const TcProgram& prog, const uint32_t* woff2, const uint8_t
 void pair_set_epilogue_warps(int ew);
 int pair_get_flags();
 void pair_set_flags(int flags);
-void pp_set_flags(int flags);   // mlp_pp.cu: bit 0 early staging in the split schedule
+void pp_set_flags(int flags);   // mlp_pp.cu schedule switches (dfn_debug_set_pp_flags)
+int pp_get_flags();
 struct TcHostDump {   // host-only view of a packed model (dfn_model_program_host)
   std::vector<float> dense;    // [layer][256][6][64]
   std::vector<float> bias;     // [TC_MAX_LAYERS][256]

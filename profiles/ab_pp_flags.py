@@ -69,8 +69,9 @@ try:
         outs[f] = (head.clone(), person.clone())
         msg = ''
         if f != flag_sets[0]:
-            msg = '  bit-identical to flags %d: %s' % (flag_sets[0], bool(torch.equal(outs[f][0], outs[flag_sets[0]][0]) and
-                                                                      torch.equal(outs[f][1], outs[flag_sets[0]][1])))
+            msg = '  bit-identical to flags %d: %s (max |d person| %.2e)' % (
+                flag_sets[0], bool(torch.equal(outs[f][0], outs[flag_sets[0]][0]) and torch.equal(outs[f][1], outs[flag_sets[0]][1])),
+                (outs[f][1] - outs[flag_sets[0]][1]).abs().max().item())
         print('Decoder head+torso bf16x3 (%d rays x 64) flags=%d: %.3f ms%s' % (R * 3, f, ms, msg), flush=True)
 finally:
     dfn.lib.dfn_debug_set_pp_flags(7)
