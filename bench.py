@@ -7,7 +7,7 @@
     python bench.py --workload head_torso       # BASELINE.json configs[2]: the reference's live two-field frame
     python bench.py --workload coarse64         # configs[0]: 64x64 rays x 64 coarse samples (the reference's CPU-sized case)
     python bench.py --workload mlp_1m           # configs[3]: flat 8x256 NeRF query, 2^20 rays x 192 samples (roofline sweep)
-    python bench.py --workload sequence --steps 1   # configs[4]: driven sequence (--frames N, default 300), frames sharded
+    python bench.py --workload sequence --steps 1   # configs[4]: driven sequence (--frames N, default 300); N > 1: frames ray-sharded
     python bench.py --workload train_step       # the reference's training step (2048 rays x 64 samples x 2 fields,
                                                 # forward + backward + Adam), value = training rays/s
 
@@ -205,7 +205,8 @@ WORKLOADS = {
     'mlp_1m': 'Synthetic random-weight 8x256 NeRF (no latent), 2^20 rays x 192 samples, flat network query + compositing '
               '(BASELINE.json configs[3]); one step = all rays',
     'sequence': 'Audio-driven FaceNeRF sequence, 450x450 x (64+128) per frame, per-frame pose + latent tables, uint8 frames '
-                'copied out double-buffered, FRAMES sharded over the GPUs (BASELINE.json configs[4]); one step = the sequence',
+                'copied out double-buffered; several GPUs: every frame sharded by rays, uint8 tiles gathered on a side stream '
+                '(BASELINE.json configs[4]); one step = the sequence',
 }
 WORKLOADS['train_step'] = 'Training step of the live model (MAIN:764-931): 2048 random rays x 64 samples x (head + torso) Decoder fields, ' \
                           'two-field compositing, two MSE losses, backward, Adam on decoder + AudNet + ExpNet; synthetic 450x450 targets; ' \
@@ -328,6 +329,9 @@ class Job:
             self.lat_host = self.seq['aud'].pin_memory()
             self.bc_dev = fr['bc_rgb'].to(dev)
             self.aud_dev = None
+            # several GPUs: every frame split by rays (1/G of the frame latency, no tail imbalance; DFN_BENCH_SEQ_SHARD=frames: whole
+            # frames per rank, the round-1 form)
+            self.seq_shard = os.environ.get('DFN_BENCH_SEQ_SHARD', 'rays') if world > 1 else 'frames'
         else:
             if prec == dfn.PREC_FP32:
                 raise SystemExit('--workload head_torso runs on the tensor-core path: --precision bf16 | fp16 | bf16x3')
@@ -368,8 +372,8 @@ class Job:
         seq, world = self.seq, self.ctx['world']
         n = self.frames if n is None else n
         frames = self.dfn.render_sequence(self.eng, H, W, seq['focal'], seq['c2w_seq'][:n], self.lat_host[:n], self.bc_dev, seq['near'],
-                                          seq['far'], seq['cx'], seq['cy'])
-        self.launches += (self.eng.last_launches + 2) * ((n + world - 1) // world)
+                                          seq['far'], seq['cx'], seq['cy'], shard=self.seq_shard)
+        self.launches += (self.eng.last_launches + 2) * (n if self.seq_shard == 'rays' else (n + world - 1) // world)
         return frames
 
     def step_train(self, e2e=False):
@@ -420,6 +424,10 @@ class Job:
         """Network evaluations this rank performs per step."""
         if self.workload == 'sequence':
             world, rank = self.ctx['world'], self.ctx['rank']
+            if self.seq_shard == 'rays':
+                from dfa_nerf_b200.distributed import shard_range
+                b, e, _ = shard_range(H * W, rank, world)
+                return (e - b) * self.evals_per_ray * self.frames
             f0, f1 = self.dfn.shard_frames(self.frames, rank, world)
             return H * W * self.evals_per_ray * (f1 - f0)
         return (self.e - self.b) * self.evals_per_ray
@@ -644,7 +652,7 @@ def main():
             'data': 'synthetic',
             'config': {'workload': WORKLOADS[args.workload],
                        'rays_per_step': job.n_rays, 'mlp_evals_per_ray': job.evals_per_ray, 'precision': args.precision,
-                       'parallelism': ('frames sharded over %d GPU(s), uint8 frames gathered to rank 0 per frame' % world)
+                       'parallelism': ('every frame ray-sharded over %d GPU(s), uint8 tiles all-gathered per frame on a side stream' % world)
                        if args.workload == 'sequence' else 'single GPU' if args.workload == 'train_step' else 'rays sharded over %d GPU(s), one all-gather of the RGB tile per frame on a side stream (frame i gathers / copies out while frame i+1 renders)' % world,
                        'l2': 'per-step intermediates (~1.4 GB of raw/z buffers) exceed the 126 MB L2; no explicit flush'},
             'e2e': main_res['e2e'], 'gpu_launches': main_res['gpu_launches'], 'clocks': clocks, 'roofline': main_res['roofline'],

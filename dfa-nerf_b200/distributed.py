@@ -82,9 +82,12 @@ class RayShardSink:
                 self.host = [h.pin_memory() for h in self.host]
         self.stream = torch.cuda.Stream(device=device) if self.cuda else None
         self.done = [None] * depth
+        self.ext = [None] * depth
         self.i = 0
 
-    def push(self, local_rgb):
+    def push(self, local_rgb, host_out=None):
+        """host_out (rank dst): a pinned [n_rays, C] tensor that receives this frame instead of the ring slot (a sequence buffer
+        the caller keeps); wait(i) then only synchronises."""
         i, s = self.i, self.i % self.depth
         rows = local_rgb.shape[0]
         if rows > self.per:
@@ -99,19 +102,22 @@ class RayShardSink:
             ready.record(cur)
             with torch.cuda.stream(self.stream):
                 self.stream.wait_event(ready)
-                self._finish_frame(s)
+                self._finish_frame(s, host_out)
                 ev = torch.cuda.Event()
                 ev.record(self.stream)
             self.done[s] = ev
         else:
-            self._finish_frame(s)
+            self._finish_frame(s, host_out)
+        self.ext[s] = host_out if self.is_dst else None
         self.i += 1
         return i
 
-    def _finish_frame(self, s):
+    def _finish_frame(self, s, host_out=None):
         if self.world > 1:
             dist.all_gather_into_tensor(self.full[s], self.send[s], group=self.group)
-        if self.host is not None:
+        if self.is_dst and host_out is not None:
+            host_out.copy_(self.full[s][:self.n].reshape(host_out.shape), non_blocking=True)
+        elif self.host is not None:
             self.host[s].copy_(self.full[s][:self.n], non_blocking=True)
 
     def _check(self, i):
@@ -123,6 +129,8 @@ class RayShardSink:
         s = self._check(i)
         if self.cuda and self.done[s] is not None:
             self.done[s].synchronize()
+        if self.ext[s] is not None:
+            return self.ext[s]
         return self.host[s] if self.host is not None else None
 
     def device(self, i):

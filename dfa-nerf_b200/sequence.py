@@ -164,24 +164,29 @@ class _Null:
 
 @torch.no_grad()
 def render_sequence(engine, H, W, focal, poses, auds, bc_rgb, near, far, cx=None, cy=None, group=None, gather=True,
-                    on_frame=None, keep=True):
+                    on_frame=None, keep=True, shard='frames'):
     """FaceNeRF / NeRF sequence: poses [N,3,4] (or [N,4,4]), auds [N,dim_aud] (None for NeRF), one background.
     One process: returns uint8 frames [N,H,W,3] in pinned host memory.  Several ranks (torch.distributed initialised): the
     frames are sharded in contiguous blocks; gather=True delivers the whole sequence to rank 0 (return value there, None on
     the other ranks), gather=False returns this rank's block [n_local,H,W,3].
     on_frame(i, u8[1,H,W,3]): called per finished frame with its global index (e.g. a FrameWriter) -- on this rank for its
     own frames (gather=False) or on rank 0 for all of them (gather=True).  keep=False (needs on_frame): stream through a
-    small pinned ring instead of keeping the sequence, returns None."""
+    small pinned ring instead of keeping the sequence, returns None.
+    shard='rays' (several ranks): every FRAME is split over the ranks by rays instead -- each rank renders 1/G of every frame, the
+    uint8 tiles are all-gathered and rank 0 copies the frame out on a side stream while the next frame renders
+    (distributed.RayShardSink).  Same frames, 1/G of the per-frame latency (a live loop), and no tail imbalance when G does not
+    divide the frame count; rank 0 returns the sequence, the other ranks None."""
     poses_host = torch.as_tensor(poses, dtype=torch.float32).detach().cpu()     # ONE device->host copy for the sequence: get_rays
     #                                                                             takes the pose as kernel arguments
-    return _run(lambda i, bc, lat: engine.render_frame(H, W, focal, poses_host[i, :3, :4], bc, lat, near, far, cx, cy)['rgb_map'],
-                H, W, poses.shape[0], bc_rgb, auds, group, gather, on_frame=on_frame, keep=keep)
+    return _run(lambda i, bc, lat, rr=None: engine.render_frame(H, W, focal, poses_host[i, :3, :4], bc, lat, near, far, cx, cy,
+                                                                ray_range=rr)['rgb_map'],
+                H, W, poses.shape[0], bc_rgb, auds, group, gather, on_frame=on_frame, keep=keep, shard=shard)
 
 
 @torch.no_grad()
 def render_sequence_head_torso(decoder, H, W, focal, poses, pose_torso, bc_rgb, z_shape, z_app, signals, signals_torso,
                                near, far, cx=None, cy=None, N_samples=64, precision=None, group=None, gather=True,
-                               on_frame=None, with_head=False, keep=True):
+                               on_frame=None, with_head=False, keep=True, shard='frames'):
     """The reference's live loop MAIN:624-733: head poses [N,3,4], one fixed body pose (MAIN:644), per-frame head
     signals [N,dim_signal] and torso signals [N,dim_et_embed].  Returns the `person` frames (MAIN:712-715) as uint8
     [N,H,W,3]; with_head=True keeps both images of a frame, [N,2,H,W,3] = (head, person) (MAIN:712-722 writes both)."""
@@ -196,16 +201,50 @@ def render_sequence_head_torso(decoder, H, W, focal, poses, pose_torso, bc_rgb, 
     rays_torso = [t.reshape(-1, 3) for t in get_rays(H, W, focal, torch.as_tensor(pose_torso).detach().cpu()[:3, :4], cx, cy,
                                                       device=bc_rgb.device)]
 
-    def frame(i, bc, l):
+    def frame(i, bc, l, rr=None):
         both = render_head_torso(decoder, H, W, focal, poses_host[i, :3, :4], None, bc, z_shape, z_app, l[:ds], l[ds:],
-                                 near, far, cx, cy, N_samples=N_samples, precision=precision, rays_torso=rays_torso)
+                                 near, far, cx, cy, N_samples=N_samples, precision=precision, rays_torso=rays_torso, ray_range=rr)
         return torch.cat(both, 0) if with_head else both[1]
-    return _run(frame, H, W, poses.shape[0], bc_rgb, lat, group, gather, planes=2 if with_head else 1, on_frame=on_frame, keep=keep)
+    if shard == 'rays' and with_head:
+        raise DfnError('render_sequence_head_torso: shard="rays" delivers the person image only (with_head=False)')
+    return _run(frame, H, W, poses.shape[0], bc_rgb, lat, group, gather, planes=2 if with_head else 1, on_frame=on_frame, keep=keep,
+                shard=shard)
 
 
-def _run(render_one, H, W, n_frames, bc_rgb, latents, group, gather, planes=1, on_frame=None, keep=True):
+def _run_ray_sharded(render_one, H, W, n_frames, bc, lat_dev, device, group, rank, world, on_frame, keep):
+    """shard='rays': every rank renders its ray range of EVERY frame; RayShardSink gathers the uint8 tiles and copies the frame out
+    on rank 0 while the next frame renders; the host hands frame i-1 on (on_frame) while frame i is in flight."""
+    from .distributed import RayShardSink, shard_range
+    n = H * W
+    b, e, _ = shard_range(n, rank, world)
+    sink = RayShardSink(n, device, channels=3, dtype=torch.uint8, group=group, to_host=True)
+    out = None
+    if rank == 0 and keep:
+        out = torch.empty((max(n_frames, 1), H, W, 3), dtype=torch.uint8).pin_memory()
+
+    def deliver(i):
+        h = sink.wait(i)
+        if rank == 0 and on_frame is not None:
+            fr = h.reshape(1, H, W, 3).numpy()
+            on_frame(i, fr if keep else fr.copy())
+
+    for i in range(n_frames):
+        tile = render_one(i, bc, lat_dev[i] if lat_dev is not None else None, (b, e)) if e > b else \
+            torch.zeros((0, 3), dtype=torch.float32, device=device)
+        sink.push(to8b(tile), host_out=out[i] if out is not None else None)
+        if i > 0:
+            deliver(i - 1)
+    if n_frames > 0:
+        deliver(n_frames - 1)
+    sink.finish()
+    return out[:n_frames] if out is not None else None
+
+
+def _run(render_one, H, W, n_frames, bc_rgb, latents, group, gather, planes=1, on_frame=None, keep=True, shard='frames'):
     if not bc_rgb.is_cuda:
         raise DfnError('dfa_nerf_b200 has no CPU path: bc_rgb must be a CUDA tensor')
+    if shard not in ('frames', 'rays'):
+        raise DfnError('shard must be "frames" or "rays"')
     device = bc_rgb.device
     multi = dist.is_available() and dist.is_initialized()
     rank = dist.get_rank(group) if multi else 0
@@ -213,6 +252,10 @@ def _run(render_one, H, W, n_frames, bc_rgb, latents, group, gather, planes=1, o
     f0, f1 = shard_frames(n_frames, rank, world)
     lat_dev = latents.to(device, torch.float32).contiguous() if latents is not None else None   # one upload for the sequence
     bc = bc_rgb.reshape(-1, 3)
+    if shard == 'rays' and world > 1:
+        if not keep and on_frame is None:
+            raise DfnError('keep=False needs an on_frame consumer')
+        return _run_ray_sharded(render_one, H, W, n_frames, bc, lat_dev, device, group, rank, world, on_frame, keep)
     squeeze = (lambda t: t[:, 0]) if planes == 1 else (lambda t: t)
     if world > 1 and gather:
         fg = FrameGather(n_frames, H, W, device, planes=planes, group=group, on_frame=on_frame)

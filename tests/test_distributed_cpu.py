@@ -183,6 +183,17 @@ def _sink_worker(rank, world, port, n, q):
                     ok &= torch.equal(h, frames[i - 1])
             ok &= torch.equal(sink.device(i), f)        # every rank holds the gathered frame
         sink.finish()
+        # uint8 tiles and a caller-owned sequence buffer (the ray-sharded sequence loop, sequence._run_ray_sharded)
+        seq = torch.zeros((3, 7, 9, 3), dtype=torch.uint8) if rank == 0 else None
+        s8 = RayShardSink(n, 'cpu', dtype=torch.uint8)
+        f8 = [(torch.arange(n * 3, dtype=torch.int64).reshape(n, 3) * (k + 3) % 251).to(torch.uint8) for k in range(3)]
+        for k, f in enumerate(f8):
+            s8.push(f[b:e], host_out=seq[k] if seq is not None else None)
+            got = s8.wait(k)
+            ok &= (got is not None) == (rank == 0)
+            if got is not None:
+                ok &= got.data_ptr() == seq[k].data_ptr() and torch.equal(seq[k].reshape(n, 3), f)
+        s8.finish()
         try:
             sink.wait(1)                                # long recycled
             ok = False
