@@ -24,16 +24,33 @@ z, _ = torch.sort(torch.rand(R, S, device=dev) * 0.6 + 0.4, -1)
 aud = fr['aud'].to(dev)
 
 
-def timed(fn, n=3):
+N_TIMED = int(os.environ.get('AB_REPEATS', 3))
+CLOCKS = os.environ.get('AB_CLOCKS') == '1'      # sample nvidia-smi SM clocks / power during the timed loop (bench.ClockSampler)
+
+
+def timed(fn, n=None):
+    n = n or N_TIMED
     for _ in range(2):
         out = fn()
     torch.cuda.synchronize()
+    smp = None
+    if CLOCKS:
+        import bench
+        smp = bench.ClockSampler(0)
+        smp.start()
+        import time
+        time.sleep(0.2)
+        smp.mark()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     for _ in range(n):
         out = fn()
     ev1.record()
     torch.cuda.synchronize()
+    if smp is not None:
+        c = smp.stop()
+        pw = sorted(float(r[2]) for t, r in smp.rows if t >= smp.t0 and len(r) > 2 and r[2].replace('.', '').isdigit())
+        print('   clocks: %s MHz median, power %.0f W median, %s' % (c['sm_mhz'], pw[len(pw) // 2] if pw else -1, c['reasons']), flush=True)
     return out, ev0.elapsed_time(ev1) / n
 
 
@@ -64,7 +81,7 @@ try:
     for f in flag_sets:
         dfn.lib.dfn_debug_set_pp_flags(f)
         (head, person), ms = timed(lambda: dfn.render_head_torso(dec, 450, 450, fr['focal'], fr['c2w'], c2w_t, fr['bc_rgb'].to(dev), zs, za, sig, sig_t,
-                                                                 fr['near'], fr['far'], fr['cx'], fr['cy'], N_samples=64, ray_range=(0, R * 3),
+                                                                 fr['near'], fr['far'], fr['cx'], fr['cy'], N_samples=64, ray_range=(0, min(R * 3, 450 * 450)),
                                                                  precision=dfn.PREC_BF16X3))
         outs[f] = (head.clone(), person.clone())
         msg = ''
@@ -72,6 +89,6 @@ try:
             msg = '  bit-identical to flags %d: %s (max |d person| %.2e)' % (
                 flag_sets[0], bool(torch.equal(outs[f][0], outs[flag_sets[0]][0]) and torch.equal(outs[f][1], outs[flag_sets[0]][1])),
                 (outs[f][1] - outs[flag_sets[0]][1]).abs().max().item())
-        print('Decoder head+torso bf16x3 (%d rays x 64) flags=%d: %.3f ms%s' % (R * 3, f, ms, msg), flush=True)
+        print('Decoder head+torso bf16x3 (%d rays x 64) flags=%d: %.3f ms%s' % (min(R * 3, 450 * 450), f, ms, msg), flush=True)
 finally:
     dfn.lib.dfn_debug_set_pp_flags(7)

@@ -110,6 +110,26 @@ if rnd == 'r01':
     report('headtorso', 'head_torso_kernel (live two-field compositing): 202,500 rays x 64 samples')
     report('sortmerge', 'sort_merge_kernel: 202,500 rays x (64 + 128)')
     report('samplepdf', 'sample_pdf_kernel: 202,500 rays, 63 bins -> 128 samples')
+elif rnd == 'r02b':
+    # late round 2: register-resident render_prep_kernel, early staging / folded density heads in the split kernels, RayShardSink
+    frame = 202500
+    launches('', 'bench.py --steps 2 --warmup 3 --no-extras --no-cpu-baseline')
+    launches('_ht', 'bench.py --workload head_torso --steps 2 --warmup 3 --no-extras --no-cpu-baseline')
+    report('bench_pair', 'mlp_pair_kernel<bf16>: the bench frame\'s coarse (202,500 x 64) and fine (202,500 x 192) launches')
+    report('bench_x3m', 'mlp_pp_kernel<fp16x3m> (early staging, alpha_linear in the last trunk layer\'s epilogue): the bench frame\'s coarse and fine launches')
+    report('bench_x3', 'mlp_pp_kernel<bf16x3> (early staging): the bench frame\'s coarse and fine launches')
+    report('bench_dec_x3', 'mlp_pp_kernel<bf16x3, Decoder> (folded-head programs, sigma_out in fp32 in the epilogue): the head_torso frame\'s head and torso launches')
+    report('stages', 'HBM-bound stage kernels of the bench frame: render_prep_kernel<27>, coarse_to_fine_kernel<2>, volume_weights_kernel<1,6>')
+    traffic('bench_pair', 'mlp_pair_kernel<bf16>', [frame * 64, frame * 192], also=('mlp_pair_kernel<fp16>',))
+    traffic('bench_x3m', 'mlp_pp_kernel<fp16x3m>', [frame * 64, frame * 192])
+    traffic('bench_x3', 'mlp_pp_kernel<bf16x3>', [frame * 64, frame * 192])
+    traffic('bench_dec_x3', 'mlp_pp_kernel<bf16x3, Decoder>', [frame * 64, frame * 64])
+    if TRAFFIC:
+        import json
+        tp = os.path.join(ROOT, 'profiles', 'traffic.json')
+        old = json.load(open(tp)) if os.path.exists(tp) else {}
+        old.update(TRAFFIC)
+        json.dump(old, open(tp, 'w'), indent=1)
 else:
     launches('', 'bench.py --steps 2 --warmup 3 --no-extras --no-cpu-baseline')
     launches('_ht', 'bench.py --workload head_torso --steps 2 --warmup 3 --no-extras --no-cpu-baseline')
