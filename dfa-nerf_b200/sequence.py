@@ -36,12 +36,17 @@ class FrameSink:
     keep=False: a ring of `depth + 2` pinned slots is recycled and on_frame receives its own copy of each frame (a job
     that streams thousands of frames to disk pins a few MB, not the sequence); finish() returns None."""
 
-    def __init__(self, n_frames, H, W, device, depth=2, planes=1, on_frame=None, keep=True):
+    def __init__(self, n_frames, H, W, device, depth=2, planes=1, on_frame=None, keep=True, host=None):
         if not keep and on_frame is None:
             raise DfnError('FrameSink(keep=False) needs an on_frame consumer')
         self.keep = keep
         self.slots = n_frames if keep else depth + 2
-        self.host = torch.empty((max(self.slots, 1), planes, H, W, 3), dtype=torch.uint8).pin_memory()
+        if host is not None:       # caller-owned pinned sequence buffer (pinning ~180 MB costs ~0.1 s: a loop that renders many
+            if not keep or not host.is_pinned() or host.dtype != torch.uint8 or host.numel() < max(self.slots, 1) * planes * H * W * 3:
+                raise DfnError('FrameSink: host must be a pinned uint8 buffer of at least n_frames*planes*H*W*3 bytes (keep=True)')
+            self.host = host.reshape(-1)[:max(self.slots, 1) * planes * H * W * 3].reshape(max(self.slots, 1), planes, H, W, 3)
+        else:                      # sequences allocates it once and passes it in)
+            self.host = torch.empty((max(self.slots, 1), planes, H, W, 3), dtype=torch.uint8).pin_memory()
         self.dev = [torch.empty((planes, H, W, 3), dtype=torch.uint8, device=device) for _ in range(depth)]
         self.copied = [None] * depth
         self.stream = torch.cuda.Stream(device=device)
@@ -164,7 +169,7 @@ class _Null:
 
 @torch.no_grad()
 def render_sequence(engine, H, W, focal, poses, auds, bc_rgb, near, far, cx=None, cy=None, group=None, gather=True,
-                    on_frame=None, keep=True, shard='frames'):
+                    on_frame=None, keep=True, shard='frames', out=None):
     """FaceNeRF / NeRF sequence: poses [N,3,4] (or [N,4,4]), auds [N,dim_aud] (None for NeRF), one background.
     One process: returns uint8 frames [N,H,W,3] in pinned host memory.  Several ranks (torch.distributed initialised): the
     frames are sharded in contiguous blocks; gather=True delivers the whole sequence to rank 0 (return value there, None on
@@ -175,12 +180,14 @@ def render_sequence(engine, H, W, focal, poses, auds, bc_rgb, near, far, cx=None
     shard='rays' (several ranks): every FRAME is split over the ranks by rays instead -- each rank renders 1/G of every frame, the
     uint8 tiles are all-gathered and rank 0 copies the frame out on a side stream while the next frame renders
     (distributed.RayShardSink).  Same frames, 1/G of the per-frame latency (a live loop), and no tail imbalance when G does not
-    divide the frame count; rank 0 returns the sequence, the other ranks None."""
+    divide the frame count; rank 0 returns the sequence, the other ranks None.
+    out: a caller-owned PINNED uint8 buffer of at least N*H*W*3 bytes that receives the frames (one process, or shard='rays' on rank 0)
+    instead of a freshly pinned one."""
     poses_host = torch.as_tensor(poses, dtype=torch.float32).detach().cpu()     # ONE device->host copy for the sequence: get_rays
     #                                                                             takes the pose as kernel arguments
     return _run(lambda i, bc, lat, rr=None: engine.render_frame(H, W, focal, poses_host[i, :3, :4], bc, lat, near, far, cx, cy,
                                                                 ray_range=rr)['rgb_map'],
-                H, W, poses.shape[0], bc_rgb, auds, group, gather, on_frame=on_frame, keep=keep, shard=shard)
+                H, W, poses.shape[0], bc_rgb, auds, group, gather, on_frame=on_frame, keep=keep, shard=shard, out=out)
 
 
 @torch.no_grad()
@@ -211,7 +218,7 @@ def render_sequence_head_torso(decoder, H, W, focal, poses, pose_torso, bc_rgb, 
                 shard=shard)
 
 
-def _run_ray_sharded(render_one, H, W, n_frames, bc, lat_dev, device, group, rank, world, on_frame, keep):
+def _run_ray_sharded(render_one, H, W, n_frames, bc, lat_dev, device, group, rank, world, on_frame, keep, host=None):
     """shard='rays': every rank renders its ray range of EVERY frame; RayShardSink gathers the uint8 tiles and copies the frame out
     on rank 0 while the next frame renders; the host hands frame i-1 on (on_frame) while frame i is in flight."""
     from .distributed import RayShardSink, shard_range
@@ -220,7 +227,12 @@ def _run_ray_sharded(render_one, H, W, n_frames, bc, lat_dev, device, group, ran
     sink = RayShardSink(n, device, channels=3, dtype=torch.uint8, group=group, to_host=True)
     out = None
     if rank == 0 and keep:
-        out = torch.empty((max(n_frames, 1), H, W, 3), dtype=torch.uint8).pin_memory()
+        if host is not None:
+            if not host.is_pinned() or host.dtype != torch.uint8 or host.numel() < max(n_frames, 1) * H * W * 3:
+                raise DfnError('render_sequence: out must be a pinned uint8 buffer of at least N*H*W*3 bytes')
+            out = host.reshape(-1)[:max(n_frames, 1) * H * W * 3].reshape(max(n_frames, 1), H, W, 3)
+        else:
+            out = torch.empty((max(n_frames, 1), H, W, 3), dtype=torch.uint8).pin_memory()
 
     def deliver(i):
         h = sink.wait(i)
@@ -240,7 +252,7 @@ def _run_ray_sharded(render_one, H, W, n_frames, bc, lat_dev, device, group, ran
     return out[:n_frames] if out is not None else None
 
 
-def _run(render_one, H, W, n_frames, bc_rgb, latents, group, gather, planes=1, on_frame=None, keep=True, shard='frames'):
+def _run(render_one, H, W, n_frames, bc_rgb, latents, group, gather, planes=1, on_frame=None, keep=True, shard='frames', out=None):
     if not bc_rgb.is_cuda:
         raise DfnError('dfa_nerf_b200 has no CPU path: bc_rgb must be a CUDA tensor')
     if shard not in ('frames', 'rays'):
@@ -255,7 +267,7 @@ def _run(render_one, H, W, n_frames, bc_rgb, latents, group, gather, planes=1, o
     if shard == 'rays' and world > 1:
         if not keep and on_frame is None:
             raise DfnError('keep=False needs an on_frame consumer')
-        return _run_ray_sharded(render_one, H, W, n_frames, bc, lat_dev, device, group, rank, world, on_frame, keep)
+        return _run_ray_sharded(render_one, H, W, n_frames, bc, lat_dev, device, group, rank, world, on_frame, keep, host=out)
     squeeze = (lambda t: t[:, 0]) if planes == 1 else (lambda t: t)
     if world > 1 and gather:
         fg = FrameGather(n_frames, H, W, device, planes=planes, group=group, on_frame=on_frame)
@@ -264,7 +276,7 @@ def _run(render_one, H, W, n_frames, bc_rgb, latents, group, gather, planes=1, o
             fg.push(to8b(render_one(i, bc, lat_dev[i] if lat_dev is not None else None)) if i < f1 else None)
         out = fg.finish()
         return squeeze(out) if out is not None else None
-    sink = FrameSink(max(f1 - f0, 1), H, W, device, planes=planes, keep=keep,
+    sink = FrameSink(max(f1 - f0, 1), H, W, device, planes=planes, keep=keep, host=out if world == 1 else None,
                      on_frame=(lambda k, fr: on_frame(f0 + k, fr)) if on_frame is not None else None)
     for i in range(f0, f1):
         sink.push(render_one(i, bc, lat_dev[i] if lat_dev is not None else None))
