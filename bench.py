@@ -20,7 +20,7 @@ stream, frame i's gather under frame i+1's kernels (dfa_nerf_b200.RayShardSink).
 Printed JSON (rank 0), one line:
   value         rays/s with inputs resident in HBM             e2e      the same through the public API, pinned-host
   roofline      tcgen05 MLP kernel vs the measured bf16 peak            inputs / outputs copied every step (the frame's
-                                                                        D2H double-buffered; the host takes frame i-1)
+                                                                        D2H triple-buffered; the host takes frame i-2)
   modes         the same frame in the other tensor-core precisions (value, e2e, roofline fraction) -- bf16x3 is the
                 mode that meets the 1e-4 float tolerance, bf16 the one BASELINE.json's config names
   parity        max-abs RGB error of every precision against the CPU arm's render of the same rays: teacher-forced (the
@@ -393,7 +393,7 @@ class Job:
 
     def sink(self, to_host):
         if to_host not in self.sinks:
-            self.sinks[to_host] = self.dfn.RayShardSink(self.n_rays, self.ctx['dev'], to_host=to_host)
+            self.sinks[to_host] = self.dfn.RayShardSink(self.n_rays, self.ctx['dev'], to_host=to_host, depth=3)
         return self.sinks[to_host]
 
     def step_resident(self):
@@ -417,12 +417,14 @@ class Job:
         bc_full = torch.empty((self.n_rays, 3), dtype=torch.float32, device=dev)
         bc_full[self.b:self.e] = bc
         rgb = self.render(bc_full, lat)
-        # frame loop as a user of the package writes it (dfa_nerf_b200.RayShardSink): frame i's all-gather and rank 0's copy into
-        # pinned host memory run on a side stream while frame i+1 renders; the host takes frame i-1 (blocking on ITS copy) each step
+        # frame loop as a user of the package writes it (dfa_nerf_b200.RayShardSink, three buffers): frame i's all-gather and rank 0's
+        # copy into pinned host memory run on a side stream while the next frames render; every step the host takes frame i-2 (blocking
+        # on ITS copy), i.e. it runs at most two frames ahead of the device -- with eight ranks coupled through the gather, one frame of
+        # slack left the GPUs waiting for the slowest host of the previous frame
         sink = self.sink(True)
         i = sink.push(rgb)
-        if i > 0:
-            sink.wait(i - 1)
+        if i > 1:
+            sink.wait(i - 2)
 
     def points_per_step(self):
         """Network evaluations this rank performs per step."""

@@ -68,7 +68,8 @@ struct Params {
   int view_w;
   unsigned long long* trace;  // debug: per-role clock64 records of CTA 0 (null in production), format of mlp_tc.cu
   int trace_tiles;
-  int flags;                  // bit 0: a layer's weights stay in the ring for both slots; bit 1: CTA-scope release on the peer's `aready` arrivals
+  int flags;                  // bit 0: a layer's weights stay in the ring for both slots; bit 1: CTA-scope release on the peer's `aready` arrivals;
+                              // bit 2: per-ray bias rows staged in shared memory (column-distributed readout of the view layer)
   int dec;                    // Decoder head program (DEC:277-349): the encoding of DEC:257-275, sigma_out as a 16-column layer, sigmoid colours
   int multires_views;         // Decoder: frequencies of the view-direction encoding
   // Staged inputs: the slot's fifth block is (re)filled n_fills times per tile by the helper warps -- fill k holds staged block
@@ -305,6 +306,18 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((4 + 2 * EW) * 32, 1
       if (!valid) pt = P.n_points - 1;
       const int64_t ray = pt / P.S;
 
+      // Per-ray-bias layer (views_linears.0, HELP:288-292): when the sample count is a multiple of 32 every warp's 32 rows lie on ONE ray,
+      // and a 128-point tile touches at most two rays -- their two bias rows [view_w] fit the slot's 256-float bias staging area, so the
+      // layer runs the column-distributed readout of every other layer (bias from shared memory, conflict-free) instead of the
+      // row-per-thread one with 64 global bias loads per thread, which was the longest epilogue of the program (2.2-2.9k against 1.7k
+      // cycles) on the chain of the program's short tail layers.  Same fp32 add, ReLU and rounding: bit-identical.
+      // (S % 32 == 0 and S >= 64: at most two rays per tile; the tile's first / last ray follow from this row's own ray without
+      // another division)
+      const bool vfast = !DEC && (P.flags & 4) && (P.S & 31) == 0 && P.S >= 64 && 2 * P.view_w <= TC_BIAS_STRIDE;
+      const int64_t vp0 = (int64_t)tile * TILE_M;
+      const int64_t vp1 = vp0 + TILE_M - 1 < P.n_points - 1 ? vp0 + TILE_M - 1 : P.n_points - 1;
+      const int64_t vray0 = ray - (ray * P.S > vp0 ? 1 : 0);
+      const int64_t vray1 = ray + ((ray + 1) * P.S - 1 < vp1 ? 1 : 0);
       stage_bias(P.bias);   // the first layer's bias
       // the tile's positional encoding was written into the PE K-block by the helper warps (below), one tile ahead
       mbar_wait(bar_peready + 8 * s, (uint32_t)(j * nf) & 1u);
@@ -318,7 +331,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((4 + 2 * EW) * 32, 1
         const bool tr = P.trace != nullptr && blockIdx.x == 0 && tid_s == 0 && j < P.trace_tiles;
         long long t_e0 = 0, t_e1 = 0;
         if (tr) t_e0 = clock64();
-        if (!DEC && L.epi == TC_EPI_VIEW0) prefetch_row_l1(P.view_bias + ray * P.view_w + hf * (P.view_w / NH), P.view_w / NH);   // hidden behind the wait
+        if (!DEC && !vfast && L.epi == TC_EPI_VIEW0) prefetch_row_l1(P.view_bias + ray * P.view_w + hf * (P.view_w / NH), P.view_w / NH);   // hidden behind the wait
         mbar_wait(bar_acc + 8 * s, acc_par);
         acc_par ^= 1u;
         tcgen05_fence_after();
@@ -373,7 +386,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((4 + 2 * EW) * 32, 1
           wait_fill_for(l + 1, j);
           signal_ready();
         } else {
-          if (!DEC && L.epi == TC_EPI_VIEW0) {
+          const bool vf = !DEC && vfast && L.epi == TC_EPI_VIEW0;
+          if (!DEC && !vf && L.epi == TC_EPI_VIEW0) {
             const int per = P.view_w / NH;
             epilogue_relu_rows16<true, F16>(acc, hf * per, (hf + 1) * per, P.view_bias + ray * P.view_w, 0u, arena, row);
             if (hf == 0) {
@@ -387,9 +401,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((4 + 2 * EW) * 32, 1
             const int per = ((int)L.n >> 6) / NH;
             alpha = epilogue_relu_cd_dotpart<F16>(acc, hf * per, (hf + 1) * per, smem_u32(bias_s), sbase + SMEM_DOT, arena,
                                                   (uint32_t)((warp & 3) * 32), (uint32_t)lane);
-          } else if ((L.n % (64 * NH)) == 0) {
-            const int per = ((int)L.n >> 6) / NH;
-            epilogue_relu_cd<F16, EW == 4>(acc, hf * per, (hf + 1) * per, smem_u32(bias_s), arena, (uint32_t)((warp & 3) * 32), (uint32_t)lane);
+          } else if (vf || (L.n % (64 * NH)) == 0) {
+            // vf: bias_s = [ray vray0's row | ray vray1's row] (staged below instead of the layer's static bias); this warp's rows are one ray's
+            const int per = ((vf ? P.view_w : (int)L.n) >> 6) / NH;
+            const uint32_t sb = smem_u32(bias_s) + (vf && ray != vray0 ? (uint32_t)P.view_w * 4u : 0u);
+            epilogue_relu_cd<F16, EW == 4>(acc, hf * per, (hf + 1) * per, sb, arena, (uint32_t)((warp & 3) * 32), (uint32_t)lane);
+            if (vf && hf == 0) {
+              uint32_t v[16];
+              tmem_ld16(acc + P.view_w, v);
+              tmem_ld_wait();
+              alpha = __uint_as_float(v[0]) + __ldg(P.bias + l * TC_BIAS_STRIDE + P.view_w);
+            }
           } else {
             const int per = (int)L.n / NH;
             epilogue_relu_rows16<false, F16>(acc, hf * per, (hf + 1) * per, nullptr, smem_u32(bias_s), arena, row);
@@ -408,7 +430,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((4 + 2 * EW) * 32, 1
         if (l + 1 < P.n_layers) {
           named_bar_sync(1 + s, ETH);
           if (dot_next_rgb && hf == 1) bias_s[tid_s] = alpha;     // tid_s = 128 + row: the second column part of the row's density
-          else stage_bias(P.bias + (l + 1) * TC_BIAS_STRIDE);
+          else if (!DEC && vfast && P.layers[l + 1].epi == TC_EPI_VIEW0) {
+            for (int i = tid_s; i < 2 * P.view_w; i += ETH)
+              bias_s[i] = __ldg(P.view_bias + (i < P.view_w ? vray0 : vray1) * P.view_w + (i < P.view_w ? i : i - P.view_w));
+          } else stage_bias(P.bias + (l + 1) * TC_BIAS_STRIDE);
           named_bar_sync(1 + s, ETH);
         }
       }
@@ -478,7 +503,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((4 + 2 * EW) * 32, 1
 
 }  // namespace tcp
 
-static int g_pair_ew = 8, g_pair_flags = 3;   // epilogue warps per slot (debug: dfn_debug_set_impl(3) -> 8, (8) -> 4)
+static int g_pair_ew = 8, g_pair_flags = 7;   // epilogue warps per slot (debug: dfn_debug_set_impl(3) -> 8, (8) -> 4)
 void pair_set_epilogue_warps(int ew) { g_pair_ew = ew == 4 ? 4 : 8; }
 void pair_set_flags(int flags) { g_pair_flags = flags; }
 int pair_get_flags() { return g_pair_flags; }

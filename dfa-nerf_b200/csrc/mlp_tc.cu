@@ -921,7 +921,7 @@ int tc_query_points(const dfn_model* m, int64_t R, int S, const float* rays_o, c
   const bool prof = profile_begin(st, macs_pt * (double)P.n_points);
   // default: bf16x3 -> mlp_pp.cu (2), bf16 / fp16 -> the CTA-pair kernel mlp_pair.cu (3)
   const int impl = g_impl >= 0 ? (g_impl & 15) : ((precision == DFN_PREC_BF16X3 || precision == DFN_PREC_FP16X3M) ? 2 : 3);
-  pair_set_flags(g_impl >= 16 ? (g_impl >> 4) - 1 : 3);   // debug: flags + 1 in the high bits (bit 3: Decoder head stays on mlp_pp.cu)
+  pair_set_flags(g_impl >= 16 ? (g_impl >> 4) - 1 : 7);   // debug: flags + 1 in the high bits (bit 3: Decoder head stays on mlp_pp.cu)
   if (precision == DFN_PREC_FP16X3M || (impl == 2 && (precision == DFN_PREC_BF16 || precision == DFN_PREC_BF16X3))) {
     int rc = pp_launch(m, bias_ws, vbias_ws, scratch_ws, R, S, rays_o, rays_d, z_vals, raw, precision, st);
     if (rc) return rc;

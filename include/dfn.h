@@ -376,8 +376,9 @@ int dfn_debug_trace(void* dev_buffer, int tiles);
  * bf16x3 / fp16x3m -> 2).  Low 4 bits: 1 the 1-CTA generation, two tiles in flight with per-tile epilogue warps (mlp_tc.cu);
  * 2 cooperative epilogue + PE through the weight ring, the split-precision schedule (mlp_pp.cu); 3 CTA pairs, cta_group::2
  * MMAs (mlp_pair.cu); 8 the same with four epilogue warps per slot.  Higher bits: (flags + 1) << 4 for the pair kernel --
- * flag 1 a layer's weights are loaded once for both slots, 2 CTA-scope release on the peer's arrivals (default 3), 8 / 16
- * keep the Decoder head / torso programs on mlp_pp.cu. */
+ * flag 1 a layer's weights are loaded once for both slots, 2 CTA-scope release on the peer's arrivals, 4 the per-ray-bias
+ * layer's two bias rows staged in shared memory and the column-distributed readout for it (default 7), 8 / 16 keep the Decoder
+ * head / torso programs on mlp_pp.cu. */
 int dfn_debug_set_impl(int impl);
 /* Schedule switches of the split-precision kernel (mlp_pp.cu; A/B measurements).  Bit 0 (default on): a layer's staged input
  * block (the positional encoding of layer 0 and of the skip layer) is copied into its ring entry at the START of the previous
