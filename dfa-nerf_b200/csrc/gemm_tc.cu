@@ -133,6 +133,51 @@ __device__ __forceinline__ void load_row(const float* __restrict__ src, const fl
   }
 }
 
+// The same for an operand whose k stride is 1 (X, dH, W as [N, K]): 32 tile rows of this warp, one 64-wide K chunk.  Sixteen lanes
+// cover a row's 256 bytes (a float4 each), so a load instruction reads two rows' full lines (4 wavefronts) where the row-per-thread
+// mapping of load_row touches 32 rows x 16 bytes (32 wavefronts, half of every sector unused); the 8-byte bf16 stores of a row fill its
+// swizzled 128-byte line.  Same values as load_row (same mask product, same hi / lo split).
+template <bool X3>
+__device__ __forceinline__ void load_rows_kcontig(const float* __restrict__ src, const float* __restrict__ msk, int mmode, int64_t ld_r,
+                                                  int64_t row_g0, int64_t rows_valid, int k0, uint8_t* hi, uint8_t* lo, uint32_t row_l0,
+                                                  uint32_t lane) {
+  const bool sig = mmode == DFN_MASK_SIGMOID;
+  const float mlo = mmode == DFN_MASK_LEAKY ? 0.02f : 0.f;
+  const uint32_t piece = lane & 15u;           // 4 consecutive k
+#pragma unroll 1
+  for (int i0 = 0; i0 < 16; i0 += 8) {
+    float4 v[8], y[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int64_t r = row_g0 + 2 * (i0 + i) + (lane >> 4);
+      const bool ok = r < rows_valid;
+      const float4* p = reinterpret_cast<const float4*>(src + r * ld_r + k0) + piece;
+      v[i] = ok ? __ldg(p) : make_float4(0.f, 0.f, 0.f, 0.f);
+      if (msk) y[i] = ok ? __ldg(reinterpret_cast<const float4*>(msk + r * ld_r + k0) + piece) : make_float4(1.f, 1.f, 1.f, 1.f);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float4 t = v[i];
+      if (msk) {
+        t.x *= mask_factor_sel(sig, mlo, y[i].x); t.y *= mask_factor_sel(sig, mlo, y[i].y);
+        t.z *= mask_factor_sel(sig, mlo, y[i].z); t.w *= mask_factor_sel(sig, mlo, y[i].w);
+      }
+      const uint32_t row = row_l0 + 2u * (uint32_t)(i0 + i) + (lane >> 4);
+      const uint32_t off = swz(row, piece >> 1) + (piece & 1u) * 8u;
+      uint2 h;
+      h.x = pack_bf16(t.x, t.y);
+      h.y = pack_bf16(t.z, t.w);
+      *reinterpret_cast<uint2*>(hi + off) = h;
+      if (X3) {
+        uint2 l;
+        l.x = pack_lo<false>(t.x, t.y, h.x);
+        l.y = pack_lo<false>(t.z, t.w, h.y);
+        *reinterpret_cast<uint2*>(lo + off) = l;
+      }
+    }
+  }
+}
+
 template <bool X3>
 __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const __grid_constant__ Params P) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -175,6 +220,12 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const __grid_consta
     const float* src = is_a ? d.A : d.B;
     const float* msk = is_a ? d.A_mask : nullptr;
     const int64_t ld_r = is_a ? d.a_ld_r : d.b_ld_r, ld_k = is_a ? d.a_ld_k : d.b_ld_k;
+    // k-contiguous operand with 16-byte aligned rows: the coalesced mapping (whole chunks only; the K tail takes the generic path)
+    const bool kcontig = ld_k == 1 && (ld_r & 3) == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0 &&
+                         (msk == nullptr || (reinterpret_cast<uintptr_t>(msk) & 15) == 0);
+    const uint32_t row_l0 = (row & ~31u);                       // this warp's first tile row
+    const int64_t rows_valid = is_a ? d.M : (int64_t)d.N;
+    const bool warp_used = is_a || (int)row_l0 < P.n_pad;
     for (int it = 0; it < n_it; ++it) {
       const int s = it % N_STAGE;
       const uint32_t par = (uint32_t)(it / N_STAGE) & 1u;
@@ -182,7 +233,10 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const __grid_consta
       uint8_t* st = smem + (size_t)s * STAGE_BYTES;
       uint8_t* hi = is_a ? st : st + 2 * A_BYTES;
       uint8_t* lo = is_a ? st + A_BYTES : st + 2 * A_BYTES + B_BYTES;
-      if (row_used) load_row<X3>(src, msk, d.a_mask_mode, ld_r, ld_k, row_g, row_ok, (kc0 + it) * BK, d.K, hi, lo, row);
+      const int k0 = (kc0 + it) * BK;
+      if (kcontig && k0 + BK <= d.K) {
+        if (warp_used) load_rows_kcontig<X3>(src, msk, d.a_mask_mode, ld_r, (is_a ? m0 : 0) + row_l0, rows_valid, k0, hi, lo, row_l0, (uint32_t)lane);
+      } else if (row_used) load_row<X3>(src, msk, d.a_mask_mode, ld_r, ld_k, row_g, row_ok, k0, d.K, hi, lo, row);
       fence_proxy_async();
       mbar_arrive(bar_full + 8 * s);
     }
@@ -210,17 +264,23 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const __grid_consta
     umma_commit(bar_acc);
   }
 
-  if (warp < 4) {
+  if (warp < 12) {
     // ================================================ epilogue ================================================
+    // All twelve loader warps (they are idle by now): warp w reads TMEM lane quarter w % 4 and takes every third 16-column group --
+    // with four warps this readout (bias, addend, activation and store per element) was two thirds of a CTA's 113k cycles.
     mbar_wait(bar_acc, 0u);
     tcgen05_fence_after();
-    const uint32_t acc = tmem_base + ((uint32_t)(warp * 32) << 16);
+    const int qw = warp & 3, cg = warp >> 2;     // lane quarter, column-group phase
+    const uint32_t acc = tmem_base + ((uint32_t)(qw * 32) << 16);
     const bool atomic = d.k_splits > 1;
     const int act = d.act & 3;
     const bool pre_add = (d.act & 4) != 0;
+    const float* const bias_p = ks == 0 ? d.bias : nullptr;       // (kernel parameters read once, not per element)
+    const float* const add_p = ks == 0 ? d.addend : nullptr;
+    const int64_t add_r = d.add_ld_r, add_c = d.add_ld_c;
     auto finish = [&](float x, int64_t m, int n) -> float {     // bias, addend, activation of one element (first K split only)
-      if (d.bias != nullptr && ks == 0) x += d.bias[n];
-      const float add = d.addend != nullptr && ks == 0 ? d.addend[m * d.add_ld_r + (int64_t)n * d.add_ld_c] : 0.f;
+      if (bias_p != nullptr) x += __ldg(bias_p + n);
+      const float add = add_p != nullptr ? add_p[m * add_r + (int64_t)n * add_c] : 0.f;
       if (pre_add) x += add;
       if (act == 1) x = fmaxf(x, 0.f);
       else if (act == 2) x = __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-x)));
@@ -228,10 +288,11 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const __grid_consta
       if (!pre_add) x += add;
       return x;
     };
-    if (!atomic) {
-      // row per thread: 16 consecutive columns per TMEM load, written as 64 contiguous bytes of the row
-      const int64_t m = m0 + (int64_t)threadIdx.x;
-      for (int c0 = 0; c0 < P.n_pad; c0 += 16) {
+    const bool pairs = d.c_ld_c == 1 && (d.c_ld_r & 1) == 0 && (reinterpret_cast<uintptr_t>(d.C) & 7) == 0;
+    if (!atomic && !pairs) {
+      // row per thread: 16 consecutive columns per TMEM load (outputs that are not row-major pairs: transposed or odd-pitched views)
+      const int64_t m = m0 + (int64_t)(qw * 32 + lane);
+      for (int c0 = cg * 16; c0 < P.n_pad; c0 += 48) {
         uint32_t v[16];
         tmem_ld16(acc + (uint32_t)c0, v);
         tmem_ld_wait();
@@ -247,10 +308,11 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const __grid_consta
         }
       }
     } else {
-      // split-K partial tile -> fp32 reductions into C.  Column-distributed readout (tcgen05.ld.16x256b): a thread holds two adjacent
-      // columns of rows r and r + 8, so a row-major C takes ONE 8-byte reduction per pair instead of two 4-byte ones.
-      const bool pairs = d.c_ld_c == 1 && (d.c_ld_r & 1) == 0 && (reinterpret_cast<uintptr_t>(d.C) & 7) == 0;
-      for (int c0 = 0; c0 < P.n_pad; c0 += 16) {
+      // Column-distributed readout (tcgen05.ld.16x256b): a thread holds two adjacent columns of rows r and r + 8, so a row-major C takes
+      // ONE 8-byte store (or, for a split-K partial tile, one 8-byte fp32 reduction) per pair and a warp's store instruction covers eight
+      // rows x 32 contiguous bytes -- the row-per-thread readout above issues 4-byte stores at a row pitch per lane, 32 partial sectors per
+      // instruction, and was a third of this kernel's time on the forward GEMM.
+      for (int c0 = cg * 16; c0 < P.n_pad; c0 += 48) {
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
           uint32_t v[8];
@@ -263,18 +325,31 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const __grid_consta
           for (int g = 0; g < 2; ++g) {
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
-              const int64_t m = m0 + warp * 32 + 16 * half + 8 * h + (lane >> 2);
+              const int64_t m = m0 + qw * 32 + 16 * half + 8 * h + (lane >> 2);
               const int n = c0 + 8 * g + 2 * (lane & 3);
               if (m >= d.M || n >= d.N) continue;
               const bool two = n + 1 < d.N;
               const float x0 = finish(__uint_as_float(v[4 * g + 2 * h]), m, n);
               const float x1 = two ? finish(__uint_as_float(v[4 * g + 2 * h + 1]), m, n + 1) : 0.f;
               float* dst = d.C + m * d.c_ld_r + (int64_t)n * d.c_ld_c;
-              if (pairs && two) {
-                atomicAdd(reinterpret_cast<float2*>(dst), make_float2(x0, x1));
+              if (atomic) {
+                if (pairs && two) {
+                  atomicAdd(reinterpret_cast<float2*>(dst), make_float2(x0, x1));
+                } else {
+                  atomicAdd(dst, x0);
+                  if (two) atomicAdd(dst + d.c_ld_c, x1);
+                }
+              } else if (two) {
+                float2* p2 = reinterpret_cast<float2*>(dst);
+                float2 o = make_float2(x0, x1);
+                if (d.beta) {
+                  const float2 old = *p2;
+                  o.x += old.x;
+                  o.y += old.y;
+                }
+                *p2 = o;
               } else {
-                atomicAdd(dst, x0);
-                if (two) atomicAdd(dst + d.c_ld_c, x1);
+                *dst = d.beta ? *dst + x0 : x0;
               }
             }
           }

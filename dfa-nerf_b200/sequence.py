@@ -220,11 +220,12 @@ def render_sequence_head_torso(decoder, H, W, focal, poses, pose_torso, bc_rgb, 
 
 def _run_ray_sharded(render_one, H, W, n_frames, bc, lat_dev, device, group, rank, world, on_frame, keep, host=None):
     """shard='rays': every rank renders its ray range of EVERY frame; RayShardSink gathers the uint8 tiles and copies the frame out
-    on rank 0 while the next frame renders; the host hands frame i-1 on (on_frame) while frame i is in flight."""
+    on rank 0 while the next frames render; the host hands frame i-2 on (on_frame) while frames i-1 and i are in flight."""
     from .distributed import RayShardSink, shard_range
     n = H * W
     b, e, _ = shard_range(n, rank, world)
-    sink = RayShardSink(n, device, channels=3, dtype=torch.uint8, group=group, to_host=True)
+    sink = RayShardSink(n, device, channels=3, dtype=torch.uint8, group=group, to_host=True, depth=3)   # the host runs two frames ahead:
+    #                                  the ranks are coupled through the gather, one frame of slack left them waiting for the slowest host
     out = None
     if rank == 0 and keep:
         if host is not None:
@@ -244,10 +245,10 @@ def _run_ray_sharded(render_one, H, W, n_frames, bc, lat_dev, device, group, ran
         tile = render_one(i, bc, lat_dev[i] if lat_dev is not None else None, (b, e)) if e > b else \
             torch.zeros((0, 3), dtype=torch.float32, device=device)
         sink.push(to8b(tile), host_out=out[i] if out is not None else None)
-        if i > 0:
-            deliver(i - 1)
-    if n_frames > 0:
-        deliver(n_frames - 1)
+        if i > 1:
+            deliver(i - 2)
+    for i in range(max(n_frames - 2, 0), n_frames):
+        deliver(i)
     sink.finish()
     return out[:n_frames] if out is not None else None
 
