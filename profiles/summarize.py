@@ -115,7 +115,8 @@ elif rnd == 'r02b':
     frame = 202500
     launches('', 'bench.py --steps 2 --warmup 3 --no-extras --no-cpu-baseline')
     launches('_ht', 'bench.py --workload head_torso --steps 2 --warmup 3 --no-extras --no-cpu-baseline')
-    report('bench_pair', 'mlp_pair_kernel<bf16>: the bench frame\'s coarse (202,500 x 64) and fine (202,500 x 192) launches')
+    launches('_train', 'bench.py --workload train_step --steps 2 --warmup 3 --no-extras --no-cpu-baseline (twelve-warp GEMM readout)')
+    report('bench_pair', 'mlp_pair_kernel<bf16> (per-ray bias rows of the view layer staged in shared memory): the bench frame\'s coarse (202,500 x 64) and fine (202,500 x 192) launches')
     report('bench_x3m', 'mlp_pp_kernel<fp16x3m> (early staging, alpha_linear in the last trunk layer\'s epilogue): the bench frame\'s coarse and fine launches')
     report('bench_x3', 'mlp_pp_kernel<bf16x3> (early staging): the bench frame\'s coarse and fine launches')
     report('bench_dec_x3', 'mlp_pp_kernel<bf16x3, Decoder> (folded-head programs, sigma_out in fp32 in the epilogue): the head_torso frame\'s head and torso launches')
