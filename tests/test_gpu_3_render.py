@@ -215,3 +215,43 @@ def test_render_rays_ragged_ray_count(dfn):
     assert torch.equal(out['z_vals'].cpu(), ref['z_vals'])
     assert maxerr(out['rgb0'], ref['rgb0']) < 1e-4 and maxerr(out['rgb_map'], ref['rgb_map']) < 1e-4
     assert maxerr(out['rgb_map'][-5:], ref['rgb_map'][-5:]) < 1e-4
+
+
+def test_ray_shard_sink_and_sequence_out_buffer(dfn):
+    """The pipelined output side on the device (one process: no gather): RayShardSink's side-stream copies with three buffers and two
+    frames of host slack deliver every frame intact and in order, also into a caller-owned pinned buffer; render_sequence(out=...) fills
+    that buffer and returns views of it."""
+    H = W = 12
+    n = 7
+    fr = synth.frame_inputs(H=H, W=W, seed=3, n_frames=n)
+    net_c, net_f = nets(dfn, 0, 1)
+    eng = dfn.RenderEngine(net_c, net_f, 64, 128, precision=dfn.PREC_BF16X3)
+    bc = fr['bc_rgb'].to(DEV)
+    ref = [eng.render_frame(H, W, fr['focal'], fr['c2w_seq'][i], bc, fr['aud'][i].to(DEV), fr['near'], fr['far'], fr['cx'], fr['cy'])['rgb_map'].clone()
+           for i in range(n)]
+    sink = dfn.RayShardSink(H * W, torch.device(DEV), depth=3)
+    seq = torch.empty((n, H * W, 3), dtype=torch.float32).pin_memory()
+    got = {}
+    for i in range(n):
+        tile = eng.render_frame(H, W, fr['focal'], fr['c2w_seq'][i], bc, fr['aud'][i].to(DEV), fr['near'], fr['far'], fr['cx'], fr['cy'])['rgb_map']
+        k = sink.push(tile, host_out=seq[i] if i % 2 else None)       # ring slots and caller-owned rows alternate
+        assert k == i
+        if i > 1:
+            got[i - 2] = sink.wait(i - 2).clone()
+    for i in (n - 2, n - 1):
+        got[i] = sink.wait(i).clone()
+    sink.finish()
+    for i in range(n):
+        assert torch.equal(got[i], ref[i].cpu()), i
+        if i % 2:
+            assert torch.equal(seq[i], ref[i].cpu())
+    with pytest.raises(IndexError):
+        sink.wait(0)
+    out = torch.empty((n, H, W, 3), dtype=torch.uint8).pin_memory()
+    frames = dfn.render_sequence(eng, H, W, fr['focal'], fr['c2w_seq'], fr['aud'], bc, fr['near'], fr['far'], fr['cx'], fr['cy'], out=out)
+    assert frames.data_ptr() == out.data_ptr()
+    for i in range(n):
+        assert torch.equal(frames[i], dfn.to8b(ref[i]).reshape(H, W, 3).cpu())
+    with pytest.raises(dfn.DfnError):
+        dfn.render_sequence(eng, H, W, fr['focal'], fr['c2w_seq'], fr['aud'], bc, fr['near'], fr['far'], fr['cx'], fr['cy'],
+                            out=torch.empty((n, H, W, 3), dtype=torch.uint8))          # not pinned
