@@ -714,6 +714,23 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1) mlp_pp_kerne
         const int ln = (l + 1) % NL, jn = j + (l + 1 == NL ? 1 : 0);
         const bool next_has_pe = layer_has_pe(P.layers[ln]);
         const uint32_t ents_next = layer_entries<NPART>(P.layers[ln]);
+        // Per-ray-bias layer (views_linears.0) on the split schedule, as in mlp_pair.cu: with a sample count that is a multiple of 32 a
+        // warp's rows lie on one ray and the tile touches at most two, so their two bias rows replace the layer's static bias in the
+        // current staging buffer and the layer takes the column-distributed readout below (its row-per-thread readout with 128 global
+        // bias loads per thread was 4.3k cycles for 128 columns, on the chain of the program's short tail layers); bit-identical.
+        const bool vfast = X3 && !DEC && (P.flags & 8) && L.epi == TC_EPI_VIEW0 && (P.S & 31) == 0 && P.S >= 64 &&
+                           2 * P.view_w <= TC_BIAS_STRIDE && valid_slot(j, 0);
+        int64_t vray0 = 0;
+        if (vfast) {
+          const int64_t vp0 = (int64_t)tile_of(j, 0) * TILE_M, last = P.n_points - 1;
+          const int64_t vp1 = vp0 + TILE_M - 1 < last ? vp0 + TILE_M - 1 : last;
+          const int64_t myray = (vp0 + row < last ? vp0 + row : last) / P.S;
+          vray0 = myray - (myray * P.S > vp0 ? 1 : 0);
+          const int64_t vray1 = myray + ((myray + 1) * P.S - 1 < vp1 ? 1 : 0);
+          if (et < 2 * P.view_w)
+            bias_s[(gl & 1) * TC_BIAS_STRIDE + et] = __ldg(P.view_bias + (et < P.view_w ? vray0 : vray1) * P.view_w + (et < P.view_w ? et : et - P.view_w));
+          named_bar_sync(2, EPI_THREADS);
+        }
 
         for (int s = 0; s < NSLOT; ++s) {
           if (!valid_slot(j, s)) continue;
@@ -730,7 +747,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1) mlp_pp_kerne
           long long t_e0 = 0, t_e1 = 0;
           if (tr) t_e0 = clock64();
 
-          if (L.epi == TC_EPI_VIEW0) prefetch_row_l1(P.view_bias + ray * P.view_w, P.view_w);   // hidden behind the wait
+          if (L.epi == TC_EPI_VIEW0 && !vfast) prefetch_row_l1(P.view_bias + ray * P.view_w, P.view_w);   // hidden behind the wait
           const bool next_valid = jn < n_iter && valid_slot(jn, s);
           const bool early_next = next_valid && early_staged(jn, ln);
           // early staging (see early_staged): the next layer's staged block is pulled from the L2-resident scratch into L1 before the
@@ -817,17 +834,18 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1) mlp_pp_kerne
               if (cc + 2 < nch) tmem_ld32(acc + (ch0 + cc + 2) * 32, v0);
               stage_chunk<X3, F16>(v1, ch0 + cc + 1, sbias, scr(j & 1, s, (ch0 + cc + 1) >> 1), row);
             }
-          } else if (L.epi == TC_EPI_RELU && (L.n & 63) == 0) {
+          } else if ((L.epi == TC_EPI_RELU && (L.n & 63) == 0) || vfast) {
             // column-distributed readout (tc_epi.cuh): the two warps of a lane quarter take its two 16-lane halves of every
             // 64-column block, so block k is complete after everybody's k-th piece and is signalled as below; the lo plane is
             // skipped when the consuming layer is single-pass
-            const int nkb_out = (int)L.n >> 6;
+            const int nkb_out = (vfast ? P.view_w : (int)L.n) >> 6;
+            const uint32_t sbias_l = sbias + (vfast && ray != vray0 ? (uint32_t)P.view_w * 4u : 0u);   // vfast: this warp's ray's row
             const bool need_lo = !(P.layers[ln].flags & TC_F_SINGLE);
             const uint32_t accp = acc + ((uint32_t)(16 * hf) << 16);
             const uint32_t r0 = (uint32_t)(q * 32 + 16 * hf) + ((uint32_t)lane >> 2);
             uint32_t v0[32], v1[32];
             auto bias16 = [&](int kb, float (&b)[16]) {
-              const uint32_t ba = sbias + (uint32_t)(kb * 64 + 2 * (lane & 3)) * 4u;
+              const uint32_t ba = sbias_l + (uint32_t)(kb * 64 + 2 * (lane & 3)) * 4u;
 #pragma unroll
               for (int g = 0; g < 8; ++g)
                 asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(b[2 * g]), "=f"(b[2 * g + 1]) : "r"(ba + (uint32_t)g * 32u));
@@ -884,6 +902,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1) mlp_pp_kerne
                 t += __shfl_xor_sync(0xffffffffu, t, 2);
                 if ((lane & 3) == 0) alpha_s[r0 + 8u * (uint32_t)h] = t + ab;     // read by the row's owner in the TC_EPI_RGB epilogue
               }
+            }
+            if (vfast && hf == 0) {  // density head riding as accumulator column view_w (its bias is no longer in the staging buffer)
+              uint32_t v[16];
+              tmem_ld16(acc + P.view_w, v);
+              tmem_ld_wait();
+              alpha[s] = __uint_as_float(v[0]) + __ldg(P.bias + l * TC_BIAS_STRIDE + P.view_w);
             }
           } else {
             const bool per_ray = L.epi == TC_EPI_VIEW0;
@@ -1004,9 +1028,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1) mlp_pp_kerne
 
 }  // namespace pp
 
-static int g_pp_flags = 7;   // bit 0: early staging in the split schedule, bit 1: weight barrier polled before the activation block's,
+static int g_pp_flags = 15;   // bit 0: early staging in the split schedule, bit 1: weight barrier polled before the activation block's,
                              // bit 2: the density head (alpha_linear in fp16x3m, the Decoder's sigma_out in bf16x3) is evaluated in fp32 inside the last
-                             // trunk layer's epilogue (debug: dfn_debug_set_pp_flags)
+                             // trunk layer's epilogue, bit 3: the per-ray-bias layer's two bias rows staged in shared memory, column-distributed readout
+                             // (debug: dfn_debug_set_pp_flags)
 void pp_set_flags(int flags) { g_pp_flags = flags; }
 int pp_get_flags() { return g_pp_flags; }
 

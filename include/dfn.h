@@ -383,7 +383,9 @@ int dfn_debug_set_impl(int impl);
 /* Schedule switches of the split-precision kernel (mlp_pp.cu; A/B measurements).  Bit 0 (default on): a layer's staged input
  * block (the positional encoding of layer 0 and of the skip layer) is copied into its ring entry at the START of the previous
  * layer's epilogue, so that layer's MMAs overlap the epilogue; 0: copied at its end (the round-1 schedule; bit-identical output).
- * Bit 1 (default on): the issuer polls a K-block's weight-stage barrier before the activation block's. */
+ * Bit 1 (default on): the issuer polls a K-block's weight-stage barrier before the activation block's.  Bit 2 (default on): the
+ * density head (alpha_linear in DFN_PREC_FP16X3M, the Decoder's sigma_out in DFN_PREC_BF16X3) is evaluated in fp32 inside the last
+ * trunk layer's epilogue.  Bit 3 (default on): the per-ray-bias layer reads its two bias rows from shared memory (bit-identical). */
 int dfn_debug_set_pp_flags(int flags);
 int dfn_profile_collect(double* kernel_ms, int64_t* launches, double* algorithmic_macs);
 

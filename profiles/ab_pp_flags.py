@@ -11,7 +11,7 @@ import dfa_nerf_b200 as dfn  # noqa: E402
 import synth  # noqa: E402
 
 R = int(sys.argv[1]) if len(sys.argv) > 1 else 20000
-flag_sets = [int(x) for x in sys.argv[2].split(',')] if len(sys.argv) > 2 else [0, 3, 7]
+flag_sets = [int(x) for x in sys.argv[2].split(',')] if len(sys.argv) > 2 else [0, 3, 7, 15]
 S = 192
 dev = torch.device('cuda', 0)
 net = dfn.FaceNeRF(D=8, W=256, input_ch=63, input_ch_views=27, dim_aud=64, output_ch=4, skips=[4], use_viewdirs=True)
@@ -91,4 +91,4 @@ try:
                 (outs[f][1] - outs[flag_sets[0]][1]).abs().max().item())
         print('Decoder head+torso bf16x3 (%d rays x 64) flags=%d: %.3f ms%s' % (min(R * 3, 450 * 450), f, ms, msg), flush=True)
 finally:
-    dfn.lib.dfn_debug_set_pp_flags(7)
+    dfn.lib.dfn_debug_set_pp_flags(15)

@@ -331,7 +331,7 @@ def test_split_schedule_switches(dfn):
     """dfn_debug_set_pp_flags: early staging of the skip layer's input and the weight-barrier order (bits 0, 1) change WHEN things
     happen, never what is computed -- bit-identical to the round-1 schedule (flags 0) in both parity modes, ragged and multi-tile sizes;
     bit 2 (fp16x3m: alpha_linear in fp32 inside the last trunk layer's epilogue, views_linears.0 single-pass) changes the arithmetic and is
-    gated against the fp32 oracle like the mode itself."""
+    gated against the fp32 oracle like the mode itself; bit 3 (the view layer's per-ray bias rows staged in shared memory) does not."""
     net = face(dfn, 1)
     sd = synth.facenerf_state_dict(1)
     try:
@@ -341,11 +341,12 @@ def test_split_schedule_switches(dfn):
             for prec in (dfn.PREC_BF16X3, dfn.PREC_FP16X3M):
                 eng = dfn.RenderEngine(net, None, S, 0, precision=prec)
                 outs = {}
-                for f in (0, 1, 2, 3, 7):
+                for f in (0, 1, 2, 3, 7, 8, 15):
                     dfn.lib.dfn_debug_set_pp_flags(f)
                     outs[f] = eng.query_points(net, *args).clone()
-                for f in (1, 2, 3):
+                for f in (1, 2, 3, 8):                            # bit 3: the view layer's bias rows from shared memory, same arithmetic
                     assert torch.equal(outs[f], outs[0]), (R, S, prec, f)
+                assert torch.equal(outs[15], outs[7]), (R, S, prec)
                 if prec == dfn.PREC_BF16X3:
                     assert torch.equal(outs[7], outs[0])          # bit 2 is an fp16x3m switch
                 elif R <= 700:
@@ -356,4 +357,4 @@ def test_split_schedule_switches(dfn):
                         print('fp16x3m flags %d R=%d: weights %.2e colours %.2e sigma %.2e' % (f, R, ew, ec, maxerr(outs[f][..., 3], ref[..., 3])))
                         assert ew < 1e-4 and ec < 1e-4, (f, ew, ec)
     finally:
-        dfn.lib.dfn_debug_set_pp_flags(7)
+        dfn.lib.dfn_debug_set_pp_flags(15)
