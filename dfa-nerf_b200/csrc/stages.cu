@@ -757,18 +757,25 @@ __global__ void __launch_bounds__(256, 4) coarse_to_fine_kernel(int R, int Nc, i
       for (int i = lane; i < n; i += 32)
         if (i != 0 && i != Nc) sorted = sorted && (v[i - 1] <= v[i]);
       if (__all_sync(0xFFFFFFFFu, sorted)) {
-        for (int i = lane; i < n; i += 32) {
-          const float x = v[i];
-          const bool from_a = i < Nc;
-          const float* other = from_a ? v + Nc : v;
-          int lo = 0, hi = from_a ? Nf : Nc;
-          while (lo < hi) {
-            const int mid = (lo + hi) >> 1;
-            const float y = other[mid];
-            if (from_a ? (y < x) : (y <= x)) lo = mid + 1;
-            else hi = mid;
-          }
-          mrg[(from_a ? i : i - Nc) + lo] = x;
+        // merge path: lane l produces the outputs [l*per, (l+1)*per) -- ONE binary search along its diagonal for the split between the
+        // two runs (ties take the coarse depth first, as the by-rank merge of sort_merge_kernel does), then `per` sequential steps;
+        // the by-rank form cost a binary search per element (a sixth of this kernel's instructions).  Values only: the same output.
+        const float* a = v;
+        const float* b = v + Nc;
+        const int per = (n + 31) >> 5;
+        const int d = min(lane * per, n);
+        int lo = max(0, d - Nf), hi = min(d, Nc);
+        while (lo < hi) {
+          const int mid = (lo + hi) >> 1;
+          if (a[mid] <= b[d - mid - 1]) lo = mid + 1;
+          else hi = mid;
+        }
+        int ia = lo, ib = d - lo;
+        for (int t = 0; t < per && d + t < n; ++t) {
+          const bool take_a = ia < Nc && (ib >= Nf || a[ia] <= b[ib]);
+          mrg[d + t] = take_a ? a[ia] : b[ib];
+          ia += take_a ? 1 : 0;
+          ib += take_a ? 0 : 1;
         }
         __syncwarp();
         for (int i = lane; i < n; i += 32) zall[(int64_t)ray * n + i] = mrg[i];
